@@ -1,0 +1,203 @@
+/*
+ * sps_b200 -- C ABI of the B200-native SPS inference hot path.
+ *
+ * The reference (ibrahimhroob/SPS) is pure Python; the arithmetic of its hot path lives behind
+ * the MinkowskiEngine (ME) Python API (a pybind11 module -- there is no C ABI upstream).  This
+ * header is the boundary a maintainer binds instead (ctypes).  Each entry
+ * point names the reference call site(s) it replaces (paths under the reference repo root).
+ *
+ * Conventions
+ *   - every function returns an int status (SPS_OK == 0); nothing throws across the boundary;
+ *   - the CALLER owns all memory: device buffers are raw pointers with element counts, the
+ *     library allocates nothing on the device (the workspace arena is handed in);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no host
+ *     synchronisation happens unless stated (the *_host and *_status calls);
+ *   - sizes that are only known on the device (voxel counts) stay on the device; the
+ *     `sps_level_view` exposes their addresses;
+ *   - one sps_ctx per stream (re-entrant across distinct contexts, no global state).
+ */
+#ifndef SPS_B200_H
+#define SPS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPS_OK 0
+#define SPS_ERR_BAD_ARG 1      /* null pointer, negative count, unsupported channel width ... */
+#define SPS_ERR_CAPACITY 2     /* n exceeds what the context / buffers were sized for       */
+#define SPS_ERR_COORD_RANGE 3  /* a quantised coordinate does not fit the 64-bit voxel key  */
+#define SPS_ERR_CUDA 4         /* a CUDA runtime call failed (see sps_last_error)           */
+#define SPS_ERR_UNSUPPORTED 5
+#define SPS_ERR_STATE 6        /* call order violated (e.g. forward before voxelize)        */
+
+#define SPS_NUM_LEVELS 5       /* tensor strides 1,2,4,8,16 (minkunet.py:64-104)            */
+
+/* Voxel key packing (device side): b:8 | x:18 | y:18 | z:16 | t:4, biased so that floor-to-
+ * stride is a mask.  Valid ranges: b in [0,254], x,y in [-131072,131071], z in [-32768,32767],
+ * t in [0,15].  Anything outside raises SPS_ERR_COORD_RANGE at the next status check. */
+#define SPS_X_BIAS 131072
+#define SPS_Z_BIAS 32768
+
+typedef struct sps_ctx sps_ctx;   /* coordinate manager + scratch for one stream  */
+typedef struct sps_net sps_net;   /* BN-folded, packed CustomMinkUNet weights      */
+
+const char* sps_version(void);
+const char* sps_last_error(void);           /* text of the last SPS_ERR_CUDA on this thread */
+
+/* ---------------------------------------------------------------- context / workspace ---- */
+/* Bytes of device workspace needed for inputs of at most `max_points` rows. */
+size_t sps_workspace_bytes(int64_t max_points);
+/* Replaces the per-forward ME CoordinateManager (src/sps/models/models.py:24). */
+int sps_ctx_create(sps_ctx** ctx, void* d_workspace, size_t workspace_bytes, int64_t max_points);
+int sps_ctx_destroy(sps_ctx* ctx);
+/* Host-synchronising: waits for `stream`, returns the sticky device status word
+ * (SPS_OK / SPS_ERR_COORD_RANGE / SPS_ERR_CAPACITY) and clears it. */
+int sps_ctx_status(sps_ctx* ctx, void* stream);
+
+typedef struct sps_level_view {
+  const uint64_t* keys;     /* [count] packed voxel keys, first-occurrence order            */
+  const int32_t* count;     /* device scalar: number of voxels at this level                */
+  const int32_t* nbr3;      /* [81][ld] 3x3x3x3 kernel map at this level's tensor stride    */
+  const int32_t* nbr5;      /* [125][ld] 5x5x5x1 kernel map (level 0 only, else NULL)       */
+  const int32_t* parent;    /* [count] parent*8 + child-offset index into level+1 (NULL at 4)*/
+  const int32_t* child;     /* [8][ld] child table of the level BELOW (NULL at level 0)     */
+  int64_t ld;               /* leading dimension (in voxels) of nbr3/nbr5/child             */
+} sps_level_view;
+int sps_ctx_level(sps_ctx* ctx, int level, sps_level_view* out);
+const int32_t* sps_ctx_inverse_map(sps_ctx* ctx);   /* [n] point -> level-0 voxel row        */
+
+/* ---------------------------------------------------------------- a1/a2 voxelisation ---- */
+/* `torch.div(coords, [1,vs,vs,vs,1])` + ME.TensorField(...).sparse()
+ * (src/sps/models/models.py:21-25): IEEE fp32 division, floor to int32, unique voxels in
+ * first-occurrence order, inverse mapping.  d_points: fp32 [n,ld_points] rows (b,x,y,z,t,...). */
+int sps_voxelize(sps_ctx* ctx, const float* d_points, int64_t n, int64_t ld_points,
+                 float voxel_size, void* stream);
+/* Strided coordinate maps (MinkowskiConvolution stride=[2,2,2,1], minkunet.py:64-104) for
+ * levels 1..4 plus every kernel map the network needs: 5x5x5x1 at level 0 (minkunet.py:55-60),
+ * 3x3x3x3 at levels 0..4 (BasicBlock convs), 2x2x2x1 parent/child tables. */
+int sps_build_maps(sps_ctx* ctx, void* stream);
+/* Unpack a level's keys into int32 [count,5] rows (b,x,y,z,t) == ME `SparseTensor.C`. */
+int sps_unpack_coords(sps_ctx* ctx, int level, int32_t* d_out, void* stream);
+
+/* ---------------------------------------------------------------- convolution ------------ */
+#define SPS_CONV_NBR 0    /* stride-1 (or child-table stride-2) conv through a [K][ld] map   */
+#define SPS_CONV_UP 1     /* transposed 2x2x2x1: out[f] = in[parent(f)] @ W[k(f)]           */
+
+typedef struct sps_conv_args {
+  int mode;                 /* SPS_CONV_NBR | SPS_CONV_UP                                    */
+  int K;                    /* kernel volume (125, 81, 8, 1)                                 */
+  int cin, cout;
+  const int32_t* map;       /* NBR: [K][map_ld] input rows (-1 = absent); K==1 && map==NULL
+                               means identity (1x1 conv).  UP: parent*8+k per output row     */
+  int64_t map_ld;
+  const int32_t* n_out;     /* device scalar: number of output rows                          */
+  int64_t n_out_max;        /* host upper bound used to size the launch                      */
+  const float* in;  int64_t in_ld;    /* fp32 rows; `in` already points at the channel slice */
+  const float* weight;      /* [K][cin][cout] fp32 (ME `.kernel` layout), BN scale folded by
+                               the caller if wanted                                          */
+  const float* shift;       /* [cout] added after the contraction (folded BN shift/bias), or NULL */
+  /* optional fused 1x1 term: + in2[row] @ weight2  (BasicBlock downsample, resnet.py:97-108) */
+  const float* in2; int64_t in2_ld; int cin2; const float* weight2;
+  /* optional identity residual: + res[row]  (BasicBlock without downsample)                */
+  const float* res; int64_t res_ld;
+  int relu;
+  float* out; int64_t out_ld;         /* may be a channel slice of a concat buffer (ME.cat)  */
+  /* optional fused head: logit[row] = dot(relu_out[row], head_w) + head_b  (final 1x1 conv,
+   * minkunet.py:152-158,219); requires cout == 8; `out` may then be NULL                   */
+  const float* head_w; float head_b; float* head_out;
+} sps_conv_args;
+/* MinkowskiConvolution / MinkowskiConvolutionTranspose (+ folded MinkowskiBatchNorm, ReLU,
+ * residual) forward: minkunet.py:55-158, resnet.py:97-108, ME BasicBlock. fp32 CUDA-core path. */
+int sps_conv_fwd(const sps_conv_args* args, void* stream);
+
+/* ---------------------------------------------------------------- network ---------------- */
+int sps_net_create(sps_net** net);
+int sps_net_destroy(sps_net* net);
+/* Hand over one state_dict tensor (host fp32, ME layout; names without the Lightning prefix
+ * `model.MinkUNet.`, cf. src/sps/datasets/util.py:33-39).  1x1 kernels may be [Cin,Cout] or
+ * [1,Cin,Cout].  `*.num_batches_tracked` entries are ignored by the caller. */
+int sps_net_set_tensor(sps_net* net, const char* name, const float* h_data, int64_t numel);
+size_t sps_net_device_bytes(void);
+/* Folds every BatchNorm (eval) into the preceding kernel + a shift, packs, uploads into the
+ * caller's device buffer.  Fails with SPS_ERR_BAD_ARG if a tensor of CustomMinkUNet(1,1,D=4)
+ * is missing or mis-sized. */
+int sps_net_finalize(sps_net* net, void* d_weights, size_t bytes, void* stream);
+
+/* SPSModel.forward (src/sps/models/models.py:20-30) end to end on device buffers:
+ * voxelize -> maps -> CustomMinkUNet (minkunet.py:161-219) -> slice + sigmoid.
+ * d_scores: fp32 [n].  No host synchronisation. */
+int sps_forward(sps_ctx* ctx, const sps_net* net, const float* d_points, int64_t n,
+                int64_t ld_points, float voxel_size, float* d_scores, void* stream);
+/* Same through HOST buffers (pinned or pageable): H2D of the points into the context's staging
+ * area, forward, D2H of the scores, stream synchronise, status check. This is the call
+ * `util.infer` (src/sps/datasets/util.py:163-184) maps onto. */
+int sps_forward_host(sps_ctx* ctx, const sps_net* net, const float* h_points, int64_t n,
+                     int64_t ld_points, float voxel_size, float* h_scores, void* stream);
+/* U-Net only, on the maps already built in `ctx` (for layer-wise parity tests):
+ * d_feat0 fp32 [V0] input feature, d_logits fp32 [V0] output of `final`. */
+int sps_unet_forward(sps_ctx* ctx, const sps_net* net, const float* d_feat0, float* d_logits,
+                     void* stream);
+/* SparseTensor.slice + sigmoid (models.py:28-29): scores[p] = sigmoid(logits[inv[p]]). */
+int sps_devox_sigmoid(const float* d_logits, const int32_t* d_inv, int64_t n, float* d_scores,
+                      void* stream);
+/* Number of kernels one sps_forward enqueues (for bench.py's gpu_launches claim). */
+int sps_forward_launch_count(void);
+
+/* ---------------------------------------------------------------- submap selection ------- */
+typedef struct sps_map sps_map;  /* replicated base-map voxel hash, built once per process  */
+size_t sps_map_bytes(int64_t max_map_points);
+/* util.to_coords_features(map,'map',ds) + the map half of util.prune
+ * (src/sps/datasets/util.py:67-82,86-89): trunc(xyz/ds) int32, de-duplicated, hashed ONCE
+ * instead of per scan.  d_map_xyz: fp32 [n,3]. */
+int sps_map_build(sps_map** map, void* d_storage, size_t bytes, const float* d_map_xyz,
+                  int64_t n, float ds, void* stream);
+int sps_map_destroy(sps_map* map);
+/* util.prune (src/sps/datasets/util.py:85-114): voxels present in both the map and the scan,
+ * returned as fp32 corners `coords*ds` [m,3]; d_counts[0] = m, d_counts[1] = number of unique
+ * scan voxels (the function's second return value).  d_scratch: sps_map_bytes(n_scan) bytes. */
+int sps_submap_crop_voxel(const sps_map* map, const float* d_scan_xyz, int64_t n_scan,
+                          void* d_scratch, size_t scratch_bytes, float* d_out_xyz,
+                          int32_t* d_counts, void* stream);
+/* Radius crop of the raw map (c_ws/src/mapmos/scripts/mapmos_node.py:63-68): indices of map
+ * points with ||p - center|| <= radius (float64, as numpy promotes) in map order; d_count[0] = how many. */
+int sps_submap_crop_radius(const float* d_map_xyz, int64_t n, const double center[3], double radius,
+                           int32_t* d_out_idx, int32_t* d_count, void* d_scratch,
+                           size_t scratch_bytes, void* stream);
+/* Assembly of the network input (util.add_timestamp + vstack/hstack, util.py:156-174):
+ * rows [b, x,y,z, t] with the scan rows (t=1) first and the submap rows (t=0) after. */
+int sps_assemble(const float* d_scan_xyz, int64_t n_scan, const float* d_sub_xyz,
+                 const int32_t* d_n_sub, int64_t n_sub_max, float batch_index, float* d_out,
+                 void* stream);
+
+/* One scan of the ROS deployment path (c_ws/src/sps_filter/scripts/sps_node.py:111-120):
+ * util.prune against the replicated map hash -> util.infer assembly -> SPSModel.forward ->
+ * scores of the scan rows only (util.py:180).  No host synchronisation: the submap size stays
+ * on the device.  ctx must be sized for 2*n_scan rows; d_counts as in sps_submap_crop_voxel. */
+size_t sps_infer_scan_scratch_bytes(int64_t n_scan);
+int sps_infer_scan(sps_ctx* ctx, const sps_net* net, const sps_map* map, const float* d_scan_xyz,
+                   int64_t n_scan, float voxel_size, float* d_scores, void* d_scratch,
+                   size_t scratch_bytes, int32_t* d_counts, void* stream);
+
+/* ---------------------------------------------------------------- tensor-core path ------- */
+/* Which kernel serves sps_conv_fwd / the fused forward: 0 = auto (tcgen05 implicit GEMM where
+ * the layer shape allows, fp32 CUDA-core otherwise), 1 = fp32 CUDA-core only, 2 = tcgen05 only
+ * (SPS_ERR_UNSUPPORTED for shapes it does not take). */
+int sps_set_conv_backend(int backend);
+/* Known-answer hook for the tcgen05 tile pipeline: D[M,N] (fp32) = A[M,K] @ B[N,K]^T with bf16
+ * operands staged exactly as the convolution stages them (K-major, 128-byte swizzle).
+ * M % 128 == 0, N in {16,32,64}, K % 64 == 0. */
+int sps_umma_selftest(const void* d_a_bf16, const void* d_b_bf16, float* d_out, int M, int N, int K,
+                      void* stream);
+
+/* Small helpers so that host code needs no second CUDA binding. */
+int sps_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream);
+int sps_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPS_B200_H */

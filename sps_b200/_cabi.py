@@ -1,0 +1,112 @@
+"""ctypes binding of ``include/sps_b200.h`` -- the only way host code reaches the kernels.
+
+There is deliberately no fallback: if ``libsps_b200.so`` cannot be loaded the import of the
+product path raises (the CUDA extension IS the product)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsps_b200.so")
+
+SPS_OK, SPS_ERR_BAD_ARG, SPS_ERR_CAPACITY, SPS_ERR_COORD_RANGE, SPS_ERR_CUDA, SPS_ERR_UNSUPPORTED, SPS_ERR_STATE = range(7)
+SPS_NUM_LEVELS = 5
+SPS_CONV_NBR, SPS_CONV_UP = 0, 1
+_ERR_NAMES = {1: "SPS_ERR_BAD_ARG", 2: "SPS_ERR_CAPACITY", 3: "SPS_ERR_COORD_RANGE", 4: "SPS_ERR_CUDA",
+              5: "SPS_ERR_UNSUPPORTED", 6: "SPS_ERR_STATE"}
+
+# every symbol include/sps_b200.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "sps_version", "sps_last_error", "sps_workspace_bytes", "sps_ctx_create", "sps_ctx_destroy", "sps_ctx_status",
+    "sps_ctx_level", "sps_ctx_inverse_map", "sps_voxelize", "sps_build_maps", "sps_unpack_coords", "sps_conv_fwd",
+    "sps_net_create", "sps_net_destroy", "sps_net_set_tensor", "sps_net_device_bytes", "sps_net_finalize",
+    "sps_forward", "sps_forward_host", "sps_unet_forward", "sps_devox_sigmoid", "sps_forward_launch_count",
+    "sps_map_bytes", "sps_map_build", "sps_map_destroy", "sps_submap_crop_voxel", "sps_submap_crop_radius",
+    "sps_assemble", "sps_memcpy_d2h", "sps_memcpy_h2d", "sps_infer_scan", "sps_infer_scan_scratch_bytes", "sps_umma_selftest",
+    "sps_set_conv_backend",
+]
+
+
+class LevelView(C.Structure):
+    _fields_ = [("keys", C.c_void_p), ("count", C.c_void_p), ("nbr3", C.c_void_p), ("nbr5", C.c_void_p),
+                ("parent", C.c_void_p), ("child", C.c_void_p), ("ld", C.c_int64)]
+
+
+class ConvArgs(C.Structure):
+    _fields_ = [("mode", C.c_int), ("K", C.c_int), ("cin", C.c_int), ("cout", C.c_int),
+                ("map", C.c_void_p), ("map_ld", C.c_int64), ("n_out", C.c_void_p), ("n_out_max", C.c_int64),
+                ("in_", C.c_void_p), ("in_ld", C.c_int64), ("weight", C.c_void_p), ("shift", C.c_void_p),
+                ("in2", C.c_void_p), ("in2_ld", C.c_int64), ("cin2", C.c_int), ("weight2", C.c_void_p),
+                ("res", C.c_void_p), ("res_ld", C.c_int64), ("relu", C.c_int),
+                ("out", C.c_void_p), ("out_ld", C.c_int64),
+                ("head_w", C.c_void_p), ("head_b", C.c_float), ("head_out", C.c_void_p)]
+
+
+class SpsError(RuntimeError):
+    def __init__(self, code, where, detail=""):
+        self.code = code
+        super().__init__(f"{where} failed: {_ERR_NAMES.get(code, code)}{(' -- ' + detail) if detail else ''}")
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the in-tree shared library; build it first when it is missing and nvcc exists."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build  # raises if nvcc is absent: no silent fallback
+        _build.build()
+    lib = C.CDLL(LIB_PATH)
+    vp, i64, i32, f32, sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t
+    sig = {
+        "sps_version": (C.c_char_p, []),
+        "sps_last_error": (C.c_char_p, []),
+        "sps_workspace_bytes": (sz, [i64]),
+        "sps_ctx_create": (i32, [C.POINTER(vp), vp, sz, i64]),
+        "sps_ctx_destroy": (i32, [vp]),
+        "sps_ctx_status": (i32, [vp, vp]),
+        "sps_ctx_level": (i32, [vp, i32, C.POINTER(LevelView)]),
+        "sps_ctx_inverse_map": (vp, [vp]),
+        "sps_voxelize": (i32, [vp, vp, i64, i64, f32, vp]),
+        "sps_build_maps": (i32, [vp, vp]),
+        "sps_unpack_coords": (i32, [vp, i32, vp, vp]),
+        "sps_conv_fwd": (i32, [C.POINTER(ConvArgs), vp]),
+        "sps_net_create": (i32, [C.POINTER(vp)]),
+        "sps_net_destroy": (i32, [vp]),
+        "sps_net_set_tensor": (i32, [vp, C.c_char_p, vp, i64]),
+        "sps_net_device_bytes": (sz, []),
+        "sps_net_finalize": (i32, [vp, vp, sz, vp]),
+        "sps_forward": (i32, [vp, vp, vp, i64, i64, f32, vp, vp]),
+        "sps_forward_host": (i32, [vp, vp, vp, i64, i64, f32, vp, vp]),
+        "sps_unet_forward": (i32, [vp, vp, vp, vp, vp]),
+        "sps_devox_sigmoid": (i32, [vp, vp, i64, vp, vp]),
+        "sps_forward_launch_count": (i32, []),
+        "sps_map_bytes": (sz, [i64]),
+        "sps_map_build": (i32, [C.POINTER(vp), vp, sz, vp, i64, f32, vp]),
+        "sps_map_destroy": (i32, [vp]),
+        "sps_submap_crop_voxel": (i32, [vp, vp, i64, vp, sz, vp, vp, vp]),
+        "sps_submap_crop_radius": (i32, [vp, i64, C.POINTER(C.c_double), C.c_double, vp, vp, vp, sz, vp]),
+        "sps_assemble": (i32, [vp, i64, vp, vp, i64, f32, vp, vp]),
+        "sps_memcpy_d2h": (i32, [vp, vp, sz, vp]),
+        "sps_memcpy_h2d": (i32, [vp, vp, sz, vp]),
+        "sps_infer_scan": (i32, [vp, vp, vp, vp, i64, f32, vp, vp, sz, vp, vp]),
+        "sps_infer_scan_scratch_bytes": (sz, [i64]),
+        "sps_umma_selftest": (i32, [vp, vp, vp, i32, i32, i32, vp]),
+        "sps_set_conv_backend": (i32, [i32]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code: int, where: str):
+    if code != SPS_OK:
+        detail = load().sps_last_error().decode() if code == SPS_ERR_CUDA else ""
+        raise SpsError(code, where, detail)

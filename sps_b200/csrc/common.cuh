@@ -1,0 +1,99 @@
+// Shared device helpers: voxel key packing, open-addressing hash slots, status flags.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/sps_b200.h"
+
+namespace sps {
+
+// ---- 64-bit voxel key: b:8 | x:18 | y:18 | z:16 | t:4 (biased; see include/sps_b200.h) ----
+constexpr int kTBits = 4, kZBits = 16, kYBits = 18, kXBits = 18, kBBits = 8;
+constexpr int kZShift = kTBits, kYShift = kZShift + kZBits, kXShift = kYShift + kYBits,
+              kBShift = kXShift + kXBits;
+constexpr unsigned long long kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+constexpr int kXBias = SPS_X_BIAS, kZBias = SPS_Z_BIAS;
+
+__host__ __device__ inline bool coord_in_range(int b, int x, int y, int z, int t) {
+  return (unsigned)b < 255u && (unsigned)(x + kXBias) < (1u << kXBits) &&
+         (unsigned)(y + kXBias) < (1u << kYBits) && (unsigned)(z + kZBias) < (1u << kZBits) &&
+         (unsigned)t < (1u << kTBits);
+}
+__host__ __device__ inline unsigned long long pack_key(int b, int x, int y, int z, int t) {
+  return ((unsigned long long)(unsigned)b << kBShift) |
+         ((unsigned long long)(unsigned)(x + kXBias) << kXShift) |
+         ((unsigned long long)(unsigned)(y + kXBias) << kYShift) |
+         ((unsigned long long)(unsigned)(z + kZBias) << kZShift) | (unsigned long long)(unsigned)t;
+}
+__host__ __device__ inline void unpack_key(unsigned long long k, int& b, int& x, int& y, int& z, int& t) {
+  b = (int)(k >> kBShift);
+  x = (int)((k >> kXShift) & ((1u << kXBits) - 1)) - kXBias;
+  y = (int)((k >> kYShift) & ((1u << kYBits) - 1)) - kXBias;
+  z = (int)((k >> kZShift) & ((1u << kZBits) - 1)) - kZBias;
+  t = (int)(k & ((1u << kTBits) - 1));
+}
+// floor(x / m) * m on every spatial field for m = 2^log2m (biases are multiples of 16).
+__host__ __device__ inline unsigned long long coarsen_key(unsigned long long k, int log2m) {
+  unsigned long long low = (1ull << log2m) - 1;
+  unsigned long long mask = ~((low << kXShift) | (low << kYShift) | (low << kZShift));
+  return k & mask;
+}
+// index of a fine voxel inside its 2x2x2 parent: ox + 2*oy + 4*oz (ME offset order, x fastest)
+__host__ __device__ inline int child_index(unsigned long long k, int log2s) {
+  int ox = (int)(k >> (kXShift + log2s)) & 1, oy = (int)(k >> (kYShift + log2s)) & 1,
+      oz = (int)(k >> (kZShift + log2s)) & 1;
+  return ox + 2 * oy + 4 * oz;
+}
+
+// ---- hash table ----
+struct __align__(16) Slot {
+  unsigned long long key;
+  int val;    // voxel row (assigned after the scan)
+  int first;  // smallest input index that mapped here (first-occurrence order)
+};
+
+__host__ __device__ inline uint32_t hash_key(unsigned long long k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+  return (uint32_t)k;
+}
+// table capacity for n keys: power of two >= 2n, at least 1024
+__host__ __device__ inline uint32_t table_capacity(int64_t n) {
+  uint32_t c = 1024;
+  while ((int64_t)c < 2 * n) c <<= 1;
+  return c;
+}
+
+__device__ inline int table_find(const Slot* __restrict__ tab, uint32_t mask, unsigned long long key) {
+  uint32_t s = hash_key(key) & mask;
+  while (true) {
+    // one 16-byte load per probe: key + val in the same sector
+    const int4 raw = __ldg(reinterpret_cast<const int4*>(tab + s));
+    unsigned long long k = ((unsigned long long)(unsigned)raw.y << 32) | (unsigned)raw.x;
+    if (k == key) return raw.z;
+    if (k == kEmptyKey) return -1;
+    s = (s + 1) & mask;
+  }
+}
+
+// returns the slot index of `key` (inserting it if absent)
+__device__ inline uint32_t table_insert(Slot* tab, uint32_t mask, unsigned long long key) {
+  uint32_t s = hash_key(key) & mask;
+  while (true) {
+    unsigned long long prev = atomicCAS(&tab[s].key, kEmptyKey, key);
+    if (prev == kEmptyKey || prev == key) return s;
+    s = (s + 1) & mask;
+  }
+}
+
+// sticky status word bits (device)
+constexpr int kStatusRange = 1, kStatusCapacity = 2;
+
+#define SPS_CUDA_CHECK(expr)                                   \
+  do {                                                         \
+    cudaError_t _e = (expr);                                   \
+    if (_e != cudaSuccess) return sps::set_cuda_error(_e, #expr); \
+  } while (0)
+int set_cuda_error(cudaError_t e, const char* what);
+
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace sps

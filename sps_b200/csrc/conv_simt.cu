@@ -1,0 +1,195 @@
+// fp32 CUDA-core sparse convolution (output-stationary gather, no atomics, deterministic).
+//
+// out[o] = act( sum_k in[map[k][o]] @ W[k] + shift (+ in2[o] @ W2) (+ res[o]) )
+// One thread owns 8 output channels of one output voxel; the threads of a warp share the
+// kernel offset and the channel group, so weight reads from shared memory are broadcasts and
+// the map reads are coalesced.  This is the parity/reference GPU path (exact fp32 FMA chain)
+// and the fallback for layers the tensor-core kernel does not take.
+#include "common.cuh"
+
+namespace sps {
+
+constexpr int kSimtThreads = 256;
+constexpr int kSimtSmemBytes = 96 * 1024;
+
+template <int COUT>
+__global__ void __launch_bounds__(kSimtThreads)
+k_conv_simt(const sps_conv_args a, const int kc) {
+  constexpr int TPV = COUT / 8;               // threads per voxel
+  constexpr int VB = kSimtThreads / TPV;      // voxels per block tile
+  extern __shared__ __align__(16) float w_s[];  // [kc][cin][COUT] (later reused for W2)
+  const int tid = threadIdx.x;
+  const int cg = tid / VB, vl = tid % VB;
+  const int n_out = *a.n_out;
+  const int cin = a.cin, K = a.K;
+  const int slab = cin * COUT;
+  const int ntiles = (n_out + VB - 1) / VB;
+  const bool resident = (kc >= K) && a.in2 == nullptr;
+  bool loaded = false;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int v = tile * VB + vl;
+    const bool active = v < n_out;
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+
+    for (int kbase = 0; kbase < K; kbase += kc) {
+      const int kn = min(kc, K - kbase);
+      if (!(resident && loaded)) {
+        __syncthreads();
+        const float4* src = reinterpret_cast<const float4*>(a.weight + (int64_t)kbase * slab);
+        float4* dst = reinterpret_cast<float4*>(w_s);
+        for (int i = tid; i < kn * slab / 4; i += kSimtThreads) dst[i] = __ldg(src + i);
+        __syncthreads();
+        loaded = true;
+      }
+      if (!active) continue;
+      for (int kk = 0; kk < kn; ++kk) {
+        const int k = kbase + kk;
+        int idx;
+        if (a.mode == SPS_CONV_UP) {
+          const int pk = __ldg(a.map + v);
+          idx = ((pk & 7) == k) ? (pk >> 3) : -1;
+        } else {
+          idx = a.map ? __ldg(a.map + (int64_t)k * a.map_ld + v) : v;
+        }
+        if (idx < 0) continue;
+        const float* row = a.in + (int64_t)idx * a.in_ld;
+        const float* wk = w_s + kk * slab + cg * 8;
+        if (cin == 1) {
+          const float x = __ldg(row);
+          const float4 w0 = *reinterpret_cast<const float4*>(wk);
+          const float4 w1 = *reinterpret_cast<const float4*>(wk + 4);
+          acc[0] = fmaf(x, w0.x, acc[0]); acc[1] = fmaf(x, w0.y, acc[1]);
+          acc[2] = fmaf(x, w0.z, acc[2]); acc[3] = fmaf(x, w0.w, acc[3]);
+          acc[4] = fmaf(x, w1.x, acc[4]); acc[5] = fmaf(x, w1.y, acc[5]);
+          acc[6] = fmaf(x, w1.z, acc[6]); acc[7] = fmaf(x, w1.w, acc[7]);
+        } else {
+          for (int ci = 0; ci < cin; ci += 4) {
+            const float4 x4 = __ldg(reinterpret_cast<const float4*>(row + ci));
+            const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 w0 = *reinterpret_cast<const float4*>(wk + (ci + j) * COUT);
+              const float4 w1 = *reinterpret_cast<const float4*>(wk + (ci + j) * COUT + 4);
+              acc[0] = fmaf(xs[j], w0.x, acc[0]); acc[1] = fmaf(xs[j], w0.y, acc[1]);
+              acc[2] = fmaf(xs[j], w0.z, acc[2]); acc[3] = fmaf(xs[j], w0.w, acc[3]);
+              acc[4] = fmaf(xs[j], w1.x, acc[4]); acc[5] = fmaf(xs[j], w1.y, acc[5]);
+              acc[6] = fmaf(xs[j], w1.z, acc[6]); acc[7] = fmaf(xs[j], w1.w, acc[7]);
+            }
+          }
+        }
+      }
+    }
+
+    // fused 1x1 term (BasicBlock downsample): + in2[v] @ W2
+    if (a.in2) {
+      __syncthreads();
+      const int n4 = a.cin2 * COUT / 4;
+      for (int i = tid; i < n4; i += kSimtThreads)
+        reinterpret_cast<float4*>(w_s)[i] = __ldg(reinterpret_cast<const float4*>(a.weight2) + i);
+      __syncthreads();
+      loaded = false;
+      if (active) {
+        const float* row = a.in2 + (int64_t)v * a.in2_ld;
+        const float* wk = w_s + cg * 8;
+        for (int ci = 0; ci < a.cin2; ci += 4) {
+          const float4 x4 = __ldg(reinterpret_cast<const float4*>(row + ci));
+          const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 w0 = *reinterpret_cast<const float4*>(wk + (ci + j) * COUT);
+            const float4 w1 = *reinterpret_cast<const float4*>(wk + (ci + j) * COUT + 4);
+            acc[0] = fmaf(xs[j], w0.x, acc[0]); acc[1] = fmaf(xs[j], w0.y, acc[1]);
+            acc[2] = fmaf(xs[j], w0.z, acc[2]); acc[3] = fmaf(xs[j], w0.w, acc[3]);
+            acc[4] = fmaf(xs[j], w1.x, acc[4]); acc[5] = fmaf(xs[j], w1.y, acc[5]);
+            acc[6] = fmaf(xs[j], w1.z, acc[6]); acc[7] = fmaf(xs[j], w1.w, acc[7]);
+          }
+        }
+      }
+    }
+    if (!active) continue;
+
+    if (a.shift) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] += __ldg(a.shift + cg * 8 + c);
+    }
+    if (a.res) {
+      const float* r = a.res + (int64_t)v * a.res_ld + cg * 8;
+      const float4 r0 = __ldg(reinterpret_cast<const float4*>(r));
+      const float4 r1 = __ldg(reinterpret_cast<const float4*>(r + 4));
+      acc[0] += r0.x; acc[1] += r0.y; acc[2] += r0.z; acc[3] += r0.w;
+      acc[4] += r1.x; acc[5] += r1.y; acc[6] += r1.z; acc[7] += r1.w;
+    }
+    if (a.relu) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] = fmaxf(acc[c], 0.f);
+    }
+    if (a.out) {
+      float* o = a.out + (int64_t)v * a.out_ld + cg * 8;
+      *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    if (COUT == 8 && a.head_out) {
+      float s = a.head_b;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) s = fmaf(acc[c], __ldg(a.head_w + c), s);
+      a.head_out[v] = s;
+    }
+  }
+}
+
+template <int COUT>
+static int launch_simt(const sps_conv_args& a, cudaStream_t st) {
+  constexpr int VB = kSimtThreads / (COUT / 8);
+  const int slab = a.cin * COUT * 4;
+  int kc = kSimtSmemBytes / slab;
+  if (kc > a.K) kc = a.K;
+  if (kc < 1) return SPS_ERR_UNSUPPORTED;
+  size_t smem = (size_t)kc * slab;
+  if (a.in2 && (size_t)a.cin2 * COUT * 4 > smem) smem = (size_t)a.cin2 * COUT * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SPS_CUDA_CHECK(cudaFuncSetAttribute(k_conv_simt<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kSimtSmemBytes));
+    attr_set = true;
+  }
+  int64_t tiles = (a.n_out_max + VB - 1) / VB;
+  if (tiles < 1) tiles = 1;
+  const int grid = (int)(tiles < 148 * 8 ? tiles : 148 * 8);
+  k_conv_simt<COUT><<<grid, kSimtThreads, smem, st>>>(a, kc);
+  SPS_CUDA_CHECK(cudaGetLastError());
+  return SPS_OK;
+}
+
+int conv_dispatch(const sps_conv_args& a, cudaStream_t st);
+
+int conv_simt(const sps_conv_args& a, cudaStream_t st) {
+  switch (a.cout) {
+    case 8: return launch_simt<8>(a, st);
+    case 16: return launch_simt<16>(a, st);
+    case 32: return launch_simt<32>(a, st);
+    case 64: return launch_simt<64>(a, st);
+    default: return SPS_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace sps
+
+extern "C" int sps_conv_fwd(const sps_conv_args* a, void* stream) {
+  if (!a || !a->in || !a->weight || !a->n_out || (!a->out && !a->head_out)) return SPS_ERR_BAD_ARG;
+  if (a->mode != SPS_CONV_NBR && a->mode != SPS_CONV_UP) return SPS_ERR_BAD_ARG;
+  if (a->mode == SPS_CONV_UP && (!a->map || a->K != 8)) return SPS_ERR_BAD_ARG;
+  if (a->mode == SPS_CONV_NBR && !a->map && a->K != 1) return SPS_ERR_BAD_ARG;
+  if (a->cin < 1 || (a->cin != 1 && a->cin % 4) || (a->in_ld % 4 && a->cin != 1)) return SPS_ERR_BAD_ARG;
+  if (a->in2 && (!a->weight2 || a->cin2 % 4 || a->in2_ld % 4)) return SPS_ERR_BAD_ARG;
+  if (a->out && a->out_ld % 4) return SPS_ERR_BAD_ARG;
+  if (a->res && a->res_ld % 4) return SPS_ERR_BAD_ARG;
+  if (a->head_out && (a->cout != 8 || !a->head_w)) return SPS_ERR_BAD_ARG;
+  if (a->n_out_max < 0) return SPS_ERR_BAD_ARG;
+  const uintptr_t al = (uintptr_t)a->weight | (uintptr_t)a->out | (uintptr_t)a->in2 | (uintptr_t)a->weight2 |
+                       (uintptr_t)a->res | (a->cin != 1 ? (uintptr_t)a->in : 0);
+  if (al & 15) return SPS_ERR_BAD_ARG;  // float4 access everywhere
+  return sps::conv_dispatch(*a, (cudaStream_t)stream);
+}

@@ -1,0 +1,45 @@
+// Host-side context: carve-up of the caller's workspace arena (no device allocation here).
+#pragma once
+#include "common.cuh"
+
+struct sps_ctx {
+  int64_t max_points = 0;
+  int64_t ld = 0;            // leading dimension of the [K][ld] map tables (multiple of 32)
+  int64_t n = 0;             // rows of the last voxelize call
+  bool have_l0 = false, have_maps = false;
+
+  char* base = nullptr;
+  size_t bytes = 0;
+
+  // scalars (device)
+  int32_t* counts = nullptr;   // [SPS_NUM_LEVELS] voxel counts
+  int32_t* status = nullptr;   // sticky status word
+  uint32_t* ticket = nullptr;  // last-block-done counters, one per unique() call
+  int32_t* n_dev = nullptr;    // device copy of n (so level-0 kernels share the code path)
+
+  float* staging = nullptr;    // [max_points][8] host->device landing zone
+  float* scores = nullptr;     // [max_points]
+  sps::Slot* table = nullptr;  // open-addressing table, capacity table_capacity(max_points)
+  uint32_t table_cap = 0;
+  uint32_t* slot_of = nullptr; // [max_points]
+  int32_t* rank = nullptr;     // [max_points]
+  int32_t* block_sums = nullptr;
+
+  unsigned long long* keys[SPS_NUM_LEVELS] = {};
+  int32_t* inv = nullptr;                      // [max_points] point -> level-0 row
+  int32_t* parent[SPS_NUM_LEVELS] = {};        // [L] fine row -> parent*8 + k   (L = 0..3)
+  int32_t* child[SPS_NUM_LEVELS] = {};         // [L] [8][ld] children of level-L rows (L = 1..4)
+  int32_t* nbr3[SPS_NUM_LEVELS] = {};          // [81][ld]
+  int32_t* nbr5 = nullptr;                     // [125][ld]
+
+  // feature buffers (fp32, row-major, upper bound max_points rows)
+  enum Buf { CAT8, E1, H1, CAT7, E2, H2, CAT6, E3, H3, CAT5, E4, H4, B4, H5, B5, H6, B6, H7, B7, H8,
+             FEAT0, LOGITS, NBUF };
+  float* buf[NBUF] = {};
+};
+
+namespace sps {
+constexpr int kBufWidth[sps_ctx::NBUF] = {16, 8, 8, 24, 8, 16, 48, 16, 32, 96, 32, 64, 64, 64, 64, 32, 32,
+                                          16, 16, 8, 1, 1};
+constexpr int kScanBlock = 1024;
+}

@@ -1,0 +1,585 @@
+// Coordinate hashing: voxelisation (a1/a2), strided coordinate maps (a4) and kernel maps.
+//
+// One primitive does all the set work: unique_by_hash() = open-addressing insert of 64-bit
+// voxel keys + "first occurrence" ranking (atomicMin of the input index per slot, then a
+// block scan with a last-block-done carry) so that the voxel order is deterministic and equal
+// to ME's CPU insert order.  Level 0 hashes the quantised points, level L+1 hashes the
+// level-L keys with the low spatial bits masked off (floor to the tensor stride).
+// All sizes below level 0 live on the device; launches are sized by the host upper bound and
+// surplus blocks exit on the device count, so a whole forward needs no host synchronisation.
+#include <limits.h>
+#include "ctx.h"
+
+namespace sps {
+
+constexpr uint32_t kInvalidSlot = 0xFFFFFFFFu;
+
+__global__ void k_set_i32(int32_t* p, int32_t v) { *p = v; }
+
+__global__ void k_table_clear(Slot* __restrict__ tab, const int32_t* __restrict__ n_ptr) {
+  const uint32_t cap = table_capacity(*n_ptr);
+  const int4 empty = make_int4(-1, -1, -1, INT_MAX);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x)
+    reinterpret_cast<int4*>(tab)[i] = empty;
+}
+
+// a1 + a2: fp32 IEEE division by the voxel size (src/sps/models/models.py:21), floor
+// (ME TensorField.sparse()), key packing, hash insert.
+__global__ void k_insert_points(const float* __restrict__ pts, int64_t ld, const int32_t* __restrict__ n_ptr,
+                                float vs, Slot* tab, uint32_t* __restrict__ slot_of, int32_t* status) {
+  const int n = *n_ptr;
+  const uint32_t mask = table_capacity(n) - 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float* p = pts + (int64_t)i * ld;
+    const float fb = floorf(__fdiv_rn(p[0], 1.0f));
+    const float fx = floorf(__fdiv_rn(p[1], vs));
+    const float fy = floorf(__fdiv_rn(p[2], vs));
+    const float fz = floorf(__fdiv_rn(p[3], vs));
+    const float ft = floorf(__fdiv_rn(p[4], 1.0f));
+    const bool ok = fb >= 0.f && fb < 255.f && fx >= -(float)kXBias && fx < (float)kXBias &&
+                    fy >= -(float)kXBias && fy < (float)kXBias && fz >= -(float)kZBias &&
+                    fz < (float)kZBias && ft >= 0.f && ft < 16.f;
+    if (!ok) {  // also catches NaN
+      atomicOr(status, kStatusRange);
+      slot_of[i] = kInvalidSlot;
+      continue;
+    }
+    const unsigned long long key = pack_key((int)fb, (int)fx, (int)fy, (int)fz, (int)ft);
+    const uint32_t s = table_insert(tab, mask, key);
+    atomicMin(&tab[s].first, i);
+    slot_of[i] = s;
+  }
+}
+
+// a4: ME stride map -- floor the spatial coordinates to the new tensor stride 2^log2m.
+__global__ void k_insert_coarse(const unsigned long long* __restrict__ fine, const int32_t* __restrict__ n_ptr,
+                                int log2m, Slot* tab, uint32_t* __restrict__ slot_of) {
+  const int n = *n_ptr;
+  const uint32_t mask = table_capacity(n) - 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t s = table_insert(tab, mask, coarsen_key(fine[i], log2m));
+    atomicMin(&tab[s].first, i);
+    slot_of[i] = s;
+  }
+}
+
+// Exclusive scan of one 0/1 flag per input over the whole grid: block scan (rank[i] = rank
+// inside the block), per-block sums, and the last block to finish turns the sums into exclusive
+// block offsets and publishes the total.  Global rank of i = rank[i] + block_sums[i / kScanBlock].
+// Must be called by every thread of every block with blockIdx.x < nb.
+__device__ inline void scan_flags(int flag, int i, int n, int nb, int32_t* __restrict__ rank, int32_t* block_sums,
+                                  uint32_t* ticket, int32_t* count_out) {
+  __shared__ int warp_sums[kScanBlock / 32];
+  __shared__ bool is_last;
+  __shared__ int carry;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  int incl = flag;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  if (lane == 31) warp_sums[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int w = warp_sums[lane];
+    int wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= d) wi += v;
+    }
+    warp_sums[lane] = wi - w;  // exclusive
+  }
+  __syncthreads();
+  const int excl = incl - flag + warp_sums[wid];
+  if (i < n) rank[i] = excl;
+  if (tid == kScanBlock - 1) {
+    block_sums[blockIdx.x] = excl + flag;
+    __threadfence();
+    is_last = (atomicAdd(ticket, 1u) == (uint32_t)(nb - 1));
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // serial-over-chunks exclusive scan of block_sums[0..nb) by this block
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += kScanBlock) {
+    const int j = base + tid;
+    const int v = (j < nb) ? ((volatile int32_t*)block_sums)[j] : 0;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int u = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += u;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      int w = warp_sums[lane];
+      int wi = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, wi, d);
+        if (lane >= d) wi += u;
+      }
+      warp_sums[lane] = wi - w;
+    }
+    __syncthreads();
+    const int ex = inc - v + warp_sums[wid] + carry;
+    if (j < nb) block_sums[j] = ex;
+    __syncthreads();
+    if (tid == kScanBlock - 1) carry = ex + v;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    *count_out = carry;
+    *ticket = 0;  // ready for the next scan on this stream
+  }
+}
+
+// flag = "this input is the first occurrence of its voxel" (optionally: "... and the voxel is
+// also present in `filter`", the map/scan intersection of util.prune).
+__global__ void __launch_bounds__(kScanBlock)
+k_first_rank(const Slot* __restrict__ tab, const uint32_t* __restrict__ slot_of, const int32_t* __restrict__ n_ptr,
+             int32_t* __restrict__ rank, int32_t* block_sums, uint32_t* ticket, int32_t* count_out,
+             const Slot* __restrict__ filter, uint32_t filter_mask, int32_t* first_count) {
+  const int n = *n_ptr;
+  const int nb = max(1, (n + kScanBlock - 1) / kScanBlock);
+  if ((int)blockIdx.x >= nb) return;
+  const int i = blockIdx.x * kScanBlock + threadIdx.x;
+  int flag = 0;
+  uint32_t s = kInvalidSlot;
+  if (i < n) {
+    s = slot_of[i];
+    flag = (s != kInvalidSlot) && (tab[s].first == i);
+  }
+  if (filter) {
+    const unsigned ballot = __ballot_sync(0xffffffffu, flag);
+    if (first_count && (threadIdx.x & 31) == 0 && ballot) atomicAdd(first_count, __popc(ballot));
+    if (flag) flag = table_find(filter, filter_mask, tab[s].key) >= 0;
+  }
+  scan_flags(flag, i, n, nb, rank, block_sums, ticket, count_out);
+}
+
+__global__ void k_fill_i32(int32_t* __restrict__ p, int64_t ld, int rows, const int32_t* __restrict__ count_ptr,
+                           int32_t value) {
+  const int n = *count_ptr;
+  const int64_t total = (int64_t)rows * n;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(idx / n), c = (int)(idx - (int64_t)r * n);
+    p[r * ld + c] = value;
+  }
+}
+
+// Level 0: inverse mapping point -> voxel row; the first occurrence publishes the voxel.
+__global__ void k_assign_points(Slot* tab, const uint32_t* __restrict__ slot_of, const int32_t* __restrict__ n_ptr,
+                                const int32_t* __restrict__ rank, const int32_t* __restrict__ block_sums,
+                                unsigned long long* __restrict__ ukeys, int32_t* __restrict__ inv) {
+  const int n = *n_ptr;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t s = slot_of[i];
+    if (s == kInvalidSlot) { inv[i] = -1; continue; }
+    const int f = tab[s].first;
+    const int id = rank[f] + block_sums[f / kScanBlock];
+    inv[i] = id;
+    if (f == i) { tab[s].val = id; ukeys[id] = tab[s].key; }
+  }
+}
+
+// Level L+1: parent row and 2x2x2x1 offset index of every fine voxel (the stride-2 kernel map
+// and, swapped, the transposed-conv map: minkunet.py:64-70,107-113), plus the child table.
+__global__ void k_assign_coarse(Slot* tab, const uint32_t* __restrict__ slot_of, const int32_t* __restrict__ n_ptr,
+                                const int32_t* __restrict__ rank, const int32_t* __restrict__ block_sums,
+                                const unsigned long long* __restrict__ fine, int log2s,
+                                unsigned long long* __restrict__ ukeys, int32_t* __restrict__ parent,
+                                int32_t* __restrict__ child, int64_t ld) {
+  const int n = *n_ptr;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t s = slot_of[i];
+    const int f = tab[s].first;
+    const int id = rank[f] + block_sums[f / kScanBlock];
+    const int k = child_index(fine[i], log2s);
+    parent[i] = id * 8 + k;
+    child[(int64_t)k * ld + id] = i;
+    if (f == i) { tab[s].val = id; ukeys[id] = tab[s].key; }
+  }
+}
+
+// Kernel map for an odd hyper-cube kernel (k0,k1,k2,k3) on tensor stride [2^log2s]*3 + [1]:
+// nbr[k][o] = row of (out[o] + delta_k) in the same coordinate set, k = i0 + k0*(i1 + k1*(i2 + k2*i3)),
+// delta_d = (i_d - k_d/2) * stride_d.  One independent hash probe per thread, o fastest so the
+// key reads and the table writes are coalesced.
+__global__ void k_kernel_map(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr,
+                             const int32_t* __restrict__ cap_n_ptr, const Slot* __restrict__ tab, int k0, int k1,
+                             int k2, int k3, int log2s, int32_t* __restrict__ nbr, int64_t ld) {
+  const int n = *n_ptr;
+  if (n == 0) return;
+  const uint32_t mask = table_capacity(*cap_n_ptr) - 1;
+  const int K = k0 * k1 * k2 * k3;
+  const int64_t total = (int64_t)K * n;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(idx / n), o = (int)(idx - (int64_t)k * n);
+    int r = k;
+    const int i0 = r % k0; r /= k0;
+    const int i1 = r % k1; r /= k1;
+    const int i2 = r % k2; r /= k2;
+    const int i3 = r;
+    int b, x, y, z, t;
+    unpack_key(keys[o], b, x, y, z, t);
+    x += (i0 - k0 / 2) << log2s;
+    y += (i1 - k1 / 2) << log2s;
+    z += (i2 - k2 / 2) << log2s;
+    t += (i3 - k3 / 2);
+    int res = -1;
+    if (coord_in_range(b, x, y, z, t)) res = table_find(tab, mask, pack_key(b, x, y, z, t));
+    nbr[(int64_t)k * ld + o] = res;
+  }
+}
+
+__global__ void k_unpack(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr,
+                         int32_t* __restrict__ out) {
+  const int n = *n_ptr;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int b, x, y, z, t;
+    unpack_key(keys[i], b, x, y, z, t);
+    int32_t* o = out + (int64_t)i * 5;
+    o[0] = b; o[1] = x; o[2] = y; o[3] = z; o[4] = t;
+  }
+}
+
+static inline int grid_for(int64_t work, int block, int cap = 148 * 32) {
+  int64_t g = (work + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (int)g;
+}
+
+}  // namespace sps
+
+using namespace sps;
+
+namespace sps {
+__global__ void k_copy_i32(int32_t* dst, const int32_t* src) { *dst = *src; }
+
+// n_upper sizes the launches; the true row count is n_upper, or *d_n when d_n is given.
+int voxelize_impl(sps_ctx* ctx, const float* d_points, int64_t n, const int32_t* d_n, int64_t ld_points,
+                  float voxel_size, cudaStream_t st) {
+  if (!ctx || (!d_points && n > 0) || n < 0 || ld_points < 5 || !(voxel_size > 0.f)) return SPS_ERR_BAD_ARG;
+  if (n > ctx->max_points) return SPS_ERR_CAPACITY;
+  ctx->n = n;
+  ctx->have_l0 = ctx->have_maps = false;
+  // n travels as a kernel-visible scalar so that every level shares one code path
+  if (d_n) k_copy_i32<<<1, 1, 0, st>>>(ctx->n_dev, d_n);
+  else k_set_i32<<<1, 1, 0, st>>>(ctx->n_dev, (int32_t)n);
+  const int nblk = cdiv(n > 0 ? n : 1, kScanBlock);
+  k_table_clear<<<grid_for(table_capacity(n), 256), 256, 0, st>>>(ctx->table, ctx->n_dev);
+  k_insert_points<<<grid_for(n, 256), 256, 0, st>>>(d_points, ld_points, ctx->n_dev, voxel_size, ctx->table,
+                                                     ctx->slot_of, ctx->status);
+  k_first_rank<<<nblk, kScanBlock, 0, st>>>(ctx->table, ctx->slot_of, ctx->n_dev, ctx->rank, ctx->block_sums,
+                                            ctx->ticket, ctx->counts + 0, nullptr, 0, nullptr);
+  k_assign_points<<<grid_for(n, 256), 256, 0, st>>>(ctx->table, ctx->slot_of, ctx->n_dev, ctx->rank,
+                                                     ctx->block_sums, ctx->keys[0], ctx->inv);
+  SPS_CUDA_CHECK(cudaGetLastError());
+  ctx->have_l0 = true;
+  return SPS_OK;
+}
+}  // namespace sps
+
+extern "C" int sps_voxelize(sps_ctx* ctx, const float* d_points, int64_t n, int64_t ld_points, float voxel_size,
+                            void* stream_) {
+  return voxelize_impl(ctx, d_points, n, nullptr, ld_points, voxel_size, (cudaStream_t)stream_);
+}
+
+extern "C" int sps_build_maps(sps_ctx* ctx, void* stream_) {
+  if (!ctx) return SPS_ERR_BAD_ARG;
+  if (!ctx->have_l0) return SPS_ERR_STATE;
+  cudaStream_t st = (cudaStream_t)stream_;
+  const int64_t n = ctx->n > 0 ? ctx->n : 1;  // host upper bound of every level's voxel count
+  const int nblk = cdiv(n, kScanBlock);
+  // level-0 kernel maps use the table left by sps_voxelize (capacity from n)
+  k_kernel_map<<<grid_for(125 * n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->n_dev, ctx->table, 5, 5,
+                                                       5, 1, 0, ctx->nbr5, ctx->ld);
+  k_kernel_map<<<grid_for(81 * n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->n_dev, ctx->table, 3, 3,
+                                                      3, 3, 0, ctx->nbr3[0], ctx->ld);
+  for (int L = 1; L < SPS_NUM_LEVELS; ++L) {
+    const int32_t* n_fine = ctx->counts + (L - 1);
+    k_table_clear<<<grid_for(table_capacity(n), 256), 256, 0, st>>>(ctx->table, n_fine);
+    k_insert_coarse<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[L - 1], n_fine, L, ctx->table, ctx->slot_of);
+    k_first_rank<<<nblk, kScanBlock, 0, st>>>(ctx->table, ctx->slot_of, n_fine, ctx->rank, ctx->block_sums,
+                                              ctx->ticket, ctx->counts + L, nullptr, 0, nullptr);
+    k_fill_i32<<<grid_for(8 * n, 256), 256, 0, st>>>(ctx->child[L], ctx->ld, 8, ctx->counts + L, -1);
+    k_assign_coarse<<<grid_for(n, 256), 256, 0, st>>>(ctx->table, ctx->slot_of, n_fine, ctx->rank, ctx->block_sums,
+                                                       ctx->keys[L - 1], L - 1, ctx->keys[L], ctx->parent[L - 1],
+                                                       ctx->child[L], ctx->ld);
+    k_kernel_map<<<grid_for(81 * n, 256), 256, 0, st>>>(ctx->keys[L], ctx->counts + L, n_fine, ctx->table, 3, 3, 3,
+                                                        3, L, ctx->nbr3[L], ctx->ld);
+  }
+  SPS_CUDA_CHECK(cudaGetLastError());
+  ctx->have_maps = true;
+  return SPS_OK;
+}
+
+extern "C" int sps_unpack_coords(sps_ctx* ctx, int level, int32_t* d_out, void* stream_) {
+  if (!ctx || !d_out || level < 0 || level >= SPS_NUM_LEVELS) return SPS_ERR_BAD_ARG;
+  if (!ctx->have_l0 || (level > 0 && !ctx->have_maps)) return SPS_ERR_STATE;
+  const int64_t n = ctx->n > 0 ? ctx->n : 1;
+  k_unpack<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream_>>>(ctx->keys[level], ctx->counts + level, d_out);
+  SPS_CUDA_CHECK(cudaGetLastError());
+  return SPS_OK;
+}
+
+// =====================================================================================
+// Submap selection: replicated base-map voxel hash + crops (a12/a13)
+// =====================================================================================
+struct sps_map {
+  sps::Slot* table = nullptr;
+  uint32_t cap = 0;
+  int64_t n = 0;
+  float ds = 0.f;
+  int32_t* scalars = nullptr;  // [0] = n (device copy), [1] = status
+};
+
+namespace sps {
+
+struct Scratch {  // carve of a sps_map_bytes(n) buffer
+  int32_t* scalars;   // 64 ints: [0]=n_dev [1]=ticket [2]=status
+  Slot* table;
+  uint32_t cap;
+  uint32_t* slot_of;
+  int32_t* rank;
+  int32_t* block_sums;
+  size_t bytes;
+};
+static Scratch carve_scratch(void* base, int64_t n) {
+  Scratch s;
+  char* p = (char*)base;
+  size_t off = 0;
+  auto take = [&](size_t b) { off = (off + 255) & ~size_t(255); char* r = p ? p + off : nullptr; off += b; return r; };
+  s.scalars = (int32_t*)take(64 * 4);
+  s.cap = table_capacity(n);
+  s.table = (Slot*)take((size_t)s.cap * sizeof(Slot));
+  s.slot_of = (uint32_t*)take((size_t)n * 4);
+  s.rank = (int32_t*)take((size_t)n * 4);
+  s.block_sums = (int32_t*)take((size_t)(n / kScanBlock + 2) * 4);
+  s.bytes = (off + 255) & ~size_t(255);
+  return s;
+}
+
+// util.to_coords_features (src/sps/datasets/util.py:72-75): fp32 division by ds, then
+// `.int()` = truncation toward zero; batch and time fields are 0 in this 3-D lattice.
+__device__ inline bool trunc_key(const float* __restrict__ p, float ds, unsigned long long& key) {
+  const float qx = truncf(__fdiv_rn(p[0], ds)), qy = truncf(__fdiv_rn(p[1], ds)), qz = truncf(__fdiv_rn(p[2], ds));
+  const bool ok = qx >= -(float)kXBias && qx < (float)kXBias && qy >= -(float)kXBias && qy < (float)kXBias &&
+                  qz >= -(float)kZBias && qz < (float)kZBias;
+  if (!ok) return false;
+  key = pack_key(0, (int)qx, (int)qy, (int)qz, 0);
+  return true;
+}
+
+__global__ void k_insert_xyz(const float* __restrict__ xyz, const int32_t* __restrict__ n_ptr, float ds, Slot* tab,
+                             uint32_t* __restrict__ slot_of, int32_t* status) {
+  const int n = *n_ptr;
+  const uint32_t mask = table_capacity(n) - 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    unsigned long long key;
+    if (!trunc_key(xyz + (int64_t)i * 3, ds, key)) {
+      atomicOr(status, kStatusRange);
+      if (slot_of) slot_of[i] = kInvalidSlot;
+      continue;
+    }
+    const uint32_t s = table_insert(tab, mask, key);
+    atomicMin(&tab[s].first, i);
+    tab[s].val = 0;
+    if (slot_of) slot_of[i] = s;
+  }
+}
+
+// util.prune tail (util.py:101-112): kept voxels -> `coordinates * ds` in fp32
+__global__ void k_write_submap(const Slot* __restrict__ tab, const uint32_t* __restrict__ slot_of,
+                               const int32_t* __restrict__ n_ptr, const int32_t* __restrict__ rank,
+                               const int32_t* __restrict__ block_sums, const Slot* __restrict__ filter,
+                               uint32_t filter_mask, float ds, float* __restrict__ out) {
+  const int n = *n_ptr;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t s = slot_of[i];
+    if (s == kInvalidSlot || tab[s].first != i) continue;
+    const unsigned long long key = tab[s].key;
+    if (table_find(filter, filter_mask, key) < 0) continue;
+    const int id = rank[i] + block_sums[i / kScanBlock];
+    int b, x, y, z, t;
+    unpack_key(key, b, x, y, z, t);
+    out[(int64_t)id * 3 + 0] = __fmul_rn((float)x, ds);
+    out[(int64_t)id * 3 + 1] = __fmul_rn((float)y, ds);
+    out[(int64_t)id * 3 + 2] = __fmul_rn((float)z, ds);
+  }
+}
+
+// mapmos_node.py:63-68: sqrt(sum((p - c)^2)) <= r in float64 (fp32 map promoted by the fp64 centre)
+__global__ void __launch_bounds__(kScanBlock)
+k_radius_rank(const float* __restrict__ xyz, const int32_t* __restrict__ n_ptr, double cx, double cy, double cz,
+              double radius, int32_t* __restrict__ rank, int32_t* block_sums, uint32_t* ticket, int32_t* count_out) {
+  const int n = *n_ptr;
+  const int nb = max(1, (n + kScanBlock - 1) / kScanBlock);
+  if ((int)blockIdx.x >= nb) return;
+  const int i = blockIdx.x * kScanBlock + threadIdx.x;
+  int flag = 0;
+  if (i < n) {
+    const double dx = __dsub_rn((double)xyz[(int64_t)i * 3 + 0], cx), dy = __dsub_rn((double)xyz[(int64_t)i * 3 + 1], cy),
+                 dz = __dsub_rn((double)xyz[(int64_t)i * 3 + 2], cz);
+    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    flag = __dsqrt_rn(d2) <= radius;
+  }
+  scan_flags(flag, i, n, nb, rank, block_sums, ticket, count_out);
+}
+__global__ void k_radius_write(const float* __restrict__ xyz, const int32_t* __restrict__ n_ptr, double cx, double cy,
+                               double cz, double radius, const int32_t* __restrict__ rank,
+                               const int32_t* __restrict__ block_sums, int32_t* __restrict__ out_idx) {
+  const int n = *n_ptr;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double dx = __dsub_rn((double)xyz[(int64_t)i * 3 + 0], cx), dy = __dsub_rn((double)xyz[(int64_t)i * 3 + 1], cy),
+                 dz = __dsub_rn((double)xyz[(int64_t)i * 3 + 2], cz);
+    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    if (__dsqrt_rn(d2) <= radius) out_idx[rank[i] + block_sums[i / kScanBlock]] = i;
+  }
+}
+
+// util.add_timestamp + vstack/hstack (util.py:156-174): [b, x,y,z, t], scan rows (t=1) then submap rows (t=0)
+__global__ void k_assemble(const float* __restrict__ scan, int64_t n_scan, const float* __restrict__ sub,
+                           const int32_t* __restrict__ n_sub_ptr, float b, float* __restrict__ out,
+                           int32_t* __restrict__ n_total) {
+  const int64_t n_sub = *n_sub_ptr;
+  const int64_t n = n_scan + n_sub;
+  if (n_total && blockIdx.x == 0 && threadIdx.x == 0) *n_total = (int32_t)n;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float* p = i < n_scan ? scan + i * 3 : sub + (i - n_scan) * 3;
+    float* o = out + i * 5;
+    o[0] = b; o[1] = p[0]; o[2] = p[1]; o[3] = p[2]; o[4] = i < n_scan ? 1.0f : 0.0f;
+  }
+}
+
+}  // namespace sps
+
+extern "C" size_t sps_map_bytes(int64_t max_points) {
+  if (max_points < 1) max_points = 1;
+  return carve_scratch(nullptr, max_points).bytes;
+}
+
+extern "C" int sps_map_build(sps_map** out, void* d_storage, size_t bytes, const float* d_map_xyz, int64_t n, float ds,
+                             void* stream_) {
+  if (!out || !d_storage || ((uintptr_t)d_storage & 255) || (!d_map_xyz && n > 0) || n < 0 || !(ds > 0.f))
+    return SPS_ERR_BAD_ARG;
+  Scratch s = carve_scratch(d_storage, n > 0 ? n : 1);
+  if (s.bytes > bytes) return SPS_ERR_CAPACITY;
+  cudaStream_t st = (cudaStream_t)stream_;
+  SPS_CUDA_CHECK(cudaMemsetAsync(s.scalars, 0, 64 * 4, st));
+  k_set_i32<<<1, 1, 0, st>>>(s.scalars + 0, (int32_t)n);
+  k_table_clear<<<grid_for(s.cap, 256), 256, 0, st>>>(s.table, s.scalars + 0);
+  k_insert_xyz<<<grid_for(n, 256), 256, 0, st>>>(d_map_xyz, s.scalars + 0, ds, s.table, nullptr, s.scalars + 2);
+  SPS_CUDA_CHECK(cudaGetLastError());
+  int32_t status = 0;
+  SPS_CUDA_CHECK(cudaMemcpyAsync(&status, s.scalars + 2, 4, cudaMemcpyDeviceToHost, st));
+  SPS_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (status & kStatusRange) return SPS_ERR_COORD_RANGE;
+  sps_map* m = new sps_map();
+  m->table = s.table; m->cap = s.cap; m->n = n; m->ds = ds; m->scalars = s.scalars;
+  *out = m;
+  return SPS_OK;
+}
+
+extern "C" int sps_map_destroy(sps_map* m) {
+  delete m;
+  return SPS_OK;
+}
+
+extern "C" int sps_submap_crop_voxel(const sps_map* map, const float* d_scan_xyz, int64_t n_scan, void* d_scratch,
+                                     size_t scratch_bytes, float* d_out_xyz, int32_t* d_counts, void* stream_) {
+  if (!map || (!d_scan_xyz && n_scan > 0) || n_scan < 0 || !d_scratch || ((uintptr_t)d_scratch & 255) ||
+      !d_out_xyz || !d_counts)
+    return SPS_ERR_BAD_ARG;
+  const int64_t n = n_scan > 0 ? n_scan : 1;
+  Scratch s = carve_scratch(d_scratch, n);
+  if (s.bytes > scratch_bytes) return SPS_ERR_CAPACITY;
+  cudaStream_t st = (cudaStream_t)stream_;
+  SPS_CUDA_CHECK(cudaMemsetAsync(s.scalars, 0, 64 * 4, st));
+  SPS_CUDA_CHECK(cudaMemsetAsync(d_counts, 0, 2 * 4, st));
+  k_set_i32<<<1, 1, 0, st>>>(s.scalars + 0, (int32_t)n_scan);
+  k_table_clear<<<grid_for(s.cap, 256), 256, 0, st>>>(s.table, s.scalars + 0);
+  k_insert_xyz<<<grid_for(n, 256), 256, 0, st>>>(d_scan_xyz, s.scalars + 0, map->ds, s.table, s.slot_of,
+                                                  s.scalars + 2);
+  k_first_rank<<<cdiv(n, kScanBlock), kScanBlock, 0, st>>>(s.table, s.slot_of, s.scalars + 0, s.rank, s.block_sums,
+                                                           (uint32_t*)(s.scalars + 1), d_counts + 0, map->table,
+                                                           map->cap - 1, d_counts + 1);
+  k_write_submap<<<grid_for(n, 256), 256, 0, st>>>(s.table, s.slot_of, s.scalars + 0, s.rank, s.block_sums,
+                                                    map->table, map->cap - 1, map->ds, d_out_xyz);
+  SPS_CUDA_CHECK(cudaGetLastError());
+  return SPS_OK;
+}
+
+extern "C" int sps_submap_crop_radius(const float* d_map_xyz, int64_t n, const double center[3], double radius,
+                                      int32_t* d_out_idx, int32_t* d_count, void* d_scratch, size_t scratch_bytes,
+                                      void* stream_) {
+  if ((!d_map_xyz && n > 0) || n < 0 || !center || !d_out_idx || !d_count || !d_scratch ||
+      ((uintptr_t)d_scratch & 255))
+    return SPS_ERR_BAD_ARG;
+  const int64_t nn = n > 0 ? n : 1;
+  Scratch s = carve_scratch(d_scratch, nn);
+  if (s.bytes > scratch_bytes) return SPS_ERR_CAPACITY;
+  cudaStream_t st = (cudaStream_t)stream_;
+  SPS_CUDA_CHECK(cudaMemsetAsync(s.scalars, 0, 64 * 4, st));
+  k_set_i32<<<1, 1, 0, st>>>(s.scalars + 0, (int32_t)n);
+  k_radius_rank<<<cdiv(nn, kScanBlock), kScanBlock, 0, st>>>(d_map_xyz, s.scalars + 0, center[0], center[1], center[2],
+                                                             radius, s.rank, s.block_sums, (uint32_t*)(s.scalars + 1),
+                                                             d_count);
+  k_radius_write<<<grid_for(nn, 256), 256, 0, st>>>(d_map_xyz, s.scalars + 0, center[0], center[1], center[2], radius,
+                                                    s.rank, s.block_sums, d_out_idx);
+  SPS_CUDA_CHECK(cudaGetLastError());
+  return SPS_OK;
+}
+
+extern "C" int sps_assemble(const float* d_scan_xyz, int64_t n_scan, const float* d_sub_xyz, const int32_t* d_n_sub,
+                            int64_t n_sub_max, float batch_index, float* d_out, void* stream_) {
+  if ((!d_scan_xyz && n_scan > 0) || n_scan < 0 || n_sub_max < 0 || !d_n_sub || !d_out) return SPS_ERR_BAD_ARG;
+  const int64_t n = n_scan + n_sub_max;
+  if (n == 0) return SPS_OK;
+  k_assemble<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream_>>>(d_scan_xyz, n_scan, d_sub_xyz, d_n_sub, batch_index,
+                                                                  d_out, nullptr);
+  SPS_CUDA_CHECK(cudaGetLastError());
+  return SPS_OK;
+}
+
+namespace sps {
+int forward_impl(sps_ctx* ctx, const sps_net* net, const float* d_points, int64_t n_upper, const int32_t* d_n,
+                 int64_t ld_points, float voxel_size, float* d_scores, int64_t n_scores, cudaStream_t st);
+}
+
+extern "C" size_t sps_infer_scan_scratch_bytes(int64_t n_scan) {
+  if (n_scan < 1) n_scan = 1;
+  // crop scratch + submap xyz [n_scan,3] + assembled rows [2*n_scan,5] + total-row scalar
+  return sps_map_bytes(n_scan) + (((size_t)n_scan * 3 * 4 + 255) & ~size_t(255)) +
+         (((size_t)n_scan * 2 * 5 * 4 + 255) & ~size_t(255)) + 256;
+}
+
+extern "C" int sps_infer_scan(sps_ctx* ctx, const sps_net* net, const sps_map* map, const float* d_scan_xyz,
+                              int64_t n_scan, float voxel_size, float* d_scores, void* d_scratch, size_t scratch_bytes,
+                              int32_t* d_counts, void* stream_) {
+  if (!ctx || !net || !map || !d_scan_xyz || n_scan < 1 || !d_scores || !d_scratch || !d_counts ||
+      ((uintptr_t)d_scratch & 255))
+    return SPS_ERR_BAD_ARG;
+  if (scratch_bytes < sps_infer_scan_scratch_bytes(n_scan)) return SPS_ERR_CAPACITY;
+  if (2 * n_scan > ctx->max_points) return SPS_ERR_CAPACITY;
+  cudaStream_t st = (cudaStream_t)stream_;
+  char* p = (char*)d_scratch;
+  const size_t crop_bytes = sps_map_bytes(n_scan);
+  float* sub = (float*)(p + crop_bytes);
+  float* rows = (float*)(p + crop_bytes + (((size_t)n_scan * 3 * 4 + 255) & ~size_t(255)));
+  int32_t* n_total = (int32_t*)((char*)rows + (((size_t)n_scan * 2 * 5 * 4 + 255) & ~size_t(255)));
+  int rc = sps_submap_crop_voxel(map, d_scan_xyz, n_scan, d_scratch, crop_bytes, sub, d_counts, stream_);
+  if (rc != SPS_OK) return rc;
+  k_assemble<<<grid_for(2 * n_scan, 256), 256, 0, st>>>(d_scan_xyz, n_scan, sub, d_counts + 0, 0.0f, rows, n_total);
+  SPS_CUDA_CHECK(cudaGetLastError());
+  return forward_impl(ctx, net, rows, 2 * n_scan, n_total, 5, voxel_size, d_scores, n_scan, st);
+}

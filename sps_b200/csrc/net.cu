@@ -1,0 +1,346 @@
+// CustomMinkUNet(1,1,D=4) weights (BN folded) and the fused forward schedule.
+//
+// Layer graph: src/sps/models/MinkowskiEngine/minkunet.py:52-219 with
+// PLANES=(8,16,32,64,64,32,16,8), INIT_DIM=8 (customminkunet.py:10-12), BasicBlock from ME
+// (mirrored at c_ws/src/mapmos/scripts/minkunet.py:31-82), downsample = 1x1 conv + BN iff
+// inplanes != planes (resnet.py:96-108).  Eval-mode MinkowskiBatchNorm is an affine map per
+// channel and is folded into the preceding kernel (scale) and a shift vector; ME.cat is free
+// because producers write straight into channel slices of the concat buffers.
+#include <map>
+#include <string>
+#include <vector>
+#include <cmath>
+#include <cstring>
+#include "ctx.h"
+
+namespace sps {
+int conv_simt(const sps_conv_args& a, cudaStream_t st);
+int conv_dispatch(const sps_conv_args& a, cudaStream_t st);
+
+struct ConvW {
+  float* w = nullptr;      // [K][cin][cout], BN scale folded
+  float* shift = nullptr;  // [cout]
+  float* w2 = nullptr;     // fused downsample [cin2][cout], BN scale folded (blocks only)
+  int K = 0, cin = 0, cout = 0, cin2 = 0;
+};
+
+constexpr int kPlanes[8] = {8, 16, 32, 64, 64, 32, 16, 8};
+constexpr int kInitDim = 8;
+}  // namespace sps
+
+struct sps_net {
+  std::map<std::string, std::vector<float>> host;
+  bool finalized = false;
+  sps::ConvW conv0, down[4], up[4], blk1[8], blk2[8];
+  float* head_w = nullptr;
+  float head_b = 0.f;
+};
+
+using namespace sps;
+
+namespace {
+
+struct Spec { std::string name; int K, cin, cout; };
+
+// total floats of the packed device image
+struct Packer {
+  std::vector<float> image;
+  size_t add(const std::vector<float>& v) {
+    size_t off = image.size();
+    image.insert(image.end(), v.begin(), v.end());
+    while (image.size() % 64) image.push_back(0.f);  // 256-byte alignment of every tensor
+    return off;
+  }
+};
+
+bool get(const sps_net* net, const std::string& name, size_t numel, const std::vector<float>** out) {
+  auto it = net->host.find(name);
+  if (it == net->host.end() || it->second.size() != numel) return false;
+  *out = &it->second;
+  return true;
+}
+
+// BN eval: y = (x - mean) / sqrt(var + 1e-5) * gamma + beta  ->  scale, shift
+bool bn_fold(const sps_net* net, const std::string& prefix, int C, std::vector<double>& scale,
+             std::vector<double>& shift) {
+  const std::vector<float>*g, *b, *m, *v;
+  if (!get(net, prefix + ".bn.weight", C, &g) || !get(net, prefix + ".bn.bias", C, &b) ||
+      !get(net, prefix + ".bn.running_mean", C, &m) || !get(net, prefix + ".bn.running_var", C, &v))
+    return false;
+  scale.resize(C); shift.resize(C);
+  for (int c = 0; c < C; ++c) {
+    // computed the way nn.BatchNorm1d does in fp32, then widened
+    const float inv = 1.0f / std::sqrt((*v)[c] + 1e-5f);
+    scale[c] = (double)(*g)[c] * inv;
+    shift[c] = (double)(*b)[c] - (double)(*m)[c] * scale[c];
+  }
+  return true;
+}
+
+bool fold_conv(const sps_net* net, const std::string& kname, const std::string& bnname, int K, int cin, int cout,
+               std::vector<float>& w, std::vector<double>& shift) {
+  const std::vector<float>* k;
+  if (!get(net, kname, (size_t)K * cin * cout, &k)) return false;
+  std::vector<double> scale;
+  if (!bn_fold(net, bnname, cout, scale, shift)) return false;
+  w.resize(k->size());
+  for (size_t i = 0; i < k->size(); ++i) w[i] = (float)((double)(*k)[i] * scale[i % cout]);
+  return true;
+}
+
+}  // namespace
+
+extern "C" int sps_net_create(sps_net** net) {
+  if (!net) return SPS_ERR_BAD_ARG;
+  *net = new sps_net();
+  return SPS_OK;
+}
+extern "C" int sps_net_destroy(sps_net* net) {
+  delete net;
+  return SPS_OK;
+}
+extern "C" int sps_net_set_tensor(sps_net* net, const char* name, const float* h_data, int64_t numel) {
+  if (!net || !name || !h_data || numel <= 0) return SPS_ERR_BAD_ARG;
+  net->host[name] = std::vector<float>(h_data, h_data + numel);
+  net->finalized = false;
+  return SPS_OK;
+}
+extern "C" size_t sps_net_device_bytes(void) { return 16u << 20; }  // 1.85 M parameters + padding
+
+extern "C" int sps_net_finalize(sps_net* net, void* d_weights, size_t bytes, void* stream) {
+  if (!net || !d_weights) return SPS_ERR_BAD_ARG;
+  Packer pk;
+  struct Pending { ConvW* cw; size_t w, shift, w2; bool has_w2; };
+  std::vector<Pending> pend;
+  auto add_conv = [&](ConvW& cw, const std::string& kname, const std::string& bn, int K, int cin, int cout) {
+    std::vector<float> w; std::vector<double> sh;
+    if (!fold_conv(net, kname, bn, K, cin, cout, w, sh)) return false;
+    std::vector<float> shf(sh.begin(), sh.end());
+    cw.K = K; cw.cin = cin; cw.cout = cout; cw.cin2 = 0;
+    pend.push_back({&cw, pk.add(w), pk.add(shf), 0, false});
+    return true;
+  };
+  auto add_block = [&](int b, const std::string& name, int cin, int cout) {
+    if (!add_conv(net->blk1[b], name + ".0.conv1.kernel", name + ".0.norm1", 81, cin, cout)) return false;
+    std::vector<float> w; std::vector<double> sh;
+    if (!fold_conv(net, name + ".0.conv2.kernel", name + ".0.norm2", 81, cout, cout, w, sh)) return false;
+    ConvW& cw = net->blk2[b];
+    cw.K = 81; cw.cin = cout; cw.cout = cout; cw.cin2 = 0;
+    Pending p{&cw, pk.add(w), 0, 0, false};
+    if (cin != cout) {
+      std::vector<float> w2; std::vector<double> sh2;
+      if (!fold_conv(net, name + ".0.downsample.0.kernel", name + ".0.downsample.1", 1, cin, cout, w2, sh2))
+        return false;
+      for (int c = 0; c < cout; ++c) sh[c] += sh2[c];
+      cw.cin2 = cin;
+      p.w2 = pk.add(w2);
+      p.has_w2 = true;
+    }
+    std::vector<float> shf(sh.begin(), sh.end());
+    p.shift = pk.add(shf);
+    pend.push_back(p);
+    return true;
+  };
+  const int I = kInitDim;
+  const int* P = kPlanes;
+  bool ok = add_conv(net->conv0, "conv0p1s1.kernel", "bn0", 125, 1, I);
+  const char* enc_c[4] = {"conv1p1s2", "conv2p2s2", "conv3p4s2", "conv4p8s2"};
+  const char* enc_b[4] = {"bn1", "bn2", "bn3", "bn4"};
+  const char* dec_c[4] = {"convtr4p16s2", "convtr5p8s2", "convtr6p4s2", "convtr7p2s2"};
+  const char* dec_b[4] = {"bntr4", "bntr5", "bntr6", "bntr7"};
+  int inpl = I;
+  for (int i = 0; i < 4 && ok; ++i) {
+    ok = ok && add_conv(net->down[i], std::string(enc_c[i]) + ".kernel", enc_b[i], 8, inpl, inpl);
+    ok = ok && add_block(i, "block" + std::to_string(i + 1), inpl, P[i]);
+    inpl = P[i];
+  }
+  const int skip[4] = {P[2], P[1], P[0], I};
+  for (int i = 0; i < 4 && ok; ++i) {
+    ok = ok && add_conv(net->up[i], std::string(dec_c[i]) + ".kernel", dec_b[i], 8, inpl, P[4 + i]);
+    ok = ok && add_block(4 + i, "block" + std::to_string(5 + i), P[4 + i] + skip[i], P[4 + i]);
+    inpl = P[4 + i];
+  }
+  const std::vector<float>*fw, *fb;
+  ok = ok && get(net, "final.kernel", P[7], &fw) && get(net, "final.bias", 1, &fb);
+  if (!ok) return SPS_ERR_BAD_ARG;
+  const size_t head_off = pk.add(*fw);
+  net->head_b = (*fb)[0];
+  if (pk.image.size() * sizeof(float) > bytes) return SPS_ERR_CAPACITY;
+  float* base = (float*)d_weights;
+  cudaStream_t st = (cudaStream_t)stream;
+  SPS_CUDA_CHECK(cudaMemcpyAsync(base, pk.image.data(), pk.image.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+  SPS_CUDA_CHECK(cudaStreamSynchronize(st));  // pk.image dies with this frame
+  for (auto& p : pend) {
+    p.cw->w = base + p.w;
+    p.cw->shift = base + p.shift;
+    p.cw->w2 = p.has_w2 ? base + p.w2 : nullptr;
+  }
+  net->head_w = base + head_off;
+  net->finalized = true;
+  return SPS_OK;
+}
+
+namespace sps {
+
+__global__ void k_fill_f32(float* __restrict__ p, const int32_t* __restrict__ n_ptr, float v) {
+  const int n = *n_ptr;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
+}
+
+// SparseTensor.slice(tensor_field) + sigmoid (src/sps/models/models.py:28-29)
+__global__ void k_devox_sigmoid(const float* __restrict__ logits, const int32_t* __restrict__ inv, int64_t n,
+                                float* __restrict__ scores) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = __ldg(inv + i);
+    float s = nanf("");
+    if (v >= 0) s = 1.0f / (1.0f + expf(-__ldg(logits + v)));
+    scores[i] = s;
+  }
+}
+
+static int g_forward_launches = 0;
+
+static int run_conv(const ConvW& w, int mode, const int32_t* map, int64_t map_ld, const int32_t* n_out,
+                    int64_t n_out_max, const float* in, int64_t in_ld, const float* in2, int64_t in2_ld,
+                    const float* res, int64_t res_ld, float* out, int64_t out_ld, cudaStream_t st,
+                    const float* head_w = nullptr, float head_b = 0.f, float* head_out = nullptr) {
+  sps_conv_args a;
+  memset(&a, 0, sizeof(a));
+  a.mode = mode; a.K = w.K; a.cin = w.cin; a.cout = w.cout;
+  a.map = map; a.map_ld = map_ld; a.n_out = n_out; a.n_out_max = n_out_max;
+  a.in = in; a.in_ld = in_ld; a.weight = w.w; a.shift = w.shift;
+  if (in2) { a.in2 = in2; a.in2_ld = in2_ld; a.cin2 = w.cin2; a.weight2 = w.w2; }
+  a.res = res; a.res_ld = res_ld; a.relu = 1; a.out = out; a.out_ld = out_ld;
+  a.head_w = head_w; a.head_b = head_b; a.head_out = head_out;
+  ++g_forward_launches;
+  return conv_dispatch(a, st);
+}
+
+int unet_forward(sps_ctx* c, const sps_net* net, const float* feat0, float* logits, cudaStream_t st) {
+  const int64_t nmax = c->n > 0 ? c->n : 1;
+  const int64_t ld = c->ld;
+  float** B = c->buf;
+  using C = sps_ctx;
+  // skip tensors live in the tail channel slice of the concat buffers (ME.cat(out, skip))
+  float* skip[4] = {B[C::CAT8] + 8, B[C::CAT7] + 16, B[C::CAT6] + 32, B[C::CAT5] + 64};
+  const int skip_ld[4] = {16, 24, 48, 96};
+  float* cat[4] = {B[C::CAT8], B[C::CAT7], B[C::CAT6], B[C::CAT5]};
+  float* E[4] = {B[C::E1], B[C::E2], B[C::E3], B[C::E4]};
+  float* H[4] = {B[C::H1], B[C::H2], B[C::H3], B[C::H4]};
+  int rc;
+#define RUN(...) do { rc = run_conv(__VA_ARGS__); if (rc != SPS_OK) return rc; } while (0)
+  // conv0p1s1 + bn0 + relu  (minkunet.py:162-164)
+  RUN(net->conv0, SPS_CONV_NBR, c->nbr5, ld, c->counts + 0, nmax, feat0, 1, nullptr, 0, nullptr, 0, skip[0],
+      skip_ld[0], st);
+  // encoder (minkunet.py:166-185)
+  for (int i = 0; i < 4; ++i) {
+    const int L = i + 1;
+    const int cw = net->down[i].cout;
+    RUN(net->down[i], SPS_CONV_NBR, c->child[L], ld, c->counts + L, nmax, skip[i], skip_ld[i], nullptr, 0, nullptr,
+        0, E[i], cw, st);
+    const ConvW& c1 = net->blk1[i];
+    const ConvW& c2 = net->blk2[i];
+    RUN(c1, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, E[i], cw, nullptr, 0, nullptr, 0, H[i], c1.cout, st);
+    float* out = (L < 4) ? skip[L] : B[C::B4];
+    const int out_ld = (L < 4) ? skip_ld[L] : 64;
+    if (c2.cin2)
+      RUN(c2, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, H[i], c1.cout, E[i], cw, nullptr, 0, out, out_ld, st);
+    else
+      RUN(c2, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, H[i], c1.cout, nullptr, 0, E[i], cw, out, out_ld, st);
+  }
+  // decoder (minkunet.py:188-217)
+  float* dec_in = B[C::B4];
+  int dec_in_ld = 64;
+  float* Hd[4] = {B[C::H5], B[C::H6], B[C::H7], B[C::H8]};
+  float* Bd[4] = {B[C::B5], B[C::B6], B[C::B7], nullptr};
+  for (int i = 0; i < 4; ++i) {
+    const int L = 3 - i;  // output level
+    RUN(net->up[i], SPS_CONV_UP, c->parent[L], 0, c->counts + L, nmax, dec_in, dec_in_ld, nullptr, 0, nullptr, 0,
+        cat[L], skip_ld[L], st);
+    const ConvW& c1 = net->blk1[4 + i];
+    const ConvW& c2 = net->blk2[4 + i];
+    RUN(c1, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, cat[L], skip_ld[L], nullptr, 0, nullptr, 0, Hd[i],
+        c1.cout, st);
+    if (i < 3) {
+      RUN(c2, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, Hd[i], c1.cout, cat[L], skip_ld[L], nullptr, 0,
+          Bd[i], c2.cout, st);
+      dec_in = Bd[i];
+      dec_in_ld = c2.cout;
+    } else {
+      // block8.conv2 + norm2 + downsample + relu, with `final` (8->1, bias; minkunet.py:219) fused
+      RUN(c2, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, Hd[i], c1.cout, cat[L], skip_ld[L], nullptr, 0,
+          nullptr, 0, st, net->head_w, net->head_b, logits);
+    }
+  }
+#undef RUN
+  return SPS_OK;
+}
+
+}  // namespace sps
+
+extern "C" int sps_unet_forward(sps_ctx* ctx, const sps_net* net, const float* d_feat0, float* d_logits,
+                                void* stream) {
+  if (!ctx || !net || !d_feat0 || !d_logits) return SPS_ERR_BAD_ARG;
+  if (!net->finalized || !ctx->have_maps) return SPS_ERR_STATE;
+  return unet_forward(ctx, net, d_feat0, d_logits, (cudaStream_t)stream);
+}
+
+extern "C" int sps_devox_sigmoid(const float* d_logits, const int32_t* d_inv, int64_t n, float* d_scores,
+                                 void* stream) {
+  if (!d_logits || !d_inv || !d_scores || n < 0) return SPS_ERR_BAD_ARG;
+  if (n == 0) return SPS_OK;
+  int64_t g = (n + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  k_devox_sigmoid<<<(int)g, 256, 0, (cudaStream_t)stream>>>(d_logits, d_inv, n, d_scores);
+  SPS_CUDA_CHECK(cudaGetLastError());
+  return SPS_OK;
+}
+
+namespace sps {
+int voxelize_impl(sps_ctx* ctx, const float* d_points, int64_t n, const int32_t* d_n, int64_t ld_points,
+                  float voxel_size, cudaStream_t st);
+
+int forward_impl(sps_ctx* ctx, const sps_net* net, const float* d_points, int64_t n, const int32_t* d_n,
+                 int64_t ld_points, float voxel_size, float* d_scores, int64_t n_scores, cudaStream_t st) {
+  if (!ctx || !net || !d_scores) return SPS_ERR_BAD_ARG;
+  if (!net->finalized) return SPS_ERR_STATE;
+  g_forward_launches = 0;
+  int rc = voxelize_impl(ctx, d_points, n, d_n, ld_points, voxel_size, st);
+  if (rc != SPS_OK) return rc;
+  rc = sps_build_maps(ctx, st);
+  if (rc != SPS_OK) return rc;
+  // TensorField.sparse(): voxel feature = mean of the constant 0.5 point features = 0.5
+  // (src/sps/models/models.py:22-25)
+  int64_t g = ((n > 0 ? n : 1) + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  k_fill_f32<<<(int)g, 256, 0, st>>>(ctx->buf[sps_ctx::FEAT0], ctx->counts + 0, 0.5f);
+  rc = unet_forward(ctx, net, ctx->buf[sps_ctx::FEAT0], ctx->buf[sps_ctx::LOGITS], st);
+  if (rc != SPS_OK) return rc;
+  rc = sps_devox_sigmoid(ctx->buf[sps_ctx::LOGITS], ctx->inv, n_scores, d_scores, st);
+  if (rc != SPS_OK) return rc;
+  g_forward_launches += 5 + 26 + 1 + 1;  // voxelize, maps, feature fill, devox
+  return SPS_OK;
+}
+}  // namespace sps
+
+extern "C" int sps_forward(sps_ctx* ctx, const sps_net* net, const float* d_points, int64_t n, int64_t ld_points,
+                           float voxel_size, float* d_scores, void* stream) {
+  return forward_impl(ctx, net, d_points, n, nullptr, ld_points, voxel_size, d_scores, n, (cudaStream_t)stream);
+}
+
+extern "C" int sps_forward_launch_count(void) { return g_forward_launches; }
+
+extern "C" int sps_forward_host(sps_ctx* ctx, const sps_net* net, const float* h_points, int64_t n,
+                                int64_t ld_points, float voxel_size, float* h_scores, void* stream) {
+  if (!ctx || !net || (!h_points && n > 0) || !h_scores || ld_points < 5 || ld_points > 8) return SPS_ERR_BAD_ARG;
+  if (n > ctx->max_points) return SPS_ERR_CAPACITY;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n > 0)
+    SPS_CUDA_CHECK(cudaMemcpyAsync(ctx->staging, h_points, (size_t)n * ld_points * sizeof(float),
+                                   cudaMemcpyHostToDevice, st));
+  int rc = sps_forward(ctx, net, ctx->staging, n, ld_points, voxel_size, ctx->scores, stream);
+  if (rc != SPS_OK) return rc;
+  if (n > 0)
+    SPS_CUDA_CHECK(cudaMemcpyAsync(h_scores, ctx->scores, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  return sps_ctx_status(ctx, stream);
+}
