@@ -193,6 +193,15 @@ int sps_set_conv_backend(int backend);
 int sps_umma_selftest(const void* d_a_bf16, const void* d_b_bf16, float* d_out, int M, int N, int K,
                       void* stream);
 
+/* ---------------------------------------------------------------- measurement ------------ */
+/* Per-stage CUDA-event timing of sps_forward on its own stream (bench.py roofline figures).
+ * sps_profile_read synchronises and returns up to `max` segments: names[i*32..] and ms[i]. */
+int sps_profile_enable(int on);
+int sps_profile_read(char* names, float* ms, int max, int* n_out);
+/* Number of (in,out) pairs of a kernel map of the last forward: kind 3 (3x3x3x3), 5 (5x5x5x1,
+ * level 0) or 8 (children of `level`).  Host-synchronising.  Used for algorithmic FLOP counts. */
+int sps_ctx_pair_count(sps_ctx* ctx, int level, int kind, int64_t* h_out, void* stream);
+
 /* Small helpers so that host code needs no second CUDA binding. */
 int sps_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream);
 int sps_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream);

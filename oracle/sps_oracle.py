@@ -399,10 +399,11 @@ def prune(map_xyz, scan_xyz, ds):
 
 def radius_crop(map_xyz, center, radius):
     """c_ws/src/mapmos/scripts/mapmos_node.py:63-68: map points with Euclidean distance
-    <= radius of ``center`` (fp32 arithmetic as numpy float32 arrays give), order kept."""
-    m = np.asarray(map_xyz, np.float32)[:, :3]
-    d = np.sqrt(np.sum((m - np.asarray(center, np.float32)) ** 2, axis=1))
-    return np.nonzero(d <= np.float32(radius))[0]
+    <= radius of ``center``, order kept.  The centre comes from a float64 pose matrix, so numpy
+    promotes the (fp32) map to float64 for the whole expression."""
+    m = np.asarray(map_xyz)[:, :3].astype(np.float64)
+    d = np.sqrt(np.sum((m - np.asarray(center, np.float64)) ** 2, axis=1))
+    return np.nonzero(d <= float(radius))[0]
 
 
 def assemble(scan_xyz, submap_xyz, batch_index=0.0):

@@ -24,7 +24,7 @@ SYMBOLS = [
     "sps_forward", "sps_forward_host", "sps_unet_forward", "sps_devox_sigmoid", "sps_forward_launch_count",
     "sps_map_bytes", "sps_map_build", "sps_map_destroy", "sps_submap_crop_voxel", "sps_submap_crop_radius",
     "sps_assemble", "sps_memcpy_d2h", "sps_memcpy_h2d", "sps_infer_scan", "sps_infer_scan_scratch_bytes", "sps_umma_selftest",
-    "sps_set_conv_backend",
+    "sps_set_conv_backend", "sps_profile_enable", "sps_profile_read", "sps_ctx_pair_count",
 ]
 
 
@@ -97,6 +97,9 @@ def load() -> C.CDLL:
         "sps_infer_scan_scratch_bytes": (sz, [i64]),
         "sps_umma_selftest": (i32, [vp, vp, vp, i32, i32, i32, vp]),
         "sps_set_conv_backend": (i32, [i32]),
+        "sps_profile_enable": (i32, [i32]),
+        "sps_profile_read": (i32, [vp, vp, i32, C.POINTER(i32)]),
+        "sps_ctx_pair_count": (i32, [vp, i32, i32, C.POINTER(i64), vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

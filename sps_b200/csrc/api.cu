@@ -146,3 +146,89 @@ extern "C" int sps_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, void
   SPS_CUDA_CHECK(cudaStreamSynchronize(st));
   return SPS_OK;
 }
+
+// ---------------------------------------------------------------- profiling ---------------
+#include <string>
+#include <vector>
+#include "profile.h"
+namespace sps {
+static bool g_prof = false;
+static std::vector<cudaEvent_t> g_ev;
+static std::vector<std::string> g_names;
+static size_t g_used = 0;
+bool prof_on() { return g_prof; }
+static cudaEvent_t next_event() {
+  if (g_used == g_ev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    g_ev.push_back(e);
+  }
+  return g_ev[g_used++];
+}
+void prof_begin(cudaStream_t st) {
+  if (!g_prof) return;
+  g_used = 0;
+  g_names.clear();
+  cudaEventRecord(next_event(), st);
+}
+void prof_mark(const char* name, cudaStream_t st) {
+  if (!g_prof || g_used == 0) return;
+  cudaEventRecord(next_event(), st);
+  g_names.push_back(name);
+}
+}  // namespace sps
+
+extern "C" int sps_profile_enable(int on) {
+  g_prof = on != 0;
+  g_used = 0;
+  g_names.clear();
+  return SPS_OK;
+}
+
+extern "C" int sps_profile_read(char* names, float* ms, int max, int* n_out) {
+  if (!names || !ms || !n_out || max < 0) return SPS_ERR_BAD_ARG;
+  int n = (int)g_names.size();
+  if (n > max) n = max;
+  if (g_used > 0) SPS_CUDA_CHECK(cudaEventSynchronize(g_ev[g_used - 1]));
+  for (int i = 0; i < n; ++i) {
+    SPS_CUDA_CHECK(cudaEventElapsedTime(&ms[i], g_ev[i], g_ev[i + 1]));
+    snprintf(names + 32 * i, 32, "%s", g_names[i].c_str());
+  }
+  *n_out = n;
+  return SPS_OK;
+}
+
+namespace sps {
+__global__ void k_count_nonneg(const int32_t* __restrict__ map, int64_t ld, int K, const int32_t* __restrict__ n_ptr,
+                               unsigned long long* out) {
+  const int n = *n_ptr;
+  const int64_t total = (int64_t)K * n;
+  unsigned long long local = 0;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(idx / n), o = (int)(idx - (int64_t)k * n);
+    local += map[(int64_t)k * ld + o] >= 0;
+  }
+  for (int d = 16; d; d >>= 1) local += __shfl_down_sync(0xffffffffu, local, d);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
+}
+}  // namespace sps
+
+extern "C" int sps_ctx_pair_count(sps_ctx* ctx, int level, int kind, int64_t* h_out, void* stream) {
+  if (!ctx || !h_out || level < 0 || level >= SPS_NUM_LEVELS) return SPS_ERR_BAD_ARG;
+  if (!ctx->have_maps) return SPS_ERR_STATE;
+  const int32_t* map = kind == 3 ? ctx->nbr3[level] : kind == 5 ? (level == 0 ? ctx->nbr5 : nullptr)
+                                                    : kind == 8 ? ctx->child[level] : nullptr;
+  const int K = kind == 3 ? 81 : kind == 5 ? 125 : 8;
+  if (!map) return SPS_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* d_out = reinterpret_cast<unsigned long long*>(ctx->counts + 16);
+  SPS_CUDA_CHECK(cudaMemsetAsync(d_out, 0, 8, st));
+  k_count_nonneg<<<148 * 8, 256, 0, st>>>(map, ctx->ld, K, ctx->counts + level, d_out);
+  SPS_CUDA_CHECK(cudaGetLastError());
+  unsigned long long h = 0;
+  SPS_CUDA_CHECK(cudaMemcpyAsync(&h, d_out, 8, cudaMemcpyDeviceToHost, st));
+  SPS_CUDA_CHECK(cudaStreamSynchronize(st));
+  *h_out = (int64_t)h;
+  return SPS_OK;
+}

@@ -9,6 +9,7 @@
 // surplus blocks exit on the device count, so a whole forward needs no host synchronisation.
 #include <limits.h>
 #include "ctx.h"
+#include "profile.h"
 
 namespace sps {
 
@@ -303,8 +304,10 @@ extern "C" int sps_build_maps(sps_ctx* ctx, void* stream_) {
   // level-0 kernel maps use the table left by sps_voxelize (capacity from n)
   k_kernel_map<<<grid_for(125 * n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->n_dev, ctx->table, 5, 5,
                                                        5, 1, 0, ctx->nbr5, ctx->ld);
+  prof_mark("kmap5.L0", st);
   k_kernel_map<<<grid_for(81 * n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->n_dev, ctx->table, 3, 3,
                                                       3, 3, 0, ctx->nbr3[0], ctx->ld);
+  prof_mark("kmap3.L0", st);
   for (int L = 1; L < SPS_NUM_LEVELS; ++L) {
     const int32_t* n_fine = ctx->counts + (L - 1);
     k_table_clear<<<grid_for(table_capacity(n), 256), 256, 0, st>>>(ctx->table, n_fine);
@@ -315,8 +318,12 @@ extern "C" int sps_build_maps(sps_ctx* ctx, void* stream_) {
     k_assign_coarse<<<grid_for(n, 256), 256, 0, st>>>(ctx->table, ctx->slot_of, n_fine, ctx->rank, ctx->block_sums,
                                                        ctx->keys[L - 1], L - 1, ctx->keys[L], ctx->parent[L - 1],
                                                        ctx->child[L], ctx->ld);
+    static const char* nm_s[5] = {"", "stride.L1", "stride.L2", "stride.L3", "stride.L4"};
+    static const char* nm_k[5] = {"", "kmap3.L1", "kmap3.L2", "kmap3.L3", "kmap3.L4"};
+    prof_mark(nm_s[L], st);
     k_kernel_map<<<grid_for(81 * n, 256), 256, 0, st>>>(ctx->keys[L], ctx->counts + L, n_fine, ctx->table, 3, 3, 3,
                                                         3, L, ctx->nbr3[L], ctx->ld);
+    prof_mark(nm_k[L], st);
   }
   SPS_CUDA_CHECK(cudaGetLastError());
   ctx->have_maps = true;

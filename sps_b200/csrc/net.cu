@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstring>
 #include "ctx.h"
+#include "profile.h"
 
 namespace sps {
 int conv_simt(const sps_conv_args& a, cudaStream_t st);
@@ -200,7 +201,7 @@ __global__ void k_devox_sigmoid(const float* __restrict__ logits, const int32_t*
 
 static int g_forward_launches = 0;
 
-static int run_conv(const ConvW& w, int mode, const int32_t* map, int64_t map_ld, const int32_t* n_out,
+static int run_conv(const char* name, const ConvW& w, int mode, const int32_t* map, int64_t map_ld, const int32_t* n_out,
                     int64_t n_out_max, const float* in, int64_t in_ld, const float* in2, int64_t in2_ld,
                     const float* res, int64_t res_ld, float* out, int64_t out_ld, cudaStream_t st,
                     const float* head_w = nullptr, float head_b = 0.f, float* head_out = nullptr) {
@@ -213,7 +214,9 @@ static int run_conv(const ConvW& w, int mode, const int32_t* map, int64_t map_ld
   a.res = res; a.res_ld = res_ld; a.relu = 1; a.out = out; a.out_ld = out_ld;
   a.head_w = head_w; a.head_b = head_b; a.head_out = head_out;
   ++g_forward_launches;
-  return conv_dispatch(a, st);
+  const int rc = conv_dispatch(a, st);
+  prof_mark(name, st);
+  return rc;
 }
 
 int unet_forward(sps_ctx* c, const sps_net* net, const float* feat0, float* logits, cudaStream_t st) {
@@ -227,26 +230,32 @@ int unet_forward(sps_ctx* c, const sps_net* net, const float* feat0, float* logi
   float* cat[4] = {B[C::CAT8], B[C::CAT7], B[C::CAT6], B[C::CAT5]};
   float* E[4] = {B[C::E1], B[C::E2], B[C::E3], B[C::E4]};
   float* H[4] = {B[C::H1], B[C::H2], B[C::H3], B[C::H4]};
+  static const char* nm_down[4] = {"conv1p1s2", "conv2p2s2", "conv3p4s2", "conv4p8s2"};
+  static const char* nm_up[4] = {"convtr4p16s2", "convtr5p8s2", "convtr6p4s2", "convtr7p2s2"};
+  static const char* nm_c1[8] = {"block1.conv1", "block2.conv1", "block3.conv1", "block4.conv1",
+                                 "block5.conv1", "block6.conv1", "block7.conv1", "block8.conv1"};
+  static const char* nm_c2[8] = {"block1.conv2", "block2.conv2", "block3.conv2", "block4.conv2",
+                                 "block5.conv2", "block6.conv2", "block7.conv2", "block8.conv2+final"};
   int rc;
 #define RUN(...) do { rc = run_conv(__VA_ARGS__); if (rc != SPS_OK) return rc; } while (0)
   // conv0p1s1 + bn0 + relu  (minkunet.py:162-164)
-  RUN(net->conv0, SPS_CONV_NBR, c->nbr5, ld, c->counts + 0, nmax, feat0, 1, nullptr, 0, nullptr, 0, skip[0],
+  RUN("conv0", net->conv0, SPS_CONV_NBR, c->nbr5, ld, c->counts + 0, nmax, feat0, 1, nullptr, 0, nullptr, 0, skip[0],
       skip_ld[0], st);
   // encoder (minkunet.py:166-185)
   for (int i = 0; i < 4; ++i) {
     const int L = i + 1;
     const int cw = net->down[i].cout;
-    RUN(net->down[i], SPS_CONV_NBR, c->child[L], ld, c->counts + L, nmax, skip[i], skip_ld[i], nullptr, 0, nullptr,
+    RUN(nm_down[i], net->down[i], SPS_CONV_NBR, c->child[L], ld, c->counts + L, nmax, skip[i], skip_ld[i], nullptr, 0, nullptr,
         0, E[i], cw, st);
     const ConvW& c1 = net->blk1[i];
     const ConvW& c2 = net->blk2[i];
-    RUN(c1, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, E[i], cw, nullptr, 0, nullptr, 0, H[i], c1.cout, st);
+    RUN(nm_c1[i], c1, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, E[i], cw, nullptr, 0, nullptr, 0, H[i], c1.cout, st);
     float* out = (L < 4) ? skip[L] : B[C::B4];
     const int out_ld = (L < 4) ? skip_ld[L] : 64;
     if (c2.cin2)
-      RUN(c2, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, H[i], c1.cout, E[i], cw, nullptr, 0, out, out_ld, st);
+      RUN(nm_c2[i], c2, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, H[i], c1.cout, E[i], cw, nullptr, 0, out, out_ld, st);
     else
-      RUN(c2, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, H[i], c1.cout, nullptr, 0, E[i], cw, out, out_ld, st);
+      RUN(nm_c2[i], c2, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, H[i], c1.cout, nullptr, 0, E[i], cw, out, out_ld, st);
   }
   // decoder (minkunet.py:188-217)
   float* dec_in = B[C::B4];
@@ -255,20 +264,20 @@ int unet_forward(sps_ctx* c, const sps_net* net, const float* feat0, float* logi
   float* Bd[4] = {B[C::B5], B[C::B6], B[C::B7], nullptr};
   for (int i = 0; i < 4; ++i) {
     const int L = 3 - i;  // output level
-    RUN(net->up[i], SPS_CONV_UP, c->parent[L], 0, c->counts + L, nmax, dec_in, dec_in_ld, nullptr, 0, nullptr, 0,
+    RUN(nm_up[i], net->up[i], SPS_CONV_UP, c->parent[L], 0, c->counts + L, nmax, dec_in, dec_in_ld, nullptr, 0, nullptr, 0,
         cat[L], skip_ld[L], st);
     const ConvW& c1 = net->blk1[4 + i];
     const ConvW& c2 = net->blk2[4 + i];
-    RUN(c1, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, cat[L], skip_ld[L], nullptr, 0, nullptr, 0, Hd[i],
+    RUN(nm_c1[4 + i], c1, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, cat[L], skip_ld[L], nullptr, 0, nullptr, 0, Hd[i],
         c1.cout, st);
     if (i < 3) {
-      RUN(c2, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, Hd[i], c1.cout, cat[L], skip_ld[L], nullptr, 0,
+      RUN(nm_c2[4 + i], c2, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, Hd[i], c1.cout, cat[L], skip_ld[L], nullptr, 0,
           Bd[i], c2.cout, st);
       dec_in = Bd[i];
       dec_in_ld = c2.cout;
     } else {
       // block8.conv2 + norm2 + downsample + relu, with `final` (8->1, bias; minkunet.py:219) fused
-      RUN(c2, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, Hd[i], c1.cout, cat[L], skip_ld[L], nullptr, 0,
+      RUN(nm_c2[4 + i], c2, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, Hd[i], c1.cout, cat[L], skip_ld[L], nullptr, 0,
           nullptr, 0, st, net->head_w, net->head_b, logits);
     }
   }
@@ -302,11 +311,19 @@ int voxelize_impl(sps_ctx* ctx, const float* d_points, int64_t n, const int32_t*
 
 int forward_impl(sps_ctx* ctx, const sps_net* net, const float* d_points, int64_t n, const int32_t* d_n,
                  int64_t ld_points, float voxel_size, float* d_scores, int64_t n_scores, cudaStream_t st) {
-  if (!ctx || !net || !d_scores) return SPS_ERR_BAD_ARG;
+  if (!ctx || !net || n < 0) return SPS_ERR_BAD_ARG;
   if (!net->finalized) return SPS_ERR_STATE;
   g_forward_launches = 0;
+  if (n == 0) {  // empty input: nothing to score (an empty TensorField in the reference)
+    ctx->n = 0;
+    ctx->have_l0 = ctx->have_maps = false;
+    return SPS_OK;
+  }
+  if (!d_scores || !d_points) return SPS_ERR_BAD_ARG;
+  prof_begin(st);
   int rc = voxelize_impl(ctx, d_points, n, d_n, ld_points, voxel_size, st);
   if (rc != SPS_OK) return rc;
+  prof_mark("voxelize", st);
   rc = sps_build_maps(ctx, st);
   if (rc != SPS_OK) return rc;
   // TensorField.sparse(): voxel feature = mean of the constant 0.5 point features = 0.5
@@ -318,6 +335,7 @@ int forward_impl(sps_ctx* ctx, const sps_net* net, const float* d_points, int64_
   if (rc != SPS_OK) return rc;
   rc = sps_devox_sigmoid(ctx->buf[sps_ctx::LOGITS], ctx->inv, n_scores, d_scores, st);
   if (rc != SPS_OK) return rc;
+  prof_mark("devox_sigmoid", st);
   g_forward_launches += 5 + 26 + 1 + 1;  // voxelize, maps, feature fill, devox
   return SPS_OK;
 }
@@ -332,7 +350,8 @@ extern "C" int sps_forward_launch_count(void) { return g_forward_launches; }
 
 extern "C" int sps_forward_host(sps_ctx* ctx, const sps_net* net, const float* h_points, int64_t n,
                                 int64_t ld_points, float voxel_size, float* h_scores, void* stream) {
-  if (!ctx || !net || (!h_points && n > 0) || !h_scores || ld_points < 5 || ld_points > 8) return SPS_ERR_BAD_ARG;
+  if (!ctx || !net || n < 0 || (n > 0 && (!h_points || !h_scores)) || ld_points < 5 || ld_points > 8)
+    return SPS_ERR_BAD_ARG;
   if (n > ctx->max_points) return SPS_ERR_CAPACITY;
   cudaStream_t st = (cudaStream_t)stream;
   if (n > 0)

@@ -138,6 +138,7 @@ class SPSModel(nn.Module):
         self._net = None
         self._min_points = int(max_points)
         self._net_version = -1
+        self._host_out = None
 
     def invalidate(self):
         """Weights changed in place: re-fold and re-upload them at the next forward."""
@@ -170,7 +171,12 @@ class SPSModel(nn.Module):
         if device.type != "cuda":
             raise RuntimeError("move the model to a CUDA device first: sps_b200 has no CPU path")
         engine, net = self._prepare(coordinates.shape[0], device)
-        return engine.forward_host(net, coordinates.contiguous(), self.voxel_size)
+        n = coordinates.shape[0]
+        if self._host_out is None or self._host_out.numel() < n:
+            # pinned landing buffer for the D2H of the scores, reused across calls: the returned
+            # tensor is a view that the NEXT host-side forward overwrites (clone it to keep it)
+            self._host_out = torch.empty(max(n, 1), dtype=torch.float32).pin_memory()
+        return engine.forward_host(net, coordinates.contiguous(), self.voxel_size, out=self._host_out[:n])
 
     def check(self):
         """Synchronise and raise if the last forward met an out-of-range coordinate."""

@@ -1,0 +1,215 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs.  Bar: voxel coordinates / inverse maps / kernel maps bit-exact (canonical sets), scores
+within 2e-3 absolute (north star), thresholded labels >= 99.9 % equal."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import make_case
+from oracle import sps_oracle as O
+from oracle import me_cpu
+
+pytestmark = pytest.mark.gpu
+
+SCORE_TOL = 2e-3   # BASELINE.json north_star: "per-point scores must match within 2e-3 absolute"
+EPS = 0.84         # config/config.yaml:33
+
+
+@pytest.fixture(scope="module")
+def engine_mod():
+    from sps_b200 import engine
+    return engine
+
+
+def dev(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).cuda()
+
+
+def canon_kmap(nbr, coords_in, coords_out):
+    return O.canonical_kernel_map(nbr, coords_in, coords_out)
+
+
+def amplified(sd, gain=40.0):
+    """Scale the head so that scores spread over (0,1) instead of hugging sigmoid(0)."""
+    sd = dict(sd)
+    sd["final.kernel"] = sd["final.kernel"] * np.float32(gain)
+    return sd
+
+
+@pytest.mark.parametrize("sensor,seed", [("tiny", 3), ("tiny", 11), ("hdl-32", 1)])
+def test_voxelize_and_maps_bit_exact(engine_mod, sensor, seed):
+    rows = make_case(sensor, seed=seed)
+    pts = rows[:, :5]
+    eng = engine_mod.Engine(len(pts))
+    eng.voxelize(dev(pts), 0.1)
+    eng.build_maps()
+    eng.status()
+    c0, inv = O.voxelize(pts, 0.1)
+    lv = O.Levels(c0)
+    # level 0: identical rows in identical (first-occurrence) order, identical inverse map
+    got0 = eng.coords(0)
+    assert got0.shape == c0.shape and (got0 == c0).all()
+    assert (eng.inverse_map() == inv).all()
+    for L in range(5):
+        got = eng.coords(L)
+        assert (got == lv.coords[L]).all(), f"level {L} coordinates differ"
+        nbr = eng.kernel_map(L, "3")
+        assert (canon_kmap(nbr, got, got) == canon_kmap(lv.nbr3[L], lv.coords[L], lv.coords[L])).all()
+        assert (nbr == lv.nbr3[L]).all()
+    assert (eng.kernel_map(0, "5") == lv.nbr5).all()
+    for L in range(4):
+        pk = eng.parent(L)
+        assert (pk >> 3 == lv.parent[L]).all() and (pk & 7 == lv.koff[L]).all()
+        child = eng.kernel_map(L + 1, "child")
+        # child table is the stride-2 kernel map: child[k][c] = the fine voxel f with parent c, offset k
+        exp = np.full_like(child, -1)
+        exp[lv.koff[L], lv.parent[L]] = np.arange(len(lv.parent[L]))
+        assert (child == exp).all()
+
+
+def test_quantisation_quirks(engine_mod):
+    """fp32 division then floor: -0.05/0.1 -> -1; x/0.1f differs from x*10 on some inputs."""
+    rng = np.random.default_rng(0)
+    xyz = rng.uniform(-100, 100, (200000, 3)).astype(np.float32)
+    special = np.array([[-0.05, 0.05, -0.1], [0.3, -0.3, 0.7], [1e-7, -1e-7, 0.0], [-0.0, 0.1, 0.2]], np.float32)
+    xyz = np.vstack([special, xyz])
+    pts = np.hstack([np.zeros((len(xyz), 1), np.float32), xyz, np.ones((len(xyz), 1), np.float32)])
+    eng = engine_mod.Engine(len(pts))
+    eng.voxelize(dev(pts), 0.1)
+    eng.status()
+    c0, inv = O.voxelize(pts, 0.1)
+    assert (eng.coords(0) == c0).all() and (eng.inverse_map() == inv).all()
+    assert tuple(c0[inv[0]][1:4]) == (-1, 0, -1)
+
+
+def test_edge_inputs(engine_mod, state_dict):
+    net = engine_mod.Net(state_dict)
+    eng = engine_mod.Engine(4096)
+    # empty input
+    out = eng.forward(net, torch.zeros((0, 5), device="cuda"), 0.1)
+    eng.status()
+    assert out.shape == (0,)
+    # one point / all points in one voxel / duplicates
+    for pts in (np.array([[0, 1.0, 2.0, 3.0, 1]], np.float32),
+                np.tile(np.array([[0, 1.01, 2.02, 3.03, 1]], np.float32), (100, 1)),
+                np.array([[0, 0, 0, 0, 1], [0, 0, 0, 0, 0], [1, 0, 0, 0, 1], [1, 0, 0, 0, 0]], np.float32)):
+        got = eng.forward(net, dev(pts), 0.1).cpu().numpy()
+        eng.status()
+        ref = O.sps_forward(pts, 0.1, state_dict)
+        assert np.abs(got - ref).max() < 1e-5
+
+
+def test_coordinate_range_is_reported(engine_mod, state_dict):
+    from sps_b200._cabi import SpsError, SPS_ERR_COORD_RANGE
+    eng = engine_mod.Engine(1024)
+    pts = np.array([[0, 0, 0, 0, 1], [0, 2.0e4, 0, 0, 1], [300, 0, 0, 0, 1], [0, float("nan"), 0, 0, 1]], np.float32)
+    eng.voxelize(dev(pts), 0.1)
+    with pytest.raises(SpsError) as e:
+        eng.status()
+    assert e.value.code == SPS_ERR_COORD_RANGE
+    eng.status()  # sticky word was cleared
+
+
+@pytest.mark.parametrize("sensor,seed,submap", [("tiny", 3, "voxel"), ("hdl-32", 2, "voxel"), ("os1-64", 0, "radius")])
+def test_scores_match_oracle(engine_mod, state_dict, sensor, seed, submap):
+    rows = make_case(sensor, seed=seed, submap=submap, n_map_poses=6)
+    pts = rows[:, :5]
+    for sd in (state_dict, amplified(state_dict)):
+        net = engine_mod.Net(sd)
+        eng = engine_mod.Engine(len(pts))
+        got = eng.forward(net, dev(pts), 0.1).cpu().numpy()
+        eng.status()
+        ref, _, _ = me_cpu.forward(pts, 0.1, me_cpu.pack_weights(sd))
+        err = np.abs(got - ref)
+        assert err.max() < SCORE_TOL, f"max |score diff| {err.max():.3e}"
+        agree = np.mean(O.threshold_labels(got, EPS) == O.threshold_labels(ref, EPS))
+        assert agree >= 0.999
+    if sensor == "tiny":
+        ref64 = O.sps_forward(pts, 0.1, sd, dtype=np.float64)
+        assert np.abs(got - ref64).max() < SCORE_TOL
+
+
+def test_batched_scans_are_independent(engine_mod, state_dict):
+    """Batch index is a coordinate that receives no kernel offset (blt_dataset.py:173-182)."""
+    rows = make_case("tiny", seed=5, batch=3)
+    pts = rows[:, :5]
+    net = engine_mod.Net(state_dict)
+    eng = engine_mod.Engine(len(pts))
+    got = eng.forward(net, dev(pts), 0.1).cpu().numpy()
+    eng.status()
+    for b in range(3):
+        sel = pts[:, 0] == b
+        one = pts[sel].copy()
+        one[:, 0] = 0
+        ref = O.sps_forward(one, 0.1, state_dict)
+        assert np.abs(got[sel] - ref).max() < 1e-5
+
+
+def test_host_entry_point_and_model_api(engine_mod, state_dict):
+    """SPSModel / SPSNet keep the reference call shape (models.py:13-30, 56-60, 84-104)."""
+    from sps_b200.models import SPSNet
+    rows = make_case("tiny", seed=7, batch=2)
+    cfg = {"MODEL": {"VOXEL_SIZE": 0.1}, "FILTER": {"THRESHOLD": EPS}, "DATA": {"SPLIT": {"TEST": ["synthetic"]}}}
+    model = SPSNet(cfg)
+    model.model.MinkUNet.load_state_dict({k: torch.as_tensor(v) for k, v in state_dict.items()})
+    model = model.cuda()
+    model.freeze()
+    ref = O.sps_forward(rows[:, :5], 0.1, state_dict)
+    batch = torch.as_tensor(rows)
+    got_host = model(batch)                       # CPU tensor -> sps_forward_host
+    assert not got_host.is_cuda and np.abs(got_host.numpy() - ref).max() < 1e-5
+    got_dev = model(batch.cuda())                 # CUDA tensor -> sps_forward
+    assert got_dev.is_cuda and np.abs(got_dev.cpu().numpy() - ref).max() < 1e-5
+    model.predict_step(batch.cuda(), 0)
+    m = O.predict_step_metrics(ref, rows[:, 5], rows[:, 4], EPS)
+    s = model.summary()
+    assert abs(s["Loss"] - m["loss"]) < 1e-5 and abs(s["dIoU"] - m["dIoU"]) < 1e-6
+    assert abs(s["Precision"] - m["precision"]) < 1e-6 and abs(s["Recall"] - m["recall"]) < 1e-6
+    assert abs(s["F1"] - m["f1"]) < 1e-6 and abs(s["R2"] - m["r2"]) < 1e-3
+
+
+def test_prune_crop_and_streamed_infer(engine_mod, state_dict):
+    """util.to_coords_features / prune / infer (util.py:67-114,163-184) incl. the trunc-vs-floor
+    lattice mismatch and the x ds round trip at negative coordinates."""
+    from sps_b200 import synth, util
+    world = synth.World(2)
+    map_xyz = synth.base_map(world, "tiny", n_poses=8, seed=2)
+    scan = synth.scan(world, "hdl-32", pose=(1.0, -2.0, 0.3), seed=9)
+    ref_sub, ref_n = O.prune(map_xyz, scan, 0.1)
+    map_cf = util.to_coords_features(torch.as_tensor(map_xyz), "map", 0.1)
+    scan_cf = util.to_coords_features(torch.as_tensor(scan), "scan", 0.1)
+    assert (map_cf.cloud_coords.cpu().numpy() == O.to_coords(map_xyz, 0.1)).all()
+    sub, n_scan_vox = util.prune(map_cf, scan_cf, 0.1)
+    assert n_scan_vox == ref_n
+    sub = sub.cpu().numpy()
+    assert sub.shape == ref_sub.shape
+    assert (O.canonical(sub.view(np.int32)) == O.canonical(ref_sub.view(np.int32))).all()   # bit-exact fp32
+    # deterministic order: first occurrence among the scan points
+    cs, _ = O.unique_first(O.to_coords(scan, 0.1))
+    lo, rng = O._extent(cs, O.to_coords(map_xyz, 0.1))
+    keep = np.isin(O._pack(cs, lo, rng), O._pack(O.to_coords(map_xyz, 0.1), lo, rng))
+    assert (sub == cs[keep].astype(np.float32) * np.float32(0.1)).all()
+
+    class M:  # util.infer only needs .forward
+        def __init__(self):
+            from sps_b200.models import SPSModel
+            self.m = SPSModel(0.1)
+            self.m.MinkUNet.load_state_dict({k: torch.as_tensor(v) for k, v in state_dict.items()})
+            self.m = self.m.cuda().eval()
+        def forward(self, t):
+            return self.m(t)
+    model = M()
+    scores, _ = util.infer(torch.as_tensor(scan).cuda(), torch.as_tensor(sub).cuda(), model)
+    ref = O.infer(scan, ref_sub[np.lexsort(ref_sub.T[::-1])], 0.1, state_dict)
+    assert np.abs(scores.cpu().numpy() - ref).max() < 1e-5
+    # fused streamed path: crop + assemble + forward without host sync
+    mh = map_cf.map_hash
+    eng = engine_mod.Engine(2 * len(scan))
+    net = engine_mod.Net(state_dict)
+    out, counts = mh.infer_scan(eng, net, torch.as_tensor(scan).cuda(), 0.1)
+    eng.status()
+    assert counts.cpu().tolist() == [len(ref_sub), ref_n]
+    assert np.abs(out.cpu().numpy() - ref).max() < 1e-5
+    # radius crop (mapmos_node.py:63-68)
+    idx = mh.crop_radius((1.0, -2.0, 1.8), 30.0).cpu().numpy()
+    assert (idx == O.radius_crop(map_xyz.astype(np.float64), np.array([1.0, -2.0, 1.8]), 30.0)).all()
