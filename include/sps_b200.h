@@ -109,9 +109,16 @@ typedef struct sps_conv_args {
   /* optional fused head: logit[row] = dot(relu_out[row], head_w) + head_b  (final 1x1 conv,
    * minkunet.py:152-158,219); requires cout == 8; `out` may then be NULL                   */
   const float* head_w; float head_b; float* head_out;
+  /* tensor-core path (optional): the same weights (and weight2) as a K-major [cout][kmajor_ld]
+   * matrix, TF32-rounded, made by sps_conv_pack_kmajor; NULL -> only the CUDA-core kernel fits */
+  const float* weight_kmajor; int64_t kmajor_ld;
+  int round_out;            /* store outputs rounded to TF32 (nearest), so that a following
+                               tensor-core layer does not truncate its operand               */
 } sps_conv_args;
 /* MinkowskiConvolution / MinkowskiConvolutionTranspose (+ folded MinkowskiBatchNorm, ReLU,
- * residual) forward: minkunet.py:55-158, resnet.py:97-108, ME BasicBlock. fp32 CUDA-core path. */
+ * residual) forward: minkunet.py:55-158, resnet.py:97-108, ME BasicBlock.  Served by the tcgen05
+ * implicit-GEMM kernel (TF32 operands, fp32 accumulate) or the fp32 CUDA-core kernel, see
+ * sps_set_conv_backend. */
 int sps_conv_fwd(const sps_conv_args* args, void* stream);
 
 /* ---------------------------------------------------------------- network ---------------- */
@@ -187,11 +194,12 @@ int sps_infer_scan(sps_ctx* ctx, const sps_net* net, const sps_map* map, const f
  * the layer shape allows, fp32 CUDA-core otherwise), 1 = fp32 CUDA-core only, 2 = tcgen05 only
  * (SPS_ERR_UNSUPPORTED for shapes it does not take). */
 int sps_set_conv_backend(int backend);
-/* Known-answer hook for the tcgen05 tile pipeline: D[M,N] (fp32) = A[M,K] @ B[N,K]^T with bf16
- * operands staged exactly as the convolution stages them (K-major, 128-byte swizzle).
- * M % 128 == 0, N in {16,32,64}, K % 64 == 0. */
-int sps_umma_selftest(const void* d_a_bf16, const void* d_b_bf16, float* d_out, int M, int N, int K,
-                      void* stream);
+/* Host helper for the tensor-core path: ME-layout weights [K][cin][cout] (+ optional fused 1x1
+ * term w2 [cin2][cout]) -> K-major [cout][ld], ld = sps_conv_kmajor_ld(K,cin,cin2), values
+ * rounded to TF32 (nearest even).  `out` is a HOST buffer of cout*ld floats. */
+int64_t sps_conv_kmajor_ld(int K, int cin, int cin2);
+int sps_conv_pack_kmajor(const float* w, int K, int cin, int cout, const float* w2, int cin2,
+                         float* out);
 
 /* ---------------------------------------------------------------- measurement ------------ */
 /* Per-stage CUDA-event timing of sps_forward on its own stream (bench.py roofline figures).

@@ -1,0 +1,71 @@
+"""Python entry to the layer-level C-ABI call ``sps_conv_fwd`` (used by the ME-shaped layer
+shim and by the layer-wise parity tests).  All tensors are CUDA fp32/int32; nothing is computed
+in torch."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import check
+from .engine import _ptr, _stream
+
+
+def pack_kmajor(weight: torch.Tensor, weight2: torch.Tensor | None = None) -> torch.Tensor:
+    """ME-layout ``[K,Cin,Cout]`` (+ fused 1x1 ``[Cin2,Cout]``) -> K-major TF32 matrix for the
+    tcgen05 kernel (host-side packing in the library, result on the weights' device)."""
+    lib = _cabi.load()
+    w = np.ascontiguousarray(weight.detach().cpu().numpy(), np.float32)
+    K, cin, cout = w.shape
+    w2 = None if weight2 is None else np.ascontiguousarray(weight2.detach().cpu().numpy(), np.float32)
+    cin2 = 0 if w2 is None else w2.shape[0]
+    ld = lib.sps_conv_kmajor_ld(K, cin, cin2)
+    out = np.empty((cout, ld), np.float32)
+    check(lib.sps_conv_pack_kmajor(w.ctypes.data_as(C.c_void_p), K, cin, cout,
+                                   None if w2 is None else w2.ctypes.data_as(C.c_void_p), cin2,
+                                   out.ctypes.data_as(C.c_void_p)), "sps_conv_pack_kmajor")
+    return torch.as_tensor(out).to(weight.device)
+
+
+def conv_fwd(inp, weight, n_out, *, map=None, map_ld=0, mode=_cabi.SPS_CONV_NBR, shift=None, in2=None, weight2=None,
+             res=None, relu=False, out=None, head_w=None, head_b=0.0, head_out=None, weight_kmajor=None,
+             round_out=False, n_out_max=None, backend=None):
+    """out[o] = act(sum_k in[map[k][o]] @ W[k] (+ in2[o] @ W2) + shift (+ res[o])); ``n_out`` is a
+    1-element int32 CUDA tensor (device-side count).  ``inp``/``out``/``in2``/``res`` may be
+    channel slices (stride(0) is the leading dimension)."""
+    lib = _cabi.load()
+    K = weight.shape[0] if weight.dim() == 3 else 1
+    cin, cout = weight.shape[-2], weight.shape[-1]
+    if n_out_max is None:
+        n_out_max = int(n_out.item())
+    if out is None and head_out is None:
+        out = torch.empty((max(n_out_max, 1), cout), dtype=torch.float32, device=inp.device)
+    a = _cabi.ConvArgs()
+    a.mode, a.K, a.cin, a.cout = mode, K, cin, cout
+    a.map, a.map_ld = (map.data_ptr() if map is not None else None), int(map_ld)
+    a.n_out, a.n_out_max = n_out.data_ptr(), int(n_out_max)
+    a.in_, a.in_ld = inp.data_ptr(), inp.stride(0)
+    a.weight = weight.data_ptr()
+    a.shift = shift.data_ptr() if shift is not None else None
+    if in2 is not None:
+        a.in2, a.in2_ld, a.cin2, a.weight2 = in2.data_ptr(), in2.stride(0), weight2.shape[0], weight2.data_ptr()
+    if res is not None:
+        a.res, a.res_ld = res.data_ptr(), res.stride(0)
+    a.relu = int(relu)
+    if out is not None:
+        a.out, a.out_ld = out.data_ptr(), out.stride(0)
+    if head_out is not None:
+        a.head_w, a.head_b, a.head_out = head_w.data_ptr(), float(head_b), head_out.data_ptr()
+    if weight_kmajor is not None:
+        a.weight_kmajor, a.kmajor_ld = weight_kmajor.data_ptr(), weight_kmajor.stride(0)
+    a.round_out = int(round_out)
+    if backend is not None:
+        check(lib.sps_set_conv_backend(backend), "sps_set_conv_backend")
+    try:
+        check(lib.sps_conv_fwd(C.byref(a), _stream()), "sps_conv_fwd")
+    finally:
+        if backend is not None:
+            lib.sps_set_conv_backend(0)
+    return out if out is not None else head_out

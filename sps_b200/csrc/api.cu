@@ -59,6 +59,7 @@ int conv_simt(const sps_conv_args& a, cudaStream_t st);
 int conv_umma(const sps_conv_args& a, cudaStream_t st);
 bool conv_umma_supports(const sps_conv_args& a);
 static int g_backend = 0;  // 0 auto, 1 fp32 CUDA-core, 2 tcgen05
+int conv_backend() { return g_backend; }
 int conv_dispatch(const sps_conv_args& a, cudaStream_t st) {
   if (g_backend == 2) return conv_umma_supports(a) ? conv_umma(a, st) : SPS_ERR_UNSUPPORTED;
   if (g_backend == 0 && conv_umma_supports(a)) return conv_umma(a, st);

@@ -126,6 +126,14 @@ k_conv_simt(const sps_conv_args a, const int kc) {
 #pragma unroll
       for (int c = 0; c < 8; ++c) acc[c] = fmaxf(acc[c], 0.f);
     }
+    if (a.round_out) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint32_t r;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(acc[c]));
+        acc[c] = __uint_as_float(r);
+      }
+    }
     if (a.out) {
       float* o = a.out + (int64_t)v * a.out_ld + cg * 8;
       *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);

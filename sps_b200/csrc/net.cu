@@ -17,11 +17,14 @@
 namespace sps {
 int conv_simt(const sps_conv_args& a, cudaStream_t st);
 int conv_dispatch(const sps_conv_args& a, cudaStream_t st);
+int conv_backend();
 
 struct ConvW {
   float* w = nullptr;      // [K][cin][cout], BN scale folded
   float* shift = nullptr;  // [cout]
   float* w2 = nullptr;     // fused downsample [cin2][cout], BN scale folded (blocks only)
+  float* wt = nullptr;     // K-major TF32 copy for the tcgen05 kernel (81-offset convs)
+  int64_t ldk = 0;
   int K = 0, cin = 0, cout = 0, cin2 = 0;
 };
 
@@ -106,19 +109,30 @@ extern "C" int sps_net_set_tensor(sps_net* net, const char* name, const float* h
   net->finalized = false;
   return SPS_OK;
 }
-extern "C" size_t sps_net_device_bytes(void) { return 16u << 20; }  // 1.85 M parameters + padding
+extern "C" size_t sps_net_device_bytes(void) { return 32u << 20; }  // 1.85 M parameters, ME + K-major copies, padding
 
 extern "C" int sps_net_finalize(sps_net* net, void* d_weights, size_t bytes, void* stream) {
   if (!net || !d_weights) return SPS_ERR_BAD_ARG;
   Packer pk;
-  struct Pending { ConvW* cw; size_t w, shift, w2; bool has_w2; };
+  struct Pending { ConvW* cw; size_t w, shift, w2; bool has_w2; size_t wt = 0; bool has_wt = false; };
+  auto add_kmajor = [&](Pending& p, const std::vector<float>& w, int K, int cin, int cout,
+                        const std::vector<float>* w2, int cin2) {
+    const int64_t ldk = sps_conv_kmajor_ld(K, cin, cin2);
+    std::vector<float> wt((size_t)cout * ldk);
+    sps_conv_pack_kmajor(w.data(), K, cin, cout, w2 ? w2->data() : nullptr, cin2, wt.data());
+    p.cw->ldk = ldk;
+    p.wt = pk.add(wt);
+    p.has_wt = true;
+  };
   std::vector<Pending> pend;
   auto add_conv = [&](ConvW& cw, const std::string& kname, const std::string& bn, int K, int cin, int cout) {
     std::vector<float> w; std::vector<double> sh;
     if (!fold_conv(net, kname, bn, K, cin, cout, w, sh)) return false;
     std::vector<float> shf(sh.begin(), sh.end());
     cw.K = K; cw.cin = cin; cw.cout = cout; cw.cin2 = 0;
-    pend.push_back({&cw, pk.add(w), pk.add(shf), 0, false});
+    Pending p{&cw, pk.add(w), pk.add(shf), 0, false};
+    if (K == 81) add_kmajor(p, w, K, cin, cout, nullptr, 0);
+    pend.push_back(p);
     return true;
   };
   auto add_block = [&](int b, const std::string& name, int cin, int cout) {
@@ -136,6 +150,9 @@ extern "C" int sps_net_finalize(sps_net* net, void* d_weights, size_t bytes, voi
       cw.cin2 = cin;
       p.w2 = pk.add(w2);
       p.has_w2 = true;
+      add_kmajor(p, w, 81, cout, cout, &w2, cin);
+    } else {
+      add_kmajor(p, w, 81, cout, cout, nullptr, 0);
     }
     std::vector<float> shf(sh.begin(), sh.end());
     p.shift = pk.add(shf);
@@ -175,6 +192,7 @@ extern "C" int sps_net_finalize(sps_net* net, void* d_weights, size_t bytes, voi
     p.cw->w = base + p.w;
     p.cw->shift = base + p.shift;
     p.cw->w2 = p.has_w2 ? base + p.w2 : nullptr;
+    p.cw->wt = p.has_wt ? base + p.wt : nullptr;
   }
   net->head_w = base + head_off;
   net->finalized = true;
@@ -213,6 +231,8 @@ static int run_conv(const char* name, const ConvW& w, int mode, const int32_t* m
   if (in2) { a.in2 = in2; a.in2_ld = in2_ld; a.cin2 = w.cin2; a.weight2 = w.w2; }
   a.res = res; a.res_ld = res_ld; a.relu = 1; a.out = out; a.out_ld = out_ld;
   a.head_w = head_w; a.head_b = head_b; a.head_out = head_out;
+  a.weight_kmajor = w.wt; a.kmajor_ld = w.ldk;
+  a.round_out = conv_backend() != 1;   // pure fp32 mode keeps full-precision activations
   ++g_forward_launches;
   const int rc = conv_dispatch(a, st);
   prof_mark(name, st);
