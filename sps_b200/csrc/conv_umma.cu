@@ -2,33 +2,36 @@
 //
 //   out[o] = act( sum_k in[map[k][o]] @ W[k]  (+ in2[o] @ W2)  + shift (+ res[o]) )
 //
-// One CTA owns a tile of 128 output voxels = the 128 TMEM lanes of one fp32 accumulator
-// [128 x N] (N = Cout padded to 16).  The GEMM K dimension is the im2col row
+// One CTA (256 threads) owns a tile of 128 output voxels = the 128 TMEM lanes of one fp32
+// accumulator [128 x N] (N = Cout padded to 16).  The GEMM K dimension is the im2col row
 // (kernel offset k, input channel ci), walked in 16-byte groups (4 fp32 channels):
-//   * per tile, a prologue ballots which kernel offsets have at least one neighbour present in
-//     the tile and only those offsets are walked (sparsity skip at tile granularity);
-//   * 8 groups = one pipeline stage = 128 rows x 128 B, written by cp.async (zero-fill for
-//     absent neighbours) straight into the UMMA canonical K-major SWIZZLE_128B layout; the
-//     matching weight stage (N rows x 128 B of the K-major, TF32-rounded weight matrix) is
-//     fetched the same way from L2;
-//   * one elected thread issues 4 x tcgen05.mma.kind::tf32 (M=128, N, K=8) per stage into TMEM,
-//     tcgen05.commit releases the stage through an mbarrier; a 4-deep ring overlaps gather
-//     and MMA;
-//   * epilogue: tcgen05.ld the accumulator row of each voxel, add the folded BatchNorm shift,
-//     optional residual, ReLU, optional fused 8->1 head, store fp32 (optionally TF32-rounded so
-//     that the next layer's operand rounding is round-to-nearest, not truncation).
-// Operands are TF32 (fp32 storage), accumulation is fp32: the north star's 2e-3 score budget
-// leaves ~10x margin (DESIGN.md "precision"); bf16 storage would halve the gather bytes but
-// measured 6e-4..2e-2 score error on the same network.
+//   * prologue: the tile's slice of the kernel map is staged in shared memory with cp.async
+//     (all K loads in flight at once) and a warp ballot finds the offsets that have at least
+//     one neighbour inside the tile -- only those are walked (sparsity skip at tile level);
+//   * one pipeline stage = 128 rows x 128 B of gathered A (8 groups) written by cp.async
+//     (zero-fill for absent neighbours) straight into the UMMA canonical K-major SWIZZLE_128B
+//     layout, plus the matching N rows x 128 B of the K-major, TF32-rounded weight matrix.
+//     Channel counts are padded per kernel offset so that a stage never straddles offsets in
+//     an irregular way: Cin <= 16 packs 8/(Cin/4) offsets per stage, Cin >= 24 uses
+//     ceil(Cin/32) stages per offset;
+//   * one elected thread issues 4 x tcgen05.mma.kind::tf32 (M=128, N, K=8) per stage into
+//     TMEM; tcgen05.commit releases the stage through an mbarrier; a 3-deep ring keeps two
+//     stages of gathers in flight behind the MMAs, two CTAs per SM overlap prologue/epilogue;
+//   * epilogue: all 8 warps tcgen05.ld half an accumulator row each, add the folded BatchNorm
+//     shift, optional residual, ReLU, optional fused 8->1 head, store fp32 (optionally
+//     TF32-rounded so the next layer's operand rounding is nearest, not truncation).
+// Operands are TF32 (fp32 storage), accumulation fp32: ~1e-4 score error on the reference
+// network against the 2e-3 budget; bf16 operands measured 6e-4..2e-2 (DESIGN.md "precision").
 #include <cstring>
 #include "common.cuh"
 
 namespace sps {
 
 constexpr int kTileM = 128;
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr int kAStageBytes = kTileM * 128;  // 16 KB
-constexpr int kUmmaThreads = 128;
+constexpr int kUmmaThreads = 256;
+constexpr int kMaxK = 81;  // kernel volumes this kernel takes (neighbour indices are staged in smem)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -61,11 +64,11 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // apart (SBO); LBO unused for swizzled K-major; version 1; layout type 2.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);         // start address   bits [0,14)
-  d |= (uint64_t)1 << 16;                          // LBO (ignored)   bits [16,30)
-  d |= (uint64_t)(1024 >> 4) << 32;                // SBO = 1024 B    bits [32,46)
-  d |= (uint64_t)1 << 46;                          // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);  // start address   bits [0,14)
+  d |= (uint64_t)1 << 16;                   // LBO (ignored)   bits [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;         // SBO = 1024 B    bits [32,46)
+  d |= (uint64_t)1 << 46;                   // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                   // SWIZZLE_128B
   return d;
 }
 // kind::tf32, fp32 accumulate, both operands K-major: c_format F32 (1<<4), a/b format TF32 (2),
@@ -100,33 +103,44 @@ __device__ __forceinline__ float round_tf32(float x) {
   return __uint_as_float(r);
 }
 
+// groups (of 4 channels) reserved per kernel offset in the K-major weight matrix / the stage plan
+__host__ __device__ inline int padded_groups(int cin) {
+  const int g = (cin + 3) >> 2;
+  return g <= 2 ? 2 : g <= 4 ? 4 : (g + 7) & ~7;
+}
+
 struct UmmaParams {
-  const float* wt;   // [cout][ldk] K-major, TF32-rounded; K index = k*cin + ci, then cin2 entries of the 1x1 term
+  const float* wt;  // [cout][ldk] K-major, TF32-rounded (layout: sps_conv_pack_kmajor)
   int64_t ldk;
   int round_out;
 };
 
-template <int NPAD>
+// GPC = padded groups per offset class: 2 or 4 (several offsets per stage) or 8 (= "8 or more":
+// one offset spans GP/8 stages)
+template <int NPAD, int GPC>
 __global__ void __launch_bounds__(kUmmaThreads, 2) k_conv_umma(const sps_conv_args a, const UmmaParams p) {
   constexpr int kBStageBytes = NPAD * 128;
   constexpr int kTmemCols = NPAD < 32 ? 32 : NPAD;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // 1024-byte alignment is required by the 128B swizzle atoms
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + kStages * kAStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kStages * kBStageBytes);  // [kStages] empty + [1] accum
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kStages + 1);
-  uint32_t* kmask = tmem_slot + 1;                        // [4] bitmask of active offsets
-  uint8_t* klist = reinterpret_cast<uint8_t*>(kmask + 4);  // [128] active offsets in order
+  constexpr int S = kStages;
+  constexpr int HC = NPAD / 2;  // accumulator columns per epilogue thread
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;                                                   // [S][128 rows x 128 B], 128B-swizzled
+  uint8_t* sB = smem + S * kAStageBytes;                                // [S][NPAD rows x 128 B]
+  int32_t* sidx = reinterpret_cast<int32_t*>(sB + S * kBStageBytes);    // [K][128] neighbour rows of this tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sidx + kMaxK * kTileM);  // [S] empty + [1] accum
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + S + 1);
+  uint32_t* kmask = tmem_slot + 1;                         // [4] bitmask of offsets present in the tile
+  uint8_t* klist = reinterpret_cast<uint8_t*>(kmask + 4);  // [128] present offsets, ascending
   int* nact_s = reinterpret_cast<int*>(klist + 128);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
-  const uint32_t bar_empty = smem_u32(bars), bar_accum = smem_u32(bars + kStages);
+  const int r = tid & 127, half = tid >> 7;  // A gather: row r, chunks 4*half .. 4*half+3
+  const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB), sidx_u = smem_u32(sidx);
+  const uint32_t bar_empty = smem_u32(bars), bar_accum = smem_u32(bars + S);
+  if (sA_u & 1023) __trap();  // SWIZZLE_128B atoms need 1024-byte aligned stage bases
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) mbar_init(bar_empty + 8 * s, 1);
+    for (int s = 0; s < S; ++s) mbar_init(bar_empty + 8 * s, 1);
     mbar_init(bar_accum, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -144,150 +158,197 @@ __global__ void __launch_bounds__(kUmmaThreads, 2) k_conv_umma(const sps_conv_ar
 
   const int n_out = *a.n_out;
   const int ntiles = (n_out + kTileM - 1) / kTileM;
-  const int K = a.K, gpk = a.cin >> 2, gpk2 = a.in2 ? (a.cin2 >> 2) : 0;
+  const int K = a.K;
+  const int gpk = a.cin >> 2;                      // real groups per offset
+  const int GP = GPC < 8 ? GPC : padded_groups(a.cin);  // padded groups per offset
+  const int SPE = GPC < 8 ? 1 : GP >> 3;           // stages per offset (large Cin)
+  constexpr int EPS = GPC < 8 ? 8 / GPC : 1;       // offsets per stage (small Cin)
+  const int gpk2 = a.in2 ? (a.cin2 >> 2) : 0;
+  const int st2 = (gpk2 + 7) >> 3;                 // stages of the fused 1x1 term
+  const uint32_t in_ld_b = (uint32_t)a.in_ld * 4u, in2_ld_b = (uint32_t)a.in2_ld * 4u;
   const uint32_t idesc = make_idesc_tf32(NPAD);
-  const uint32_t swz = (uint32_t)(tid & 7);
-  const uint32_t a_row_off = (uint32_t)((tid >> 3) * 1024 + (tid & 7) * 128);
+  // A destination of this thread inside a stage: row r, chunks c = 4*half + j, 128B swizzle
+  const uint32_t a_row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+  const uint32_t swz = (uint32_t)(r & 7);
+  // B chunk(s) of this thread: column cB = tid & 7, rows nB = tid/8 + 32*i
+  const int cB = tid & 7;
+  const char* in_b = reinterpret_cast<const char*>(a.in);
+  const char* in2_b = reinterpret_cast<const char*>(a.in2);
 
-  uint32_t gstage = 0;  // stages issued so far by this CTA (ring position + mbarrier phases)
+  uint32_t gstage = 0;  // stages issued so far by this CTA (ring slot + mbarrier phase bookkeeping)
   uint32_t accum_uses = 0;
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int row = tile * kTileM + tid;
+    const int row = tile * kTileM + r;
     const bool row_ok = row < n_out;
 
-    // ---- prologue: which kernel offsets are present anywhere in this tile? ----
+    // ---- prologue: stage the tile's kernel-map slice, find the offsets present in the tile ----
     if (tid < 4) kmask[tid] = 0;
+    if (row_ok) {
+      const int32_t* src = a.map + row;
+      for (int k = half; k < K; k += 2)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sidx_u + (uint32_t)(k * kTileM + r) * 4),
+                     "l"(src + (int64_t)k * a.map_ld)
+                     : "memory");
+    } else {
+      for (int k = half; k < K; k += 2) sidx[k * kTileM + r] = -1;  // rows past the end have no neighbours
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
-    for (int k = 0; k < K; ++k) {
-      const int idx = row_ok ? __ldg(a.map + (int64_t)k * a.map_ld + row) : -1;
-      const bool any = __any_sync(0xffffffffu, idx >= 0);
-      if (lane == 0 && any) atomicOr(&kmask[k >> 5], 1u << (k & 31));
+    for (int k = warp; k < K; k += 8) {  // warp w scans offsets w, w+8, ...; each lane looks at 4 rows
+      const int32_t* q = sidx + k * kTileM + lane;
+      const bool any = (q[0] >= 0) | (q[32] >= 0) | (q[64] >= 0) | (q[96] >= 0);
+      if (__any_sync(0xffffffffu, any) && lane == 0) atomicOr(&kmask[k >> 5], 1u << (k & 31));
     }
     __syncthreads();
-    if (tid == 0) {
-      int n = 0;
-      for (int k = 0; k < K; ++k)
-        if (kmask[k >> 5] & (1u << (k & 31))) klist[n++] = (uint8_t)k;
-      *nact_s = n;
+    if (warp == 0) {  // ordered compaction of the present offsets
+      int base = 0;
+      for (int w = 0; w < 3; ++w) {
+        const uint32_t bits = kmask[w];
+        if ((bits >> lane) & 1u) klist[base + __popc(bits & ((1u << lane) - 1u))] = (uint8_t)(32 * w + lane);
+        base += __popc(bits);
+      }
+      if (lane == 0) *nact_s = base;
     }
     __syncthreads();
     const int nact = *nact_s;
-    const int G = nact * gpk + gpk2;          // 16-byte groups along the im2col K dimension
-    const int nstages = (G + 7) >> 3;
+    const int nst_map = GPC < 8 ? (nact + EPS - 1) / EPS : nact * SPE;
+    const int nstages = nst_map + st2;
 
-    // ---- main loop: gather (cp.async) -> MMA (tcgen05) through a kStages-deep ring ----
-    for (int st = 0; st < nstages + kStages - 1; ++st) {
-      if (st < nstages) {
-        const uint32_t gs = gstage + st;
-        const uint32_t slot = gs % kStages, use = gs / kStages;
-        if (use > 0) mbar_wait(bar_empty + 8 * slot, (use - 1) & 1);  // MMAs that read this slot are done
-        const uint32_t a_dst = sA_u + slot * kAStageBytes + a_row_off;
-        int cur_e = -1, idx = -1;
+    auto issue_stage = [&](int st) {
+      const uint32_t gs = gstage + (uint32_t)st;
+      const uint32_t slot = gs % S, use = gs / S;
+      if (use > 0) mbar_wait(bar_empty + 8 * slot, (use - 1) & 1);  // the MMAs that read this slot are done
+      const uint32_t a_dst = sA_u + slot * kAStageBytes + a_row_off;
+      const uint32_t b_dst = sB_u + slot * kBStageBytes;
+      int64_t kofB = -1;  // float offset of this thread's weight chunk inside a K-major row
+      if (st < nst_map) {
+        if (GPC < 8) {
+          // small Cin: EPS offsets per stage, GPC chunks each; this thread covers chunks 4*half..+3
+          constexpr int EPT = GPC == 2 ? 2 : 1;  // offsets touched by one thread
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const int gi = st * 8 + c;
-          const float* src = a.in;
-          uint32_t bytes = 0;
-          if (gi < nact * gpk) {
-            const int e = gi / gpk, cg = gi - e * gpk;
-            if (e != cur_e) {
-              cur_e = e;
-              idx = row_ok ? __ldg(a.map + (int64_t)klist[e] * a.map_ld + row) : -1;
+          for (int j = 0; j < EPT; ++j) {
+            const int e = st * EPS + (GPC == 2 ? 2 * half + j : half);
+            const int idx = e < nact ? sidx[klist[e] * kTileM + r] : -1;
+            const char* src = in_b + (idx >= 0 ? (uint32_t)idx * in_ld_b : 0u);
+            const uint32_t bytes = idx >= 0 ? 16u : 0u;
+#pragma unroll
+            for (int g = 0; g < (GPC == 2 ? 2 : 4); ++g) {
+              const int c = 4 * half + (GPC == 2 ? 2 * j : 0) + g;
+              const bool real = g < gpk;  // Cin = 4 uses only the first group of its pair
+              cp_async16(a_dst + (((uint32_t)c ^ swz) << 4), src + g * 16, real ? bytes : 0u);
             }
-            if (idx >= 0) { src = a.in + (int64_t)idx * a.in_ld + cg * 4; bytes = 16; }
-          } else if (gi < G && row_ok) {
-            src = a.in2 + (int64_t)row * a.in2_ld + (gi - nact * gpk) * 4;
-            bytes = 16;
           }
-          cp_async16(a_dst + (((uint32_t)c ^ swz) << 4), src, bytes);
-        }
-        // weights: chunk column c = tid & 7 of rows n = tid/8 + 16*i
-        {
-          const int c = tid & 7;
-          const int gi = st * 8 + c;
-          int64_t koff = -1;
-          if (gi < nact * gpk) {
-            const int e = gi / gpk, cg = gi - e * gpk;
-            koff = ((int64_t)klist[e] * gpk + cg) * 4;
-          } else if (gi < G) {
-            koff = ((int64_t)K * gpk + (gi - nact * gpk)) * 4;
-          }
-          const uint32_t b_dst = sB_u + slot * kBStageBytes;
+          const int eB = st * EPS + cB / GPC;
+          if (eB < nact) kofB = ((int64_t)klist[eB] * GPC + (cB % GPC)) * 4;
+        } else {
+          // large Cin: one offset per SPE stages, 8 consecutive chunks of the same neighbour row
+          const int e = st / SPE, sub = st - e * SPE;
+          const int k = klist[e];
+          const int idx = sidx[k * kTileM + r];
+          const int cg0 = sub * 8 + 4 * half;
+          const char* src = in_b + (idx >= 0 ? (uint32_t)idx * in_ld_b : 0u) + cg0 * 16;
 #pragma unroll
-          for (int i = 0; i < NPAD / 16; ++i) {
-            const int n = (tid >> 3) + 16 * i;
-            const bool ok = koff >= 0 && n < a.cout;
-            const float* src = ok ? p.wt + (int64_t)n * p.ldk + koff : p.wt;
-            cp_async16(b_dst + (uint32_t)((n >> 3) * 1024 + (n & 7) * 128) + (((uint32_t)c ^ (uint32_t)(n & 7)) << 4), src,
-                       ok ? 16u : 0u);
+          for (int g = 0; g < 4; ++g) {
+            const bool ok = idx >= 0 && cg0 + g < gpk;
+            cp_async16(a_dst + (((uint32_t)(4 * half + g) ^ swz) << 4), ok ? src + g * 16 : in_b, ok ? 16u : 0u);
           }
+          kofB = ((int64_t)k * GP + sub * 8 + cB) * 4;
+        }
+      } else {
+        // fused 1x1 term: identity gather from in2
+        const int s2 = st - nst_map;
+        const int cg0 = s2 * 8 + 4 * half;
+        const char* src = in2_b + (row_ok ? (uint32_t)row * in2_ld_b : 0u) + cg0 * 16;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const bool ok = row_ok && cg0 + g < gpk2;
+          cp_async16(a_dst + (((uint32_t)(4 * half + g) ^ swz) << 4), ok ? src + g * 16 : in_b, ok ? 16u : 0u);
+        }
+        if (s2 * 8 + cB < gpk2) kofB = ((int64_t)K * GP + s2 * 8 + cB) * 4;
+      }
+#pragma unroll
+      for (int i = 0; i < (NPAD * 8 + kUmmaThreads - 1) / kUmmaThreads; ++i) {
+        const int n = (tid >> 3) + 32 * i;
+        if (NPAD * 8 >= kUmmaThreads || n < NPAD) {
+          const bool ok = kofB >= 0 && n < a.cout;
+          const float* src = ok ? p.wt + (int64_t)n * p.ldk + kofB : p.wt;
+          cp_async16(b_dst + (uint32_t)((n >> 3) * 1024 + (n & 7) * 128) + (((uint32_t)cB ^ (uint32_t)(n & 7)) << 4), src,
+                     ok ? 16u : 0u);
         }
       }
-      cp_async_commit();
-      const int cs = st - (kStages - 1);
-      if (cs >= 0) {
-        cp_async_wait<kStages - 1>();
-        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        __syncthreads();
-        if (tid == 0) {
-          tc_fence_after();
-          const uint32_t slot = (gstage + cs) % kStages;
-          const uint64_t adesc = make_smem_desc(sA_u + slot * kAStageBytes);
-          const uint64_t bdesc = make_smem_desc(sB_u + slot * kBStageBytes);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)  // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle atom
-            umma_tf32(tmem_base, adesc + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (cs | j) ? 1u : 0u);
-          umma_commit(bar_empty + 8 * slot);
-          if (cs == nstages - 1) umma_commit(bar_accum);
-        }
-      }
-    }
-    gstage += nstages;
+    };
 
-    // ---- epilogue ----
-    float acc[NPAD];
+    // ---- main loop: S-deep ring, the gather (cp.async) runs S-1 stages ahead of the MMAs ----
+    for (int st = 0; st < S - 1; ++st) {
+      if (st < nstages) issue_stage(st);
+      cp_async_commit();
+    }
+    for (int it = 0; it < nstages; ++it) {
+      cp_async_wait<S - 2>();  // this thread's part of stage `it` has landed
+      fence_proxy_async();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      __syncthreads();         // ... and everybody else's
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t slot = (gstage + (uint32_t)it) % S;
+        const uint64_t adesc = make_smem_desc(sA_u + slot * kAStageBytes);
+        const uint64_t bdesc = make_smem_desc(sB_u + slot * kBStageBytes);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)  // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle atom
+          umma_tf32(tmem_base, adesc + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (it | j) ? 1u : 0u);
+        umma_commit(bar_empty + 8 * slot);
+        if (it == nstages - 1) umma_commit(bar_accum);
+      }
+      const int nx = it + S - 1;
+      if (nx < nstages) issue_stage(nx);
+      cp_async_commit();
+    }
+    cp_async_wait<0>();
+    gstage += (uint32_t)nstages;
+
+    // ---- epilogue: warp w reads TMEM lanes 32*(w&3).., columns [HC*(w>>2), +HC) ----
+    float acc[HC];
+    const int c0 = HC * half;
     if (nstages > 0) {
       mbar_wait(bar_accum, accum_uses & 1);
       ++accum_uses;
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0;
 #pragma unroll
-      for (int cb = 0; cb < NPAD / 8; ++cb) tmem_ld8(taddr + cb * 8, acc + cb * 8);
+      for (int cb = 0; cb < HC / 8; ++cb) tmem_ld8(taddr + cb * 8, acc + cb * 8);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     } else {
 #pragma unroll
-      for (int c = 0; c < NPAD; ++c) acc[c] = 0.f;
+      for (int c = 0; c < HC; ++c) acc[c] = 0.f;
     }
-    if (row_ok) {
-      const int cout = a.cout;
+    if (row_ok && c0 < a.cout) {
 #pragma unroll
-      for (int c = 0; c < NPAD; ++c)
-        if (c < cout) {
-          float v = acc[c];
-          if (a.shift) v += __ldg(a.shift + c);
-          if (a.res) v += __ldg(a.res + (int64_t)row * a.res_ld + c);
-          if (a.relu) v = fmaxf(v, 0.f);
-          acc[c] = v;
-        }
-      if (a.head_out) {
+      for (int c = 0; c < HC; ++c) {
+        float v = acc[c];
+        if (a.shift) v += __ldg(a.shift + c0 + c);
+        if (a.res) v += __ldg(a.res + (int64_t)row * a.res_ld + c0 + c);
+        if (a.relu) v = fmaxf(v, 0.f);
+        acc[c] = v;
+      }
+      if (a.head_out) {  // cout == 8: all eight channels sit in the half == 0 thread
         float s = a.head_b;
 #pragma unroll
         for (int c = 0; c < 8; ++c) s = fmaf(acc[c], __ldg(a.head_w + c), s);
         a.head_out[row] = s;
       }
       if (a.out) {
-        float* o = a.out + (int64_t)row * a.out_ld;
+        float* o = a.out + (int64_t)row * a.out_ld + c0;
 #pragma unroll
-        for (int c = 0; c < NPAD; c += 4)
-          if (c < cout) {
-            float4 v = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
-            if (p.round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
-            *reinterpret_cast<float4*>(o + c) = v;
-          }
+        for (int c = 0; c < HC; c += 4) {
+          float4 v = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+          if (p.round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+          *reinterpret_cast<float4*>(o + c) = v;
+        }
       }
     }
-    // the next tile's first MMA overwrites the accumulator: order it after these TMEM reads
+    // the next tile's first MMA overwrites the accumulator and its prologue overwrites sidx:
+    // order both after this tile's TMEM reads / smem reads
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -299,30 +360,40 @@ __global__ void __launch_bounds__(kUmmaThreads, 2) k_conv_umma(const sps_conv_ar
                  : "memory");
 }
 
-template <int NPAD>
+template <int NPAD, int GPC>
 static int launch_umma(const sps_conv_args& a, const UmmaParams& p, cudaStream_t st) {
-  const size_t smem = 1024 + kStages * (kAStageBytes + NPAD * 128) + 8 * (kStages + 1) + 4 + 16 + 128 + 16;
+  const size_t smem = kStages * (kAStageBytes + NPAD * 128) + (size_t)kMaxK * kTileM * 4 + 8 * (kStages + 1) + 4 + 16 +
+                      128 + 16;
   static bool attr_set = false;
   if (!attr_set) {
-    SPS_CUDA_CHECK(cudaFuncSetAttribute(k_conv_umma<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SPS_CUDA_CHECK(
+        cudaFuncSetAttribute(k_conv_umma<NPAD, GPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   int64_t tiles = (a.n_out_max + kTileM - 1) / kTileM;
   if (tiles < 1) tiles = 1;
   const int grid = (int)(tiles < 148 * 2 ? tiles : 148 * 2);
-  k_conv_umma<NPAD><<<grid, kUmmaThreads, smem, st>>>(a, p);
+  k_conv_umma<NPAD, GPC><<<grid, kUmmaThreads, smem, st>>>(a, p);
   SPS_CUDA_CHECK(cudaGetLastError());
   return SPS_OK;
 }
 
 bool conv_umma_supports(const sps_conv_args& a) {
   if (a.mode != SPS_CONV_NBR || !a.map || !a.weight_kmajor) return false;
-  if (a.K < 1 || a.K > 125) return false;
+  if (a.K < 1 || a.K > kMaxK) return false;
   if (a.cin < 4 || (a.cin & 3) || (a.in_ld & 3)) return false;
   if (a.in2 && ((a.cin2 & 3) || (a.in2_ld & 3))) return false;
   if (!(a.cout == 8 || a.cout == 16 || a.cout == 32 || a.cout == 64)) return false;
   if (a.kmajor_ld & 3) return false;
   return true;
+}
+
+template <int NPAD>
+static int launch_umma_n(const sps_conv_args& a, const UmmaParams& p, cudaStream_t st) {
+  const int gp = padded_groups(a.cin);
+  if (gp == 2) return launch_umma<NPAD, 2>(a, p, st);
+  if (gp == 4) return launch_umma<NPAD, 4>(a, p, st);
+  return launch_umma<NPAD, 8>(a, p, st);
 }
 
 int conv_umma(const sps_conv_args& a, cudaStream_t st) {
@@ -332,9 +403,9 @@ int conv_umma(const sps_conv_args& a, cudaStream_t st) {
   p.round_out = a.round_out;
   switch (a.cout) {
     case 8:
-    case 16: return launch_umma<16>(a, p, st);
-    case 32: return launch_umma<32>(a, p, st);
-    case 64: return launch_umma<64>(a, p, st);
+    case 16: return launch_umma_n<16>(a, p, st);
+    case 32: return launch_umma_n<32>(a, p, st);
+    case 64: return launch_umma_n<64>(a, p, st);
     default: return SPS_ERR_UNSUPPORTED;
   }
 }
@@ -342,12 +413,17 @@ int conv_umma(const sps_conv_args& a, cudaStream_t st) {
 }  // namespace sps
 
 // Host helper: ME-layout weights [K][cin][cout] (+ optional 1x1 term [cin2][cout]) -> K-major
-// [cout][ldk] with ldk = K*cin + cin2 rounded up to 4, values rounded to TF32 (nearest-even).
-extern "C" int64_t sps_conv_kmajor_ld(int K, int cin, int cin2) { return ((int64_t)K * cin + cin2 + 3) & ~int64_t(3); }
+// [cout][ld]: row n holds, for every kernel offset k, padded_groups(cin)*4 floats (channels of
+// W[k][:, n], zero padded), then the 1x1 term padded to a multiple of 32; values rounded to
+// TF32 (nearest even).
+extern "C" int64_t sps_conv_kmajor_ld(int K, int cin, int cin2) {
+  return (int64_t)K * sps::padded_groups(cin) * 4 + ((cin2 + 31) & ~31);
+}
 
 extern "C" int sps_conv_pack_kmajor(const float* w, int K, int cin, int cout, const float* w2, int cin2, float* out) {
   if (!w || !out || K < 1 || cin < 1 || cout < 1 || (w2 == nullptr) != (cin2 == 0)) return SPS_ERR_BAD_ARG;
   const int64_t ldk = sps_conv_kmajor_ld(K, cin, cin2);
+  const int cpad = sps::padded_groups(cin) * 4;
   auto rnd = [](float x) {
     uint32_t u;
     memcpy(&u, &x, 4);
@@ -361,8 +437,8 @@ extern "C" int sps_conv_pack_kmajor(const float* w, int K, int cin, int cout, co
     float* row = out + (int64_t)n * ldk;
     for (int64_t i = 0; i < ldk; ++i) row[i] = 0.f;
     for (int k = 0; k < K; ++k)
-      for (int ci = 0; ci < cin; ++ci) row[(int64_t)k * cin + ci] = rnd(w[((int64_t)k * cin + ci) * cout + n]);
-    for (int ci = 0; ci < cin2; ++ci) row[(int64_t)K * cin + ci] = rnd(w2[(int64_t)ci * cout + n]);
+      for (int ci = 0; ci < cin; ++ci) row[(int64_t)k * cpad + ci] = rnd(w[((int64_t)k * cin + ci) * cout + n]);
+    for (int ci = 0; ci < cin2; ++ci) row[(int64_t)K * cpad + ci] = rnd(w2[(int64_t)ci * cout + n]);
   }
   return SPS_OK;
 }
