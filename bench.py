@@ -110,6 +110,7 @@ def stage_accounting(engine, n_points):
     P5 = pairs(0, 5)
     acc = {}
     acc["voxelize"] = {"bytes": n_points * 20 + n_points * 4 + V[0] * 20}
+    acc["blocks.L0"] = {"bytes": V[0] * 8 + V[0] * 4}
     acc["kmap5.L0"] = {"bytes": V[0] * 20 + 125 * V[0] * 4}
     for L in range(5):
         acc[f"kmap3.L{L}"] = {"bytes": V[L] * 20 + 81 * V[L] * 4}

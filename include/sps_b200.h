@@ -85,14 +85,15 @@ int sps_unpack_coords(sps_ctx* ctx, int level, int32_t* d_out, void* stream);
 
 /* ---------------------------------------------------------------- convolution ------------ */
 #define SPS_CONV_NBR 0    /* stride-1 (or child-table stride-2) conv through a [K][ld] map   */
-#define SPS_CONV_UP 1     /* transposed 2x2x2x1: out[f] = in[parent(f)] @ W[k(f)]           */
+#define SPS_CONV_UP 1     /* transposed 2x2x2x1: out[child[k][c]] = in[c] @ W[k] for coarse rows c */
 
 typedef struct sps_conv_args {
   int mode;                 /* SPS_CONV_NBR | SPS_CONV_UP                                    */
   int K;                    /* kernel volume (125, 81, 8, 1)                                 */
   int cin, cout;
   const int32_t* map;       /* NBR: [K][map_ld] input rows (-1 = absent); K==1 && map==NULL
-                               means identity (1x1 conv).  UP: parent*8+k per output row     */
+                               means identity (1x1 conv).  UP: [8][map_ld] child table of the
+                               coarse (input) level; n_out then counts the COARSE rows        */
   int64_t map_ld;
   const int32_t* n_out;     /* device scalar: number of output rows                          */
   int64_t n_out_max;        /* host upper bound used to size the launch                      */

@@ -36,6 +36,8 @@ static size_t carve(sps_ctx* c, void* base, int64_t max_points) {
   c->status = c->counts + 8;
   c->ticket = reinterpret_cast<uint32_t*>(c->counts + 9);
   c->n_dev = c->counts + 10;
+  c->nblocks = c->counts + 11;
+  c->cells = cv.take<int32_t>((size_t)N * 64);
   c->staging = cv.take<float>((size_t)N * 8);
   c->scores = cv.take<float>(N);
   c->table_cap = table_capacity(N);

@@ -47,13 +47,7 @@ k_conv_simt(const sps_conv_args a, const int kc) {
       if (!active) continue;
       for (int kk = 0; kk < kn; ++kk) {
         const int k = kbase + kk;
-        int idx;
-        if (a.mode == SPS_CONV_UP) {
-          const int pk = __ldg(a.map + v);
-          idx = ((pk & 7) == k) ? (pk >> 3) : -1;
-        } else {
-          idx = a.map ? __ldg(a.map + (int64_t)k * a.map_ld + v) : v;
-        }
+        const int idx = a.map ? __ldg(a.map + (int64_t)k * a.map_ld + v) : v;
         if (idx < 0) continue;
         const float* row = a.in + (int64_t)idx * a.in_ld;
         const float* wk = w_s + kk * slab + cg * 8;
@@ -171,9 +165,110 @@ static int launch_simt(const sps_conv_args& a, cudaStream_t st) {
   return SPS_OK;
 }
 
+// Transposed 2x2x2x1 convolution onto the existing finer map (minkunet.py:107-113): every coarse
+// row c scatters in[c] @ W[k] (+shift, ReLU) to its child child[k][c].  Each fine row has exactly
+// one parent, so every output row is written once -- no accumulation, no atomics.
+template <int COUT>
+__global__ void __launch_bounds__(kSimtThreads)
+k_conv_up(const sps_conv_args a, const int kc) {
+  constexpr int TPV = COUT / 8;
+  constexpr int VB = kSimtThreads / TPV;
+  extern __shared__ __align__(16) float w_s[];  // [kc][cin][COUT]
+  const int tid = threadIdx.x;
+  const int cg = tid / VB, vl = tid % VB;
+  const int n_in = *a.n_out;   // UP mode: rows iterated = coarse rows
+  const int cin = a.cin;
+  const int slab = cin * COUT;
+  const int ntiles = (n_in + VB - 1) / VB;
+  const bool resident = kc >= 8;
+  bool loaded = false;
+  float sh[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) sh[c] = a.shift ? __ldg(a.shift + cg * 8 + c) : 0.f;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int v = tile * VB + vl;
+    const bool active = v < n_in;
+    const float* row = a.in + (int64_t)(active ? v : 0) * a.in_ld;
+    for (int kbase = 0; kbase < 8; kbase += kc) {
+      const int kn = min(kc, 8 - kbase);
+      if (!(resident && loaded)) {
+        __syncthreads();
+        const float4* src = reinterpret_cast<const float4*>(a.weight + (int64_t)kbase * slab);
+        float4* dst = reinterpret_cast<float4*>(w_s);
+        for (int i = tid; i < kn * slab / 4; i += kSimtThreads) dst[i] = __ldg(src + i);
+        __syncthreads();
+        loaded = true;
+      }
+      if (!active) continue;
+      for (int kk = 0; kk < kn; ++kk) {
+        const int f = __ldg(a.map + (int64_t)(kbase + kk) * a.map_ld + v);
+        if (f < 0) continue;
+        float acc[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = sh[c];
+        const float* wk = w_s + kk * slab + cg * 8;
+        for (int ci = 0; ci < cin; ci += 4) {
+          const float4 x4 = __ldg(reinterpret_cast<const float4*>(row + ci));
+          const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 w0 = *reinterpret_cast<const float4*>(wk + (ci + j) * COUT);
+            const float4 w1 = *reinterpret_cast<const float4*>(wk + (ci + j) * COUT + 4);
+            acc[0] = fmaf(xs[j], w0.x, acc[0]); acc[1] = fmaf(xs[j], w0.y, acc[1]);
+            acc[2] = fmaf(xs[j], w0.z, acc[2]); acc[3] = fmaf(xs[j], w0.w, acc[3]);
+            acc[4] = fmaf(xs[j], w1.x, acc[4]); acc[5] = fmaf(xs[j], w1.y, acc[5]);
+            acc[6] = fmaf(xs[j], w1.z, acc[6]); acc[7] = fmaf(xs[j], w1.w, acc[7]);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          if (a.relu) acc[c] = fmaxf(acc[c], 0.f);
+          if (a.round_out) {
+            uint32_t r;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(acc[c]));
+            acc[c] = __uint_as_float(r);
+          }
+        }
+        float* o = a.out + (int64_t)f * a.out_ld + cg * 8;
+        *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      }
+    }
+  }
+}
+
+template <int COUT>
+static int launch_up(const sps_conv_args& a, cudaStream_t st) {
+  constexpr int VB = kSimtThreads / (COUT / 8);
+  const int slab = a.cin * COUT * 4;
+  int kc = kSimtSmemBytes / slab;
+  if (kc > 8) kc = 8;
+  if (kc < 1) return SPS_ERR_UNSUPPORTED;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SPS_CUDA_CHECK(cudaFuncSetAttribute(k_conv_up<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSimtSmemBytes));
+    attr_set = true;
+  }
+  int64_t tiles = (a.n_out_max + VB - 1) / VB;
+  if (tiles < 1) tiles = 1;
+  const int grid = (int)(tiles < 148 * 8 ? tiles : 148 * 8);
+  k_conv_up<COUT><<<grid, kSimtThreads, (size_t)kc * slab, st>>>(a, kc);
+  SPS_CUDA_CHECK(cudaGetLastError());
+  return SPS_OK;
+}
+
 int conv_dispatch(const sps_conv_args& a, cudaStream_t st);
 
 int conv_simt(const sps_conv_args& a, cudaStream_t st) {
+  if (a.mode == SPS_CONV_UP) {
+    switch (a.cout) {
+      case 8: return launch_up<8>(a, st);
+      case 16: return launch_up<16>(a, st);
+      case 32: return launch_up<32>(a, st);
+      case 64: return launch_up<64>(a, st);
+      default: return SPS_ERR_UNSUPPORTED;
+    }
+  }
   switch (a.cout) {
     case 8: return launch_simt<8>(a, st);
     case 16: return launch_simt<16>(a, st);
@@ -188,7 +283,8 @@ int conv_simt(const sps_conv_args& a, cudaStream_t st) {
 extern "C" int sps_conv_fwd(const sps_conv_args* a, void* stream) {
   if (!a || !a->in || !a->weight || !a->n_out || (!a->out && !a->head_out)) return SPS_ERR_BAD_ARG;
   if (a->mode != SPS_CONV_NBR && a->mode != SPS_CONV_UP) return SPS_ERR_BAD_ARG;
-  if (a->mode == SPS_CONV_UP && (!a->map || a->K != 8)) return SPS_ERR_BAD_ARG;
+  if (a->mode == SPS_CONV_UP && (!a->map || a->K != 8 || !a->out || a->in2 || a->res || a->head_out || (a->cin & 3)))
+    return SPS_ERR_BAD_ARG;
   if (a->mode == SPS_CONV_NBR && !a->map && a->K != 1) return SPS_ERR_BAD_ARG;
   if (a->cin < 1 || (a->cin != 1 && a->cin % 4) || (a->in_ld % 4 && a->cin != 1)) return SPS_ERR_BAD_ARG;
   if (a->in2 && (!a->weight2 || a->cin2 % 4 || a->in2_ld % 4)) return SPS_ERR_BAD_ARG;

@@ -167,9 +167,6 @@ __global__ void __launch_bounds__(kUmmaThreads, 2) k_conv_umma(const sps_conv_ar
   const int st2 = (gpk2 + 7) >> 3;                 // stages of the fused 1x1 term
   const uint32_t in_ld_b = (uint32_t)a.in_ld * 4u, in2_ld_b = (uint32_t)a.in2_ld * 4u;
   const uint32_t idesc = make_idesc_tf32(NPAD);
-  // A destination of this thread inside a stage: row r, chunks c = 4*half + j, 128B swizzle
-  const uint32_t a_row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
-  const uint32_t swz = (uint32_t)(r & 7);
   // B chunk(s) of this thread: column cB = tid & 7, rows nB = tid/8 + 32*i
   const int cB = tid & 7;
   const char* in_b = reinterpret_cast<const char*>(a.in);
@@ -216,57 +213,51 @@ __global__ void __launch_bounds__(kUmmaThreads, 2) k_conv_umma(const sps_conv_ar
     const int nst_map = GPC < 8 ? (nact + EPS - 1) / EPS : nact * SPE;
     const int nstages = nst_map + st2;
 
+    // One stage = 128 rows x 8 chunks of 16 B.  Thread (tid>>3, tid&7) copies chunk column c = tid&7 of
+    // rows (tid>>3) + 32*i: the 8 lanes that share a row read one contiguous 128-byte line (or a few
+    // 32-byte sectors for narrow layers), so a warp-wide cp.async touches 4..16 L1 lines instead of 32.
     auto issue_stage = [&](int st) {
       const uint32_t gs = gstage + (uint32_t)st;
       const uint32_t slot = gs % S, use = gs / S;
       if (use > 0) mbar_wait(bar_empty + 8 * slot, (use - 1) & 1);  // the MMAs that read this slot are done
-      const uint32_t a_dst = sA_u + slot * kAStageBytes + a_row_off;
+      const int r0 = tid >> 3;
+      const uint32_t a_dst = sA_u + slot * kAStageBytes + (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128) +
+                             (((uint32_t)cB ^ (uint32_t)(r0 & 7)) << 4);
       const uint32_t b_dst = sB_u + slot * kBStageBytes;
       int64_t kofB = -1;  // float offset of this thread's weight chunk inside a K-major row
       if (st < nst_map) {
-        if (GPC < 8) {
-          // small Cin: EPS offsets per stage, GPC chunks each; this thread covers chunks 4*half..+3
-          constexpr int EPT = GPC == 2 ? 2 : 1;  // offsets touched by one thread
-#pragma unroll
-          for (int j = 0; j < EPT; ++j) {
-            const int e = st * EPS + (GPC == 2 ? 2 * half + j : half);
-            const int idx = e < nact ? sidx[klist[e] * kTileM + r] : -1;
-            const char* src = in_b + (idx >= 0 ? (uint32_t)idx * in_ld_b : 0u);
-            const uint32_t bytes = idx >= 0 ? 16u : 0u;
-#pragma unroll
-            for (int g = 0; g < (GPC == 2 ? 2 : 4); ++g) {
-              const int c = 4 * half + (GPC == 2 ? 2 * j : 0) + g;
-              const bool real = g < gpk;  // Cin = 4 uses only the first group of its pair
-              cp_async16(a_dst + (((uint32_t)c ^ swz) << 4), src + g * 16, real ? bytes : 0u);
-            }
-          }
-          const int eB = st * EPS + cB / GPC;
-          if (eB < nact) kofB = ((int64_t)klist[eB] * GPC + (cB % GPC)) * 4;
-        } else {
-          // large Cin: one offset per SPE stages, 8 consecutive chunks of the same neighbour row
+        int k, cg;
+        if (GPC < 8) {   // small Cin: EPS offsets per stage, GPC chunks each
+          const int e = st * EPS + cB / GPC;
+          cg = cB % GPC;
+          k = e < nact ? (int)klist[e] : -1;
+          if (k >= 0) kofB = ((int64_t)k * GPC + cg) * 4;
+        } else {         // large Cin: one offset per SPE stages
           const int e = st / SPE, sub = st - e * SPE;
-          const int k = klist[e];
-          const int idx = sidx[k * kTileM + r];
-          const int cg0 = sub * 8 + 4 * half;
-          const char* src = in_b + (idx >= 0 ? (uint32_t)idx * in_ld_b : 0u) + cg0 * 16;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const bool ok = idx >= 0 && cg0 + g < gpk;
-            cp_async16(a_dst + (((uint32_t)(4 * half + g) ^ swz) << 4), ok ? src + g * 16 : in_b, ok ? 16u : 0u);
-          }
-          kofB = ((int64_t)k * GP + sub * 8 + cB) * 4;
+          k = klist[e];
+          cg = sub * 8 + cB;
+          kofB = ((int64_t)k * GP + cg) * 4;
         }
-      } else {
-        // fused 1x1 term: identity gather from in2
+        const bool cg_ok = k >= 0 && cg < gpk;
+        const int32_t* sk = sidx + (k >= 0 ? k : 0) * kTileM + r0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int idx = cg_ok ? sk[32 * i] : -1;
+          const char* src = in_b + (idx >= 0 ? (uint32_t)idx * in_ld_b + (uint32_t)cg * 16u : 0u);
+          cp_async16(a_dst + i * 4096, src, idx >= 0 ? 16u : 0u);
+        }
+      } else {           // fused 1x1 term: identity gather from in2
         const int s2 = st - nst_map;
-        const int cg0 = s2 * 8 + 4 * half;
-        const char* src = in2_b + (row_ok ? (uint32_t)row * in2_ld_b : 0u) + cg0 * 16;
+        const int cg = s2 * 8 + cB;
+        const bool cg_ok = cg < gpk2;
+        if (cg_ok) kofB = ((int64_t)K * GP + cg) * 4;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const bool ok = row_ok && cg0 + g < gpk2;
-          cp_async16(a_dst + (((uint32_t)(4 * half + g) ^ swz) << 4), ok ? src + g * 16 : in_b, ok ? 16u : 0u);
+        for (int i = 0; i < 4; ++i) {
+          const int rw = tile * kTileM + r0 + 32 * i;
+          const bool ok = cg_ok && rw < n_out;
+          const char* src = ok ? in2_b + (uint32_t)rw * in2_ld_b + (uint32_t)cg * 16u : in_b;
+          cp_async16(a_dst + i * 4096, src, ok ? 16u : 0u);
         }
-        if (s2 * 8 + cB < gpk2) kofB = ((int64_t)K * GP + s2 * 8 + cB) * 4;
       }
 #pragma unroll
       for (int i = 0; i < (NPAD * 8 + kUmmaThreads - 1) / kUmmaThreads; ++i) {

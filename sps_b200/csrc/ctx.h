@@ -16,6 +16,8 @@ struct sps_ctx {
   int32_t* status = nullptr;   // sticky status word
   uint32_t* ticket = nullptr;  // last-block-done counters, one per unique() call
   int32_t* n_dev = nullptr;    // device copy of n (so level-0 kernels share the code path)
+  int32_t* nblocks = nullptr;  // blocks in the current level's block table
+  int32_t* cells = nullptr;    // [max_points][64] voxel rows per 4x4x4 block (upper bound: one block per voxel)
 
   float* staging = nullptr;    // [max_points][8] host->device landing zone
   float* scores = nullptr;     // [max_points]

@@ -209,6 +209,121 @@ __global__ void k_assign_coarse(Slot* tab, const uint32_t* __restrict__ slot_of,
   }
 }
 
+// Re-hash the (unique) voxel keys of a level into a table sized by the VOXEL count (the table left by
+// the de-duplication is sized by the number of inputs, 2-8x larger): the lookup table of the
+// kernel-map probes then fits in L2.
+__global__ void k_insert_unique(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr,
+                                Slot* tab) {
+  const int n = *n_ptr;
+  const uint32_t mask = table_capacity(n) - 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t s = table_insert(tab, mask, keys[i]);
+    tab[s].val = i;
+  }
+}
+
+// ---- block table: 4x4x4-cell blocks of a level's lattice -> 64 voxel rows each -----------------
+// The kernel-map probes of one voxel fall into at most 8 such blocks per time plane, and
+// neighbouring voxels share them, so a probe costs a (mostly L1/L2-resident) 4-byte read inside a
+// 256-byte block instead of one random 32-byte sector of a per-voxel hash table.
+__global__ void k_block_insert(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr,
+                               int log2b, Slot* tab, uint32_t* __restrict__ bslot, int32_t* nblocks) {
+  const int n = *n_ptr;
+  const uint32_t mask = table_capacity(n) - 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned long long bkey = coarsen_key(keys[i], log2b);
+    uint32_t s = hash_key(bkey) & mask;
+    while (true) {
+      const unsigned long long prev = atomicCAS(&tab[s].key, kEmptyKey, bkey);
+      if (prev == kEmptyKey) { tab[s].val = atomicAdd(nblocks, 1); break; }
+      if (prev == bkey) break;
+      s = (s + 1) & mask;
+    }
+    bslot[i] = s;
+  }
+}
+
+__global__ void k_cells_clear(int32_t* __restrict__ cells, const int32_t* __restrict__ nblocks) {
+  const int64_t total = (int64_t)(*nblocks) * 16;  // int4 stores
+  const int4 v = make_int4(-1, -1, -1, -1);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    reinterpret_cast<int4*>(cells)[i] = v;
+}
+
+__device__ __forceinline__ int cell_local(unsigned long long key, int L) {
+  return ((int)(key >> (kXShift + L)) & 3) + 4 * ((int)(key >> (kYShift + L)) & 3) + 16 * ((int)(key >> (kZShift + L)) & 3);
+}
+
+__global__ void k_cells_fill(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr, int L,
+                             const Slot* __restrict__ tab, const uint32_t* __restrict__ bslot,
+                             int32_t* __restrict__ cells) {
+  const int n = *n_ptr;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    cells[(int64_t)tab[bslot[i]].val * 64 + cell_local(keys[i], L)] = i;
+}
+
+// Kernel map of an odd hyper-cube kernel (K0,K0,K0,KT) on tensor stride [2^L]*3+[1] through the
+// block table: thread (o, it) resolves the K0^3 spatial neighbours of voxel o in time plane
+// t + (it - KT/2); k = i0 + K0*(i1 + K0*(i2 + K0*i3)) (ME order), nbr[k][o] coalesced over o.
+template <int K0, int KT>
+__global__ void __launch_bounds__(256)
+k_kernel_map_blk(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr,
+                 const Slot* __restrict__ tab, const int32_t* __restrict__ cells, int L, int32_t* __restrict__ nbr,
+                 int64_t ld) {
+  const int n = *n_ptr;
+  if (n == 0) return;
+  constexpr int R = K0 / 2, K3 = K0 * K0 * K0;
+  const uint32_t mask = table_capacity(n) - 1;
+  const int64_t total = (int64_t)KT * n;
+  const int xlim = 1 << (kXBits - L), zlim = 1 << (kZBits - L);
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int it = (int)(idx / n), o = (int)(idx - (int64_t)it * n);
+    const unsigned long long key = keys[o];
+    const int t2 = (int)(key & ((1u << kTBits) - 1)) + it - KT / 2;
+    int32_t* out = nbr + (int64_t)it * K3 * ld + o;
+    if ((unsigned)t2 >= (1u << kTBits)) {
+#pragma unroll 1
+      for (int k = 0; k < K3; ++k) out[(int64_t)k * ld] = -1;
+      continue;
+    }
+    const int cx = (int)((key >> kXShift) & ((1u << kXBits) - 1)) >> L;
+    const int cy = (int)((key >> kYShift) & ((1u << kYBits) - 1)) >> L;
+    const int cz = (int)((key >> kZShift) & ((1u << kZBits) - 1)) >> L;
+    const unsigned long long bt = (key & (0xFFull << kBShift)) | (unsigned long long)(unsigned)t2;
+    unsigned long long cached_key = kEmptyKey;
+    const int32_t* cached = nullptr;
+#pragma unroll 1
+    for (int dz = -R; dz <= R; ++dz) {
+      const int nz = cz + dz;
+      const bool zok = (unsigned)nz < (unsigned)zlim;
+#pragma unroll 1
+      for (int dy = -R; dy <= R; ++dy) {
+        const int ny = cy + dy;
+        const bool yok = zok && (unsigned)ny < (unsigned)xlim;
+        const unsigned long long byz = bt | ((unsigned long long)(unsigned)((ny >> 2) << (L + 2)) << kYShift) |
+                                       ((unsigned long long)(unsigned)((nz >> 2) << (L + 2)) << kZShift);
+        const int lyz = 4 * (ny & 3) + 16 * (nz & 3);
+#pragma unroll
+        for (int dx = -R; dx <= R; ++dx) {
+          const int nx = cx + dx;
+          int res = -1;
+          if (yok && (unsigned)nx < (unsigned)xlim) {
+            const unsigned long long bkey = byz | ((unsigned long long)(unsigned)((nx >> 2) << (L + 2)) << kXShift);
+            if (bkey != cached_key) {
+              cached_key = bkey;
+              const int id = table_find(tab, mask, bkey);
+              cached = id >= 0 ? cells + (int64_t)id * 64 : nullptr;
+            }
+            if (cached) res = __ldg(cached + lyz + (nx & 3));
+          }
+          out[(int64_t)((dx + R) + K0 * ((dy + R) + K0 * (dz + R))) * ld] = res;
+        }
+      }
+    }
+  }
+}
+
 // Kernel map for an odd hyper-cube kernel (k0,k1,k2,k3) on tensor stride [2^log2s]*3 + [1]:
 // nbr[k][o] = row of (out[o] + delta_k) in the same coordinate set, k = i0 + k0*(i1 + k1*(i2 + k2*i3)),
 // delta_d = (i_d - k_d/2) * stride_d.  One independent hash probe per thread, o fastest so the
@@ -301,12 +416,23 @@ extern "C" int sps_build_maps(sps_ctx* ctx, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   const int64_t n = ctx->n > 0 ? ctx->n : 1;  // host upper bound of every level's voxel count
   const int nblk = cdiv(n, kScanBlock);
-  // level-0 kernel maps use the table left by sps_voxelize (capacity from n)
-  k_kernel_map<<<grid_for(125 * n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->n_dev, ctx->table, 5, 5,
-                                                       5, 1, 0, ctx->nbr5, ctx->ld);
+  // level-0 block table (the voxelize table is no longer needed), then both level-0 kernel maps
+  auto build_blocks = [&](int L) {
+    k_table_clear<<<grid_for(table_capacity(n), 256), 256, 0, st>>>(ctx->table, ctx->counts + L);
+    k_set_i32<<<1, 1, 0, st>>>(ctx->nblocks, 0);
+    k_block_insert<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[L], ctx->counts + L, L + 2, ctx->table, ctx->slot_of,
+                                                      ctx->nblocks);
+    k_cells_clear<<<grid_for(n * 16, 256), 256, 0, st>>>(ctx->cells, ctx->nblocks);
+    k_cells_fill<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[L], ctx->counts + L, L, ctx->table, ctx->slot_of,
+                                                    ctx->cells);
+  };
+  build_blocks(0);
+  prof_mark("blocks.L0", st);
+  k_kernel_map_blk<5, 1><<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->table, ctx->cells, 0,
+                                                            ctx->nbr5, ctx->ld);
   prof_mark("kmap5.L0", st);
-  k_kernel_map<<<grid_for(81 * n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->n_dev, ctx->table, 3, 3,
-                                                      3, 3, 0, ctx->nbr3[0], ctx->ld);
+  k_kernel_map_blk<3, 3><<<grid_for(3 * n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->table, ctx->cells, 0,
+                                                                ctx->nbr3[0], ctx->ld);
   prof_mark("kmap3.L0", st);
   for (int L = 1; L < SPS_NUM_LEVELS; ++L) {
     const int32_t* n_fine = ctx->counts + (L - 1);
@@ -320,9 +446,10 @@ extern "C" int sps_build_maps(sps_ctx* ctx, void* stream_) {
                                                        ctx->child[L], ctx->ld);
     static const char* nm_s[5] = {"", "stride.L1", "stride.L2", "stride.L3", "stride.L4"};
     static const char* nm_k[5] = {"", "kmap3.L1", "kmap3.L2", "kmap3.L3", "kmap3.L4"};
+    build_blocks(L);
     prof_mark(nm_s[L], st);
-    k_kernel_map<<<grid_for(81 * n, 256), 256, 0, st>>>(ctx->keys[L], ctx->counts + L, n_fine, ctx->table, 3, 3, 3,
-                                                        3, L, ctx->nbr3[L], ctx->ld);
+    k_kernel_map_blk<3, 3><<<grid_for(3 * n, 256), 256, 0, st>>>(ctx->keys[L], ctx->counts + L, ctx->table, ctx->cells, L,
+                                                                  ctx->nbr3[L], ctx->ld);
     prof_mark(nm_k[L], st);
   }
   SPS_CUDA_CHECK(cudaGetLastError());

@@ -284,7 +284,7 @@ int unet_forward(sps_ctx* c, const sps_net* net, const float* feat0, float* logi
   float* Bd[4] = {B[C::B5], B[C::B6], B[C::B7], nullptr};
   for (int i = 0; i < 4; ++i) {
     const int L = 3 - i;  // output level
-    RUN(nm_up[i], net->up[i], SPS_CONV_UP, c->parent[L], 0, c->counts + L, nmax, dec_in, dec_in_ld, nullptr, 0, nullptr, 0,
+    RUN(nm_up[i], net->up[i], SPS_CONV_UP, c->child[L + 1], ld, c->counts + L + 1, nmax, dec_in, dec_in_ld, nullptr, 0, nullptr, 0,
         cat[L], skip_ld[L], st);
     const ConvW& c1 = net->blk1[4 + i];
     const ConvW& c2 = net->blk2[4 + i];
@@ -356,7 +356,7 @@ int forward_impl(sps_ctx* ctx, const sps_net* net, const float* d_points, int64_
   rc = sps_devox_sigmoid(ctx->buf[sps_ctx::LOGITS], ctx->inv, n_scores, d_scores, st);
   if (rc != SPS_OK) return rc;
   prof_mark("devox_sigmoid", st);
-  g_forward_launches += 5 + 26 + 1 + 1;  // voxelize, maps, feature fill, devox
+  g_forward_launches += 5 + 51 + 1 + 1;  // voxelize, maps, feature fill, devox
   return SPS_OK;
 }
 }  // namespace sps

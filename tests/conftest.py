@@ -11,6 +11,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "tensor_path: run with the default conv dispatch (tcgen05 TF32 kernels)")
 
 
 def pytest_collection_modifyitems(config, items):
