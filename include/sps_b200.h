@@ -211,6 +211,15 @@ int sps_profile_read(char* names, float* ms, int max, int* n_out);
  * level 0) or 8 (children of `level`).  Host-synchronising.  Used for algorithmic FLOP counts. */
 int sps_ctx_pair_count(sps_ctx* ctx, int level, int kind, int64_t* h_out, void* stream);
 
+/* SPSNet.predict_step metric partials (src/sps/models/models.py:84-104, util.py:285-299) of one
+ * scan on the device: rows fp32 [n,ld>=6] = (b,x,y,z,t,label); only rows with t == 1 (and
+ * b == batch_index when batch_index >= 0) count.  d_counts int64[4] = TP,TN,FP,FN with class 1 =
+ * unstable (value >= eps); d_sums double[5] = n, sum((score-label)^2), sum(label),
+ * sum(label^2), sum(score).  These are what the NCCL gather of metrics carries. */
+int sps_confusion_counts(const float* d_scores, const float* d_rows, int64_t ld_rows, int64_t n,
+                         float batch_index, float eps, int64_t* d_counts, double* d_sums,
+                         void* stream);
+
 /* Small helpers so that host code needs no second CUDA binding. */
 int sps_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream);
 int sps_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream);

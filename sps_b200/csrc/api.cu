@@ -235,3 +235,49 @@ extern "C" int sps_ctx_pair_count(sps_ctx* ctx, int level, int kind, int64_t* h_
   *h_out = (int64_t)h;
   return SPS_OK;
 }
+
+// ---------------------------------------------------------------- per-scan metric partials ----
+// SPSNet.predict_step (src/sps/models/models.py:84-104): over the scan rows (t == 1) of ONE scan,
+// pred = score < eps ? 0 : 1, gt = label < eps ? 0 : 1 -> TP/TN/FP/FN (class 1 = unstable), plus
+// the sums MSE and R2 need.  counts: int64 [4] = TP,TN,FP,FN; sums: double [5] = n, sum(err^2),
+// sum(label), sum(label^2), sum(score).
+namespace sps {
+__global__ void k_confusion(const float* __restrict__ scores, const float* __restrict__ rows, int64_t ld, int64_t n,
+                            float batch_index, float eps, unsigned long long* counts, double* sums) {
+  unsigned long long c[4] = {0, 0, 0, 0};
+  double s[5] = {0, 0, 0, 0, 0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float* r = rows + i * ld;
+    if (r[4] != 1.0f || (batch_index >= 0.f && r[0] != batch_index)) continue;
+    const float sc = scores[i], lb = r[5];
+    const int p = sc < eps ? 0 : 1, g = lb < eps ? 0 : 1;
+    c[(g == 1 && p == 1) ? 0 : (g == 0 && p == 0) ? 1 : (g == 0 && p == 1) ? 2 : 3] += 1;
+    const double e = (double)sc - (double)lb;
+    s[0] += 1.0; s[1] += e * e; s[2] += lb; s[3] += (double)lb * lb; s[4] += sc;
+  }
+  for (int j = 0; j < 4; ++j) {
+    for (int d = 16; d; d >>= 1) c[j] += __shfl_down_sync(0xffffffffu, c[j], d);
+    if ((threadIdx.x & 31) == 0 && c[j]) atomicAdd(counts + j, c[j]);
+  }
+  for (int j = 0; j < 5; ++j) {
+    for (int d = 16; d; d >>= 1) s[j] += __shfl_down_sync(0xffffffffu, s[j], d);
+    if ((threadIdx.x & 31) == 0 && s[j] != 0.0) atomicAdd(sums + j, s[j]);
+  }
+}
+}  // namespace sps
+
+extern "C" int sps_confusion_counts(const float* d_scores, const float* d_rows, int64_t ld_rows, int64_t n,
+                                    float batch_index, float eps, int64_t* d_counts, double* d_sums, void* stream) {
+  if (!d_scores || !d_rows || ld_rows < 6 || n < 0 || !d_counts || !d_sums) return SPS_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  SPS_CUDA_CHECK(cudaMemsetAsync(d_counts, 0, 4 * sizeof(int64_t), st));
+  SPS_CUDA_CHECK(cudaMemsetAsync(d_sums, 0, 5 * sizeof(double), st));
+  if (n > 0) {
+    int64_t g = (n + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    k_confusion<<<(int)g, 256, 0, st>>>(d_scores, d_rows, ld_rows, n, batch_index, eps,
+                                        reinterpret_cast<unsigned long long*>(d_counts), d_sums);
+    SPS_CUDA_CHECK(cudaGetLastError());
+  }
+  return SPS_OK;
+}
