@@ -454,6 +454,10 @@ def predict_step_metrics(scores, labels, t_col, eps):
     ss_res = float(np.sum((g - s) ** 2))
     ss_tot = float(np.sum((g - g.mean()) ** 2))
     r2 = 1.0 - ss_res / ss_tot if ss_tot > 0 else 0.0
-    precision, recall, f1, acc, diou = calculate_metrics(threshold_labels(g, eps), threshold_labels(s, eps))
+    # models.py:97-98 compares float32 tensors with the Python float epsilon: torch evaluates that in
+    # float32 (the scalar is cast to the tensor dtype), so 0.84f is NOT below 0.84
+    s32, g32 = np.asarray(scores, np.float32)[scan], np.asarray(labels, np.float32)[scan]
+    precision, recall, f1, acc, diou = calculate_metrics(threshold_labels(g32, np.float32(eps)),
+                                                         threshold_labels(s32, np.float32(eps)))
     return {"loss": mse, "r2": r2, "precision": precision, "recall": recall, "f1": f1,
             "accuracy": acc, "dIoU": diou}
