@@ -115,6 +115,8 @@ typedef struct sps_conv_args {
   const float* weight_kmajor; int64_t kmajor_ld;
   int round_out;            /* store outputs rounded to TF32 (nearest), so that a following
                                tensor-core layer does not truncate its operand               */
+  const uint32_t* tile_mask; /* tensor-core path: [ceil(n_out/128)][4] present-offset bitmasks of
+                               `map` per 128-row tile (sps_kernel_map_tile_masks); NULL -> CUDA-core */
 } sps_conv_args;
 /* MinkowskiConvolution / MinkowskiConvolutionTranspose (+ folded MinkowskiBatchNorm, ReLU,
  * residual) forward: minkunet.py:55-158, resnet.py:97-108, ME BasicBlock.  Served by the tcgen05
@@ -195,6 +197,10 @@ int sps_infer_scan(sps_ctx* ctx, const sps_net* net, const sps_map* map, const f
  * the layer shape allows, fp32 CUDA-core otherwise), 1 = fp32 CUDA-core only, 2 = tcgen05 only
  * (SPS_ERR_UNSUPPORTED for shapes it does not take). */
 int sps_set_conv_backend(int backend);
+/* Per-tile present-offset bitmasks of a kernel map (K <= 81) for the tensor-core path:
+ * d_masks uint32 [ceil(n_out_max/128)][4]. */
+int sps_kernel_map_tile_masks(const int32_t* d_map, int64_t map_ld, int K, const int32_t* d_n_out,
+                              int64_t n_out_max, uint32_t* d_masks, void* stream);
 /* Host helper for the tensor-core path: ME-layout weights [K][cin][cout] (+ optional fused 1x1
  * term w2 [cin2][cout]) -> K-major [cout][ld], ld = sps_conv_kmajor_ld(K,cin,cin2), values
  * rounded to TF32 (nearest even).  `out` is a HOST buffer of cout*ld floats. */

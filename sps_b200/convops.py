@@ -29,9 +29,18 @@ def pack_kmajor(weight: torch.Tensor, weight2: torch.Tensor | None = None) -> to
     return torch.as_tensor(out).to(weight.device)
 
 
+def kernel_map_tile_masks(map, map_ld, K, n_out, n_out_max):
+    """Present-offset bitmask per 128-row tile of a dense kernel map (tensor-core path input)."""
+    lib = _cabi.load()
+    masks = torch.zeros(((n_out_max + 127) // 128 + 1, 4), dtype=torch.int32, device=map.device)
+    check(lib.sps_kernel_map_tile_masks(_ptr(map), int(map_ld), int(K), _ptr(n_out), int(n_out_max), _ptr(masks), _stream()),
+          "sps_kernel_map_tile_masks")
+    return masks
+
+
 def conv_fwd(inp, weight, n_out, *, map=None, map_ld=0, mode=_cabi.SPS_CONV_NBR, shift=None, in2=None, weight2=None,
              res=None, relu=False, out=None, head_w=None, head_b=0.0, head_out=None, weight_kmajor=None,
-             round_out=False, n_out_max=None, backend=None):
+             round_out=False, n_out_max=None, backend=None, tile_mask=None):
     """out[o] = act(sum_k in[map[k][o]] @ W[k] (+ in2[o] @ W2) + shift (+ res[o])); ``n_out`` is a
     1-element int32 CUDA tensor (device-side count).  ``inp``/``out``/``in2``/``res`` may be
     channel slices (stride(0) is the leading dimension)."""
@@ -61,6 +70,10 @@ def conv_fwd(inp, weight, n_out, *, map=None, map_ld=0, mode=_cabi.SPS_CONV_NBR,
     if weight_kmajor is not None:
         a.weight_kmajor, a.kmajor_ld = weight_kmajor.data_ptr(), weight_kmajor.stride(0)
     a.round_out = int(round_out)
+    if weight_kmajor is not None and map is not None and tile_mask is None and K <= 81:
+        tile_mask = kernel_map_tile_masks(map, map_ld, K, n_out, n_out_max)
+    if tile_mask is not None:
+        a.tile_mask = tile_mask.data_ptr()
     if backend is not None:
         check(lib.sps_set_conv_backend(backend), "sps_set_conv_backend")
     try:

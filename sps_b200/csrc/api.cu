@@ -49,6 +49,7 @@ static size_t carve(sps_ctx* c, void* base, int64_t max_points) {
   for (int L = 0; L < SPS_NUM_LEVELS; ++L) {
     c->keys[L] = cv.take<unsigned long long>(N);
     c->nbr3[L] = cv.take<int32_t>((size_t)81 * ld);
+    c->tmask3[L] = cv.take<uint32_t>((size_t)(ld / 128 + 1) * 4);
     c->parent[L] = (L < SPS_NUM_LEVELS - 1) ? cv.take<int32_t>(N) : nullptr;
     c->child[L] = (L > 0) ? cv.take<int32_t>((size_t)8 * ld) : nullptr;
   }

@@ -2,8 +2,12 @@
 //
 //   out[o] = act( sum_k in[map[k][o]] @ W[k]  (+ in2[o] @ W2)  + shift (+ res[o]) )
 //
-// One CTA (256 threads) owns a tile of 128 output voxels = the 128 TMEM lanes of one fp32
-// accumulator [128 x N] (N = Cout padded to 16).  The GEMM K dimension is the im2col row
+// A tile is 128 output voxels = the 128 TMEM lanes of one fp32 accumulator [128 x N] (N = Cout
+// padded to 16).  One persistent CTA per SM (416 threads) is warp-specialised the Blackwell way:
+// 8 producer warps gather, 1 warp issues tcgen05.mma, 4 warps run the epilogue; they only meet
+// through mbarrier rings (stage full/empty, accumulator full/empty, kernel-map slice ready), so
+// the gathers of tile i+1 overlap the MMAs of tile i and the epilogue of tile i-1 (two TMEM
+// accumulators).  The GEMM K dimension is the im2col row
 // (kernel offset k, input channel ci), walked in 16-byte groups (4 fp32 channels):
 //   * prologue: the tile's slice of the kernel map is staged in shared memory with cp.async
 //     (all K loads in flight at once) and a warp ballot finds the offsets that have at least
@@ -28,9 +32,7 @@
 namespace sps {
 
 constexpr int kTileM = 128;
-constexpr int kStages = 3;
 constexpr int kAStageBytes = kTileM * 128;  // 16 KB
-constexpr int kUmmaThreads = 256;
 constexpr int kMaxK = 81;  // kernel volumes this kernel takes (neighbour indices are staged in smem)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -115,39 +117,64 @@ struct UmmaParams {
   int round_out;
 };
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive on `bar` once all cp.async issued so far by this thread have landed (no pending-count bump)
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+constexpr int kProducerThreads = 256;                 // warps 0-7: gather A/B, stage kernel-map slices
+constexpr int kMmaWarp = 8;                           // warp 8: tcgen05.mma issue
+// warps 9-12: epilogue (TMEM -> registers -> global)
+constexpr int kCtaThreads = kProducerThreads + 32 + 128;
+
+template <int NPAD>
+struct UmmaCfg {
+  static constexpr int S = NPAD == 64 ? 5 : 6;        // ring depth
+  static constexpr int kBStage = NPAD * 128;
+  static constexpr int kTmemCols = 2 * NPAD < 32 ? 32 : 2 * NPAD;   // two accumulators (double buffered)
+  static constexpr size_t smem = (size_t)S * (kAStageBytes + kBStage) + 2 * (size_t)kMaxK * kTileM * 4 +
+                                 8 * (2 * S + 6) + 2 * 96 + 32;
+};
+
 // GPC = padded groups per offset class: 2 or 4 (several offsets per stage) or 8 (= "8 or more":
-// one offset spans GP/8 stages)
+// one offset spans GP/8 stages).  Persistent, warp-specialised: producers, MMA issuer and
+// epilogue run decoupled through mbarrier rings and never meet at a block-wide barrier.
 template <int NPAD, int GPC>
-__global__ void __launch_bounds__(kUmmaThreads, 2) k_conv_umma(const sps_conv_args a, const UmmaParams p) {
-  constexpr int kBStageBytes = NPAD * 128;
-  constexpr int kTmemCols = NPAD < 32 ? 32 : NPAD;
-  constexpr int S = kStages;
-  constexpr int HC = NPAD / 2;  // accumulator columns per epilogue thread
+__global__ void __launch_bounds__(kCtaThreads, 1) k_conv_umma(const sps_conv_args a, const UmmaParams p) {
+  using Cfg = UmmaCfg<NPAD>;
+  constexpr int S = Cfg::S;
+  constexpr int kBStageBytes = Cfg::kBStage;
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sA = smem;                                                   // [S][128 rows x 128 B], 128B-swizzled
-  uint8_t* sB = smem + S * kAStageBytes;                                // [S][NPAD rows x 128 B]
-  int32_t* sidx = reinterpret_cast<int32_t*>(sB + S * kBStageBytes);    // [K][128] neighbour rows of this tile
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sidx + kMaxK * kTileM);  // [S] empty + [1] accum
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + S + 1);
-  uint32_t* kmask = tmem_slot + 1;                         // [4] bitmask of offsets present in the tile
-  uint8_t* klist = reinterpret_cast<uint8_t*>(kmask + 4);  // [128] present offsets, ascending
-  int* nact_s = reinterpret_cast<int*>(klist + 128);
+  uint8_t* sA = smem;                                                     // [S][128 rows x 128 B], 128B-swizzled
+  uint8_t* sB = smem + S * kAStageBytes;                                  // [S][NPAD rows x 128 B]
+  int32_t* sidx = reinterpret_cast<int32_t*>(sB + S * kBStageBytes);      // [2][K][128] kernel-map slices (tile parity)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sidx + 2 * kMaxK * kTileM);
+  // bars: full[S], empty[S], idx_full[2], acc_full[2], acc_empty[2]
+  uint8_t* klist = reinterpret_cast<uint8_t*>(bars + 2 * S + 6);           // [2][96] present offsets per tile parity
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(klist + 2 * 96);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int r = tid & 127, half = tid >> 7;  // A gather: row r, chunks 4*half .. 4*half+3
   const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB), sidx_u = smem_u32(sidx);
-  const uint32_t bar_empty = smem_u32(bars), bar_accum = smem_u32(bars + S);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * S, bar_idx = bar_empty + 8 * S,
+                 bar_accf = bar_idx + 16, bar_acce = bar_accf + 16;
   if (sA_u & 1023) __trap();  // SWIZZLE_128B atoms need 1024-byte aligned stage bases
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) mbar_init(bar_empty + 8 * s, 1);
-    mbar_init(bar_accum, 1);
+    for (int s = 0; s < S; ++s) { mbar_init(bar_full + 8 * s, kProducerThreads); mbar_init(bar_empty + 8 * s, 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_idx + 8 * i, kProducerThreads);
+      mbar_init(bar_accf + 8 * i, 1);
+      mbar_init(bar_acce + 8 * i, 128);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
-    __syncwarp();
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)kTmemCols)
+                 "r"((uint32_t)Cfg::kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -159,202 +186,208 @@ __global__ void __launch_bounds__(kUmmaThreads, 2) k_conv_umma(const sps_conv_ar
   const int n_out = *a.n_out;
   const int ntiles = (n_out + kTileM - 1) / kTileM;
   const int K = a.K;
-  const int gpk = a.cin >> 2;                      // real groups per offset
+  const int gpk = a.cin >> 2;                           // real groups per offset
   const int GP = GPC < 8 ? GPC : padded_groups(a.cin);  // padded groups per offset
-  const int SPE = GPC < 8 ? 1 : GP >> 3;           // stages per offset (large Cin)
-  constexpr int EPS = GPC < 8 ? 8 / GPC : 1;       // offsets per stage (small Cin)
+  const int SPE = GPC < 8 ? 1 : GP >> 3;                // stages per offset (large Cin)
+  constexpr int EPS = GPC < 8 ? 8 / GPC : 1;            // offsets per stage (small Cin)
   const int gpk2 = a.in2 ? (a.cin2 >> 2) : 0;
-  const int st2 = (gpk2 + 7) >> 3;                 // stages of the fused 1x1 term
-  const uint32_t in_ld_b = (uint32_t)a.in_ld * 4u, in2_ld_b = (uint32_t)a.in2_ld * 4u;
-  const uint32_t idesc = make_idesc_tf32(NPAD);
-  // B chunk(s) of this thread: column cB = tid & 7, rows nB = tid/8 + 32*i
-  const int cB = tid & 7;
-  const char* in_b = reinterpret_cast<const char*>(a.in);
-  const char* in2_b = reinterpret_cast<const char*>(a.in2);
+  const int st2 = (gpk2 + 7) >> 3;                      // stages of the fused 1x1 term
+  const uint32_t* tmask = a.tile_mask;
+  auto tile_nact = [&](int tile) {
+    return __popc(__ldg(tmask + 4 * tile)) + __popc(__ldg(tmask + 4 * tile + 1)) + __popc(__ldg(tmask + 4 * tile + 2));
+  };
+  auto tile_stages = [&](int nact) { return (GPC < 8 ? (nact + EPS - 1) / EPS : nact * SPE) + st2; };
 
-  uint32_t gstage = 0;  // stages issued so far by this CTA (ring slot + mbarrier phase bookkeeping)
-  uint32_t accum_uses = 0;
+  if (warp < kMmaWarp) {
+    // =========================== PRODUCERS (256 threads) ===========================
+    const uint32_t in_ld_b = (uint32_t)a.in_ld * 4u, in2_ld_b = (uint32_t)a.in2_ld * 4u;
+    const char* in_b = reinterpret_cast<const char*>(a.in);
+    const char* in2_b = reinterpret_cast<const char*>(a.in2);
+    const int r0 = tid >> 3, cB = tid & 7;      // gather: chunk column cB of rows r0 + 32*i
+    const int rI = tid & 127, hI = tid >> 7;    // kernel-map staging: row rI, every other offset
+    const uint32_t a_off = (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128) + (((uint32_t)cB ^ (uint32_t)(r0 & 7)) << 4);
 
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int row = tile * kTileM + r;
-    const bool row_ok = row < n_out;
-
-    // ---- prologue: stage the tile's kernel-map slice, find the offsets present in the tile ----
-    if (tid < 4) kmask[tid] = 0;
-    if (row_ok) {
-      const int32_t* src = a.map + row;
-      for (int k = half; k < K; k += 2)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sidx_u + (uint32_t)(k * kTileM + r) * 4),
-                     "l"(src + (int64_t)k * a.map_ld)
-                     : "memory");
-    } else {
-      for (int k = half; k < K; k += 2) sidx[k * kTileM + r] = -1;  // rows past the end have no neighbours
-    }
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
-    for (int k = warp; k < K; k += 8) {  // warp w scans offsets w, w+8, ...; each lane looks at 4 rows
-      const int32_t* q = sidx + k * kTileM + lane;
-      const bool any = (q[0] >= 0) | (q[32] >= 0) | (q[64] >= 0) | (q[96] >= 0);
-      if (__any_sync(0xffffffffu, any) && lane == 0) atomicOr(&kmask[k >> 5], 1u << (k & 31));
-    }
-    __syncthreads();
-    if (warp == 0) {  // ordered compaction of the present offsets
-      int base = 0;
-      for (int w = 0; w < 3; ++w) {
-        const uint32_t bits = kmask[w];
-        if ((bits >> lane) & 1u) klist[base + __popc(bits & ((1u << lane) - 1u))] = (uint8_t)(32 * w + lane);
-        base += __popc(bits);
-      }
-      if (lane == 0) *nact_s = base;
-    }
-    __syncthreads();
-    const int nact = *nact_s;
-    const int nst_map = GPC < 8 ? (nact + EPS - 1) / EPS : nact * SPE;
-    const int nstages = nst_map + st2;
-
-    // One stage = 128 rows x 8 chunks of 16 B.  Thread (tid>>3, tid&7) copies chunk column c = tid&7 of
-    // rows (tid>>3) + 32*i: the 8 lanes that share a row read one contiguous 128-byte line (or a few
-    // 32-byte sectors for narrow layers), so a warp-wide cp.async touches 4..16 L1 lines instead of 32.
-    auto issue_stage = [&](int st) {
-      const uint32_t gs = gstage + (uint32_t)st;
-      const uint32_t slot = gs % S, use = gs / S;
-      if (use > 0) mbar_wait(bar_empty + 8 * slot, (use - 1) & 1);  // the MMAs that read this slot are done
-      const int r0 = tid >> 3;
-      const uint32_t a_dst = sA_u + slot * kAStageBytes + (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128) +
-                             (((uint32_t)cB ^ (uint32_t)(r0 & 7)) << 4);
-      const uint32_t b_dst = sB_u + slot * kBStageBytes;
-      int64_t kofB = -1;  // float offset of this thread's weight chunk inside a K-major row
-      if (st < nst_map) {
-        int k, cg;
-        if (GPC < 8) {   // small Cin: EPS offsets per stage, GPC chunks each
-          const int e = st * EPS + cB / GPC;
-          cg = cB % GPC;
-          k = e < nact ? (int)klist[e] : -1;
-          if (k >= 0) kofB = ((int64_t)k * GPC + cg) * 4;
-        } else {         // large Cin: one offset per SPE stages
-          const int e = st / SPE, sub = st - e * SPE;
-          k = klist[e];
-          cg = sub * 8 + cB;
-          kofB = ((int64_t)k * GP + cg) * 4;
-        }
-        const bool cg_ok = k >= 0 && cg < gpk;
-        const int32_t* sk = sidx + (k >= 0 ? k : 0) * kTileM + r0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int idx = cg_ok ? sk[32 * i] : -1;
-          const char* src = in_b + (idx >= 0 ? (uint32_t)idx * in_ld_b + (uint32_t)cg * 16u : 0u);
-          cp_async16(a_dst + i * 4096, src, idx >= 0 ? 16u : 0u);
-        }
-      } else {           // fused 1x1 term: identity gather from in2
-        const int s2 = st - nst_map;
-        const int cg = s2 * 8 + cB;
-        const bool cg_ok = cg < gpk2;
-        if (cg_ok) kofB = ((int64_t)K * GP + cg) * 4;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rw = tile * kTileM + r0 + 32 * i;
-          const bool ok = cg_ok && rw < n_out;
-          const char* src = ok ? in2_b + (uint32_t)rw * in2_ld_b + (uint32_t)cg * 16u : in_b;
-          cp_async16(a_dst + i * 4096, src, ok ? 16u : 0u);
+    // stage the kernel-map slice of `tile` (only the offsets present in it) into parity buffer `par`
+    auto prepare = [&](int tile, int par) {
+      producer_bar();   // everybody is done reading klist/sidx of the tile that used this parity before
+      if (warp == 0) {  // ordered list of present offsets from the precomputed tile mask
+        int base = 0;
+        for (int w = 0; w < 3; ++w) {
+          const uint32_t bits = __ldg(tmask + 4 * tile + w);
+          if ((bits >> lane) & 1u) klist[par * 96 + base + __popc(bits & ((1u << lane) - 1u))] = (uint8_t)(32 * w + lane);
+          base += __popc(bits);
         }
       }
-#pragma unroll
-      for (int i = 0; i < (NPAD * 8 + kUmmaThreads - 1) / kUmmaThreads; ++i) {
-        const int n = (tid >> 3) + 32 * i;
-        if (NPAD * 8 >= kUmmaThreads || n < NPAD) {
-          const bool ok = kofB >= 0 && n < a.cout;
-          const float* src = ok ? p.wt + (int64_t)n * p.ldk + kofB : p.wt;
-          cp_async16(b_dst + (uint32_t)((n >> 3) * 1024 + (n & 7) * 128) + (((uint32_t)cB ^ (uint32_t)(n & 7)) << 4), src,
-                     ok ? 16u : 0u);
-        }
+      producer_bar();
+      const int nact = tile_nact(tile);
+      const int row = tile * kTileM + rI;
+      const uint32_t dst = sidx_u + (uint32_t)(par * kMaxK * kTileM + rI) * 4u;
+      if (row < n_out) {
+        const int32_t* src = a.map + row;
+        for (int e = hI; e < nact; e += 2)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (uint32_t)(e * kTileM) * 4u),
+                       "l"(src + (int64_t)klist[par * 96 + e] * a.map_ld)
+                       : "memory");
+      } else {
+        for (int e = hI; e < nact; e += 2) sidx[(par * kMaxK + e) * kTileM + rI] = -1;  // rows past the end
       }
+      cp_async_arrive(bar_idx + 8 * par);
     };
 
-    // ---- main loop: S-deep ring, the gather (cp.async) runs S-1 stages ahead of the MMAs ----
-    for (int st = 0; st < S - 1; ++st) {
-      if (st < nstages) issue_stage(st);
-      cp_async_commit();
-    }
-    for (int it = 0; it < nstages; ++it) {
-      cp_async_wait<S - 2>();  // this thread's part of stage `it` has landed
-      fence_proxy_async();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      __syncthreads();         // ... and everybody else's
-      if (tid == 0) {
-        tc_fence_after();
-        const uint32_t slot = (gstage + (uint32_t)it) % S;
-        const uint64_t adesc = make_smem_desc(sA_u + slot * kAStageBytes);
-        const uint64_t bdesc = make_smem_desc(sB_u + slot * kBStageBytes);
+    uint32_t gs = 0;  // global stage counter (ring slot + phase)
+    int it_tile = 0;
+    if ((int)blockIdx.x < ntiles) prepare(blockIdx.x, 0);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it_tile) {
+      const int par = it_tile & 1;
+      const int next = tile + gridDim.x;
+      if (next < ntiles) prepare(next, par ^ 1);   // one tile ahead: its latency hides behind this tile's gathers
+      const int nact = tile_nact(tile);
+      const int nst_map = GPC < 8 ? (nact + EPS - 1) / EPS : nact * SPE;
+      const int nstages = nst_map + st2;
+      mbar_wait(bar_idx + 8 * par, (it_tile >> 1) & 1);
+      const int32_t* sx = sidx + par * kMaxK * kTileM + r0;   // [e][128] compacted by present offset
+      const uint8_t* kl = klist + par * 96;
+      for (int st = 0; st < nstages; ++st, ++gs) {
+        const uint32_t slot = gs % S, use = gs / S;
+        mbar_wait(bar_empty + 8 * slot, (use & 1) ^ 1);  // MMAs that read this slot have completed
+        const uint32_t a_dst = sA_u + slot * kAStageBytes + a_off;
+        const uint32_t b_dst = sB_u + slot * kBStageBytes;
+        int64_t kofB = -1;  // float offset of this thread's weight chunk inside a K-major row
+        if (st < nst_map) {
+          int e, cg;
+          if (GPC < 8) { e = st * EPS + cB / GPC; cg = cB % GPC; }
+          else { e = st / SPE; cg = (st - e * SPE) * 8 + cB; }
+          const bool e_ok = e < nact;
+          if (e_ok) kofB = ((int64_t)kl[e] * GP + cg) * 4;
+          const bool cg_ok = e_ok && cg < gpk;
+          const int32_t* sk = sx + (e_ok ? e : 0) * kTileM;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)  // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle atom
-          umma_tf32(tmem_base, adesc + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (it | j) ? 1u : 0u);
-        umma_commit(bar_empty + 8 * slot);
-        if (it == nstages - 1) umma_commit(bar_accum);
+          for (int i = 0; i < 4; ++i) {
+            const int idx = cg_ok ? sk[32 * i] : -1;
+            const char* src = in_b + (idx >= 0 ? (uint32_t)idx * in_ld_b + (uint32_t)cg * 16u : 0u);
+            cp_async16(a_dst + i * 4096, src, idx >= 0 ? 16u : 0u);
+          }
+        } else {  // fused 1x1 term: identity gather from in2
+          const int cg = (st - nst_map) * 8 + cB;
+          const bool cg_ok = cg < gpk2;
+          if (cg_ok) kofB = ((int64_t)K * GP + cg) * 4;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rw = tile * kTileM + r0 + 32 * i;
+            const bool ok = cg_ok && rw < n_out;
+            const char* src = ok ? in2_b + (uint32_t)rw * in2_ld_b + (uint32_t)cg * 16u : in_b;
+            cp_async16(a_dst + i * 4096, src, ok ? 16u : 0u);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < (NPAD + 31) / 32; ++i) {
+          const int n = r0 + 32 * i;
+          if (NPAD >= 32 || n < NPAD) {
+            const bool ok = kofB >= 0 && n < a.cout;
+            const float* src = ok ? p.wt + (int64_t)n * p.ldk + kofB : p.wt;
+            cp_async16(b_dst + (uint32_t)((n >> 3) * 1024 + (n & 7) * 128) + (((uint32_t)cB ^ (uint32_t)(n & 7)) << 4), src,
+                       ok ? 16u : 0u);
+          }
+        }
+        cp_async_arrive(bar_full + 8 * slot);   // fires when this thread's copies of the stage have landed
       }
-      const int nx = it + S - 1;
-      if (nx < nstages) issue_stage(nx);
-      cp_async_commit();
     }
     cp_async_wait<0>();
-    gstage += (uint32_t)nstages;
-
-    // ---- epilogue: warp w reads TMEM lanes 32*(w&3).., columns [HC*(w>>2), +HC) ----
-    float acc[HC];
-    const int c0 = HC * half;
-    if (nstages > 0) {
-      mbar_wait(bar_accum, accum_uses & 1);
-      ++accum_uses;
+  } else if (warp == kMmaWarp) {
+    // =========================== MMA ISSUER (one lane) ===========================
+    const uint32_t idesc = make_idesc_tf32(NPAD);
+    uint32_t gs = 0;
+    int n_acc = 0;   // tiles that actually accumulate (both sides count the same way)
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int nstages = tile_stages(tile_nact(tile));
+      if (nstages == 0) continue;   // nothing to accumulate: the epilogue uses zeros
+      const int b = n_acc & 1;
+      mbar_wait(bar_acce + 8 * b, ((n_acc >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+      ++n_acc;
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0;
+      const uint32_t tacc = tmem_base + (uint32_t)(b * NPAD);
+      for (int it = 0; it < nstages; ++it, ++gs) {
+        const uint32_t slot = gs % S;
+        mbar_wait(bar_full + 8 * slot, (gs / S) & 1);
+        fence_proxy_async();
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t adesc = make_smem_desc(sA_u + slot * kAStageBytes);
+          const uint64_t bdesc = make_smem_desc(sB_u + slot * kBStageBytes);
 #pragma unroll
-      for (int cb = 0; cb < HC / 8; ++cb) tmem_ld8(taddr + cb * 8, acc + cb * 8);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    } else {
-#pragma unroll
-      for (int c = 0; c < HC; ++c) acc[c] = 0.f;
-    }
-    if (row_ok && c0 < a.cout) {
-#pragma unroll
-      for (int c = 0; c < HC; ++c) {
-        float v = acc[c];
-        if (a.shift) v += __ldg(a.shift + c0 + c);
-        if (a.res) v += __ldg(a.res + (int64_t)row * a.res_ld + c0 + c);
-        if (a.relu) v = fmaxf(v, 0.f);
-        acc[c] = v;
+          for (int j = 0; j < 4; ++j)  // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle atom
+            umma_tf32(tacc, adesc + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (it | j) ? 1u : 0u);
+          umma_commit(bar_empty + 8 * slot);
+          if (it == nstages - 1) umma_commit(bar_accf + 8 * b);
+        }
+        __syncwarp();
       }
-      if (a.head_out) {  // cout == 8: all eight channels sit in the half == 0 thread
+    }
+  } else {
+    // =========================== EPILOGUE (4 warps = 128 TMEM lanes) ===========================
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int r = q * 32 + lane;
+    int n_acc = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int nstages = tile_stages(tile_nact(tile));
+      const int b = n_acc & 1;
+      const int row = tile * kTileM + r;
+      const bool row_ok = row < n_out;
+      float acc[NPAD];
+      if (nstages > 0) {
+        mbar_wait(bar_accf + 8 * b, (n_acc >> 1) & 1);
+        ++n_acc;
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * NPAD);
+#pragma unroll
+        for (int cb = 0; cb < NPAD / 8; ++cb) tmem_ld8(taddr + cb * 8, acc + cb * 8);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(bar_acce + 8 * b);      // accumulator may be overwritten by the tile after next
+      } else {
+#pragma unroll
+        for (int c = 0; c < NPAD; ++c) acc[c] = 0.f;
+      }
+      if (!row_ok) continue;
+      const int cout = a.cout;
+#pragma unroll
+      for (int c = 0; c < NPAD; ++c)
+        if (c < cout) {
+          float v = acc[c];
+          if (a.shift) v += __ldg(a.shift + c);
+          if (a.res) v += __ldg(a.res + (int64_t)row * a.res_ld + c);
+          if (a.relu) v = fmaxf(v, 0.f);
+          acc[c] = v;
+        }
+      if (a.head_out) {
         float s = a.head_b;
 #pragma unroll
         for (int c = 0; c < 8; ++c) s = fmaf(acc[c], __ldg(a.head_w + c), s);
         a.head_out[row] = s;
       }
       if (a.out) {
-        float* o = a.out + (int64_t)row * a.out_ld + c0;
+        float* o = a.out + (int64_t)row * a.out_ld;
 #pragma unroll
-        for (int c = 0; c < HC; c += 4) {
-          float4 v = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
-          if (p.round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
-          *reinterpret_cast<float4*>(o + c) = v;
-        }
+        for (int c = 0; c < NPAD; c += 4)
+          if (c < cout) {
+            float4 v = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+            if (p.round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+            *reinterpret_cast<float4*>(o + c) = v;
+          }
       }
     }
-    // the next tile's first MMA overwrites the accumulator and its prologue overwrites sidx:
-    // order both after this tile's TMEM reads / smem reads
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
   }
 
+  tc_fence_before();
   __syncthreads();
-  if (warp == 0)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols)
+  if (warp == kMmaWarp)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols)
                  : "memory");
 }
 
 template <int NPAD, int GPC>
 static int launch_umma(const sps_conv_args& a, const UmmaParams& p, cudaStream_t st) {
-  const size_t smem = kStages * (kAStageBytes + NPAD * 128) + (size_t)kMaxK * kTileM * 4 + 8 * (kStages + 1) + 4 + 16 +
-                      128 + 16;
+  const size_t smem = UmmaCfg<NPAD>::smem;
   static bool attr_set = false;
   if (!attr_set) {
     SPS_CUDA_CHECK(
@@ -363,14 +396,36 @@ static int launch_umma(const sps_conv_args& a, const UmmaParams& p, cudaStream_t
   }
   int64_t tiles = (a.n_out_max + kTileM - 1) / kTileM;
   if (tiles < 1) tiles = 1;
-  const int grid = (int)(tiles < 148 * 2 ? tiles : 148 * 2);
-  k_conv_umma<NPAD, GPC><<<grid, kUmmaThreads, smem, st>>>(a, p);
+  const int grid = (int)(tiles < 148 ? tiles : 148);
+  k_conv_umma<NPAD, GPC><<<grid, kCtaThreads, smem, st>>>(a, p);
   SPS_CUDA_CHECK(cudaGetLastError());
   return SPS_OK;
 }
 
+// Per-tile (128 consecutive output rows) bitmask of the kernel offsets that have at least one
+// neighbour in the tile: masks[tile][4] (bits 0..K-1 over the first 3 words).
+__global__ void __launch_bounds__(128)
+k_tile_masks(const int32_t* __restrict__ map, int64_t ld, int K, const int32_t* __restrict__ n_ptr,
+             uint32_t* __restrict__ masks) {
+  const int n = *n_ptr;
+  const int ntiles = (n + kTileM - 1) / kTileM;
+  __shared__ uint32_t m[4];
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (threadIdx.x < 4) m[threadIdx.x] = 0;
+    __syncthreads();
+    const int row = tile * kTileM + threadIdx.x;
+    for (int k = 0; k < K; ++k) {
+      const bool hit = row < n && __ldg(map + (int64_t)k * ld + row) >= 0;
+      if (__any_sync(0xffffffffu, hit) && (threadIdx.x & 31) == 0) atomicOr(&m[k >> 5], 1u << (k & 31));
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) masks[4 * tile + threadIdx.x] = m[threadIdx.x];
+    __syncthreads();
+  }
+}
+
 bool conv_umma_supports(const sps_conv_args& a) {
-  if (a.mode != SPS_CONV_NBR || !a.map || !a.weight_kmajor) return false;
+  if (a.mode != SPS_CONV_NBR || !a.map || !a.weight_kmajor || !a.tile_mask) return false;
   if (a.K < 1 || a.K > kMaxK) return false;
   if (a.cin < 4 || (a.cin & 3) || (a.in_ld & 3)) return false;
   if (a.in2 && ((a.cin2 & 3) || (a.in2_ld & 3))) return false;
@@ -402,6 +457,17 @@ int conv_umma(const sps_conv_args& a, cudaStream_t st) {
 }
 
 }  // namespace sps
+
+extern "C" int sps_kernel_map_tile_masks(const int32_t* d_map, int64_t map_ld, int K, const int32_t* d_n_out,
+                                         int64_t n_out_max, uint32_t* d_masks, void* stream) {
+  if (!d_map || !d_n_out || !d_masks || K < 1 || K > sps::kMaxK || n_out_max < 0) return SPS_ERR_BAD_ARG;
+  int64_t tiles = (n_out_max + sps::kTileM - 1) / sps::kTileM;
+  if (tiles < 1) tiles = 1;
+  const int grid = (int)(tiles < 148 * 16 ? tiles : 148 * 16);
+  sps::k_tile_masks<<<grid, 128, 0, (cudaStream_t)stream>>>(d_map, map_ld, K, d_n_out, d_masks);
+  SPS_CUDA_CHECK(cudaGetLastError());
+  return SPS_OK;
+}
 
 // Host helper: ME-layout weights [K][cin][cout] (+ optional 1x1 term [cin2][cout]) -> K-major
 // [cout][ld]: row n holds, for every kernel offset k, padded_groups(cin)*4 floats (channels of

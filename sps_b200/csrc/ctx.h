@@ -33,6 +33,7 @@ struct sps_ctx {
   int32_t* child[SPS_NUM_LEVELS] = {};         // [L] [8][ld] children of level-L rows (L = 1..4)
   int32_t* nbr3[SPS_NUM_LEVELS] = {};          // [81][ld]
   int32_t* nbr5 = nullptr;                     // [125][ld]
+  uint32_t* tmask3[SPS_NUM_LEVELS] = {};       // [L] [tiles][4] present-offset masks of nbr3 per 128-row tile
 
   // feature buffers (fp32, row-major, upper bound max_points rows)
   enum Buf { CAT8, E1, H1, CAT7, E2, H2, CAT6, E3, H3, CAT5, E4, H4, B4, H5, B5, H6, B6, H7, B7, H8,

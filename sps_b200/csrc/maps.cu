@@ -433,6 +433,7 @@ extern "C" int sps_build_maps(sps_ctx* ctx, void* stream_) {
   prof_mark("kmap5.L0", st);
   k_kernel_map_blk<3, 3><<<grid_for(3 * n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->table, ctx->cells, 0,
                                                                 ctx->nbr3[0], ctx->ld);
+  sps_kernel_map_tile_masks(ctx->nbr3[0], ctx->ld, 81, ctx->counts + 0, n, ctx->tmask3[0], st);
   prof_mark("kmap3.L0", st);
   for (int L = 1; L < SPS_NUM_LEVELS; ++L) {
     const int32_t* n_fine = ctx->counts + (L - 1);
@@ -450,6 +451,7 @@ extern "C" int sps_build_maps(sps_ctx* ctx, void* stream_) {
     prof_mark(nm_s[L], st);
     k_kernel_map_blk<3, 3><<<grid_for(3 * n, 256), 256, 0, st>>>(ctx->keys[L], ctx->counts + L, ctx->table, ctx->cells, L,
                                                                   ctx->nbr3[L], ctx->ld);
+    sps_kernel_map_tile_masks(ctx->nbr3[L], ctx->ld, 81, ctx->counts + L, n, ctx->tmask3[L], st);
     prof_mark(nm_k[L], st);
   }
   SPS_CUDA_CHECK(cudaGetLastError());

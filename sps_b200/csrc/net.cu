@@ -219,7 +219,7 @@ __global__ void k_devox_sigmoid(const float* __restrict__ logits, const int32_t*
 
 static int g_forward_launches = 0;
 
-static int run_conv(const char* name, const ConvW& w, int mode, const int32_t* map, int64_t map_ld, const int32_t* n_out,
+static int run_conv(const uint32_t* tmask, const char* name, const ConvW& w, int mode, const int32_t* map, int64_t map_ld, const int32_t* n_out,
                     int64_t n_out_max, const float* in, int64_t in_ld, const float* in2, int64_t in2_ld,
                     const float* res, int64_t res_ld, float* out, int64_t out_ld, cudaStream_t st,
                     const float* head_w = nullptr, float head_b = 0.f, float* head_out = nullptr) {
@@ -231,7 +231,7 @@ static int run_conv(const char* name, const ConvW& w, int mode, const int32_t* m
   if (in2) { a.in2 = in2; a.in2_ld = in2_ld; a.cin2 = w.cin2; a.weight2 = w.w2; }
   a.res = res; a.res_ld = res_ld; a.relu = 1; a.out = out; a.out_ld = out_ld;
   a.head_w = head_w; a.head_b = head_b; a.head_out = head_out;
-  a.weight_kmajor = w.wt; a.kmajor_ld = w.ldk;
+  a.weight_kmajor = w.wt; a.kmajor_ld = w.ldk; a.tile_mask = tmask;
   a.round_out = conv_backend() != 1;   // pure fp32 mode keeps full-precision activations
   ++g_forward_launches;
   const int rc = conv_dispatch(a, st);
@@ -257,7 +257,8 @@ int unet_forward(sps_ctx* c, const sps_net* net, const float* feat0, float* logi
   static const char* nm_c2[8] = {"block1.conv2", "block2.conv2", "block3.conv2", "block4.conv2",
                                  "block5.conv2", "block6.conv2", "block7.conv2", "block8.conv2+final"};
   int rc;
-#define RUN(...) do { rc = run_conv(__VA_ARGS__); if (rc != SPS_OK) return rc; } while (0)
+#define RUN(...) do { rc = run_conv(nullptr, __VA_ARGS__); if (rc != SPS_OK) return rc; } while (0)
+#define RUN3(L_, ...) do { rc = run_conv(c->tmask3[L_], __VA_ARGS__); if (rc != SPS_OK) return rc; } while (0)
   // conv0p1s1 + bn0 + relu  (minkunet.py:162-164)
   RUN("conv0", net->conv0, SPS_CONV_NBR, c->nbr5, ld, c->counts + 0, nmax, feat0, 1, nullptr, 0, nullptr, 0, skip[0],
       skip_ld[0], st);
@@ -269,13 +270,13 @@ int unet_forward(sps_ctx* c, const sps_net* net, const float* feat0, float* logi
         0, E[i], cw, st);
     const ConvW& c1 = net->blk1[i];
     const ConvW& c2 = net->blk2[i];
-    RUN(nm_c1[i], c1, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, E[i], cw, nullptr, 0, nullptr, 0, H[i], c1.cout, st);
+    RUN3(L, nm_c1[i], c1, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, E[i], cw, nullptr, 0, nullptr, 0, H[i], c1.cout, st);
     float* out = (L < 4) ? skip[L] : B[C::B4];
     const int out_ld = (L < 4) ? skip_ld[L] : 64;
     if (c2.cin2)
-      RUN(nm_c2[i], c2, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, H[i], c1.cout, E[i], cw, nullptr, 0, out, out_ld, st);
+      RUN3(L, nm_c2[i], c2, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, H[i], c1.cout, E[i], cw, nullptr, 0, out, out_ld, st);
     else
-      RUN(nm_c2[i], c2, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, H[i], c1.cout, nullptr, 0, E[i], cw, out, out_ld, st);
+      RUN3(L, nm_c2[i], c2, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, H[i], c1.cout, nullptr, 0, E[i], cw, out, out_ld, st);
   }
   // decoder (minkunet.py:188-217)
   float* dec_in = B[C::B4];
@@ -288,20 +289,21 @@ int unet_forward(sps_ctx* c, const sps_net* net, const float* feat0, float* logi
         cat[L], skip_ld[L], st);
     const ConvW& c1 = net->blk1[4 + i];
     const ConvW& c2 = net->blk2[4 + i];
-    RUN(nm_c1[4 + i], c1, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, cat[L], skip_ld[L], nullptr, 0, nullptr, 0, Hd[i],
+    RUN3(L, nm_c1[4 + i], c1, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, cat[L], skip_ld[L], nullptr, 0, nullptr, 0, Hd[i],
         c1.cout, st);
     if (i < 3) {
-      RUN(nm_c2[4 + i], c2, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, Hd[i], c1.cout, cat[L], skip_ld[L], nullptr, 0,
+      RUN3(L, nm_c2[4 + i], c2, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, Hd[i], c1.cout, cat[L], skip_ld[L], nullptr, 0,
           Bd[i], c2.cout, st);
       dec_in = Bd[i];
       dec_in_ld = c2.cout;
     } else {
       // block8.conv2 + norm2 + downsample + relu, with `final` (8->1, bias; minkunet.py:219) fused
-      RUN(nm_c2[4 + i], c2, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, Hd[i], c1.cout, cat[L], skip_ld[L], nullptr, 0,
+      RUN3(L, nm_c2[4 + i], c2, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, Hd[i], c1.cout, cat[L], skip_ld[L], nullptr, 0,
           nullptr, 0, st, net->head_w, net->head_b, logits);
     }
   }
 #undef RUN
+#undef RUN3
   return SPS_OK;
 }
 
@@ -356,7 +358,7 @@ int forward_impl(sps_ctx* ctx, const sps_net* net, const float* d_points, int64_
   rc = sps_devox_sigmoid(ctx->buf[sps_ctx::LOGITS], ctx->inv, n_scores, d_scores, st);
   if (rc != SPS_OK) return rc;
   prof_mark("devox_sigmoid", st);
-  g_forward_launches += 5 + 51 + 1 + 1;  // voxelize, maps, feature fill, devox
+  g_forward_launches += 5 + 56 + 1 + 1;  // voxelize, maps, feature fill, devox
   return SPS_OK;
 }
 }  // namespace sps
