@@ -23,7 +23,7 @@ def _digest() -> str:
         if os.path.exists(path):
             with open(path, "rb") as fh:
                 h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update((" ".join(NVCC_FLAGS) + os.environ.get("SPS_NVCC_EXTRA", "")).encode())
     return h.hexdigest()
 
 
@@ -34,7 +34,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     srcs = [os.path.join(CSRC, f) for f in SOURCES if os.path.exists(os.path.join(CSRC, f))]
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + srcs
+    extra = os.environ.get("SPS_NVCC_EXTRA", "").split()
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", LIB] + srcs
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -133,7 +133,13 @@ constexpr int kCtaThreads = kProducerThreads + 32 + 128;
 
 template <int NPAD>
 struct UmmaCfg {
-  static constexpr int S = NPAD == 64 ? 5 : 6;        // ring depth
+#ifndef SPS_S64
+#define SPS_S64 5
+#endif
+#ifndef SPS_S32
+#define SPS_S32 6
+#endif
+  static constexpr int S = NPAD == 64 ? SPS_S64 : SPS_S32;        // ring depth
   static constexpr int kBStage = NPAD * 128;
   static constexpr int kTmemCols = 2 * NPAD < 32 ? 32 : 2 * NPAD;   // two accumulators (double buffered)
   static constexpr size_t smem = (size_t)S * (kAStageBytes + kBStage) + 2 * (size_t)kMaxK * kTileM * 4 +
@@ -234,7 +240,47 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_conv_umma(const sps_conv_arg
       cp_async_arrive(bar_idx + 8 * par);
     };
 
-    uint32_t gs = 0;  // global stage counter (ring slot + phase)
+    // ---- per-thread invariants of the stage writer (kept out of the stage loop: the producers are
+    //      issue-bound, every instruction here is paid once per stage per warp) ----
+    constexpr int NB = (NPAD + 31) / 32;            // weight chunks per thread per stage
+    const float* wrow[NB];
+    uint32_t b_off[NB];
+    bool wok[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      const int n = r0 + 32 * i;
+      wok[i] = n < a.cout && (NPAD >= 32 || n < NPAD);
+      wrow[i] = p.wt + (int64_t)(wok[i] ? n : 0) * p.ldk;
+      b_off[i] = (uint32_t)((n >> 3) * 1024 + (n & 7) * 128) + (((uint32_t)cB ^ (uint32_t)(n & 7)) << 4);
+    }
+    const bool b_lane = NPAD >= 32 || r0 < NPAD;    // NPAD = 16: only half of the threads carry a weight chunk
+    uint32_t slot = 0, phase = 0;
+    uint32_t a_slot = sA_u + a_off, b_slot = sB_u, bar_e = bar_empty, bar_f = bar_full;
+
+    // write this thread's share of one stage: 4 A chunks (rows r0+32i, column cB) + its weight chunk(s)
+    auto emit = [&](const char* base, uint32_t ld_b, const int (&idx)[4], uint32_t cg_off, bool cg_ok, int kofB) {
+      mbar_wait(bar_e, phase ^ 1);                  // the MMAs that read this slot have completed
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool ok = cg_ok && idx[i] >= 0;
+        cp_async16(a_slot + i * 4096, base + (ok ? (uint32_t)idx[i] * ld_b + cg_off : 0u), ok ? 16u : 0u);
+      }
+      if (b_lane) {
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+          const bool ok = kofB >= 0 && wok[i];
+          cp_async16(b_slot + b_off[i], ok ? wrow[i] + kofB : p.wt, ok ? 16u : 0u);
+        }
+      }
+      cp_async_arrive(bar_f);                       // fires when this thread's copies of the stage have landed
+      if (++slot == S) {
+        slot = 0; phase ^= 1;
+        a_slot = sA_u + a_off; b_slot = sB_u; bar_e = bar_empty; bar_f = bar_full;
+      } else {
+        a_slot += kAStageBytes; b_slot += kBStageBytes; bar_e += 8; bar_f += 8;
+      }
+    };
+
     int it_tile = 0;
     if ((int)blockIdx.x < ntiles) prepare(blockIdx.x, 0);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it_tile) {
@@ -242,54 +288,43 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_conv_umma(const sps_conv_arg
       const int next = tile + gridDim.x;
       if (next < ntiles) prepare(next, par ^ 1);   // one tile ahead: its latency hides behind this tile's gathers
       const int nact = tile_nact(tile);
-      const int nst_map = GPC < 8 ? (nact + EPS - 1) / EPS : nact * SPE;
-      const int nstages = nst_map + st2;
       mbar_wait(bar_idx + 8 * par, (it_tile >> 1) & 1);
       const int32_t* sx = sidx + par * kMaxK * kTileM + r0;   // [e][128] compacted by present offset
       const uint8_t* kl = klist + par * 96;
-      for (int st = 0; st < nstages; ++st, ++gs) {
-        const uint32_t slot = gs % S, use = gs / S;
-        mbar_wait(bar_empty + 8 * slot, (use & 1) ^ 1);  // MMAs that read this slot have completed
-        const uint32_t a_dst = sA_u + slot * kAStageBytes + a_off;
-        const uint32_t b_dst = sB_u + slot * kBStageBytes;
-        int64_t kofB = -1;  // float offset of this thread's weight chunk inside a K-major row
-        if (st < nst_map) {
-          int e, cg;
-          if (GPC < 8) { e = st * EPS + cB / GPC; cg = cB % GPC; }
-          else { e = st / SPE; cg = (st - e * SPE) * 8 + cB; }
+      int idx[4];
+      if (GPC < 8) {
+        // small Cin: EPS offsets per stage, GPC chunks each; this thread's chunk column picks offset e_off
+        constexpr int GPCc = GPC < 8 ? GPC : 1;
+        const int e_off = cB / GPCc, cg = cB % GPCc;
+        const bool cg_ok = cg < gpk;
+        const int nst_map = (nact + EPS - 1) / EPS;
+        for (int st = 0, e = e_off; st < nst_map; ++st, e += EPS) {
           const bool e_ok = e < nact;
-          if (e_ok) kofB = ((int64_t)kl[e] * GP + cg) * 4;
-          const bool cg_ok = e_ok && cg < gpk;
           const int32_t* sk = sx + (e_ok ? e : 0) * kTileM;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int idx = cg_ok ? sk[32 * i] : -1;
-            const char* src = in_b + (idx >= 0 ? (uint32_t)idx * in_ld_b + (uint32_t)cg * 16u : 0u);
-            cp_async16(a_dst + i * 4096, src, idx >= 0 ? 16u : 0u);
-          }
-        } else {  // fused 1x1 term: identity gather from in2
-          const int cg = (st - nst_map) * 8 + cB;
-          const bool cg_ok = cg < gpk2;
-          if (cg_ok) kofB = ((int64_t)K * GP + cg) * 4;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rw = tile * kTileM + r0 + 32 * i;
-            const bool ok = cg_ok && rw < n_out;
-            const char* src = ok ? in2_b + (uint32_t)rw * in2_ld_b + (uint32_t)cg * 16u : in_b;
-            cp_async16(a_dst + i * 4096, src, ok ? 16u : 0u);
-          }
+          for (int i = 0; i < 4; ++i) idx[i] = e_ok ? sk[32 * i] : -1;
+          emit(in_b, in_ld_b, idx, (uint32_t)cg * 16u, cg_ok, e_ok ? ((int)kl[e] * GPCc + cg) * 4 : -1);
         }
+      } else {
+        // large Cin: one offset per SPE stages, the neighbour rows are looked up once per offset
+        for (int e = 0; e < nact; ++e) {
+          const int32_t* sk = sx + e * kTileM;
 #pragma unroll
-        for (int i = 0; i < (NPAD + 31) / 32; ++i) {
-          const int n = r0 + 32 * i;
-          if (NPAD >= 32 || n < NPAD) {
-            const bool ok = kofB >= 0 && n < a.cout;
-            const float* src = ok ? p.wt + (int64_t)n * p.ldk + kofB : p.wt;
-            cp_async16(b_dst + (uint32_t)((n >> 3) * 1024 + (n & 7) * 128) + (((uint32_t)cB ^ (uint32_t)(n & 7)) << 4), src,
-                       ok ? 16u : 0u);
-          }
+          for (int i = 0; i < 4; ++i) idx[i] = sk[32 * i];
+          const int kbase = (int)kl[e] * GP;
+          for (int sub = 0, cg = cB; sub < SPE; ++sub, cg += 8)
+            emit(in_b, in_ld_b, idx, (uint32_t)cg * 16u, cg < gpk, (kbase + cg) * 4);
         }
-        cp_async_arrive(bar_full + 8 * slot);   // fires when this thread's copies of the stage have landed
+      }
+      if (st2 > 0) {  // fused 1x1 term: identity gather from in2
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rw = tile * kTileM + r0 + 32 * i;
+          idx[i] = rw < n_out ? rw : -1;
+        }
+        const int kbase2 = K * GP;
+        for (int s2 = 0, cg = cB; s2 < st2; ++s2, cg += 8)
+          emit(in2_b, in2_ld_b, idx, (uint32_t)cg * 16u, cg < gpk2, cg < gpk2 ? (kbase2 + cg) * 4 : -1);
       }
     }
     cp_async_wait<0>();
