@@ -197,6 +197,10 @@ int sps_infer_scan(sps_ctx* ctx, const sps_net* net, const sps_map* map, const f
  * the layer shape allows, fp32 CUDA-core otherwise), 1 = fp32 CUDA-core only, 2 = tcgen05 only
  * (SPS_ERR_UNSUPPORTED for shapes it does not take). */
 int sps_set_conv_backend(int backend);
+/* 1: wide layers (Cin >= 24) gather through TMA `tile::gather4` (conv_umma_tma.cu); default 0 =
+ * the cp.async producer kernel everywhere.  The TMA variant is parity-clean but measured ~3x
+ * slower (128-byte boxes are too small for the TMA engine), kept for A/B measurements. */
+int sps_set_tma_gather(int on);
 /* Per-tile present-offset bitmasks of a kernel map (K <= 81) for the tensor-core path:
  * d_masks uint32 [ceil(n_out_max/128)][4]. */
 int sps_kernel_map_tile_masks(const int32_t* d_map, int64_t map_ld, int K, const int32_t* d_n_out,

@@ -26,109 +26,21 @@
 //     TF32-rounded so the next layer's operand rounding is nearest, not truncation).
 // Operands are TF32 (fp32 storage), accumulation fp32: ~1e-4 score error on the reference
 // network against the 2e-3 budget; bf16 operands measured 6e-4..2e-2 (DESIGN.md "precision").
-#include <cstring>
-#include "common.cuh"
+#include "umma_common.cuh"
 
 namespace sps {
 
-constexpr int kTileM = 128;
-constexpr int kAStageBytes = kTileM * 128;  // 16 KB
-constexpr int kMaxK = 81;  // kernel volumes this kernel takes (neighbour indices are staged in smem)
+#ifndef SPS_PRODUCER_WARPS
+#define SPS_PRODUCER_WARPS 8
+#endif
+constexpr int kProducerWarps = SPS_PRODUCER_WARPS;    // 8 or 16
+__device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kProducerWarps * 32) : "memory"); }
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(bar), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// SM100 shared-memory matrix descriptor, K-major, SWIZZLE_128B: 8-row x 128-byte atoms, 1024 B
-// apart (SBO); LBO unused for swizzled K-major; version 1; layout type 2.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);  // start address   bits [0,14)
-  d |= (uint64_t)1 << 16;                   // LBO (ignored)   bits [16,30)
-  d |= (uint64_t)(1024 >> 4) << 32;         // SBO = 1024 B    bits [32,46)
-  d |= (uint64_t)1 << 46;                   // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                   // SWIZZLE_128B
-  return d;
-}
-// kind::tf32, fp32 accumulate, both operands K-major: c_format F32 (1<<4), a/b format TF32 (2),
-// N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
-  uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr));
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ float round_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-
-// groups (of 4 channels) reserved per kernel offset in the K-major weight matrix / the stage plan
-__host__ __device__ inline int padded_groups(int cin) {
-  const int g = (cin + 3) >> 2;
-  return g <= 2 ? 2 : g <= 4 ? 4 : (g + 7) & ~7;
-}
-
-struct UmmaParams {
-  const float* wt;  // [cout][ldk] K-major, TF32-rounded (layout: sps_conv_pack_kmajor)
-  int64_t ldk;
-  int round_out;
-};
-
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// arrive on `bar` once all cp.async issued so far by this thread have landed (no pending-count bump)
-__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-constexpr int kProducerThreads = 256;                 // warps 0-7: gather A/B, stage kernel-map slices
-constexpr int kMmaWarp = 8;                           // warp 8: tcgen05.mma issue
-// warps 9-12: epilogue (TMEM -> registers -> global)
+constexpr int kProducerThreads = kProducerWarps * 32;  // producer warps: gather A/B, stage kernel-map slices
+constexpr int kRowsPerThread = kTileM * 8 / kProducerThreads;   // A chunks per thread per stage (4 or 2)
+constexpr int kRowStep = kProducerThreads / 8;        // row distance between a thread's chunks
+constexpr int kMmaWarp = kProducerWarps;              // next warp: tcgen05.mma issue
+// the 4 warps after it: epilogue (TMEM -> registers -> global)
 constexpr int kCtaThreads = kProducerThreads + 32 + 128;
 
 template <int NPAD>
@@ -209,8 +121,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_conv_umma(const sps_conv_arg
     const uint32_t in_ld_b = (uint32_t)a.in_ld * 4u, in2_ld_b = (uint32_t)a.in2_ld * 4u;
     const char* in_b = reinterpret_cast<const char*>(a.in);
     const char* in2_b = reinterpret_cast<const char*>(a.in2);
-    const int r0 = tid >> 3, cB = tid & 7;      // gather: chunk column cB of rows r0 + 32*i
-    const int rI = tid & 127, hI = tid >> 7;    // kernel-map staging: row rI, every other offset
+    const int r0 = tid >> 3, cB = tid & 7;      // gather: chunk column cB of rows r0 + kRowStep*i
+    const int rI = tid & 127, hI = tid >> 7;    // kernel-map staging: row rI, offsets hI, hI + kProducerThreads/128, ...
     const uint32_t a_off = (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128) + (((uint32_t)cB ^ (uint32_t)(r0 & 7)) << 4);
 
     // stage the kernel-map slice of `tile` (only the offsets present in it) into parity buffer `par`
@@ -230,40 +142,40 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_conv_umma(const sps_conv_arg
       const uint32_t dst = sidx_u + (uint32_t)(par * kMaxK * kTileM + rI) * 4u;
       if (row < n_out) {
         const int32_t* src = a.map + row;
-        for (int e = hI; e < nact; e += 2)
+        for (int e = hI; e < nact; e += kProducerThreads / 128)
           asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (uint32_t)(e * kTileM) * 4u),
                        "l"(src + (int64_t)klist[par * 96 + e] * a.map_ld)
                        : "memory");
       } else {
-        for (int e = hI; e < nact; e += 2) sidx[(par * kMaxK + e) * kTileM + rI] = -1;  // rows past the end
+        for (int e = hI; e < nact; e += kProducerThreads / 128) sidx[(par * kMaxK + e) * kTileM + rI] = -1;  // rows past the end
       }
       cp_async_arrive(bar_idx + 8 * par);
     };
 
     // ---- per-thread invariants of the stage writer (kept out of the stage loop: the producers are
     //      issue-bound, every instruction here is paid once per stage per warp) ----
-    constexpr int NB = (NPAD + 31) / 32;            // weight chunks per thread per stage
+    constexpr int NB = (NPAD + kRowStep - 1) / kRowStep;   // weight chunks per thread per stage
     const float* wrow[NB];
     uint32_t b_off[NB];
     bool wok[NB];
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
-      const int n = r0 + 32 * i;
-      wok[i] = n < a.cout && (NPAD >= 32 || n < NPAD);
+      const int n = r0 + kRowStep * i;
+      wok[i] = n < a.cout && n < NPAD;
       wrow[i] = p.wt + (int64_t)(wok[i] ? n : 0) * p.ldk;
       b_off[i] = (uint32_t)((n >> 3) * 1024 + (n & 7) * 128) + (((uint32_t)cB ^ (uint32_t)(n & 7)) << 4);
     }
-    const bool b_lane = NPAD >= 32 || r0 < NPAD;    // NPAD = 16: only half of the threads carry a weight chunk
+    const bool b_lane = r0 < NPAD;                  // narrow layers: only some threads carry a weight chunk
     uint32_t slot = 0, phase = 0;
     uint32_t a_slot = sA_u + a_off, b_slot = sB_u, bar_e = bar_empty, bar_f = bar_full;
 
     // write this thread's share of one stage: 4 A chunks (rows r0+32i, column cB) + its weight chunk(s)
-    auto emit = [&](const char* base, uint32_t ld_b, const int (&idx)[4], uint32_t cg_off, bool cg_ok, int kofB) {
+    auto emit = [&](const char* base, uint32_t ld_b, const int (&idx)[kRowsPerThread], uint32_t cg_off, bool cg_ok, int kofB) {
       mbar_wait(bar_e, phase ^ 1);                  // the MMAs that read this slot have completed
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < kRowsPerThread; ++i) {
         const bool ok = cg_ok && idx[i] >= 0;
-        cp_async16(a_slot + i * 4096, base + (ok ? (uint32_t)idx[i] * ld_b + cg_off : 0u), ok ? 16u : 0u);
+        cp_async16(a_slot + i * (kRowStep * 128), base + (ok ? (uint32_t)idx[i] * ld_b + cg_off : 0u), ok ? 16u : 0u);
       }
       if (b_lane) {
 #pragma unroll
@@ -291,7 +203,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_conv_umma(const sps_conv_arg
       mbar_wait(bar_idx + 8 * par, (it_tile >> 1) & 1);
       const int32_t* sx = sidx + par * kMaxK * kTileM + r0;   // [e][128] compacted by present offset
       const uint8_t* kl = klist + par * 96;
-      int idx[4];
+      int idx[kRowsPerThread];
       if (GPC < 8) {
         // small Cin: EPS offsets per stage, GPC chunks each; this thread's chunk column picks offset e_off
         constexpr int GPCc = GPC < 8 ? GPC : 1;
@@ -302,7 +214,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_conv_umma(const sps_conv_arg
           const bool e_ok = e < nact;
           const int32_t* sk = sx + (e_ok ? e : 0) * kTileM;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) idx[i] = e_ok ? sk[32 * i] : -1;
+          for (int i = 0; i < kRowsPerThread; ++i) idx[i] = e_ok ? sk[kRowStep * i] : -1;
           emit(in_b, in_ld_b, idx, (uint32_t)cg * 16u, cg_ok, e_ok ? ((int)kl[e] * GPCc + cg) * 4 : -1);
         }
       } else {
@@ -310,7 +222,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_conv_umma(const sps_conv_arg
         for (int e = 0; e < nact; ++e) {
           const int32_t* sk = sx + e * kTileM;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) idx[i] = sk[32 * i];
+          for (int i = 0; i < kRowsPerThread; ++i) idx[i] = sk[kRowStep * i];
           const int kbase = (int)kl[e] * GP;
           for (int sub = 0, cg = cB; sub < SPE; ++sub, cg += 8)
             emit(in_b, in_ld_b, idx, (uint32_t)cg * 16u, cg < gpk, (kbase + cg) * 4);
@@ -318,8 +230,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_conv_umma(const sps_conv_arg
       }
       if (st2 > 0) {  // fused 1x1 term: identity gather from in2
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rw = tile * kTileM + r0 + 32 * i;
+        for (int i = 0; i < kRowsPerThread; ++i) {
+          const int rw = tile * kTileM + r0 + kRowStep * i;
           idx[i] = rw < n_out ? rw : -1;
         }
         const int kbase2 = K * GP;
@@ -477,11 +389,16 @@ static int launch_umma_n(const sps_conv_args& a, const UmmaParams& p, cudaStream
   return launch_umma<NPAD, 8>(a, p, st);
 }
 
+bool conv_umma_tma_supports(const sps_conv_args& a);
+int conv_umma_tma(const sps_conv_args& a, const UmmaParams& p, cudaStream_t st);
+static int g_use_tma = 0;   // 1: wide layers gather through TMA tile::gather4 (measured 3x slower than cp.async producers: 128-byte boxes)
+
 int conv_umma(const sps_conv_args& a, cudaStream_t st) {
   UmmaParams p;
   p.wt = a.weight_kmajor;
   p.ldk = a.kmajor_ld;
   p.round_out = a.round_out;
+  if (g_use_tma && conv_umma_tma_supports(a)) return conv_umma_tma(a, p, st);
   switch (a.cout) {
     case 8:
     case 16: return launch_umma_n<16>(a, p, st);
@@ -492,6 +409,11 @@ int conv_umma(const sps_conv_args& a, cudaStream_t st) {
 }
 
 }  // namespace sps
+
+extern "C" int sps_set_tma_gather(int on) {
+  sps::g_use_tma = on != 0;
+  return SPS_OK;
+}
 
 extern "C" int sps_kernel_map_tile_masks(const int32_t* d_map, int64_t map_ld, int K, const int32_t* d_n_out,
                                          int64_t n_out_max, uint32_t* d_masks, void* stream) {
