@@ -95,11 +95,14 @@ def load_peaks():
     return {"hbm": 6650.0, "tensor": 1400.0, "src": "fallback"}
 
 
-def stage_accounting(engine, n_points):
+def stage_accounting(engine, points):
     """Algorithmic bytes / FLOPs per stage of ONE forward (SURVEY.md §8d formulas; fp32 activations)."""
     lib, h = engine.lib, engine.handle
     import ctypes as C
     from sps_b200.engine import _stream
+    n_points = len(points)
+    engine.voxelize(points, VOXEL)      # explicit (un-fused) map build so that every table can be counted
+    engine.build_maps()
 
     def pairs(level, kind):
         out = C.c_int64()
@@ -123,6 +126,7 @@ def stage_accounting(engine, n_points):
                      "flops": 2 * npairs * cin * cout + extra_flops}
     P = (8, 16, 32, 64, 64, 32, 16, 8)
     conv("conv0", V[0], V[0], 125, P5, 1, 8)
+    acc["conv0+kmap5"] = {"bytes": V[0] * 20 + 4 * V[0] + 32 * V[0], "flops": 2 * P5 * 8}
     c = 8
     for i in range(4):
         L = i + 1
@@ -345,7 +349,7 @@ def main():
     if rank == 0:
         peaks = load_peaks()
         stage_ms = profile_pass(engine, net, dev, min(args.steps, 5))
-        acc, V, P3, P5 = stage_accounting(engine, len(dev[(min(args.steps, 5) - 1) % len(dev)]))
+        acc, V, P3, P5 = stage_accounting(engine, dev[(min(args.steps, 5) - 1) % len(dev)])
         roof, rows = roofline_from(stage_ms, acc, peaks)
         result["roofline"] = roof
         result["stages"] = rows

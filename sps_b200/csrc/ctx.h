@@ -6,7 +6,7 @@ struct sps_ctx {
   int64_t max_points = 0;
   int64_t ld = 0;            // leading dimension of the [K][ld] map tables (multiple of 32)
   int64_t n = 0;             // rows of the last voxelize call
-  bool have_l0 = false, have_maps = false;
+  bool have_l0 = false, have_maps = false, have_nbr5 = false;
 
   char* base = nullptr;
   size_t bytes = 0;
@@ -42,6 +42,10 @@ struct sps_ctx {
 };
 
 namespace sps {
+// conv0 fused into the map-building pass (level-0 block table still alive): see maps.cu
+struct Conv0Fused {
+  const float* feat; const float* w; const float* shift; int round_out; float* out; int64_t out_ld;
+};
 constexpr int kBufWidth[sps_ctx::NBUF] = {16, 8, 8, 24, 8, 16, 48, 16, 32, 96, 32, 64, 64, 64, 64, 32, 32,
                                           16, 16, 8, 1, 1};
 constexpr int kScanBlock = 1024;

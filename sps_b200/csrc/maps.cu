@@ -324,6 +324,83 @@ k_kernel_map_blk(const unsigned long long* __restrict__ keys, const int32_t* __r
   }
 }
 
+// conv0p1s1 (5x5x5x1, Cin = 1 -> 8; minkunet.py:55-62,162-164) fused with its kernel-map probes:
+// out[o] = relu( sum_k feat[nbr5(k, o)] * W[k][:] + shift ), the 125 neighbours resolved through the
+// block table on the fly, so the 125 x V index table is neither written nor read back.
+__global__ void __launch_bounds__(256)
+k_conv0_blk(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr,
+            const Slot* __restrict__ tab, const int32_t* __restrict__ cells, const float* __restrict__ feat,
+            const float* __restrict__ w, const float* __restrict__ shift, int round_out, float* __restrict__ out,
+            int64_t out_ld) {
+  __shared__ float w_s[125 * 8];
+  for (int i = threadIdx.x; i < 125 * 8; i += blockDim.x) w_s[i] = __ldg(w + i);
+  __syncthreads();
+  const int n = *n_ptr;
+  if (n == 0) return;
+  const uint32_t mask = table_capacity(n) - 1;
+  const int xlim = 1 << kXBits, zlim = 1 << kZBits;
+  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += gridDim.x * blockDim.x) {
+    const unsigned long long key = keys[o];
+    const int cx = (int)((key >> kXShift) & ((1u << kXBits) - 1));
+    const int cy = (int)((key >> kYShift) & ((1u << kYBits) - 1));
+    const int cz = (int)((key >> kZShift) & ((1u << kZBits) - 1));
+    const unsigned long long bt = key & ((0xFFull << kBShift) | ((1ull << kTBits) - 1));
+    unsigned long long cached_key = kEmptyKey;
+    const int32_t* cached = nullptr;
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+#pragma unroll 1
+    for (int dz = -2; dz <= 2; ++dz) {
+      const int nz = cz + dz;
+      const bool zok = (unsigned)nz < (unsigned)zlim;
+#pragma unroll 1
+      for (int dy = -2; dy <= 2; ++dy) {
+        const int ny = cy + dy;
+        const bool yok = zok && (unsigned)ny < (unsigned)xlim;
+        const unsigned long long byz = bt | ((unsigned long long)(unsigned)((ny >> 2) << 2) << kYShift) |
+                                       ((unsigned long long)(unsigned)((nz >> 2) << 2) << kZShift);
+        const int lyz = 4 * (ny & 3) + 16 * (nz & 3);
+        const float* wk = w_s + ((dy + 2) * 5 + (dz + 2) * 25) * 8;
+#pragma unroll
+        for (int dx = -2; dx <= 2; ++dx) {
+          const int nx = cx + dx;
+          if (!(yok && (unsigned)nx < (unsigned)xlim)) continue;
+          const unsigned long long bkey = byz | ((unsigned long long)(unsigned)((nx >> 2) << 2) << kXShift);
+          if (bkey != cached_key) {
+            cached_key = bkey;
+            const int id = table_find(tab, mask, bkey);
+            cached = id >= 0 ? cells + (int64_t)id * 64 : nullptr;
+          }
+          if (!cached) continue;
+          const int idx = __ldg(cached + lyz + (nx & 3));
+          if (idx < 0) continue;
+          const float x = __ldg(feat + idx);
+          const float4 w0 = *reinterpret_cast<const float4*>(wk + (dx + 2) * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(wk + (dx + 2) * 8 + 4);
+          acc[0] = fmaf(x, w0.x, acc[0]); acc[1] = fmaf(x, w0.y, acc[1]);
+          acc[2] = fmaf(x, w0.z, acc[2]); acc[3] = fmaf(x, w0.w, acc[3]);
+          acc[4] = fmaf(x, w1.x, acc[4]); acc[5] = fmaf(x, w1.y, acc[5]);
+          acc[6] = fmaf(x, w1.z, acc[6]); acc[7] = fmaf(x, w1.w, acc[7]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float v = fmaxf(acc[c] + __ldg(shift + c), 0.f);
+      if (round_out) {
+        uint32_t r;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+        v = __uint_as_float(r);
+      }
+      acc[c] = v;
+    }
+    float* op = out + (int64_t)o * out_ld;
+    *reinterpret_cast<float4*>(op) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(op + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+}
+
 // Kernel map for an odd hyper-cube kernel (k0,k1,k2,k3) on tensor stride [2^log2s]*3 + [1]:
 // nbr[k][o] = row of (out[o] + delta_k) in the same coordinate set, k = i0 + k0*(i1 + k1*(i2 + k2*i3)),
 // delta_d = (i_d - k_d/2) * stride_d.  One independent hash probe per thread, o fastest so the
@@ -410,10 +487,18 @@ extern "C" int sps_voxelize(sps_ctx* ctx, const float* d_points, int64_t n, int6
   return voxelize_impl(ctx, d_points, n, nullptr, ld_points, voxel_size, (cudaStream_t)stream_);
 }
 
+namespace sps {
+int build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st);
+}
 extern "C" int sps_build_maps(sps_ctx* ctx, void* stream_) {
+  return build_maps_impl(ctx, nullptr, (cudaStream_t)stream_);
+}
+
+// c0 != nullptr: the fused forward -- conv0 runs here, straight off the level-0 block table, and the
+// 5x5x5x1 index table is not materialised.
+int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
   if (!ctx) return SPS_ERR_BAD_ARG;
   if (!ctx->have_l0) return SPS_ERR_STATE;
-  cudaStream_t st = (cudaStream_t)stream_;
   const int64_t n = ctx->n > 0 ? ctx->n : 1;  // host upper bound of every level's voxel count
   const int nblk = cdiv(n, kScanBlock);
   // level-0 block table (the voxelize table is no longer needed), then both level-0 kernel maps
@@ -428,9 +513,16 @@ extern "C" int sps_build_maps(sps_ctx* ctx, void* stream_) {
   };
   build_blocks(0);
   prof_mark("blocks.L0", st);
-  k_kernel_map_blk<5, 1><<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->table, ctx->cells, 0,
-                                                            ctx->nbr5, ctx->ld);
-  prof_mark("kmap5.L0", st);
+  if (c0) {
+    k_conv0_blk<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->table, ctx->cells, c0->feat, c0->w,
+                                                   c0->shift, c0->round_out, c0->out, c0->out_ld);
+    prof_mark("conv0+kmap5", st);
+  } else {
+    k_kernel_map_blk<5, 1><<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->table, ctx->cells, 0,
+                                                              ctx->nbr5, ctx->ld);
+    prof_mark("kmap5.L0", st);
+  }
+  ctx->have_nbr5 = c0 == nullptr;
   k_kernel_map_blk<3, 3><<<grid_for(3 * n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->table, ctx->cells, 0,
                                                                 ctx->nbr3[0], ctx->ld);
   sps_kernel_map_tile_masks(ctx->nbr3[0], ctx->ld, 81, ctx->counts + 0, n, ctx->tmask3[0], st);

@@ -239,7 +239,8 @@ static int run_conv(const uint32_t* tmask, const char* name, const ConvW& w, int
   return rc;
 }
 
-int unet_forward(sps_ctx* c, const sps_net* net, const float* feat0, float* logits, cudaStream_t st) {
+int unet_forward(sps_ctx* c, const sps_net* net, const float* feat0, float* logits, cudaStream_t st,
+                 bool conv0_done = false) {
   const int64_t nmax = c->n > 0 ? c->n : 1;
   const int64_t ld = c->ld;
   float** B = c->buf;
@@ -260,8 +261,11 @@ int unet_forward(sps_ctx* c, const sps_net* net, const float* feat0, float* logi
 #define RUN(...) do { rc = run_conv(nullptr, __VA_ARGS__); if (rc != SPS_OK) return rc; } while (0)
 #define RUN3(L_, ...) do { rc = run_conv(c->tmask3[L_], __VA_ARGS__); if (rc != SPS_OK) return rc; } while (0)
   // conv0p1s1 + bn0 + relu  (minkunet.py:162-164)
-  RUN("conv0", net->conv0, SPS_CONV_NBR, c->nbr5, ld, c->counts + 0, nmax, feat0, 1, nullptr, 0, nullptr, 0, skip[0],
-      skip_ld[0], st);
+  if (!conv0_done) {
+    if (!c->have_nbr5) return SPS_ERR_STATE;
+    RUN("conv0", net->conv0, SPS_CONV_NBR, c->nbr5, ld, c->counts + 0, nmax, feat0, 1, nullptr, 0, nullptr, 0, skip[0],
+        skip_ld[0], st);
+  }
   // encoder (minkunet.py:166-185)
   for (int i = 0; i < 4; ++i) {
     const int L = i + 1;
@@ -330,6 +334,7 @@ extern "C" int sps_devox_sigmoid(const float* d_logits, const int32_t* d_inv, in
 namespace sps {
 int voxelize_impl(sps_ctx* ctx, const float* d_points, int64_t n, const int32_t* d_n, int64_t ld_points,
                   float voxel_size, cudaStream_t st);
+int build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st);
 
 int forward_impl(sps_ctx* ctx, const sps_net* net, const float* d_points, int64_t n, const int32_t* d_n,
                  int64_t ld_points, float voxel_size, float* d_scores, int64_t n_scores, cudaStream_t st) {
@@ -346,14 +351,16 @@ int forward_impl(sps_ctx* ctx, const sps_net* net, const float* d_points, int64_
   int rc = voxelize_impl(ctx, d_points, n, d_n, ld_points, voxel_size, st);
   if (rc != SPS_OK) return rc;
   prof_mark("voxelize", st);
-  rc = sps_build_maps(ctx, st);
-  if (rc != SPS_OK) return rc;
   // TensorField.sparse(): voxel feature = mean of the constant 0.5 point features = 0.5
   // (src/sps/models/models.py:22-25)
   int64_t g = ((n > 0 ? n : 1) + 255) / 256;
   if (g > 148 * 8) g = 148 * 8;
   k_fill_f32<<<(int)g, 256, 0, st>>>(ctx->buf[sps_ctx::FEAT0], ctx->counts + 0, 0.5f);
-  rc = unet_forward(ctx, net, ctx->buf[sps_ctx::FEAT0], ctx->buf[sps_ctx::LOGITS], st);
+  Conv0Fused c0{ctx->buf[sps_ctx::FEAT0], net->conv0.w, net->conv0.shift, conv_backend() != 1,
+                ctx->buf[sps_ctx::CAT8] + 8, 16};
+  rc = build_maps_impl(ctx, &c0, st);
+  if (rc != SPS_OK) return rc;
+  rc = unet_forward(ctx, net, ctx->buf[sps_ctx::FEAT0], ctx->buf[sps_ctx::LOGITS], st, /*conv0_done=*/true);
   if (rc != SPS_OK) return rc;
   rc = sps_devox_sigmoid(ctx->buf[sps_ctx::LOGITS], ctx->inv, n_scores, d_scores, st);
   if (rc != SPS_OK) return rc;

@@ -239,3 +239,28 @@ def test_prune_crop_and_streamed_infer(engine_mod, state_dict):
     # radius crop (mapmos_node.py:63-68)
     idx = mh.crop_radius((1.0, -2.0, 1.8), 30.0).cpu().numpy()
     assert (idx == O.radius_crop(map_xyz.astype(np.float64), np.array([1.0, -2.0, 1.8]), 30.0)).all()
+
+
+def test_generic_unet_entry_matches_fused_forward(engine_mod, state_dict):
+    """sps_unet_forward (explicit feature vector, 5x5x5x1 table materialised) against the fused
+    sps_forward (conv0 computed straight off the block table)."""
+    rows = make_case("hdl-32", seed=6, n_map_poses=5)
+    pts = rows[:, :5]
+    net = engine_mod.Net(state_dict)
+    eng = engine_mod.Engine(len(pts))
+    fused = eng.forward(net, dev(pts), 0.1).cpu().numpy()
+    eng.status()
+    eng.voxelize(dev(pts), 0.1)
+    eng.build_maps()
+    v0 = eng.count(0)
+    logits = eng.unet_forward(net, torch.full((v0,), 0.5, device="cuda")).cpu().numpy()
+    inv = eng.inverse_map()
+    generic = 1.0 / (1.0 + np.exp(-logits[inv].astype(np.float64)))
+    assert np.abs(generic - fused).max() < 1e-6
+    # a non-constant feature vector goes through the generic path only: check it against the oracle
+    rng = np.random.default_rng(0)
+    f = rng.uniform(0, 1, v0).astype(np.float32)
+    got = eng.unet_forward(net, dev(f)).cpu().numpy()
+    c0, _ = O.voxelize(pts, 0.1)
+    ref = O.unet_forward(O.Levels(c0), f[:, None], state_dict)[:, 0]
+    assert np.abs(got - ref).max() < 5e-5
