@@ -269,34 +269,33 @@ template <int K0, int KT>
 __global__ void __launch_bounds__(256)
 k_kernel_map_blk(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr,
                  const Slot* __restrict__ tab, const int32_t* __restrict__ cells, int L, int32_t* __restrict__ nbr,
-                 int64_t ld) {
+                 int64_t ld, uint32_t* __restrict__ tile_masks) {
   const int n = *n_ptr;
   if (n == 0) return;
   constexpr int R = K0 / 2, K3 = K0 * K0 * K0;
   const uint32_t mask = table_capacity(n) - 1;
-  const int64_t total = (int64_t)KT * n;
   const int xlim = 1 << (kXBits - L), zlim = 1 << (kZBits - L);
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int it = (int)(idx / n), o = (int)(idx - (int64_t)it * n);
-    const unsigned long long key = keys[o];
+  const int it = blockIdx.y;   // time plane of the kernel: t + (it - KT/2)
+  const int lane = threadIdx.x & 31;
+  // warps stay converged (o is warp-aligned): the per-tile "offset present" bits come from a ballot
+  for (int o0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; o0 < n; o0 += gridDim.x * blockDim.x) {
+    const int o = o0 + lane;
+    const bool live = o < n;
+    const unsigned long long key = live ? keys[o] : 0ull;
     const int t2 = (int)(key & ((1u << kTBits) - 1)) + it - KT / 2;
+    const bool pok = live && (unsigned)t2 < (1u << kTBits);
     int32_t* out = nbr + (int64_t)it * K3 * ld + o;
-    if ((unsigned)t2 >= (1u << kTBits)) {
-#pragma unroll 1
-      for (int k = 0; k < K3; ++k) out[(int64_t)k * ld] = -1;
-      continue;
-    }
     const int cx = (int)((key >> kXShift) & ((1u << kXBits) - 1)) >> L;
     const int cy = (int)((key >> kYShift) & ((1u << kYBits) - 1)) >> L;
     const int cz = (int)((key >> kZShift) & ((1u << kZBits) - 1)) >> L;
-    const unsigned long long bt = (key & (0xFFull << kBShift)) | (unsigned long long)(unsigned)t2;
+    const unsigned long long bt = (key & (0xFFull << kBShift)) | (unsigned long long)(unsigned)(pok ? t2 : 0);
     unsigned long long cached_key = kEmptyKey;
     const int32_t* cached = nullptr;
+    uint32_t* tm = tile_masks ? tile_masks + 4 * (o0 >> 7) : nullptr;
 #pragma unroll 1
     for (int dz = -R; dz <= R; ++dz) {
       const int nz = cz + dz;
-      const bool zok = (unsigned)nz < (unsigned)zlim;
+      const bool zok = pok && (unsigned)nz < (unsigned)zlim;
 #pragma unroll 1
       for (int dy = -R; dy <= R; ++dy) {
         const int ny = cy + dy;
@@ -317,7 +316,12 @@ k_kernel_map_blk(const unsigned long long* __restrict__ keys, const int32_t* __r
             }
             if (cached) res = __ldg(cached + lyz + (nx & 3));
           }
-          out[(int64_t)((dx + R) + K0 * ((dy + R) + K0 * (dz + R))) * ld] = res;
+          const int k3 = (dx + R) + K0 * ((dy + R) + K0 * (dz + R));
+          if (live) out[(int64_t)k3 * ld] = res;
+          if (tm) {
+            const int k = it * K3 + k3;
+            if (__any_sync(0xffffffffu, res >= 0) && lane == 0) atomicOr(tm + (k >> 5), 1u << (k & 31));
+          }
         }
       }
     }
@@ -519,13 +523,15 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
     prof_mark("conv0+kmap5", st);
   } else {
     k_kernel_map_blk<5, 1><<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->table, ctx->cells, 0,
-                                                              ctx->nbr5, ctx->ld);
+                                                              ctx->nbr5, ctx->ld, nullptr);
     prof_mark("kmap5.L0", st);
   }
   ctx->have_nbr5 = c0 == nullptr;
-  k_kernel_map_blk<3, 3><<<grid_for(3 * n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->table, ctx->cells, 0,
-                                                                ctx->nbr3[0], ctx->ld);
-  sps_kernel_map_tile_masks(ctx->nbr3[0], ctx->ld, 81, ctx->counts + 0, n, ctx->tmask3[0], st);
+  const size_t mask_bytes = (size_t)(n / 128 + 1) * 16;
+  SPS_CUDA_CHECK(cudaMemsetAsync(ctx->tmask3[0], 0, mask_bytes, st));
+  k_kernel_map_blk<3, 3><<<dim3(grid_for(n, 256, 148 * 8), 3), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->table,
+                                                                              ctx->cells, 0, ctx->nbr3[0], ctx->ld,
+                                                                              ctx->tmask3[0]);
   prof_mark("kmap3.L0", st);
   for (int L = 1; L < SPS_NUM_LEVELS; ++L) {
     const int32_t* n_fine = ctx->counts + (L - 1);
@@ -541,9 +547,10 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
     static const char* nm_k[5] = {"", "kmap3.L1", "kmap3.L2", "kmap3.L3", "kmap3.L4"};
     build_blocks(L);
     prof_mark(nm_s[L], st);
-    k_kernel_map_blk<3, 3><<<grid_for(3 * n, 256), 256, 0, st>>>(ctx->keys[L], ctx->counts + L, ctx->table, ctx->cells, L,
-                                                                  ctx->nbr3[L], ctx->ld);
-    sps_kernel_map_tile_masks(ctx->nbr3[L], ctx->ld, 81, ctx->counts + L, n, ctx->tmask3[L], st);
+    SPS_CUDA_CHECK(cudaMemsetAsync(ctx->tmask3[L], 0, mask_bytes, st));
+    k_kernel_map_blk<3, 3><<<dim3(grid_for(n, 256, 148 * 8), 3), 256, 0, st>>>(ctx->keys[L], ctx->counts + L, ctx->table,
+                                                                                ctx->cells, L, ctx->nbr3[L], ctx->ld,
+                                                                                ctx->tmask3[L]);
     prof_mark(nm_k[L], st);
   }
   SPS_CUDA_CHECK(cudaGetLastError());
