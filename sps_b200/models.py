@@ -127,6 +127,19 @@ class CustomMinkUNet(nn.Module):
                 nn.init.constant_(m.bn.bias, 0)
 
 
+class _Pending:
+    """Handle of an in-flight ``SPSModel.forward_async`` call."""
+
+    def __init__(self, event, out, engine):
+        self._event, self._out, self._engine = event, out, engine
+
+    def result(self, check: bool = False) -> torch.Tensor:
+        self._event.synchronize()
+        if check:
+            self._engine.status()
+        return self._out
+
+
 class SPSModel(nn.Module):
     def __init__(self, voxel_size: float, max_points: int = 0):
         super().__init__()
@@ -139,6 +152,7 @@ class SPSModel(nn.Module):
         self._min_points = int(max_points)
         self._net_version = -1
         self._host_out = None
+        self._pipe = None
 
     def invalidate(self):
         """Weights changed in place: re-fold and re-upload them at the next forward."""
@@ -177,6 +191,46 @@ class SPSModel(nn.Module):
             # tensor is a view that the NEXT host-side forward overwrites (clone it to keep it)
             self._host_out = torch.empty(max(n, 1), dtype=torch.float32).pin_memory()
         return engine.forward_host(net, coordinates.contiguous(), self.voxel_size, out=self._host_out[:n])
+
+    def forward_async(self, coordinates: torch.Tensor):
+        """Pipelined host entry point: ``coordinates`` is a (preferably pinned) HOST tensor; the H2D
+        copy runs on a side stream into one of two device staging buffers, the forward and the D2H of
+        the scores are queued behind it, and a handle is returned immediately -- so the copies of
+        call k+1 overlap the kernels of call k.  ``handle.result()`` waits for and returns the scores
+        (a pinned host tensor that the call after next reuses)."""
+        if self.training:
+            raise RuntimeError("sps_b200 is inference-only (call .eval()); training is out of scope")
+        assert not coordinates.is_cuda and coordinates.dtype == torch.float32 and coordinates.dim() == 2
+        device = next(self.MinkUNet.parameters()).device
+        if device.type != "cuda":
+            raise RuntimeError("move the model to a CUDA device first: sps_b200 has no CPU path")
+        n, ld = coordinates.shape
+        engine, net = self._prepare(n, device)
+        p = self._pipe
+        if p is None or p["cap"] < n or p["ld"] != ld:
+            cap = max(n, engine.max_points)
+            p = self._pipe = {"cap": cap, "ld": ld, "k": 0, "copy": torch.cuda.Stream(device=device),
+                              "d_in": [torch.empty((cap, ld), dtype=torch.float32, device=device) for _ in range(2)],
+                              "d_out": [torch.empty(cap, dtype=torch.float32, device=device) for _ in range(2)],
+                              "h_out": [torch.empty(cap, dtype=torch.float32).pin_memory() for _ in range(2)],
+                              "busy": [None, None]}
+        slot = p["k"] & 1
+        p["k"] += 1
+        if p["busy"][slot] is not None:
+            p["busy"][slot].synchronize()          # the buffers of this slot are free again
+        compute = torch.cuda.current_stream(device)
+        d_in, d_out, h_out = p["d_in"][slot][:n], p["d_out"][slot][:n], p["h_out"][slot][:n]
+        with torch.cuda.stream(p["copy"]):
+            d_in.copy_(coordinates, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(p["copy"])
+        compute.wait_event(ready)
+        engine.forward(net, d_in, self.voxel_size, out=d_out)
+        h_out.copy_(d_out, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(compute)
+        p["busy"][slot] = done
+        return _Pending(done, h_out, engine)
 
     def check(self):
         """Synchronise and raise if the last forward met an out-of-range coordinate."""

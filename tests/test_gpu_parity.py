@@ -186,6 +186,9 @@ def test_host_entry_point_and_model_api(engine_mod, state_dict):
     assert not got_host.is_cuda and np.abs(got_host.numpy() - ref).max() < 1e-5
     got_dev = model(batch.cuda())                 # CUDA tensor -> sps_forward
     assert got_dev.is_cuda and np.abs(got_dev.cpu().numpy() - ref).max() < 1e-5
+    h1 = model.model.forward_async(batch[:, :5].contiguous().pin_memory())     # pipelined host entry point
+    h2 = model.model.forward_async(batch[:, :5].contiguous().pin_memory())
+    assert np.abs(h1.result(check=True).numpy() - ref).max() < 1e-5 and np.abs(h2.result().numpy() - ref).max() < 1e-5
     model.predict_step(batch.cuda(), 0)
     m = O.predict_step_metrics(ref, rows[:, 5], rows[:, 4], EPS)
     s = model.summary()
