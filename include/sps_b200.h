@@ -230,6 +230,19 @@ int sps_confusion_counts(const float* d_scores, const float* d_rows, int64_t ld_
                          float batch_index, float eps, int64_t* d_counts, double* d_sums,
                          void* stream);
 
+/* ---------------------------------------------------------------- layer-level pieces ----- */
+/* ME.TensorField(...).sparse() feature reduction (UNWEIGHTED_AVERAGE, models.py:24-25): mean of the
+ * point features per level-0 voxel of the last sps_voxelize.  d_out [>= n rows, channels],
+ * d_count [>= n] scratch. */
+int sps_voxel_mean(sps_ctx* ctx, const float* d_feat, int64_t ld, int channels, float* d_out,
+                   float* d_count, void* stream);
+/* SparseTensor.slice(tensor_field) (models.py:28): out[p, :] = F[inv[p], :]. */
+int sps_gather_rows(const float* d_f, int64_t ld, int channels, const int32_t* d_inv, int64_t n,
+                    float* d_out, void* stream);
+/* MinkowskiBatchNorm (eval: per-channel affine) / MinkowskiReLU on a feature matrix. */
+int sps_affine_relu(const float* d_x, int64_t ld, int channels, int64_t n, const float* d_scale,
+                    const float* d_shift, int relu, float* d_y, int64_t ldy, void* stream);
+
 /* Small helpers so that host code needs no second CUDA binding. */
 int sps_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream);
 int sps_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream);

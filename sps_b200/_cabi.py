@@ -25,7 +25,7 @@ SYMBOLS = [
     "sps_map_bytes", "sps_map_build", "sps_map_destroy", "sps_submap_crop_voxel", "sps_submap_crop_radius",
     "sps_assemble", "sps_memcpy_d2h", "sps_memcpy_h2d", "sps_infer_scan", "sps_infer_scan_scratch_bytes", "sps_conv_kmajor_ld", "sps_conv_pack_kmajor", "sps_kernel_map_tile_masks", "sps_set_tma_gather",
     "sps_set_conv_backend", "sps_profile_enable", "sps_profile_read", "sps_ctx_pair_count",
-    "sps_confusion_counts",
+    "sps_confusion_counts", "sps_voxel_mean", "sps_gather_rows", "sps_affine_relu",
 ]
 
 
@@ -104,6 +104,9 @@ def load() -> C.CDLL:
         "sps_conv_pack_kmajor": (i32, [vp, i32, i32, i32, vp, i32, vp]),
         "sps_set_conv_backend": (i32, [i32]),
         "sps_confusion_counts": (i32, [vp, vp, i64, i64, f32, f32, vp, vp, vp]),
+        "sps_voxel_mean": (i32, [vp, vp, i64, i32, vp, vp, vp]),
+        "sps_gather_rows": (i32, [vp, i64, i32, vp, i64, vp, vp]),
+        "sps_affine_relu": (i32, [vp, i64, i32, i64, vp, vp, i32, vp, i64, vp]),
         "sps_profile_enable": (i32, [i32]),
         "sps_profile_read": (i32, [vp, vp, i32, C.POINTER(i32)]),
         "sps_ctx_pair_count": (i32, [vp, i32, i32, C.POINTER(i64), vp]),

@@ -282,3 +282,87 @@ extern "C" int sps_confusion_counts(const float* d_scores, const float* d_rows, 
   }
   return SPS_OK;
 }
+
+// ---------------------------------------------------------------- layer-level helpers (ME-shaped API) ----
+namespace sps {
+// ME.TensorField.sparse() with UNWEIGHTED_AVERAGE: voxel feature = mean of its points' features
+__global__ void k_voxel_accumulate(const float* __restrict__ feat, int64_t ld, int c, const int32_t* __restrict__ inv,
+                                   int64_t n, float* __restrict__ sum, float* __restrict__ cnt) {
+  const int64_t total = n * c;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / c;
+    const int j = (int)(i - p * c);
+    const int v = inv[p];
+    if (v < 0) continue;
+    atomicAdd(sum + (int64_t)v * c + j, feat[p * ld + j]);
+    if (j == 0) atomicAdd(cnt + v, 1.0f);
+  }
+}
+__global__ void k_voxel_divide(float* __restrict__ sum, const float* __restrict__ cnt, int c, const int32_t* __restrict__ v_ptr) {
+  const int64_t total = (int64_t)(*v_ptr) * c;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    sum[i] = sum[i] / cnt[i / c];
+}
+// SparseTensor.slice(field): out[p] = F[inv[p]]
+__global__ void k_gather_rows(const float* __restrict__ f, int64_t ld, int c, const int32_t* __restrict__ inv, int64_t n,
+                              float* __restrict__ out) {
+  const int64_t total = n * c;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / c;
+    const int j = (int)(i - p * c);
+    const int v = inv[p];
+    out[i] = v >= 0 ? f[(int64_t)v * ld + j] : nanf("");
+  }
+}
+// MinkowskiBatchNorm (eval) / MinkowskiReLU: y = x * scale + shift, optional ReLU (scale/shift may be NULL)
+__global__ void k_affine_relu(const float* __restrict__ x, int64_t ld, int c, int64_t n, const float* __restrict__ scale,
+                              const float* __restrict__ shift, int relu, float* __restrict__ y, int64_t ldy) {
+  const int64_t total = n * c;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / c;
+    const int j = (int)(i - p * c);
+    float v = x[p * ld + j];
+    if (scale) v *= scale[j];
+    if (shift) v += shift[j];
+    if (relu) v = fmaxf(v, 0.f);
+    y[p * ldy + j] = v;
+  }
+}
+static inline int ew_grid(int64_t total) {
+  int64_t g = (total + 255) / 256;
+  return (int)(g < 1 ? 1 : g > 148 * 16 ? 148 * 16 : g);
+}
+}  // namespace sps
+
+extern "C" int sps_voxel_mean(sps_ctx* ctx, const float* d_feat, int64_t ld, int channels, float* d_out, float* d_count,
+                              void* stream) {
+  if (!ctx || !d_feat || !d_out || !d_count || channels < 1 || ld < channels) return SPS_ERR_BAD_ARG;
+  if (!ctx->have_l0) return SPS_ERR_STATE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = ctx->n;
+  SPS_CUDA_CHECK(cudaMemsetAsync(d_out, 0, (size_t)n * channels * sizeof(float), st));   // V0 <= n rows
+  SPS_CUDA_CHECK(cudaMemsetAsync(d_count, 0, (size_t)n * sizeof(float), st));
+  if (n > 0) {
+    k_voxel_accumulate<<<ew_grid(n * channels), 256, 0, st>>>(d_feat, ld, channels, ctx->inv, n, d_out, d_count);
+    k_voxel_divide<<<ew_grid(n * channels), 256, 0, st>>>(d_out, d_count, channels, ctx->counts + 0);
+  }
+  SPS_CUDA_CHECK(cudaGetLastError());
+  return SPS_OK;
+}
+
+extern "C" int sps_gather_rows(const float* d_f, int64_t ld, int channels, const int32_t* d_inv, int64_t n, float* d_out,
+                               void* stream) {
+  if (!d_f || !d_inv || !d_out || channels < 1 || n < 0) return SPS_ERR_BAD_ARG;
+  if (n) k_gather_rows<<<ew_grid(n * channels), 256, 0, (cudaStream_t)stream>>>(d_f, ld, channels, d_inv, n, d_out);
+  SPS_CUDA_CHECK(cudaGetLastError());
+  return SPS_OK;
+}
+
+extern "C" int sps_affine_relu(const float* d_x, int64_t ld, int channels, int64_t n, const float* d_scale,
+                               const float* d_shift, int relu, float* d_y, int64_t ldy, void* stream) {
+  if (!d_x || !d_y || channels < 1 || n < 0) return SPS_ERR_BAD_ARG;
+  if (n) k_affine_relu<<<ew_grid(n * channels), 256, 0, (cudaStream_t)stream>>>(d_x, ld, channels, n, d_scale, d_shift, relu,
+                                                                             d_y, ldy);
+  SPS_CUDA_CHECK(cudaGetLastError());
+  return SPS_OK;
+}

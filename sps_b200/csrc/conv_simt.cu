@@ -257,9 +257,31 @@ static int launch_up(const sps_conv_args& a, cudaStream_t st) {
   return SPS_OK;
 }
 
+// 1x1 convolution with a narrow output (the `final` 8 -> 1 layer used as a standalone module,
+// minkunet.py:152-158): one thread per row.
+__global__ void k_linear_narrow(const sps_conv_args a) {
+  const int n = *a.n_out;
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+    const float* row = a.in + (int64_t)v * a.in_ld;
+    for (int c = 0; c < a.cout; ++c) {
+      float acc = a.shift ? __ldg(a.shift + c) : 0.f;
+      for (int ci = 0; ci < a.cin; ++ci) acc = fmaf(__ldg(row + ci), __ldg(a.weight + ci * a.cout + c), acc);
+      if (a.res) acc += __ldg(a.res + (int64_t)v * a.res_ld + c);
+      if (a.relu) acc = fmaxf(acc, 0.f);
+      a.out[(int64_t)v * a.out_ld + c] = acc;
+    }
+  }
+}
+
 int conv_dispatch(const sps_conv_args& a, cudaStream_t st);
 
 int conv_simt(const sps_conv_args& a, cudaStream_t st) {
+  if (a.mode == SPS_CONV_NBR && a.K == 1 && !a.map && a.cout < 8 && !a.in2 && !a.head_out && a.out) {
+    int64_t g = (a.n_out_max + 255) / 256;
+    k_linear_narrow<<<(int)(g < 1 ? 1 : g > 148 * 8 ? 148 * 8 : g), 256, 0, st>>>(a);
+    SPS_CUDA_CHECK(cudaGetLastError());
+    return SPS_OK;
+  }
   if (a.mode == SPS_CONV_UP) {
     switch (a.cout) {
       case 8: return launch_up<8>(a, st);
@@ -288,6 +310,8 @@ extern "C" int sps_conv_fwd(const sps_conv_args* a, void* stream) {
   if (a->mode == SPS_CONV_NBR && !a->map && a->K != 1) return SPS_ERR_BAD_ARG;
   if (a->cin < 1 || (a->cin != 1 && a->cin % 4) || (a->in_ld % 4 && a->cin != 1)) return SPS_ERR_BAD_ARG;
   if (a->in2 && (!a->weight2 || a->cin2 % 4 || a->in2_ld % 4)) return SPS_ERR_BAD_ARG;
+  const bool narrow = a->K == 1 && !a->map && a->cout < 8;   // scalar kernel, no vector alignment needed
+  if (narrow) return sps::conv_dispatch(*a, (cudaStream_t)stream);
   if (a->out && a->out_ld % 4) return SPS_ERR_BAD_ARG;
   if (a->res && a->res_ld % 4) return SPS_ERR_BAD_ARG;
   if (a->head_out && (a->cout != 8 || !a->head_w)) return SPS_ERR_BAD_ARG;
