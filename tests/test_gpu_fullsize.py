@@ -1,0 +1,94 @@
+"""Full-size configurations of BASELINE.json on the GPU: parity against the C/OpenMP oracle where it
+finishes in seconds, plus size-independent properties (determinism, row-permutation invariance,
+batch independence, score range)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sps_oracle as O
+from oracle import me_cpu
+
+pytestmark = [pytest.mark.gpu]
+EPS = 0.84
+
+
+def run(pts, sd, backend=0):
+    from sps_b200 import engine, _cabi
+    lib = _cabi.load()
+    lib.sps_set_conv_backend(backend)
+    try:
+        eng = engine.Engine(len(pts))
+        out = eng.forward(engine.Net(sd), torch.as_tensor(np.ascontiguousarray(pts)).cuda(), 0.1 if pts is None else run.voxel)
+        eng.status()
+        return out.cpu().numpy(), [eng.count(L) for L in range(5)]
+    finally:
+        lib.sps_set_conv_backend(0)
+
+
+run.voxel = 0.1
+
+
+def check_against_oracle(pts, sd, voxel, tol):
+    run.voxel = voxel
+    got, counts = run(pts, sd)
+    ref, ref_counts, _ = me_cpu.forward(pts, voxel, me_cpu.pack_weights(sd))
+    assert counts == ref_counts.tolist()
+    assert np.isfinite(got).all() and got.min() > 0 and got.max() < 1
+    err = np.abs(got - ref)
+    assert err.max() < tol, err.max()
+    assert np.mean((got < EPS) == (ref < EPS)) >= 0.999
+    return got
+
+
+def test_config1_128k_scan_voxel_submap():
+    """configs[0]: one 131 072-point scan + 0.1 m voxel-overlap submap, batch 1."""
+    from sps_b200 import synth
+    world = synth.World(0)
+    scan = synth.scan(world, "os1-128", seed=0)
+    base = synth.base_map(world, "os1-128", n_poses=10, seed=0)
+    sub = synth.submap_voxel_overlap(base, scan, 0.1)
+    pts = synth.assemble(scan, sub)[:, :5]
+    assert len(scan) == 131072
+    sd = O.make_state_dict(seed=0)
+    got = check_against_oracle(pts, sd, 0.1, 2e-3)
+    # determinism: bit-identical on a second run
+    again, _ = run(pts, sd)
+    assert np.array_equal(got, again)
+    # row-permutation invariance: the voxel set, hence every point's score, does not depend on row order
+    perm = np.random.default_rng(0).permutation(len(pts))
+    shuffled, _ = run(pts[perm], sd)
+    assert np.abs(shuffled - got[perm]).max() < 1e-6
+
+
+def test_config2_batch8_radius_submaps_batch_independence():
+    """configs[1] shape (the bench workload): batch items never interact."""
+    import bench
+    rows = bench.make_batches(0, n_distinct=1, batch=8)[0]
+    pts = np.ascontiguousarray(rows[:, :5])
+    sd = O.make_state_dict(seed=0)
+    run.voxel = 0.1
+    got, counts = run(pts, sd)
+    assert np.isfinite(got).all()
+    for b in (0, 5):
+        one = pts[pts[:, 0] == b].copy()
+        one[:, 0] = 0
+        ref, c1, _ = me_cpu.forward(one, 0.1, me_cpu.pack_weights(sd))
+        sel = got[pts[:, 0] == b]
+        assert np.abs(sel - ref).max() < 2e-3
+        assert np.mean((sel < EPS) == (ref < EPS)) >= 0.999
+
+
+def test_config5_stress_dense_scan_small_voxels_radius_crop():
+    """configs[4] shape: 524 288-point scan, 0.05 m voxels, 30 m radius crop of the base map."""
+    from sps_b200 import synth
+    from sps_b200.engine import MapHash
+    world = synth.World(3)
+    scan = synth.scan(world, "dense-128x4096", pose=(2.0, -1.0, 0.4), seed=3)
+    base = synth.base_map(world, "os1-128", n_poses=12, seed=3, voxel=0.05)
+    mh = MapHash(torch.as_tensor(base).cuda(), 0.05)
+    idx = mh.crop_radius((2.0, -1.0, 1.8), 30.0).cpu().numpy()
+    assert np.array_equal(idx, O.radius_crop(base, np.array([2.0, -1.0, 1.8]), 30.0))
+    pts = synth.assemble(scan, base[idx])[:, :5]
+    assert len(scan) == 524288
+    sd = O.make_state_dict(seed=1)
+    check_against_oracle(pts, sd, 0.05, 2e-3)
