@@ -1,6 +1,7 @@
 // Context management, workspace carve-up, status plumbing and small helpers of the C ABI.
 #include <cstdio>
 #include <cstring>
+#include <vector>
 #include "ctx.h"
 
 namespace sps {
@@ -52,8 +53,10 @@ static size_t carve(sps_ctx* c, void* base, int64_t max_points) {
     c->tmask3[L] = cv.take<uint32_t>((size_t)(ld / 128 + 1) * 4);
     c->parent[L] = (L < SPS_NUM_LEVELS - 1) ? cv.take<int32_t>(N) : nullptr;
     c->child[L] = (L > 0) ? cv.take<int32_t>((size_t)8 * ld) : nullptr;
+    c->upmap[L] = (L < SPS_NUM_LEVELS - 1) ? cv.take<int32_t>((size_t)8 * ld) : nullptr;
   }
   c->nbr5 = cv.take<int32_t>((size_t)125 * ld);
+  c->tmask8 = cv.take<uint32_t>((size_t)(ld / 128 + 1) * 4);
   for (int b = 0; b < sps_ctx::NBUF; ++b) c->buf[b] = cv.take<float>((size_t)N * kBufWidth[b]);
   return (cv.off + 255) & ~size_t(255);
 }
@@ -96,6 +99,11 @@ extern "C" int sps_ctx_create(sps_ctx** out, void* d_workspace, size_t workspace
   c->base = (char*)d_workspace;
   c->bytes = workspace_bytes;
   cudaError_t e = cudaMemset(c->counts, 0, 64 * sizeof(int32_t));
+  if (e == cudaSuccess) {  // every 128-row tile of a 2x2x2x1 map may hold all eight offsets
+    std::vector<uint32_t> m((size_t)(c->ld / 128 + 1) * 4, 0u);
+    for (size_t i = 0; i < m.size(); i += 4) m[i] = 0xFFu;
+    e = cudaMemcpy(c->tmask8, m.data(), m.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+  }
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { delete c; return set_cuda_error(e, "cudaMemset(ctx scalars)"); }
   *out = c;

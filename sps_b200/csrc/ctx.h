@@ -31,6 +31,8 @@ struct sps_ctx {
   int32_t* inv = nullptr;                      // [max_points] point -> level-0 row
   int32_t* parent[SPS_NUM_LEVELS] = {};        // [L] fine row -> parent*8 + k   (L = 0..3)
   int32_t* child[SPS_NUM_LEVELS] = {};         // [L] [8][ld] children of level-L rows (L = 1..4)
+  int32_t* upmap[SPS_NUM_LEVELS] = {};         // [L] [8][ld] transposed-conv map of level-L rows (L = 0..3)
+  uint32_t* tmask8 = nullptr;                  // [tiles][4] all-eight-offsets mask for the 2x2x2x1 maps
   int32_t* nbr3[SPS_NUM_LEVELS] = {};          // [81][ld]
   int32_t* nbr5 = nullptr;                     // [125][ld]
   uint32_t* tmask3[SPS_NUM_LEVELS] = {};       // [L] [tiles][4] present-offset masks of nbr3 per 128-row tile

@@ -196,7 +196,7 @@ __global__ void k_assign_coarse(Slot* tab, const uint32_t* __restrict__ slot_of,
                                 const int32_t* __restrict__ rank, const int32_t* __restrict__ block_sums,
                                 const unsigned long long* __restrict__ fine, int log2s,
                                 unsigned long long* __restrict__ ukeys, int32_t* __restrict__ parent,
-                                int32_t* __restrict__ child, int64_t ld) {
+                                int32_t* __restrict__ child, int32_t* __restrict__ upmap, int64_t ld) {
   const int n = *n_ptr;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t s = slot_of[i];
@@ -205,6 +205,10 @@ __global__ void k_assign_coarse(Slot* tab, const uint32_t* __restrict__ slot_of,
     const int k = child_index(fine[i], log2s);
     parent[i] = id * 8 + k;
     child[(int64_t)k * ld + id] = i;
+    // transposed-conv kernel map in the dense [8][ld] form the tensor-core kernel walks:
+    // upmap[k'][f] = parent row if k' == k(f), else absent
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) upmap[(int64_t)kk * ld + i] = kk == k ? id : -1;
     if (f == i) { tab[s].val = id; ukeys[id] = tab[s].key; }
   }
 }
@@ -542,7 +546,7 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
     k_fill_i32<<<grid_for(8 * n, 256), 256, 0, st>>>(ctx->child[L], ctx->ld, 8, ctx->counts + L, -1);
     k_assign_coarse<<<grid_for(n, 256), 256, 0, st>>>(ctx->table, ctx->slot_of, n_fine, ctx->rank, ctx->block_sums,
                                                        ctx->keys[L - 1], L - 1, ctx->keys[L], ctx->parent[L - 1],
-                                                       ctx->child[L], ctx->ld);
+                                                       ctx->child[L], ctx->upmap[L - 1], ctx->ld);
     static const char* nm_s[5] = {"", "stride.L1", "stride.L2", "stride.L3", "stride.L4"};
     static const char* nm_k[5] = {"", "kmap3.L1", "kmap3.L2", "kmap3.L3", "kmap3.L4"};
     build_blocks(L);

@@ -131,7 +131,7 @@ extern "C" int sps_net_finalize(sps_net* net, void* d_weights, size_t bytes, voi
     std::vector<float> shf(sh.begin(), sh.end());
     cw.K = K; cw.cin = cin; cw.cout = cout; cw.cin2 = 0;
     Pending p{&cw, pk.add(w), pk.add(shf), 0, false};
-    if (K == 81) add_kmajor(p, w, K, cin, cout, nullptr, 0);
+    if (K == 81 || (K == 8 && cin >= 16 && cin % 4 == 0)) add_kmajor(p, w, K, cin, cout, nullptr, 0);  // 8-channel 2x2x2 layers stay on the CUDA-core kernel (measured faster)
     pend.push_back(p);
     return true;
   };
@@ -259,6 +259,7 @@ int unet_forward(sps_ctx* c, const sps_net* net, const float* feat0, float* logi
                                  "block5.conv2", "block6.conv2", "block7.conv2", "block8.conv2+final"};
   int rc;
 #define RUN(...) do { rc = run_conv(nullptr, __VA_ARGS__); if (rc != SPS_OK) return rc; } while (0)
+#define RUN8(...) do { rc = run_conv(c->tmask8, __VA_ARGS__); if (rc != SPS_OK) return rc; } while (0)
 #define RUN3(L_, ...) do { rc = run_conv(c->tmask3[L_], __VA_ARGS__); if (rc != SPS_OK) return rc; } while (0)
   // conv0p1s1 + bn0 + relu  (minkunet.py:162-164)
   if (!conv0_done) {
@@ -270,8 +271,8 @@ int unet_forward(sps_ctx* c, const sps_net* net, const float* feat0, float* logi
   for (int i = 0; i < 4; ++i) {
     const int L = i + 1;
     const int cw = net->down[i].cout;
-    RUN(nm_down[i], net->down[i], SPS_CONV_NBR, c->child[L], ld, c->counts + L, nmax, skip[i], skip_ld[i], nullptr, 0, nullptr,
-        0, E[i], cw, st);
+    RUN8(nm_down[i], net->down[i], SPS_CONV_NBR, c->child[L], ld, c->counts + L, nmax, skip[i], skip_ld[i], nullptr, 0,
+         nullptr, 0, E[i], cw, st);
     const ConvW& c1 = net->blk1[i];
     const ConvW& c2 = net->blk2[i];
     RUN3(L, nm_c1[i], c1, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, E[i], cw, nullptr, 0, nullptr, 0, H[i], c1.cout, st);
@@ -289,8 +290,13 @@ int unet_forward(sps_ctx* c, const sps_net* net, const float* feat0, float* logi
   float* Bd[4] = {B[C::B5], B[C::B6], B[C::B7], nullptr};
   for (int i = 0; i < 4; ++i) {
     const int L = 3 - i;  // output level
-    RUN(nm_up[i], net->up[i], SPS_CONV_UP, c->child[L + 1], ld, c->counts + L + 1, nmax, dec_in, dec_in_ld, nullptr, 0, nullptr, 0,
-        cat[L], skip_ld[L], st);
+    if (conv_backend() == 1) {   // exact-fp32 mode: scatter over the child table (no atomics, each row once)
+      RUN(nm_up[i], net->up[i], SPS_CONV_UP, c->child[L + 1], ld, c->counts + L + 1, nmax, dec_in, dec_in_ld, nullptr, 0,
+          nullptr, 0, cat[L], skip_ld[L], st);
+    } else {                     // tensor path: the same transposed conv as an 8-offset gather map of the fine rows
+      RUN8(nm_up[i], net->up[i], SPS_CONV_NBR, c->upmap[L], ld, c->counts + L, nmax, dec_in, dec_in_ld, nullptr, 0,
+           nullptr, 0, cat[L], skip_ld[L], st);
+    }
     const ConvW& c1 = net->blk1[4 + i];
     const ConvW& c2 = net->blk2[4 + i];
     RUN3(L, nm_c1[4 + i], c1, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, cat[L], skip_ld[L], nullptr, 0, nullptr, 0, Hd[i],
@@ -308,6 +314,7 @@ int unet_forward(sps_ctx* c, const sps_net* net, const float* feat0, float* logi
   }
 #undef RUN
 #undef RUN3
+#undef RUN8
   return SPS_OK;
 }
 

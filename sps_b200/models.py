@@ -209,7 +209,11 @@ class SPSModel(nn.Module):
         p = self._pipe
         if p is None or p["cap"] < n or p["ld"] != ld:
             cap = max(n, engine.max_points)
+            # two complete lanes (engine context + stream + staging buffers): consecutive calls alternate,
+            # so the hash/kernel-map phase of one call overlaps the convolution phase of the other
             p = self._pipe = {"cap": cap, "ld": ld, "k": 0, "copy": torch.cuda.Stream(device=device),
+                              "engine": [engine, Engine(engine.max_points, device)],
+                              "stream": [torch.cuda.Stream(device=device) for _ in range(2)],
                               "d_in": [torch.empty((cap, ld), dtype=torch.float32, device=device) for _ in range(2)],
                               "d_out": [torch.empty(cap, dtype=torch.float32, device=device) for _ in range(2)],
                               "h_out": [torch.empty(cap, dtype=torch.float32).pin_memory() for _ in range(2)],
@@ -217,19 +221,22 @@ class SPSModel(nn.Module):
         slot = p["k"] & 1
         p["k"] += 1
         if p["busy"][slot] is not None:
-            p["busy"][slot].synchronize()          # the buffers of this slot are free again
-        compute = torch.cuda.current_stream(device)
+            p["busy"][slot].synchronize()          # the buffers of this lane are free again
+        lane_engine, compute = p["engine"][slot], p["stream"][slot]
         d_in, d_out, h_out = p["d_in"][slot][:n], p["d_out"][slot][:n], p["h_out"][slot][:n]
+        compute.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(p["copy"]):
             d_in.copy_(coordinates, non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(p["copy"])
-        compute.wait_event(ready)
-        engine.forward(net, d_in, self.voxel_size, out=d_out)
-        h_out.copy_(d_out, non_blocking=True)
-        done = torch.cuda.Event()
-        done.record(compute)
+        with torch.cuda.stream(compute):
+            compute.wait_event(ready)
+            lane_engine.forward(net, d_in, self.voxel_size, out=d_out)
+            h_out.copy_(d_out, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(compute)
         p["busy"][slot] = done
+        engine = lane_engine
         return _Pending(done, h_out, engine)
 
     def check(self):
