@@ -153,6 +153,7 @@ class SPSModel(nn.Module):
         self._net_version = -1
         self._host_out = None
         self._pipe = None
+        self.lanes = 2            # engine contexts / streams that forward_async alternates between
 
     def invalidate(self):
         """Weights changed in place: re-fold and re-upload them at the next forward."""
@@ -193,14 +194,16 @@ class SPSModel(nn.Module):
         return engine.forward_host(net, coordinates.contiguous(), self.voxel_size, out=self._host_out[:n])
 
     def forward_async(self, coordinates: torch.Tensor):
-        """Pipelined host entry point: ``coordinates`` is a (preferably pinned) HOST tensor; the H2D
+        """Pipelined entry point.  ``coordinates`` may live on the device (no copies at all) or be a
+        (preferably pinned) HOST tensor; in the latter case the H2D
         copy runs on a side stream into one of two device staging buffers, the forward and the D2H of
         the scores are queued behind it, and a handle is returned immediately -- so the copies of
         call k+1 overlap the kernels of call k.  ``handle.result()`` waits for and returns the scores
         (a pinned host tensor that the call after next reuses)."""
         if self.training:
             raise RuntimeError("sps_b200 is inference-only (call .eval()); training is out of scope")
-        assert not coordinates.is_cuda and coordinates.dtype == torch.float32 and coordinates.dim() == 2
+        assert coordinates.dtype == torch.float32 and coordinates.dim() == 2
+        on_device = coordinates.is_cuda
         device = next(self.MinkUNet.parameters()).device
         if device.type != "cuda":
             raise RuntimeError("move the model to a CUDA device first: sps_b200 has no CPU path")
@@ -212,19 +215,27 @@ class SPSModel(nn.Module):
             # two complete lanes (engine context + stream + staging buffers): consecutive calls alternate,
             # so the hash/kernel-map phase of one call overlaps the convolution phase of the other
             p = self._pipe = {"cap": cap, "ld": ld, "k": 0, "copy": torch.cuda.Stream(device=device),
-                              "engine": [engine, Engine(engine.max_points, device)],
-                              "stream": [torch.cuda.Stream(device=device) for _ in range(2)],
-                              "d_in": [torch.empty((cap, ld), dtype=torch.float32, device=device) for _ in range(2)],
-                              "d_out": [torch.empty(cap, dtype=torch.float32, device=device) for _ in range(2)],
-                              "h_out": [torch.empty(cap, dtype=torch.float32).pin_memory() for _ in range(2)],
-                              "busy": [None, None]}
-        slot = p["k"] & 1
+                              "engine": [engine] + [Engine(engine.max_points, device) for _ in range(self.lanes - 1)],
+                              "stream": [torch.cuda.Stream(device=device) for _ in range(self.lanes)],
+                              "d_in": [torch.empty((cap, ld), dtype=torch.float32, device=device) for _ in range(self.lanes)],
+                              "d_out": [torch.empty(cap, dtype=torch.float32, device=device) for _ in range(self.lanes)],
+                              "h_out": [torch.empty(cap, dtype=torch.float32).pin_memory() for _ in range(self.lanes)],
+                              "busy": [None] * self.lanes}
+        slot = p["k"] % self.lanes
         p["k"] += 1
         if p["busy"][slot] is not None:
             p["busy"][slot].synchronize()          # the buffers of this lane are free again
         lane_engine, compute = p["engine"][slot], p["stream"][slot]
         d_in, d_out, h_out = p["d_in"][slot][:n], p["d_out"][slot][:n], p["h_out"][slot][:n]
         compute.wait_stream(torch.cuda.current_stream(device))
+        if on_device:
+            # inputs already resident in HBM: no copies, the scores stay on the device
+            with torch.cuda.stream(compute):
+                lane_engine.forward(net, coordinates, self.voxel_size, out=d_out)
+                done = torch.cuda.Event()
+                done.record(compute)
+            p["busy"][slot] = done
+            return _Pending(done, d_out, lane_engine)
         with torch.cuda.stream(p["copy"]):
             d_in.copy_(coordinates, non_blocking=True)
             ready = torch.cuda.Event()
