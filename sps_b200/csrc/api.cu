@@ -39,6 +39,7 @@ static size_t carve(sps_ctx* c, void* base, int64_t max_points) {
   c->n_dev = c->counts + 10;
   c->nblocks = c->counts + 11;
   c->cells = cv.take<int32_t>((size_t)N * 64);
+  c->occ = cv.take<unsigned long long>(N);
   c->staging = cv.take<float>((size_t)N * 8);
   c->scores = cv.take<float>(N);
   c->table_cap = table_capacity(N);

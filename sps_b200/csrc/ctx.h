@@ -18,6 +18,7 @@ struct sps_ctx {
   int32_t* n_dev = nullptr;    // device copy of n (so level-0 kernels share the code path)
   int32_t* nblocks = nullptr;  // blocks in the current level's block table
   int32_t* cells = nullptr;    // [max_points][64] voxel rows per 4x4x4 block (upper bound: one block per voxel)
+  unsigned long long* occ = nullptr;  // [max_points] 64-bit occupancy word per block
 
   float* staging = nullptr;    // [max_points][8] host->device landing zone
   float* scores = nullptr;     // [max_points]
@@ -46,7 +47,9 @@ struct sps_ctx {
 namespace sps {
 // conv0 fused into the map-building pass (level-0 block table still alive): see maps.cu
 struct Conv0Fused {
-  const float* feat; const float* w; const float* shift; int round_out; float* out; int64_t out_ld;
+  const float* feat;   // per-voxel input feature, or nullptr: every voxel carries `cfeat`
+  float cfeat;
+  const float* w; const float* shift; int round_out; float* out; int64_t out_ld;
 };
 constexpr int kBufWidth[sps_ctx::NBUF] = {16, 8, 8, 24, 8, 16, 48, 16, 32, 96, 32, 64, 64, 64, 64, 32, 32,
                                           16, 16, 8, 1, 1};

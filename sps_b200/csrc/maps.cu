@@ -247,11 +247,15 @@ __global__ void k_block_insert(const unsigned long long* __restrict__ keys, cons
   }
 }
 
-__global__ void k_cells_clear(int32_t* __restrict__ cells, const int32_t* __restrict__ nblocks) {
-  const int64_t total = (int64_t)(*nblocks) * 16;  // int4 stores
+__global__ void k_cells_clear(int32_t* __restrict__ cells, unsigned long long* __restrict__ occ,
+                              const int32_t* __restrict__ nblocks) {
+  const int64_t nb = *nblocks;
+  const int64_t total = nb * 16;  // int4 stores
   const int4 v = make_int4(-1, -1, -1, -1);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     reinterpret_cast<int4*>(cells)[i] = v;
+    if (i < nb) occ[i] = 0ull;
+  }
 }
 
 __device__ __forceinline__ int cell_local(unsigned long long key, int L) {
@@ -260,10 +264,13 @@ __device__ __forceinline__ int cell_local(unsigned long long key, int L) {
 
 __global__ void k_cells_fill(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr, int L,
                              const Slot* __restrict__ tab, const uint32_t* __restrict__ bslot,
-                             int32_t* __restrict__ cells) {
+                             int32_t* __restrict__ cells, unsigned long long* __restrict__ occ) {
   const int n = *n_ptr;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    cells[(int64_t)tab[bslot[i]].val * 64 + cell_local(keys[i], L)] = i;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int id = tab[bslot[i]].val, l = cell_local(keys[i], L);
+    cells[(int64_t)id * 64 + l] = i;
+    atomicOr(occ + id, 1ull << l);     // 64-bit occupancy word per block: presence tests without the index read
+  }
 }
 
 // Kernel map of an odd hyper-cube kernel (K0,K0,K0,KT) on tensor stride [2^L]*3+[1] through the
@@ -272,8 +279,9 @@ __global__ void k_cells_fill(const unsigned long long* __restrict__ keys, const 
 template <int K0, int KT>
 __global__ void __launch_bounds__(256)
 k_kernel_map_blk(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr,
-                 const Slot* __restrict__ tab, const int32_t* __restrict__ cells, int L, int32_t* __restrict__ nbr,
-                 int64_t ld, uint32_t* __restrict__ tile_masks) {
+                 const Slot* __restrict__ tab, const int32_t* __restrict__ cells,
+                 const unsigned long long* __restrict__ occ, int L, int32_t* __restrict__ nbr, int64_t ld,
+                 uint32_t* __restrict__ tile_masks) {
   const int n = *n_ptr;
   if (n == 0) return;
   constexpr int R = K0 / 2, K3 = K0 * K0 * K0;
@@ -293,15 +301,15 @@ k_kernel_map_blk(const unsigned long long* __restrict__ keys, const int32_t* __r
     const int cy = (int)((key >> kYShift) & ((1u << kYBits) - 1)) >> L;
     const int cz = (int)((key >> kZShift) & ((1u << kZBits) - 1)) >> L;
     const unsigned long long bt = (key & (0xFFull << kBShift)) | (unsigned long long)(unsigned)(pok ? t2 : 0);
-    unsigned long long cached_key = kEmptyKey;
+    unsigned long long cached_key = kEmptyKey, cached_occ = 0ull;
     const int32_t* cached = nullptr;
     uint32_t* tm = tile_masks ? tile_masks + 4 * (o0 >> 7) : nullptr;
 #pragma unroll 1
     for (int dz = -R; dz <= R; ++dz) {
       const int nz = cz + dz;
       const bool zok = pok && (unsigned)nz < (unsigned)zlim;
-#pragma unroll 1
-      for (int dy = -R; dy <= R; ++dy) {
+#pragma unroll
+      for (int dy = -R; dy <= R; ++dy) {   // (dy, dx) unrolled: up to K0*K0 independent probes in flight per thread
         const int ny = cy + dy;
         const bool yok = zok && (unsigned)ny < (unsigned)xlim;
         const unsigned long long byz = bt | ((unsigned long long)(unsigned)((ny >> 2) << (L + 2)) << kYShift) |
@@ -316,9 +324,11 @@ k_kernel_map_blk(const unsigned long long* __restrict__ keys, const int32_t* __r
             if (bkey != cached_key) {
               cached_key = bkey;
               const int id = table_find(tab, mask, bkey);
-              cached = id >= 0 ? cells + (int64_t)id * 64 : nullptr;
+              cached = cells + (int64_t)(id >= 0 ? id : 0) * 64;
+              cached_occ = id >= 0 ? __ldg(occ + id) : 0ull;
             }
-            if (cached) res = __ldg(cached + lyz + (nx & 3));
+            const int l = lyz + (nx & 3);
+            if ((cached_occ >> l) & 1ull) res = __ldg(cached + l);
           }
           const int k3 = (dx + R) + K0 * ((dy + R) + K0 * (dz + R));
           if (live) out[(int64_t)k3 * ld] = res;
@@ -329,6 +339,89 @@ k_kernel_map_blk(const unsigned long long* __restrict__ keys, const int32_t* __r
         }
       }
     }
+  }
+}
+
+// conv0 when every voxel carries the SAME input feature c (SPSModel.forward: the mean of the constant
+// 0.5 point features, models.py:22-25): out[o] = relu(c * sum_{k present} W[k][:] + shift).  Only the
+// PRESENCE of the 125 neighbours matters, and that is one bit of the 64-bit occupancy word of a 4x4x4
+// block: 8 block probes + 125 bit tests per voxel, no index reads at all.
+__global__ void __launch_bounds__(256)
+k_conv0_const(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr,
+              const Slot* __restrict__ tab, const unsigned long long* __restrict__ occ, float cfeat,
+              const float* __restrict__ w, const float* __restrict__ shift, int round_out, float* __restrict__ out,
+              int64_t out_ld) {
+  __shared__ float w_s[125 * 8];
+  for (int i = threadIdx.x; i < 125 * 8; i += blockDim.x) w_s[i] = __ldg(w + i);
+  __syncthreads();
+  const int n = *n_ptr;
+  if (n == 0) return;
+  const uint32_t mask = table_capacity(n) - 1;
+  const int blim = 1 << (kXBits - 2), zblim = 1 << (kZBits - 2);
+  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += gridDim.x * blockDim.x) {
+    const unsigned long long key = keys[o];
+    const int cx = (int)((key >> kXShift) & ((1u << kXBits) - 1));
+    const int cy = (int)((key >> kYShift) & ((1u << kYBits) - 1));
+    const int cz = (int)((key >> kZShift) & ((1u << kZBits) - 1));
+    const unsigned long long bt = key & ((0xFFull << kBShift) | ((1ull << kTBits) - 1));
+    // the window [c-2, c+2] touches at most two blocks per axis: b0 and b0 + 1.  Pass 1 (block-relative,
+    // divergent but ALU-only): collect the presence bits of the 125 neighbours into a 128-bit vector,
+    // bit k = kernel offset index.  Pass 2 (warp-uniform over k): weights are shared-memory broadcasts.
+    const int bx0 = (cx - 2) >> 2, by0 = (cy - 2) >> 2, bz0 = (cz - 2) >> 2;
+    unsigned long long p_lo = 0ull, p_hi = 0ull;
+#pragma unroll
+    for (int jb = 0; jb < 8; ++jb) {
+      const int bx = bx0 + (jb & 1), by = by0 + ((jb >> 1) & 1), bz = bz0 + (jb >> 2);
+      const int x_lo = max(cx - 2, bx * 4), x_hi = min(cx + 2, bx * 4 + 3);
+      const int y_lo = max(cy - 2, by * 4), y_hi = min(cy + 2, by * 4 + 3);
+      const int z_lo = max(cz - 2, bz * 4), z_hi = min(cz + 2, bz * 4 + 3);
+      if (x_lo > x_hi || y_lo > y_hi || z_lo > z_hi) continue;
+      if ((unsigned)bx >= (unsigned)blim || (unsigned)by >= (unsigned)blim || (unsigned)bz >= (unsigned)zblim) continue;
+      const unsigned long long bkey = bt | ((unsigned long long)(unsigned)(bx << 2) << kXShift) |
+                                      ((unsigned long long)(unsigned)(by << 2) << kYShift) |
+                                      ((unsigned long long)(unsigned)(bz << 2) << kZShift);
+      const int id = table_find(tab, mask, bkey);
+      if (id < 0) continue;
+      const unsigned long long m = __ldg(occ + id);
+      const unsigned long long xmask = (1ull << (x_hi - x_lo + 1)) - 1ull;
+      for (int nz = z_lo; nz <= z_hi; ++nz)
+        for (int ny = y_lo; ny <= y_hi; ++ny) {
+          const unsigned long long bits = (m >> (4 * (ny & 3) + 16 * (nz & 3) + (x_lo & 3))) & xmask;
+          const int k0 = (x_lo - cx + 2) + 5 * ((ny - cy + 2) + 5 * (nz - cz + 2));   // 0..124
+          if (k0 < 64) {
+            p_lo |= bits << k0;
+            if (k0 > 60) p_hi |= bits >> (64 - k0);
+          } else {
+            p_hi |= bits << (k0 - 64);
+          }
+        }
+    }
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+#pragma unroll 5
+    for (int k = 0; k < 125; ++k) {
+      const bool hit = ((k < 64 ? p_lo >> k : p_hi >> (k - 64)) & 1ull) != 0ull;
+      const float4 w0 = *reinterpret_cast<const float4*>(w_s + k * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(w_s + k * 8 + 4);
+      if (hit) {
+        acc[0] += w0.x; acc[1] += w0.y; acc[2] += w0.z; acc[3] += w0.w;
+        acc[4] += w1.x; acc[5] += w1.y; acc[6] += w1.z; acc[7] += w1.w;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float v = fmaxf(fmaf(cfeat, acc[c], __ldg(shift + c)), 0.f);
+      if (round_out) {
+        uint32_t r;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+        v = __uint_as_float(r);
+      }
+      acc[c] = v;
+    }
+    float* op = out + (int64_t)o * out_ld;
+    *reinterpret_cast<float4*>(op) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(op + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
 }
 
@@ -515,18 +608,22 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
     k_set_i32<<<1, 1, 0, st>>>(ctx->nblocks, 0);
     k_block_insert<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[L], ctx->counts + L, L + 2, ctx->table, ctx->slot_of,
                                                       ctx->nblocks);
-    k_cells_clear<<<grid_for(n * 16, 256), 256, 0, st>>>(ctx->cells, ctx->nblocks);
+    k_cells_clear<<<grid_for(n * 16, 256), 256, 0, st>>>(ctx->cells, ctx->occ, ctx->nblocks);
     k_cells_fill<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[L], ctx->counts + L, L, ctx->table, ctx->slot_of,
-                                                    ctx->cells);
+                                                    ctx->cells, ctx->occ);
   };
   build_blocks(0);
   prof_mark("blocks.L0", st);
   if (c0) {
-    k_conv0_blk<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->table, ctx->cells, c0->feat, c0->w,
-                                                   c0->shift, c0->round_out, c0->out, c0->out_ld);
+    if (c0->feat)   // per-voxel features: gather them through the block table
+      k_conv0_blk<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->table, ctx->cells, c0->feat,
+                                                     c0->w, c0->shift, c0->round_out, c0->out, c0->out_ld);
+    else            // one constant feature (SPSModel.forward): presence bits only
+      k_conv0_const<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->table, ctx->occ, c0->cfeat,
+                                                       c0->w, c0->shift, c0->round_out, c0->out, c0->out_ld);
     prof_mark("conv0+kmap5", st);
   } else {
-    k_kernel_map_blk<5, 1><<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->table, ctx->cells, 0,
+    k_kernel_map_blk<5, 1><<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->table, ctx->cells, ctx->occ, 0,
                                                               ctx->nbr5, ctx->ld, nullptr);
     prof_mark("kmap5.L0", st);
   }
@@ -534,8 +631,8 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
   const size_t mask_bytes = (size_t)(n / 128 + 1) * 16;
   SPS_CUDA_CHECK(cudaMemsetAsync(ctx->tmask3[0], 0, mask_bytes, st));
   k_kernel_map_blk<3, 3><<<dim3(grid_for(n, 256, 148 * 8), 3), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->table,
-                                                                              ctx->cells, 0, ctx->nbr3[0], ctx->ld,
-                                                                              ctx->tmask3[0]);
+                                                                              ctx->cells, ctx->occ, 0, ctx->nbr3[0],
+                                                                              ctx->ld, ctx->tmask3[0]);
   prof_mark("kmap3.L0", st);
   for (int L = 1; L < SPS_NUM_LEVELS; ++L) {
     const int32_t* n_fine = ctx->counts + (L - 1);
@@ -553,8 +650,8 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
     prof_mark(nm_s[L], st);
     SPS_CUDA_CHECK(cudaMemsetAsync(ctx->tmask3[L], 0, mask_bytes, st));
     k_kernel_map_blk<3, 3><<<dim3(grid_for(n, 256, 148 * 8), 3), 256, 0, st>>>(ctx->keys[L], ctx->counts + L, ctx->table,
-                                                                                ctx->cells, L, ctx->nbr3[L], ctx->ld,
-                                                                                ctx->tmask3[L]);
+                                                                                ctx->cells, ctx->occ, L, ctx->nbr3[L],
+                                                                                ctx->ld, ctx->tmask3[L]);
     prof_mark(nm_k[L], st);
   }
   SPS_CUDA_CHECK(cudaGetLastError());

@@ -360,11 +360,7 @@ int forward_impl(sps_ctx* ctx, const sps_net* net, const float* d_points, int64_
   prof_mark("voxelize", st);
   // TensorField.sparse(): voxel feature = mean of the constant 0.5 point features = 0.5
   // (src/sps/models/models.py:22-25)
-  int64_t g = ((n > 0 ? n : 1) + 255) / 256;
-  if (g > 148 * 8) g = 148 * 8;
-  k_fill_f32<<<(int)g, 256, 0, st>>>(ctx->buf[sps_ctx::FEAT0], ctx->counts + 0, 0.5f);
-  Conv0Fused c0{ctx->buf[sps_ctx::FEAT0], net->conv0.w, net->conv0.shift, conv_backend() != 1,
-                ctx->buf[sps_ctx::CAT8] + 8, 16};
+  Conv0Fused c0{nullptr, 0.5f, net->conv0.w, net->conv0.shift, conv_backend() != 1, ctx->buf[sps_ctx::CAT8] + 8, 16};
   rc = build_maps_impl(ctx, &c0, st);
   if (rc != SPS_OK) return rc;
   rc = unet_forward(ctx, net, ctx->buf[sps_ctx::FEAT0], ctx->buf[sps_ctx::LOGITS], st, /*conv0_done=*/true);
@@ -372,7 +368,7 @@ int forward_impl(sps_ctx* ctx, const sps_net* net, const float* d_points, int64_
   rc = sps_devox_sigmoid(ctx->buf[sps_ctx::LOGITS], ctx->inv, n_scores, d_scores, st);
   if (rc != SPS_OK) return rc;
   prof_mark("devox_sigmoid", st);
-  g_forward_launches += 5 + 56 + 1 + 1;  // voxelize, maps, feature fill, devox
+  g_forward_launches += 5 + 56 + 1;  // voxelize, maps, feature fill, devox
   return SPS_OK;
 }
 }  // namespace sps
