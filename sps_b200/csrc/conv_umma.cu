@@ -30,15 +30,29 @@
 
 namespace sps {
 
-#ifndef SPS_PRODUCER_WARPS
-#define SPS_PRODUCER_WARPS 8
+#ifndef SPS_PRODUCER_GROUPS
+#define SPS_PRODUCER_GROUPS 1
 #endif
-constexpr int kProducerWarps = SPS_PRODUCER_WARPS;    // 8 or 16
+// Producer groups of 8 warps; group g writes the stages with (stage index % groups) == g, so several stages
+// of one tile are being gathered at once without multiplying the per-stage instruction count.
+constexpr int kGroups = SPS_PRODUCER_GROUPS;
+constexpr int kProducerWarps = 8 * kGroups;
 __device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kProducerWarps * 32) : "memory"); }
 
 constexpr int kProducerThreads = kProducerWarps * 32;  // producer warps: gather A/B, stage kernel-map slices
-constexpr int kRowsPerThread = kTileM * 8 / kProducerThreads;   // A chunks per thread per stage (4 or 2)
-constexpr int kRowStep = kProducerThreads / 8;        // row distance between a thread's chunks
+constexpr int kGroupThreads = 256;                    // threads that write one stage
+#ifndef SPS_ARRIVE_LAG
+#define SPS_ARRIVE_LAG 0
+#endif
+// Stage-full signalling.  LAG > 0: every thread commits its copies as a cp.async group, and once the group
+// issued LAG stages earlier has landed (cp.async.wait_group) ONE lane per warp arrives on that stage's
+// barrier -- 8 arrivals per stage.  LAG == 0: every thread arrives asynchronously
+// (cp.async.mbarrier.arrive.noinc) -- 256 arrivals on one mbarrier word per stage, which serialise.
+constexpr int kArriveLag = SPS_ARRIVE_LAG;
+constexpr int kFullArrivals = kArriveLag > 0 ? kGroupThreads / 32 : kGroupThreads;
+static_assert(kGroups == 1 || kArriveLag == 0, "lagged arrivals assume one producer group");
+constexpr int kRowsPerThread = kTileM * 8 / kGroupThreads;      // A chunks per thread per stage (4)
+constexpr int kRowStep = kGroupThreads / 8;           // row distance between a thread's chunks
 constexpr int kMmaWarp = kProducerWarps;              // next warp: tcgen05.mma issue
 // the 4 warps after it: epilogue (TMEM -> registers -> global)
 constexpr int kCtaThreads = kProducerThreads + 32 + 128;
@@ -82,7 +96,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_conv_umma(const sps_conv_arg
   if (sA_u & 1023) __trap();  // SWIZZLE_128B atoms need 1024-byte aligned stage bases
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(bar_full + 8 * s, kProducerThreads); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(bar_full + 8 * s, kFullArrivals); mbar_init(bar_empty + 8 * s, 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_idx + 8 * i, kProducerThreads);
       mbar_init(bar_accf + 8 * i, 1);
@@ -117,11 +131,12 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_conv_umma(const sps_conv_arg
   auto tile_stages = [&](int nact) { return (GPC < 8 ? (nact + EPS - 1) / EPS : nact * SPE) + st2; };
 
   if (warp < kMmaWarp) {
-    // =========================== PRODUCERS (256 threads) ===========================
+    // =========================== PRODUCERS (kGroups x 256 threads) ===========================
     const uint32_t in_ld_b = (uint32_t)a.in_ld * 4u, in2_ld_b = (uint32_t)a.in2_ld * 4u;
     const char* in_b = reinterpret_cast<const char*>(a.in);
     const char* in2_b = reinterpret_cast<const char*>(a.in2);
-    const int r0 = tid >> 3, cB = tid & 7;      // gather: chunk column cB of rows r0 + kRowStep*i
+    const int grp = tid / kGroupThreads, tg = tid % kGroupThreads;
+    const int r0 = tg >> 3, cB = tg & 7;        // gather: chunk column cB of rows r0 + kRowStep*i
     const int rI = tid & 127, hI = tid >> 7;    // kernel-map staging: row rI, offsets hI, hI + kProducerThreads/128, ...
     const uint32_t a_off = (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128) + (((uint32_t)cB ^ (uint32_t)(r0 & 7)) << 4);
 
@@ -168,23 +183,40 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_conv_umma(const sps_conv_arg
     const bool b_lane = r0 < NPAD;                  // narrow layers: only some threads carry a weight chunk
     uint32_t slot = 0, phase = 0;
     uint32_t a_slot = sA_u + a_off, b_slot = sB_u, bar_e = bar_empty, bar_f = bar_full;
+    int turn = 0;   // stage counter modulo kGroups: whose turn it is to write the next stage
+    int issued = 0;                 // stages this thread has written so far (lagged arrival bookkeeping)
+    uint32_t bar_lag = bar_full;    // barrier of the oldest stage whose arrival is still owed
 
     // write this thread's share of one stage: 4 A chunks (rows r0+32i, column cB) + its weight chunk(s)
     auto emit = [&](const char* base, uint32_t ld_b, const int (&idx)[kRowsPerThread], uint32_t cg_off, bool cg_ok, int kofB) {
-      mbar_wait(bar_e, phase ^ 1);                  // the MMAs that read this slot have completed
+      if (turn == grp) {
+        mbar_wait(bar_e, phase ^ 1);                // the MMAs that read this slot have completed
 #pragma unroll
-      for (int i = 0; i < kRowsPerThread; ++i) {
-        const bool ok = cg_ok && idx[i] >= 0;
-        cp_async16(a_slot + i * (kRowStep * 128), base + (ok ? (uint32_t)idx[i] * ld_b + cg_off : 0u), ok ? 16u : 0u);
-      }
-      if (b_lane) {
+        for (int i = 0; i < kRowsPerThread; ++i) {
+          const bool ok = cg_ok && idx[i] >= 0;
+          cp_async16(a_slot + i * (kRowStep * 128), base + (ok ? (uint32_t)idx[i] * ld_b + cg_off : 0u), ok ? 16u : 0u);
+        }
+        if (b_lane) {
 #pragma unroll
-        for (int i = 0; i < NB; ++i) {
-          const bool ok = kofB >= 0 && wok[i];
-          cp_async16(b_slot + b_off[i], ok ? wrow[i] + kofB : p.wt, ok ? 16u : 0u);
+          for (int i = 0; i < NB; ++i) {
+            const bool ok = kofB >= 0 && wok[i];
+            cp_async16(b_slot + b_off[i], ok ? wrow[i] + kofB : p.wt, ok ? 16u : 0u);
+          }
+        }
+        if (kArriveLag == 0) {
+          cp_async_arrive(bar_f);                   // fires when this thread's copies of the stage have landed
+        } else {
+          cp_async_commit();
+          if (++issued > kArriveLag) {              // the stage issued kArriveLag stages ago has landed by now
+            cp_async_wait<kArriveLag>();
+            fence_proxy_async();                    // generic-proxy smem writes -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_lag);
+            bar_lag = (bar_lag == bar_full + 8 * (S - 1)) ? bar_full : bar_lag + 8;
+          }
         }
       }
-      cp_async_arrive(bar_f);                       // fires when this thread's copies of the stage have landed
+      if (++turn == kGroups) turn = 0;
       if (++slot == S) {
         slot = 0; phase ^= 1;
         a_slot = sA_u + a_off; b_slot = sB_u; bar_e = bar_empty; bar_f = bar_full;
@@ -211,7 +243,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_conv_umma(const sps_conv_arg
         const bool cg_ok = cg < gpk;
         const int nst_map = (nact + EPS - 1) / EPS;
         for (int st = 0, e = e_off; st < nst_map; ++st, e += EPS) {
-          const bool e_ok = e < nact;
+          const bool e_ok = e < nact && turn == grp;   // another group's stage: nothing to look up
           const int32_t* sk = sx + (e_ok ? e : 0) * kTileM;
 #pragma unroll
           for (int i = 0; i < kRowsPerThread; ++i) idx[i] = e_ok ? sk[kRowStep * i] : -1;
@@ -240,6 +272,15 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_conv_umma(const sps_conv_arg
       }
     }
     cp_async_wait<0>();
+    if (kArriveLag > 0) {           // flush the arrivals still owed for the last stages
+      fence_proxy_async();
+      __syncwarp();
+      const int owed = issued < kArriveLag ? issued : kArriveLag;
+      for (int i = 0; i < owed; ++i) {
+        if (lane == 0) mbar_arrive(bar_lag);
+        bar_lag = (bar_lag == bar_full + 8 * (S - 1)) ? bar_full : bar_lag + 8;
+      }
+    }
   } else if (warp == kMmaWarp) {
     // =========================== MMA ISSUER (one lane) ===========================
     const uint32_t idesc = make_idesc_tf32(NPAD);
@@ -256,7 +297,9 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_conv_umma(const sps_conv_arg
       for (int it = 0; it < nstages; ++it, ++gs) {
         const uint32_t slot = gs % S;
         mbar_wait(bar_full + 8 * slot, (gs / S) & 1);
-        fence_proxy_async();
+#ifdef SPS_MMA_PROXY_FENCE
+        fence_proxy_async();   // not needed: completion of cp.async through the mbarrier orders the writes (as CUTLASS)
+#endif
         tc_fence_after();
         if (lane == 0) {
           const uint64_t adesc = make_smem_desc(sA_u + slot * kAStageBytes);

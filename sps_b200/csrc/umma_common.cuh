@@ -27,8 +27,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}\n" ::"r"(bar), "r"(parity)
       : "memory");
 }
+#ifdef SPS_CP_CG
+#define SPS_CP_ASYNC16 "cp.async.cg.shared.global [%0], [%1], 16, %2;"
+#else
+#define SPS_CP_ASYNC16 "cp.async.ca.shared.global [%0], [%1], 16, %2;"
+#endif
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+  asm volatile(SPS_CP_ASYNC16 ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
