@@ -117,6 +117,9 @@ typedef struct sps_conv_args {
                                tensor-core layer does not truncate its operand               */
   const uint32_t* tile_mask; /* tensor-core path: [ceil(n_out/128)][4] present-offset bitmasks of
                                `map` per 128-row tile (sps_kernel_map_tile_masks); NULL -> CUDA-core */
+  const int32_t* perm;      /* optional processing order: tile t covers output rows perm[128t..128t+127]
+                               (tile_mask must describe the tiles in THIS order); results do not
+                               depend on it.  NULL = identity                                  */
 } sps_conv_args;
 /* MinkowskiConvolution / MinkowskiConvolutionTranspose (+ folded MinkowskiBatchNorm, ReLU,
  * residual) forward: minkunet.py:55-158, resnet.py:97-108, ME BasicBlock.  Served by the tcgen05
@@ -201,6 +204,9 @@ int sps_set_conv_backend(int backend);
  * the cp.async producer kernel everywhere.  The TMA variant is parity-clean but measured ~3x
  * slower (128-byte boxes are too small for the TMA engine), kept for A/B measurements. */
 int sps_set_tma_gather(int on);
+/* 1 (default): the fused forward visits the rows of every 3x3x3x3 convolution in an order sorted
+ * by neighbourhood shape (fewer kernel offsets per 128-row tile); 0: physical row order. */
+int sps_set_pattern_sort(int on);
 /* Per-tile present-offset bitmasks of a kernel map (K <= 81) for the tensor-core path:
  * d_masks uint32 [ceil(n_out_max/128)][4]. */
 int sps_kernel_map_tile_masks(const int32_t* d_map, int64_t map_ld, int K, const int32_t* d_n_out,

@@ -52,12 +52,24 @@ static size_t carve(sps_ctx* c, void* base, int64_t max_points) {
     c->keys[L] = cv.take<unsigned long long>(N);
     c->nbr3[L] = cv.take<int32_t>((size_t)81 * ld);
     c->tmask3[L] = cv.take<uint32_t>((size_t)(ld / 128 + 1) * 4);
+    c->ptmask[L] = cv.take<uint32_t>((size_t)(ld / 128 + 1) * 4);
+    c->perm[L] = cv.take<int32_t>(N);
     c->parent[L] = (L < SPS_NUM_LEVELS - 1) ? cv.take<int32_t>(N) : nullptr;
     c->child[L] = (L > 0) ? cv.take<int32_t>((size_t)8 * ld) : nullptr;
     c->upmap[L] = (L < SPS_NUM_LEVELS - 1) ? cv.take<int32_t>((size_t)8 * ld) : nullptr;
   }
   c->nbr5 = cv.take<int32_t>((size_t)125 * ld);
   c->tmask8 = cv.take<uint32_t>((size_t)(ld / 128 + 1) * 4);
+  c->vmask = cv.take<uint32_t>((size_t)3 * ld);
+  c->sort_keys[0] = cv.take<uint32_t>(N);
+  c->sort_keys[1] = cv.take<uint32_t>(N);
+  c->sort_vals = cv.take<int32_t>(N);
+  {
+    const size_t hn = (size_t)256 * (N / 1024 + 1);
+    c->sort_hist = cv.take<int32_t>(hn);
+    c->sort_hrank = cv.take<int32_t>(hn);
+    c->sort_hsums = cv.take<int32_t>(hn / 1024 + 2);
+  }
   for (int b = 0; b < sps_ctx::NBUF; ++b) c->buf[b] = cv.take<float>((size_t)N * kBufWidth[b]);
   return (cv.off + 255) & ~size_t(255);
 }

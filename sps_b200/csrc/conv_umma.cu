@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_conv_umma(const sps_conv_arg
       const int row = tile * kTileM + rI;
       const uint32_t dst = sidx_u + (uint32_t)(par * kMaxK * kTileM + rI) * 4u;
       if (row < n_out) {
-        const int32_t* src = a.map + row;
+        const int32_t* src = a.map + (a.perm ? __ldg(a.perm + row) : row);
         for (int e = hI; e < nact; e += kProducerThreads / 128)
           asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (uint32_t)(e * kTileM) * 4u),
                        "l"(src + (int64_t)klist[par * 96 + e] * a.map_ld)
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_conv_umma(const sps_conv_arg
 #pragma unroll
         for (int i = 0; i < kRowsPerThread; ++i) {
           const int rw = tile * kTileM + r0 + kRowStep * i;
-          idx[i] = rw < n_out ? rw : -1;
+          idx[i] = rw < n_out ? (a.perm ? __ldg(a.perm + rw) : rw) : -1;
         }
         const int kbase2 = K * GP;
         for (int s2 = 0, cg = cB; s2 < st2; ++s2, cg += 8)
@@ -321,8 +321,9 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_conv_umma(const sps_conv_arg
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int nstages = tile_stages(tile_nact(tile));
       const int b = n_acc & 1;
-      const int row = tile * kTileM + r;
-      const bool row_ok = row < n_out;
+      const int prow = tile * kTileM + r;
+      const bool row_ok = prow < n_out;
+      const int row = row_ok && a.perm ? __ldg(a.perm + prow) : prow;   // output row this tile lane stands for
       float acc[NPAD];
       if (nstages > 0) {
         mbar_wait(bar_accf + 8 * b, (n_acc >> 1) & 1);

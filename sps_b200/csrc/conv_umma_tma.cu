@@ -311,7 +311,7 @@ static int launch_tma(const sps_conv_args& a, const UmmaParams& p, cudaStream_t 
 
 bool conv_umma_tma_supports(const sps_conv_args& a) {
   // 16-byte global alignment of rows (TMA stride rule) and the wide-channel stage plan
-  return padded_groups(a.cin) >= 8 && (a.in_ld % 4) == 0 && (!a.in2 || (a.in2_ld % 4) == 0) && get_encode() != nullptr;
+  return !a.perm && padded_groups(a.cin) >= 8 && (a.in_ld % 4) == 0 && (!a.in2 || (a.in2_ld % 4) == 0) && get_encode() != nullptr;
 }
 
 int conv_umma_tma(const sps_conv_args& a, const UmmaParams& p, cudaStream_t st) {

@@ -6,7 +6,8 @@ struct sps_ctx {
   int64_t max_points = 0;
   int64_t ld = 0;            // leading dimension of the [K][ld] map tables (multiple of 32)
   int64_t n = 0;             // rows of the last voxelize call
-  bool have_l0 = false, have_maps = false, have_nbr5 = false;
+  bool have_l0 = false, have_maps = false, have_nbr5 = false, have_perm = false;
+  int first_sorted = 0, last_sorted = -1;   // levels whose 3^4 convs may visit rows in pattern-sorted order
 
   char* base = nullptr;
   size_t bytes = 0;
@@ -33,6 +34,12 @@ struct sps_ctx {
   int32_t* parent[SPS_NUM_LEVELS] = {};        // [L] fine row -> parent*8 + k   (L = 0..3)
   int32_t* child[SPS_NUM_LEVELS] = {};         // [L] [8][ld] children of level-L rows (L = 1..4)
   int32_t* upmap[SPS_NUM_LEVELS] = {};         // [L] [8][ld] transposed-conv map of level-L rows (L = 0..3)
+  uint32_t* vmask = nullptr;                   // [3][ld] per-voxel 27-bit presence of the 3x3x3 neighbours per time plane (current level)
+  int32_t* perm[SPS_NUM_LEVELS] = {};          // [L] rows of level L in neighbourhood-shape order (conv processing order)
+  uint32_t* ptmask[SPS_NUM_LEVELS] = {};       // [L] tile masks of nbr3 in perm order
+  uint32_t* sort_keys[2] = {};                 // radix sort ping-pong
+  int32_t* sort_vals = nullptr;
+  int32_t* sort_hist = nullptr; int32_t* sort_hrank = nullptr; int32_t* sort_hsums = nullptr;
   uint32_t* tmask8 = nullptr;                  // [tiles][4] all-eight-offsets mask for the 2x2x2x1 maps
   int32_t* nbr3[SPS_NUM_LEVELS] = {};          // [81][ld]
   int32_t* nbr5 = nullptr;                     // [125][ld]

@@ -219,7 +219,7 @@ __global__ void k_devox_sigmoid(const float* __restrict__ logits, const int32_t*
 
 static int g_forward_launches = 0;
 
-static int run_conv(const uint32_t* tmask, const char* name, const ConvW& w, int mode, const int32_t* map, int64_t map_ld, const int32_t* n_out,
+static int run_conv(const uint32_t* tmask, const int32_t* perm, const char* name, const ConvW& w, int mode, const int32_t* map, int64_t map_ld, const int32_t* n_out,
                     int64_t n_out_max, const float* in, int64_t in_ld, const float* in2, int64_t in2_ld,
                     const float* res, int64_t res_ld, float* out, int64_t out_ld, cudaStream_t st,
                     const float* head_w = nullptr, float head_b = 0.f, float* head_out = nullptr) {
@@ -231,12 +231,21 @@ static int run_conv(const uint32_t* tmask, const char* name, const ConvW& w, int
   if (in2) { a.in2 = in2; a.in2_ld = in2_ld; a.cin2 = w.cin2; a.weight2 = w.w2; }
   a.res = res; a.res_ld = res_ld; a.relu = 1; a.out = out; a.out_ld = out_ld;
   a.head_w = head_w; a.head_b = head_b; a.head_out = head_out;
-  a.weight_kmajor = w.wt; a.kmajor_ld = w.ldk; a.tile_mask = tmask;
+  a.weight_kmajor = w.wt; a.kmajor_ld = w.ldk; a.tile_mask = tmask; a.perm = perm;
   a.round_out = conv_backend() != 1;   // pure fp32 mode keeps full-precision activations
   ++g_forward_launches;
   const int rc = conv_dispatch(a, st);
   prof_mark(name, st);
   return rc;
+}
+
+// 3x3x3x3 conv at level L: rows are visited in neighbourhood-shape order where that pays (sorted level and
+// at least 16 input channels -- for 8-channel layers the scattered row access costs more than the skipped
+// offsets save), otherwise in physical order; both sets of tile masks exist.
+template <class... Args>
+static int run_conv3(sps_ctx* c, int L, const char* name, const ConvW& w, Args... args) {
+  const bool pm = c->have_perm && L >= c->first_sorted && L <= c->last_sorted && w.cin >= 16;
+  return run_conv(pm ? c->ptmask[L] : c->tmask3[L], pm ? c->perm[L] : nullptr, name, w, args...);
 }
 
 int unet_forward(sps_ctx* c, const sps_net* net, const float* feat0, float* logits, cudaStream_t st,
@@ -258,9 +267,9 @@ int unet_forward(sps_ctx* c, const sps_net* net, const float* feat0, float* logi
   static const char* nm_c2[8] = {"block1.conv2", "block2.conv2", "block3.conv2", "block4.conv2",
                                  "block5.conv2", "block6.conv2", "block7.conv2", "block8.conv2+final"};
   int rc;
-#define RUN(...) do { rc = run_conv(nullptr, __VA_ARGS__); if (rc != SPS_OK) return rc; } while (0)
-#define RUN8(...) do { rc = run_conv(c->tmask8, __VA_ARGS__); if (rc != SPS_OK) return rc; } while (0)
-#define RUN3(L_, ...) do { rc = run_conv(c->tmask3[L_], __VA_ARGS__); if (rc != SPS_OK) return rc; } while (0)
+#define RUN(...) do { rc = run_conv(nullptr, nullptr, __VA_ARGS__); if (rc != SPS_OK) return rc; } while (0)
+#define RUN8(...) do { rc = run_conv(c->tmask8, nullptr, __VA_ARGS__); if (rc != SPS_OK) return rc; } while (0)
+#define RUN3(L_, ...) do { rc = run_conv3(c, L_, __VA_ARGS__); if (rc != SPS_OK) return rc; } while (0)
   // conv0p1s1 + bn0 + relu  (minkunet.py:162-164)
   if (!conv0_done) {
     if (!c->have_nbr5) return SPS_ERR_STATE;
@@ -368,7 +377,7 @@ int forward_impl(sps_ctx* ctx, const sps_net* net, const float* d_points, int64_
   rc = sps_devox_sigmoid(ctx->buf[sps_ctx::LOGITS], ctx->inv, n_scores, d_scores, st);
   if (rc != SPS_OK) return rc;
   prof_mark("devox_sigmoid", st);
-  g_forward_launches += 5 + 56 + 1;  // voxelize, maps, feature fill, devox
+  g_forward_launches += 5 + 93 + 1;  // voxelize 5, map building 93 (block tables, strided levels, kernel maps, shape sorts), devox 1  // voxelize, maps, feature fill, devox
   return SPS_OK;
 }
 }  // namespace sps
