@@ -713,11 +713,12 @@ constexpr int kFirstSortedLevel = SPS_FIRST_SORTED_LEVEL;
 #ifndef SPS_LAST_SORTED_LEVEL
 #define SPS_LAST_SORTED_LEVEL 3
 #endif
-constexpr int kLastSortedLevel = SPS_LAST_SORTED_LEVEL;     // level 4 is too small: the sort's launches cost more than it saves   // level 0 hosts only the 8/16-channel block8 convs: sorting it does not pay
+constexpr int kLastSortedLevel = SPS_LAST_SORTED_LEVEL;
+constexpr int64_t kMinRowsForSort = 400000;   // small inputs (single scans) are launch-bound: 42 extra launches do not pay     // level 4 is too small: the sort's launches cost more than it saves   // level 0 hosts only the 8/16-channel block8 convs: sorting it does not pay
 
 // perm[L] = voxel rows of level L sorted by neighbourhood-shape key; ptmask[L] = tile masks in that order
 static int pattern_order(sps_ctx* ctx, int L, cudaStream_t st) {
-  if (!g_pattern_sort || L < kFirstSortedLevel || L > kLastSortedLevel) return SPS_OK;
+  if (!g_pattern_sort || L < kFirstSortedLevel || L > kLastSortedLevel || ctx->n < kMinRowsForSort) return SPS_OK;
   const int64_t n = ctx->n > 0 ? ctx->n : 1;
   const int nb_max = cdiv(n, kSortBlock);
   const int hist_n = 256 * nb_max;
@@ -812,7 +813,7 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
   }
   SPS_CUDA_CHECK(cudaGetLastError());
   ctx->have_maps = true;
-  ctx->have_perm = g_pattern_sort != 0;
+  ctx->have_perm = g_pattern_sort != 0 && ctx->n >= kMinRowsForSort;
   ctx->first_sorted = kFirstSortedLevel;
   ctx->last_sorted = kLastSortedLevel;
   return SPS_OK;
