@@ -204,9 +204,11 @@ int sps_set_conv_backend(int backend);
  * the cp.async producer kernel everywhere.  The TMA variant is parity-clean but measured ~3x
  * slower (128-byte boxes are too small for the TMA engine), kept for A/B measurements. */
 int sps_set_tma_gather(int on);
-/* 1 (default): the fused forward visits the rows of every 3x3x3x3 convolution in an order sorted
- * by neighbourhood shape (fewer kernel offsets per 128-row tile); 0: physical row order. */
-int sps_set_pattern_sort(int on);
+/* The fused forward can visit the rows of the 3x3x3x3 convolutions (levels 1-3, >= 16 input
+ * channels) in an order sorted by neighbourhood shape: fewer kernel offsets per 128-row tile.
+ * mode 0: never (physical row order); 1 (default): for inputs of >= 400 000 rows (smaller ones
+ * are launch-bound, the sort's 42 launches do not pay); 2: always.  Results do not depend on it. */
+int sps_set_pattern_sort(int mode);
 /* Per-tile present-offset bitmasks of a kernel map (K <= 81) for the tensor-core path:
  * d_masks uint32 [ceil(n_out_max/128)][4]. */
 int sps_kernel_map_tile_masks(const int32_t* d_map, int64_t map_ld, int K, const int32_t* d_n_out,

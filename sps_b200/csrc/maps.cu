@@ -718,7 +718,7 @@ constexpr int64_t kMinRowsForSort = 400000;   // small inputs (single scans) are
 
 // perm[L] = voxel rows of level L sorted by neighbourhood-shape key; ptmask[L] = tile masks in that order
 static int pattern_order(sps_ctx* ctx, int L, cudaStream_t st) {
-  if (!g_pattern_sort || L < kFirstSortedLevel || L > kLastSortedLevel || ctx->n < kMinRowsForSort) return SPS_OK;
+  if (!g_pattern_sort || L < kFirstSortedLevel || L > kLastSortedLevel || (g_pattern_sort == 1 && ctx->n < kMinRowsForSort)) return SPS_OK;
   const int64_t n = ctx->n > 0 ? ctx->n : 1;
   const int nb_max = cdiv(n, kSortBlock);
   const int hist_n = 256 * nb_max;
@@ -742,8 +742,9 @@ static int pattern_order(sps_ctx* ctx, int L, cudaStream_t st) {
   return SPS_OK;
 }
 }
-extern "C" int sps_set_pattern_sort(int on) {
-  sps::g_pattern_sort = on != 0;
+extern "C" int sps_set_pattern_sort(int mode) {
+  if (mode < 0 || mode > 2) return SPS_ERR_BAD_ARG;
+  sps::g_pattern_sort = mode;   // 0 off, 1 on for inputs of >= 400k rows (default), 2 always
   return SPS_OK;
 }
 extern "C" int sps_build_maps(sps_ctx* ctx, void* stream_) {
@@ -813,7 +814,7 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
   }
   SPS_CUDA_CHECK(cudaGetLastError());
   ctx->have_maps = true;
-  ctx->have_perm = g_pattern_sort != 0 && ctx->n >= kMinRowsForSort;
+  ctx->have_perm = g_pattern_sort == 2 || (g_pattern_sort == 1 && ctx->n >= kMinRowsForSort);
   ctx->first_sorted = kFirstSortedLevel;
   ctx->last_sorted = kLastSortedLevel;
   return SPS_OK;

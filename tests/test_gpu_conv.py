@@ -115,3 +115,28 @@ def test_unet_backends_agree():
     assert np.abs(res[1] - ref).max() < 1e-5
     assert np.abs(res[0] - ref).max() < 5e-4, np.abs(res[0] - ref).max()
     assert np.mean((res[0] < 0.84) == (ref < 0.84)) >= 0.999
+
+
+def test_pattern_sorted_processing_order_does_not_change_results():
+    """sps_set_pattern_sort: rows visited in neighbourhood-shape order (radix sort + permuted tile masks)."""
+    from conftest import make_case
+    from oracle import sps_oracle as O, me_cpu
+    from sps_b200 import engine, _cabi
+    lib = _cabi.load()
+    rows = make_case("hdl-32", seed=9, n_map_poses=6)
+    pts = rows[:, :5]
+    sd = O.make_state_dict(seed=0, randomize_bn=True)
+    net = engine.Net(sd)
+    eng = engine.Engine(len(pts))
+    d = torch.as_tensor(pts).cuda()
+    out = {}
+    try:
+        for mode in (0, 2):
+            assert lib.sps_set_pattern_sort(mode) == 0
+            out[mode] = eng.forward(net, d, 0.1).cpu().numpy()
+            eng.status()
+    finally:
+        lib.sps_set_pattern_sort(1)
+    ref, _, _ = me_cpu.forward(pts, 0.1, me_cpu.pack_weights(sd))
+    assert np.abs(out[0] - out[2]).max() < 2e-6          # only the grouping of zero contributions differs
+    assert np.abs(out[2] - ref).max() < 5e-4
