@@ -204,6 +204,10 @@ int sps_set_conv_backend(int backend);
  * the cp.async producer kernel everywhere.  The TMA variant is parity-clean but measured ~3x
  * slower (128-byte boxes are too small for the TMA engine), kept for A/B measurements. */
 int sps_set_tma_gather(int on);
+/* Generation of the tensor-core convolution kernel: 6 (default) = k_conv_umma6 (loader warp stages
+ * the kernel-map slices, producers walk the stage ring with compile-time slots); 5 = k_conv_umma
+ * (the round-1 baseline kept for A/B measurements).  Same results bit for bit. */
+int sps_set_umma_variant(int v);
 /* The fused forward can visit the rows of the 3x3x3x3 convolutions (levels 1-3, >= 16 input
  * channels) in an order sorted by neighbourhood shape: fewer kernel offsets per 128-row tile.
  * mode 0: never (physical row order); 1 (default): for inputs of >= 400 000 rows (smaller ones

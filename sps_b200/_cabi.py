@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsps_b200.so")
+# SPS_B200_LIB: an alternative build of the same library (kernel A/B measurements, tools/build_variant.py)
+LIB_PATH = os.environ.get("SPS_B200_LIB") or os.path.join(HERE, "libsps_b200.so")
 
 SPS_OK, SPS_ERR_BAD_ARG, SPS_ERR_CAPACITY, SPS_ERR_COORD_RANGE, SPS_ERR_CUDA, SPS_ERR_UNSUPPORTED, SPS_ERR_STATE = range(7)
 SPS_NUM_LEVELS = 5
@@ -23,7 +24,7 @@ SYMBOLS = [
     "sps_net_create", "sps_net_destroy", "sps_net_set_tensor", "sps_net_device_bytes", "sps_net_finalize",
     "sps_forward", "sps_forward_host", "sps_unet_forward", "sps_devox_sigmoid", "sps_forward_launch_count",
     "sps_map_bytes", "sps_map_build", "sps_map_destroy", "sps_submap_crop_voxel", "sps_submap_crop_radius",
-    "sps_assemble", "sps_memcpy_d2h", "sps_memcpy_h2d", "sps_infer_scan", "sps_infer_scan_scratch_bytes", "sps_conv_kmajor_ld", "sps_conv_pack_kmajor", "sps_kernel_map_tile_masks", "sps_set_tma_gather", "sps_set_pattern_sort",
+    "sps_assemble", "sps_memcpy_d2h", "sps_memcpy_h2d", "sps_infer_scan", "sps_infer_scan_scratch_bytes", "sps_conv_kmajor_ld", "sps_conv_pack_kmajor", "sps_kernel_map_tile_masks", "sps_set_tma_gather", "sps_set_umma_variant", "sps_set_pattern_sort",
     "sps_set_conv_backend", "sps_profile_enable", "sps_profile_read", "sps_ctx_pair_count",
     "sps_confusion_counts", "sps_voxel_mean", "sps_gather_rows", "sps_affine_relu",
 ]
@@ -99,6 +100,7 @@ def load() -> C.CDLL:
         "sps_infer_scan": (i32, [vp, vp, vp, vp, i64, f32, vp, vp, sz, vp, vp]),
         "sps_infer_scan_scratch_bytes": (sz, [i64]),
         "sps_set_tma_gather": (i32, [i32]),
+        "sps_set_umma_variant": (i32, [i32]),
         "sps_set_pattern_sort": (i32, [i32]),
         "sps_kernel_map_tile_masks": (i32, [vp, i64, i32, vp, i64, vp, vp]),
         "sps_conv_kmajor_ld": (i64, [i32, i32, i32]),

@@ -26,6 +26,7 @@
 //     TF32-rounded so the next layer's operand rounding is nearest, not truncation).
 // Operands are TF32 (fp32 storage), accumulation fp32: ~1e-4 score error on the reference
 // network against the 2e-3 budget; bf16 operands measured 6e-4..2e-2 (DESIGN.md "precision").
+#include <cstdlib>
 #include "umma_common.cuh"
 
 namespace sps {
@@ -435,6 +436,8 @@ static int launch_umma_n(const sps_conv_args& a, const UmmaParams& p, cudaStream
 
 bool conv_umma_tma_supports(const sps_conv_args& a);
 int conv_umma_tma(const sps_conv_args& a, const UmmaParams& p, cudaStream_t st);
+int conv_umma6(const sps_conv_args& a, const UmmaParams& p, cudaStream_t st);
+static int g_variant = 6;   // 6: k_conv_umma6 (loader warp, static-slot producers); 5: k_conv_umma
 static int g_use_tma = 0;   // 1: wide layers gather through TMA tile::gather4 (measured 3x slower than cp.async producers: 128-byte boxes)
 
 int conv_umma(const sps_conv_args& a, cudaStream_t st) {
@@ -443,6 +446,9 @@ int conv_umma(const sps_conv_args& a, cudaStream_t st) {
   p.ldk = a.kmajor_ld;
   p.round_out = a.round_out;
   if (g_use_tma && conv_umma_tma_supports(a)) return conv_umma_tma(a, p, st);
+  static const char* env = getenv("SPS_UMMA_VARIANT");   // A/B runs without touching the host code
+  static const int env_variant = env ? atoi(env) : 0;
+  if ((env_variant ? env_variant : g_variant) == 6) return conv_umma6(a, p, st);
   switch (a.cout) {
     case 8:
     case 16: return launch_umma_n<16>(a, p, st);
@@ -453,6 +459,12 @@ int conv_umma(const sps_conv_args& a, cudaStream_t st) {
 }
 
 }  // namespace sps
+
+extern "C" int sps_set_umma_variant(int v) {
+  if (v != 5 && v != 6) return SPS_ERR_BAD_ARG;
+  sps::g_variant = v;
+  return SPS_OK;
+}
 
 extern "C" int sps_set_tma_gather(int on) {
   sps::g_use_tma = on != 0;

@@ -1,0 +1,448 @@
+// tcgen05 implicit-GEMM sparse convolution, generation 6: same maths, tiles, stage layout and
+// epilogue as k_conv_umma (conv_umma.cu), with the gather side rebuilt around what ncu's source
+// view showed about that kernel (profiles/r1_conv_source_level.md): its 8 producer warps spent
+// 27 % of their time staging the next tile's kernel-map slice, 54 % executing ~130 instructions per
+// pipeline stage (ring bookkeeping, 64-bit address selects, a divergent-address arrive loop) and
+// only 8 % waiting for a free stage.  Here
+//   * a dedicated LOADER warp builds the per-tile list of present offsets and stages the kernel-map
+//     slice (and the tile's own row numbers) one tile ahead with cp.async, in a
+//     [entry][row%32][row/32] layout so that a producer thread fetches its four row indices with one
+//     16-byte shared load;
+//   * the stage ring is 4 deep: the gathered rows are re-read from L1 by neighbouring output rows,
+//     and measured run time follows the L1 size the carve-out leaves (4 stages beat 2, 3 and 5-7;
+//     +40 KB of unused shared memory costs +25 % on the 32/48-channel layers).  A variant that
+//     streamed the slices through a 16 KB ring with synchronous L1::no_allocate loads (88 KB of
+//     shared memory in total) was not faster on the wide layers and starved the narrow ones;
+//   * the producers walk the stage ring with COMPILE-TIME slot numbers (the stage loop is unrolled
+//     by the ring depth), so every shared address and mbarrier address is base + immediate and the
+//     "copies landed" arrive is a single uniform-address instruction;
+//   * the per-stage parameters of the next stage are fetched before waiting for its slot;
+//   * global addresses are one IMAD.WIDE per 16-byte chunk.
+// Warp roles (448 threads): 0-7 producers, 8 loader, 9 MMA issuer, 10-13 epilogue.
+#include "umma_common.cuh"
+
+namespace sps {
+
+// ring depth per accumulator width (measured: 4 beats 2, 3 and 5-7; deeper rings cost L1)
+#ifndef SPS_V6_S16
+#define SPS_V6_S16 4
+#endif
+#ifndef SPS_V6_S32
+#define SPS_V6_S32 4
+#endif
+#ifndef SPS_V6_S64
+#define SPS_V6_S64 4
+#endif
+constexpr int kV6ProducerWarps = 8;
+constexpr int kV6ProducerThreads = kV6ProducerWarps * 32;
+constexpr int kV6LoaderWarp = kV6ProducerWarps;
+constexpr int kV6MmaWarp = kV6LoaderWarp + 1;
+constexpr int kV6EpiWarp0 = kV6MmaWarp + 1;
+constexpr int kV6Threads = (kV6EpiWarp0 + 4) * 32;
+constexpr int kV6Entries = kMaxK + 1;                 // present offsets + the tile's own rows
+constexpr int kV6EntryBytes = kTileM * 4;
+constexpr int kV6ParBytes = kV6Entries * kV6EntryBytes;  // one parity buffer of staged row indices
+
+#ifndef SPS_V6_PAD_KB
+#define SPS_V6_PAD_KB 0   // experiment: unused shared memory, shrinks the L1 side of the unified array
+#endif
+template <int NPAD>
+struct V6Cfg {
+  static constexpr int S = NPAD == 64 ? SPS_V6_S64 : NPAD == 32 ? SPS_V6_S32 : SPS_V6_S16;
+  static constexpr int kBStage = NPAD * 128;
+  static constexpr int kTmemCols = 2 * NPAD < 32 ? 32 : 2 * NPAD;
+  // A ring | B ring | row indices [2][82][128] | barriers | klist [2][96] | nact [2] | shift [64] | tmem slot
+  static constexpr size_t smem = (size_t)S * (kAStageBytes + kBStage) + 2 * (size_t)kV6ParBytes +
+                                 8 * (2 * S + 8) + 2 * 96 + 16 + 64 * 4 + 16 + SPS_V6_PAD_KB * 1024;
+};
+
+// 16-byte copy that writes zeros instead when `skip` is set (the ignore-src form: one predicate, no size select)
+__device__ __forceinline__ void cp_async16_or_zero(uint32_t dst, const void* src, bool skip) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %2, 0;\n"
+      "cp.async.ca.shared.global [%0], [%1], 16, p;\n"
+      "}\n" ::"r"(dst), "l"(src), "r"((int)skip)
+      : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+
+template <int NPAD, int GPC>
+__global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_args a, const UmmaParams p) {
+  using Cfg = V6Cfg<NPAD>;
+  constexpr int S = Cfg::S;
+  constexpr int kBStageBytes = Cfg::kBStage;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + S * kAStageBytes;
+  int32_t* sidx = reinterpret_cast<int32_t*>(sB + S * kBStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sidx) + 2 * kV6ParBytes);
+  // bars: full[S], empty[S], idx_full[2], idx_empty[2], acc_full[2], acc_empty[2]
+  uint8_t* klist = reinterpret_cast<uint8_t*>(bars + 2 * S + 8);
+  int32_t* snact = reinterpret_cast<int32_t*>(klist + 2 * 96);
+  float* sshift = reinterpret_cast<float*>(snact + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sshift + 64);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB), sidx_u = smem_u32(sidx);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * S, bar_idxf = bar_empty + 8 * S,
+                 bar_idxe = bar_idxf + 16, bar_accf = bar_idxe + 16, bar_acce = bar_accf + 16;
+  if (sA_u & 1023) __trap();
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(bar_full + 8 * s, kV6ProducerThreads); mbar_init(bar_empty + 8 * s, 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_idxf + 8 * i, 33);                 // 32 async arrivals (copies landed) + 1 for the plain stores
+      mbar_init(bar_idxe + 8 * i, kV6ProducerWarps);
+      mbar_init(bar_accf + 8 * i, 1);
+      mbar_init(bar_acce + 8 * i, 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 64) sshift[tid] = (a.shift && tid < a.cout) ? __ldg(a.shift + tid) : 0.f;
+  if (warp == kV6MmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_out = *a.n_out;
+  const int ntiles = (n_out + kTileM - 1) / kTileM;
+  const int K = a.K;
+  const int gpk = a.cin >> 2;                           // real 16-byte groups per offset
+  const int GP = GPC < 8 ? GPC : padded_groups(a.cin);  // padded groups per offset
+  const int SPE = GPC < 8 ? 1 : GP >> 3;                // stages per offset (Cin >= 24)
+  constexpr int EPS = GPC < 8 ? 8 / GPC : 1;            // offsets per stage (Cin <= 16)
+  const int gpk2 = a.in2 ? (a.cin2 >> 2) : 0;
+  const int st2 = (gpk2 + 7) >> 3;                      // stages of the fused 1x1 term
+  const uint32_t* tmask = a.tile_mask;
+  const int gstep = gridDim.x;
+  auto tile_nact = [&](int tile) {
+    return __popc(__ldg(tmask + 4 * tile)) + __popc(__ldg(tmask + 4 * tile + 1)) + __popc(__ldg(tmask + 4 * tile + 2));
+  };
+  auto tile_stages = [&](int nact) { return (GPC < 8 ? (nact + EPS - 1) / EPS : nact * SPE) + st2; };
+
+  if (warp < kV6ProducerWarps) {
+    // =========================== PRODUCERS (256 threads) ===========================
+    const int r0 = tid >> 3, cB = tid & 7;          // chunk column cB of rows r0 + 32 i
+    const uint32_t a_off = (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128) + (((uint32_t)cB ^ (uint32_t)(r0 & 7)) << 4);
+    const uint32_t in_ld_b = (uint32_t)a.in_ld * 4u, in2_ld_b = (uint32_t)a.in2_ld * 4u;
+    const char* in_b = reinterpret_cast<const char*>(a.in);
+    const char* in2_b = reinterpret_cast<const char*>(a.in2);
+    constexpr int NB = (NPAD + 31) / 32;            // weight chunks per thread per stage
+    const char* wrow[NB];
+    uint32_t b_off[NB];
+    bool wok[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      const int n = r0 + 32 * i;
+      wok[i] = n < a.cout && n < NPAD;
+      wrow[i] = reinterpret_cast<const char*>(p.wt + (int64_t)(wok[i] ? n : 0) * p.ldk);
+      b_off[i] = (uint32_t)((n >> 3) * 1024 + (n & 7) * 128) + (((uint32_t)cB ^ (uint32_t)(n & 7)) << 4);
+    }
+    const bool b_lane = r0 < NPAD;
+    constexpr int GPCc = GPC < 8 ? GPC : 1;
+    const int e_off = GPC < 8 ? cB / GPCc : 0;      // small Cin: which of the stage's offsets this column belongs to
+    const int cg0 = GPC < 8 ? cB % GPCc : cB;       // channel group inside the offset
+
+    // ---- cursor over the stages of this CTA's tiles ----
+    int tile = blockIdx.x, it_tile = 0;
+    int nact = 0, m = 0, nst = 0;                   // present offsets, current stage, stages of the tile
+    int e = 0, sub = 0;                             // large Cin: offset entry and sub-stage
+    uint32_t sx = 0;                                // shared byte address of this thread's int4 in entry 0
+    const uint8_t* kl = klist;
+    // parameters of the stage about to be issued
+    int idx[4] = {-1, -1, -1, -1};
+    const char* base = in_b;
+    uint32_t ld_b = in_ld_b;
+    bool okc = false, bok = false;
+    uint32_t wofs = 0;
+
+    auto lds4 = [&](uint32_t addr) {
+      asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(idx[0]), "=r"(idx[1]), "=r"(idx[2]), "=r"(idx[3])
+                   : "r"(addr));
+    };
+    // fetch the parameters of stage m of the current tile
+    auto fetch = [&]() {
+      if (GPC < 8) {
+        const int nmap = (nact + EPS - 1) / EPS;
+        if (m < nmap) {
+          const int ee = m * EPS + e_off;
+          const bool e_ok = ee < nact;
+          lds4(sx + (uint32_t)(e_ok ? ee : 0) * kV6EntryBytes);
+          base = in_b + cg0 * 16; ld_b = in_ld_b;
+          okc = e_ok && cg0 < gpk; bok = e_ok;
+          wofs = (uint32_t)((int)kl[e_ok ? ee : 0] * GPCc + cg0) * 16u;
+        } else {
+          const int cg = cB + 8 * (m - nmap);
+          lds4(sx + (uint32_t)nact * kV6EntryBytes);
+          base = in2_b + cg * 16; ld_b = in2_ld_b;
+          okc = cg < gpk2; bok = okc;
+          wofs = (uint32_t)(K * GPCc + cg) * 16u;
+        }
+      } else {
+        // entry e (< nact: kernel offset klist[e]; == nact: the fused 1x1 term on the tile's own rows)
+        if (sub == 0) lds4(sx + (uint32_t)e * kV6EntryBytes);
+        const int cg = cB + 8 * sub;
+        const bool self = e >= nact;
+        base = (self ? in2_b : in_b) + cg * 16; ld_b = self ? in2_ld_b : in_ld_b;
+        okc = cg < (self ? gpk2 : gpk); bok = okc;
+        wofs = (uint32_t)((self ? K : (int)kl[e]) * GP + cg) * 16u;
+      }
+    };
+    // make `tile` current (skipping tiles without stages); false when the CTA has no tile left
+    auto open_tile = [&]() -> bool {
+      for (;;) {
+        if (tile >= ntiles) return false;
+        const int par = it_tile & 1;
+        mbar_wait(bar_idxf + 8 * par, (it_tile >> 1) & 1);
+        nact = snact[par];
+        nst = tile_stages(nact);
+        sx = sidx_u + (uint32_t)par * kV6ParBytes + (uint32_t)r0 * 16u;
+        kl = klist + par * 96;
+        m = 0; e = 0; sub = 0;
+        if (nst > 0) { fetch(); return true; }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_idxe + 8 * par);
+        tile += gstep; ++it_tile;
+      }
+    };
+    // step to the next stage; false when the CTA is out of work
+    auto advance = [&]() -> bool {
+      ++m;
+      if (m < nst) {
+        if (GPC >= 8) {
+          const int lim = e < nact ? SPE : st2;
+          if (++sub == lim) { sub = 0; ++e; }
+        }
+        fetch();
+        return true;
+      }
+      __syncwarp();                                   // every lane holds its indices in registers by now
+      if (lane == 0) mbar_arrive(bar_idxe + 8 * (it_tile & 1));
+      tile += gstep; ++it_tile;
+      return open_tile();
+    };
+
+    bool more = open_tile();
+    uint32_t phase = 0;
+    while (more) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        if (more) {
+          mbar_wait(bar_empty + 8 * s, phase ^ 1);    // the MMAs that read slot s have completed
+          const uint32_t dstA = sA_u + (uint32_t)s * kAStageBytes + a_off;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const bool ok = okc && idx[i] >= 0;
+            const uint32_t row = (uint32_t)(idx[i] < 0 ? 0 : idx[i]);
+            cp_async16_or_zero(dstA + i * 4096, base + (uint64_t)row * ld_b, !ok);
+          }
+          if (b_lane) {
+#pragma unroll
+            for (int i = 0; i < NB; ++i)
+              cp_async16_or_zero(sB_u + (uint32_t)s * kBStageBytes + b_off[i], wrow[i] + wofs, !(bok && wok[i]));
+          }
+          cp_async_arrive(bar_full + 8 * s);          // fires when this thread's copies of the stage have landed
+          more = advance();
+        }
+      }
+      phase ^= 1;
+    }
+    cp_async_wait<0>();
+  } else if (warp == kV6LoaderWarp) {
+    // =========================== LOADER (one warp, one tile ahead) ===========================
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gstep, ++it) {
+      const int par = it & 1;
+      mbar_wait(bar_idxe + 8 * par, ((it >> 1) & 1) ^ 1);     // producers are done with this buffer
+      uint8_t* klp = klist + par * 96;
+      int nact = 0;
+#pragma unroll
+      for (int w = 0; w < 3; ++w) {
+        const uint32_t bits = __ldg(tmask + 4 * tile + w);
+        if ((bits >> lane) & 1u) klp[nact + __popc(bits & ((1u << lane) - 1u))] = (uint8_t)(32 * w + lane);
+        nact += __popc(bits);
+      }
+      if (lane == 0) snact[par] = nact;
+      __syncwarp();
+      // lane owns rows lane + 32 i of the tile; staged at [entry][lane][i]
+      const uint32_t dst = sidx_u + (uint32_t)par * kV6ParBytes + (uint32_t)lane * 16u;
+      const int32_t* src[4];
+      bool rok[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int prow = tile * kTileM + lane + 32 * i;
+        rok[i] = prow < n_out;
+        const int row = rok[i] ? (a.perm ? __ldg(a.perm + prow) : prow) : 0;
+        src[i] = a.map + row;
+        asm volatile("st.shared.s32 [%0], %1;" ::"r"(dst + (uint32_t)nact * kV6EntryBytes + 4u * i), "r"(rok[i] ? row : -1) : "memory");
+      }
+      for (int e = 0; e < nact; ++e) {
+        const int64_t koff = (int64_t)klp[e] * a.map_ld;
+        const uint32_t d = dst + (uint32_t)e * kV6EntryBytes;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (rok[i]) cp_async4(d + 4u * i, src[i] + koff);
+          else asm volatile("st.shared.s32 [%0], %1;" ::"r"(d + 4u * i), "r"(-1) : "memory");
+        }
+      }
+      cp_async_arrive(bar_idxf + 8 * par);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_idxf + 8 * par);         // orders the plain shared stores of the whole warp
+    }
+    cp_async_wait<0>();
+  } else if (warp == kV6MmaWarp) {
+    // =========================== MMA ISSUER (one lane) ===========================
+    const uint32_t idesc = make_idesc_tf32(NPAD);
+    uint32_t gs = 0;
+    int n_acc = 0;
+    int tile = blockIdx.x;
+    int nact_next = tile < ntiles ? tile_nact(tile) : 0;
+    for (; tile < ntiles; tile += gstep) {
+      const int nstages = tile_stages(nact_next);
+      if (tile + gstep < ntiles) nact_next = tile_nact(tile + gstep);   // in flight behind this tile's stages
+      if (nstages == 0) continue;
+      const int b = n_acc & 1;
+      mbar_wait(bar_acce + 8 * b, ((n_acc >> 1) & 1) ^ 1);
+      ++n_acc;
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(b * NPAD);
+      for (int it = 0; it < nstages; ++it, ++gs) {
+        const uint32_t slot = gs % S;
+        mbar_wait(bar_full + 8 * slot, (gs / S) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t adesc = make_smem_desc(sA_u + slot * kAStageBytes);
+          const uint64_t bdesc = make_smem_desc(sB_u + slot * kBStageBytes);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            umma_tf32(tacc, adesc + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (it | j) ? 1u : 0u);
+          umma_commit(bar_empty + 8 * slot);
+          if (it == nstages - 1) umma_commit(bar_accf + 8 * b);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // =========================== EPILOGUE (4 warps = 128 TMEM lanes) ===========================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int cout = a.cout;
+    const bool res_vec = a.res && ((reinterpret_cast<uintptr_t>(a.res) & 15) == 0) && ((a.res_ld & 3) == 0);
+    int n_acc = 0;
+    int tile = blockIdx.x;
+    int nact_next = 0, row_next = -1;
+    auto look = [&](int t) {
+      nact_next = tile_nact(t);
+      const int prow = t * kTileM + r;
+      row_next = prow < n_out ? (a.perm ? __ldg(a.perm + prow) : prow) : -1;
+    };
+    if (tile < ntiles) look(tile);
+    for (; tile < ntiles; tile += gstep) {
+      const int nstages = tile_stages(nact_next);
+      const int row = row_next;
+      if (tile + gstep < ntiles) look(tile + gstep);
+      const int b = n_acc & 1;
+      float acc[NPAD];
+      if (nstages > 0) {
+        mbar_wait(bar_accf + 8 * b, (n_acc >> 1) & 1);
+        ++n_acc;
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * NPAD);
+#pragma unroll
+        for (int cb = 0; cb < NPAD / 8; ++cb) tmem_ld8(taddr + cb * 8, acc + cb * 8);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(bar_acce + 8 * b);
+      } else {
+#pragma unroll
+        for (int c = 0; c < NPAD; ++c) acc[c] = 0.f;
+      }
+      if (row < 0) continue;
+      const float* resp = a.res ? a.res + (int64_t)row * a.res_ld : nullptr;
+#pragma unroll
+      for (int c = 0; c < NPAD; c += 4)
+        if (c < cout) {
+          float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (resp) {
+            if (res_vec) rv = __ldg(reinterpret_cast<const float4*>(resp + c));
+            else rv = make_float4(__ldg(resp + c), __ldg(resp + c + 1), __ldg(resp + c + 2), __ldg(resp + c + 3));
+          }
+          const float4 sh = *reinterpret_cast<const float4*>(sshift + c);
+          float v0 = acc[c] + sh.x + rv.x, v1 = acc[c + 1] + sh.y + rv.y, v2 = acc[c + 2] + sh.z + rv.z,
+                v3 = acc[c + 3] + sh.w + rv.w;
+          if (a.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+          acc[c] = v0; acc[c + 1] = v1; acc[c + 2] = v2; acc[c + 3] = v3;
+        }
+      if (a.head_out) {
+        float s = a.head_b;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) s = fmaf(acc[c], __ldg(a.head_w + c), s);
+        a.head_out[row] = s;
+      }
+      if (a.out) {
+        float* o = a.out + (int64_t)row * a.out_ld;
+#pragma unroll
+        for (int c = 0; c < NPAD; c += 4)
+          if (c < cout) {
+            float4 v = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+            if (p.round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+            *reinterpret_cast<float4*>(o + c) = v;
+          }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kV6MmaWarp)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols)
+                 : "memory");
+}
+
+template <int NPAD, int GPC>
+static int launch_umma6(const sps_conv_args& a, const UmmaParams& p, cudaStream_t st) {
+  const size_t smem = V6Cfg<NPAD>::smem;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SPS_CUDA_CHECK(
+        cudaFuncSetAttribute(k_conv_umma6<NPAD, GPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  int64_t tiles = (a.n_out_max + kTileM - 1) / kTileM;
+  if (tiles < 1) tiles = 1;
+  const int grid = (int)(tiles < 148 ? tiles : 148);
+  k_conv_umma6<NPAD, GPC><<<grid, kV6Threads, smem, st>>>(a, p);
+  SPS_CUDA_CHECK(cudaGetLastError());
+  return SPS_OK;
+}
+
+template <int NPAD>
+static int launch_umma6_n(const sps_conv_args& a, const UmmaParams& p, cudaStream_t st) {
+  const int gp = padded_groups(a.cin);
+  if (gp == 2) return launch_umma6<NPAD, 2>(a, p, st);
+  if (gp == 4) return launch_umma6<NPAD, 4>(a, p, st);
+  return launch_umma6<NPAD, 8>(a, p, st);
+}
+
+int conv_umma6(const sps_conv_args& a, const UmmaParams& p, cudaStream_t st) {
+  switch (a.cout) {
+    case 8:
+    case 16: return launch_umma6_n<16>(a, p, st);
+    case 32: return launch_umma6_n<32>(a, p, st);
+    case 64: return launch_umma6_n<64>(a, p, st);
+    default: return SPS_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace sps
