@@ -87,6 +87,7 @@ int sps_unpack_coords(sps_ctx* ctx, int level, int32_t* d_out, void* stream);
 #define SPS_CONV_NBR 0    /* stride-1 (or child-table stride-2) conv through a [K][ld] map   */
 #define SPS_CONV_UP 1     /* transposed 2x2x2x1: out[child[k][c]] = in[c] @ W[k] for coarse rows c */
 
+#define SPS_TILE_SLICE_ENTRIES 82
 typedef struct sps_conv_args {
   int mode;                 /* SPS_CONV_NBR | SPS_CONV_UP                                    */
   int K;                    /* kernel volume (125, 81, 8, 1)                                 */
@@ -120,6 +121,11 @@ typedef struct sps_conv_args {
   const int32_t* perm;      /* optional processing order: tile t covers output rows perm[128t..128t+127]
                                (tile_mask must describe the tiles in THIS order); results do not
                                depend on it.  NULL = identity                                  */
+  const int32_t* tile_slices; /* optional, with perm: the kernel map already gathered per tile --
+                               [tile][SPS_TILE_SLICE_ENTRIES][128] int32, entry e < popcount(mask) = input
+                               rows of the tile's e-th present offset, entry popcount(mask) = the tile's own
+                               rows (perm), each entry laid out [row % 32][row / 32].  NULL = the kernel
+                               gathers from `map` through `perm` itself                          */
 } sps_conv_args;
 /* MinkowskiConvolution / MinkowskiConvolutionTranspose (+ folded MinkowskiBatchNorm, ReLU,
  * residual) forward: minkunet.py:55-158, resnet.py:97-108, ME BasicBlock.  Served by the tcgen05

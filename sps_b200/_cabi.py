@@ -44,7 +44,7 @@ class ConvArgs(C.Structure):
                 ("out", C.c_void_p), ("out_ld", C.c_int64),
                 ("head_w", C.c_void_p), ("head_b", C.c_float), ("head_out", C.c_void_p),
                 ("weight_kmajor", C.c_void_p), ("kmajor_ld", C.c_int64), ("round_out", C.c_int),
-                ("tile_mask", C.c_void_p), ("perm", C.c_void_p)]
+                ("tile_mask", C.c_void_p), ("perm", C.c_void_p), ("tile_slices", C.c_void_p)]
 
 
 class SpsError(RuntimeError):

@@ -54,6 +54,7 @@ static size_t carve(sps_ctx* c, void* base, int64_t max_points) {
     c->tmask3[L] = cv.take<uint32_t>((size_t)(ld / 128 + 1) * 4);
     c->ptmask[L] = cv.take<uint32_t>((size_t)(ld / 128 + 1) * 4);
     c->perm[L] = cv.take<int32_t>(N);
+    c->tslice[L] = (L <= 3) ? cv.take<int32_t>((size_t)(ld / 128 + 1) * SPS_TILE_SLICE_ENTRIES * 128) : nullptr;
     c->parent[L] = (L < SPS_NUM_LEVELS - 1) ? cv.take<int32_t>(N) : nullptr;
     c->child[L] = (L > 0) ? cv.take<int32_t>((size_t)8 * ld) : nullptr;
     c->upmap[L] = (L < SPS_NUM_LEVELS - 1) ? cv.take<int32_t>((size_t)8 * ld) : nullptr;

@@ -57,15 +57,31 @@ struct V6Cfg {
 };
 
 // 16-byte copy that writes zeros instead when `skip` is set (the ignore-src form: one predicate, no size select)
+template <bool kBypassL1>
 __device__ __forceinline__ void cp_async16_or_zero(uint32_t dst, const void* src, bool skip) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %2, 0;\n"
-      "cp.async.ca.shared.global [%0], [%1], 16, p;\n"
-      "}\n" ::"r"(dst), "l"(src), "r"((int)skip)
-      : "memory");
+  if (kBypassL1)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %2, 0;\n"
+        "cp.async.cg.shared.global [%0], [%1], 16, p;\n"
+        "}\n" ::"r"(dst), "l"(src), "r"((int)skip)
+        : "memory");
+  else
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %2, 0;\n"
+        "cp.async.ca.shared.global [%0], [%1], 16, p;\n"
+        "}\n" ::"r"(dst), "l"(src), "r"((int)skip)
+        : "memory");
 }
+#ifndef SPS_V6_A_CG
+#define SPS_V6_A_CG 0
+#endif
+#ifndef SPS_V6_B_CG
+#define SPS_V6_B_CG 0
+#endif
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -245,12 +261,12 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
           for (int i = 0; i < 4; ++i) {
             const bool ok = okc && idx[i] >= 0;
             const uint32_t row = (uint32_t)(idx[i] < 0 ? 0 : idx[i]);
-            cp_async16_or_zero(dstA + i * 4096, base + (uint64_t)row * ld_b, !ok);
+            cp_async16_or_zero<SPS_V6_A_CG != 0>(dstA + i * 4096, base + (uint64_t)row * ld_b, !ok);
           }
           if (b_lane) {
 #pragma unroll
             for (int i = 0; i < NB; ++i)
-              cp_async16_or_zero(sB_u + (uint32_t)s * kBStageBytes + b_off[i], wrow[i] + wofs, !(bok && wok[i]));
+              cp_async16_or_zero<SPS_V6_B_CG != 0>(sB_u + (uint32_t)s * kBStageBytes + b_off[i], wrow[i] + wofs, !(bok && wok[i]));
           }
           cp_async_arrive(bar_full + 8 * s);          // fires when this thread's copies of the stage have landed
           more = advance();
@@ -275,25 +291,34 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
       }
       if (lane == 0) snact[par] = nact;
       __syncwarp();
-      // lane owns rows lane + 32 i of the tile; staged at [entry][lane][i]
       const uint32_t dst = sidx_u + (uint32_t)par * kV6ParBytes + (uint32_t)lane * 16u;
-      const int32_t* src[4];
-      bool rok[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int prow = tile * kTileM + lane + 32 * i;
-        rok[i] = prow < n_out;
-        const int row = rok[i] ? (a.perm ? __ldg(a.perm + prow) : prow) : 0;
-        src[i] = a.map + row;
-        asm volatile("st.shared.s32 [%0], %1;" ::"r"(dst + (uint32_t)nact * kV6EntryBytes + 4u * i), "r"(rok[i] ? row : -1) : "memory");
-      }
-      for (int e = 0; e < nact; ++e) {
-        const int64_t koff = (int64_t)klp[e] * a.map_ld;
-        const uint32_t d = dst + (uint32_t)e * kV6EntryBytes;
+      if (a.tile_slices) {
+        // the level's pass already gathered this tile's slice (entries 0..nact, the last one = own rows)
+        const char* src = reinterpret_cast<const char*>(a.tile_slices + (int64_t)tile * (SPS_TILE_SLICE_ENTRIES * kTileM)) + lane * 16;
+        for (int e = 0; e <= nact; ++e)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)e * kV6EntryBytes),
+                       "l"(src + (size_t)e * kV6EntryBytes)
+                       : "memory");
+      } else {
+        // lane owns rows lane + 32 i of the tile; staged at [entry][lane][i]
+        const int32_t* src[4];
+        bool rok[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          if (rok[i]) cp_async4(d + 4u * i, src[i] + koff);
-          else asm volatile("st.shared.s32 [%0], %1;" ::"r"(d + 4u * i), "r"(-1) : "memory");
+          const int prow = tile * kTileM + lane + 32 * i;
+          rok[i] = prow < n_out;
+          const int row = rok[i] ? (a.perm ? __ldg(a.perm + prow) : prow) : 0;
+          src[i] = a.map + row;
+          asm volatile("st.shared.s32 [%0], %1;" ::"r"(dst + (uint32_t)nact * kV6EntryBytes + 4u * i), "r"(rok[i] ? row : -1) : "memory");
+        }
+        for (int e = 0; e < nact; ++e) {
+          const int64_t koff = (int64_t)klp[e] * a.map_ld;
+          const uint32_t d = dst + (uint32_t)e * kV6EntryBytes;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (rok[i]) cp_async4(d + 4u * i, src[i] + koff);
+            else asm volatile("st.shared.s32 [%0], %1;" ::"r"(d + 4u * i), "r"(-1) : "memory");
+          }
         }
       }
       cp_async_arrive(bar_idxf + 8 * par);

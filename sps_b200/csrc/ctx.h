@@ -6,7 +6,7 @@ struct sps_ctx {
   int64_t max_points = 0;
   int64_t ld = 0;            // leading dimension of the [K][ld] map tables (multiple of 32)
   int64_t n = 0;             // rows of the last voxelize call
-  bool have_l0 = false, have_maps = false, have_nbr5 = false, have_perm = false;
+  bool have_l0 = false, have_maps = false, have_nbr5 = false, have_perm = false, have_slices = false;
   int first_sorted = 0, last_sorted = -1;   // levels whose 3^4 convs may visit rows in pattern-sorted order
 
   char* base = nullptr;
@@ -37,6 +37,7 @@ struct sps_ctx {
   uint32_t* vmask = nullptr;                   // [3][ld] per-voxel 27-bit presence of the 3x3x3 neighbours per time plane (current level)
   int32_t* perm[SPS_NUM_LEVELS] = {};          // [L] rows of level L in neighbourhood-shape order (conv processing order)
   uint32_t* ptmask[SPS_NUM_LEVELS] = {};       // [L] tile masks of nbr3 in perm order
+  int32_t* tslice[SPS_NUM_LEVELS] = {};        // [L] [tiles][82][128] nbr3 gathered per tile in perm order (sorted levels)
   uint32_t* sort_keys[2] = {};                 // radix sort ping-pong
   int32_t* sort_vals = nullptr;
   int32_t* sort_hist = nullptr; int32_t* sort_hrank = nullptr; int32_t* sort_hsums = nullptr;

@@ -427,31 +427,58 @@ k_radix_scatter(const uint32_t* __restrict__ keys, const int32_t* __restrict__ v
   }
 }
 
-// present-offset masks of the 128-row tiles taken in `perm` order
+// present-offset masks of the 128-row tiles taken in `perm` order, and (slices != nullptr) the tiles' slices of
+// the kernel map gathered once for all the convolutions of the level: slices[tile][e][r%32][r/32] = input row
+// of sorted row r under the tile's e-th present offset, entry e = #present = the tile's own rows.
 __global__ void __launch_bounds__(128)
 k_tile_masks_perm(const uint32_t* __restrict__ vmask, int64_t ld, const int32_t* __restrict__ perm,
-                  const int32_t* __restrict__ n_ptr, uint32_t* __restrict__ masks) {
+                  const int32_t* __restrict__ n_ptr, uint32_t* __restrict__ masks,
+                  const int32_t* __restrict__ nbr, int32_t* __restrict__ slices) {
   const int n = *n_ptr;
   const int ntiles = (n + 127) / 128;
   __shared__ uint32_t m[4][3];
+  __shared__ uint8_t klist[96];
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int r = tile * 128 + threadIdx.x;
     uint32_t w0 = 0, w1 = 0, w2 = 0;
+    int v = -1;
     if (r < n) {
-      const int v = perm[r];
+      v = perm[r];
       const uint32_t m0 = vmask[v], m1 = vmask[ld + v], m2 = vmask[2 * ld + v];   // 27 bits per time plane
       w0 = m0 | (m1 << 27);
       w1 = (m1 >> 5) | (m2 << 22);
       w2 = m2 >> 10;
     }
-    w0 = __reduce_or_sync(0xffffffffu, w0);
-    w1 = __reduce_or_sync(0xffffffffu, w1);
-    w2 = __reduce_or_sync(0xffffffffu, w2);
-    if ((threadIdx.x & 31) == 0) { m[threadIdx.x >> 5][0] = w0; m[threadIdx.x >> 5][1] = w1; m[threadIdx.x >> 5][2] = w2; }
+    const uint32_t t0 = __reduce_or_sync(0xffffffffu, w0);
+    const uint32_t t1 = __reduce_or_sync(0xffffffffu, w1);
+    const uint32_t t2 = __reduce_or_sync(0xffffffffu, w2);
+    if ((threadIdx.x & 31) == 0) { m[threadIdx.x >> 5][0] = t0; m[threadIdx.x >> 5][1] = t1; m[threadIdx.x >> 5][2] = t2; }
     __syncthreads();
-    if (threadIdx.x < 3)
-      masks[4 * tile + threadIdx.x] = m[0][threadIdx.x] | m[1][threadIdx.x] | m[2][threadIdx.x] | m[3][threadIdx.x];
+    const uint32_t tm[3] = {m[0][0] | m[1][0] | m[2][0] | m[3][0], m[0][1] | m[1][1] | m[2][1] | m[3][1],
+                            m[0][2] | m[1][2] | m[2][2] | m[3][2]};
+    if (threadIdx.x < 3) masks[4 * tile + threadIdx.x] = tm[threadIdx.x];
     if (threadIdx.x == 3) masks[4 * tile + 3] = 0;
+    if (slices) {
+      const int nact = __popc(tm[0]) + __popc(tm[1]) + __popc(tm[2]);
+      if (threadIdx.x < 96) {
+        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+        if ((tm[w] >> l) & 1u) {
+          const int before = (w > 0 ? __popc(tm[0]) : 0) + (w > 1 ? __popc(tm[1]) : 0) + __popc(tm[w] & ((1u << l) - 1u));
+          klist[before] = (uint8_t)threadIdx.x;
+        }
+      }
+      __syncthreads();
+      int32_t* dst = slices + (int64_t)tile * (SPS_TILE_SLICE_ENTRIES * 128) + (threadIdx.x & 31) * 4 + (threadIdx.x >> 5);
+      const uint32_t mine[3] = {w0, w1, w2};
+#pragma unroll 4
+      for (int e = 0; e < nact; ++e) {
+        const int k = klist[e];
+        int val = -1;
+        if ((mine[k >> 5] >> (k & 31)) & 1u) val = __ldg(nbr + (int64_t)k * ld + v);
+        dst[e * 128] = val;
+      }
+      dst[nact * 128] = v;
+    }
     __syncthreads();
   }
 }
@@ -706,6 +733,10 @@ namespace sps {
 int build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st);
 
 static int g_pattern_sort = 1;
+#ifndef SPS_TILE_SLICES
+#define SPS_TILE_SLICES 1
+#endif
+static const int g_tile_slices = SPS_TILE_SLICES;   // gather the kernel map per sorted tile once per level
 #ifndef SPS_FIRST_SORTED_LEVEL
 #define SPS_FIRST_SORTED_LEVEL 1
 #endif
@@ -737,7 +768,8 @@ static int pattern_order(sps_ctx* ctx, int L, cudaStream_t st) {
     std::swap(va, vb);
   }
   k_tile_masks_perm<<<grid_for(n / 128 + 1, 1, 148 * 16), 128, 0, st>>>(ctx->vmask, ctx->ld, ctx->perm[L], cnt,
-                                                                       ctx->ptmask[L]);
+                                                                       ctx->ptmask[L], ctx->nbr3[L],
+                                                                       g_tile_slices && ctx->tslice[L] ? ctx->tslice[L] : nullptr);
   SPS_CUDA_CHECK(cudaGetLastError());
   return SPS_OK;
 }
@@ -815,6 +847,7 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
   SPS_CUDA_CHECK(cudaGetLastError());
   ctx->have_maps = true;
   ctx->have_perm = g_pattern_sort == 2 || (g_pattern_sort == 1 && ctx->n >= kMinRowsForSort);
+  ctx->have_slices = ctx->have_perm && g_tile_slices && kLastSortedLevel <= 3;
   ctx->first_sorted = kFirstSortedLevel;
   ctx->last_sorted = kLastSortedLevel;
   return SPS_OK;

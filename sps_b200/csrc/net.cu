@@ -219,7 +219,10 @@ __global__ void k_devox_sigmoid(const float* __restrict__ logits, const int32_t*
 
 static int g_forward_launches = 0;
 
-static int run_conv(const uint32_t* tmask, const int32_t* perm, const char* name, const ConvW& w, int mode, const int32_t* map, int64_t map_ld, const int32_t* n_out,
+#ifndef SPS_SORT_MIN_CIN
+#define SPS_SORT_MIN_CIN 8    // measured: sorting pays for the 8-channel convs of levels 1-3 too (block1 0.23 -> 0.17 ms)
+#endif
+static int run_conv(const uint32_t* tmask, const int32_t* perm, const int32_t* slices, const char* name, const ConvW& w, int mode, const int32_t* map, int64_t map_ld, const int32_t* n_out,
                     int64_t n_out_max, const float* in, int64_t in_ld, const float* in2, int64_t in2_ld,
                     const float* res, int64_t res_ld, float* out, int64_t out_ld, cudaStream_t st,
                     const float* head_w = nullptr, float head_b = 0.f, float* head_out = nullptr) {
@@ -231,7 +234,7 @@ static int run_conv(const uint32_t* tmask, const int32_t* perm, const char* name
   if (in2) { a.in2 = in2; a.in2_ld = in2_ld; a.cin2 = w.cin2; a.weight2 = w.w2; }
   a.res = res; a.res_ld = res_ld; a.relu = 1; a.out = out; a.out_ld = out_ld;
   a.head_w = head_w; a.head_b = head_b; a.head_out = head_out;
-  a.weight_kmajor = w.wt; a.kmajor_ld = w.ldk; a.tile_mask = tmask; a.perm = perm;
+  a.weight_kmajor = w.wt; a.kmajor_ld = w.ldk; a.tile_mask = tmask; a.perm = perm; a.tile_slices = perm ? slices : nullptr;
   a.round_out = conv_backend() != 1;   // pure fp32 mode keeps full-precision activations
   ++g_forward_launches;
   const int rc = conv_dispatch(a, st);
@@ -244,8 +247,9 @@ static int run_conv(const uint32_t* tmask, const int32_t* perm, const char* name
 // offsets save), otherwise in physical order; both sets of tile masks exist.
 template <class... Args>
 static int run_conv3(sps_ctx* c, int L, const char* name, const ConvW& w, Args... args) {
-  const bool pm = c->have_perm && L >= c->first_sorted && L <= c->last_sorted && w.cin >= 16;
-  return run_conv(pm ? c->ptmask[L] : c->tmask3[L], pm ? c->perm[L] : nullptr, name, w, args...);
+  const bool pm = c->have_perm && L >= c->first_sorted && L <= c->last_sorted && w.cin >= SPS_SORT_MIN_CIN;
+  return run_conv(pm ? c->ptmask[L] : c->tmask3[L], pm ? c->perm[L] : nullptr, pm && c->have_slices ? c->tslice[L] : nullptr, name, w,
+                  args...);
 }
 
 int unet_forward(sps_ctx* c, const sps_net* net, const float* feat0, float* logits, cudaStream_t st,
@@ -267,8 +271,8 @@ int unet_forward(sps_ctx* c, const sps_net* net, const float* feat0, float* logi
   static const char* nm_c2[8] = {"block1.conv2", "block2.conv2", "block3.conv2", "block4.conv2",
                                  "block5.conv2", "block6.conv2", "block7.conv2", "block8.conv2+final"};
   int rc;
-#define RUN(...) do { rc = run_conv(nullptr, nullptr, __VA_ARGS__); if (rc != SPS_OK) return rc; } while (0)
-#define RUN8(...) do { rc = run_conv(c->tmask8, nullptr, __VA_ARGS__); if (rc != SPS_OK) return rc; } while (0)
+#define RUN(...) do { rc = run_conv(nullptr, nullptr, nullptr, __VA_ARGS__); if (rc != SPS_OK) return rc; } while (0)
+#define RUN8(...) do { rc = run_conv(c->tmask8, nullptr, nullptr, __VA_ARGS__); if (rc != SPS_OK) return rc; } while (0)
 #define RUN3(L_, ...) do { rc = run_conv3(c, L_, __VA_ARGS__); if (rc != SPS_OK) return rc; } while (0)
   // conv0p1s1 + bn0 + relu  (minkunet.py:162-164)
   if (!conv0_done) {
