@@ -88,6 +88,8 @@ int sps_unpack_coords(sps_ctx* ctx, int level, int32_t* d_out, void* stream);
 #define SPS_CONV_UP 1     /* transposed 2x2x2x1: out[child[k][c]] = in[c] @ W[k] for coarse rows c */
 
 #define SPS_TILE_SLICE_ENTRIES 82
+#define SPS_IO_F32 0
+#define SPS_IO_F16 1
 typedef struct sps_conv_args {
   int mode;                 /* SPS_CONV_NBR | SPS_CONV_UP                                    */
   int K;                    /* kernel volume (125, 81, 8, 1)                                 */
@@ -126,6 +128,11 @@ typedef struct sps_conv_args {
                                rows of the tile's e-th present offset, entry popcount(mask) = the tile's own
                                rows (perm), each entry laid out [row % 32][row / 32].  NULL = the kernel
                                gathers from `map` through `perm` itself                          */
+  int io_dtype;             /* SPS_IO_F32 (0): `in`, `in2`, `res`, `out` are fp32 rows.  SPS_IO_F16: they point
+                               at fp16 rows (leading dimensions in halves, multiples of 8) and weight_kmajor is
+                               the sps_conv_pack_kmajor_f16 matrix: the fused forward's storage format
+                               (same 10-bit mantissa as the TF32 operands, half the bytes per gathered row;
+                               tensor-core path only)                                          */
 } sps_conv_args;
 /* MinkowskiConvolution / MinkowskiConvolutionTranspose (+ folded MinkowskiBatchNorm, ReLU,
  * residual) forward: minkunet.py:55-158, resnet.py:97-108, ME BasicBlock.  Served by the tcgen05
@@ -203,12 +210,18 @@ int sps_infer_scan(sps_ctx* ctx, const sps_net* net, const sps_map* map, const f
 
 /* ---------------------------------------------------------------- tensor-core path ------- */
 /* Which kernel serves sps_conv_fwd / the fused forward: 0 = auto (tcgen05 implicit GEMM where
- * the layer shape allows, fp32 CUDA-core otherwise), 1 = fp32 CUDA-core only, 2 = tcgen05 only
- * (SPS_ERR_UNSUPPORTED for shapes it does not take). */
+ * the layer shape allows, fp32 CUDA-core otherwise; the fused forward keeps its activations as
+ * fp16 rows -- operands with the 10-bit mantissa of TF32 at half the gathered bytes, fp32
+ * accumulation and epilogue), 1 = fp32 CUDA-core only (exact fp32), 2 = as 0 but fp32 rows with
+ * TF32 operands everywhere (the round-1 default), 3 = as 0 (fp16 storage regardless of build flags). */
 int sps_set_conv_backend(int backend);
 /* 1: wide layers (Cin >= 24) gather through TMA `tile::gather4` (conv_umma_tma.cu); default 0 =
  * the cp.async producer kernel everywhere.  The TMA variant is parity-clean but measured ~3x
  * slower (128-byte boxes are too small for the TMA engine), kept for A/B measurements. */
+/* fp16 twins of sps_conv_kmajor_ld / sps_conv_pack_kmajor below (out: __half [cout][ld]; per offset 1, 2, 4 or
+ * 8k groups of 8 channels). */
+int64_t sps_conv_kmajor_ld_f16(int K, int cin, int cin2);
+int sps_conv_pack_kmajor_f16(const float* w, int K, int cin, int cout, const float* w2, int cin2, void* out);
 int sps_set_tma_gather(int on);
 /* Generation of the tensor-core convolution kernel: 6 (default) = k_conv_umma6 (loader warp stages
  * the kernel-map slices, producers walk the stage ring with compile-time slots); 5 = k_conv_umma

@@ -78,11 +78,16 @@ static size_t carve(sps_ctx* c, void* base, int64_t max_points) {
 int conv_simt(const sps_conv_args& a, cudaStream_t st);
 int conv_umma(const sps_conv_args& a, cudaStream_t st);
 bool conv_umma_supports(const sps_conv_args& a);
-static int g_backend = 0;  // 0 auto, 1 fp32 CUDA-core, 2 tcgen05
+bool conv_umma6_f16_supports(const sps_conv_args& a);
+#ifndef SPS_AUTO_F16
+#define SPS_AUTO_F16 1   // backend 0 (auto): the fused forward stores activations as fp16
+#endif
+static int g_backend = 0;  // 0 auto, 1 fp32 CUDA-core, 2 tcgen05 TF32 on fp32 rows, 3 tcgen05 on fp16 rows
 int conv_backend() { return g_backend; }
+bool conv_half_storage() { return g_backend == 3 || (g_backend == 0 && SPS_AUTO_F16); }
 int conv_dispatch(const sps_conv_args& a, cudaStream_t st) {
-  if (g_backend == 2) return conv_umma_supports(a) ? conv_umma(a, st) : SPS_ERR_UNSUPPORTED;
-  if (g_backend == 0 && conv_umma_supports(a)) return conv_umma(a, st);
+  if (a.io_dtype == SPS_IO_F16) return conv_umma6_f16_supports(a) ? conv_umma(a, st) : SPS_ERR_UNSUPPORTED;
+  if (g_backend != 1 && conv_umma_supports(a)) return conv_umma(a, st);
   return conv_simt(a, st);
 }
 
@@ -91,7 +96,7 @@ int conv_dispatch(const sps_conv_args& a, cudaStream_t st) {
 using namespace sps;
 
 extern "C" int sps_set_conv_backend(int backend) {
-  if (backend < 0 || backend > 2) return SPS_ERR_BAD_ARG;
+  if (backend < 0 || backend > 3) return SPS_ERR_BAD_ARG;
   g_backend = backend;
   return SPS_OK;
 }

@@ -1,10 +1,43 @@
 // Shared device helpers: voxel key packing, open-addressing hash slots, status flags.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include "../../include/sps_b200.h"
 
 namespace sps {
+
+// ---- activation storage of the fused forward ----
+// mode 0: fp32 as computed; 1: fp32 rounded to TF32 (nearest), so a tensor-core consumer does not truncate;
+// 2: fp16 rows (`out` then points at __half, out_ld counts halves) -- same 10-bit mantissa as TF32, half the
+// bytes per gathered row; saturating conversion (|x| > 65504 -> +-65504).
+enum { kStoreF32 = 0, kStoreTF32 = 1, kStoreF16 = 2 };
+__device__ __forceinline__ uint32_t pack_half2_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // low half = a
+  return r;
+}
+__device__ __forceinline__ void store_row8(float* out, int64_t out_ld, int64_t row, const float (&v)[8], int mode) {
+  if (mode == kStoreF16) {
+    __half* op = reinterpret_cast<__half*>(out) + row * out_ld;
+    *reinterpret_cast<uint4*>(op) = make_uint4(pack_half2_sat(v[0], v[1]), pack_half2_sat(v[2], v[3]),
+                                               pack_half2_sat(v[4], v[5]), pack_half2_sat(v[6], v[7]));
+  } else {
+    float w[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      w[c] = v[c];
+      if (mode == kStoreTF32) {
+        uint32_t r;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v[c]));
+        w[c] = __uint_as_float(r);
+      }
+    }
+    float* op = out + row * out_ld;
+    *reinterpret_cast<float4*>(op) = make_float4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<float4*>(op + 4) = make_float4(w[4], w[5], w[6], w[7]);
+  }
+}
 
 // ---- 64-bit voxel key: b:8 | x:18 | y:18 | z:16 | t:4 (biased; see include/sps_b200.h) ----
 constexpr int kTBits = 4, kZBits = 16, kYBits = 18, kXBits = 18, kBBits = 8;

@@ -445,6 +445,7 @@ int conv_umma(const sps_conv_args& a, cudaStream_t st) {
   p.wt = a.weight_kmajor;
   p.ldk = a.kmajor_ld;
   p.round_out = a.round_out;
+  if (a.io_dtype == SPS_IO_F16) return conv_umma6(a, p, st);   // fp16 rows: generation 6 only
   if (g_use_tma && conv_umma_tma_supports(a)) return conv_umma_tma(a, p, st);
   static const char* env = getenv("SPS_UMMA_VARIANT");   // A/B runs without touching the host code
   static const int env_variant = env ? atoi(env) : 0;

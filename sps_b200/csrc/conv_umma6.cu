@@ -86,9 +86,14 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 
-template <int NPAD, int GPC>
+// T = float: fp32 rows, TF32 operands (kind::tf32); T = __half: fp16 rows and weights (kind::f16, 8 channels per
+// 16-byte group, so a stage carries twice the channels).  GPC = 16-byte groups per kernel offset: 1 (fp16
+// only), 2 or 4 -> 8/GPC offsets share a stage; 8 -> one offset spans GP/8 stages.
+template <int NPAD, int GPC, typename T>
 __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_args a, const UmmaParams p) {
   using Cfg = V6Cfg<NPAD>;
+  constexpr int EB = sizeof(T);                         // bytes per stored activation
+  constexpr bool kHalf = EB == 2;
   constexpr int S = Cfg::S;
   constexpr int kBStageBytes = Cfg::kBStage;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -133,11 +138,11 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
   const int n_out = *a.n_out;
   const int ntiles = (n_out + kTileM - 1) / kTileM;
   const int K = a.K;
-  const int gpk = a.cin >> 2;                           // real 16-byte groups per offset
-  const int GP = GPC < 8 ? GPC : padded_groups(a.cin);  // padded groups per offset
+  const int gpk = (a.cin * EB) >> 4;                    // real 16-byte groups per offset
+  const int GP = GPC < 8 ? GPC : padded_groups_of(gpk, kHalf);  // padded groups per offset
   const int SPE = GPC < 8 ? 1 : GP >> 3;                // stages per offset (Cin >= 24)
   constexpr int EPS = GPC < 8 ? 8 / GPC : 1;            // offsets per stage (Cin <= 16)
-  const int gpk2 = a.in2 ? (a.cin2 >> 2) : 0;
+  const int gpk2 = a.in2 ? ((a.cin2 * EB) >> 4) : 0;
   const int st2 = (gpk2 + 7) >> 3;                      // stages of the fused 1x1 term
   const uint32_t* tmask = a.tile_mask;
   const int gstep = gridDim.x;
@@ -150,7 +155,7 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
     // =========================== PRODUCERS (256 threads) ===========================
     const int r0 = tid >> 3, cB = tid & 7;          // chunk column cB of rows r0 + 32 i
     const uint32_t a_off = (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128) + (((uint32_t)cB ^ (uint32_t)(r0 & 7)) << 4);
-    const uint32_t in_ld_b = (uint32_t)a.in_ld * 4u, in2_ld_b = (uint32_t)a.in2_ld * 4u;
+    const uint32_t in_ld_b = (uint32_t)a.in_ld * EB, in2_ld_b = (uint32_t)a.in2_ld * EB;
     const char* in_b = reinterpret_cast<const char*>(a.in);
     const char* in2_b = reinterpret_cast<const char*>(a.in2);
     constexpr int NB = (NPAD + 31) / 32;            // weight chunks per thread per stage
@@ -161,7 +166,7 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
     for (int i = 0; i < NB; ++i) {
       const int n = r0 + 32 * i;
       wok[i] = n < a.cout && n < NPAD;
-      wrow[i] = reinterpret_cast<const char*>(p.wt + (int64_t)(wok[i] ? n : 0) * p.ldk);
+      wrow[i] = reinterpret_cast<const char*>(p.wt) + (int64_t)(wok[i] ? n : 0) * p.ldk * EB;
       b_off[i] = (uint32_t)((n >> 3) * 1024 + (n & 7) * 128) + (((uint32_t)cB ^ (uint32_t)(n & 7)) << 4);
     }
     const bool b_lane = r0 < NPAD;
@@ -328,7 +333,7 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
     cp_async_wait<0>();
   } else if (warp == kV6MmaWarp) {
     // =========================== MMA ISSUER (one lane) ===========================
-    const uint32_t idesc = make_idesc_tf32(NPAD);
+    const uint32_t idesc = kHalf ? make_idesc_f16(NPAD) : make_idesc_tf32(NPAD);
     uint32_t gs = 0;
     int n_acc = 0;
     int tile = blockIdx.x;
@@ -350,8 +355,10 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
           const uint64_t adesc = make_smem_desc(sA_u + slot * kAStageBytes);
           const uint64_t bdesc = make_smem_desc(sB_u + slot * kBStageBytes);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            umma_tf32(tacc, adesc + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (it | j) ? 1u : 0u);
+          for (int j = 0; j < 4; ++j) {   // 4 x 32 bytes of K (8 tf32 / 16 fp16) inside the 128-byte swizzle atom
+            if (kHalf) umma_f16(tacc, adesc + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (it | j) ? 1u : 0u);
+            else umma_tf32(tacc, adesc + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (it | j) ? 1u : 0u);
+          }
           umma_commit(bar_empty + 8 * slot);
           if (it == nstages - 1) umma_commit(bar_accf + 8 * b);
         }
@@ -394,20 +401,33 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
         for (int c = 0; c < NPAD; ++c) acc[c] = 0.f;
       }
       if (row < 0) continue;
-      const float* resp = a.res ? a.res + (int64_t)row * a.res_ld : nullptr;
 #pragma unroll
-      for (int c = 0; c < NPAD; c += 4)
+      for (int c = 0; c < NPAD; c += 8)
         if (c < cout) {
-          float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (resp) {
-            if (res_vec) rv = __ldg(reinterpret_cast<const float4*>(resp + c));
-            else rv = make_float4(__ldg(resp + c), __ldg(resp + c + 1), __ldg(resp + c + 2), __ldg(resp + c + 3));
+          float rv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (a.res) {
+            if (kHalf) {
+              const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.res) + (int64_t)row * a.res_ld + c));
+              const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); rv[2 * j] = f.x; rv[2 * j + 1] = f.y; }
+            } else {
+              const float* resp = a.res + (int64_t)row * a.res_ld + c;
+              if (res_vec) {
+                const float4 r0 = __ldg(reinterpret_cast<const float4*>(resp)), r1 = __ldg(reinterpret_cast<const float4*>(resp + 4));
+                rv[0] = r0.x; rv[1] = r0.y; rv[2] = r0.z; rv[3] = r0.w; rv[4] = r1.x; rv[5] = r1.y; rv[6] = r1.z; rv[7] = r1.w;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rv[j] = __ldg(resp + j);
+              }
+            }
           }
-          const float4 sh = *reinterpret_cast<const float4*>(sshift + c);
-          float v0 = acc[c] + sh.x + rv.x, v1 = acc[c + 1] + sh.y + rv.y, v2 = acc[c + 2] + sh.z + rv.z,
-                v3 = acc[c + 3] + sh.w + rv.w;
-          if (a.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-          acc[c] = v0; acc[c + 1] = v1; acc[c + 2] = v2; acc[c + 3] = v3;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float v = acc[c + j] + sshift[c + j] + rv[j];
+            if (a.relu) v = fmaxf(v, 0.f);
+            acc[c + j] = v;
+          }
         }
       if (a.head_out) {
         float s = a.head_b;
@@ -416,13 +436,11 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
         a.head_out[row] = s;
       }
       if (a.out) {
-        float* o = a.out + (int64_t)row * a.out_ld;
 #pragma unroll
-        for (int c = 0; c < NPAD; c += 4)
+        for (int c = 0; c < NPAD; c += 8)
           if (c < cout) {
-            float4 v = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
-            if (p.round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
-            *reinterpret_cast<float4*>(o + c) = v;
+            const float v8[8] = {acc[c], acc[c + 1], acc[c + 2], acc[c + 3], acc[c + 4], acc[c + 5], acc[c + 6], acc[c + 7]};
+            store_row8(a.out + (kHalf ? c / 2 : c), a.out_ld, row, v8, kHalf ? kStoreF16 : (p.round_out ? kStoreTF32 : kStoreF32));
           }
       }
     }
@@ -435,39 +453,79 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
                  : "memory");
 }
 
-template <int NPAD, int GPC>
+template <int NPAD, int GPC, typename T>
 static int launch_umma6(const sps_conv_args& a, const UmmaParams& p, cudaStream_t st) {
   const size_t smem = V6Cfg<NPAD>::smem;
   static bool attr_set = false;
   if (!attr_set) {
     SPS_CUDA_CHECK(
-        cudaFuncSetAttribute(k_conv_umma6<NPAD, GPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaFuncSetAttribute(k_conv_umma6<NPAD, GPC, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   int64_t tiles = (a.n_out_max + kTileM - 1) / kTileM;
   if (tiles < 1) tiles = 1;
   const int grid = (int)(tiles < 148 ? tiles : 148);
-  k_conv_umma6<NPAD, GPC><<<grid, kV6Threads, smem, st>>>(a, p);
+  k_conv_umma6<NPAD, GPC, T><<<grid, kV6Threads, smem, st>>>(a, p);
   SPS_CUDA_CHECK(cudaGetLastError());
   return SPS_OK;
 }
 
-template <int NPAD>
+template <int NPAD, typename T>
 static int launch_umma6_n(const sps_conv_args& a, const UmmaParams& p, cudaStream_t st) {
-  const int gp = padded_groups(a.cin);
-  if (gp == 2) return launch_umma6<NPAD, 2>(a, p, st);
-  if (gp == 4) return launch_umma6<NPAD, 4>(a, p, st);
-  return launch_umma6<NPAD, 8>(a, p, st);
+  constexpr bool kHalf = sizeof(T) == 2;
+  const int gp = padded_groups_of((a.cin * (int)sizeof(T)) >> 4, kHalf);
+  if (kHalf && gp == 1) return launch_umma6<NPAD, kHalf ? 1 : 2, T>(a, p, st);
+  if (gp == 2) return launch_umma6<NPAD, 2, T>(a, p, st);
+  if (gp == 4) return launch_umma6<NPAD, 4, T>(a, p, st);
+  return launch_umma6<NPAD, 8, T>(a, p, st);
 }
 
-int conv_umma6(const sps_conv_args& a, const UmmaParams& p, cudaStream_t st) {
+template <typename T>
+static int conv_umma6_t(const sps_conv_args& a, const UmmaParams& p, cudaStream_t st) {
   switch (a.cout) {
     case 8:
-    case 16: return launch_umma6_n<16>(a, p, st);
-    case 32: return launch_umma6_n<32>(a, p, st);
-    case 64: return launch_umma6_n<64>(a, p, st);
+    case 16: return launch_umma6_n<16, T>(a, p, st);
+    case 32: return launch_umma6_n<32, T>(a, p, st);
+    case 64: return launch_umma6_n<64, T>(a, p, st);
     default: return SPS_ERR_UNSUPPORTED;
   }
 }
 
+int conv_umma6(const sps_conv_args& a, const UmmaParams& p, cudaStream_t st) {
+  return a.io_dtype == SPS_IO_F16 ? conv_umma6_t<__half>(a, p, st) : conv_umma6_t<float>(a, p, st);
+}
+
+// fp16 storage: every layer of the network fits (channel counts are multiples of 8, rows 16-byte aligned)
+bool conv_umma6_f16_supports(const sps_conv_args& a) {
+  if (a.io_dtype != SPS_IO_F16 || a.mode != SPS_CONV_NBR || !a.map || !a.weight_kmajor || !a.tile_mask) return false;
+  if (a.K < 1 || a.K > kMaxK) return false;
+  if (a.cin < 8 || (a.cin & 7) || (a.in_ld & 7)) return false;
+  if (a.in2 && ((a.cin2 & 7) || (a.in2_ld & 7))) return false;
+  if (a.res && (a.res_ld & 7)) return false;
+  if (a.out && (a.out_ld & 7)) return false;
+  if (!(a.cout == 8 || a.cout == 16 || a.cout == 32 || a.cout == 64)) return false;
+  if (a.kmajor_ld & 7) return false;
+  return true;
+}
+
 }  // namespace sps
+
+// fp16 twin of sps_conv_pack_kmajor: ME-layout weights [K][cin][cout] (+ optional 1x1 term [cin2][cout]) ->
+// K-major __half [cout][ld]; per kernel offset padded_groups_of(cin/8) * 8 halves, the 1x1 term padded to 64.
+extern "C" int64_t sps_conv_kmajor_ld_f16(int K, int cin, int cin2) {
+  return (int64_t)K * sps::padded_groups_of((cin + 7) >> 3, true) * 8 + ((cin2 + 63) & ~63);
+}
+extern "C" int sps_conv_pack_kmajor_f16(const float* w, int K, int cin, int cout, const float* w2, int cin2, void* out_) {
+  if (!w || !out_ || K < 1 || cin < 1 || cout < 1 || (w2 == nullptr) != (cin2 == 0)) return SPS_ERR_BAD_ARG;
+  __half* out = static_cast<__half*>(out_);
+  const int64_t ldk = sps_conv_kmajor_ld_f16(K, cin, cin2);
+  const int cpad = sps::padded_groups_of((cin + 7) >> 3, true) * 8;
+  for (int n = 0; n < cout; ++n) {
+    __half* row = out + (int64_t)n * ldk;
+    for (int64_t i = 0; i < ldk; ++i) row[i] = __float2half_rn(0.f);
+    for (int k = 0; k < K; ++k)
+      for (int ci = 0; ci < cin; ++ci) row[(int64_t)k * cpad + ci] = __float2half_rn(w[((int64_t)k * cin + ci) * cout + n]);
+    for (int ci = 0; ci < cin2; ++ci) row[(int64_t)K * cpad + ci] = __float2half_rn(w2[(int64_t)ci * cout + n]);
+  }
+  return SPS_OK;
+}

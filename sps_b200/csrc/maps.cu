@@ -551,18 +551,8 @@ k_conv0_const(const unsigned long long* __restrict__ keys, const int32_t* __rest
       }
     }
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float v = fmaxf(fmaf(cfeat, acc[c], __ldg(shift + c)), 0.f);
-      if (round_out) {
-        uint32_t r;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-        v = __uint_as_float(r);
-      }
-      acc[c] = v;
-    }
-    float* op = out + (int64_t)o * out_ld;
-    *reinterpret_cast<float4*>(op) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    *reinterpret_cast<float4*>(op + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    for (int c = 0; c < 8; ++c) acc[c] = fmaxf(fmaf(cfeat, acc[c], __ldg(shift + c)), 0.f);
+    store_row8(out, out_ld, o, acc, round_out);
   }
 }
 
@@ -628,18 +618,8 @@ k_conv0_blk(const unsigned long long* __restrict__ keys, const int32_t* __restri
       }
     }
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float v = fmaxf(acc[c] + __ldg(shift + c), 0.f);
-      if (round_out) {
-        uint32_t r;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-        v = __uint_as_float(r);
-      }
-      acc[c] = v;
-    }
-    float* op = out + (int64_t)o * out_ld;
-    *reinterpret_cast<float4*>(op) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    *reinterpret_cast<float4*>(op + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    for (int c = 0; c < 8; ++c) acc[c] = fmaxf(acc[c] + __ldg(shift + c), 0.f);
+    store_row8(out, out_ld, o, acc, round_out);
   }
 }
 
@@ -738,7 +718,7 @@ static int g_pattern_sort = 1;
 #endif
 static const int g_tile_slices = SPS_TILE_SLICES;   // gather the kernel map per sorted tile once per level
 #ifndef SPS_FIRST_SORTED_LEVEL
-#define SPS_FIRST_SORTED_LEVEL 1
+#define SPS_FIRST_SORTED_LEVEL 0
 #endif
 constexpr int kFirstSortedLevel = SPS_FIRST_SORTED_LEVEL;
 #ifndef SPS_LAST_SORTED_LEVEL

@@ -18,6 +18,7 @@ namespace sps {
 int conv_simt(const sps_conv_args& a, cudaStream_t st);
 int conv_dispatch(const sps_conv_args& a, cudaStream_t st);
 int conv_backend();
+bool conv_half_storage();
 
 struct ConvW {
   float* w = nullptr;      // [K][cin][cout], BN scale folded
@@ -25,6 +26,8 @@ struct ConvW {
   float* w2 = nullptr;     // fused downsample [cin2][cout], BN scale folded (blocks only)
   float* wt = nullptr;     // K-major TF32 copy for the tcgen05 kernel (81-offset convs)
   int64_t ldk = 0;
+  float* wth = nullptr;    // K-major fp16 copy (every conv but conv0): the fp16-storage forward
+  int64_t ldkh = 0;
   int K = 0, cin = 0, cout = 0, cin2 = 0;
 };
 
@@ -114,7 +117,17 @@ extern "C" size_t sps_net_device_bytes(void) { return 32u << 20; }  // 1.85 M pa
 extern "C" int sps_net_finalize(sps_net* net, void* d_weights, size_t bytes, void* stream) {
   if (!net || !d_weights) return SPS_ERR_BAD_ARG;
   Packer pk;
-  struct Pending { ConvW* cw; size_t w, shift, w2; bool has_w2; size_t wt = 0; bool has_wt = false; };
+  struct Pending { ConvW* cw; size_t w, shift, w2; bool has_w2; size_t wt = 0; bool has_wt = false; size_t wth = 0; bool has_wth = false; };
+  // fp16 K-major copy, stored inside the float image (two halves per float slot)
+  auto add_kmajor_h = [&](Pending& p, const std::vector<float>& w, int K, int cin, int cout,
+                          const std::vector<float>* w2, int cin2) {
+    const int64_t ldk = sps_conv_kmajor_ld_f16(K, cin, cin2);
+    std::vector<float> wt(((size_t)cout * ldk + 1) / 2);
+    sps_conv_pack_kmajor_f16(w.data(), K, cin, cout, w2 ? w2->data() : nullptr, cin2, wt.data());
+    p.cw->ldkh = ldk;
+    p.wth = pk.add(wt);
+    p.has_wth = true;
+  };
   auto add_kmajor = [&](Pending& p, const std::vector<float>& w, int K, int cin, int cout,
                         const std::vector<float>* w2, int cin2) {
     const int64_t ldk = sps_conv_kmajor_ld(K, cin, cin2);
@@ -132,6 +145,7 @@ extern "C" int sps_net_finalize(sps_net* net, void* d_weights, size_t bytes, voi
     cw.K = K; cw.cin = cin; cw.cout = cout; cw.cin2 = 0;
     Pending p{&cw, pk.add(w), pk.add(shf), 0, false};
     if (K == 81 || (K == 8 && cin >= 16 && cin % 4 == 0)) add_kmajor(p, w, K, cin, cout, nullptr, 0);  // 8-channel 2x2x2 layers stay on the CUDA-core kernel (measured faster)
+    if (K == 81 || K == 8) add_kmajor_h(p, w, K, cin, cout, nullptr, 0);
     pend.push_back(p);
     return true;
   };
@@ -151,8 +165,10 @@ extern "C" int sps_net_finalize(sps_net* net, void* d_weights, size_t bytes, voi
       p.w2 = pk.add(w2);
       p.has_w2 = true;
       add_kmajor(p, w, 81, cout, cout, &w2, cin);
+      add_kmajor_h(p, w, 81, cout, cout, &w2, cin);
     } else {
       add_kmajor(p, w, 81, cout, cout, nullptr, 0);
+      add_kmajor_h(p, w, 81, cout, cout, nullptr, 0);
     }
     std::vector<float> shf(sh.begin(), sh.end());
     p.shift = pk.add(shf);
@@ -193,6 +209,7 @@ extern "C" int sps_net_finalize(sps_net* net, void* d_weights, size_t bytes, voi
     p.cw->shift = base + p.shift;
     p.cw->w2 = p.has_w2 ? base + p.w2 : nullptr;
     p.cw->wt = p.has_wt ? base + p.wt : nullptr;
+    p.cw->wth = p.has_wth ? base + p.wth : nullptr;
   }
   net->head_w = base + head_off;
   net->finalized = true;
@@ -222,6 +239,7 @@ static int g_forward_launches = 0;
 #ifndef SPS_SORT_MIN_CIN
 #define SPS_SORT_MIN_CIN 8    // measured: sorting pays for the 8-channel convs of levels 1-3 too (block1 0.23 -> 0.17 ms)
 #endif
+static bool g_run_half = false;   // the forward being enqueued stores its activations as fp16
 static int run_conv(const uint32_t* tmask, const int32_t* perm, const int32_t* slices, const char* name, const ConvW& w, int mode, const int32_t* map, int64_t map_ld, const int32_t* n_out,
                     int64_t n_out_max, const float* in, int64_t in_ld, const float* in2, int64_t in2_ld,
                     const float* res, int64_t res_ld, float* out, int64_t out_ld, cudaStream_t st,
@@ -234,7 +252,9 @@ static int run_conv(const uint32_t* tmask, const int32_t* perm, const int32_t* s
   if (in2) { a.in2 = in2; a.in2_ld = in2_ld; a.cin2 = w.cin2; a.weight2 = w.w2; }
   a.res = res; a.res_ld = res_ld; a.relu = 1; a.out = out; a.out_ld = out_ld;
   a.head_w = head_w; a.head_b = head_b; a.head_out = head_out;
-  a.weight_kmajor = w.wt; a.kmajor_ld = w.ldk; a.tile_mask = tmask; a.perm = perm; a.tile_slices = perm ? slices : nullptr;
+  a.weight_kmajor = g_run_half ? w.wth : w.wt; a.kmajor_ld = g_run_half ? w.ldkh : w.ldk;
+  a.io_dtype = g_run_half ? SPS_IO_F16 : SPS_IO_F32;
+  a.tile_mask = tmask; a.perm = perm; a.tile_slices = perm ? slices : nullptr;
   a.round_out = conv_backend() != 1;   // pure fp32 mode keeps full-precision activations
   ++g_forward_launches;
   const int rc = conv_dispatch(a, st);
@@ -258,8 +278,12 @@ int unet_forward(sps_ctx* c, const sps_net* net, const float* feat0, float* logi
   const int64_t ld = c->ld;
   float** B = c->buf;
   using C = sps_ctx;
+  // fp16 storage needs conv0's output in fp16, which only the fused forward produces
+  const bool hm = conv_half_storage() && conv0_done;
+  g_run_half = hm;
+  auto at = [&](float* base, int off) { return hm ? reinterpret_cast<float*>(reinterpret_cast<__half*>(base) + off) : base + off; };
   // skip tensors live in the tail channel slice of the concat buffers (ME.cat(out, skip))
-  float* skip[4] = {B[C::CAT8] + 8, B[C::CAT7] + 16, B[C::CAT6] + 32, B[C::CAT5] + 64};
+  float* skip[4] = {at(B[C::CAT8], 8), at(B[C::CAT7], 16), at(B[C::CAT6], 32), at(B[C::CAT5], 64)};
   const int skip_ld[4] = {16, 24, 48, 96};
   float* cat[4] = {B[C::CAT8], B[C::CAT7], B[C::CAT6], B[C::CAT5]};
   float* E[4] = {B[C::E1], B[C::E2], B[C::E3], B[C::E4]};
@@ -373,7 +397,9 @@ int forward_impl(sps_ctx* ctx, const sps_net* net, const float* d_points, int64_
   prof_mark("voxelize", st);
   // TensorField.sparse(): voxel feature = mean of the constant 0.5 point features = 0.5
   // (src/sps/models/models.py:22-25)
-  Conv0Fused c0{nullptr, 0.5f, net->conv0.w, net->conv0.shift, conv_backend() != 1, ctx->buf[sps_ctx::CAT8] + 8, 16};
+  const bool hm = conv_half_storage();
+  float* c0_out = hm ? reinterpret_cast<float*>(reinterpret_cast<__half*>(ctx->buf[sps_ctx::CAT8]) + 8) : ctx->buf[sps_ctx::CAT8] + 8;
+  Conv0Fused c0{nullptr, 0.5f, net->conv0.w, net->conv0.shift, hm ? kStoreF16 : (conv_backend() != 1 ? kStoreTF32 : kStoreF32), c0_out, 16};
   rc = build_maps_impl(ctx, &c0, st);
   if (rc != SPS_OK) return rc;
   rc = unet_forward(ctx, net, ctx->buf[sps_ctx::FEAT0], ctx->buf[sps_ctx::LOGITS], st, /*conv0_done=*/true);

@@ -68,6 +68,20 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f16 with fp16 operands (a/b format 0), fp32 accumulate, both operands K-major
+__host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -91,8 +105,14 @@ __host__ __device__ inline int padded_groups(int cin) {
   return g <= 2 ? 2 : g <= 4 ? 4 : (g + 7) & ~7;
 }
 
+// the same for a row of `groups` 16-byte groups; fp16 rows may be a single group (8 channels)
+__host__ __device__ inline int padded_groups_of(int groups, bool allow_one) {
+  return groups <= 1 && allow_one ? 1 : groups <= 2 ? 2 : groups <= 4 ? 4 : (groups + 7) & ~7;
+}
+
 struct UmmaParams {
-  const float* wt;  // [cout][ldk] K-major, TF32-rounded (layout: sps_conv_pack_kmajor)
+  const float* wt;  // [cout][ldk] K-major, TF32-rounded (layout: sps_conv_pack_kmajor); fp16 storage: __half,
+                    // layout sps_conv_pack_kmajor_f16, ldk in halves
   int64_t ldk;
   int round_out;
 };

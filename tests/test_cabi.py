@@ -34,7 +34,8 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_cabi.LevelView) == 56
     a = _cabi.ConvArgs
     assert a.mode.offset == 0 and a.map.offset == 16 and a.n_out.offset == 32
-    assert a.weight_kmajor.offset == a.head_out.offset + 8 and a.perm.offset + 8 == C.sizeof(a)
+    assert a.weight_kmajor.offset == a.head_out.offset + 8 and a.tile_slices.offset == a.perm.offset + 8
+    assert a.io_dtype.offset == a.tile_slices.offset + 8 and a.io_dtype.offset + 8 == C.sizeof(a)
 
 
 def test_argument_validation_without_gpu():

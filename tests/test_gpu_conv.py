@@ -107,14 +107,15 @@ def test_unet_backends_agree():
     eng = engine.Engine(len(pts))
     d = torch.as_tensor(pts).cuda()
     res = {}
-    for backend in (1, 0):
+    for backend in (1, 2, 0):   # exact fp32 / TF32 operands on fp32 rows / fp16 rows (default)
         lib.sps_set_conv_backend(backend)
         res[backend] = eng.forward(net, d, 0.1).cpu().numpy()
         eng.status()
     lib.sps_set_conv_backend(0)
     assert np.abs(res[1] - ref).max() < 1e-5
-    assert np.abs(res[0] - ref).max() < 5e-4, np.abs(res[0] - ref).max()
-    assert np.mean((res[0] < 0.84) == (ref < 0.84)) >= 0.999
+    for backend in (2, 0):
+        assert np.abs(res[backend] - ref).max() < 5e-4, (backend, np.abs(res[backend] - ref).max())
+        assert np.mean((res[backend] < 0.84) == (ref < 0.84)) >= 0.999
 
 
 def test_pattern_sorted_processing_order_does_not_change_results():
@@ -129,14 +130,19 @@ def test_pattern_sorted_processing_order_does_not_change_results():
     net = engine.Net(sd)
     eng = engine.Engine(len(pts))
     d = torch.as_tensor(pts).cuda()
-    out = {}
-    try:
-        for mode in (0, 2):
-            assert lib.sps_set_pattern_sort(mode) == 0
-            out[mode] = eng.forward(net, d, 0.1).cpu().numpy()
-            eng.status()
-    finally:
-        lib.sps_set_pattern_sort(1)
     ref, _, _ = me_cpu.forward(pts, 0.1, me_cpu.pack_weights(sd))
-    assert np.abs(out[0] - out[2]).max() < 2e-6          # only the grouping of zero contributions differs
-    assert np.abs(out[2] - ref).max() < 5e-4
+    # fp32 rows: only the grouping of zero contributions differs.  fp16 rows: a last-bit fp32 difference can
+    # flip the rounding of a stored activation (2^-11 relative), so the two orders agree to ~3e-4.
+    for backend, tol in ((2, 2e-6), (0, 1e-3)):
+        out = {}
+        try:
+            lib.sps_set_conv_backend(backend)
+            for mode in (0, 2):
+                assert lib.sps_set_pattern_sort(mode) == 0
+                out[mode] = eng.forward(net, d, 0.1).cpu().numpy()
+                eng.status()
+        finally:
+            lib.sps_set_pattern_sort(1)
+            lib.sps_set_conv_backend(0)
+        assert np.abs(out[0] - out[2]).max() < tol, (backend, np.abs(out[0] - out[2]).max())
+        assert np.abs(out[2] - ref).max() < 5e-4
