@@ -95,8 +95,9 @@ def load_peaks():
     return {"hbm": 6650.0, "tensor": 1400.0, "src": "fallback"}
 
 
-def stage_accounting(engine, points):
-    """Algorithmic bytes / FLOPs per stage of ONE forward (SURVEY.md §8d formulas; fp32 activations)."""
+def stage_accounting(engine, points, act_bytes=4):
+    """Algorithmic bytes / FLOPs per stage of ONE forward (SURVEY.md §8d formulas; `act_bytes` per stored
+    activation / weight element: 2 with fp16 rows, 4 with fp32 rows)."""
     lib, h = engine.lib, engine.handle
     import ctypes as C
     from sps_b200.engine import _stream
@@ -122,18 +123,21 @@ def stage_accounting(engine, points):
     acc["devox_sigmoid"] = {"bytes": n_points * 4 + V[0] * 4 + n_points * 4}
 
     def conv(name, vin, vout, K, npairs, cin, cout, extra_flops=0, extra_bytes=0):
-        acc[name] = {"bytes": 4 * (vin * cin + vout * cout + K * cin * cout) + 4 * K * vout + extra_bytes,
+        acc[name] = {"bytes": act_bytes * (vin * cin + vout * cout + K * cin * cout) + 4 * K * vout + extra_bytes,
                      "flops": 2 * npairs * cin * cout + extra_flops}
     P = (8, 16, 32, 64, 64, 32, 16, 8)
     conv("conv0", V[0], V[0], 125, P5, 1, 8)
-    acc["conv0+kmap5"] = {"bytes": V[0] * 20 + 4 * V[0] + 32 * V[0], "flops": 2 * P5 * 8}
+    acc["conv0+kmap5"] = {"bytes": V[0] * 20 + 4 * V[0] + 8 * act_bytes * V[0], "flops": 2 * P5 * 8}
+    for L in range(4):   # shape sort (key + row index in, row index out) and per-tile slices (present entries x 4 B, twice)
+        acc[f"sort.L{L}"] = {"bytes": V[L] * 12 + V[L] * 4}
+        acc[f"slices.L{L}"] = {"bytes": 2 * 4 * P3[L] + V[L] * 16}
     c = 8
     for i in range(4):
         L = i + 1
         conv(["conv1p1s2", "conv2p2s2", "conv3p4s2", "conv4p8s2"][i], V[L - 1], V[L], 8, V[L - 1], c, c)
         conv(f"block{L}.conv1", V[L], V[L], 81, P3[L], c, P[i])
         ds = 2 * V[L] * c * P[i] if c != P[i] else 0
-        conv(f"block{L}.conv2", V[L], V[L], 81, P3[L], P[i], P[i], ds, 4 * V[L] * c)
+        conv(f"block{L}.conv2", V[L], V[L], 81, P3[L], P[i], P[i], ds, act_bytes * V[L] * c)
         c = P[i]
     skip = (32, 16, 8, 8)
     for i in range(4):
@@ -143,7 +147,7 @@ def stage_accounting(engine, points):
         cin = co + skip[i]
         conv(f"block{5 + i}.conv1", V[L], V[L], 81, P3[L], cin, co)
         name = f"block{5 + i}.conv2" + ("+final" if i == 3 else "")
-        conv(name, V[L], V[L], 81, P3[L], co, co, 2 * V[L] * cin * co, 4 * V[L] * cin)
+        conv(name, V[L], V[L], 81, P3[L], co, co, 2 * V[L] * cin * co, act_bytes * V[L] * cin)
         c = co
     return acc, V, P3, P5
 
@@ -251,9 +255,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--backend", type=int, default=0, help="0 auto, 1 fp32 CUDA-core, 2 tcgen05")
+    ap.add_argument("--backend", type=int, default=0,
+                    help="0 auto (tcgen05, fp16 rows), 1 fp32 CUDA-core, 2 tcgen05 TF32 on fp32 rows, 3 = 0")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--lanes", type=int, default=2, help="engine contexts/streams forward_async alternates between")
+    ap.add_argument("--lanes", type=int, default=3, help="engine contexts/streams forward_async alternates between")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -360,8 +365,12 @@ def main():
     result = {
         "metric": "scans/s", "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rows_per_step": int(np.mean([len(h) for h in host])),
+        "scaling": "weak", "vs_baseline": None, "dtype": {0: "f16", 1: "f32", 2: "tf32", 3: "f16"}[args.backend],
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "arithmetic": {0: "fp16 operands and stored activations, fp32 accumulate and epilogue",
+                                                         1: "fp32 CUDA cores", 2: "TF32 operands on fp32 rows, fp32 accumulate",
+                                                         3: "fp16 operands and stored activations, fp32 accumulate and epilogue"}[args.backend],
+                   "rows_per_step": int(np.mean([len(h) for h in host])),
                    "scans_per_step_per_gpu": BATCH, "weights": "random-init (seed 0), BN eval fresh stats",
                    "l2": f"per-step working set (kernel maps + features, several GB) exceeds the 126 MB L2; "
                          f"{len(host)} distinct batches rotate",
@@ -375,7 +384,8 @@ def main():
     if rank == 0:
         peaks = load_peaks()
         stage_ms = profile_pass(engine, net, dev, min(args.steps, 5))
-        acc, V, P3, P5 = stage_accounting(engine, dev[(min(args.steps, 5) - 1) % len(dev)])
+        acc, V, P3, P5 = stage_accounting(engine, dev[(min(args.steps, 5) - 1) % len(dev)],
+                                          act_bytes=2 if args.backend in (0, 3) else 4)
         roof, rows = roofline_from(stage_ms, acc, peaks)
         result["roofline"] = roof
         result["stages"] = rows

@@ -346,6 +346,88 @@ k_kernel_map_blk(const unsigned long long* __restrict__ keys, const int32_t* __r
   }
 }
 
+// The 3x3x3 case, restructured around the probes: a voxel's 27 spatial neighbours live in its own 4x4x4 block
+// and, per axis, in at most ONE adjacent block (when the voxel sits on that face), i.e. in 1, 2, 4 or 8 blocks
+// (3.4 on average).  Each thread first resolves those blocks (independent hash probes, all in flight), parks
+// block id + occupancy word in shared memory, then answers the 27 lookups with a bit test and, for present
+// neighbours only, one 4-byte read.  (The generic kernel above re-probes whenever the block changes along
+// x: ~13 probes per thread; this was the dominant kernel after the convolutions were sped up.)
+template <int KT>
+__global__ void __launch_bounds__(256)
+k_kernel_map_blk3(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr,
+                  const Slot* __restrict__ tab, const int32_t* __restrict__ cells,
+                  const unsigned long long* __restrict__ occ, int L, int32_t* __restrict__ nbr, int64_t ld,
+                  uint32_t* __restrict__ tile_masks, uint32_t* __restrict__ vmask) {
+  __shared__ int sId[8][256];
+  __shared__ unsigned long long sOcc[8][256];
+  const int n = *n_ptr;
+  if (n == 0) return;
+  const uint32_t mask = table_capacity(n) - 1;
+  const int xlim = 1 << (kXBits - L), zlim = 1 << (kZBits - L);
+  const int it = blockIdx.y;   // time plane of the kernel: t + (it - KT/2)
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int o0 = (blockIdx.x * blockDim.x + tid) & ~31; o0 < n; o0 += gridDim.x * blockDim.x) {
+    const int o = o0 + lane;
+    const bool live = o < n;
+    const unsigned long long key = live ? keys[o] : 0ull;
+    const int t2 = (int)(key & ((1u << kTBits) - 1)) + it - KT / 2;
+    const bool pok = live && (unsigned)t2 < (1u << kTBits);
+    int32_t* out = nbr + (int64_t)it * 27 * ld + o;
+    const int cx = (int)((key >> kXShift) & ((1u << kXBits) - 1)) >> L;
+    const int cy = (int)((key >> kYShift) & ((1u << kYBits) - 1)) >> L;
+    const int cz = (int)((key >> kZShift) & ((1u << kZBits) - 1)) >> L;
+    const unsigned long long bt = (key & (0xFFull << kBShift)) | (unsigned long long)(unsigned)(pok ? t2 : 0);
+    // which face of its block the voxel touches per axis: -1 / +1, or 0 (interior along that axis)
+    const int sx = (cx & 3) == 0 ? -1 : ((cx & 3) == 3 ? 1 : 0);
+    const int sy = (cy & 3) == 0 ? -1 : ((cy & 3) == 3 ? 1 : 0);
+    const int sz = (cz & 3) == 0 ? -1 : ((cz & 3) == 3 ? 1 : 0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int jx = j & 1, jy = (j >> 1) & 1, jz = j >> 2;
+      const int bx = cx + (jx ? sx : 0), by = cy + (jy ? sy : 0), bz = cz + (jz ? sz : 0);   // a cell of block j
+      const bool need = pok && (!jx || sx) && (!jy || sy) && (!jz || sz) && (unsigned)bx < (unsigned)xlim &&
+                        (unsigned)by < (unsigned)xlim && (unsigned)bz < (unsigned)zlim;
+      int id = -1;
+      unsigned long long oc = 0ull;
+      if (need) {
+        const unsigned long long bkey = bt | ((unsigned long long)(unsigned)((bx >> 2) << (L + 2)) << kXShift) |
+                                        ((unsigned long long)(unsigned)((by >> 2) << (L + 2)) << kYShift) |
+                                        ((unsigned long long)(unsigned)((bz >> 2) << (L + 2)) << kZShift);
+        id = table_find(tab, mask, bkey);
+        if (id >= 0) oc = __ldg(occ + id);
+      }
+      sId[j][tid] = id;
+      sOcc[j][tid] = oc;
+    }
+    uint32_t* tm = tile_masks ? tile_masks + 4 * (o0 >> 7) : nullptr;
+    uint32_t present = 0;   // bit k3: neighbour k3 of this time plane exists
+#pragma unroll
+    for (int dz = -1; dz <= 1; ++dz) {
+      const int jz = (sz != 0 && dz == sz) ? 4 : 0;
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int jyz = jz + ((sy != 0 && dy == sy) ? 2 : 0);
+        const int lyz = 4 * ((cy + dy) & 3) + 16 * ((cz + dz) & 3);
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int j = jyz + ((sx != 0 && dx == sx) ? 1 : 0);
+          const int l = lyz + ((cx + dx) & 3);
+          int res = -1;
+          if ((sOcc[j][tid] >> l) & 1ull) res = __ldg(cells + (int64_t)sId[j][tid] * 64 + l);
+          const int k3 = (dx + 1) + 3 * ((dy + 1) + 3 * (dz + 1));
+          if (live) out[(int64_t)k3 * ld] = res;
+          if (res >= 0) present |= 1u << k3;
+          if (tm) {
+            const int k = it * 27 + k3;
+            if (__any_sync(0xffffffffu, res >= 0) && lane == 0) atomicOr(tm + (k >> 5), 1u << (k & 31));
+          }
+        }
+      }
+    }
+    if (vmask && live) vmask[(int64_t)it * ld + o] = present;
+  }
+}
+
 // ---- pattern-sorted processing order for the 3x3x3x3 convolutions ---------------------------------
 // Only 22-36 % of the (row, offset) slots of an output-stationary 128-row tile hold a neighbour, and a tile
 // must walk every offset that ANY of its rows uses.  Rows with the same neighbourhood shape use the same
@@ -747,9 +829,13 @@ static int pattern_order(sps_ctx* ctx, int L, cudaStream_t st) {
     std::swap(ka, kb);
     std::swap(va, vb);
   }
+  static const char* nm_sort[5] = {"sort.L0", "sort.L1", "sort.L2", "sort.L3", "sort.L4"};
+  static const char* nm_slice[5] = {"slices.L0", "slices.L1", "slices.L2", "slices.L3", "slices.L4"};
+  prof_mark(nm_sort[L], st);
   k_tile_masks_perm<<<grid_for(n / 128 + 1, 1, 148 * 16), 128, 0, st>>>(ctx->vmask, ctx->ld, ctx->perm[L], cnt,
                                                                        ctx->ptmask[L], ctx->nbr3[L],
                                                                        g_tile_slices && ctx->tslice[L] ? ctx->tslice[L] : nullptr);
+  prof_mark(nm_slice[L], st);
   SPS_CUDA_CHECK(cudaGetLastError());
   return SPS_OK;
 }
@@ -798,11 +884,11 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
   ctx->have_nbr5 = c0 == nullptr;
   const size_t mask_bytes = (size_t)(n / 128 + 1) * 16;
   SPS_CUDA_CHECK(cudaMemsetAsync(ctx->tmask3[0], 0, mask_bytes, st));
-  k_kernel_map_blk<3, 3><<<dim3(grid_for(n, 256, 148 * 8), 3), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->table,
+  k_kernel_map_blk3<3><<<dim3(grid_for(n, 256, 148 * 8), 3), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->table,
                                                                               ctx->cells, ctx->occ, 0, ctx->nbr3[0],
                                                                               ctx->ld, ctx->tmask3[0], ctx->vmask);
-  { const int rc = pattern_order(ctx, 0, st); if (rc != SPS_OK) return rc; }
   prof_mark("kmap3.L0", st);
+  { const int rc = pattern_order(ctx, 0, st); if (rc != SPS_OK) return rc; }
   for (int L = 1; L < SPS_NUM_LEVELS; ++L) {
     const int32_t* n_fine = ctx->counts + (L - 1);
     k_table_clear<<<grid_for(table_capacity(n), 256), 256, 0, st>>>(ctx->table, n_fine);
@@ -818,11 +904,11 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
     build_blocks(L);
     prof_mark(nm_s[L], st);
     SPS_CUDA_CHECK(cudaMemsetAsync(ctx->tmask3[L], 0, mask_bytes, st));
-    k_kernel_map_blk<3, 3><<<dim3(grid_for(n, 256, 148 * 8), 3), 256, 0, st>>>(ctx->keys[L], ctx->counts + L, ctx->table,
+    k_kernel_map_blk3<3><<<dim3(grid_for(n, 256, 148 * 8), 3), 256, 0, st>>>(ctx->keys[L], ctx->counts + L, ctx->table,
                                                                                 ctx->cells, ctx->occ, L, ctx->nbr3[L],
                                                                                 ctx->ld, ctx->tmask3[L], ctx->vmask);
-    { const int rc = pattern_order(ctx, L, st); if (rc != SPS_OK) return rc; }
     prof_mark(nm_k[L], st);
+    { const int rc = pattern_order(ctx, L, st); if (rc != SPS_OK) return rc; }
   }
   SPS_CUDA_CHECK(cudaGetLastError());
   ctx->have_maps = true;

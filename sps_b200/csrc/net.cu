@@ -407,7 +407,10 @@ int forward_impl(sps_ctx* ctx, const sps_net* net, const float* d_points, int64_
   rc = sps_devox_sigmoid(ctx->buf[sps_ctx::LOGITS], ctx->inv, n_scores, d_scores, st);
   if (rc != SPS_OK) return rc;
   prof_mark("devox_sigmoid", st);
-  g_forward_launches += 5 + 93 + 1;  // voxelize 5, map building 93 (block tables, strided levels, kernel maps, shape sorts), devox 1  // voxelize, maps, feature fill, devox
+  // voxelize 5; map building 51 (block tables, strided levels, kernel maps) + 14 per shape-sorted level (keys,
+  // 4 radix passes of 3 kernels, permuted tile masks + slices); devox 1
+  const int sorted_levels = ctx->have_perm ? ctx->last_sorted - ctx->first_sorted + 1 : 0;
+  g_forward_launches += 5 + 51 + 14 * sorted_levels + 1;
   return SPS_OK;
 }
 }  // namespace sps

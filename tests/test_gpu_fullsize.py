@@ -54,10 +54,15 @@ def test_config1_128k_scan_voxel_submap():
     # determinism: bit-identical on a second run
     again, _ = run(pts, sd)
     assert np.array_equal(got, again)
-    # row-permutation invariance: the voxel set, hence every point's score, does not depend on row order
+    # row-permutation invariance: the voxel set, hence every point's score, does not depend on row order.
+    # fp32 rows (backend 2): only the grouping of exact zeros changes.  fp16 rows (default): a last-bit fp32
+    # difference may flip the rounding of a stored activation (2^-11 relative) -> 5e-5 on the scores.
     perm = np.random.default_rng(0).permutation(len(pts))
     shuffled, _ = run(pts[perm], sd)
-    assert np.abs(shuffled - got[perm]).max() < 1e-6
+    assert np.abs(shuffled - got[perm]).max() < 3e-4
+    got32, _ = run(pts, sd, backend=2)
+    shuffled32, _ = run(pts[perm], sd, backend=2)
+    assert np.abs(shuffled32 - got32[perm]).max() < 1e-6
 
 
 def test_config2_batch8_radius_submaps_batch_independence():
