@@ -113,8 +113,15 @@ def stage_accounting(engine, points, act_bytes=4):
     P3 = [pairs(L, 3) for L in range(5)]
     P5 = pairs(0, 5)
     acc = {}
-    acc["voxelize"] = {"bytes": n_points * 20 + n_points * 4 + V[0] * 20}
-    acc["blocks.L0"] = {"bytes": V[0] * 8 + V[0] * 4}
+    cap = 1024
+    while cap < 2 * n_points:
+        cap *= 2
+    acc["vox.clear"] = {"bytes": cap * 16}                       # the open-addressing table, 16-byte slots
+    acc["vox.insert"] = {"bytes": n_points * 20 + n_points * 4}   # rows in, slot index out
+    acc["vox.rank"] = {"bytes": n_points * 4 + n_points * 4}      # slot index in, block-local rank out
+    acc["vox.assign"] = {"bytes": n_points * 4 + n_points * 4 + V[0] * 8}   # slot index in, inverse map + voxel keys out
+    for L in range(5):
+        acc[f"blocks.L{L}"] = {"bytes": V[L] * 8 + V[L] * 4}
     acc["kmap5.L0"] = {"bytes": V[0] * 20 + 125 * V[0] * 4}
     for L in range(5):
         acc[f"kmap3.L{L}"] = {"bytes": V[L] * 20 + 81 * V[L] * 4}

@@ -80,7 +80,7 @@ __host__ __device__ inline int child_index(unsigned long long k, int log2s) {
 // ---- hash table ----
 struct __align__(16) Slot {
   unsigned long long key;
-  int val;    // voxel row (assigned after the scan)
+  int val;    // voxel tables: block-local rank of the first occurrence (k_first_rank); block tables: block id
   int first;  // smallest input index that mapped here (first-occurrence order)
 };
 
@@ -89,10 +89,15 @@ __host__ __device__ inline uint32_t hash_key(unsigned long long k) {
   return (uint32_t)k;
 }
 // table capacity for n keys: power of two >= 2n, at least 1024
-__host__ __device__ inline uint32_t table_capacity(int64_t n) {
+__host__ __device__ inline uint32_t table_capacity(int64_t n) {   // smallest power of two >= max(1024, 2n)
+#ifdef __CUDA_ARCH__
+  const unsigned long long need = (unsigned long long)(2 * n);
+  return need <= 1024ull ? 1024u : 1u << (64 - __clzll((long long)(need - 1)));
+#else
   uint32_t c = 1024;
   while ((int64_t)c < 2 * n) c <<= 1;
   return c;
+#endif
 }
 
 __device__ inline int table_find(const Slot* __restrict__ tab, uint32_t mask, unsigned long long key) {

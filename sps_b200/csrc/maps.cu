@@ -69,8 +69,8 @@ __global__ void k_insert_coarse(const unsigned long long* __restrict__ fine, con
 // inside the block), per-block sums, and the last block to finish turns the sums into exclusive
 // block offsets and publishes the total.  Global rank of i = rank[i] + block_sums[i / kScanBlock].
 // Must be called by every thread of every block with blockIdx.x < nb.
-__device__ inline void scan_flags(int flag, int i, int n, int nb, int32_t* __restrict__ rank, int32_t* block_sums,
-                                  uint32_t* ticket, int32_t* count_out) {
+__device__ inline int scan_flags(int flag, int i, int n, int nb, int32_t* __restrict__ rank, int32_t* block_sums,
+                                 uint32_t* ticket, int32_t* count_out) {
   __shared__ int warp_sums[kScanBlock / 32];
   __shared__ bool is_last;
   __shared__ int carry;
@@ -102,7 +102,7 @@ __device__ inline void scan_flags(int flag, int i, int n, int nb, int32_t* __res
     is_last = (atomicAdd(ticket, 1u) == (uint32_t)(nb - 1));
   }
   __syncthreads();
-  if (!is_last) return;
+  if (!is_last) return excl;
   __threadfence();
   // serial-over-chunks exclusive scan of block_sums[0..nb) by this block
   if (tid == 0) carry = 0;
@@ -139,12 +139,13 @@ __device__ inline void scan_flags(int flag, int i, int n, int nb, int32_t* __res
     *count_out = carry;
     *ticket = 0;  // ready for the next scan on this stream
   }
+  return excl;
 }
 
 // flag = "this input is the first occurrence of its voxel" (optionally: "... and the voxel is
 // also present in `filter`", the map/scan intersection of util.prune).
 __global__ void __launch_bounds__(kScanBlock)
-k_first_rank(const Slot* __restrict__ tab, const uint32_t* __restrict__ slot_of, const int32_t* __restrict__ n_ptr,
+k_first_rank(Slot* tab, const uint32_t* __restrict__ slot_of, const int32_t* __restrict__ n_ptr,
              int32_t* __restrict__ rank, int32_t* block_sums, uint32_t* ticket, int32_t* count_out,
              const Slot* __restrict__ filter, uint32_t filter_mask, int32_t* first_count) {
   const int n = *n_ptr;
@@ -162,7 +163,10 @@ k_first_rank(const Slot* __restrict__ tab, const uint32_t* __restrict__ slot_of,
     if (first_count && (threadIdx.x & 31) == 0 && ballot) atomicAdd(first_count, __popc(ballot));
     if (flag) flag = table_find(filter, filter_mask, tab[s].key) >= 0;
   }
-  scan_flags(flag, i, n, nb, rank, block_sums, ticket, count_out);
+  const int excl = scan_flags(flag, i, n, nb, rank, block_sums, ticket, count_out);
+  // the first occurrence leaves its block-local rank in the slot: whoever maps an input to its voxel row later
+  // reads ONE 16-byte slot (key, local rank, first index) instead of chasing slot -> first -> rank[first]
+  if (flag && !filter) tab[s].val = excl;
 }
 
 __global__ void k_fill_i32(int32_t* __restrict__ p, int64_t ld, int rows, const int32_t* __restrict__ count_ptr,
@@ -184,10 +188,11 @@ __global__ void k_assign_points(Slot* tab, const uint32_t* __restrict__ slot_of,
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t s = slot_of[i];
     if (s == kInvalidSlot) { inv[i] = -1; continue; }
-    const int f = tab[s].first;
-    const int id = rank[f] + block_sums[f / kScanBlock];
+    const int4 raw = *reinterpret_cast<const int4*>(tab + s);   // key | block-local rank | first input
+    const int f = raw.w;
+    const int id = raw.z + block_sums[f / kScanBlock];
     inv[i] = id;
-    if (f == i) { tab[s].val = id; ukeys[id] = tab[s].key; }
+    if (f == i) ukeys[id] = ((unsigned long long)(unsigned)raw.y << 32) | (unsigned)raw.x;
   }
 }
 
@@ -201,8 +206,9 @@ __global__ void k_assign_coarse(Slot* tab, const uint32_t* __restrict__ slot_of,
   const int n = *n_ptr;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t s = slot_of[i];
-    const int f = tab[s].first;
-    const int id = rank[f] + block_sums[f / kScanBlock];
+    const int4 raw = *reinterpret_cast<const int4*>(tab + s);   // key | block-local rank | first input
+    const int f = raw.w;
+    const int id = raw.z + block_sums[f / kScanBlock];
     const int k = child_index(fine[i], log2s);
     parent[i] = id * 8 + k;
     child[(int64_t)k * ld + id] = i;
@@ -210,7 +216,7 @@ __global__ void k_assign_coarse(Slot* tab, const uint32_t* __restrict__ slot_of,
     // upmap[k'][f] = parent row if k' == k(f), else absent
 #pragma unroll
     for (int kk = 0; kk < 8; ++kk) upmap[(int64_t)kk * ld + i] = kk == k ? id : -1;
-    if (f == i) { tab[s].val = id; ukeys[id] = tab[s].key; }
+    if (f == i) ukeys[id] = ((unsigned long long)(unsigned)raw.y << 32) | (unsigned)raw.x;
   }
 }
 
@@ -774,12 +780,16 @@ int voxelize_impl(sps_ctx* ctx, const float* d_points, int64_t n, const int32_t*
   else k_set_i32<<<1, 1, 0, st>>>(ctx->n_dev, (int32_t)n);
   const int nblk = cdiv(n > 0 ? n : 1, kScanBlock);
   k_table_clear<<<grid_for(table_capacity(n), 256), 256, 0, st>>>(ctx->table, ctx->n_dev);
+  prof_mark("vox.clear", st);
   k_insert_points<<<grid_for(n, 256), 256, 0, st>>>(d_points, ld_points, ctx->n_dev, voxel_size, ctx->table,
                                                      ctx->slot_of, ctx->status);
+  prof_mark("vox.insert", st);
   k_first_rank<<<nblk, kScanBlock, 0, st>>>(ctx->table, ctx->slot_of, ctx->n_dev, ctx->rank, ctx->block_sums,
                                             ctx->ticket, ctx->counts + 0, nullptr, 0, nullptr);
+  prof_mark("vox.rank", st);
   k_assign_points<<<grid_for(n, 256), 256, 0, st>>>(ctx->table, ctx->slot_of, ctx->n_dev, ctx->rank,
                                                      ctx->block_sums, ctx->keys[0], ctx->inv);
+  prof_mark("vox.assign", st);
   SPS_CUDA_CHECK(cudaGetLastError());
   ctx->have_l0 = true;
   return SPS_OK;
@@ -900,9 +910,11 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
                                                        ctx->keys[L - 1], L - 1, ctx->keys[L], ctx->parent[L - 1],
                                                        ctx->child[L], ctx->upmap[L - 1], ctx->ld);
     static const char* nm_s[5] = {"", "stride.L1", "stride.L2", "stride.L3", "stride.L4"};
+    static const char* nm_b[5] = {"", "blocks.L1", "blocks.L2", "blocks.L3", "blocks.L4"};
     static const char* nm_k[5] = {"", "kmap3.L1", "kmap3.L2", "kmap3.L3", "kmap3.L4"};
-    build_blocks(L);
     prof_mark(nm_s[L], st);
+    build_blocks(L);
+    prof_mark(nm_b[L], st);
     SPS_CUDA_CHECK(cudaMemsetAsync(ctx->tmask3[L], 0, mask_bytes, st));
     k_kernel_map_blk3<3><<<dim3(grid_for(n, 256, 148 * 8), 3), 256, 0, st>>>(ctx->keys[L], ctx->counts + L, ctx->table,
                                                                                 ctx->cells, ctx->occ, L, ctx->nbr3[L],

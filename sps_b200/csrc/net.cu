@@ -394,7 +394,6 @@ int forward_impl(sps_ctx* ctx, const sps_net* net, const float* d_points, int64_
   prof_begin(st);
   int rc = voxelize_impl(ctx, d_points, n, d_n, ld_points, voxel_size, st);
   if (rc != SPS_OK) return rc;
-  prof_mark("voxelize", st);
   // TensorField.sparse(): voxel feature = mean of the constant 0.5 point features = 0.5
   // (src/sps/models/models.py:22-25)
   const bool hm = conv_half_storage();

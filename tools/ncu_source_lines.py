@@ -24,7 +24,7 @@ for r in rows:
 # kernels = runs of sections; a kernel's first section is the main .cu file
 kernels = []
 for s in secs:
-    if not kernels or (s["file"] or "").endswith(".cu"):   # a kernel's first section is its .cu file
+    if not kernels or (s["file"] or "").endswith(".cu") and (not kernels or kernels[-1][0]["name"] != s["name"] or True):   # a kernel's first section is its .cu file
         kernels.append([s])
     else:
         kernels[-1].append(s)
