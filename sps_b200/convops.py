@@ -29,6 +29,21 @@ def pack_kmajor(weight: torch.Tensor, weight2: torch.Tensor | None = None) -> to
     return torch.as_tensor(out).to(weight.device)
 
 
+def pack_kmajor_f16(weight: torch.Tensor, weight2: torch.Tensor | None = None) -> torch.Tensor:
+    """fp16 twin of :func:`pack_kmajor` (``sps_conv_pack_kmajor_f16``): the weight matrix of the fp16-row path."""
+    lib = _cabi.load()
+    w = np.ascontiguousarray(weight.detach().cpu().numpy(), np.float32)
+    K, cin, cout = w.shape
+    w2 = None if weight2 is None else np.ascontiguousarray(weight2.detach().cpu().numpy(), np.float32)
+    cin2 = 0 if w2 is None else w2.shape[0]
+    ld = lib.sps_conv_kmajor_ld_f16(K, cin, cin2)
+    out = np.empty((cout, ld), np.float16)
+    check(lib.sps_conv_pack_kmajor_f16(w.ctypes.data_as(C.c_void_p), K, cin, cout,
+                                       None if w2 is None else w2.ctypes.data_as(C.c_void_p), cin2,
+                                       out.ctypes.data_as(C.c_void_p)), "sps_conv_pack_kmajor_f16")
+    return torch.as_tensor(out).to(weight.device)
+
+
 def kernel_map_tile_masks(map, map_ld, K, n_out, n_out_max):
     """Present-offset bitmask per 128-row tile of a dense kernel map (tensor-core path input)."""
     lib = _cabi.load()
@@ -40,17 +55,18 @@ def kernel_map_tile_masks(map, map_ld, K, n_out, n_out_max):
 
 def conv_fwd(inp, weight, n_out, *, map=None, map_ld=0, mode=_cabi.SPS_CONV_NBR, shift=None, in2=None, weight2=None,
              res=None, relu=False, out=None, head_w=None, head_b=0.0, head_out=None, weight_kmajor=None,
-             round_out=False, n_out_max=None, backend=None, tile_mask=None):
+             round_out=False, n_out_max=None, backend=None, tile_mask=None, io_f16=False):
     """out[o] = act(sum_k in[map[k][o]] @ W[k] (+ in2[o] @ W2) + shift (+ res[o])); ``n_out`` is a
     1-element int32 CUDA tensor (device-side count).  ``inp``/``out``/``in2``/``res`` may be
-    channel slices (stride(0) is the leading dimension)."""
+    channel slices (stride(0) is the leading dimension).  ``io_f16``: ``inp``/``in2``/``res``/``out`` are fp16
+    rows and ``weight_kmajor`` comes from :func:`pack_kmajor_f16` (SPS_IO_F16, the fused forward's format)."""
     lib = _cabi.load()
     K = weight.shape[0] if weight.dim() == 3 else 1
     cin, cout = weight.shape[-2], weight.shape[-1]
     if n_out_max is None:
         n_out_max = int(n_out.item())
     if out is None and head_out is None:
-        out = torch.empty((max(n_out_max, 1), cout), dtype=torch.float32, device=inp.device)
+        out = torch.empty((max(n_out_max, 1), cout), dtype=torch.float16 if io_f16 else torch.float32, device=inp.device)
     a = _cabi.ConvArgs()
     a.mode, a.K, a.cin, a.cout = mode, K, cin, cout
     a.map, a.map_ld = (map.data_ptr() if map is not None else None), int(map_ld)
@@ -70,6 +86,7 @@ def conv_fwd(inp, weight, n_out, *, map=None, map_ld=0, mode=_cabi.SPS_CONV_NBR,
     if weight_kmajor is not None:
         a.weight_kmajor, a.kmajor_ld = weight_kmajor.data_ptr(), weight_kmajor.stride(0)
     a.round_out = int(round_out)
+    a.io_dtype = 1 if io_f16 else 0
     if weight_kmajor is not None and map is not None and tile_mask is None and K <= 81:
         tile_mask = kernel_map_tile_masks(map, map_ld, K, n_out, n_out_max)
     if tile_mask is not None:

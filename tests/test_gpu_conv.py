@@ -93,6 +93,51 @@ def test_sparse_conv_81_offsets(cin, cout, backend):
     assert np.abs(got - ref_conv(x, nbr, w, res=res, quant=quant)).max() < tol
 
 
+def f16(x):
+    return np.ascontiguousarray(x, np.float32).astype(np.float16).astype(np.float32)
+
+
+@pytest.mark.parametrize("cin,cout", [(8, 8), (8, 16), (16, 16), (24, 16), (16, 32), (32, 32), (48, 32), (64, 64), (96, 64),
+                                      (16, 8)])
+def test_sparse_conv_fp16_rows(cin, cout):
+    """SPS_IO_F16 through sps_conv_fwd: fp16 rows and weights (kind::f16), fp32 accumulate and epilogue, fp16 out;
+    81 offsets, the fused 1x1 term, residual, ReLU -- against float64 numpy on the fp16-rounded operands."""
+    from sps_b200 import convops
+    rng = np.random.default_rng(cin * 100 + cout)
+    V, K = 1500, 81
+    nbr = random_map(rng, K, V, V, 0.3)
+    nbr[:, 700:900] = -1                      # rows without any neighbour
+    nbr[40:, 1000:1200] = -1                  # tiles that use only some offsets
+    x = rng.standard_normal((V, cin)).astype(np.float32)
+    w = (rng.standard_normal((K, cin, cout)) / np.sqrt(cin * 8)).astype(np.float32)
+    shift = rng.standard_normal(cout).astype(np.float32)
+    cin2 = 8 if cin == 8 else cin // 2 if (cin // 2) % 8 == 0 else cin
+    x2 = rng.standard_normal((V, cin2)).astype(np.float32)
+    w2 = (rng.standard_normal((cin2, cout)) / np.sqrt(cin2)).astype(np.float32)
+    res = rng.standard_normal((V, cout)).astype(np.float32)
+    ld = (V + 31) // 32 * 32
+    m = np.full((K, ld), -1, np.int32)
+    m[:, :V] = nbr
+    dev = lambda a, dt=None: torch.as_tensor(np.ascontiguousarray(a)).cuda().to(dt) if dt else torch.as_tensor(np.ascontiguousarray(a)).cuda()
+    n_out = torch.tensor([V], dtype=torch.int32, device="cuda")
+    half = torch.float16
+    for kw in (dict(shift=True, relu=True), dict(shift=True, relu=True, fused=True), dict(res=True)):
+        wt = convops.pack_kmajor_f16(dev(w), dev(w2) if kw.get("fused") else None)
+        out = convops.conv_fwd(dev(x, half), dev(w), n_out, map=dev(m), map_ld=ld,
+                               shift=dev(shift) if kw.get("shift") else None,
+                               in2=dev(x2, half) if kw.get("fused") else None, weight2=dev(w2) if kw.get("fused") else None,
+                               res=dev(res, half) if kw.get("res") else None, relu=kw.get("relu", False),
+                               weight_kmajor=wt, io_f16=True)
+        torch.cuda.synchronize()
+        assert out.dtype == half
+        got = out[:V].float().cpu().numpy()
+        ref = ref_conv(x, nbr, w, shift=shift if kw.get("shift") else None, x2=x2 if kw.get("fused") else None,
+                       w2=w2 if kw.get("fused") else None, res=f16(res) if kw.get("res") else None,
+                       relu=kw.get("relu", False), quant=f16)
+        # fp32 accumulation of exact fp16 products, then ONE rounding to fp16 on the way out (2^-11 relative)
+        assert np.abs(got - ref).max() < 2e-3 * max(1.0, np.abs(ref).max()), (kw, np.abs(got - ref).max())
+
+
 def test_unet_backends_agree():
     """Whole forward: tcgen05 path vs fp32 CUDA-core path vs CPU oracle (2e-3 bar, north star)."""
     from conftest import make_case
