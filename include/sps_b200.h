@@ -208,6 +208,29 @@ int sps_infer_scan(sps_ctx* ctx, const sps_net* net, const sps_map* map, const f
                    int64_t n_scan, float voxel_size, float* d_scores, void* d_scratch,
                    size_t scratch_bytes, int32_t* d_counts, void* stream);
 
+/* ---------------------------------------------------------------- offline-loader submap --- */
+/* BLTDataset.select_closest_points (src/sps/datasets/blt_dataset.py:222-226,258-271):
+ *     kd_tree_scan.query_ball_tree(kd_tree_target, VOXEL_SIZE) -> np.concatenate(lists)
+ * = for every scan point, in scan order, the indices of ALL map points within Euclidean distance
+ * <= radius (evaluated in fp64 like scipy), duplicates kept across scan points.  The two kd-trees
+ * are replaced by a uniform grid of edge `radius` over the static map (27-cell ball query). */
+typedef struct sps_ballmap sps_ballmap;
+size_t sps_ballmap_bytes(int64_t n_map);
+/* Built once per map (= kd_tree_target, blt_dataset.py:193).  d_map_xyz fp32 [n,3] must stay alive. */
+int sps_ballmap_build(sps_ballmap** bm, void* d_storage, size_t bytes, const float* d_map_xyz,
+                      int64_t n, double radius, void* stream);
+int sps_ballmap_destroy(sps_ballmap* bm);
+size_t sps_ball_query_scratch_bytes(int64_t n_scan);
+/* d_out_idx int32 [out_capacity]: map indices, scan point by scan point; inside one scan point's
+ * list: cell by cell (dz, dy, dx ascending), ascending map index inside a cell (scipy's order inside
+ * a list is its tree-traversal order; the lists hold the same indices).  d_offsets (optional) int32
+ * [n_scan+1]: list i = d_out_idx[d_offsets[i] .. d_offsets[i+1]).  *d_total = number of hits (the
+ * caller compares it with out_capacity after its synchronisation: entries past the capacity are
+ * counted but not written). */
+int sps_submap_ball_query(const sps_ballmap* bm, const float* d_scan_xyz, int64_t n_scan,
+                          int32_t* d_offsets, int32_t* d_out_idx, int64_t out_capacity, int32_t* d_total,
+                          void* d_scratch, size_t scratch_bytes, void* stream);
+
 /* ---------------------------------------------------------------- tensor-core path ------- */
 /* Which kernel serves sps_conv_fwd / the fused forward: 0 = auto (tcgen05 implicit GEMM where
  * the layer shape allows, fp32 CUDA-core otherwise; the fused forward keeps its activations as

@@ -27,6 +27,7 @@ SYMBOLS = [
     "sps_assemble", "sps_memcpy_d2h", "sps_memcpy_h2d", "sps_infer_scan", "sps_infer_scan_scratch_bytes", "sps_conv_kmajor_ld", "sps_conv_pack_kmajor", "sps_conv_kmajor_ld_f16", "sps_conv_pack_kmajor_f16", "sps_kernel_map_tile_masks", "sps_set_tma_gather", "sps_set_umma_variant", "sps_set_pattern_sort",
     "sps_set_conv_backend", "sps_profile_enable", "sps_profile_read", "sps_ctx_pair_count",
     "sps_confusion_counts", "sps_voxel_mean", "sps_gather_rows", "sps_affine_relu",
+    "sps_ballmap_bytes", "sps_ballmap_build", "sps_ballmap_destroy", "sps_ball_query_scratch_bytes", "sps_submap_ball_query",
 ]
 
 
@@ -112,6 +113,11 @@ def load() -> C.CDLL:
         "sps_voxel_mean": (i32, [vp, vp, i64, i32, vp, vp, vp]),
         "sps_gather_rows": (i32, [vp, i64, i32, vp, i64, vp, vp]),
         "sps_affine_relu": (i32, [vp, i64, i32, i64, vp, vp, i32, vp, i64, vp]),
+        "sps_ballmap_bytes": (sz, [i64]),
+        "sps_ballmap_build": (i32, [C.POINTER(vp), vp, sz, vp, i64, C.c_double, vp]),
+        "sps_ballmap_destroy": (i32, [vp]),
+        "sps_ball_query_scratch_bytes": (sz, [i64]),
+        "sps_submap_ball_query": (i32, [vp, vp, i64, vp, vp, i64, vp, vp, sz, vp]),
         "sps_profile_enable": (i32, [i32]),
         "sps_profile_read": (i32, [vp, vp, i32, C.POINTER(i32)]),
         "sps_ctx_pair_count": (i32, [vp, i32, i32, C.POINTER(i64), vp]),

@@ -59,6 +59,16 @@ def test_argument_validation_without_gpu():
     assert lib.sps_net_destroy(net) == 0
 
 
+def test_ballmap_argument_validation_without_gpu():
+    from sps_b200 import _cabi
+    lib = _cabi.load()
+    assert lib.sps_ballmap_bytes(1000) > 0 and lib.sps_ballmap_bytes(100000) > lib.sps_ballmap_bytes(1000)
+    assert lib.sps_ball_query_scratch_bytes(1000) >= 2 * 4 * 1000
+    h = C.c_void_p()
+    assert lib.sps_ballmap_build(C.byref(h), None, 0, None, 10, 0.1, None) == _cabi.SPS_ERR_BAD_ARG
+    assert lib.sps_submap_ball_query(None, None, 0, None, None, 0, None, None, 0, None) == _cabi.SPS_ERR_BAD_ARG
+
+
 def test_key_packing_contract():
     """The documented coordinate range of the 64-bit voxel key."""
     text = open(os.path.join(ROOT, "include", "sps_b200.h")).read()
