@@ -440,6 +440,14 @@ int conv_umma6(const sps_conv_args& a, const UmmaParams& p, cudaStream_t st);
 static int g_variant = 6;   // 6: k_conv_umma6 (loader warp, static-slot producers); 5: k_conv_umma
 static int g_use_tma = 0;   // 1: wide layers gather through TMA tile::gather4 (measured 3x slower than cp.async producers: 128-byte boxes)
 
+// true when the selected kernel generation gathers from the dense map itself (generation 5, TMA variant): the map
+// builder must then keep the dense tables complete (maps.cu writes only present entries otherwise)
+bool conv_needs_dense_maps() {
+  static const char* env = getenv("SPS_UMMA_VARIANT");
+  static const int env_variant = env ? atoi(env) : 0;
+  return (env_variant ? env_variant : g_variant) != 6 || g_use_tma != 0;
+}
+
 int conv_umma(const sps_conv_args& a, cudaStream_t st) {
   UmmaParams p;
   p.wt = a.weight_kmajor;

@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(256)
 k_kernel_map_blk3(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr,
                   const Slot* __restrict__ tab, const int32_t* __restrict__ cells,
                   const unsigned long long* __restrict__ occ, int L, int32_t* __restrict__ nbr, int64_t ld,
-                  uint32_t* __restrict__ tile_masks, uint32_t* __restrict__ vmask) {
+                  uint32_t* __restrict__ tile_masks, uint32_t* __restrict__ vmask, int dense) {
   __shared__ int sId[8][256];
   __shared__ unsigned long long sOcc[8][256];
   const int n = *n_ptr;
@@ -421,7 +421,9 @@ k_kernel_map_blk3(const unsigned long long* __restrict__ keys, const int32_t* __
           int res = -1;
           if ((sOcc[j][tid] >> l) & 1ull) res = __ldg(cells + (int64_t)sId[j][tid] * 64 + l);
           const int k3 = (dx + 1) + 3 * ((dy + 1) + 3 * (dz + 1));
-          if (live) out[(int64_t)k3 * ld] = res;
+          // dense = 0: only present entries are stored (87 % of the table is -1); allowed when every reader of this
+          // level's table goes through the presence words `vmask` (the tile slices of a shape-sorted level)
+          if (live && (dense || res >= 0)) out[(int64_t)k3 * ld] = res;
           if (res >= 0) present |= 1u << k3;
           if (tm) {
             const int k = it * 27 + k3;
@@ -574,14 +576,23 @@ k_tile_masks_perm(const uint32_t* __restrict__ vmask, int64_t ld, const int32_t*
 // conv0 when every voxel carries the SAME input feature c (SPSModel.forward: the mean of the constant
 // 0.5 point features, models.py:22-25): out[o] = relu(c * sum_{k present} W[k][:] + shift).  Only the
 // PRESENCE of the 125 neighbours matters, and that is one bit of the 64-bit occupancy word of a 4x4x4
-// block: 8 block probes + 125 bit tests per voxel, no index reads at all.
+// block: 8 block probes per voxel, no index reads at all; the weight sum goes through per-row tables.
 __global__ void __launch_bounds__(256)
 k_conv0_const(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr,
               const Slot* __restrict__ tab, const unsigned long long* __restrict__ occ, float cfeat,
               const float* __restrict__ w, const float* __restrict__ shift, int round_out, float* __restrict__ out,
               int64_t out_ld) {
-  __shared__ float w_s[125 * 8];
-  for (int i = threadIdx.x; i < 125 * 8; i += blockDim.x) w_s[i] = __ldg(w + i);
+  // row tables: T[row = (dz, dy)][5-bit x pattern][8] = sum of W[k][:] over the pattern's present dx.  A voxel then
+  // needs 25 table rows (skipping empty ones) instead of 125 predicated weight adds.
+  __shared__ __align__(16) float w_t[25 * 32 * 8];
+  for (int e = threadIdx.x; e < 25 * 32; e += blockDim.x) {
+    const int row = e >> 5, pat = e & 31;
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int dx = 0; dx < 5; ++dx)
+      if ((pat >> dx) & 1)
+        for (int c = 0; c < 8; ++c) a[c] += __ldg(w + (row * 5 + dx) * 8 + c);
+    for (int c = 0; c < 8; ++c) w_t[e * 8 + c] = a[c];
+  }
   __syncthreads();
   const int n = *n_ptr;
   if (n == 0) return;
@@ -628,12 +639,16 @@ k_conv0_const(const unsigned long long* __restrict__ keys, const int32_t* __rest
     float acc[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[c] = 0.f;
-#pragma unroll 5
-    for (int k = 0; k < 125; ++k) {
-      const bool hit = ((k < 64 ? p_lo >> k : p_hi >> (k - 64)) & 1ull) != 0ull;
-      const float4 w0 = *reinterpret_cast<const float4*>(w_s + k * 8);
-      const float4 w1 = *reinterpret_cast<const float4*>(w_s + k * 8 + 4);
-      if (hit) {
+#pragma unroll
+    for (int row = 0; row < 25; ++row) {
+      const int k0 = row * 5;   // compile-time after unrolling
+      unsigned pat;
+      if (k0 + 5 <= 64) pat = (unsigned)(p_lo >> k0) & 31u;
+      else if (k0 >= 64) pat = (unsigned)(p_hi >> (k0 - 64)) & 31u;
+      else pat = (unsigned)((p_lo >> k0) | (p_hi << (64 - k0))) & 31u;
+      if (pat) {
+        const float4 w0 = *reinterpret_cast<const float4*>(w_t + (row * 32 + pat) * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(w_t + (row * 32 + pat) * 8 + 4);
         acc[0] += w0.x; acc[1] += w0.y; acc[2] += w0.z; acc[3] += w0.w;
         acc[4] += w1.x; acc[5] += w1.y; acc[6] += w1.z; acc[7] += w1.w;
       }
@@ -803,6 +818,9 @@ extern "C" int sps_voxelize(sps_ctx* ctx, const float* d_points, int64_t n, int6
 
 namespace sps {
 int build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st);
+bool conv_needs_dense_maps();
+int conv_backend();
+static inline bool conv_half_off() { return conv_backend() == 1; }   // exact-fp32 mode gathers from the dense maps (CUDA-core kernels)
 
 static int g_pattern_sort = 1;
 #ifndef SPS_TILE_SLICES
@@ -894,9 +912,15 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
   ctx->have_nbr5 = c0 == nullptr;
   const size_t mask_bytes = (size_t)(n / 128 + 1) * 16;
   SPS_CUDA_CHECK(cudaMemsetAsync(ctx->tmask3[0], 0, mask_bytes, st));
+  // fused forward on a shape-sorted level: the convolutions read the tile slices, the slices read only present entries
+  auto sparse_ok = [&](int L) {
+    return c0 != nullptr && !conv_needs_dense_maps() && !conv_half_off() && g_tile_slices && ctx->tslice[L] != nullptr && g_pattern_sort && L >= kFirstSortedLevel &&
+           L <= kLastSortedLevel && (g_pattern_sort == 2 || ctx->n >= kMinRowsForSort);
+  };
   k_kernel_map_blk3<3><<<dim3(grid_for(n, 256, 148 * 8), 3), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->table,
                                                                               ctx->cells, ctx->occ, 0, ctx->nbr3[0],
-                                                                              ctx->ld, ctx->tmask3[0], ctx->vmask);
+                                                                              ctx->ld, ctx->tmask3[0], ctx->vmask,
+                                                                              sparse_ok(0) ? 0 : 1);
   prof_mark("kmap3.L0", st);
   { const int rc = pattern_order(ctx, 0, st); if (rc != SPS_OK) return rc; }
   for (int L = 1; L < SPS_NUM_LEVELS; ++L) {
@@ -918,7 +942,8 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
     SPS_CUDA_CHECK(cudaMemsetAsync(ctx->tmask3[L], 0, mask_bytes, st));
     k_kernel_map_blk3<3><<<dim3(grid_for(n, 256, 148 * 8), 3), 256, 0, st>>>(ctx->keys[L], ctx->counts + L, ctx->table,
                                                                                 ctx->cells, ctx->occ, L, ctx->nbr3[L],
-                                                                                ctx->ld, ctx->tmask3[L], ctx->vmask);
+                                                                                ctx->ld, ctx->tmask3[L], ctx->vmask,
+                                                                                sparse_ok(L) ? 0 : 1);
     prof_mark(nm_k[L], st);
     { const int rc = pattern_order(ctx, L, st); if (rc != SPS_OK) return rc; }
   }
