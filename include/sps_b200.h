@@ -147,6 +147,10 @@ int sps_net_destroy(sps_net* net);
  * `model.MinkUNet.`, cf. src/sps/datasets/util.py:33-39).  1x1 kernels may be [Cin,Cout] or
  * [1,Cin,Cout].  `*.num_batches_tracked` entries are ignored by the caller. */
 int sps_net_set_tensor(sps_net* net, const char* name, const float* h_data, int64_t numel);
+/* Which column of `final` ([8, Cout] kernel, [1, Cout] bias) the forward returns, and whether the sigmoid of
+ * models.py:29 is applied.  Default (0, 1) = SPSModel.  MOS4DNet (c_ws/src/mos4d/scripts/mos4d.py:15,32:
+ * CustomMinkUNet(1, 3, D=4), `out.features[:, 2]`, no sigmoid) = (2, 0).  Call before sps_net_finalize. */
+int sps_net_set_output(sps_net* net, int channel, int apply_sigmoid);
 size_t sps_net_device_bytes(void);
 /* Folds every BatchNorm (eval) into the preceding kernel + a shift, packs, uploads into the
  * caller's device buffer.  Fails with SPS_ERR_BAD_ARG if a tensor of CustomMinkUNet(1,1,D=4)

@@ -38,6 +38,8 @@ constexpr int kInitDim = 8;
 struct sps_net {
   std::map<std::string, std::vector<float>> host;
   bool finalized = false;
+  int head_channel = 0;      // column of `final` that the forward returns (out_channels > 1: MOS4DNet returns column 2)
+  int apply_sigmoid = 1;     // SPSModel: sigmoid(logit); MOS4DNet: the raw logit
   sps::ConvW conv0, down[4], up[4], blk1[8], blk2[8];
   float* head_w = nullptr;
   float head_b = 0.f;
@@ -109,6 +111,13 @@ extern "C" int sps_net_destroy(sps_net* net) {
 extern "C" int sps_net_set_tensor(sps_net* net, const char* name, const float* h_data, int64_t numel) {
   if (!net || !name || !h_data || numel <= 0) return SPS_ERR_BAD_ARG;
   net->host[name] = std::vector<float>(h_data, h_data + numel);
+  net->finalized = false;
+  return SPS_OK;
+}
+extern "C" int sps_net_set_output(sps_net* net, int channel, int apply_sigmoid) {
+  if (!net || channel < 0) return SPS_ERR_BAD_ARG;
+  net->head_channel = channel;
+  net->apply_sigmoid = apply_sigmoid != 0;
   net->finalized = false;
   return SPS_OK;
 }
@@ -195,10 +204,17 @@ extern "C" int sps_net_finalize(sps_net* net, void* d_weights, size_t bytes, voi
     inpl = P[4 + i];
   }
   const std::vector<float>*fw, *fb;
-  ok = ok && get(net, "final.kernel", P[7], &fw) && get(net, "final.bias", 1, &fb);
+  // final: [8, Cout] kernel + [1, Cout] bias (minkunet.py:152-158); the forward returns ONE column of it
+  // (SPSModel: Cout = 1; MOS4DNet, c_ws/src/mos4d/scripts/mos4d.py:15,32: Cout = 3, `out.features[:, 2]`)
+  auto itb = net->host.find("final.bias");
+  const int cout_final = itb == net->host.end() ? 0 : (int)itb->second.size();
+  ok = ok && cout_final >= 1 && net->head_channel < cout_final &&
+       get(net, "final.kernel", (size_t)P[7] * cout_final, &fw) && get(net, "final.bias", cout_final, &fb);
   if (!ok) return SPS_ERR_BAD_ARG;
-  const size_t head_off = pk.add(*fw);
-  net->head_b = (*fb)[0];
+  std::vector<float> head(P[7]);
+  for (int c = 0; c < P[7]; ++c) head[c] = (*fw)[(size_t)c * cout_final + net->head_channel];
+  const size_t head_off = pk.add(head);
+  net->head_b = (*fb)[net->head_channel];
   if (pk.image.size() * sizeof(float) > bytes) return SPS_ERR_CAPACITY;
   float* base = (float*)d_weights;
   cudaStream_t st = (cudaStream_t)stream;
@@ -225,11 +241,14 @@ __global__ void k_fill_f32(float* __restrict__ p, const int32_t* __restrict__ n_
 
 // SparseTensor.slice(tensor_field) + sigmoid (src/sps/models/models.py:28-29)
 __global__ void k_devox_sigmoid(const float* __restrict__ logits, const int32_t* __restrict__ inv, int64_t n,
-                                float* __restrict__ scores) {
+                                float* __restrict__ scores, int apply_sigmoid) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int v = __ldg(inv + i);
     float s = nanf("");
-    if (v >= 0) s = 1.0f / (1.0f + expf(-__ldg(logits + v)));
+    if (v >= 0) {
+      s = __ldg(logits + v);
+      if (apply_sigmoid) s = 1.0f / (1.0f + expf(-s));
+    }
     scores[i] = s;
   }
 }
@@ -364,15 +383,18 @@ extern "C" int sps_unet_forward(sps_ctx* ctx, const sps_net* net, const float* d
   return unet_forward(ctx, net, d_feat0, d_logits, (cudaStream_t)stream);
 }
 
-extern "C" int sps_devox_sigmoid(const float* d_logits, const int32_t* d_inv, int64_t n, float* d_scores,
-                                 void* stream) {
+static int devox(const float* d_logits, const int32_t* d_inv, int64_t n, float* d_scores, int apply_sigmoid, void* stream) {
   if (!d_logits || !d_inv || !d_scores || n < 0) return SPS_ERR_BAD_ARG;
   if (n == 0) return SPS_OK;
   int64_t g = (n + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
-  k_devox_sigmoid<<<(int)g, 256, 0, (cudaStream_t)stream>>>(d_logits, d_inv, n, d_scores);
+  k_devox_sigmoid<<<(int)g, 256, 0, (cudaStream_t)stream>>>(d_logits, d_inv, n, d_scores, apply_sigmoid);
   SPS_CUDA_CHECK(cudaGetLastError());
   return SPS_OK;
+}
+extern "C" int sps_devox_sigmoid(const float* d_logits, const int32_t* d_inv, int64_t n, float* d_scores,
+                                 void* stream) {
+  return devox(d_logits, d_inv, n, d_scores, 1, stream);
 }
 
 namespace sps {
@@ -403,7 +425,7 @@ int forward_impl(sps_ctx* ctx, const sps_net* net, const float* d_points, int64_
   if (rc != SPS_OK) return rc;
   rc = unet_forward(ctx, net, ctx->buf[sps_ctx::FEAT0], ctx->buf[sps_ctx::LOGITS], st, /*conv0_done=*/true);
   if (rc != SPS_OK) return rc;
-  rc = sps_devox_sigmoid(ctx->buf[sps_ctx::LOGITS], ctx->inv, n_scores, d_scores, st);
+  rc = devox(ctx->buf[sps_ctx::LOGITS], ctx->inv, n_scores, d_scores, net->apply_sigmoid, st);
   if (rc != SPS_OK) return rc;
   prof_mark("devox_sigmoid", st);
   // voxelize 5; map building 51 (block tables, strided levels, kernel maps) + 14 per shape-sorted level (keys,

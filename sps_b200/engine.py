@@ -35,7 +35,9 @@ def _require_cuda(t: torch.Tensor, name: str):
 class Net:
     """BN-folded, packed ``CustomMinkUNet(1,1,D=4)`` weights on the device (sps_net)."""
 
-    def __init__(self, state_dict, device="cuda"):
+    def __init__(self, state_dict, device="cuda", output_channel=0, apply_sigmoid=True):
+        """``output_channel`` / ``apply_sigmoid``: which column of ``final`` the forward returns and whether
+        the sigmoid is applied (SPSModel: 0, True; MOS4DNet: 2, False)."""
         self.lib = _cabi.load()
         self.device = norm_device(device)
         h = C.c_void_p()
@@ -49,6 +51,7 @@ class Net:
             arr = np.ascontiguousarray(arr, dtype=np.float32)
             check(self.lib.sps_net_set_tensor(h, name.encode(), arr.ctypes.data_as(C.c_void_p), arr.size),
                   f"sps_net_set_tensor({name})")
+        check(self.lib.sps_net_set_output(h, int(output_channel), int(bool(apply_sigmoid))), "sps_net_set_output")
         nbytes = self.lib.sps_net_device_bytes()
         with torch.cuda.device(self.device):
             self.storage = torch.empty(nbytes, dtype=torch.uint8, device=self.device)

@@ -83,8 +83,8 @@ class CustomMinkUNet(nn.Module):
 
     def __init__(self, in_channels=1, out_channels=1, D=4):
         super().__init__()
-        if (in_channels, out_channels, D) != (1, 1, 4):
-            raise NotImplementedError("the B200 engine implements CustomMinkUNet(1, 1, D=4) (models.py:17)")
+        if (in_channels, D) != (1, 4) or out_channels < 1:
+            raise NotImplementedError("the B200 engine implements CustomMinkUNet(1, out_channels, D=4) (models.py:17, mos4d.py:15)")
         P, self.inplanes = PLANES, INIT_DIM
         self.conv0p1s1 = _Kernel(125, in_channels, self.inplanes)
         self.bn0 = _BatchNorm(self.inplanes)
@@ -153,7 +153,8 @@ class SPSModel(nn.Module):
         self._net_version = -1
         self._host_out = None
         self._pipe = None
-        self.lanes = 2            # engine contexts / streams that forward_async alternates between
+        self.lanes = 3            # engine contexts / streams that forward_async alternates between
+        self.output_channel, self.apply_sigmoid = 0, True   # models.py:28-29: sigmoid of the single output channel
 
     def invalidate(self):
         """Weights changed in place: re-fold and re-upload them at the next forward."""
@@ -162,7 +163,7 @@ class SPSModel(nn.Module):
     def _prepare(self, n, device):
         device = norm_device(device)
         if self._net is None or self._net.device != device or self._net_version != self.MinkUNet.weights_version:
-            self._net = Net(self.MinkUNet.state_dict(), device)
+            self._net = Net(self.MinkUNet.state_dict(), device, self.output_channel, self.apply_sigmoid)
             self._net_version = self.MinkUNet.weights_version
         if self._engine is None or self._engine.max_points < n or self._engine.device != device:
             cap = max(self._min_points, 1 << max(10, int(math.ceil(math.log2(max(n, 1))))))
@@ -254,6 +255,26 @@ class SPSModel(nn.Module):
         """Synchronise and raise if the last forward met an out-of-range coordinate."""
         if self._engine is not None:
             self._engine.status()
+
+
+class MOS4DNet(SPSModel):
+    """The 4DMOS baseline the reference ships (c_ws/src/mos4d/scripts/mos4d.py:10-32): the same network with
+    ``CustomMinkUNet(in_channels=1, out_channels=3, D=4)``; ``forward`` returns the raw logit of class 2 (moving)
+    for every point.  The time column is the scan index of a sliding window (mos4d_node.py:98-117); only time
+    DIFFERENCES matter to the sparse convolutions, so the window is shifted to start at t = 0 (the voxel key holds
+    16 time planes: windows of up to 16 scans, the node uses 10)."""
+
+    def __init__(self, voxel_size: float, max_points: int = 0):
+        super().__init__(voxel_size, max_points)
+        self.MinkUNet = CustomMinkUNet(in_channels=1, out_channels=3, D=4)
+        self.output_channel, self.apply_sigmoid = 2, False     # mos4d.py:32 `out.features[:, 2]`
+
+    def forward(self, coordinates: torch.Tensor):
+        coordinates = coordinates.reshape(-1, coordinates.shape[-1]).to(torch.float32)
+        if coordinates.shape[0]:
+            coordinates = coordinates.clone()
+            coordinates[:, 4] -= torch.floor(coordinates[:, 4].min())
+        return super().forward(coordinates)
 
 
 class SPSNet(nn.Module):
