@@ -126,8 +126,7 @@ typedef struct sps_conv_args {
   const int32_t* tile_slices; /* optional, with perm: the kernel map already gathered per tile --
                                [tile][SPS_TILE_SLICE_ENTRIES][128] int32, entry e < popcount(mask) = input
                                rows of the tile's e-th present offset, entry popcount(mask) = the tile's own
-                               rows (perm), each entry laid out [row % 32][row / 32].  NULL = the kernel
-                               gathers from `map` through `perm` itself                          */
+                               rows (perm).  NULL = the kernel gathers from `map` through `perm` itself */
   int io_dtype;             /* SPS_IO_F32 (0): `in`, `in2`, `res`, `out` are fp32 rows.  SPS_IO_F16: they point
                                at fp16 rows (leading dimensions in halves, multiples of 8) and weight_kmajor is
                                the sps_conv_pack_kmajor_f16 matrix: the fused forward's storage format

@@ -5,9 +5,8 @@
 // pipeline stage (ring bookkeeping, 64-bit address selects, a divergent-address arrive loop) and
 // only 8 % waiting for a free stage.  Here
 //   * a dedicated LOADER warp builds the per-tile list of present offsets and stages the kernel-map
-//     slice (and the tile's own row numbers) one tile ahead with cp.async, in a
-//     [entry][row%32][row/32] layout so that a producer thread fetches its four row indices with one
-//     16-byte shared load;
+//     slice (and the tile's own row numbers) up to 7 tiles ahead with 16-byte cp.async copies; a
+//     producer thread fetches the indices of its four rows with one 16-byte shared load;
 //   * the stage ring is 4 deep: the gathered rows are re-read from L1 by neighbouring output rows,
 //     and measured run time follows the L1 size the carve-out leaves (4 stages beat 2, 3 and 5-7;
 //     +40 KB of unused shared memory costs +25 % on the 32/48-channel layers).  A variant that
@@ -41,7 +40,11 @@ constexpr int kV6EpiWarp0 = kV6MmaWarp + 1;
 constexpr int kV6Threads = (kV6EpiWarp0 + 4) * 32;
 constexpr int kV6Entries = kMaxK + 1;                 // present offsets + the tile's own rows
 constexpr int kV6EntryBytes = kTileM * 4;
-constexpr int kV6ParBytes = kV6Entries * kV6EntryBytes;  // one parity buffer of staged row indices
+constexpr int kV6ParBytes = kV6Entries * kV6EntryBytes;  // staged row indices of one 81-offset tile
+// The index area (2 x 82 entries) holds as many tiles as fit: 2 for the 81-offset kernels, 8 for the 2x2x2 ones
+// (9 entries per tile).  Tiles of the small kernels are one or two stages long, so the number of tiles in flight
+// -- not the stage ring -- bounds their memory-level parallelism.
+constexpr int kV6MaxTilesAhead = 8;
 
 #ifndef SPS_V6_PAD_KB
 #define SPS_V6_PAD_KB 0   // experiment: unused shared memory, shrinks the L1 side of the unified array
@@ -51,9 +54,10 @@ struct V6Cfg {
   static constexpr int S = NPAD == 64 ? SPS_V6_S64 : NPAD == 32 ? SPS_V6_S32 : SPS_V6_S16;
   static constexpr int kBStage = NPAD * 128;
   static constexpr int kTmemCols = 2 * NPAD < 32 ? 32 : 2 * NPAD;
-  // A ring | B ring | row indices [2][82][128] | barriers | klist [2][96] | nact [2] | shift [64] | tmem slot
+  // A ring | B ring | row indices [2][82][128] | barriers | klist [8][96] | nact [8] | shift [64] | tmem slot
   static constexpr size_t smem = (size_t)S * (kAStageBytes + kBStage) + 2 * (size_t)kV6ParBytes +
-                                 8 * (2 * S + 8) + 2 * 96 + 16 + 64 * 4 + 16 + SPS_V6_PAD_KB * 1024;
+                                 8 * (2 * S + 2 * kV6MaxTilesAhead + 4) + kV6MaxTilesAhead * 96 + 4 * kV6MaxTilesAhead +
+                                 64 * 4 + 16 + SPS_V6_PAD_KB * 1024;
 };
 
 // 16-byte copy that writes zeros instead when `skip` is set (the ignore-src form: one predicate, no size select)
@@ -101,23 +105,26 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
   uint8_t* sB = smem + S * kAStageBytes;
   int32_t* sidx = reinterpret_cast<int32_t*>(sB + S * kBStageBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sidx) + 2 * kV6ParBytes);
-  // bars: full[S], empty[S], idx_full[2], idx_empty[2], acc_full[2], acc_empty[2]
-  uint8_t* klist = reinterpret_cast<uint8_t*>(bars + 2 * S + 8);
-  int32_t* snact = reinterpret_cast<int32_t*>(klist + 2 * 96);
-  float* sshift = reinterpret_cast<float*>(snact + 4);
+  // bars: full[S], empty[S], idx_full[8], idx_empty[8], acc_full[2], acc_empty[2]
+  uint8_t* klist = reinterpret_cast<uint8_t*>(bars + 2 * S + 2 * kV6MaxTilesAhead + 4);
+  int32_t* snact = reinterpret_cast<int32_t*>(klist + kV6MaxTilesAhead * 96);
+  float* sshift = reinterpret_cast<float*>(snact + kV6MaxTilesAhead);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sshift + 64);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB), sidx_u = smem_u32(sidx);
   const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * S, bar_idxf = bar_empty + 8 * S,
-                 bar_idxe = bar_idxf + 16, bar_accf = bar_idxe + 16, bar_acce = bar_accf + 16;
+                 bar_idxe = bar_idxf + 8 * kV6MaxTilesAhead, bar_accf = bar_idxe + 8 * kV6MaxTilesAhead,
+                 bar_acce = bar_accf + 16;
   if (sA_u & 1023) __trap();
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(bar_full + 8 * s, kV6ProducerThreads); mbar_init(bar_empty + 8 * s, 1); }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kV6MaxTilesAhead; ++i) {
       mbar_init(bar_idxf + 8 * i, 33);                 // 32 async arrivals (copies landed) + 1 for the plain stores
       mbar_init(bar_idxe + 8 * i, kV6ProducerWarps);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(bar_accf + 8 * i, 1);
       mbar_init(bar_acce + 8 * i, 128);
     }
@@ -146,6 +153,9 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
   const int st2 = (gpk2 + 7) >> 3;                      // stages of the fused 1x1 term
   const uint32_t* tmask = a.tile_mask;
   const int gstep = gridDim.x;
+  // tiles whose index slices fit in the staging area at once, and the bytes each takes
+  const int NP = min(kV6MaxTilesAhead, (2 * kV6Entries) / (K + 1));
+  const uint32_t par_bytes = (uint32_t)(K + 1) * kV6EntryBytes;
   auto tile_nact = [&](int tile) {
     return __popc(__ldg(tmask + 4 * tile)) + __popc(__ldg(tmask + 4 * tile + 1)) + __popc(__ldg(tmask + 4 * tile + 2));
   };
@@ -153,8 +163,13 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
 
   if (warp < kV6ProducerWarps) {
     // =========================== PRODUCERS (256 threads) ===========================
-    const int r0 = tid >> 3, cB = tid & 7;          // chunk column cB of rows r0 + 32 i
-    const uint32_t a_off = (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128) + (((uint32_t)cB ^ (uint32_t)(r0 & 7)) << 4);
+    const int r0 = tid >> 3, cB = tid & 7;          // chunk column cB of rows 4 r0 + i (one 16-byte index load)
+    uint32_t a_off[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = 4 * r0 + i;
+      a_off[i] = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128) + (((uint32_t)cB ^ (uint32_t)(r & 7)) << 4);
+    }
     const uint32_t in_ld_b = (uint32_t)a.in_ld * EB, in2_ld_b = (uint32_t)a.in2_ld * EB;
     const char* in_b = reinterpret_cast<const char*>(a.in);
     const char* in2_b = reinterpret_cast<const char*>(a.in2);
@@ -224,11 +239,11 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
     auto open_tile = [&]() -> bool {
       for (;;) {
         if (tile >= ntiles) return false;
-        const int par = it_tile & 1;
-        mbar_wait(bar_idxf + 8 * par, (it_tile >> 1) & 1);
+        const int par = it_tile % NP;
+        mbar_wait(bar_idxf + 8 * par, (it_tile / NP) & 1);
         nact = snact[par];
         nst = tile_stages(nact);
-        sx = sidx_u + (uint32_t)par * kV6ParBytes + (uint32_t)r0 * 16u;
+        sx = sidx_u + (uint32_t)par * par_bytes + (uint32_t)r0 * 16u;
         kl = klist + par * 96;
         m = 0; e = 0; sub = 0;
         if (nst > 0) { fetch(); return true; }
@@ -249,7 +264,7 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
         return true;
       }
       __syncwarp();                                   // every lane holds its indices in registers by now
-      if (lane == 0) mbar_arrive(bar_idxe + 8 * (it_tile & 1));
+      if (lane == 0) mbar_arrive(bar_idxe + 8 * (it_tile % NP));
       tile += gstep; ++it_tile;
       return open_tile();
     };
@@ -261,12 +276,12 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
       for (int s = 0; s < S; ++s) {
         if (more) {
           mbar_wait(bar_empty + 8 * s, phase ^ 1);    // the MMAs that read slot s have completed
-          const uint32_t dstA = sA_u + (uint32_t)s * kAStageBytes + a_off;
+          const uint32_t dstA = sA_u + (uint32_t)s * kAStageBytes;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const bool ok = okc && idx[i] >= 0;
             const uint32_t row = (uint32_t)(idx[i] < 0 ? 0 : idx[i]);
-            cp_async16_or_zero<SPS_V6_A_CG != 0>(dstA + i * 4096, base + (uint64_t)row * ld_b, !ok);
+            cp_async16_or_zero<SPS_V6_A_CG != 0>(dstA + a_off[i], base + (uint64_t)row * ld_b, !ok);
           }
           if (b_lane) {
 #pragma unroll
@@ -283,20 +298,33 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
   } else if (warp == kV6LoaderWarp) {
     // =========================== LOADER (one warp, one tile ahead) ===========================
     int it = 0;
+    const bool map_vec = ((reinterpret_cast<uintptr_t>(a.map) & 15) == 0) && ((a.map_ld & 3) == 0);
+    // the tile mask is the head of every tile's dependency chain: keep the NEXT tile's words in flight
+    uint32_t mw[3] = {0u, 0u, 0u};
+    if ((int)blockIdx.x < ntiles) {
+#pragma unroll
+      for (int w = 0; w < 3; ++w) mw[w] = __ldg(tmask + 4 * blockIdx.x + w);
+    }
     for (int tile = blockIdx.x; tile < ntiles; tile += gstep, ++it) {
-      const int par = it & 1;
-      mbar_wait(bar_idxe + 8 * par, ((it >> 1) & 1) ^ 1);     // producers are done with this buffer
+      const int par = it % NP;
+      const uint32_t cur[3] = {mw[0], mw[1], mw[2]};
+      if (tile + gstep < ntiles) {
+#pragma unroll
+        for (int w = 0; w < 3; ++w) mw[w] = __ldg(tmask + 4 * (tile + gstep) + w);
+      }
+      mbar_wait(bar_idxe + 8 * par, ((it / NP) & 1) ^ 1);     // producers are done with this buffer
       uint8_t* klp = klist + par * 96;
       int nact = 0;
 #pragma unroll
       for (int w = 0; w < 3; ++w) {
-        const uint32_t bits = __ldg(tmask + 4 * tile + w);
+        const uint32_t bits = cur[w];
         if ((bits >> lane) & 1u) klp[nact + __popc(bits & ((1u << lane) - 1u))] = (uint8_t)(32 * w + lane);
         nact += __popc(bits);
       }
       if (lane == 0) snact[par] = nact;
       __syncwarp();
-      const uint32_t dst = sidx_u + (uint32_t)par * kV6ParBytes + (uint32_t)lane * 16u;
+      // entries are 128 row indices in tile order; lane owns rows 4 lane .. 4 lane + 3 (one 16-byte chunk per entry)
+      const uint32_t dst = sidx_u + (uint32_t)par * par_bytes + (uint32_t)lane * 16u;
       if (a.tile_slices) {
         // the level's pass already gathered this tile's slice (entries 0..nact, the last one = own rows)
         const char* src = reinterpret_cast<const char*>(a.tile_slices + (int64_t)tile * (SPS_TILE_SLICE_ENTRIES * kTileM)) + lane * 16;
@@ -304,13 +332,23 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)e * kV6EntryBytes),
                        "l"(src + (size_t)e * kV6EntryBytes)
                        : "memory");
+      } else if (!a.perm && map_vec && tile * kTileM + kTileM <= n_out) {
+        // physical row order, full tile: the slice of map[k] is contiguous -> one 16-byte copy per lane and entry
+        const int row0 = tile * kTileM + 4 * lane;
+        asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)nact * kV6EntryBytes), "r"(row0),
+                     "r"(row0 + 1), "r"(row0 + 2), "r"(row0 + 3)
+                     : "memory");
+        const int32_t* src = a.map + row0;
+        for (int e = 0; e < nact; ++e)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)e * kV6EntryBytes),
+                       "l"(src + (int64_t)klp[e] * a.map_ld)
+                       : "memory");
       } else {
-        // lane owns rows lane + 32 i of the tile; staged at [entry][lane][i]
         const int32_t* src[4];
         bool rok[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int prow = tile * kTileM + lane + 32 * i;
+          const int prow = tile * kTileM + 4 * lane + i;
           rok[i] = prow < n_out;
           const int row = rok[i] ? (a.perm ? __ldg(a.perm + prow) : prow) : 0;
           src[i] = a.map + row;

@@ -518,7 +518,7 @@ k_radix_scatter(const uint32_t* __restrict__ keys, const int32_t* __restrict__ v
 }
 
 // present-offset masks of the 128-row tiles taken in `perm` order, and (slices != nullptr) the tiles' slices of
-// the kernel map gathered once for all the convolutions of the level: slices[tile][e][r%32][r/32] = input row
+// the kernel map gathered once for all the convolutions of the level: slices[tile][e][r] = input row
 // of sorted row r under the tile's e-th present offset, entry e = #present = the tile's own rows.
 __global__ void __launch_bounds__(128)
 k_tile_masks_perm(const uint32_t* __restrict__ vmask, int64_t ld, const int32_t* __restrict__ perm,
@@ -558,7 +558,7 @@ k_tile_masks_perm(const uint32_t* __restrict__ vmask, int64_t ld, const int32_t*
         }
       }
       __syncthreads();
-      int32_t* dst = slices + (int64_t)tile * (SPS_TILE_SLICE_ENTRIES * 128) + (threadIdx.x & 31) * 4 + (threadIdx.x >> 5);
+      int32_t* dst = slices + (int64_t)tile * (SPS_TILE_SLICE_ENTRIES * 128) + threadIdx.x;
       const uint32_t mine[3] = {w0, w1, w2};
 #pragma unroll 4
       for (int e = 0; e < nact; ++e) {
