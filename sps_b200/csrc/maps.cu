@@ -912,15 +912,16 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
   ctx->have_nbr5 = c0 == nullptr;
   const size_t mask_bytes = (size_t)(n / 128 + 1) * 16;
   SPS_CUDA_CHECK(cudaMemsetAsync(ctx->tmask3[0], 0, mask_bytes, st));
-  // fused forward on a shape-sorted level: the convolutions read the tile slices, the slices read only present entries
+  // fused forward on a shape-sorted level: the convolutions read the tile slices and the sorted tile masks, the slices
+  // read only present entries -> neither the -1 entries nor the physical-order tile masks are produced
   auto sparse_ok = [&](int L) {
     return c0 != nullptr && !conv_needs_dense_maps() && !conv_half_off() && g_tile_slices && ctx->tslice[L] != nullptr && g_pattern_sort && L >= kFirstSortedLevel &&
            L <= kLastSortedLevel && (g_pattern_sort == 2 || ctx->n >= kMinRowsForSort);
   };
   k_kernel_map_blk3<3><<<dim3(grid_for(n, 256, 148 * 8), 3), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->table,
                                                                               ctx->cells, ctx->occ, 0, ctx->nbr3[0],
-                                                                              ctx->ld, ctx->tmask3[0], ctx->vmask,
-                                                                              sparse_ok(0) ? 0 : 1);
+                                                                              ctx->ld, sparse_ok(0) ? nullptr : ctx->tmask3[0],
+                                                                              ctx->vmask, sparse_ok(0) ? 0 : 1);
   prof_mark("kmap3.L0", st);
   { const int rc = pattern_order(ctx, 0, st); if (rc != SPS_OK) return rc; }
   for (int L = 1; L < SPS_NUM_LEVELS; ++L) {
@@ -942,8 +943,8 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
     SPS_CUDA_CHECK(cudaMemsetAsync(ctx->tmask3[L], 0, mask_bytes, st));
     k_kernel_map_blk3<3><<<dim3(grid_for(n, 256, 148 * 8), 3), 256, 0, st>>>(ctx->keys[L], ctx->counts + L, ctx->table,
                                                                                 ctx->cells, ctx->occ, L, ctx->nbr3[L],
-                                                                                ctx->ld, ctx->tmask3[L], ctx->vmask,
-                                                                                sparse_ok(L) ? 0 : 1);
+                                                                                ctx->ld, sparse_ok(L) ? nullptr : ctx->tmask3[L],
+                                                                                ctx->vmask, sparse_ok(L) ? 0 : 1);
     prof_mark(nm_k[L], st);
     { const int rc = pattern_order(ctx, L, st); if (rc != SPS_OK) return rc; }
   }
