@@ -33,11 +33,13 @@ static size_t carve(sps_ctx* c, void* base, int64_t max_points) {
   const int64_t ld = (N + 31) & ~int64_t(31);
   c->max_points = N;
   c->ld = ld;
-  c->counts = cv.take<int32_t>(64);  // counts[5], status, ticket, n_dev share one cache line group
-  c->status = c->counts + 8;
-  c->ticket = reinterpret_cast<uint32_t*>(c->counts + 9);
-  c->n_dev = c->counts + 10;
-  c->nblocks = c->counts + 11;
+  // Device scalars, one 128-byte line per role: counts[0..4] + n_dev are READ by every thread of every map kernel,
+  // the words that kernels hit with atomics (scan tickets, the block-id counter, the status word) get their own lines.
+  c->counts = cv.take<int32_t>(256);
+  c->n_dev = c->counts + 5;
+  c->ticket = reinterpret_cast<uint32_t*>(c->counts + 32);
+  c->nblocks = c->counts + 64;
+  c->status = c->counts + 96;
   c->cells = cv.take<int32_t>((size_t)N * 64);
   c->occ = cv.take<unsigned long long>(N);
   c->staging = cv.take<float>((size_t)N * 8);
@@ -117,7 +119,7 @@ extern "C" int sps_ctx_create(sps_ctx** out, void* d_workspace, size_t workspace
   if (need > workspace_bytes) { delete c; return SPS_ERR_CAPACITY; }
   c->base = (char*)d_workspace;
   c->bytes = workspace_bytes;
-  cudaError_t e = cudaMemset(c->counts, 0, 64 * sizeof(int32_t));
+  cudaError_t e = cudaMemset(c->counts, 0, 256 * sizeof(int32_t));
   if (e == cudaSuccess) {  // every 128-row tile of a 2x2x2x1 map may hold all eight offsets
     std::vector<uint32_t> m((size_t)(c->ld / 128 + 1) * 4, 0u);
     for (size_t i = 0; i < m.size(); i += 4) m[i] = 0xFFu;
@@ -253,7 +255,7 @@ extern "C" int sps_ctx_pair_count(sps_ctx* ctx, int level, int kind, int64_t* h_
   const int K = kind == 3 ? 81 : kind == 5 ? 125 : 8;
   if (!map) return SPS_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  unsigned long long* d_out = reinterpret_cast<unsigned long long*>(ctx->counts + 16);
+  unsigned long long* d_out = reinterpret_cast<unsigned long long*>(ctx->counts + 128);
   SPS_CUDA_CHECK(cudaMemsetAsync(d_out, 0, 8, st));
   k_count_nonneg<<<148 * 8, 256, 0, st>>>(map, ctx->ld, K, ctx->counts + level, d_out);
   SPS_CUDA_CHECK(cudaGetLastError());

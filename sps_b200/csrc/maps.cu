@@ -852,7 +852,7 @@ static int pattern_order(sps_ctx* ctx, int L, cudaStream_t st) {
   for (int pass = 0; pass < 4; ++pass) {
     k_radix_hist<<<nb_max, kSortBlock, 0, st>>>(ka, cnt, 8 * pass, ctx->sort_hist);
     k_scan_hist<<<cdiv(hist_n, kScanBlock), kScanBlock, 0, st>>>(ctx->sort_hist, cnt, ctx->sort_hrank, ctx->sort_hsums,
-                                                                   ctx->ticket, ctx->counts + 12);
+                                                                   ctx->ticket, ctx->counts + 160);
     k_radix_scatter<<<nb_max, kSortBlock, 0, st>>>(ka, va, cnt, 8 * pass, ctx->sort_hrank, ctx->sort_hsums, kb, vb);
     std::swap(ka, kb);
     std::swap(va, vb);
@@ -980,7 +980,7 @@ struct sps_map {
 namespace sps {
 
 struct Scratch {  // carve of a sps_map_bytes(n) buffer
-  int32_t* scalars;   // 64 ints: [0]=n_dev [1]=ticket [2]=status
+  int32_t* scalars;   // 64 ints: [0]=n_dev; second 128-byte line (atomics): [32]=ticket [40]=status
   Slot* table;
   uint32_t cap;
   uint32_t* slot_of;
@@ -1112,10 +1112,10 @@ extern "C" int sps_map_build(sps_map** out, void* d_storage, size_t bytes, const
   SPS_CUDA_CHECK(cudaMemsetAsync(s.scalars, 0, 64 * 4, st));
   k_set_i32<<<1, 1, 0, st>>>(s.scalars + 0, (int32_t)n);
   k_table_clear<<<grid_for(s.cap, 256), 256, 0, st>>>(s.table, s.scalars + 0);
-  k_insert_xyz<<<grid_for(n, 256), 256, 0, st>>>(d_map_xyz, s.scalars + 0, ds, s.table, nullptr, s.scalars + 2);
+  k_insert_xyz<<<grid_for(n, 256), 256, 0, st>>>(d_map_xyz, s.scalars + 0, ds, s.table, nullptr, s.scalars + 40);
   SPS_CUDA_CHECK(cudaGetLastError());
   int32_t status = 0;
-  SPS_CUDA_CHECK(cudaMemcpyAsync(&status, s.scalars + 2, 4, cudaMemcpyDeviceToHost, st));
+  SPS_CUDA_CHECK(cudaMemcpyAsync(&status, s.scalars + 40, 4, cudaMemcpyDeviceToHost, st));
   SPS_CUDA_CHECK(cudaStreamSynchronize(st));
   if (status & kStatusRange) return SPS_ERR_COORD_RANGE;
   sps_map* m = new sps_map();
@@ -1143,9 +1143,9 @@ extern "C" int sps_submap_crop_voxel(const sps_map* map, const float* d_scan_xyz
   k_set_i32<<<1, 1, 0, st>>>(s.scalars + 0, (int32_t)n_scan);
   k_table_clear<<<grid_for(s.cap, 256), 256, 0, st>>>(s.table, s.scalars + 0);
   k_insert_xyz<<<grid_for(n, 256), 256, 0, st>>>(d_scan_xyz, s.scalars + 0, map->ds, s.table, s.slot_of,
-                                                  s.scalars + 2);
+                                                  s.scalars + 40);
   k_first_rank<<<cdiv(n, kScanBlock), kScanBlock, 0, st>>>(s.table, s.slot_of, s.scalars + 0, s.rank, s.block_sums,
-                                                           (uint32_t*)(s.scalars + 1), d_counts + 0, map->table,
+                                                           (uint32_t*)(s.scalars + 32), d_counts + 0, map->table,
                                                            map->cap - 1, d_counts + 1);
   k_write_submap<<<grid_for(n, 256), 256, 0, st>>>(s.table, s.slot_of, s.scalars + 0, s.rank, s.block_sums,
                                                     map->table, map->cap - 1, map->ds, d_out_xyz);
@@ -1166,7 +1166,7 @@ extern "C" int sps_submap_crop_radius(const float* d_map_xyz, int64_t n, const d
   SPS_CUDA_CHECK(cudaMemsetAsync(s.scalars, 0, 64 * 4, st));
   k_set_i32<<<1, 1, 0, st>>>(s.scalars + 0, (int32_t)n);
   k_radius_rank<<<cdiv(nn, kScanBlock), kScanBlock, 0, st>>>(d_map_xyz, s.scalars + 0, center[0], center[1], center[2],
-                                                             radius, s.rank, s.block_sums, (uint32_t*)(s.scalars + 1),
+                                                             radius, s.rank, s.block_sums, (uint32_t*)(s.scalars + 32),
                                                              d_count);
   k_radius_write<<<grid_for(nn, 256), 256, 0, st>>>(d_map_xyz, s.scalars + 0, center[0], center[1], center[2], radius,
                                                     s.rank, s.block_sums, d_out_idx);
