@@ -59,7 +59,13 @@ struct Conv0Fused {
   float cfeat;
   const float* w; const float* shift; int round_out; float* out; int64_t out_ld;
 };
-constexpr int kBufWidth[sps_ctx::NBUF] = {16, 8, 8, 24, 8, 16, 48, 16, 32, 96, 32, 64, 64, 64, 64, 32, 32,
+// SPS_CAT_PAD=1 pads the row strides of the concat buffers to a power of two (24 -> 32, 48 -> 64, 96 -> 128 channels) so that a
+// gathered fp16 row never straddles a 128-byte line; measured neutral (block6.conv1 0.1685 ms either way), off by default.
+#ifndef SPS_CAT_PAD
+#define SPS_CAT_PAD 0
+#endif
+constexpr int kCatLd[4] = {16, SPS_CAT_PAD ? 32 : 24, SPS_CAT_PAD ? 64 : 48, SPS_CAT_PAD ? 128 : 96};   // CAT8, CAT7, CAT6, CAT5
+constexpr int kBufWidth[sps_ctx::NBUF] = {16, 8, 8, kCatLd[1], 8, 16, kCatLd[2], 16, 32, kCatLd[3], 32, 64, 64, 64, 64, 32, 32,
                                           16, 16, 8, 1, 1};
 constexpr int kScanBlock = 1024;
 }

@@ -303,7 +303,7 @@ int unet_forward(sps_ctx* c, const sps_net* net, const float* feat0, float* logi
   auto at = [&](float* base, int off) { return hm ? reinterpret_cast<float*>(reinterpret_cast<__half*>(base) + off) : base + off; };
   // skip tensors live in the tail channel slice of the concat buffers (ME.cat(out, skip))
   float* skip[4] = {at(B[C::CAT8], 8), at(B[C::CAT7], 16), at(B[C::CAT6], 32), at(B[C::CAT5], 64)};
-  const int skip_ld[4] = {16, 24, 48, 96};
+  const int skip_ld[4] = {kCatLd[0], kCatLd[1], kCatLd[2], kCatLd[3]};
   float* cat[4] = {B[C::CAT8], B[C::CAT7], B[C::CAT6], B[C::CAT5]};
   float* E[4] = {B[C::E1], B[C::E2], B[C::E3], B[C::E4]};
   float* H[4] = {B[C::H1], B[C::H2], B[C::H3], B[C::H4]};
