@@ -45,6 +45,9 @@ constexpr int kV6ParBytes = kV6Entries * kV6EntryBytes;  // staged row indices o
 // (9 entries per tile).  Tiles of the small kernels are one or two stages long, so the number of tiles in flight
 // -- not the stage ring -- bounds their memory-level parallelism.
 constexpr int kV6MaxTilesAhead = 8;
+// ordered present-offset lists of the staged tiles: (K + 1) bytes each, rounded to 16 -> at most 224 bytes.  (Every
+// byte counts here: 167 936 bytes per CTA is the last size that still gets the 164 KB carve-out, i.e. 92 KB of L1.)
+constexpr int kV6KlistBytes = 256;
 
 #ifndef SPS_V6_PAD_KB
 #define SPS_V6_PAD_KB 0   // experiment: unused shared memory, shrinks the L1 side of the unified array
@@ -54,9 +57,9 @@ struct V6Cfg {
   static constexpr int S = NPAD == 64 ? SPS_V6_S64 : NPAD == 32 ? SPS_V6_S32 : SPS_V6_S16;
   static constexpr int kBStage = NPAD * 128;
   static constexpr int kTmemCols = 2 * NPAD < 32 ? 32 : 2 * NPAD;
-  // A ring | B ring | row indices [2][82][128] | barriers | klist [8][96] | nact [8] | shift [64] | tmem slot
+  // A ring | B ring | row indices [2][82][128] | barriers | klists | nact [8] | shift [64] | tmem slot
   static constexpr size_t smem = (size_t)S * (kAStageBytes + kBStage) + 2 * (size_t)kV6ParBytes +
-                                 8 * (2 * S + 2 * kV6MaxTilesAhead + 4) + kV6MaxTilesAhead * 96 + 4 * kV6MaxTilesAhead +
+                                 8 * (2 * S + 2 * kV6MaxTilesAhead + 4) + kV6KlistBytes + 4 * kV6MaxTilesAhead +
                                  64 * 4 + 16 + SPS_V6_PAD_KB * 1024;
 };
 
@@ -107,7 +110,7 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sidx) + 2 * kV6ParBytes);
   // bars: full[S], empty[S], idx_full[8], idx_empty[8], acc_full[2], acc_empty[2]
   uint8_t* klist = reinterpret_cast<uint8_t*>(bars + 2 * S + 2 * kV6MaxTilesAhead + 4);
-  int32_t* snact = reinterpret_cast<int32_t*>(klist + kV6MaxTilesAhead * 96);
+  int32_t* snact = reinterpret_cast<int32_t*>(klist + kV6KlistBytes);
   float* sshift = reinterpret_cast<float*>(snact + kV6MaxTilesAhead);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sshift + 64);
 
@@ -156,6 +159,7 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
   // tiles whose index slices fit in the staging area at once, and the bytes each takes
   const int NP = min(kV6MaxTilesAhead, (2 * kV6Entries) / (K + 1));
   const uint32_t par_bytes = (uint32_t)(K + 1) * kV6EntryBytes;
+  const int kl_stride = (K + 1 + 15) & ~15;
   auto tile_nact = [&](int tile) {
     return __popc(__ldg(tmask + 4 * tile)) + __popc(__ldg(tmask + 4 * tile + 1)) + __popc(__ldg(tmask + 4 * tile + 2));
   };
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
         nact = snact[par];
         nst = tile_stages(nact);
         sx = sidx_u + (uint32_t)par * par_bytes + (uint32_t)r0 * 16u;
-        kl = klist + par * 96;
+        kl = klist + par * kl_stride;
         m = 0; e = 0; sub = 0;
         if (nst > 0) { fetch(); return true; }
         __syncwarp();
@@ -313,7 +317,7 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
         for (int w = 0; w < 3; ++w) mw[w] = __ldg(tmask + 4 * (tile + gstep) + w);
       }
       mbar_wait(bar_idxe + 8 * par, ((it / NP) & 1) ^ 1);     // producers are done with this buffer
-      uint8_t* klp = klist + par * 96;
+      uint8_t* klp = klist + par * kl_stride;
       int nact = 0;
 #pragma unroll
       for (int w = 0; w < 3; ++w) {
