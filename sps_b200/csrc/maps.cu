@@ -220,18 +220,6 @@ __global__ void k_assign_coarse(Slot* tab, const uint32_t* __restrict__ slot_of,
   }
 }
 
-// Re-hash the (unique) voxel keys of a level into a table sized by the VOXEL count (the table left by
-// the de-duplication is sized by the number of inputs, 2-8x larger): the lookup table of the
-// kernel-map probes then fits in L2.
-__global__ void k_insert_unique(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr,
-                                Slot* tab) {
-  const int n = *n_ptr;
-  const uint32_t mask = table_capacity(n) - 1;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t s = table_insert(tab, mask, keys[i]);
-    tab[s].val = i;
-  }
-}
 
 // ---- block table: 4x4x4-cell blocks of a level's lattice -> 64 voxel rows each -----------------
 // The kernel-map probes of one voxel fall into at most 8 such blocks per time plane, and
@@ -726,37 +714,6 @@ k_conv0_blk(const unsigned long long* __restrict__ keys, const int32_t* __restri
   }
 }
 
-// Kernel map for an odd hyper-cube kernel (k0,k1,k2,k3) on tensor stride [2^log2s]*3 + [1]:
-// nbr[k][o] = row of (out[o] + delta_k) in the same coordinate set, k = i0 + k0*(i1 + k1*(i2 + k2*i3)),
-// delta_d = (i_d - k_d/2) * stride_d.  One independent hash probe per thread, o fastest so the
-// key reads and the table writes are coalesced.
-__global__ void k_kernel_map(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr,
-                             const int32_t* __restrict__ cap_n_ptr, const Slot* __restrict__ tab, int k0, int k1,
-                             int k2, int k3, int log2s, int32_t* __restrict__ nbr, int64_t ld) {
-  const int n = *n_ptr;
-  if (n == 0) return;
-  const uint32_t mask = table_capacity(*cap_n_ptr) - 1;
-  const int K = k0 * k1 * k2 * k3;
-  const int64_t total = (int64_t)K * n;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int k = (int)(idx / n), o = (int)(idx - (int64_t)k * n);
-    int r = k;
-    const int i0 = r % k0; r /= k0;
-    const int i1 = r % k1; r /= k1;
-    const int i2 = r % k2; r /= k2;
-    const int i3 = r;
-    int b, x, y, z, t;
-    unpack_key(keys[o], b, x, y, z, t);
-    x += (i0 - k0 / 2) << log2s;
-    y += (i1 - k1 / 2) << log2s;
-    z += (i2 - k2 / 2) << log2s;
-    t += (i3 - k3 / 2);
-    int res = -1;
-    if (coord_in_range(b, x, y, z, t)) res = table_find(tab, mask, pack_key(b, x, y, z, t));
-    nbr[(int64_t)k * ld + o] = res;
-  }
-}
 
 __global__ void k_unpack(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr,
                          int32_t* __restrict__ out) {
