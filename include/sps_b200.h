@@ -161,6 +161,12 @@ int sps_net_finalize(sps_net* net, void* d_weights, size_t bytes, void* stream);
  * d_scores: fp32 [n].  No host synchronisation. */
 int sps_forward(sps_ctx* ctx, const sps_net* net, const float* d_points, int64_t n,
                 int64_t ld_points, float voxel_size, float* d_scores, void* stream);
+/* As sps_forward with one input feature per point (d_feat fp32 [n]): the voxel feature is the mean of its points'
+ * features (ME.TensorField(features=[N,1]).sparse(), UNWEIGHTED_AVERAGE) -- MapMOSNet.forward,
+ * c_ws/src/mapmos/scripts/mapmos.py:59-83 (index-normalised features, raw logits: sps_net_set_output(net, 0, 0)). */
+int sps_forward_features(sps_ctx* ctx, const sps_net* net, const float* d_points, int64_t n,
+                         int64_t ld_points, const float* d_feat, float voxel_size, float* d_scores,
+                         void* stream);
 /* Same through HOST buffers (pinned or pageable): H2D of the points into the context's staging
  * area, forward, D2H of the scores, stream synchronise, status check. This is the call
  * `util.infer` (src/sps/datasets/util.py:163-184) maps onto. */

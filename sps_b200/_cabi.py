@@ -22,7 +22,7 @@ SYMBOLS = [
     "sps_version", "sps_last_error", "sps_workspace_bytes", "sps_ctx_create", "sps_ctx_destroy", "sps_ctx_status",
     "sps_ctx_level", "sps_ctx_inverse_map", "sps_voxelize", "sps_build_maps", "sps_unpack_coords", "sps_conv_fwd",
     "sps_net_create", "sps_net_destroy", "sps_net_set_tensor", "sps_net_set_output", "sps_net_device_bytes", "sps_net_finalize",
-    "sps_forward", "sps_forward_host", "sps_unet_forward", "sps_devox_sigmoid", "sps_forward_launch_count",
+    "sps_forward", "sps_forward_features", "sps_forward_host", "sps_unet_forward", "sps_devox_sigmoid", "sps_forward_launch_count",
     "sps_map_bytes", "sps_map_build", "sps_map_destroy", "sps_submap_crop_voxel", "sps_submap_crop_radius",
     "sps_assemble", "sps_memcpy_d2h", "sps_memcpy_h2d", "sps_infer_scan", "sps_infer_scan_scratch_bytes", "sps_conv_kmajor_ld", "sps_conv_pack_kmajor", "sps_conv_kmajor_ld_f16", "sps_conv_pack_kmajor_f16", "sps_kernel_map_tile_masks", "sps_set_tma_gather", "sps_set_umma_variant", "sps_set_pattern_sort",
     "sps_set_conv_backend", "sps_profile_enable", "sps_profile_read", "sps_ctx_pair_count",
@@ -72,6 +72,7 @@ def load() -> C.CDLL:
         "sps_last_error": (C.c_char_p, []),
         "sps_workspace_bytes": (sz, [i64]),
         "sps_net_set_output": (i32, [vp, i32, i32]),
+        "sps_forward_features": (i32, [vp, vp, vp, i64, i64, vp, f32, vp, vp]),
         "sps_ctx_create": (i32, [C.POINTER(vp), vp, sz, i64]),
         "sps_ctx_destroy": (i32, [vp]),
         "sps_ctx_status": (i32, [vp, vp]),

@@ -402,8 +402,18 @@ int voxelize_impl(sps_ctx* ctx, const float* d_points, int64_t n, const int32_t*
                   float voxel_size, cudaStream_t st);
 int build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st);
 
+static int forward_feat_impl(sps_ctx* ctx, const sps_net* net, const float* d_points, int64_t n, const int32_t* d_n,
+                             int64_t ld_points, const float* d_feat, float voxel_size, float* d_scores, int64_t n_scores,
+                             cudaStream_t st);
 int forward_impl(sps_ctx* ctx, const sps_net* net, const float* d_points, int64_t n, const int32_t* d_n,
                  int64_t ld_points, float voxel_size, float* d_scores, int64_t n_scores, cudaStream_t st) {
+  return forward_feat_impl(ctx, net, d_points, n, d_n, ld_points, nullptr, voxel_size, d_scores, n_scores, st);
+}
+// d_feat == nullptr: SPSModel.forward (every point carries 0.5); else one input feature per point, averaged per voxel
+// (ME.TensorField(...).sparse(), UNWEIGHTED_AVERAGE): MapMOSNet.forward, c_ws/src/mapmos/scripts/mapmos.py:59-83
+static int forward_feat_impl(sps_ctx* ctx, const sps_net* net, const float* d_points, int64_t n, const int32_t* d_n,
+                             int64_t ld_points, const float* d_feat, float voxel_size, float* d_scores, int64_t n_scores,
+                             cudaStream_t st) {
   if (!ctx || !net || n < 0) return SPS_ERR_BAD_ARG;
   if (!net->finalized) return SPS_ERR_STATE;
   g_forward_launches = 0;
@@ -420,7 +430,13 @@ int forward_impl(sps_ctx* ctx, const sps_net* net, const float* d_points, int64_
   // (src/sps/models/models.py:22-25)
   const bool hm = conv_half_storage();
   float* c0_out = hm ? reinterpret_cast<float*>(reinterpret_cast<__half*>(ctx->buf[sps_ctx::CAT8]) + 8) : ctx->buf[sps_ctx::CAT8] + 8;
-  Conv0Fused c0{nullptr, 0.5f, net->conv0.w, net->conv0.shift, hm ? kStoreF16 : (conv_backend() != 1 ? kStoreTF32 : kStoreF32), c0_out, 16};
+  const float* vfeat = nullptr;
+  if (d_feat) {   // voxel feature = mean of its points' features; the logits buffer is free until the last layer
+    rc = sps_voxel_mean(ctx, d_feat, 1, 1, ctx->buf[sps_ctx::FEAT0], ctx->buf[sps_ctx::LOGITS], st);
+    if (rc != SPS_OK) return rc;
+    vfeat = ctx->buf[sps_ctx::FEAT0];
+  }
+  Conv0Fused c0{vfeat, 0.5f, net->conv0.w, net->conv0.shift, hm ? kStoreF16 : (conv_backend() != 1 ? kStoreTF32 : kStoreF32), c0_out, 16};
   rc = build_maps_impl(ctx, &c0, st);
   if (rc != SPS_OK) return rc;
   rc = unet_forward(ctx, net, ctx->buf[sps_ctx::FEAT0], ctx->buf[sps_ctx::LOGITS], st, /*conv0_done=*/true);
@@ -439,6 +455,12 @@ int forward_impl(sps_ctx* ctx, const sps_net* net, const float* d_points, int64_
 extern "C" int sps_forward(sps_ctx* ctx, const sps_net* net, const float* d_points, int64_t n, int64_t ld_points,
                            float voxel_size, float* d_scores, void* stream) {
   return forward_impl(ctx, net, d_points, n, nullptr, ld_points, voxel_size, d_scores, n, (cudaStream_t)stream);
+}
+
+extern "C" int sps_forward_features(sps_ctx* ctx, const sps_net* net, const float* d_points, int64_t n, int64_t ld_points,
+                                    const float* d_feat, float voxel_size, float* d_scores, void* stream) {
+  if (!d_feat && n > 0) return SPS_ERR_BAD_ARG;
+  return forward_feat_impl(ctx, net, d_points, n, nullptr, ld_points, d_feat, voxel_size, d_scores, n, (cudaStream_t)stream);
 }
 
 extern "C" int sps_forward_launch_count(void) { return g_forward_launches; }

@@ -160,6 +160,24 @@ class Engine:
                                    _ptr(out), _stream()), "sps_forward")
         return out
 
+    def forward_features(self, net: Net, points: torch.Tensor, features: torch.Tensor, voxel_size: float,
+                         out: torch.Tensor | None = None):
+        """As :meth:`forward` with one input feature per point (voxel feature = mean of its points' features):
+        MapMOSNet.forward (c_ws/src/mapmos/scripts/mapmos.py:59-83).  Asynchronous."""
+        _require_cuda(points, "points")
+        _require_cuda(features, "features")
+        assert points.dtype == torch.float32 and points.dim() == 2 and points.stride(1) == 1
+        features = features.reshape(-1).to(torch.float32).contiguous()
+        n = points.shape[0]
+        assert features.numel() == n
+        if out is None:
+            out = torch.empty(n, dtype=torch.float32, device=points.device)
+        self._points, self._features = points, features
+        self.n = n
+        check(self.lib.sps_forward_features(self.handle, net.handle, _ptr(points), n, points.stride(0), _ptr(features),
+                                            float(voxel_size), _ptr(out), _stream()), "sps_forward_features")
+        return out
+
     def forward_host(self, net: Net, points: torch.Tensor, voxel_size: float, out: torch.Tensor | None = None):
         """Same through HOST tensors (H2D + forward + D2H + sync + status check)."""
         assert not points.is_cuda and points.dtype == torch.float32 and points.is_contiguous()

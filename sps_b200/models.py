@@ -277,6 +277,40 @@ class MOS4DNet(SPSModel):
         return super().forward(coordinates)
 
 
+class MapMOSNet(SPSModel):
+    """The MapMOS baseline the reference ships (c_ws/src/mapmos/scripts/mapmos.py:32-90): the same network
+    (``CustomMinkUNet14(1, 1, D=4)``), input features = index-normalised scan/map indices averaged per voxel, t = 0 for
+    the scan and -1 for the map (shifted to 1 / 0 here: only time differences matter), raw logits out."""
+
+    def __init__(self, voxel_size: float, max_points: int = 0):
+        super().__init__(voxel_size, max_points)
+        self.output_channel, self.apply_sigmoid = 0, False
+
+    def forward(self, coordinates: torch.Tensor, indices: torch.Tensor):
+        if self.training:
+            raise RuntimeError("sps_b200 is inference-only (call .eval()); training is out of scope")
+        coordinates = coordinates.reshape(-1, 5).to(torch.float32)
+        if not coordinates.is_cuda:
+            raise RuntimeError("MapMOSNet.forward needs CUDA tensors: sps_b200 has no CPU path")
+        indices = indices.reshape(-1).to(coordinates)
+        i_max, i_min = torch.max(indices), torch.min(indices)                     # mapmos.py:66-71
+        features = torch.ones_like(indices) if bool(i_min == i_max) else 1 + (i_max - indices) / (i_max - i_min)
+        coordinates = coordinates.clone()
+        coordinates[:, 4] -= torch.floor(coordinates[:, 4].min())
+        engine, net = self._prepare(coordinates.shape[0], coordinates.device)
+        return engine.forward_features(net, coordinates, features, self.voxel_size)
+
+    def predict(self, scan_input, map_input, scan_indices, map_indices):          # mapmos.py:39-57
+        def extend(tensor, batch_idx, time_idx):
+            ones = torch.ones(len(tensor), 1).type_as(tensor)
+            return torch.hstack([batch_idx * ones, tensor, time_idx * ones])
+        coordinates = torch.vstack([extend(scan_input, 0, 0).reshape(-1, 5), extend(map_input, 0, -1).reshape(-1, 5)])
+        indices = torch.vstack([scan_indices.reshape(-1, 1), map_indices.reshape(-1, 1)])
+        logits = self.forward(coordinates, indices)
+        mask_scan = coordinates[:, 4] == 0.0
+        return logits[mask_scan], logits[~mask_scan]
+
+
 class SPSNet(nn.Module):
     """Inference surface of the reference's LightningModule (models.py:33-111)."""
 

@@ -67,3 +67,44 @@ def test_window_longer_than_16_scans_is_rejected():
     with pytest.raises(SpsError):
         model(torch.as_tensor(pts).cuda())
         model.check()
+
+
+def test_mapmosnet_matches_oracle():
+    """MapMOSNet (c_ws/src/mapmos/scripts/mapmos.py:32-90): per-point index features averaged per voxel, t = 0 / -1,
+    raw logits -- through sps_forward_features."""
+    from oracle import sps_oracle as O
+    from sps_b200 import synth, _cabi
+    from sps_b200.models import MapMOSNet
+    world = synth.World(5)
+    scan = synth.scan(world, "tiny", pose=(0.2, 0.1, 0.0), seed=3).astype(np.float32)
+    mp = synth.base_map(world, "tiny", n_poses=5, seed=5).astype(np.float32)[:6000]
+    rng = np.random.default_rng(1)
+    scan_idx = np.full(len(scan), 7.0, np.float32)
+    map_idx = rng.integers(0, 7, len(mp)).astype(np.float32)
+    sd = O.make_state_dict(seed=3, randomize_bn=True)
+    model = MapMOSNet(0.1)
+    model.MinkUNet.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()})
+    model = model.cuda().eval()
+    # oracle (mapmos.py:59-83 on the shifted time axis)
+    coords = np.vstack([np.hstack([np.zeros((len(scan), 1), np.float32), scan, np.ones((len(scan), 1), np.float32)]),
+                        np.hstack([np.zeros((len(mp), 1), np.float32), mp, np.zeros((len(mp), 1), np.float32)])])
+    idx = np.concatenate([scan_idx, map_idx])
+    feats = (1 + (idx.max() - idx) / (idx.max() - idx.min())).astype(np.float32)
+    c0, inv = O.voxelize(coords, 0.1)
+    s = np.zeros(len(c0), np.float64); cnt = np.zeros(len(c0), np.float64)
+    np.add.at(s, inv, feats); np.add.at(cnt, inv, 1.0)
+    feat0 = (s / cnt).astype(np.float32)[:, None]
+    ref = O.unet_forward(O.Levels(c0), feat0, sd)[inv, 0]
+    lib = _cabi.load()
+    t = lambda a: torch.as_tensor(a).cuda()
+    for backend, tol in ((1, 2e-4), (0, 2e-2)):
+        lib.sps_set_conv_backend(backend)
+        try:
+            ls, lm = model.predict(t(scan), t(mp), t(scan_idx), t(map_idx))
+            model.check()
+        finally:
+            lib.sps_set_conv_backend(0)
+        got = np.concatenate([ls.cpu().numpy(), lm.cpu().numpy()])
+        scale = max(1.0, np.abs(ref).max())
+        assert np.abs(got - ref).max() < tol * scale, (backend, np.abs(got - ref).max(), scale)
+        assert np.mean((got > 0) == (ref > 0)) >= 0.995

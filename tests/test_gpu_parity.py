@@ -270,3 +270,27 @@ def test_generic_unet_entry_matches_fused_forward(engine_mod, state_dict):
     c0, _ = O.voxelize(pts, 0.1)
     ref = O.unet_forward(O.Levels(c0), f[:, None], state_dict)[:, 0]
     assert np.abs(got - ref).max() < 5e-5
+
+
+@pytest.mark.tensor_path
+def test_scan_streamer_graph_replay_matches_eager_call(engine_mod, state_dict):
+    """ScanStreamer: the per-scan loop of sps_node.py:111-120 (prune -> assemble -> forward) captured once as a CUDA graph.
+    Replays must reproduce the eager `infer_scan` bit for bit, for full-size scans and for shorter (padded) ones."""
+    from sps_b200 import synth, util
+    world = synth.World(4)
+    map_xyz = synth.base_map(world, "tiny", n_poses=8, seed=4)
+    mh = engine_mod.MapHash(torch.as_tensor(np.ascontiguousarray(map_xyz, np.float32)).cuda(), 0.1)
+    scans = [synth.scan(world, "tiny", pose=(0.3 * i, -0.2 * i, 0.1 * i), seed=20 + i).astype(np.float32) for i in range(4)]
+    n_scan = len(scans[0])
+    net = engine_mod.Net(state_dict)
+    streamer = engine_mod.ScanStreamer(mh, engine_mod.Engine(2 * n_scan), net, n_scan, 0.1)
+    eager_engine = engine_mod.Engine(2 * n_scan)
+    for i, s in enumerate(scans):
+        pts = s if i % 2 == 0 else s[: n_scan - 37 * i]            # every other scan is shorter than the captured size
+        d = torch.as_tensor(np.ascontiguousarray(pts)).cuda()
+        got = streamer.infer(d).clone()
+        ref, _ = mh.infer_scan(eager_engine, net, d, 0.1)
+        eager_engine.status()
+        torch.cuda.synchronize()
+        assert got.shape == ref.shape == (len(pts),)
+        assert torch.equal(got, ref), (i, float((got - ref).abs().max()))
