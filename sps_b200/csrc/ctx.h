@@ -2,6 +2,11 @@
 #pragma once
 #include "common.cuh"
 
+// 8-bit radix passes of the shape sort: 4 = full 29-bit key; 3 = 20-bit key without the centre and corner offsets
+#ifndef SPS_SORT_PASSES
+#define SPS_SORT_PASSES 4
+#endif
+
 struct sps_ctx {
   int64_t max_points = 0;
   int64_t ld = 0;            // leading dimension of the [K][ld] map tables (multiple of 32)

@@ -436,7 +436,18 @@ __global__ void k_pattern_keys(const uint32_t* __restrict__ vmask, int64_t ld, c
   const int n = *n_ptr;
   for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += gridDim.x * blockDim.x) {
     const uint32_t m0 = vmask[o], m1 = vmask[ld + o], m2 = vmask[2 * ld + o];
-    keys[o] = (m0 | m1 | m2) | ((m0 ? 1u : 0u) << 27) | ((m2 ? 1u : 0u) << 28);
+    const uint32_t pat = m0 | m1 | m2;
+#if SPS_SORT_PASSES == 3
+    // 20-bit key, three 8-bit passes: the centre (always present) and the 8 corner offsets (rarest on surfaces) are left
+    // out of the key; rows that differ only there share a bucket
+    constexpr int kept[18] = {1, 3, 4, 5, 7, 9, 10, 11, 12, 14, 15, 16, 17, 19, 21, 22, 23, 25};
+    uint32_t key = 0;
+#pragma unroll
+    for (int j = 0; j < 18; ++j) key |= ((pat >> kept[j]) & 1u) << j;
+    keys[o] = key | ((m0 ? 1u : 0u) << 18) | ((m2 ? 1u : 0u) << 19);
+#else
+    keys[o] = pat | ((m0 ? 1u : 0u) << 27) | ((m2 ? 1u : 0u) << 28);
+#endif
     vals[o] = o;
   }
 }
@@ -803,10 +814,11 @@ static int pattern_order(sps_ctx* ctx, int L, cudaStream_t st) {
   const int32_t* cnt = ctx->counts + L;
   uint32_t* ka = ctx->sort_keys[0];
   uint32_t* kb = ctx->sort_keys[1];
-  int32_t* va = ctx->perm[L];          // 4 passes: a->b->a->b->a, so the result lands in perm[L]
-  int32_t* vb = ctx->sort_vals;
+  // the values ping-pong between two buffers; start so that the LAST pass writes perm[L]
+  int32_t* va = (SPS_SORT_PASSES % 2 == 0) ? ctx->perm[L] : ctx->sort_vals;
+  int32_t* vb = (SPS_SORT_PASSES % 2 == 0) ? ctx->sort_vals : ctx->perm[L];
   k_pattern_keys<<<grid_for(n, 256), 256, 0, st>>>(ctx->vmask, ctx->ld, cnt, ka, va);
-  for (int pass = 0; pass < 4; ++pass) {
+  for (int pass = 0; pass < SPS_SORT_PASSES; ++pass) {
     k_radix_hist<<<nb_max, kSortBlock, 0, st>>>(ka, cnt, 8 * pass, ctx->sort_hist);
     k_scan_hist<<<cdiv(hist_n, kScanBlock), kScanBlock, 0, st>>>(ctx->sort_hist, cnt, ctx->sort_hrank, ctx->sort_hsums,
                                                                    ctx->ticket, ctx->counts + 160);
