@@ -461,3 +461,55 @@ def predict_step_metrics(scores, labels, t_col, eps):
                                                          threshold_labels(s32, np.float32(eps)))
     return {"loss": mse, "r2": r2, "precision": precision, "recall": recall, "f1": f1,
             "accuracy": acc, "dIoU": diou}
+
+
+# --------------------------------------------------------------------------------------
+# "next" rows: offline-loader submap selection, 4DMOS and MapMOS forwards
+# --------------------------------------------------------------------------------------
+def select_closest_points(map_xyz, scan_xyz, radius):
+    """BLTDataset.select_closest_points (src/sps/datasets/blt_dataset.py:258-271): for every scan point, in scan
+    order, the indices of all map points within ``radius`` (Euclidean, float64), as one list per scan point.
+    Brute force over a uniform grid in float64 -- an independent restatement, checked against the reference's own
+    call (scipy ``cKDTree.query_ball_tree``) in tests/test_oracle.py."""
+    m = np.asarray(map_xyz, np.float64)[:, :3]
+    s = np.asarray(scan_xyz, np.float64)[:, :3]
+    r = float(radius)
+    cells = {}
+    for i, c in enumerate(map(tuple, np.floor(m / r).astype(np.int64))):
+        cells.setdefault(c, []).append(i)
+    out = []
+    for p, c in zip(s, np.floor(s / r).astype(np.int64)):
+        hits = []
+        for dx in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                for dz in (-1, 0, 1):
+                    for j in cells.get((c[0] + dx, c[1] + dy, c[2] + dz), ()):
+                        d = m[j] - p
+                        if d[0] * d[0] + d[1] * d[1] + d[2] * d[2] <= r * r:
+                            hits.append(j)
+        out.append(sorted(hits))
+    return out
+
+
+def mos4d_forward(points, voxel_size, sd, dtype=np.float32):
+    """MOS4DNet.forward (c_ws/src/mos4d/scripts/mos4d.py:17-32): the SPS graph with ``out_channels = 3``, features 0.5,
+    returns the raw logit of channel 2 per point.  ``points`` [N,5] = (b, x, y, z, t = scan index)."""
+    c0, inv = voxelize(points, voxel_size)
+    logits = unet_forward(Levels(c0), np.full((len(c0), 1), 0.5, dtype=dtype), sd, dtype)
+    return logits[inv, 2].astype(dtype)
+
+
+def mapmos_forward(coordinates, indices, voxel_size, sd, dtype=np.float32):
+    """MapMOSNet.forward (c_ws/src/mapmos/scripts/mapmos.py:59-83): index-normalised point features
+    ``1 + (i_max - i) / (i_max - i_min)`` (ones when all equal), ``TensorField.sparse()`` averages them per voxel
+    (UNWEIGHTED_AVERAGE), raw logits out.  ``coordinates`` [N,5] = (b, x, y, z, t)."""
+    idx = np.asarray(indices, np.float32).reshape(-1)
+    i_max, i_min = idx.max(), idx.min()
+    feats = np.ones_like(idx) if i_max == i_min else (1 + (i_max - idx) / (i_max - i_min)).astype(np.float32)
+    c0, inv = voxelize(coordinates, voxel_size)
+    s = np.zeros(len(c0), np.float64)
+    cnt = np.zeros(len(c0), np.float64)
+    np.add.at(s, inv, feats)
+    np.add.at(cnt, inv, 1.0)
+    feat0 = (s / cnt).astype(dtype)[:, None]
+    return unet_forward(Levels(c0), feat0, sd, dtype)[inv, 0].astype(dtype)

@@ -40,11 +40,9 @@ def test_mos4dnet_matches_oracle(n_scans, t0):
     # oracle: the reference's graph on the window shifted to t = 0 (translation in t leaves ME's maps unchanged)
     shifted = pts.copy()
     shifted[:, 4] -= t0
-    c0, inv = O.voxelize(shifted, 0.1)
-    levels = O.Levels(c0)
+    c0, _ = O.voxelize(shifted, 0.1)
     assert len(np.unique(c0[:, 4])) == n_scans                       # a true 4-D input: one time plane per scan
-    logits = O.unet_forward(levels, np.full((len(c0), 1), 0.5, np.float32), sd)
-    ref = logits[inv, 2]                                             # mos4d.py:32  out.features[:, 2]
+    ref = O.mos4d_forward(shifted, 0.1, sd)                          # mos4d.py:32  out.features[:, 2]
     lib = _cabi.load()
     for backend, tol in ((1, 2e-4), (0, 2e-2)):
         lib.sps_set_conv_backend(backend)
@@ -88,13 +86,7 @@ def test_mapmosnet_matches_oracle():
     # oracle (mapmos.py:59-83 on the shifted time axis)
     coords = np.vstack([np.hstack([np.zeros((len(scan), 1), np.float32), scan, np.ones((len(scan), 1), np.float32)]),
                         np.hstack([np.zeros((len(mp), 1), np.float32), mp, np.zeros((len(mp), 1), np.float32)])])
-    idx = np.concatenate([scan_idx, map_idx])
-    feats = (1 + (idx.max() - idx) / (idx.max() - idx.min())).astype(np.float32)
-    c0, inv = O.voxelize(coords, 0.1)
-    s = np.zeros(len(c0), np.float64); cnt = np.zeros(len(c0), np.float64)
-    np.add.at(s, inv, feats); np.add.at(cnt, inv, 1.0)
-    feat0 = (s / cnt).astype(np.float32)[:, None]
-    ref = O.unet_forward(O.Levels(c0), feat0, sd)[inv, 0]
+    ref = O.mapmos_forward(coords, np.concatenate([scan_idx, map_idx]), 0.1, sd)
     lib = _cabi.load()
     t = lambda a: torch.as_tensor(a).cuda()
     for backend, tol in ((1, 2e-4), (0, 2e-2)):
