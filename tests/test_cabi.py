@@ -130,6 +130,27 @@ def test_no_cpu_fallback():
         Engine(100, device="cpu")
 
 
+def test_next_row_mirrors_refuse_cpu_and_keep_the_reference_layout():
+    """RadiusSubmap / MOS4DNet / MapMOSNet: same rules as the hot path -- no CPU fallback; state_dict keys and shapes of
+    the baselines the reference ships (mos4d.py:15 CustomMinkUNet(1, 3, D=4); mapmos.py:37 CustomMinkUNet14(1, 1, D=4))."""
+    from sps_b200.datasets import RadiusSubmap
+    from sps_b200.models import MOS4DNet, MapMOSNet, SPSModel
+    with pytest.raises(RuntimeError):
+        RadiusSubmap(torch.zeros(10, 3), 0.1)
+    mos, mapmos, sps = MOS4DNet(0.1).eval(), MapMOSNet(0.1).eval(), SPSModel(0.1)
+    assert tuple(mos.MinkUNet.state_dict()["final.kernel"].shape) == (8, 3)
+    assert tuple(mos.MinkUNet.state_dict()["final.bias"].shape) == (1, 3)
+    assert (mos.output_channel, mos.apply_sigmoid) == (2, False)
+    assert (mapmos.output_channel, mapmos.apply_sigmoid) == (0, False)
+    assert (sps.output_channel, sps.apply_sigmoid) == (0, True)
+    keys = lambda m: {k: tuple(v.shape) for k, v in m.MinkUNet.state_dict().items() if not k.startswith("final")}
+    assert keys(mos) == keys(sps) == keys(mapmos)
+    with pytest.raises(RuntimeError):
+        mos(torch.zeros(4, 5))
+    with pytest.raises(RuntimeError):
+        mapmos(torch.zeros(4, 5), torch.zeros(4))
+
+
 def test_product_never_imports_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "sps_b200")):
         for f in files:
