@@ -225,20 +225,36 @@ __global__ void k_assign_coarse(Slot* tab, const uint32_t* __restrict__ slot_of,
 // The kernel-map probes of one voxel fall into at most 8 such blocks per time plane, and
 // neighbouring voxels share them, so a probe costs a (mostly L1/L2-resident) 4-byte read inside a
 // 256-byte block instead of one random 32-byte sector of a per-voxel hash table.
-__global__ void k_block_insert(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr,
-                               int log2b, Slot* tab, uint32_t* __restrict__ bslot, int32_t* nblocks) {
+__global__ void __launch_bounds__(256)
+k_block_insert(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr,
+               int log2b, Slot* tab, uint32_t* __restrict__ bslot, int32_t* nblocks) {
+  // Block ids come from ONE global counter.  ncu's source view put 75 % of this kernel's stall samples on the result of
+  // that same-address atomicAdd (the compiler's warp aggregation still leaves ~10^5 of them at level 0), so the winners
+  // of a whole CTA are ranked in shared memory first and one thread takes the CTA's id range with a single global atomic.
+  __shared__ int s_cnt, s_base;
   const int n = *n_ptr;
   const uint32_t mask = table_capacity(n) - 1;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const unsigned long long bkey = coarsen_key(keys[i], log2b);
-    uint32_t s = hash_key(bkey) & mask;
-    while (true) {
-      const unsigned long long prev = atomicCAS(&tab[s].key, kEmptyKey, bkey);
-      if (prev == kEmptyKey) { tab[s].val = atomicAdd(nblocks, 1); break; }
-      if (prev == bkey) break;
-      s = (s + 1) & mask;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {   // CTA-uniform trip count
+    const int i = base + threadIdx.x;
+    uint32_t s = 0;
+    int local = -1;
+    if (i < n) {
+      const unsigned long long bkey = coarsen_key(keys[i], log2b);
+      s = hash_key(bkey) & mask;
+      while (true) {
+        const unsigned long long prev = atomicCAS(&tab[s].key, kEmptyKey, bkey);
+        if (prev == kEmptyKey) { local = atomicAdd(&s_cnt, 1); break; }
+        if (prev == bkey) break;
+        s = (s + 1) & mask;
+      }
+      bslot[i] = s;
     }
-    bslot[i] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { s_base = s_cnt ? atomicAdd(nblocks, s_cnt) : 0; s_cnt = 0; }
+    __syncthreads();
+    if (local >= 0) tab[s].val = s_base + local;
   }
 }
 
