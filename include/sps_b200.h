@@ -67,6 +67,10 @@ typedef struct sps_level_view {
   const int32_t* child;     /* [8][ld] child table of the level BELOW (NULL at level 0)     */
   int64_t ld;               /* leading dimension (in voxels) of nbr3/nbr5/child             */
 } sps_level_view;
+/* Valid after sps_voxelize (+ sps_build_maps for the maps).  After a FUSED forward (sps_forward*, sps_infer_scan) on
+ * an input large enough for the shape sort (>= 400 000 rows), nbr3 of levels 0-3 holds only its PRESENT entries (absent
+ * ones are not rewritten to -1: every reader inside the library goes through the presence words); call sps_build_maps
+ * to get the complete tables back.  sps_ctx_pair_count returns SPS_ERR_STATE in that state. */
 int sps_ctx_level(sps_ctx* ctx, int level, sps_level_view* out);
 const int32_t* sps_ctx_inverse_map(sps_ctx* ctx);   /* [n] point -> level-0 voxel row        */
 

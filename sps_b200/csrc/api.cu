@@ -250,6 +250,7 @@ __global__ void k_count_nonneg(const int32_t* __restrict__ map, int64_t ld, int 
 extern "C" int sps_ctx_pair_count(sps_ctx* ctx, int level, int kind, int64_t* h_out, void* stream) {
   if (!ctx || !h_out || level < 0 || level >= SPS_NUM_LEVELS) return SPS_ERR_BAD_ARG;
   if (!ctx->have_maps || (kind == 5 && !ctx->have_nbr5)) return SPS_ERR_STATE;
+  if (kind == 3 && !ctx->dense_maps) return SPS_ERR_STATE;   // the fused forward left sparse tables: call sps_build_maps
   const int32_t* map = kind == 3 ? ctx->nbr3[level] : kind == 5 ? (level == 0 ? ctx->nbr5 : nullptr)
                                                     : kind == 8 ? ctx->child[level] : nullptr;
   const int K = kind == 3 ? 81 : kind == 5 ? 125 : 8;

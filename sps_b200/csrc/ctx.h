@@ -12,6 +12,7 @@ struct sps_ctx {
   int64_t ld = 0;            // leading dimension of the [K][ld] map tables (multiple of 32)
   int64_t n = 0;             // rows of the last voxelize call
   bool have_l0 = false, have_maps = false, have_nbr5 = false, have_perm = false, have_slices = false;
+  bool dense_maps = true;    // false after a fused forward that stored only the present entries of the sorted levels' tables
   int first_sorted = 0, last_sorted = -1;   // levels whose 3^4 convs may visit rows in pattern-sorted order
 
   char* base = nullptr;

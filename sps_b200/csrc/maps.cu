@@ -935,6 +935,7 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
   }
   SPS_CUDA_CHECK(cudaGetLastError());
   ctx->have_maps = true;
+  ctx->dense_maps = !(sparse_ok(0) || sparse_ok(1) || sparse_ok(2) || sparse_ok(3));
   ctx->have_perm = g_pattern_sort == 2 || (g_pattern_sort == 1 && ctx->n >= kMinRowsForSort);
   ctx->have_slices = ctx->have_perm && g_tile_slices && kLastSortedLevel <= 3;
   ctx->first_sorted = kFirstSortedLevel;
