@@ -151,6 +151,45 @@ def test_next_row_mirrors_refuse_cpu_and_keep_the_reference_layout():
         mapmos(torch.zeros(4, 5), torch.zeros(4))
 
 
+def test_kmajor_weight_packers_host_side():
+    """sps_conv_pack_kmajor / _f16 are host functions: K-major rows [cout][ld], per kernel offset a group-padded channel
+    run (4 fp32 / 8 fp16 channels per 16-byte group; 1, 2, 4 or 8k groups), then the fused 1x1 term padded to a stage."""
+    from sps_b200 import _cabi
+    lib = _cabi.load()
+    rng = np.random.default_rng(0)
+    for K, cin, cout, cin2 in [(81, 8, 8, 0), (81, 16, 8, 16), (81, 24, 16, 24), (81, 48, 32, 48), (81, 96, 64, 96), (8, 8, 8, 0),
+                               (8, 64, 32, 0)]:
+        w = rng.standard_normal((K, cin, cout)).astype(np.float32)
+        w2 = rng.standard_normal((cin2, cout)).astype(np.float32) if cin2 else None
+        p2 = w2.ctypes.data_as(C.c_void_p) if cin2 else None
+        # fp16
+        g = (cin + 7) // 8
+        gp = 1 if g <= 1 else 2 if g <= 2 else 4 if g <= 4 else (g + 7) // 8 * 8
+        ld = lib.sps_conv_kmajor_ld_f16(K, cin, cin2)
+        assert ld == K * gp * 8 + (cin2 + 63) // 64 * 64 and ld % 8 == 0
+        out = np.full((cout, ld), 7, np.float16)
+        assert lib.sps_conv_pack_kmajor_f16(w.ctypes.data_as(C.c_void_p), K, cin, cout, p2, cin2, out.ctypes.data_as(C.c_void_p)) == 0
+        blk = out[:, : K * gp * 8].reshape(cout, K, gp * 8)
+        assert np.array_equal(blk[:, :, :cin], w.astype(np.float16).transpose(2, 0, 1))
+        assert not blk[:, :, cin:].any()
+        tail = out[:, K * gp * 8:]
+        if cin2:
+            assert np.array_equal(tail[:, :cin2], w2.astype(np.float16).T) and not tail[:, cin2:].any()
+        # fp32 / TF32 (round to nearest even on 13 dropped bits)
+        g4 = (cin + 3) // 4
+        gp4 = 2 if g4 <= 2 else 4 if g4 <= 4 else (g4 + 7) // 8 * 8
+        ld4 = lib.sps_conv_kmajor_ld(K, cin, cin2)
+        assert ld4 == K * gp4 * 4 + (cin2 + 31) // 32 * 32
+        out4 = np.full((cout, ld4), 7, np.float32)
+        assert lib.sps_conv_pack_kmajor(w.ctypes.data_as(C.c_void_p), K, cin, cout, p2, cin2, out4.ctypes.data_as(C.c_void_p)) == 0
+        blk4 = out4[:, : K * gp4 * 4].reshape(cout, K, gp4 * 4)
+        ref = w.transpose(2, 0, 1)
+        assert (blk4[:, :, :cin].view(np.uint32) & 0x1FFF == 0).all()                  # TF32: low 13 mantissa bits cleared
+        assert np.abs(blk4[:, :, :cin] - ref).max() <= np.abs(ref).max() * 2.0 ** -11
+        assert not blk4[:, :, cin:].any()
+    assert lib.sps_conv_pack_kmajor_f16(None, 81, 8, 8, None, 0, None) == _cabi.SPS_ERR_BAD_ARG
+
+
 def test_product_never_imports_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "sps_b200")):
         for f in files:
