@@ -64,7 +64,53 @@ def build_case(name):
     return out
 
 
+# ---- "next" rows: radius submap selection, 4DMOS window, MapMOS scan + map pair ----
+def next_rows_inputs():
+    """Seeded inputs shared by the generator and the tests."""
+    from sps_b200 import synth
+    world = synth.World(11)
+    base = synth.base_map(world, "tiny", n_poses=6, seed=11, voxel=0.1).astype(np.float32)
+    scans = [synth.scan(world, "tiny", pose=(0.3 * i, -0.25 * i, 0.07 * i), seed=40 + i).astype(np.float32) for i in range(4)]
+    window = np.vstack([np.hstack([np.zeros((len(s), 1), np.float32), s, np.full((len(s), 1), 200 + i, np.float32)])
+                        for i, s in enumerate(scans)])                               # mos4d_node.py:98-117
+    rng = np.random.default_rng(11)
+    map_idx = rng.integers(0, 6, len(base)).astype(np.float32)
+    return base, scans, window, map_idx
+
+
+def next_rows_state_dicts():
+    from oracle import sps_oracle as O
+    sd = O.make_state_dict(seed=5, randomize_bn=True)
+    sd3 = dict(sd)
+    rng = np.random.default_rng(6)
+    sd3["final.kernel"] = (rng.standard_normal((8, 3)) * np.sqrt(2.0 / 3)).astype(np.float32)
+    sd3["final.bias"] = rng.uniform(-0.3, 0.3, (1, 3)).astype(np.float32)
+    return sd, sd3
+
+
+def build_next_rows():
+    """Ball-query lists come from the call the REFERENCE makes (scipy cKDTree.query_ball_tree, blt_dataset.py:258-262);
+    the 4DMOS / MapMOS logits from the oracle's restatements (mos4d.py:17-32, mapmos.py:59-83)."""
+    from scipy.spatial import cKDTree
+    from oracle import sps_oracle as O
+    base, scans, window, map_idx = next_rows_inputs()
+    sd, sd3 = next_rows_state_dicts()
+    lists = cKDTree(scans[0].astype(np.float64)).query_ball_tree(cKDTree(base.astype(np.float64)), 0.1)
+    counts = np.array([len(l) for l in lists], np.int32)
+    flat = np.concatenate([np.sort(np.asarray(l, np.int64)) for l in lists]) if counts.sum() else np.zeros(0, np.int64)
+    shifted = window.copy()
+    shifted[:, 4] -= 200
+    coords = np.vstack([np.hstack([np.zeros((len(scans[0]), 1), np.float32), scans[0], np.ones((len(scans[0]), 1), np.float32)]),
+                        np.hstack([np.zeros((len(base), 1), np.float32), base, np.zeros((len(base), 1), np.float32)])])
+    idx = np.concatenate([np.full(len(scans[0]), 6.0, np.float32), map_idx])
+    return {"inputs_digest": digest(np.concatenate([base.ravel(), window.ravel(), map_idx])),
+            "ball_counts": counts, "ball_sorted_digest": digest(flat), "ball_total": np.array([len(flat)]),
+            "mos4d_logits": O.mos4d_forward(shifted, 0.1, sd3).astype(np.float32),
+            "mapmos_logits": O.mapmos_forward(coords, idx, 0.1, sd).astype(np.float32)}
+
+
 def main():
+    np.savez_compressed(os.path.join(HERE, "next_rows_s11.npz"), **build_next_rows())
     index = {}
     for name in CASES:
         data = build_case(name)

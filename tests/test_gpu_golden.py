@@ -66,3 +66,41 @@ def test_device_metric_partials_match_reference_formulas():
     assert abs(got["Precision"] - m["precision"]) < 1e-12 and abs(got["Recall"] - m["recall"]) < 1e-12
     assert abs(got["F1"] - m["f1"]) < 1e-12 and abs(got["dIoU"] - m["dIoU"]) < 1e-12
     assert int(c.sum()) == int((rows[:, 4] == 1).sum())
+
+
+def test_next_rows_reproduce_golden():
+    """Radius submap selection against lists produced by the reference's own call (scipy), MOS4DNet / MapMOSNet against
+    the oracle's logits (tests/golden/next_rows_s11.npz)."""
+    from golden.make_golden import next_rows_inputs, next_rows_state_dicts
+    from sps_b200 import _cabi
+    from sps_b200.datasets import RadiusSubmap
+    from sps_b200.models import MOS4DNet, MapMOSNet
+    g = np.load(os.path.join(GOLDEN, "next_rows_s11.npz"))
+    base, scans, window, map_idx = next_rows_inputs()
+    assert np.array_equal(digest(np.concatenate([base.ravel(), window.ravel(), map_idx])), g["inputs_digest"]), "generator drifted"
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a)).cuda()
+    idx, off = RadiusSubmap(t(base), 0.1).select_closest_points(t(scans[0]), return_offsets=True)
+    idx, off = idx.cpu().numpy(), off.cpu().numpy()
+    assert np.array_equal(np.diff(off).astype(np.int32), g["ball_counts"]) and len(idx) == int(g["ball_total"][0])
+    flat = np.concatenate([np.sort(idx[off[i]:off[i + 1]]) for i in range(len(scans[0]))]).astype(np.int64)
+    assert np.array_equal(digest(flat), g["ball_sorted_digest"])
+    sd, sd3 = next_rows_state_dicts()
+    lib = _cabi.load()
+    mos = MOS4DNet(0.1)
+    mos.MinkUNet.load_state_dict({k: torch.as_tensor(v) for k, v in sd3.items()})
+    mos = mos.cuda().eval()
+    mm = MapMOSNet(0.1)
+    mm.MinkUNet.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()})
+    mm = mm.cuda().eval()
+    for backend, tol in ((1, 2e-4), (0, 2e-2)):
+        lib.sps_set_conv_backend(backend)
+        try:
+            a = mos(t(window)).cpu().numpy()
+            ls, lm = mm.predict(t(scans[0]), t(base), t(np.full(len(scans[0]), 6.0, np.float32)), t(map_idx))
+            b = np.concatenate([ls.cpu().numpy(), lm.cpu().numpy()])
+            mos.check(); mm.check()
+        finally:
+            lib.sps_set_conv_backend(0)
+        for got, ref in ((a, g["mos4d_logits"]), (b, g["mapmos_logits"])):
+            assert got.shape == ref.shape
+            assert np.abs(got - ref).max() < tol * max(1.0, np.abs(ref).max()), (backend, np.abs(got - ref).max())
