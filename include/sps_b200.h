@@ -14,7 +14,10 @@
  *     synchronisation happens unless stated (the *_host and *_status calls);
  *   - sizes that are only known on the device (voxel counts) stay on the device; the
  *     `sps_level_view` exposes their addresses;
- *   - one sps_ctx per stream (re-entrant across distinct contexts, no global state).
+ *   - one sps_ctx per stream.  The library keeps NO process-wide mutable state: arithmetic mode, processing-order
+ *     mode, launch counters and stage timers live in the sps_ctx, a sps_net is read-only after sps_net_finalize,
+ *     sps_last_error is thread-local.  Distinct host threads may drive distinct contexts concurrently (also on
+ *     distinct devices); one context must not be used from two threads at once.
  */
 #ifndef SPS_B200_H
 #define SPS_B200_H
@@ -68,9 +71,10 @@ typedef struct sps_level_view {
   int64_t ld;               /* leading dimension (in voxels) of nbr3/nbr5/child             */
 } sps_level_view;
 /* Valid after sps_voxelize (+ sps_build_maps for the maps).  After a FUSED forward (sps_forward*, sps_infer_scan) on
- * an input large enough for the shape sort (>= 400 000 rows), nbr3 of levels 0-3 holds only its PRESENT entries (absent
- * ones are not rewritten to -1: every reader inside the library goes through the presence words); call sps_build_maps
- * to get the complete tables back.  sps_ctx_pair_count returns SPS_ERR_STATE in that state. */
+ * an input large enough for the shape sort (>= 400 000 rows), the 3x3x3x3 tables of levels 0-3 hold only their PRESENT
+ * entries (absent ones are not rewritten to -1: every reader inside the library goes through the presence words):
+ * the view then carries nbr3 == NULL for every level and sps_ctx_pair_count returns SPS_ERR_STATE; call
+ * sps_build_maps to get the complete tables back. */
 int sps_ctx_level(sps_ctx* ctx, int level, sps_level_view* out);
 const int32_t* sps_ctx_inverse_map(sps_ctx* ctx);   /* [n] point -> level-0 voxel row        */
 
@@ -92,8 +96,14 @@ int sps_unpack_coords(sps_ctx* ctx, int level, int32_t* d_out, void* stream);
 #define SPS_CONV_UP 1     /* transposed 2x2x2x1: out[child[k][c]] = in[c] @ W[k] for coarse rows c */
 
 #define SPS_TILE_SLICE_ENTRIES 82
+/* sps_conv_args.io_dtype: bit 0 = `in` rows are fp16, bit 1 = `in2` / `res` rows are fp16, bit 2 = `out` rows are fp16
+ * (leading dimensions then count halves).  The tensor-core kernel takes all-fp32 (0) or all-fp16 (7) rows; the
+ * 8-output-channel CUDA-core kernel takes any combination. */
 #define SPS_IO_F32 0
-#define SPS_IO_F16 1
+#define SPS_IO_IN_F16 1
+#define SPS_IO_IN2_F16 2
+#define SPS_IO_OUT_F16 4
+#define SPS_IO_F16 7
 typedef struct sps_conv_args {
   int mode;                 /* SPS_CONV_NBR | SPS_CONV_UP                                    */
   int K;                    /* kernel volume (125, 81, 8, 1)                                 */
@@ -134,13 +144,14 @@ typedef struct sps_conv_args {
   int io_dtype;             /* SPS_IO_F32 (0): `in`, `in2`, `res`, `out` are fp32 rows.  SPS_IO_F16: they point
                                at fp16 rows (leading dimensions in halves, multiples of 8) and weight_kmajor is
                                the sps_conv_pack_kmajor_f16 matrix: the fused forward's storage format
-                               (same 10-bit mantissa as the TF32 operands, half the bytes per gathered row;
-                               tensor-core path only)                                          */
+                               (same 10-bit mantissa as the TF32 operands, half the bytes per gathered row)   */
+  int backend;              /* SPS_BACKEND_*: which kernel family serves this call (AUTO: tensor cores where
+                               the layer shape and the optional inputs allow, CUDA cores otherwise)          */
 } sps_conv_args;
 /* MinkowskiConvolution / MinkowskiConvolutionTranspose (+ folded MinkowskiBatchNorm, ReLU,
  * residual) forward: minkunet.py:55-158, resnet.py:97-108, ME BasicBlock.  Served by the tcgen05
- * implicit-GEMM kernel (TF32 operands, fp32 accumulate) or the fp32 CUDA-core kernel, see
- * sps_set_conv_backend. */
+ * implicit-GEMM kernel (TF32 / fp16 operands, fp32 accumulate) or the fp32 CUDA-core kernels, see
+ * sps_conv_args.backend. */
 int sps_conv_fwd(const sps_conv_args* args, void* stream);
 
 /* ---------------------------------------------------------------- network ---------------- */
@@ -183,8 +194,8 @@ int sps_unet_forward(sps_ctx* ctx, const sps_net* net, const float* d_feat0, flo
 /* SparseTensor.slice + sigmoid (models.py:28-29): scores[p] = sigmoid(logits[inv[p]]). */
 int sps_devox_sigmoid(const float* d_logits, const int32_t* d_inv, int64_t n, float* d_scores,
                       void* stream);
-/* Number of kernels one sps_forward enqueues (for bench.py's gpu_launches claim). */
-int sps_forward_launch_count(void);
+/* Number of kernels the last fused forward of this context enqueued (bench.py's gpu_launches claim). */
+int sps_ctx_launch_count(const sps_ctx* ctx);
 
 /* ---------------------------------------------------------------- submap selection ------- */
 typedef struct sps_map sps_map;  /* replicated base-map voxel hash, built once per process  */
@@ -244,30 +255,29 @@ int sps_submap_ball_query(const sps_ballmap* bm, const float* d_scan_xyz, int64_
                           int32_t* d_offsets, int32_t* d_out_idx, int64_t out_capacity, int32_t* d_total,
                           void* d_scratch, size_t scratch_bytes, void* stream);
 
-/* ---------------------------------------------------------------- tensor-core path ------- */
-/* Which kernel serves sps_conv_fwd / the fused forward: 0 = auto (tcgen05 implicit GEMM where
- * the layer shape allows, fp32 CUDA-core otherwise; the fused forward keeps its activations as
- * fp16 rows -- operands with the 10-bit mantissa of TF32 at half the gathered bytes, fp32
- * accumulation and epilogue), 1 = fp32 CUDA-core only (exact fp32), 2 = as 0 but fp32 rows with
- * TF32 operands everywhere (the round-1 default), 3 = as 0 (fp16 storage regardless of build flags). */
-int sps_set_conv_backend(int backend);
-/* 1: wide layers (Cin >= 24) gather through TMA `tile::gather4` (conv_umma_tma.cu); default 0 =
- * the cp.async producer kernel everywhere.  The TMA variant is parity-clean but measured ~3x
- * slower (128-byte boxes are too small for the TMA engine), kept for A/B measurements. */
+/* ---------------------------------------------------------------- arithmetic / processing order ---- */
+/* Which kernels serve the fused forward of a context (and, through sps_conv_args.backend, one sps_conv_fwd call):
+ *   SPS_BACKEND_AUTO (0)  tcgen05 implicit GEMM on fp16 rows (fp16 operands, fp32 accumulate and epilogue) for the
+ *                         layers with >= 16 output channels; fp32 CUDA-core FMA kernels with fp32 weights for the
+ *                         8-output-channel layers; the level-0 tail of the network (conv0 output, convtr7p2s2,
+ *                         block8) keeps fp32 rows, which is what holds the 2e-3 score bar on spread-out scores;
+ *   SPS_BACKEND_FP32 (1)  fp32 CUDA-core kernels everywhere (exact fp32);
+ *   SPS_BACKEND_TF32 (2)  as AUTO but fp32 rows everywhere, TF32 operands in the tensor-core layers;
+ *   SPS_BACKEND_F16  (3)  = AUTO regardless of build flags. */
+#define SPS_BACKEND_AUTO 0
+#define SPS_BACKEND_FP32 1
+#define SPS_BACKEND_TF32 2
+#define SPS_BACKEND_F16 3
+int sps_ctx_set_conv_backend(sps_ctx* ctx, int backend);
+/* The fused forward can visit the rows of the 3x3x3x3 convolutions (levels 0-3) in an order sorted by
+ * neighbourhood shape: fewer kernel offsets per 128-row tile.  mode 0: never (physical row order); 1 (default): for
+ * inputs of >= 400 000 rows (smaller ones are launch-bound); 2: always.  Results do not depend on it beyond the last
+ * bit of a stored fp16 activation. */
+int sps_ctx_set_pattern_sort(sps_ctx* ctx, int mode);
 /* fp16 twins of sps_conv_kmajor_ld / sps_conv_pack_kmajor below (out: __half [cout][ld]; per offset 1, 2, 4 or
  * 8k groups of 8 channels). */
 int64_t sps_conv_kmajor_ld_f16(int K, int cin, int cin2);
 int sps_conv_pack_kmajor_f16(const float* w, int K, int cin, int cout, const float* w2, int cin2, void* out);
-int sps_set_tma_gather(int on);
-/* Generation of the tensor-core convolution kernel: 6 (default) = k_conv_umma6 (loader warp stages
- * the kernel-map slices, producers walk the stage ring with compile-time slots); 5 = k_conv_umma
- * (the round-1 baseline kept for A/B measurements).  Same results bit for bit. */
-int sps_set_umma_variant(int v);
-/* The fused forward can visit the rows of the 3x3x3x3 convolutions (levels 1-3, >= 16 input
- * channels) in an order sorted by neighbourhood shape: fewer kernel offsets per 128-row tile.
- * mode 0: never (physical row order); 1 (default): for inputs of >= 400 000 rows (smaller ones
- * are launch-bound, the sort's 42 launches do not pay); 2: always.  Results do not depend on it. */
-int sps_set_pattern_sort(int mode);
 /* Per-tile present-offset bitmasks of a kernel map (K <= 81) for the tensor-core path:
  * d_masks uint32 [ceil(n_out_max/128)][4]. */
 int sps_kernel_map_tile_masks(const int32_t* d_map, int64_t map_ld, int K, const int32_t* d_n_out,
@@ -280,10 +290,10 @@ int sps_conv_pack_kmajor(const float* w, int K, int cin, int cout, const float* 
                          float* out);
 
 /* ---------------------------------------------------------------- measurement ------------ */
-/* Per-stage CUDA-event timing of sps_forward on its own stream (bench.py roofline figures).
- * sps_profile_read synchronises and returns up to `max` segments: names[i*32..] and ms[i]. */
-int sps_profile_enable(int on);
-int sps_profile_read(char* names, float* ms, int max, int* n_out);
+/* Per-stage CUDA-event timing of the fused forward of one context on its launch stream (bench.py roofline
+ * figures).  sps_profile_read synchronises and returns up to `max` segments: names[i*32..] and ms[i]. */
+int sps_profile_enable(sps_ctx* ctx, int on);
+int sps_profile_read(sps_ctx* ctx, char* names, float* ms, int max, int* n_out);
 /* Number of (in,out) pairs of a kernel map of the last forward: kind 3 (3x3x3x3), 5 (5x5x5x1,
  * level 0) or 8 (children of `level`).  Host-synchronising.  Used for algorithmic FLOP counts. */
 int sps_ctx_pair_count(sps_ctx* ctx, int level, int kind, int64_t* h_out, void* stream);

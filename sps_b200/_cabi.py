@@ -14,6 +14,8 @@ LIB_PATH = os.environ.get("SPS_B200_LIB") or os.path.join(HERE, "libsps_b200.so"
 SPS_OK, SPS_ERR_BAD_ARG, SPS_ERR_CAPACITY, SPS_ERR_COORD_RANGE, SPS_ERR_CUDA, SPS_ERR_UNSUPPORTED, SPS_ERR_STATE = range(7)
 SPS_NUM_LEVELS = 5
 SPS_CONV_NBR, SPS_CONV_UP = 0, 1
+SPS_BACKEND_AUTO, SPS_BACKEND_FP32, SPS_BACKEND_TF32, SPS_BACKEND_F16 = 0, 1, 2, 3
+SPS_IO_F32, SPS_IO_IN_F16, SPS_IO_IN2_F16, SPS_IO_OUT_F16, SPS_IO_F16 = 0, 1, 2, 4, 7
 _ERR_NAMES = {1: "SPS_ERR_BAD_ARG", 2: "SPS_ERR_CAPACITY", 3: "SPS_ERR_COORD_RANGE", 4: "SPS_ERR_CUDA",
               5: "SPS_ERR_UNSUPPORTED", 6: "SPS_ERR_STATE"}
 
@@ -22,10 +24,10 @@ SYMBOLS = [
     "sps_version", "sps_last_error", "sps_workspace_bytes", "sps_ctx_create", "sps_ctx_destroy", "sps_ctx_status",
     "sps_ctx_level", "sps_ctx_inverse_map", "sps_voxelize", "sps_build_maps", "sps_unpack_coords", "sps_conv_fwd",
     "sps_net_create", "sps_net_destroy", "sps_net_set_tensor", "sps_net_set_output", "sps_net_device_bytes", "sps_net_finalize",
-    "sps_forward", "sps_forward_features", "sps_forward_host", "sps_unet_forward", "sps_devox_sigmoid", "sps_forward_launch_count",
+    "sps_forward", "sps_forward_features", "sps_forward_host", "sps_unet_forward", "sps_devox_sigmoid", "sps_ctx_launch_count",
     "sps_map_bytes", "sps_map_build", "sps_map_destroy", "sps_submap_crop_voxel", "sps_submap_crop_radius",
-    "sps_assemble", "sps_memcpy_d2h", "sps_memcpy_h2d", "sps_infer_scan", "sps_infer_scan_scratch_bytes", "sps_conv_kmajor_ld", "sps_conv_pack_kmajor", "sps_conv_kmajor_ld_f16", "sps_conv_pack_kmajor_f16", "sps_kernel_map_tile_masks", "sps_set_tma_gather", "sps_set_umma_variant", "sps_set_pattern_sort",
-    "sps_set_conv_backend", "sps_profile_enable", "sps_profile_read", "sps_ctx_pair_count",
+    "sps_assemble", "sps_memcpy_d2h", "sps_memcpy_h2d", "sps_infer_scan", "sps_infer_scan_scratch_bytes", "sps_conv_kmajor_ld", "sps_conv_pack_kmajor", "sps_conv_kmajor_ld_f16", "sps_conv_pack_kmajor_f16", "sps_kernel_map_tile_masks", "sps_ctx_set_pattern_sort",
+    "sps_ctx_set_conv_backend", "sps_profile_enable", "sps_profile_read", "sps_ctx_pair_count",
     "sps_confusion_counts", "sps_voxel_mean", "sps_gather_rows", "sps_affine_relu",
     "sps_ballmap_bytes", "sps_ballmap_build", "sps_ballmap_destroy", "sps_ball_query_scratch_bytes", "sps_submap_ball_query",
 ]
@@ -45,7 +47,8 @@ class ConvArgs(C.Structure):
                 ("out", C.c_void_p), ("out_ld", C.c_int64),
                 ("head_w", C.c_void_p), ("head_b", C.c_float), ("head_out", C.c_void_p),
                 ("weight_kmajor", C.c_void_p), ("kmajor_ld", C.c_int64), ("round_out", C.c_int),
-                ("tile_mask", C.c_void_p), ("perm", C.c_void_p), ("tile_slices", C.c_void_p), ("io_dtype", C.c_int)]
+                ("tile_mask", C.c_void_p), ("perm", C.c_void_p), ("tile_slices", C.c_void_p), ("io_dtype", C.c_int),
+                ("backend", C.c_int)]
 
 
 class SpsError(RuntimeError):
@@ -91,7 +94,7 @@ def load() -> C.CDLL:
         "sps_forward_host": (i32, [vp, vp, vp, i64, i64, f32, vp, vp]),
         "sps_unet_forward": (i32, [vp, vp, vp, vp, vp]),
         "sps_devox_sigmoid": (i32, [vp, vp, i64, vp, vp]),
-        "sps_forward_launch_count": (i32, []),
+        "sps_ctx_launch_count": (i32, [vp]),
         "sps_map_bytes": (sz, [i64]),
         "sps_map_build": (i32, [C.POINTER(vp), vp, sz, vp, i64, f32, vp]),
         "sps_map_destroy": (i32, [vp]),
@@ -102,15 +105,13 @@ def load() -> C.CDLL:
         "sps_memcpy_h2d": (i32, [vp, vp, sz, vp]),
         "sps_infer_scan": (i32, [vp, vp, vp, vp, i64, f32, vp, vp, sz, vp, vp]),
         "sps_infer_scan_scratch_bytes": (sz, [i64]),
-        "sps_set_tma_gather": (i32, [i32]),
-        "sps_set_umma_variant": (i32, [i32]),
-        "sps_set_pattern_sort": (i32, [i32]),
+        "sps_ctx_set_pattern_sort": (i32, [vp, i32]),
         "sps_kernel_map_tile_masks": (i32, [vp, i64, i32, vp, i64, vp, vp]),
         "sps_conv_kmajor_ld": (i64, [i32, i32, i32]),
         "sps_conv_pack_kmajor": (i32, [vp, i32, i32, i32, vp, i32, vp]),
         "sps_conv_kmajor_ld_f16": (i64, [i32, i32, i32]),
         "sps_conv_pack_kmajor_f16": (i32, [vp, i32, i32, i32, vp, i32, vp]),
-        "sps_set_conv_backend": (i32, [i32]),
+        "sps_ctx_set_conv_backend": (i32, [vp, i32]),
         "sps_confusion_counts": (i32, [vp, vp, i64, i64, f32, f32, vp, vp, vp]),
         "sps_voxel_mean": (i32, [vp, vp, i64, i32, vp, vp, vp]),
         "sps_gather_rows": (i32, [vp, i64, i32, vp, i64, vp, vp]),
@@ -120,8 +121,8 @@ def load() -> C.CDLL:
         "sps_ballmap_destroy": (i32, [vp]),
         "sps_ball_query_scratch_bytes": (sz, [i64]),
         "sps_submap_ball_query": (i32, [vp, vp, i64, vp, vp, i64, vp, vp, sz, vp]),
-        "sps_profile_enable": (i32, [i32]),
-        "sps_profile_read": (i32, [vp, vp, i32, C.POINTER(i32)]),
+        "sps_profile_enable": (i32, [vp, i32]),
+        "sps_profile_read": (i32, [vp, vp, vp, i32, C.POINTER(i32)]),
         "sps_ctx_pair_count": (i32, [vp, i32, i32, C.POINTER(i64), vp]),
     }
     for name, (res, args) in sig.items():

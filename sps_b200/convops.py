@@ -59,14 +59,17 @@ def conv_fwd(inp, weight, n_out, *, map=None, map_ld=0, mode=_cabi.SPS_CONV_NBR,
     """out[o] = act(sum_k in[map[k][o]] @ W[k] (+ in2[o] @ W2) + shift (+ res[o])); ``n_out`` is a
     1-element int32 CUDA tensor (device-side count).  ``inp``/``out``/``in2``/``res`` may be
     channel slices (stride(0) is the leading dimension).  ``io_f16``: ``inp``/``in2``/``res``/``out`` are fp16
-    rows and ``weight_kmajor`` comes from :func:`pack_kmajor_f16` (SPS_IO_F16, the fused forward's format)."""
+    rows and ``weight_kmajor`` comes from :func:`pack_kmajor_f16` (SPS_IO_F16, the fused forward's format); a
+    3-tuple gives the formats of (in, in2/res, out) separately (the 8-output-channel FMA kernel takes any mix).
+    ``backend``: SPS_BACKEND_* of this one call (default AUTO) -- the library has no process-wide switch."""
     lib = _cabi.load()
     K = weight.shape[0] if weight.dim() == 3 else 1
     cin, cout = weight.shape[-2], weight.shape[-1]
     if n_out_max is None:
         n_out_max = int(n_out.item())
     if out is None and head_out is None:
-        out = torch.empty((max(n_out_max, 1), cout), dtype=torch.float16 if io_f16 else torch.float32, device=inp.device)
+        out_f16 = io_f16[2] if isinstance(io_f16, (tuple, list)) else io_f16
+        out = torch.empty((max(n_out_max, 1), cout), dtype=torch.float16 if out_f16 else torch.float32, device=inp.device)
     a = _cabi.ConvArgs()
     a.mode, a.K, a.cin, a.cout = mode, K, cin, cout
     a.map, a.map_ld = (map.data_ptr() if map is not None else None), int(map_ld)
@@ -86,16 +89,15 @@ def conv_fwd(inp, weight, n_out, *, map=None, map_ld=0, mode=_cabi.SPS_CONV_NBR,
     if weight_kmajor is not None:
         a.weight_kmajor, a.kmajor_ld = weight_kmajor.data_ptr(), weight_kmajor.stride(0)
     a.round_out = int(round_out)
-    a.io_dtype = 1 if io_f16 else 0
+    if isinstance(io_f16, (tuple, list)):      # (in, in2/res, out) row formats given separately
+        a.io_dtype = (1 if io_f16[0] else 0) | (2 if io_f16[1] else 0) | (4 if io_f16[2] else 0)
+    else:
+        a.io_dtype = _cabi.SPS_IO_F16 if io_f16 else _cabi.SPS_IO_F32
+    a.backend = int(backend) if backend is not None else _cabi.SPS_BACKEND_AUTO
     if weight_kmajor is not None and map is not None and tile_mask is None and K <= 81:
         tile_mask = kernel_map_tile_masks(map, map_ld, K, n_out, n_out_max)
     if tile_mask is not None:
         a.tile_mask = tile_mask.data_ptr()
-    if backend is not None:
-        check(lib.sps_set_conv_backend(backend), "sps_set_conv_backend")
-    try:
+    with torch.cuda.device(inp.device):
         check(lib.sps_conv_fwd(C.byref(a), _stream()), "sps_conv_fwd")
-    finally:
-        if backend is not None:
-            lib.sps_set_conv_backend(0)
     return out if out is not None else head_out

@@ -79,17 +79,22 @@ static size_t carve(sps_ctx* c, void* base, int64_t max_points) {
 
 int conv_simt(const sps_conv_args& a, cudaStream_t st);
 int conv_umma(const sps_conv_args& a, cudaStream_t st);
+int conv_fma8(const sps_conv_args& a, cudaStream_t st);
 bool conv_umma_supports(const sps_conv_args& a);
-bool conv_umma6_f16_supports(const sps_conv_args& a);
-#ifndef SPS_AUTO_F16
-#define SPS_AUTO_F16 1   // backend 0 (auto): the fused forward stores activations as fp16
-#endif
-static int g_backend = 0;  // 0 auto, 1 fp32 CUDA-core, 2 tcgen05 TF32 on fp32 rows, 3 tcgen05 on fp16 rows
-int conv_backend() { return g_backend; }
-bool conv_half_storage() { return g_backend == 3 || (g_backend == 0 && SPS_AUTO_F16); }
+bool conv_umma_f16_supports(const sps_conv_args& a);
+bool conv_fma8_supports(const sps_conv_args& a);
+
+// Kernel family of one convolution call (sps_conv_args.backend; the fused forward passes its context's mode):
+//   FP32: CUDA-core fp32 kernels.  TF32 / F16: the tensor-core kernel whenever the call fits it.  AUTO: the
+//   8-output-channel FMA kernel where it fits, else the tensor-core kernel, else the generic CUDA-core kernel.
 int conv_dispatch(const sps_conv_args& a, cudaStream_t st) {
-  if (a.io_dtype == SPS_IO_F16) return conv_umma6_f16_supports(a) ? conv_umma(a, st) : SPS_ERR_UNSUPPORTED;
-  if (g_backend != 1 && conv_umma_supports(a)) return conv_umma(a, st);
+  const bool mixed = a.io_dtype != SPS_IO_F32 && a.io_dtype != SPS_IO_F16;
+  if (a.backend == SPS_BACKEND_FP32) return a.io_dtype == SPS_IO_F32 ? conv_simt(a, st) : SPS_ERR_UNSUPPORTED;
+  if (a.backend == SPS_BACKEND_AUTO && conv_fma8_supports(a)) return conv_fma8(a, st);
+  if (a.io_dtype == SPS_IO_F16 && conv_umma_f16_supports(a)) return conv_umma(a, st);
+  if (a.io_dtype == SPS_IO_F32 && conv_umma_supports(a)) return conv_umma(a, st);
+  if (conv_fma8_supports(a)) return conv_fma8(a, st);
+  if (mixed || a.io_dtype == SPS_IO_F16) return SPS_ERR_UNSUPPORTED;
   return conv_simt(a, st);
 }
 
@@ -97,11 +102,17 @@ int conv_dispatch(const sps_conv_args& a, cudaStream_t st) {
 
 using namespace sps;
 
-extern "C" int sps_set_conv_backend(int backend) {
-  if (backend < 0 || backend > 3) return SPS_ERR_BAD_ARG;
-  g_backend = backend;
+extern "C" int sps_ctx_set_conv_backend(sps_ctx* ctx, int backend) {
+  if (!ctx || backend < 0 || backend > 3) return SPS_ERR_BAD_ARG;
+  ctx->backend = backend;
   return SPS_OK;
 }
+extern "C" int sps_ctx_set_pattern_sort(sps_ctx* ctx, int mode) {
+  if (!ctx || mode < 0 || mode > 2) return SPS_ERR_BAD_ARG;
+  ctx->pattern_sort = mode;
+  return SPS_OK;
+}
+extern "C" int sps_ctx_launch_count(const sps_ctx* ctx) { return ctx ? ctx->forward_launches : 0; }
 extern "C" const char* sps_version(void) { return "sps_b200 0.1 (sm_100a)"; }
 extern "C" const char* sps_last_error(void) { return g_err; }
 
@@ -155,7 +166,7 @@ extern "C" int sps_ctx_level(sps_ctx* ctx, int level, sps_level_view* v) {
   if (!ctx || !v || level < 0 || level >= SPS_NUM_LEVELS) return SPS_ERR_BAD_ARG;
   v->keys = (const uint64_t*)ctx->keys[level];
   v->count = ctx->counts + level;
-  v->nbr3 = ctx->nbr3[level];
+  v->nbr3 = ctx->dense_maps ? ctx->nbr3[level] : nullptr;   // sparse tables are never handed out
   v->nbr5 = level == 0 ? ctx->nbr5 : nullptr;
   v->parent = ctx->parent[level];
   v->child = ctx->child[level];
@@ -181,51 +192,45 @@ extern "C" int sps_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, void
 }
 
 // ---------------------------------------------------------------- profiling ---------------
-#include <string>
-#include <vector>
 #include "profile.h"
 namespace sps {
-static bool g_prof = false;
-static std::vector<cudaEvent_t> g_ev;
-static std::vector<std::string> g_names;
-static size_t g_used = 0;
-bool prof_on() { return g_prof; }
-static cudaEvent_t next_event() {
-  if (g_used == g_ev.size()) {
+static cudaEvent_t next_event(sps_ctx* c) {
+  if (c->prof_used == c->prof_ev.size()) {
     cudaEvent_t e;
     cudaEventCreate(&e);
-    g_ev.push_back(e);
+    c->prof_ev.push_back(e);
   }
-  return g_ev[g_used++];
+  return c->prof_ev[c->prof_used++];
 }
-void prof_begin(cudaStream_t st) {
-  if (!g_prof) return;
-  g_used = 0;
-  g_names.clear();
-  cudaEventRecord(next_event(), st);
+void prof_begin(sps_ctx* c, cudaStream_t st) {
+  if (!c->prof) return;
+  c->prof_used = 0;
+  c->prof_names.clear();
+  cudaEventRecord(next_event(c), st);
 }
-void prof_mark(const char* name, cudaStream_t st) {
-  if (!g_prof || g_used == 0) return;
-  cudaEventRecord(next_event(), st);
-  g_names.push_back(name);
+void prof_mark(sps_ctx* c, const char* name, cudaStream_t st) {
+  if (!c->prof || c->prof_used == 0) return;
+  cudaEventRecord(next_event(c), st);
+  c->prof_names.push_back(name);
 }
 }  // namespace sps
 
-extern "C" int sps_profile_enable(int on) {
-  g_prof = on != 0;
-  g_used = 0;
-  g_names.clear();
+extern "C" int sps_profile_enable(sps_ctx* ctx, int on) {
+  if (!ctx) return SPS_ERR_BAD_ARG;
+  ctx->prof = on != 0;
+  ctx->prof_used = 0;
+  ctx->prof_names.clear();
   return SPS_OK;
 }
 
-extern "C" int sps_profile_read(char* names, float* ms, int max, int* n_out) {
-  if (!names || !ms || !n_out || max < 0) return SPS_ERR_BAD_ARG;
-  int n = (int)g_names.size();
+extern "C" int sps_profile_read(sps_ctx* ctx, char* names, float* ms, int max, int* n_out) {
+  if (!ctx || !names || !ms || !n_out || max < 0) return SPS_ERR_BAD_ARG;
+  int n = (int)ctx->prof_names.size();
   if (n > max) n = max;
-  if (g_used > 0) SPS_CUDA_CHECK(cudaEventSynchronize(g_ev[g_used - 1]));
+  if (ctx->prof_used > 0) SPS_CUDA_CHECK(cudaEventSynchronize(ctx->prof_ev[ctx->prof_used - 1]));
   for (int i = 0; i < n; ++i) {
-    SPS_CUDA_CHECK(cudaEventElapsedTime(&ms[i], g_ev[i], g_ev[i + 1]));
-    snprintf(names + 32 * i, 32, "%s", g_names[i].c_str());
+    SPS_CUDA_CHECK(cudaEventElapsedTime(&ms[i], ctx->prof_ev[i], ctx->prof_ev[i + 1]));
+    snprintf(names + 32 * i, 32, "%s", ctx->prof_names[i].c_str());
   }
   *n_out = n;
   return SPS_OK;

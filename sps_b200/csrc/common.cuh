@@ -132,6 +132,19 @@ constexpr int kStatusRange = 1, kStatusCapacity = 2;
   } while (0)
 int set_cuda_error(cudaError_t e, const char* what);
 
+// per-device one-time opt-in to large dynamic shared memory (the attribute is per device AND per kernel)
+template <class Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, size_t bytes, unsigned long long* done_mask) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (__atomic_load_n(done_mask, __ATOMIC_ACQUIRE) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) __atomic_fetch_or(done_mask, bit, __ATOMIC_RELEASE);
+  return e;
+}
+
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 }  // namespace sps

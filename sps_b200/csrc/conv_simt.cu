@@ -151,12 +151,8 @@ static int launch_simt(const sps_conv_args& a, cudaStream_t st) {
   if (kc < 1) return SPS_ERR_UNSUPPORTED;
   size_t smem = (size_t)kc * slab;
   if (a.in2 && (size_t)a.cin2 * COUT * 4 > smem) smem = (size_t)a.cin2 * COUT * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SPS_CUDA_CHECK(cudaFuncSetAttribute(k_conv_simt<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kSimtSmemBytes));
-    attr_set = true;
-  }
+  static unsigned long long attr_done = 0;   // bit per device
+  SPS_CUDA_CHECK(ensure_dynamic_smem(k_conv_simt<COUT>, kSimtSmemBytes, &attr_done));
   int64_t tiles = (a.n_out_max + VB - 1) / VB;
   if (tiles < 1) tiles = 1;
   const int grid = (int)(tiles < 148 * 8 ? tiles : 148 * 8);
@@ -244,11 +240,8 @@ static int launch_up(const sps_conv_args& a, cudaStream_t st) {
   int kc = kSimtSmemBytes / slab;
   if (kc > 8) kc = 8;
   if (kc < 1) return SPS_ERR_UNSUPPORTED;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SPS_CUDA_CHECK(cudaFuncSetAttribute(k_conv_up<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSimtSmemBytes));
-    attr_set = true;
-  }
+  static unsigned long long attr_done = 0;   // bit per device
+  SPS_CUDA_CHECK(ensure_dynamic_smem(k_conv_up<COUT>, kSimtSmemBytes, &attr_done));
   int64_t tiles = (a.n_out_max + VB - 1) / VB;
   if (tiles < 1) tiles = 1;
   const int grid = (int)(tiles < 148 * 8 ? tiles : 148 * 8);
@@ -305,19 +298,23 @@ int conv_simt(const sps_conv_args& a, cudaStream_t st) {
 extern "C" int sps_conv_fwd(const sps_conv_args* a, void* stream) {
   if (!a || !a->in || !a->weight || !a->n_out || (!a->out && !a->head_out)) return SPS_ERR_BAD_ARG;
   if (a->mode != SPS_CONV_NBR && a->mode != SPS_CONV_UP) return SPS_ERR_BAD_ARG;
+  if (a->backend < SPS_BACKEND_AUTO || a->backend > SPS_BACKEND_F16 || (a->io_dtype & ~SPS_IO_F16)) return SPS_ERR_BAD_ARG;
   if (a->mode == SPS_CONV_UP && (!a->map || a->K != 8 || !a->out || a->in2 || a->res || a->head_out || (a->cin & 3)))
     return SPS_ERR_BAD_ARG;
   if (a->mode == SPS_CONV_NBR && !a->map && a->K != 1) return SPS_ERR_BAD_ARG;
-  if (a->cin < 1 || (a->cin != 1 && a->cin % 4) || (a->in_ld % 4 && a->cin != 1)) return SPS_ERR_BAD_ARG;
-  if (a->in2 && (!a->weight2 || a->cin2 % 4 || a->in2_ld % 4)) return SPS_ERR_BAD_ARG;
-  const bool narrow = a->K == 1 && !a->map && a->cout < 8;   // scalar kernel, no vector alignment needed
+  // element counts per 16 bytes of the three row formats (fp32: 4, fp16: 8)
+  const int ea = (a->io_dtype & SPS_IO_IN_F16) ? 8 : 4, e2 = (a->io_dtype & SPS_IO_IN2_F16) ? 8 : 4,
+            eo = (a->io_dtype & SPS_IO_OUT_F16) ? 8 : 4;
+  if (a->cin < 1 || (a->cin != 1 && a->cin % ea) || (a->in_ld % ea && a->cin != 1)) return SPS_ERR_BAD_ARG;
+  if (a->in2 && (!a->weight2 || a->cin2 % e2 || a->in2_ld % e2)) return SPS_ERR_BAD_ARG;
+  const bool narrow = a->K == 1 && !a->map && a->cout < 8 && a->io_dtype == SPS_IO_F32;   // scalar kernel, no vector alignment needed
   if (narrow) return sps::conv_dispatch(*a, (cudaStream_t)stream);
-  if (a->out && a->out_ld % 4) return SPS_ERR_BAD_ARG;
-  if (a->res && a->res_ld % 4) return SPS_ERR_BAD_ARG;
+  if (a->out && a->out_ld % eo) return SPS_ERR_BAD_ARG;
+  if (a->res && a->res_ld % e2) return SPS_ERR_BAD_ARG;
   if (a->head_out && (a->cout != 8 || !a->head_w)) return SPS_ERR_BAD_ARG;
   if (a->n_out_max < 0) return SPS_ERR_BAD_ARG;
   const uintptr_t al = (uintptr_t)a->weight | (uintptr_t)a->out | (uintptr_t)a->in2 | (uintptr_t)a->weight2 |
                        (uintptr_t)a->res | (a->cin != 1 ? (uintptr_t)a->in : 0);
-  if (al & 15) return SPS_ERR_BAD_ARG;  // float4 access everywhere
+  if (al & 15) return SPS_ERR_BAD_ARG;  // 16-byte vector access everywhere
   return sps::conv_dispatch(*a, (cudaStream_t)stream);
 }

@@ -1,111 +1,142 @@
-// tcgen05 implicit-GEMM sparse convolution for sm_100a (the one dense contraction of the path).
-//
-//   out[o] = act( sum_k in[map[k][o]] @ W[k]  (+ in2[o] @ W2)  + shift (+ res[o]) )
-//
-// A tile is 128 output voxels = the 128 TMEM lanes of one fp32 accumulator [128 x N] (N = Cout
-// padded to 16).  One persistent CTA per SM (416 threads) is warp-specialised the Blackwell way:
-// 8 producer warps gather, 1 warp issues tcgen05.mma, 4 warps run the epilogue; they only meet
-// through mbarrier rings (stage full/empty, accumulator full/empty, kernel-map slice ready), so
-// the gathers of tile i+1 overlap the MMAs of tile i and the epilogue of tile i-1 (two TMEM
-// accumulators).  The GEMM K dimension is the im2col row
-// (kernel offset k, input channel ci), walked in 16-byte groups (4 fp32 channels):
-//   * prologue: the tile's slice of the kernel map is staged in shared memory with cp.async
-//     (all K loads in flight at once) and a warp ballot finds the offsets that have at least
-//     one neighbour inside the tile -- only those are walked (sparsity skip at tile level);
-//   * one pipeline stage = 128 rows x 128 B of gathered A (8 groups) written by cp.async
-//     (zero-fill for absent neighbours) straight into the UMMA canonical K-major SWIZZLE_128B
-//     layout, plus the matching N rows x 128 B of the K-major, TF32-rounded weight matrix.
-//     Channel counts are padded per kernel offset so that a stage never straddles offsets in
-//     an irregular way: Cin <= 16 packs 8/(Cin/4) offsets per stage, Cin >= 24 uses
-//     ceil(Cin/32) stages per offset;
-//   * one elected thread issues 4 x tcgen05.mma.kind::tf32 (M=128, N, K=8) per stage into
-//     TMEM; tcgen05.commit releases the stage through an mbarrier; a 3-deep ring keeps two
-//     stages of gathers in flight behind the MMAs, two CTAs per SM overlap prologue/epilogue;
-//   * epilogue: all 8 warps tcgen05.ld half an accumulator row each, add the folded BatchNorm
-//     shift, optional residual, ReLU, optional fused 8->1 head, store fp32 (optionally
-//     TF32-rounded so the next layer's operand rounding is nearest, not truncation).
-// Operands are TF32 (fp32 storage), accumulation fp32: ~1e-4 score error on the reference
-// network against the 2e-3 budget; bf16 operands measured 6e-4..2e-2 (DESIGN.md "precision").
-#include <cstdlib>
+// tcgen05 implicit-GEMM sparse convolution (the layers with >= 16 output channels of the fused forward, and
+// sps_conv_fwd on its tensor-core backends):
+//   out[o] = act( sum_k in[nbr[k][o]] . W[k]  (+ in2[o] . W2)  + shift (+ res[o]) )
+// 128 output rows = the 128 TMEM lanes of one fp32 accumulator, two accumulators per CTA, persistent
+// warp-specialised CTAs.  The gather side is built around what ncu's source view showed about the first
+// generations (profiles/r1_conv_source_level.md): 8 producer warps that spent 27 % of their time staging the
+// next tile's kernel-map slice, 54 % executing ~130 instructions per pipeline stage and only 8 % waiting for
+// a free stage.  Here
+//   * a dedicated LOADER warp builds the per-tile list of present offsets and stages the kernel-map
+//     slice (and the tile's own row numbers) up to 7 tiles ahead with 16-byte cp.async copies; a
+//     producer thread fetches the indices of its four rows with one 16-byte shared load;
+//   * the stage ring is 4 deep: the gathered rows are re-read from L1 by neighbouring output rows,
+//     and measured run time follows the L1 size the carve-out leaves (4 stages beat 2, 3 and 5-7;
+//     +40 KB of unused shared memory costs +25 % on the 32/48-channel layers).  A variant that
+//     streamed the slices through a 16 KB ring with synchronous L1::no_allocate loads (88 KB of
+//     shared memory in total) was not faster on the wide layers and starved the narrow ones;
+//   * the producers walk the stage ring with COMPILE-TIME slot numbers (the stage loop is unrolled
+//     by the ring depth), so every shared address and mbarrier address is base + immediate and the
+//     "copies landed" arrive is a single uniform-address instruction;
+//   * the per-stage parameters of the next stage are fetched before waiting for its slot;
+//   * global addresses are one IMAD.WIDE per 16-byte chunk.
+// Warp roles (448 threads): 0-7 producers, 8 loader, 9 MMA issuer, 10-13 epilogue.
 #include "umma_common.cuh"
 
 namespace sps {
 
-#ifndef SPS_PRODUCER_GROUPS
-#define SPS_PRODUCER_GROUPS 1
+// ring depth per accumulator width (measured: 4 beats 2, 3 and 5-7; deeper rings cost L1)
+#ifndef SPS_V6_S16
+#define SPS_V6_S16 4
 #endif
-// Producer groups of 8 warps; group g writes the stages with (stage index % groups) == g, so several stages
-// of one tile are being gathered at once without multiplying the per-stage instruction count.
-constexpr int kGroups = SPS_PRODUCER_GROUPS;
-constexpr int kProducerWarps = 8 * kGroups;
-__device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kProducerWarps * 32) : "memory"); }
-
-constexpr int kProducerThreads = kProducerWarps * 32;  // producer warps: gather A/B, stage kernel-map slices
-constexpr int kGroupThreads = 256;                    // threads that write one stage
-#ifndef SPS_ARRIVE_LAG
-#define SPS_ARRIVE_LAG 0
+#ifndef SPS_V6_S32
+#define SPS_V6_S32 4
 #endif
-// Stage-full signalling.  LAG > 0: every thread commits its copies as a cp.async group, and once the group
-// issued LAG stages earlier has landed (cp.async.wait_group) ONE lane per warp arrives on that stage's
-// barrier -- 8 arrivals per stage.  LAG == 0: every thread arrives asynchronously
-// (cp.async.mbarrier.arrive.noinc) -- 256 arrivals on one mbarrier word per stage, which serialise.
-constexpr int kArriveLag = SPS_ARRIVE_LAG;
-constexpr int kFullArrivals = kArriveLag > 0 ? kGroupThreads / 32 : kGroupThreads;
-static_assert(kGroups == 1 || kArriveLag == 0, "lagged arrivals assume one producer group");
-constexpr int kRowsPerThread = kTileM * 8 / kGroupThreads;      // A chunks per thread per stage (4)
-constexpr int kRowStep = kGroupThreads / 8;           // row distance between a thread's chunks
-constexpr int kMmaWarp = kProducerWarps;              // next warp: tcgen05.mma issue
-// the 4 warps after it: epilogue (TMEM -> registers -> global)
-constexpr int kCtaThreads = kProducerThreads + 32 + 128;
+#ifndef SPS_V6_S64
+#define SPS_V6_S64 4
+#endif
+constexpr int kV6ProducerWarps = 8;
+constexpr int kV6ProducerThreads = kV6ProducerWarps * 32;
+constexpr int kV6LoaderWarp = kV6ProducerWarps;
+constexpr int kV6MmaWarp = kV6LoaderWarp + 1;
+constexpr int kV6EpiWarp0 = kV6MmaWarp + 1;
+constexpr int kV6Threads = (kV6EpiWarp0 + 4) * 32;
+constexpr int kV6Entries = kMaxK + 1;                 // present offsets + the tile's own rows
+constexpr int kV6EntryBytes = kTileM * 4;
+constexpr int kV6ParBytes = kV6Entries * kV6EntryBytes;  // staged row indices of one 81-offset tile
+// The index area (2 x 82 entries) holds as many tiles as fit: 2 for the 81-offset kernels, 8 for the 2x2x2 ones
+// (9 entries per tile).  Tiles of the small kernels are one or two stages long, so the number of tiles in flight
+// -- not the stage ring -- bounds their memory-level parallelism.
+constexpr int kV6MaxTilesAhead = 8;
+// ordered present-offset lists of the staged tiles: (K + 1) bytes each, rounded to 16 -> at most 224 bytes.  (Every
+// byte counts here: 167 936 bytes per CTA is the last size that still gets the 164 KB carve-out, i.e. 92 KB of L1.)
+constexpr int kV6KlistBytes = 256;
 
+#ifndef SPS_V6_PAD_KB
+#define SPS_V6_PAD_KB 0   // experiment: unused shared memory, shrinks the L1 side of the unified array
+#endif
 template <int NPAD>
-struct UmmaCfg {
-#ifndef SPS_S64
-#define SPS_S64 5
-#endif
-#ifndef SPS_S32
-#define SPS_S32 6
-#endif
-  static constexpr int S = NPAD == 64 ? SPS_S64 : SPS_S32;        // ring depth
+struct V6Cfg {
+  static constexpr int S = NPAD == 64 ? SPS_V6_S64 : NPAD == 32 ? SPS_V6_S32 : SPS_V6_S16;
   static constexpr int kBStage = NPAD * 128;
-  static constexpr int kTmemCols = 2 * NPAD < 32 ? 32 : 2 * NPAD;   // two accumulators (double buffered)
-  static constexpr size_t smem = (size_t)S * (kAStageBytes + kBStage) + 2 * (size_t)kMaxK * kTileM * 4 +
-                                 8 * (2 * S + 6) + 2 * 96 + 32;
+  static constexpr int kTmemCols = 2 * NPAD < 32 ? 32 : 2 * NPAD;
+  // A ring | B ring | row indices [2][82][128] | barriers | klists | nact [8] | shift [64] | tmem slot
+  static constexpr size_t smem = (size_t)S * (kAStageBytes + kBStage) + 2 * (size_t)kV6ParBytes +
+                                 8 * (2 * S + 2 * kV6MaxTilesAhead + 4) + kV6KlistBytes + 4 * kV6MaxTilesAhead +
+                                 64 * 4 + 16 + SPS_V6_PAD_KB * 1024;
 };
 
-// GPC = padded groups per offset class: 2 or 4 (several offsets per stage) or 8 (= "8 or more":
-// one offset spans GP/8 stages).  Persistent, warp-specialised: producers, MMA issuer and
-// epilogue run decoupled through mbarrier rings and never meet at a block-wide barrier.
-template <int NPAD, int GPC>
-__global__ void __launch_bounds__(kCtaThreads, 1) k_conv_umma(const sps_conv_args a, const UmmaParams p) {
-  using Cfg = UmmaCfg<NPAD>;
+// 16-byte copy that writes zeros instead when `skip` is set (the ignore-src form: one predicate, no size select)
+template <bool kBypassL1>
+__device__ __forceinline__ void cp_async16_or_zero(uint32_t dst, const void* src, bool skip) {
+  if (kBypassL1)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %2, 0;\n"
+        "cp.async.cg.shared.global [%0], [%1], 16, p;\n"
+        "}\n" ::"r"(dst), "l"(src), "r"((int)skip)
+        : "memory");
+  else
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %2, 0;\n"
+        "cp.async.ca.shared.global [%0], [%1], 16, p;\n"
+        "}\n" ::"r"(dst), "l"(src), "r"((int)skip)
+        : "memory");
+}
+#ifndef SPS_V6_A_CG
+#define SPS_V6_A_CG 0
+#endif
+#ifndef SPS_V6_B_CG
+#define SPS_V6_B_CG 0
+#endif
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+
+// T = float: fp32 rows, TF32 operands (kind::tf32); T = __half: fp16 rows and weights (kind::f16, 8 channels per
+// 16-byte group, so a stage carries twice the channels).  GPC = 16-byte groups per kernel offset: 1 (fp16
+// only), 2 or 4 -> 8/GPC offsets share a stage; 8 -> one offset spans GP/8 stages.
+template <int NPAD, int GPC, typename T>
+__global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_args a, const UmmaParams p) {
+  using Cfg = V6Cfg<NPAD>;
+  constexpr int EB = sizeof(T);                         // bytes per stored activation
+  constexpr bool kHalf = EB == 2;
   constexpr int S = Cfg::S;
   constexpr int kBStageBytes = Cfg::kBStage;
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sA = smem;                                                     // [S][128 rows x 128 B], 128B-swizzled
-  uint8_t* sB = smem + S * kAStageBytes;                                  // [S][NPAD rows x 128 B]
-  int32_t* sidx = reinterpret_cast<int32_t*>(sB + S * kBStageBytes);      // [2][K][128] kernel-map slices (tile parity)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sidx + 2 * kMaxK * kTileM);
-  // bars: full[S], empty[S], idx_full[2], acc_full[2], acc_empty[2]
-  uint8_t* klist = reinterpret_cast<uint8_t*>(bars + 2 * S + 6);           // [2][96] present offsets per tile parity
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(klist + 2 * 96);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + S * kAStageBytes;
+  int32_t* sidx = reinterpret_cast<int32_t*>(sB + S * kBStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sidx) + 2 * kV6ParBytes);
+  // bars: full[S], empty[S], idx_full[8], idx_empty[8], acc_full[2], acc_empty[2]
+  uint8_t* klist = reinterpret_cast<uint8_t*>(bars + 2 * S + 2 * kV6MaxTilesAhead + 4);
+  int32_t* snact = reinterpret_cast<int32_t*>(klist + kV6KlistBytes);
+  float* sshift = reinterpret_cast<float*>(snact + kV6MaxTilesAhead);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sshift + 64);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB), sidx_u = smem_u32(sidx);
-  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * S, bar_idx = bar_empty + 8 * S,
-                 bar_accf = bar_idx + 16, bar_acce = bar_accf + 16;
-  if (sA_u & 1023) __trap();  // SWIZZLE_128B atoms need 1024-byte aligned stage bases
+  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * S, bar_idxf = bar_empty + 8 * S,
+                 bar_idxe = bar_idxf + 8 * kV6MaxTilesAhead, bar_accf = bar_idxe + 8 * kV6MaxTilesAhead,
+                 bar_acce = bar_accf + 16;
+  if (sA_u & 1023) __trap();
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(bar_full + 8 * s, kFullArrivals); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(bar_full + 8 * s, kV6ProducerThreads); mbar_init(bar_empty + 8 * s, 1); }
+    for (int i = 0; i < kV6MaxTilesAhead; ++i) {
+      mbar_init(bar_idxf + 8 * i, 33);                 // 32 async arrivals (copies landed) + 1 for the plain stores
+      mbar_init(bar_idxe + 8 * i, kV6ProducerWarps);
+    }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_idx + 8 * i, kProducerThreads);
       mbar_init(bar_accf + 8 * i, 1);
       mbar_init(bar_acce + 8 * i, 128);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == kMmaWarp) {
+  if (tid < 64) sshift[tid] = (a.shift && tid < a.cout) ? __ldg(a.shift + tid) : 0.f;
+  if (warp == kV6MmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)Cfg::kTmemCols)
                  : "memory");
@@ -119,195 +150,259 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_conv_umma(const sps_conv_arg
   const int n_out = *a.n_out;
   const int ntiles = (n_out + kTileM - 1) / kTileM;
   const int K = a.K;
-  const int gpk = a.cin >> 2;                           // real groups per offset
-  const int GP = GPC < 8 ? GPC : padded_groups(a.cin);  // padded groups per offset
-  const int SPE = GPC < 8 ? 1 : GP >> 3;                // stages per offset (large Cin)
-  constexpr int EPS = GPC < 8 ? 8 / GPC : 1;            // offsets per stage (small Cin)
-  const int gpk2 = a.in2 ? (a.cin2 >> 2) : 0;
+  const int gpk = (a.cin * EB) >> 4;                    // real 16-byte groups per offset
+  const int GP = GPC < 8 ? GPC : padded_groups_of(gpk, kHalf);  // padded groups per offset
+  const int SPE = GPC < 8 ? 1 : GP >> 3;                // stages per offset (Cin >= 24)
+  constexpr int EPS = GPC < 8 ? 8 / GPC : 1;            // offsets per stage (Cin <= 16)
+  const int gpk2 = a.in2 ? ((a.cin2 * EB) >> 4) : 0;
   const int st2 = (gpk2 + 7) >> 3;                      // stages of the fused 1x1 term
   const uint32_t* tmask = a.tile_mask;
+  const int gstep = gridDim.x;
+  // tiles whose index slices fit in the staging area at once, and the bytes each takes
+  const int NP = min(kV6MaxTilesAhead, (2 * kV6Entries) / (K + 1));
+  const uint32_t par_bytes = (uint32_t)(K + 1) * kV6EntryBytes;
+  const int kl_stride = (K + 1 + 15) & ~15;
   auto tile_nact = [&](int tile) {
     return __popc(__ldg(tmask + 4 * tile)) + __popc(__ldg(tmask + 4 * tile + 1)) + __popc(__ldg(tmask + 4 * tile + 2));
   };
   auto tile_stages = [&](int nact) { return (GPC < 8 ? (nact + EPS - 1) / EPS : nact * SPE) + st2; };
 
-  if (warp < kMmaWarp) {
-    // =========================== PRODUCERS (kGroups x 256 threads) ===========================
-    const uint32_t in_ld_b = (uint32_t)a.in_ld * 4u, in2_ld_b = (uint32_t)a.in2_ld * 4u;
+  if (warp < kV6ProducerWarps) {
+    // =========================== PRODUCERS (256 threads) ===========================
+    const int r0 = tid >> 3, cB = tid & 7;          // chunk column cB of rows 4 r0 + i (one 16-byte index load)
+    uint32_t a_off[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = 4 * r0 + i;
+      a_off[i] = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128) + (((uint32_t)cB ^ (uint32_t)(r & 7)) << 4);
+    }
+    const uint32_t in_ld_b = (uint32_t)a.in_ld * EB, in2_ld_b = (uint32_t)a.in2_ld * EB;
     const char* in_b = reinterpret_cast<const char*>(a.in);
     const char* in2_b = reinterpret_cast<const char*>(a.in2);
-    const int grp = tid / kGroupThreads, tg = tid % kGroupThreads;
-    const int r0 = tg >> 3, cB = tg & 7;        // gather: chunk column cB of rows r0 + kRowStep*i
-    const int rI = tid & 127, hI = tid >> 7;    // kernel-map staging: row rI, offsets hI, hI + kProducerThreads/128, ...
-    const uint32_t a_off = (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128) + (((uint32_t)cB ^ (uint32_t)(r0 & 7)) << 4);
-
-    // stage the kernel-map slice of `tile` (only the offsets present in it) into parity buffer `par`
-    auto prepare = [&](int tile, int par) {
-      producer_bar();   // everybody is done reading klist/sidx of the tile that used this parity before
-      if (warp == 0) {  // ordered list of present offsets from the precomputed tile mask
-        int base = 0;
-        for (int w = 0; w < 3; ++w) {
-          const uint32_t bits = __ldg(tmask + 4 * tile + w);
-          if ((bits >> lane) & 1u) klist[par * 96 + base + __popc(bits & ((1u << lane) - 1u))] = (uint8_t)(32 * w + lane);
-          base += __popc(bits);
-        }
-      }
-      producer_bar();
-      const int nact = tile_nact(tile);
-      const int row = tile * kTileM + rI;
-      const uint32_t dst = sidx_u + (uint32_t)(par * kMaxK * kTileM + rI) * 4u;
-      if (row < n_out) {
-        const int32_t* src = a.map + (a.perm ? __ldg(a.perm + row) : row);
-        for (int e = hI; e < nact; e += kProducerThreads / 128)
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (uint32_t)(e * kTileM) * 4u),
-                       "l"(src + (int64_t)klist[par * 96 + e] * a.map_ld)
-                       : "memory");
-      } else {
-        for (int e = hI; e < nact; e += kProducerThreads / 128) sidx[(par * kMaxK + e) * kTileM + rI] = -1;  // rows past the end
-      }
-      cp_async_arrive(bar_idx + 8 * par);
-    };
-
-    // ---- per-thread invariants of the stage writer (kept out of the stage loop: the producers are
-    //      issue-bound, every instruction here is paid once per stage per warp) ----
-    constexpr int NB = (NPAD + kRowStep - 1) / kRowStep;   // weight chunks per thread per stage
-    const float* wrow[NB];
+    constexpr int NB = (NPAD + 31) / 32;            // weight chunks per thread per stage
+    const char* wrow[NB];
     uint32_t b_off[NB];
     bool wok[NB];
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
-      const int n = r0 + kRowStep * i;
+      const int n = r0 + 32 * i;
       wok[i] = n < a.cout && n < NPAD;
-      wrow[i] = p.wt + (int64_t)(wok[i] ? n : 0) * p.ldk;
+      wrow[i] = reinterpret_cast<const char*>(p.wt) + (int64_t)(wok[i] ? n : 0) * p.ldk * EB;
       b_off[i] = (uint32_t)((n >> 3) * 1024 + (n & 7) * 128) + (((uint32_t)cB ^ (uint32_t)(n & 7)) << 4);
     }
-    const bool b_lane = r0 < NPAD;                  // narrow layers: only some threads carry a weight chunk
-    uint32_t slot = 0, phase = 0;
-    uint32_t a_slot = sA_u + a_off, b_slot = sB_u, bar_e = bar_empty, bar_f = bar_full;
-    int turn = 0;   // stage counter modulo kGroups: whose turn it is to write the next stage
-    int issued = 0;                 // stages this thread has written so far (lagged arrival bookkeeping)
-    uint32_t bar_lag = bar_full;    // barrier of the oldest stage whose arrival is still owed
+    const bool b_lane = r0 < NPAD;
+    constexpr int GPCc = GPC < 8 ? GPC : 1;
+    const int e_off = GPC < 8 ? cB / GPCc : 0;      // small Cin: which of the stage's offsets this column belongs to
+    const int cg0 = GPC < 8 ? cB % GPCc : cB;       // channel group inside the offset
 
-    // write this thread's share of one stage: 4 A chunks (rows r0+32i, column cB) + its weight chunk(s)
-    auto emit = [&](const char* base, uint32_t ld_b, const int (&idx)[kRowsPerThread], uint32_t cg_off, bool cg_ok, int kofB) {
-      if (turn == grp) {
-        mbar_wait(bar_e, phase ^ 1);                // the MMAs that read this slot have completed
-#pragma unroll
-        for (int i = 0; i < kRowsPerThread; ++i) {
-          const bool ok = cg_ok && idx[i] >= 0;
-          cp_async16(a_slot + i * (kRowStep * 128), base + (ok ? (uint32_t)idx[i] * ld_b + cg_off : 0u), ok ? 16u : 0u);
-        }
-        if (b_lane) {
-#pragma unroll
-          for (int i = 0; i < NB; ++i) {
-            const bool ok = kofB >= 0 && wok[i];
-            cp_async16(b_slot + b_off[i], ok ? wrow[i] + kofB : p.wt, ok ? 16u : 0u);
-          }
-        }
-        if (kArriveLag == 0) {
-          cp_async_arrive(bar_f);                   // fires when this thread's copies of the stage have landed
+    // ---- cursor over the stages of this CTA's tiles ----
+    int tile = blockIdx.x, it_tile = 0;
+    int nact = 0, m = 0, nst = 0;                   // present offsets, current stage, stages of the tile
+    int e = 0, sub = 0;                             // large Cin: offset entry and sub-stage
+    uint32_t sx = 0;                                // shared byte address of this thread's int4 in entry 0
+    const uint8_t* kl = klist;
+    // parameters of the stage about to be issued
+    int idx[4] = {-1, -1, -1, -1};
+    const char* base = in_b;
+    uint32_t ld_b = in_ld_b;
+    bool okc = false, bok = false;
+    uint32_t wofs = 0;
+
+    auto lds4 = [&](uint32_t addr) {
+      asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(idx[0]), "=r"(idx[1]), "=r"(idx[2]), "=r"(idx[3])
+                   : "r"(addr));
+    };
+    // fetch the parameters of stage m of the current tile
+    auto fetch = [&]() {
+      if (GPC < 8) {
+        const int nmap = (nact + EPS - 1) / EPS;
+        if (m < nmap) {
+          const int ee = m * EPS + e_off;
+          const bool e_ok = ee < nact;
+          lds4(sx + (uint32_t)(e_ok ? ee : 0) * kV6EntryBytes);
+          base = in_b + cg0 * 16; ld_b = in_ld_b;
+          okc = e_ok && cg0 < gpk; bok = e_ok;
+          wofs = (uint32_t)((int)kl[e_ok ? ee : 0] * GPCc + cg0) * 16u;
         } else {
-          cp_async_commit();
-          if (++issued > kArriveLag) {              // the stage issued kArriveLag stages ago has landed by now
-            cp_async_wait<kArriveLag>();
-            fence_proxy_async();                    // generic-proxy smem writes -> visible to the tensor core
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_lag);
-            bar_lag = (bar_lag == bar_full + 8 * (S - 1)) ? bar_full : bar_lag + 8;
-          }
+          const int cg = cB + 8 * (m - nmap);
+          lds4(sx + (uint32_t)nact * kV6EntryBytes);
+          base = in2_b + cg * 16; ld_b = in2_ld_b;
+          okc = cg < gpk2; bok = okc;
+          wofs = (uint32_t)(K * GPCc + cg) * 16u;
         }
-      }
-      if (++turn == kGroups) turn = 0;
-      if (++slot == S) {
-        slot = 0; phase ^= 1;
-        a_slot = sA_u + a_off; b_slot = sB_u; bar_e = bar_empty; bar_f = bar_full;
       } else {
-        a_slot += kAStageBytes; b_slot += kBStageBytes; bar_e += 8; bar_f += 8;
+        // entry e (< nact: kernel offset klist[e]; == nact: the fused 1x1 term on the tile's own rows)
+        if (sub == 0) lds4(sx + (uint32_t)e * kV6EntryBytes);
+        const int cg = cB + 8 * sub;
+        const bool self = e >= nact;
+        base = (self ? in2_b : in_b) + cg * 16; ld_b = self ? in2_ld_b : in_ld_b;
+        okc = cg < (self ? gpk2 : gpk); bok = okc;
+        wofs = (uint32_t)((self ? K : (int)kl[e]) * GP + cg) * 16u;
       }
     };
+    // make `tile` current (skipping tiles without stages); false when the CTA has no tile left
+    auto open_tile = [&]() -> bool {
+      for (;;) {
+        if (tile >= ntiles) return false;
+        const int par = it_tile % NP;
+        mbar_wait(bar_idxf + 8 * par, (it_tile / NP) & 1);
+        nact = snact[par];
+        nst = tile_stages(nact);
+        sx = sidx_u + (uint32_t)par * par_bytes + (uint32_t)r0 * 16u;
+        kl = klist + par * kl_stride;
+        m = 0; e = 0; sub = 0;
+        if (nst > 0) { fetch(); return true; }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_idxe + 8 * par);
+        tile += gstep; ++it_tile;
+      }
+    };
+    // step to the next stage; false when the CTA is out of work
+    auto advance = [&]() -> bool {
+      ++m;
+      if (m < nst) {
+        if (GPC >= 8) {
+          const int lim = e < nact ? SPE : st2;
+          if (++sub == lim) { sub = 0; ++e; }
+        }
+        fetch();
+        return true;
+      }
+      __syncwarp();                                   // every lane holds its indices in registers by now
+      if (lane == 0) mbar_arrive(bar_idxe + 8 * (it_tile % NP));
+      tile += gstep; ++it_tile;
+      return open_tile();
+    };
 
-    int it_tile = 0;
-    if ((int)blockIdx.x < ntiles) prepare(blockIdx.x, 0);
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it_tile) {
-      const int par = it_tile & 1;
-      const int next = tile + gridDim.x;
-      if (next < ntiles) prepare(next, par ^ 1);   // one tile ahead: its latency hides behind this tile's gathers
-      const int nact = tile_nact(tile);
-      mbar_wait(bar_idx + 8 * par, (it_tile >> 1) & 1);
-      const int32_t* sx = sidx + par * kMaxK * kTileM + r0;   // [e][128] compacted by present offset
-      const uint8_t* kl = klist + par * 96;
-      int idx[kRowsPerThread];
-      if (GPC < 8) {
-        // small Cin: EPS offsets per stage, GPC chunks each; this thread's chunk column picks offset e_off
-        constexpr int GPCc = GPC < 8 ? GPC : 1;
-        const int e_off = cB / GPCc, cg = cB % GPCc;
-        const bool cg_ok = cg < gpk;
-        const int nst_map = (nact + EPS - 1) / EPS;
-        for (int st = 0, e = e_off; st < nst_map; ++st, e += EPS) {
-          const bool e_ok = e < nact && turn == grp;   // another group's stage: nothing to look up
-          const int32_t* sk = sx + (e_ok ? e : 0) * kTileM;
+    bool more = open_tile();
+    uint32_t phase = 0;
+    while (more) {
 #pragma unroll
-          for (int i = 0; i < kRowsPerThread; ++i) idx[i] = e_ok ? sk[kRowStep * i] : -1;
-          emit(in_b, in_ld_b, idx, (uint32_t)cg * 16u, cg_ok, e_ok ? ((int)kl[e] * GPCc + cg) * 4 : -1);
-        }
-      } else {
-        // large Cin: one offset per SPE stages, the neighbour rows are looked up once per offset
-        for (int e = 0; e < nact; ++e) {
-          const int32_t* sk = sx + e * kTileM;
+      for (int s = 0; s < S; ++s) {
+        if (more) {
+          mbar_wait(bar_empty + 8 * s, phase ^ 1);    // the MMAs that read slot s have completed
+          const uint32_t dstA = sA_u + (uint32_t)s * kAStageBytes;
 #pragma unroll
-          for (int i = 0; i < kRowsPerThread; ++i) idx[i] = sk[kRowStep * i];
-          const int kbase = (int)kl[e] * GP;
-          for (int sub = 0, cg = cB; sub < SPE; ++sub, cg += 8)
-            emit(in_b, in_ld_b, idx, (uint32_t)cg * 16u, cg < gpk, (kbase + cg) * 4);
+          for (int i = 0; i < 4; ++i) {
+            const bool ok = okc && idx[i] >= 0;
+            const uint32_t row = (uint32_t)(idx[i] < 0 ? 0 : idx[i]);
+            cp_async16_or_zero<SPS_V6_A_CG != 0>(dstA + a_off[i], base + (uint64_t)row * ld_b, !ok);
+          }
+          if (b_lane) {
+#pragma unroll
+            for (int i = 0; i < NB; ++i)
+              cp_async16_or_zero<SPS_V6_B_CG != 0>(sB_u + (uint32_t)s * kBStageBytes + b_off[i], wrow[i] + wofs, !(bok && wok[i]));
+          }
+          cp_async_arrive(bar_full + 8 * s);          // fires when this thread's copies of the stage have landed
+          more = advance();
         }
       }
-      if (st2 > 0) {  // fused 1x1 term: identity gather from in2
-#pragma unroll
-        for (int i = 0; i < kRowsPerThread; ++i) {
-          const int rw = tile * kTileM + r0 + kRowStep * i;
-          idx[i] = rw < n_out ? (a.perm ? __ldg(a.perm + rw) : rw) : -1;
-        }
-        const int kbase2 = K * GP;
-        for (int s2 = 0, cg = cB; s2 < st2; ++s2, cg += 8)
-          emit(in2_b, in2_ld_b, idx, (uint32_t)cg * 16u, cg < gpk2, cg < gpk2 ? (kbase2 + cg) * 4 : -1);
-      }
+      phase ^= 1;
     }
     cp_async_wait<0>();
-    if (kArriveLag > 0) {           // flush the arrivals still owed for the last stages
-      fence_proxy_async();
-      __syncwarp();
-      const int owed = issued < kArriveLag ? issued : kArriveLag;
-      for (int i = 0; i < owed; ++i) {
-        if (lane == 0) mbar_arrive(bar_lag);
-        bar_lag = (bar_lag == bar_full + 8 * (S - 1)) ? bar_full : bar_lag + 8;
-      }
+  } else if (warp == kV6LoaderWarp) {
+    // =========================== LOADER (one warp, one tile ahead) ===========================
+    int it = 0;
+    const bool map_vec = ((reinterpret_cast<uintptr_t>(a.map) & 15) == 0) && ((a.map_ld & 3) == 0);
+    // the tile mask is the head of every tile's dependency chain: keep the NEXT tile's words in flight
+    uint32_t mw[3] = {0u, 0u, 0u};
+    if ((int)blockIdx.x < ntiles) {
+#pragma unroll
+      for (int w = 0; w < 3; ++w) mw[w] = __ldg(tmask + 4 * blockIdx.x + w);
     }
-  } else if (warp == kMmaWarp) {
+    for (int tile = blockIdx.x; tile < ntiles; tile += gstep, ++it) {
+      const int par = it % NP;
+      const uint32_t cur[3] = {mw[0], mw[1], mw[2]};
+      if (tile + gstep < ntiles) {
+#pragma unroll
+        for (int w = 0; w < 3; ++w) mw[w] = __ldg(tmask + 4 * (tile + gstep) + w);
+      }
+      mbar_wait(bar_idxe + 8 * par, ((it / NP) & 1) ^ 1);     // producers are done with this buffer
+      uint8_t* klp = klist + par * kl_stride;
+      int nact = 0;
+#pragma unroll
+      for (int w = 0; w < 3; ++w) {
+        const uint32_t bits = cur[w];
+        if ((bits >> lane) & 1u) klp[nact + __popc(bits & ((1u << lane) - 1u))] = (uint8_t)(32 * w + lane);
+        nact += __popc(bits);
+      }
+      if (lane == 0) snact[par] = nact;
+      __syncwarp();
+      // entries are 128 row indices in tile order; lane owns rows 4 lane .. 4 lane + 3 (one 16-byte chunk per entry)
+      const uint32_t dst = sidx_u + (uint32_t)par * par_bytes + (uint32_t)lane * 16u;
+      if (a.tile_slices) {
+        // the level's pass already gathered this tile's slice (entries 0..nact, the last one = own rows)
+        const char* src = reinterpret_cast<const char*>(a.tile_slices + (int64_t)tile * (SPS_TILE_SLICE_ENTRIES * kTileM)) + lane * 16;
+        for (int e = 0; e <= nact; ++e)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)e * kV6EntryBytes),
+                       "l"(src + (size_t)e * kV6EntryBytes)
+                       : "memory");
+      } else if (!a.perm && map_vec && tile * kTileM + kTileM <= n_out) {
+        // physical row order, full tile: the slice of map[k] is contiguous -> one 16-byte copy per lane and entry
+        const int row0 = tile * kTileM + 4 * lane;
+        asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)nact * kV6EntryBytes), "r"(row0),
+                     "r"(row0 + 1), "r"(row0 + 2), "r"(row0 + 3)
+                     : "memory");
+        const int32_t* src = a.map + row0;
+        for (int e = 0; e < nact; ++e)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)e * kV6EntryBytes),
+                       "l"(src + (int64_t)klp[e] * a.map_ld)
+                       : "memory");
+      } else {
+        const int32_t* src[4];
+        bool rok[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int prow = tile * kTileM + 4 * lane + i;
+          rok[i] = prow < n_out;
+          const int row = rok[i] ? (a.perm ? __ldg(a.perm + prow) : prow) : 0;
+          src[i] = a.map + row;
+          asm volatile("st.shared.s32 [%0], %1;" ::"r"(dst + (uint32_t)nact * kV6EntryBytes + 4u * i), "r"(rok[i] ? row : -1) : "memory");
+        }
+        for (int e = 0; e < nact; ++e) {
+          const int64_t koff = (int64_t)klp[e] * a.map_ld;
+          const uint32_t d = dst + (uint32_t)e * kV6EntryBytes;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (rok[i]) cp_async4(d + 4u * i, src[i] + koff);
+            else asm volatile("st.shared.s32 [%0], %1;" ::"r"(d + 4u * i), "r"(-1) : "memory");
+          }
+        }
+      }
+      cp_async_arrive(bar_idxf + 8 * par);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_idxf + 8 * par);         // orders the plain shared stores of the whole warp
+    }
+    cp_async_wait<0>();
+  } else if (warp == kV6MmaWarp) {
     // =========================== MMA ISSUER (one lane) ===========================
-    const uint32_t idesc = make_idesc_tf32(NPAD);
+    const uint32_t idesc = kHalf ? make_idesc_f16(NPAD) : make_idesc_tf32(NPAD);
     uint32_t gs = 0;
-    int n_acc = 0;   // tiles that actually accumulate (both sides count the same way)
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int nstages = tile_stages(tile_nact(tile));
-      if (nstages == 0) continue;   // nothing to accumulate: the epilogue uses zeros
+    int n_acc = 0;
+    int tile = blockIdx.x;
+    int nact_next = tile < ntiles ? tile_nact(tile) : 0;
+    for (; tile < ntiles; tile += gstep) {
+      const int nstages = tile_stages(nact_next);
+      if (tile + gstep < ntiles) nact_next = tile_nact(tile + gstep);   // in flight behind this tile's stages
+      if (nstages == 0) continue;
       const int b = n_acc & 1;
-      mbar_wait(bar_acce + 8 * b, ((n_acc >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+      mbar_wait(bar_acce + 8 * b, ((n_acc >> 1) & 1) ^ 1);
       ++n_acc;
       tc_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)(b * NPAD);
       for (int it = 0; it < nstages; ++it, ++gs) {
         const uint32_t slot = gs % S;
         mbar_wait(bar_full + 8 * slot, (gs / S) & 1);
-#ifdef SPS_MMA_PROXY_FENCE
-        fence_proxy_async();   // not needed: completion of cp.async through the mbarrier orders the writes (as CUTLASS)
-#endif
         tc_fence_after();
         if (lane == 0) {
           const uint64_t adesc = make_smem_desc(sA_u + slot * kAStageBytes);
           const uint64_t bdesc = make_smem_desc(sB_u + slot * kBStageBytes);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)  // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle atom
-            umma_tf32(tacc, adesc + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (it | j) ? 1u : 0u);
+          for (int j = 0; j < 4; ++j) {   // 4 x 32 bytes of K (8 tf32 / 16 fp16) inside the 128-byte swizzle atom
+            if (kHalf) umma_f16(tacc, adesc + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (it | j) ? 1u : 0u);
+            else umma_tf32(tacc, adesc + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (it | j) ? 1u : 0u);
+          }
           umma_commit(bar_empty + 8 * slot);
           if (it == nstages - 1) umma_commit(bar_accf + 8 * b);
         }
@@ -316,15 +411,24 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_conv_umma(const sps_conv_arg
     }
   } else {
     // =========================== EPILOGUE (4 warps = 128 TMEM lanes) ===========================
-    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int q = warp & 3;
     const int r = q * 32 + lane;
+    const int cout = a.cout;
+    const bool res_vec = a.res && ((reinterpret_cast<uintptr_t>(a.res) & 15) == 0) && ((a.res_ld & 3) == 0);
     int n_acc = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int nstages = tile_stages(tile_nact(tile));
+    int tile = blockIdx.x;
+    int nact_next = 0, row_next = -1;
+    auto look = [&](int t) {
+      nact_next = tile_nact(t);
+      const int prow = t * kTileM + r;
+      row_next = prow < n_out ? (a.perm ? __ldg(a.perm + prow) : prow) : -1;
+    };
+    if (tile < ntiles) look(tile);
+    for (; tile < ntiles; tile += gstep) {
+      const int nstages = tile_stages(nact_next);
+      const int row = row_next;
+      if (tile + gstep < ntiles) look(tile + gstep);
       const int b = n_acc & 1;
-      const int prow = tile * kTileM + r;
-      const bool row_ok = prow < n_out;
-      const int row = row_ok && a.perm ? __ldg(a.perm + prow) : prow;   // output row this tile lane stands for
       float acc[NPAD];
       if (nstages > 0) {
         mbar_wait(bar_accf + 8 * b, (n_acc >> 1) & 1);
@@ -335,21 +439,39 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_conv_umma(const sps_conv_arg
         for (int cb = 0; cb < NPAD / 8; ++cb) tmem_ld8(taddr + cb * 8, acc + cb * 8);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         tc_fence_before();
-        mbar_arrive(bar_acce + 8 * b);      // accumulator may be overwritten by the tile after next
+        mbar_arrive(bar_acce + 8 * b);
       } else {
 #pragma unroll
         for (int c = 0; c < NPAD; ++c) acc[c] = 0.f;
       }
-      if (!row_ok) continue;
-      const int cout = a.cout;
+      if (row < 0) continue;
 #pragma unroll
-      for (int c = 0; c < NPAD; ++c)
+      for (int c = 0; c < NPAD; c += 8)
         if (c < cout) {
-          float v = acc[c];
-          if (a.shift) v += __ldg(a.shift + c);
-          if (a.res) v += __ldg(a.res + (int64_t)row * a.res_ld + c);
-          if (a.relu) v = fmaxf(v, 0.f);
-          acc[c] = v;
+          float rv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (a.res) {
+            if (kHalf) {
+              const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.res) + (int64_t)row * a.res_ld + c));
+              const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); rv[2 * j] = f.x; rv[2 * j + 1] = f.y; }
+            } else {
+              const float* resp = a.res + (int64_t)row * a.res_ld + c;
+              if (res_vec) {
+                const float4 r0 = __ldg(reinterpret_cast<const float4*>(resp)), r1 = __ldg(reinterpret_cast<const float4*>(resp + 4));
+                rv[0] = r0.x; rv[1] = r0.y; rv[2] = r0.z; rv[3] = r0.w; rv[4] = r1.x; rv[5] = r1.y; rv[6] = r1.z; rv[7] = r1.w;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rv[j] = __ldg(resp + j);
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float v = acc[c + j] + sshift[c + j] + rv[j];
+            if (a.relu) v = fmaxf(v, 0.f);
+            acc[c + j] = v;
+          }
         }
       if (a.head_out) {
         float s = a.head_b;
@@ -358,13 +480,11 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_conv_umma(const sps_conv_arg
         a.head_out[row] = s;
       }
       if (a.out) {
-        float* o = a.out + (int64_t)row * a.out_ld;
 #pragma unroll
-        for (int c = 0; c < NPAD; c += 4)
+        for (int c = 0; c < NPAD; c += 8)
           if (c < cout) {
-            float4 v = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
-            if (p.round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
-            *reinterpret_cast<float4*>(o + c) = v;
+            const float v8[8] = {acc[c], acc[c + 1], acc[c + 2], acc[c + 3], acc[c + 4], acc[c + 5], acc[c + 6], acc[c + 7]};
+            store_row8(a.out + (kHalf ? c / 2 : c), a.out_ld, row, v8, kHalf ? kStoreF16 : (p.round_out ? kStoreTF32 : kStoreF32));
           }
       }
     }
@@ -372,26 +492,62 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_conv_umma(const sps_conv_arg
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp)
+  if (warp == kV6MmaWarp)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols)
                  : "memory");
 }
 
-template <int NPAD, int GPC>
-static int launch_umma(const sps_conv_args& a, const UmmaParams& p, cudaStream_t st) {
-  const size_t smem = UmmaCfg<NPAD>::smem;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SPS_CUDA_CHECK(
-        cudaFuncSetAttribute(k_conv_umma<NPAD, GPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+template <int NPAD, int GPC, typename T>
+static int launch_umma6(const sps_conv_args& a, const UmmaParams& p, cudaStream_t st) {
+  const size_t smem = V6Cfg<NPAD>::smem;
+  static unsigned long long attr_done = 0;   // bit per device: the opt-in is per device and per kernel
+  SPS_CUDA_CHECK(ensure_dynamic_smem(k_conv_umma6<NPAD, GPC, T>, smem, &attr_done));
   int64_t tiles = (a.n_out_max + kTileM - 1) / kTileM;
   if (tiles < 1) tiles = 1;
   const int grid = (int)(tiles < 148 ? tiles : 148);
-  k_conv_umma<NPAD, GPC><<<grid, kCtaThreads, smem, st>>>(a, p);
+  k_conv_umma6<NPAD, GPC, T><<<grid, kV6Threads, smem, st>>>(a, p);
   SPS_CUDA_CHECK(cudaGetLastError());
   return SPS_OK;
+}
+
+template <int NPAD, typename T>
+static int launch_umma6_n(const sps_conv_args& a, const UmmaParams& p, cudaStream_t st) {
+  constexpr bool kHalf = sizeof(T) == 2;
+  const int gp = padded_groups_of((a.cin * (int)sizeof(T)) >> 4, kHalf);
+  if (kHalf && gp == 1) return launch_umma6<NPAD, kHalf ? 1 : 2, T>(a, p, st);
+  if (gp == 2) return launch_umma6<NPAD, 2, T>(a, p, st);
+  if (gp == 4) return launch_umma6<NPAD, 4, T>(a, p, st);
+  return launch_umma6<NPAD, 8, T>(a, p, st);
+}
+
+template <typename T>
+static int conv_umma6_t(const sps_conv_args& a, const UmmaParams& p, cudaStream_t st) {
+  switch (a.cout) {
+    case 8:
+    case 16: return launch_umma6_n<16, T>(a, p, st);
+    case 32: return launch_umma6_n<32, T>(a, p, st);
+    case 64: return launch_umma6_n<64, T>(a, p, st);
+    default: return SPS_ERR_UNSUPPORTED;
+  }
+}
+
+int conv_umma(const sps_conv_args& a, cudaStream_t st) {
+  UmmaParams p;
+  p.wt = a.weight_kmajor;
+  p.ldk = a.kmajor_ld;
+  p.round_out = a.round_out;
+  return a.io_dtype == SPS_IO_F16 ? conv_umma6_t<__half>(a, p, st) : conv_umma6_t<float>(a, p, st);
+}
+
+// fp32 rows, TF32 operands
+bool conv_umma_supports(const sps_conv_args& a) {
+  if (a.io_dtype != SPS_IO_F32 || a.mode != SPS_CONV_NBR || !a.map || !a.weight_kmajor || !a.tile_mask) return false;
+  if (a.K < 1 || a.K > kMaxK) return false;
+  if (a.cin < 4 || (a.cin & 3) || (a.in_ld & 3)) return false;
+  if (a.in2 && ((a.cin2 & 3) || (a.in2_ld & 3))) return false;
+  if (!(a.cout == 8 || a.cout == 16 || a.cout == 32 || a.cout == 64)) return false;
+  if (a.kmajor_ld & 3) return false;
+  return true;
 }
 
 // Per-tile (128 consecutive output rows) bitmask of the kernel offsets that have at least one
@@ -416,67 +572,38 @@ k_tile_masks(const int32_t* __restrict__ map, int64_t ld, int K, const int32_t* 
   }
 }
 
-bool conv_umma_supports(const sps_conv_args& a) {
-  if (a.mode != SPS_CONV_NBR || !a.map || !a.weight_kmajor || !a.tile_mask) return false;
+// fp16 storage: every layer of the network fits (channel counts are multiples of 8, rows 16-byte aligned)
+bool conv_umma_f16_supports(const sps_conv_args& a) {
+  if (a.io_dtype != SPS_IO_F16 || a.mode != SPS_CONV_NBR || !a.map || !a.weight_kmajor || !a.tile_mask) return false;
   if (a.K < 1 || a.K > kMaxK) return false;
-  if (a.cin < 4 || (a.cin & 3) || (a.in_ld & 3)) return false;
-  if (a.in2 && ((a.cin2 & 3) || (a.in2_ld & 3))) return false;
+  if (a.cin < 8 || (a.cin & 7) || (a.in_ld & 7)) return false;
+  if (a.in2 && ((a.cin2 & 7) || (a.in2_ld & 7))) return false;
+  if (a.res && (a.res_ld & 7)) return false;
+  if (a.out && (a.out_ld & 7)) return false;
   if (!(a.cout == 8 || a.cout == 16 || a.cout == 32 || a.cout == 64)) return false;
-  if (a.kmajor_ld & 3) return false;
+  if (a.kmajor_ld & 7) return false;
   return true;
-}
-
-template <int NPAD>
-static int launch_umma_n(const sps_conv_args& a, const UmmaParams& p, cudaStream_t st) {
-  const int gp = padded_groups(a.cin);
-  if (gp == 2) return launch_umma<NPAD, 2>(a, p, st);
-  if (gp == 4) return launch_umma<NPAD, 4>(a, p, st);
-  return launch_umma<NPAD, 8>(a, p, st);
-}
-
-bool conv_umma_tma_supports(const sps_conv_args& a);
-int conv_umma_tma(const sps_conv_args& a, const UmmaParams& p, cudaStream_t st);
-int conv_umma6(const sps_conv_args& a, const UmmaParams& p, cudaStream_t st);
-static int g_variant = 6;   // 6: k_conv_umma6 (loader warp, static-slot producers); 5: k_conv_umma
-static int g_use_tma = 0;   // 1: wide layers gather through TMA tile::gather4 (measured 3x slower than cp.async producers: 128-byte boxes)
-
-// true when the selected kernel generation gathers from the dense map itself (generation 5, TMA variant): the map
-// builder must then keep the dense tables complete (maps.cu writes only present entries otherwise)
-bool conv_needs_dense_maps() {
-  static const char* env = getenv("SPS_UMMA_VARIANT");
-  static const int env_variant = env ? atoi(env) : 0;
-  return (env_variant ? env_variant : g_variant) != 6 || g_use_tma != 0;
-}
-
-int conv_umma(const sps_conv_args& a, cudaStream_t st) {
-  UmmaParams p;
-  p.wt = a.weight_kmajor;
-  p.ldk = a.kmajor_ld;
-  p.round_out = a.round_out;
-  if (a.io_dtype == SPS_IO_F16) return conv_umma6(a, p, st);   // fp16 rows: generation 6 only
-  if (g_use_tma && conv_umma_tma_supports(a)) return conv_umma_tma(a, p, st);
-  static const char* env = getenv("SPS_UMMA_VARIANT");   // A/B runs without touching the host code
-  static const int env_variant = env ? atoi(env) : 0;
-  if ((env_variant ? env_variant : g_variant) == 6) return conv_umma6(a, p, st);
-  switch (a.cout) {
-    case 8:
-    case 16: return launch_umma_n<16>(a, p, st);
-    case 32: return launch_umma_n<32>(a, p, st);
-    case 64: return launch_umma_n<64>(a, p, st);
-    default: return SPS_ERR_UNSUPPORTED;
-  }
 }
 
 }  // namespace sps
 
-extern "C" int sps_set_umma_variant(int v) {
-  if (v != 5 && v != 6) return SPS_ERR_BAD_ARG;
-  sps::g_variant = v;
-  return SPS_OK;
+// fp16 twin of sps_conv_pack_kmajor: ME-layout weights [K][cin][cout] (+ optional 1x1 term [cin2][cout]) ->
+// K-major __half [cout][ld]; per kernel offset padded_groups_of(cin/8) * 8 halves, the 1x1 term padded to 64.
+extern "C" int64_t sps_conv_kmajor_ld_f16(int K, int cin, int cin2) {
+  return (int64_t)K * sps::padded_groups_of((cin + 7) >> 3, true) * 8 + ((cin2 + 63) & ~63);
 }
-
-extern "C" int sps_set_tma_gather(int on) {
-  sps::g_use_tma = on != 0;
+extern "C" int sps_conv_pack_kmajor_f16(const float* w, int K, int cin, int cout, const float* w2, int cin2, void* out_) {
+  if (!w || !out_ || K < 1 || cin < 1 || cout < 1 || (w2 == nullptr) != (cin2 == 0)) return SPS_ERR_BAD_ARG;
+  __half* out = static_cast<__half*>(out_);
+  const int64_t ldk = sps_conv_kmajor_ld_f16(K, cin, cin2);
+  const int cpad = sps::padded_groups_of((cin + 7) >> 3, true) * 8;
+  for (int n = 0; n < cout; ++n) {
+    __half* row = out + (int64_t)n * ldk;
+    for (int64_t i = 0; i < ldk; ++i) row[i] = __float2half_rn(0.f);
+    for (int k = 0; k < K; ++k)
+      for (int ci = 0; ci < cin; ++ci) row[(int64_t)k * cpad + ci] = __float2half_rn(w[((int64_t)k * cin + ci) * cout + n]);
+    for (int ci = 0; ci < cin2; ++ci) row[(int64_t)K * cpad + ci] = __float2half_rn(w2[(int64_t)ci * cout + n]);
+  }
   return SPS_OK;
 }
 

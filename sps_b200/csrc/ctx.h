@@ -1,5 +1,9 @@
-// Host-side context: carve-up of the caller's workspace arena (no device allocation here).
+// Host-side context: carve-up of the caller's workspace arena (no device allocation here), plus every
+// piece of mutable host state of the library (arithmetic mode, processing-order mode, launch counter,
+// stage timers): there are no process-wide switches, two host threads may drive two contexts freely.
 #pragma once
+#include <string>
+#include <vector>
 #include "common.cuh"
 
 // 8-bit radix passes of the shape sort: 4 = full 29-bit key; 3 = 20-bit key without the centre and corner offsets
@@ -14,6 +18,17 @@ struct sps_ctx {
   bool have_l0 = false, have_maps = false, have_nbr5 = false, have_perm = false, have_slices = false;
   bool dense_maps = true;    // false after a fused forward that stored only the present entries of the sorted levels' tables
   int first_sorted = 0, last_sorted = -1;   // levels whose 3^4 convs may visit rows in pattern-sorted order
+
+  // ---- settings (sps_ctx_set_conv_backend / sps_ctx_set_pattern_sort) and per-forward state ----
+  int backend = SPS_BACKEND_AUTO;
+  int pattern_sort = 1;      // 0 never, 1 for inputs of >= 400 000 rows, 2 always
+  bool run_half = false;     // the forward being enqueued stores its activations as fp16
+  int forward_launches = 0;  // kernels enqueued by the last fused forward
+  // stage timers (sps_profile_enable): CUDA events recorded on the launch stream
+  bool prof = false;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<std::string> prof_names;
+  size_t prof_used = 0;
 
   char* base = nullptr;
   size_t bytes = 0;
@@ -52,10 +67,14 @@ struct sps_ctx {
   int32_t* nbr5 = nullptr;                     // [125][ld]
   uint32_t* tmask3[SPS_NUM_LEVELS] = {};       // [L] [tiles][4] present-offset masks of nbr3 per 128-row tile
 
-  // feature buffers (fp32, row-major, upper bound max_points rows)
+  // feature buffers (row-major, upper bound max_points rows; widths in fp32 elements, so that every storage mode fits)
   enum Buf { CAT8, E1, H1, CAT7, E2, H2, CAT6, E3, H3, CAT5, E4, H4, B4, H5, B5, H6, B6, H7, B7, H8,
              FEAT0, LOGITS, NBUF };
   float* buf[NBUF] = {};
+
+  ~sps_ctx() {
+    for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
+  }
 };
 
 namespace sps {
@@ -74,4 +93,8 @@ constexpr int kCatLd[4] = {16, SPS_CAT_PAD ? 32 : 24, SPS_CAT_PAD ? 64 : 48, SPS
 constexpr int kBufWidth[sps_ctx::NBUF] = {16, 8, 8, kCatLd[1], 8, 16, kCatLd[2], 16, 32, kCatLd[3], 32, 64, 64, 64, 64, 32, 32,
                                           16, 16, 8, 1, 1};
 constexpr int kScanBlock = 1024;
+
+// arithmetic mode of a context (see sps_ctx_set_conv_backend)
+inline bool ctx_half_storage(const sps_ctx* c) { return c->backend == SPS_BACKEND_AUTO || c->backend == SPS_BACKEND_F16; }
+
 }

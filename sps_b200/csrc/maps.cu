@@ -779,16 +779,16 @@ int voxelize_impl(sps_ctx* ctx, const float* d_points, int64_t n, const int32_t*
   else k_set_i32<<<1, 1, 0, st>>>(ctx->n_dev, (int32_t)n);
   const int nblk = cdiv(n > 0 ? n : 1, kScanBlock);
   k_table_clear<<<grid_for(table_capacity(n), 256), 256, 0, st>>>(ctx->table, ctx->n_dev);
-  prof_mark("vox.clear", st);
+  prof_mark(ctx, "vox.clear", st);
   k_insert_points<<<grid_for(n, 256), 256, 0, st>>>(d_points, ld_points, ctx->n_dev, voxel_size, ctx->table,
                                                      ctx->slot_of, ctx->status);
-  prof_mark("vox.insert", st);
+  prof_mark(ctx, "vox.insert", st);
   k_first_rank<<<nblk, kScanBlock, 0, st>>>(ctx->table, ctx->slot_of, ctx->n_dev, ctx->rank, ctx->block_sums,
                                             ctx->ticket, ctx->counts + 0, nullptr, 0, nullptr);
-  prof_mark("vox.rank", st);
+  prof_mark(ctx, "vox.rank", st);
   k_assign_points<<<grid_for(n, 256), 256, 0, st>>>(ctx->table, ctx->slot_of, ctx->n_dev, ctx->rank,
                                                      ctx->block_sums, ctx->keys[0], ctx->inv);
-  prof_mark("vox.assign", st);
+  prof_mark(ctx, "vox.assign", st);
   SPS_CUDA_CHECK(cudaGetLastError());
   ctx->have_l0 = true;
   return SPS_OK;
@@ -802,11 +802,9 @@ extern "C" int sps_voxelize(sps_ctx* ctx, const float* d_points, int64_t n, int6
 
 namespace sps {
 int build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st);
-bool conv_needs_dense_maps();
-int conv_backend();
-static inline bool conv_half_off() { return conv_backend() == 1; }   // exact-fp32 mode gathers from the dense maps (CUDA-core kernels)
+// exact-fp32 mode gathers from the dense maps (generic CUDA-core kernels)
+static inline bool needs_dense_maps(const sps_ctx* ctx) { return ctx->backend == SPS_BACKEND_FP32; }
 
-static int g_pattern_sort = 1;
 #ifndef SPS_TILE_SLICES
 #define SPS_TILE_SLICES 1
 #endif
@@ -823,7 +821,7 @@ constexpr int64_t kMinRowsForSort = 400000;   // small inputs (single scans) are
 
 // perm[L] = voxel rows of level L sorted by neighbourhood-shape key; ptmask[L] = tile masks in that order
 static int pattern_order(sps_ctx* ctx, int L, cudaStream_t st) {
-  if (!g_pattern_sort || L < kFirstSortedLevel || L > kLastSortedLevel || (g_pattern_sort == 1 && ctx->n < kMinRowsForSort)) return SPS_OK;
+  if (!ctx->pattern_sort || L < kFirstSortedLevel || L > kLastSortedLevel || (ctx->pattern_sort == 1 && ctx->n < kMinRowsForSort)) return SPS_OK;
   const int64_t n = ctx->n > 0 ? ctx->n : 1;
   const int nb_max = cdiv(n, kSortBlock);
   const int hist_n = 256 * nb_max;
@@ -844,19 +842,14 @@ static int pattern_order(sps_ctx* ctx, int L, cudaStream_t st) {
   }
   static const char* nm_sort[5] = {"sort.L0", "sort.L1", "sort.L2", "sort.L3", "sort.L4"};
   static const char* nm_slice[5] = {"slices.L0", "slices.L1", "slices.L2", "slices.L3", "slices.L4"};
-  prof_mark(nm_sort[L], st);
+  prof_mark(ctx, nm_sort[L], st);
   k_tile_masks_perm<<<grid_for(n / 128 + 1, 1, 148 * 16), 128, 0, st>>>(ctx->vmask, ctx->ld, ctx->perm[L], cnt,
                                                                        ctx->ptmask[L], ctx->nbr3[L],
                                                                        g_tile_slices && ctx->tslice[L] ? ctx->tslice[L] : nullptr);
-  prof_mark(nm_slice[L], st);
+  prof_mark(ctx, nm_slice[L], st);
   SPS_CUDA_CHECK(cudaGetLastError());
   return SPS_OK;
 }
-}
-extern "C" int sps_set_pattern_sort(int mode) {
-  if (mode < 0 || mode > 2) return SPS_ERR_BAD_ARG;
-  sps::g_pattern_sort = mode;   // 0 off, 1 on for inputs of >= 400k rows (default), 2 always
-  return SPS_OK;
 }
 extern "C" int sps_build_maps(sps_ctx* ctx, void* stream_) {
   return build_maps_impl(ctx, nullptr, (cudaStream_t)stream_);
@@ -880,7 +873,7 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
                                                     ctx->cells, ctx->occ);
   };
   build_blocks(0);
-  prof_mark("blocks.L0", st);
+  prof_mark(ctx, "blocks.L0", st);
   if (c0) {
     if (c0->feat)   // per-voxel features: gather them through the block table
       k_conv0_blk<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->table, ctx->cells, c0->feat,
@@ -888,11 +881,11 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
     else            // one constant feature (SPSModel.forward): presence bits only
       k_conv0_const<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->table, ctx->occ, c0->cfeat,
                                                        c0->w, c0->shift, c0->round_out, c0->out, c0->out_ld);
-    prof_mark("conv0+kmap5", st);
+    prof_mark(ctx, "conv0+kmap5", st);
   } else {
     k_kernel_map_blk<5, 1><<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->table, ctx->cells, ctx->occ, 0,
                                                               ctx->nbr5, ctx->ld, nullptr, nullptr);
-    prof_mark("kmap5.L0", st);
+    prof_mark(ctx, "kmap5.L0", st);
   }
   ctx->have_nbr5 = c0 == nullptr;
   const size_t mask_bytes = (size_t)(n / 128 + 1) * 16;
@@ -900,14 +893,14 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
   // fused forward on a shape-sorted level: the convolutions read the tile slices and the sorted tile masks, the slices
   // read only present entries -> neither the -1 entries nor the physical-order tile masks are produced
   auto sparse_ok = [&](int L) {
-    return c0 != nullptr && !conv_needs_dense_maps() && !conv_half_off() && g_tile_slices && ctx->tslice[L] != nullptr && g_pattern_sort && L >= kFirstSortedLevel &&
-           L <= kLastSortedLevel && (g_pattern_sort == 2 || ctx->n >= kMinRowsForSort);
+    return c0 != nullptr && !needs_dense_maps(ctx) && g_tile_slices && ctx->tslice[L] != nullptr && ctx->pattern_sort && L >= kFirstSortedLevel &&
+           L <= kLastSortedLevel && (ctx->pattern_sort == 2 || ctx->n >= kMinRowsForSort);
   };
   k_kernel_map_blk3<3><<<dim3(grid_for(n, 256, 148 * 8), 3), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->table,
                                                                               ctx->cells, ctx->occ, 0, ctx->nbr3[0],
                                                                               ctx->ld, sparse_ok(0) ? nullptr : ctx->tmask3[0],
                                                                               ctx->vmask, sparse_ok(0) ? 0 : 1);
-  prof_mark("kmap3.L0", st);
+  prof_mark(ctx, "kmap3.L0", st);
   { const int rc = pattern_order(ctx, 0, st); if (rc != SPS_OK) return rc; }
   for (int L = 1; L < SPS_NUM_LEVELS; ++L) {
     const int32_t* n_fine = ctx->counts + (L - 1);
@@ -922,21 +915,21 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
     static const char* nm_s[5] = {"", "stride.L1", "stride.L2", "stride.L3", "stride.L4"};
     static const char* nm_b[5] = {"", "blocks.L1", "blocks.L2", "blocks.L3", "blocks.L4"};
     static const char* nm_k[5] = {"", "kmap3.L1", "kmap3.L2", "kmap3.L3", "kmap3.L4"};
-    prof_mark(nm_s[L], st);
+    prof_mark(ctx, nm_s[L], st);
     build_blocks(L);
-    prof_mark(nm_b[L], st);
+    prof_mark(ctx, nm_b[L], st);
     SPS_CUDA_CHECK(cudaMemsetAsync(ctx->tmask3[L], 0, mask_bytes, st));
     k_kernel_map_blk3<3><<<dim3(grid_for(n, 256, 148 * 8), 3), 256, 0, st>>>(ctx->keys[L], ctx->counts + L, ctx->table,
                                                                                 ctx->cells, ctx->occ, L, ctx->nbr3[L],
                                                                                 ctx->ld, sparse_ok(L) ? nullptr : ctx->tmask3[L],
                                                                                 ctx->vmask, sparse_ok(L) ? 0 : 1);
-    prof_mark(nm_k[L], st);
+    prof_mark(ctx, nm_k[L], st);
     { const int rc = pattern_order(ctx, L, st); if (rc != SPS_OK) return rc; }
   }
   SPS_CUDA_CHECK(cudaGetLastError());
   ctx->have_maps = true;
   ctx->dense_maps = !(sparse_ok(0) || sparse_ok(1) || sparse_ok(2) || sparse_ok(3));
-  ctx->have_perm = g_pattern_sort == 2 || (g_pattern_sort == 1 && ctx->n >= kMinRowsForSort);
+  ctx->have_perm = ctx->pattern_sort == 2 || (ctx->pattern_sort == 1 && ctx->n >= kMinRowsForSort);
   ctx->have_slices = ctx->have_perm && g_tile_slices && kLastSortedLevel <= 3;
   ctx->first_sorted = kFirstSortedLevel;
   ctx->last_sorted = kLastSortedLevel;

@@ -15,10 +15,7 @@
 #include "profile.h"
 
 namespace sps {
-int conv_simt(const sps_conv_args& a, cudaStream_t st);
 int conv_dispatch(const sps_conv_args& a, cudaStream_t st);
-int conv_backend();
-bool conv_half_storage();
 
 struct ConvW {
   float* w = nullptr;      // [K][cin][cout], BN scale folded
@@ -234,11 +231,6 @@ extern "C" int sps_net_finalize(sps_net* net, void* d_weights, size_t bytes, voi
 
 namespace sps {
 
-__global__ void k_fill_f32(float* __restrict__ p, const int32_t* __restrict__ n_ptr, float v) {
-  const int n = *n_ptr;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
-}
-
 // SparseTensor.slice(tensor_field) + sigmoid (src/sps/models/models.py:28-29)
 __global__ void k_devox_sigmoid(const float* __restrict__ logits, const int32_t* __restrict__ inv, int64_t n,
                                 float* __restrict__ scores, int apply_sigmoid) {
@@ -253,60 +245,81 @@ __global__ void k_devox_sigmoid(const float* __restrict__ logits, const int32_t*
   }
 }
 
-static int g_forward_launches = 0;
+// A feature matrix (or a channel slice of one): pointer, leading dimension in elements of ITS dtype, dtype.
+struct Act {
+  float* p = nullptr;
+  int64_t ld = 0;
+  bool f16 = false;
+  Act() {}
+  Act(float* p_, int64_t ld_, bool f16_) : p(p_), ld(ld_), f16(f16_) {}
+  Act at(int ch) const { return Act(f16 ? reinterpret_cast<float*>(reinterpret_cast<__half*>(p) + ch) : p + ch, ld, f16); }
+};
 
-#ifndef SPS_SORT_MIN_CIN
-#define SPS_SORT_MIN_CIN 8    // measured: sorting pays for the 8-channel convs of levels 1-3 too (block1 0.23 -> 0.17 ms)
-#endif
-static bool g_run_half = false;   // the forward being enqueued stores its activations as fp16
-static int run_conv(const uint32_t* tmask, const int32_t* perm, const int32_t* slices, const char* name, const ConvW& w, int mode, const int32_t* map, int64_t map_ld, const int32_t* n_out,
-                    int64_t n_out_max, const float* in, int64_t in_ld, const float* in2, int64_t in2_ld,
-                    const float* res, int64_t res_ld, float* out, int64_t out_ld, cudaStream_t st,
-                    const float* head_w = nullptr, float head_b = 0.f, float* head_out = nullptr) {
+struct ConvIo {
+  const uint32_t* tmask; const int32_t* perm; const int32_t* slices;   // processing order (see sps_conv_args)
+  int mode; const int32_t* map;
+};
+
+// One layer of the fused forward.  Kernel family by arithmetic mode of the context and by layer shape:
+//   FP32 mode: generic fp32 CUDA-core kernels.  Otherwise: 8 output channels -> the fp32 FMA kernel (exact weights),
+//   >= 16 output channels -> the tcgen05 kernel on fp16 rows (AUTO / F16) or TF32 operands on fp32 rows (TF32).
+static int run_conv(sps_ctx* c, const ConvIo& io, const char* name, const ConvW& w, const int32_t* n_out, int64_t n_out_max,
+                    Act in, Act in2, Act res, Act out, bool round_out, cudaStream_t st, const float* head_w = nullptr,
+                    float head_b = 0.f, float* head_out = nullptr) {
   sps_conv_args a;
   memset(&a, 0, sizeof(a));
-  a.mode = mode; a.K = w.K; a.cin = w.cin; a.cout = w.cout;
-  a.map = map; a.map_ld = map_ld; a.n_out = n_out; a.n_out_max = n_out_max;
-  a.in = in; a.in_ld = in_ld; a.weight = w.w; a.shift = w.shift;
-  if (in2) { a.in2 = in2; a.in2_ld = in2_ld; a.cin2 = w.cin2; a.weight2 = w.w2; }
-  a.res = res; a.res_ld = res_ld; a.relu = 1; a.out = out; a.out_ld = out_ld;
+  a.mode = io.mode; a.K = w.K; a.cin = w.cin; a.cout = w.cout;
+  a.map = io.map; a.map_ld = c->ld; a.n_out = n_out; a.n_out_max = n_out_max;
+  a.in = in.p; a.in_ld = in.ld; a.weight = w.w; a.shift = w.shift;
+  if (in2.p) { a.in2 = in2.p; a.in2_ld = in2.ld; a.cin2 = w.cin2; a.weight2 = w.w2; }
+  a.res = res.p; a.res_ld = res.ld; a.relu = 1; a.out = out.p; a.out_ld = out.ld;
   a.head_w = head_w; a.head_b = head_b; a.head_out = head_out;
-  a.weight_kmajor = g_run_half ? w.wth : w.wt; a.kmajor_ld = g_run_half ? w.ldkh : w.ldk;
-  a.io_dtype = g_run_half ? SPS_IO_F16 : SPS_IO_F32;
-  a.tile_mask = tmask; a.perm = perm; a.tile_slices = perm ? slices : nullptr;
-  a.round_out = conv_backend() != 1;   // pure fp32 mode keeps full-precision activations
-  ++g_forward_launches;
+  const bool side_f16 = in2.p ? in2.f16 : res.p ? res.f16 : in.f16;
+  a.io_dtype = (in.f16 ? SPS_IO_IN_F16 : 0) | (side_f16 ? SPS_IO_IN2_F16 : 0) | ((out.p ? out.f16 : in.f16) ? SPS_IO_OUT_F16 : 0);
+  const bool fma = c->backend != SPS_BACKEND_FP32 && w.cout == 8 && io.mode == SPS_CONV_NBR;
+  if (!fma && c->backend != SPS_BACKEND_FP32) {
+    if (a.io_dtype != SPS_IO_F16 && a.io_dtype != SPS_IO_F32) return SPS_ERR_STATE;   // the tensor-core kernel takes one row format
+    a.weight_kmajor = c->run_half ? w.wth : w.wt; a.kmajor_ld = c->run_half ? w.ldkh : w.ldk;
+  }
+  a.tile_mask = io.tmask; a.perm = io.perm; a.tile_slices = io.perm ? io.slices : nullptr;
+  a.round_out = round_out;
+  // FMA layers go to their kernel explicitly (AUTO prefers it anyway); the other layers take the context's family
+  a.backend = c->backend == SPS_BACKEND_FP32 ? SPS_BACKEND_FP32 : fma ? SPS_BACKEND_AUTO : c->run_half ? SPS_BACKEND_F16 : SPS_BACKEND_TF32;
+  ++c->forward_launches;
   const int rc = conv_dispatch(a, st);
-  prof_mark(name, st);
+  prof_mark(c, name, st);
   return rc;
 }
 
-// 3x3x3x3 conv at level L: rows are visited in neighbourhood-shape order where that pays (sorted level and
-// at least 16 input channels -- for 8-channel layers the scattered row access costs more than the skipped
-// offsets save), otherwise in physical order; both sets of tile masks exist.
-template <class... Args>
-static int run_conv3(sps_ctx* c, int L, const char* name, const ConvW& w, Args... args) {
-  const bool pm = c->have_perm && L >= c->first_sorted && L <= c->last_sorted && w.cin >= SPS_SORT_MIN_CIN;
-  return run_conv(pm ? c->ptmask[L] : c->tmask3[L], pm ? c->perm[L] : nullptr, pm && c->have_slices ? c->tslice[L] : nullptr, name, w,
-                  args...);
+// processing order of the 3x3x3x3 convs at level L: rows in neighbourhood-shape order where the level was sorted,
+// otherwise physical order; both kinds of tile masks exist.
+static ConvIo io3(const sps_ctx* c, int L) {
+  const bool pm = c->have_perm && L >= c->first_sorted && L <= c->last_sorted;
+  return ConvIo{pm ? c->ptmask[L] : c->tmask3[L], pm ? c->perm[L] : nullptr, pm && c->have_slices ? c->tslice[L] : nullptr,
+                SPS_CONV_NBR, c->nbr3[L]};
 }
 
 int unet_forward(sps_ctx* c, const sps_net* net, const float* feat0, float* logits, cudaStream_t st,
                  bool conv0_done = false) {
   const int64_t nmax = c->n > 0 ? c->n : 1;
-  const int64_t ld = c->ld;
   float** B = c->buf;
   using C = sps_ctx;
-  // fp16 storage needs conv0's output in fp16, which only the fused forward produces
-  const bool hm = conv_half_storage() && conv0_done;
-  g_run_half = hm;
-  auto at = [&](float* base, int off) { return hm ? reinterpret_cast<float*>(reinterpret_cast<__half*>(base) + off) : base + off; };
-  // skip tensors live in the tail channel slice of the concat buffers (ME.cat(out, skip))
-  float* skip[4] = {at(B[C::CAT8], 8), at(B[C::CAT7], 16), at(B[C::CAT6], 32), at(B[C::CAT5], 64)};
-  const int skip_ld[4] = {kCatLd[0], kCatLd[1], kCatLd[2], kCatLd[3]};
-  float* cat[4] = {B[C::CAT8], B[C::CAT7], B[C::CAT6], B[C::CAT5]};
-  float* E[4] = {B[C::E1], B[C::E2], B[C::E3], B[C::E4]};
-  float* H[4] = {B[C::H1], B[C::H2], B[C::H3], B[C::H4]};
+  const bool exact = c->backend == SPS_BACKEND_FP32;
+  const bool hm = ctx_half_storage(c);     // fp16 rows (except the level-0 tail, which is fp32 in every mode)
+  c->run_half = hm;
+  const bool rnd = c->backend == SPS_BACKEND_TF32;   // fp32 rows that a TF32 tensor-core layer reads are stored rounded (cvt.rna)
+  // Storage plan.  Level-0 tail (conv0 output = skip0, convtr7p2s2 output, block8.conv1 output): fp32 rows in every
+  // mode -- their rounding is what dominated the score error of fp16 storage (tools/precision_study.py).
+  const Act cat8(B[C::CAT8], kCatLd[0], false), h8(B[C::H8], 8, false);
+  const Act cat[4] = {cat8, Act(B[C::CAT7], kCatLd[1], hm), Act(B[C::CAT6], kCatLd[2], hm), Act(B[C::CAT5], kCatLd[3], hm)};
+  // skip tensors live in the tail channel slice of the concat buffers (ME.cat(out, skip), minkunet.py:192)
+  const Act skip[4] = {cat[0].at(8), cat[1].at(16), cat[2].at(32), cat[3].at(64)};
+  const Act E[4] = {Act(B[C::E1], 8, hm), Act(B[C::E2], 8, hm), Act(B[C::E3], 16, hm), Act(B[C::E4], 32, hm)};
+  const Act H[4] = {Act(B[C::H1], 8, hm), Act(B[C::H2], 16, hm), Act(B[C::H3], 32, hm), Act(B[C::H4], 64, hm)};
+  const Act b4(B[C::B4], 64, hm);
+  const Act Hd[4] = {Act(B[C::H5], 64, hm), Act(B[C::H6], 32, hm), Act(B[C::H7], 16, hm), h8};
+  const Act Bd[3] = {Act(B[C::B5], 64, hm), Act(B[C::B6], 32, hm), Act(B[C::B7], 16, hm)};
+  const Act none;
   static const char* nm_down[4] = {"conv1p1s2", "conv2p2s2", "conv3p4s2", "conv4p8s2"};
   static const char* nm_up[4] = {"convtr4p16s2", "convtr5p8s2", "convtr6p4s2", "convtr7p2s2"};
   static const char* nm_c1[8] = {"block1.conv1", "block2.conv1", "block3.conv1", "block4.conv1",
@@ -314,63 +327,55 @@ int unet_forward(sps_ctx* c, const sps_net* net, const float* feat0, float* logi
   static const char* nm_c2[8] = {"block1.conv2", "block2.conv2", "block3.conv2", "block4.conv2",
                                  "block5.conv2", "block6.conv2", "block7.conv2", "block8.conv2+final"};
   int rc;
-#define RUN(...) do { rc = run_conv(nullptr, nullptr, nullptr, __VA_ARGS__); if (rc != SPS_OK) return rc; } while (0)
-#define RUN8(...) do { rc = run_conv(c->tmask8, nullptr, nullptr, __VA_ARGS__); if (rc != SPS_OK) return rc; } while (0)
-#define RUN3(L_, ...) do { rc = run_conv3(c, L_, __VA_ARGS__); if (rc != SPS_OK) return rc; } while (0)
-  // conv0p1s1 + bn0 + relu  (minkunet.py:162-164)
+#define RUN(...) do { rc = run_conv(c, __VA_ARGS__); if (rc != SPS_OK) return rc; } while (0)
+  // conv0p1s1 + bn0 + relu  (minkunet.py:162-164); the fused forward computed it while the level-0 block table was alive
   if (!conv0_done) {
     if (!c->have_nbr5) return SPS_ERR_STATE;
-    RUN("conv0", net->conv0, SPS_CONV_NBR, c->nbr5, ld, c->counts + 0, nmax, feat0, 1, nullptr, 0, nullptr, 0, skip[0],
-        skip_ld[0], st);
+    const int keep = c->backend;
+    c->backend = SPS_BACKEND_FP32;   // Cin = 1, 125 offsets: the generic fp32 kernel in every mode
+    const Act f0(const_cast<float*>(feat0), 1, false);
+    rc = run_conv(c, ConvIo{nullptr, nullptr, nullptr, SPS_CONV_NBR, c->nbr5}, "conv0", net->conv0, c->counts + 0, nmax, f0, none, none,
+                  skip[0], false, st);
+    c->backend = keep;
+    if (rc != SPS_OK) return rc;
   }
   // encoder (minkunet.py:166-185)
   for (int i = 0; i < 4; ++i) {
     const int L = i + 1;
-    const int cw = net->down[i].cout;
-    RUN8(nm_down[i], net->down[i], SPS_CONV_NBR, c->child[L], ld, c->counts + L, nmax, skip[i], skip_ld[i], nullptr, 0,
-         nullptr, 0, E[i], cw, st);
+    const ConvIo down{c->tmask8, nullptr, nullptr, SPS_CONV_NBR, c->child[L]};
+    // E2 feeds a tensor-core layer (block2.conv1): stored TF32-rounded in TF32 mode; E1 only feeds FMA layers
+    RUN(down, nm_down[i], net->down[i], c->counts + L, nmax, skip[i], none, none, E[i], rnd && i >= 1, st);
     const ConvW& c1 = net->blk1[i];
     const ConvW& c2 = net->blk2[i];
-    RUN3(L, nm_c1[i], c1, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, E[i], cw, nullptr, 0, nullptr, 0, H[i], c1.cout, st);
-    float* out = (L < 4) ? skip[L] : B[C::B4];
-    const int out_ld = (L < 4) ? skip_ld[L] : 64;
-    if (c2.cin2)
-      RUN3(L, nm_c2[i], c2, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, H[i], c1.cout, E[i], cw, nullptr, 0, out, out_ld, st);
-    else
-      RUN3(L, nm_c2[i], c2, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, H[i], c1.cout, nullptr, 0, E[i], cw, out, out_ld, st);
+    RUN(io3(c, L), nm_c1[i], c1, c->counts + L, nmax, E[i], none, none, H[i], rnd && i >= 1, st);
+    const Act out = (L < 4) ? skip[L] : b4;
+    if (c2.cin2) RUN(io3(c, L), nm_c2[i], c2, c->counts + L, nmax, H[i], E[i], none, out, rnd, st);
+    else RUN(io3(c, L), nm_c2[i], c2, c->counts + L, nmax, H[i], none, E[i], out, rnd, st);
   }
   // decoder (minkunet.py:188-217)
-  float* dec_in = B[C::B4];
-  int dec_in_ld = 64;
-  float* Hd[4] = {B[C::H5], B[C::H6], B[C::H7], B[C::H8]};
-  float* Bd[4] = {B[C::B5], B[C::B6], B[C::B7], nullptr};
+  Act dec_in = b4;
   for (int i = 0; i < 4; ++i) {
     const int L = 3 - i;  // output level
-    if (conv_backend() == 1) {   // exact-fp32 mode: scatter over the child table (no atomics, each row once)
-      RUN(nm_up[i], net->up[i], SPS_CONV_UP, c->child[L + 1], ld, c->counts + L + 1, nmax, dec_in, dec_in_ld, nullptr, 0,
-          nullptr, 0, cat[L], skip_ld[L], st);
-    } else {                     // tensor path: the same transposed conv as an 8-offset gather map of the fine rows
-      RUN8(nm_up[i], net->up[i], SPS_CONV_NBR, c->upmap[L], ld, c->counts + L, nmax, dec_in, dec_in_ld, nullptr, 0,
-           nullptr, 0, cat[L], skip_ld[L], st);
+    if (exact) {   // exact-fp32 mode: scatter over the child table (no atomics, each row once)
+      RUN(ConvIo{nullptr, nullptr, nullptr, SPS_CONV_UP, c->child[L + 1]}, nm_up[i], net->up[i], c->counts + L + 1, nmax, dec_in, none,
+          none, cat[L], false, st);
+    } else {       // the same transposed conv as an 8-offset gather map of the fine rows
+      RUN(ConvIo{c->tmask8, nullptr, nullptr, SPS_CONV_NBR, c->upmap[L]}, nm_up[i], net->up[i], c->counts + L, nmax, dec_in, none, none,
+          cat[L], rnd && L > 0, st);
     }
     const ConvW& c1 = net->blk1[4 + i];
     const ConvW& c2 = net->blk2[4 + i];
-    RUN3(L, nm_c1[4 + i], c1, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, cat[L], skip_ld[L], nullptr, 0, nullptr, 0, Hd[i],
-        c1.cout, st);
+    RUN(io3(c, L), nm_c1[4 + i], c1, c->counts + L, nmax, cat[L], none, none, Hd[i], rnd && L > 0, st);
     if (i < 3) {
-      RUN3(L, nm_c2[4 + i], c2, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, Hd[i], c1.cout, cat[L], skip_ld[L], nullptr, 0,
-          Bd[i], c2.cout, st);
+      // B7 (block7 output) only feeds the FMA layer convtr7p2s2
+      RUN(io3(c, L), nm_c2[4 + i], c2, c->counts + L, nmax, Hd[i], cat[L], none, Bd[i], rnd && i < 2, st);
       dec_in = Bd[i];
-      dec_in_ld = c2.cout;
     } else {
       // block8.conv2 + norm2 + downsample + relu, with `final` (8->1, bias; minkunet.py:219) fused
-      RUN3(L, nm_c2[4 + i], c2, SPS_CONV_NBR, c->nbr3[L], ld, c->counts + L, nmax, Hd[i], c1.cout, cat[L], skip_ld[L], nullptr, 0,
-          nullptr, 0, st, net->head_w, net->head_b, logits);
+      RUN(io3(c, L), nm_c2[4 + i], c2, c->counts + L, nmax, Hd[i], cat[L], none, none, false, st, net->head_w, net->head_b, logits);
     }
   }
 #undef RUN
-#undef RUN3
-#undef RUN8
   return SPS_OK;
 }
 
@@ -416,38 +421,38 @@ static int forward_feat_impl(sps_ctx* ctx, const sps_net* net, const float* d_po
                              cudaStream_t st) {
   if (!ctx || !net || n < 0) return SPS_ERR_BAD_ARG;
   if (!net->finalized) return SPS_ERR_STATE;
-  g_forward_launches = 0;
+  ctx->forward_launches = 0;
   if (n == 0) {  // empty input: nothing to score (an empty TensorField in the reference)
     ctx->n = 0;
     ctx->have_l0 = ctx->have_maps = false;
     return SPS_OK;
   }
   if (!d_scores || !d_points) return SPS_ERR_BAD_ARG;
-  prof_begin(st);
+  prof_begin(ctx, st);
   int rc = voxelize_impl(ctx, d_points, n, d_n, ld_points, voxel_size, st);
   if (rc != SPS_OK) return rc;
   // TensorField.sparse(): voxel feature = mean of the constant 0.5 point features = 0.5
   // (src/sps/models/models.py:22-25)
-  const bool hm = conv_half_storage();
-  float* c0_out = hm ? reinterpret_cast<float*>(reinterpret_cast<__half*>(ctx->buf[sps_ctx::CAT8]) + 8) : ctx->buf[sps_ctx::CAT8] + 8;
+  // conv0's output (skip0 = channels 8..15 of the level-0 concat buffer) is stored as fp32 rows in every mode
+  float* c0_out = ctx->buf[sps_ctx::CAT8] + 8;
   const float* vfeat = nullptr;
   if (d_feat) {   // voxel feature = mean of its points' features; the logits buffer is free until the last layer
     rc = sps_voxel_mean(ctx, d_feat, 1, 1, ctx->buf[sps_ctx::FEAT0], ctx->buf[sps_ctx::LOGITS], st);
     if (rc != SPS_OK) return rc;
     vfeat = ctx->buf[sps_ctx::FEAT0];
   }
-  Conv0Fused c0{vfeat, 0.5f, net->conv0.w, net->conv0.shift, hm ? kStoreF16 : (conv_backend() != 1 ? kStoreTF32 : kStoreF32), c0_out, 16};
+  Conv0Fused c0{vfeat, 0.5f, net->conv0.w, net->conv0.shift, kStoreF32, c0_out, kCatLd[0]};
   rc = build_maps_impl(ctx, &c0, st);
   if (rc != SPS_OK) return rc;
   rc = unet_forward(ctx, net, ctx->buf[sps_ctx::FEAT0], ctx->buf[sps_ctx::LOGITS], st, /*conv0_done=*/true);
   if (rc != SPS_OK) return rc;
   rc = devox(ctx->buf[sps_ctx::LOGITS], ctx->inv, n_scores, d_scores, net->apply_sigmoid, st);
   if (rc != SPS_OK) return rc;
-  prof_mark("devox_sigmoid", st);
+  prof_mark(ctx, "devox_sigmoid", st);
   // voxelize 5; map building 51 (block tables, strided levels, kernel maps) + 2 + 3 * passes per shape-sorted level (keys,
   // the radix passes of 3 kernels each, permuted tile masks + slices); devox 1
   const int sorted_levels = ctx->have_perm ? ctx->last_sorted - ctx->first_sorted + 1 : 0;
-  g_forward_launches += 5 + 51 + (2 + 3 * SPS_SORT_PASSES) * sorted_levels + 1;
+  ctx->forward_launches += 5 + 51 + (2 + 3 * SPS_SORT_PASSES) * sorted_levels + 1;
   return SPS_OK;
 }
 }  // namespace sps
@@ -462,8 +467,6 @@ extern "C" int sps_forward_features(sps_ctx* ctx, const sps_net* net, const floa
   if (!d_feat && n > 0) return SPS_ERR_BAD_ARG;
   return forward_feat_impl(ctx, net, d_points, n, nullptr, ld_points, d_feat, voxel_size, d_scores, n, (cudaStream_t)stream);
 }
-
-extern "C" int sps_forward_launch_count(void) { return g_forward_launches; }
 
 extern "C" int sps_forward_host(sps_ctx* ctx, const sps_net* net, const float* h_points, int64_t n,
                                 int64_t ld_points, float voxel_size, float* h_scores, void* stream) {

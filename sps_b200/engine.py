@@ -16,8 +16,36 @@ def _ptr(t) -> C.c_void_p:
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
-def _stream() -> C.c_void_p:
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+# Host-side defaults for NEW engines (the C library itself keeps no process-wide state: every setting lives in a
+# context, see include/sps_b200.h).  conv_backend: 0 auto / 1 exact fp32 / 2 TF32 on fp32 rows / 3 fp16 rows.
+DEFAULTS = {"conv_backend": 0, "pattern_sort": 1}
+
+
+def set_defaults(conv_backend=None, pattern_sort=None):
+    """Arithmetic / processing-order mode that engines created from now on start with."""
+    if conv_backend is not None:
+        if conv_backend not in (0, 1, 2, 3):
+            raise ValueError("conv_backend must be 0 (auto), 1 (fp32), 2 (tf32) or 3 (fp16)")
+        DEFAULTS["conv_backend"] = int(conv_backend)
+    if pattern_sort is not None:
+        if pattern_sort not in (0, 1, 2):
+            raise ValueError("pattern_sort must be 0, 1 or 2")
+        DEFAULTS["pattern_sort"] = int(pattern_sort)
+
+
+def _on_device(fn):
+    """Run a method with ``self.device`` current: the C calls enqueue on that device's current stream."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        with torch.cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+    return wrapper
 
 
 def norm_device(device) -> torch.device:
@@ -82,6 +110,19 @@ class Engine:
             check(self.lib.sps_ctx_create(C.byref(h), _ptr(self.workspace), nbytes, self.max_points), "sps_ctx_create")
         self.handle = h
         self.n = 0
+        self.conv_backend = self.pattern_sort = None
+        self.set_conv_backend(DEFAULTS["conv_backend"])
+        self.set_pattern_sort(DEFAULTS["pattern_sort"])
+
+    def set_conv_backend(self, backend: int):
+        """0 auto (tcgen05 on fp16 rows + fp32 FMA kernels for the 8-channel layers), 1 exact fp32 CUDA cores,
+        2 TF32 operands on fp32 rows, 3 = 0 (sps_ctx_set_conv_backend)."""
+        check(self.lib.sps_ctx_set_conv_backend(self.handle, int(backend)), "sps_ctx_set_conv_backend")
+        self.conv_backend = int(backend)
+
+    def set_pattern_sort(self, mode: int):
+        check(self.lib.sps_ctx_set_pattern_sort(self.handle, int(mode)), "sps_ctx_set_pattern_sort")
+        self.pattern_sort = int(mode)
 
     def __del__(self):
         try:
@@ -92,6 +133,7 @@ class Engine:
             pass
 
     # ---- coordinate maps -------------------------------------------------------------
+    @_on_device
     def voxelize(self, points: torch.Tensor, voxel_size: float):
         _require_cuda(points, "points")
         assert points.dtype == torch.float32 and points.dim() == 2 and points.stride(1) == 1
@@ -100,9 +142,11 @@ class Engine:
         check(self.lib.sps_voxelize(self.handle, _ptr(points), self.n, points.stride(0), float(voxel_size), _stream()),
               "sps_voxelize")
 
+    @_on_device
     def build_maps(self):
         check(self.lib.sps_build_maps(self.handle, _stream()), "sps_build_maps")
 
+    @_on_device
     def status(self):
         check(self.lib.sps_ctx_status(self.handle, _stream()), "sps_ctx_status")
 
@@ -111,6 +155,7 @@ class Engine:
         check(self.lib.sps_ctx_level(self.handle, L, C.byref(v)), "sps_ctx_level")
         return v
 
+    @_on_device
     def _read(self, ptr, count, dtype):
         out = np.empty(count, dtype=dtype)
         if count:
@@ -121,6 +166,7 @@ class Engine:
     def count(self, L: int) -> int:
         return int(self._read(self.level(L).count, 1, np.int32)[0])
 
+    @_on_device
     def coords(self, L: int) -> np.ndarray:
         """int32 [V_L, 5] rows (b, x, y, z, t) == ME ``SparseTensor.C`` at tensor stride 2**L."""
         n = self.count(L)
@@ -147,6 +193,7 @@ class Engine:
         return self._read(v.parent, self.count(L), np.int32)
 
     # ---- network ---------------------------------------------------------------------
+    @_on_device
     def forward(self, net: Net, points: torch.Tensor, voxel_size: float, out: torch.Tensor | None = None):
         """SPSModel.forward on device tensors; asynchronous (no host sync)."""
         _require_cuda(points, "points")
@@ -160,6 +207,7 @@ class Engine:
                                    _ptr(out), _stream()), "sps_forward")
         return out
 
+    @_on_device
     def forward_features(self, net: Net, points: torch.Tensor, features: torch.Tensor, voxel_size: float,
                          out: torch.Tensor | None = None):
         """As :meth:`forward` with one input feature per point (voxel feature = mean of its points' features):
@@ -190,6 +238,7 @@ class Engine:
                                             _stream()), "sps_forward_host")
         return out
 
+    @_on_device
     def unet_forward(self, net: Net, feat0: torch.Tensor) -> torch.Tensor:
         logits = torch.empty(feat0.shape[0], dtype=torch.float32, device=self.device)
         check(self.lib.sps_unet_forward(self.handle, net.handle, _ptr(feat0), _ptr(logits), _stream()),
@@ -197,7 +246,23 @@ class Engine:
         return logits
 
     def launch_count(self) -> int:
-        return int(self.lib.sps_forward_launch_count())
+        """Kernels the last fused forward of this engine enqueued."""
+        return int(self.lib.sps_ctx_launch_count(self.handle))
+
+    def profile(self, on: bool):
+        check(self.lib.sps_profile_enable(self.handle, int(bool(on))), "sps_profile_enable")
+
+    def profile_read(self, max_segments: int = 160) -> dict:
+        """Synchronises; {stage name: milliseconds} of the last profiled forward (names repeat -> summed)."""
+        names = C.create_string_buffer(32 * max_segments)
+        ms = (C.c_float * max_segments)()
+        cnt = C.c_int()
+        check(self.lib.sps_profile_read(self.handle, names, ms, max_segments, C.byref(cnt)), "sps_profile_read")
+        out = {}
+        for i in range(cnt.value):
+            nm = names.raw[32 * i:32 * i + 32].split(b"\0")[0].decode()
+            out[nm] = out.get(nm, 0.0) + ms[i]
+        return out
 
 
 class MapHash:
@@ -211,10 +276,11 @@ class MapHash:
         self.map_xyz = map_xyz[:, :3].contiguous().to(torch.float32)
         n = self.map_xyz.shape[0]
         nbytes = self.lib.sps_map_bytes(n)
-        self.storage = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         h = C.c_void_p()
-        check(self.lib.sps_map_build(C.byref(h), _ptr(self.storage), nbytes, _ptr(self.map_xyz), n, self.ds, _stream()),
-              "sps_map_build")
+        with torch.cuda.device(self.device):
+            self.storage = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            check(self.lib.sps_map_build(C.byref(h), _ptr(self.storage), nbytes, _ptr(self.map_xyz), n, self.ds, _stream()),
+                  "sps_map_build")
         self.handle = h
         self._scratch = None
 
@@ -231,6 +297,7 @@ class MapHash:
             self._scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         return self._scratch
 
+    @_on_device
     def crop_voxel(self, scan_xyz: torch.Tensor):
         """``util.prune`` semantics -> (submap_points fp32 [M,3] on device, n_unique_scan_voxels)."""
         _require_cuda(scan_xyz, "scan_xyz")
@@ -245,6 +312,7 @@ class MapHash:
         m, nuniq = counts.cpu().tolist()
         return out[:m], nuniq
 
+    @_on_device
     def crop_radius(self, center, radius: float) -> torch.Tensor:
         """MapMOS-style radius crop: indices (int32, map order) of map points within ``radius``."""
         n = self.map_xyz.shape[0]
@@ -257,6 +325,7 @@ class MapHash:
                                               _ptr(scratch), nbytes, _stream()), "sps_submap_crop_radius")
         return idx[: int(count.item())]
 
+    @_on_device
     def infer_scan(self, engine: Engine, net: Net, scan_xyz: torch.Tensor, voxel_size: float,
                    out: torch.Tensor | None = None, counts: torch.Tensor | None = None):
         """prune -> assemble -> forward for one scan, fully asynchronous (no host sync)."""
@@ -306,14 +375,14 @@ class ScanStreamer:
                                      counts=self.counts)
 
     def infer(self, scan_xyz: torch.Tensor) -> torch.Tensor:
-        """scan_xyz fp32 CUDA [n <= n_scan, 3] in the map frame -> scores [n] (a view of a static buffer that
-        the next call overwrites).  Asynchronous."""
+        """scan_xyz fp32 [n <= n_scan, 3] in the map frame, on the device or in (pinned) host memory -> scores [n]
+        (a view of a static device buffer that the next call overwrites).  Asynchronous."""
         n = scan_xyz.shape[0]
         if n > self.n_scan or n == 0:
             raise ValueError(f"scan has {n} points, streamer was built for 1..{self.n_scan}")
-        self.scan[:n].copy_(scan_xyz[:, :3])
+        self.scan[:n].copy_(scan_xyz[:, :3], non_blocking=True)     # device tensor, or (pinned) host tensor: H2D on this stream
         if n < self.n_scan:
-            self.scan[n:] = scan_xyz[0, :3]
+            self.scan[n:] = self.scan[0]
         if self.graph is None:
             self._capture()
         self.graph.replay()

@@ -165,11 +165,9 @@ class _ConvBase(nn.Module):
             b = self.bias.detach().reshape(-1).contiguous()
             a.shift = b.data_ptr()
         a.out, a.out_ld = out.data_ptr(), out.stride(0)
-        check(lib.sps_set_conv_backend(1), "sps_set_conv_backend")     # layer API: exact fp32 kernels
-        try:
+        a.backend = _cabi.SPS_BACKEND_FP32                       # layer API: exact fp32 kernels, chosen per call
+        with torch.cuda.device(x.F.device):
             check(lib.sps_conv_fwd(C.byref(a), _stream()), "sps_conv_fwd")
-        finally:
-            lib.sps_set_conv_backend(0)
         return SparseTensor(out[:n_out], coordinate_manager=mgr, level=out_level)
 
 

@@ -130,10 +130,14 @@ class CustomMinkUNet(nn.Module):
 class _Pending:
     """Handle of an in-flight ``SPSModel.forward_async`` call."""
 
-    def __init__(self, event, out, engine):
+    def __init__(self, event, out, engine, device_scores=None):
         self._event, self._out, self._engine = event, out, engine
+        # the scores on the device (valid once the call is done; the lane reuses the buffer `lanes` calls later)
+        self.device_scores = device_scores if device_scores is not None else out
 
-    def result(self, check: bool = False) -> torch.Tensor:
+    def result(self, check: bool = True) -> torch.Tensor:
+        """Wait for the call and return its scores.  ``check`` (default) also reads the engine's sticky status word,
+        so a coordinate outside the voxel-key range raises here instead of leaving NaN scores behind."""
         self._event.synchronize()
         if check:
             self._engine.status()
@@ -155,6 +159,25 @@ class SPSModel(nn.Module):
         self._pipe = None
         self.lanes = 3            # engine contexts / streams that forward_async alternates between
         self.output_channel, self.apply_sigmoid = 0, True   # models.py:28-29: sigmoid of the single output channel
+        self.conv_backend = None  # None: the host default of sps_b200.engine.DEFAULTS at engine creation
+
+    def set_conv_backend(self, backend: int):
+        """Arithmetic mode of every engine this model owns (0 auto, 1 exact fp32, 2 TF32 on fp32 rows, 3 fp16 rows)."""
+        self.conv_backend = int(backend)
+        for eng in self._engines():
+            eng.set_conv_backend(self.conv_backend)
+
+    def _engines(self):
+        out = [self._engine] if self._engine is not None else []
+        if self._pipe is not None:
+            out += [e for e in self._pipe["engine"] if e is not self._engine]
+        return out
+
+    def _new_engine(self, cap, device):
+        eng = Engine(cap, device)
+        if self.conv_backend is not None:
+            eng.set_conv_backend(self.conv_backend)
+        return eng
 
     def invalidate(self):
         """Weights changed in place: re-fold and re-upload them at the next forward."""
@@ -168,13 +191,15 @@ class SPSModel(nn.Module):
         if self._engine is None or self._engine.max_points < n or self._engine.device != device:
             cap = max(self._min_points, 1 << max(10, int(math.ceil(math.log2(max(n, 1))))))
             self._engine = None  # release the old workspace before growing
-            self._engine = Engine(cap, device)
+            self._engine = self._new_engine(cap, device)
         return self._engine, self._net
 
     def forward(self, coordinates: torch.Tensor):
         """coordinates fp32 [N,5] = (b, x, y, z, t) in metres, t in {0,1} -> scores fp32 [N]
-        (models.py:20-30).  CUDA tensors run asynchronously on the current stream; CPU tensors
-        go through the host entry point (H2D + forward + D2H, synchronising)."""
+        (models.py:20-30).  CUDA tensors run asynchronously on the current stream (no host synchronisation: a
+        coordinate outside the voxel-key range -- INTEGRATION.md "Coordinate limits" -- leaves NaN scores and a
+        sticky status word that ``check()`` / ``predict_step`` / ``util.infer`` raise on); CPU tensors go
+        through the host entry point (H2D + forward + D2H, synchronising, status checked)."""
         if self.training:
             raise RuntimeError("sps_b200 is inference-only (call .eval()); training is out of scope")
         coordinates = coordinates.reshape(-1, coordinates.shape[-1]).to(torch.float32)
@@ -216,7 +241,7 @@ class SPSModel(nn.Module):
             # two complete lanes (engine context + stream + staging buffers): consecutive calls alternate,
             # so the hash/kernel-map phase of one call overlaps the convolution phase of the other
             p = self._pipe = {"cap": cap, "ld": ld, "k": 0, "copy": torch.cuda.Stream(device=device),
-                              "engine": [engine] + [Engine(engine.max_points, device) for _ in range(self.lanes - 1)],
+                              "engine": [engine] + [self._new_engine(engine.max_points, device) for _ in range(self.lanes - 1)],
                               "stream": [torch.cuda.Stream(device=device) for _ in range(self.lanes)],
                               "d_in": [torch.empty((cap, ld), dtype=torch.float32, device=device) for _ in range(self.lanes)],
                               "d_out": [torch.empty(cap, dtype=torch.float32, device=device) for _ in range(self.lanes)],
@@ -249,12 +274,12 @@ class SPSModel(nn.Module):
             done.record(compute)
         p["busy"][slot] = done
         engine = lane_engine
-        return _Pending(done, h_out, engine)
+        return _Pending(done, h_out, engine, device_scores=d_out)
 
     def check(self):
-        """Synchronise and raise if the last forward met an out-of-range coordinate."""
-        if self._engine is not None:
-            self._engine.status()
+        """Synchronise and raise if a forward since the last check met an out-of-range coordinate."""
+        for eng in self._engines():
+            eng.status()
 
 
 class MOS4DNet(SPSModel):
@@ -349,6 +374,9 @@ class SPSNet(nn.Module):
         gt_labels = batch[:, 5].reshape(-1)
         scan_mask = coordinates[:, 4] == 1                 # models.py:87
         scores = self.model(coordinates)
+        self.model.check()                                 # raises on out-of-range coordinates instead of scoring NaN
+        if not scores.is_cuda:
+            scores = scores.clone()                        # the host path returns a view of a reused pinned buffer
         scan_scores, scan_gt = scores[scan_mask.to(scores.device)], gt_labels[scan_mask].to(scores.device)
         loss = self.loss(scan_scores, scan_gt)
         r2 = self.r2score(scan_scores, scan_gt)

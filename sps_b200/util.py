@@ -87,6 +87,9 @@ def infer(scan_points, submap_points, model, device="cuda"):
     tensor = torch.hstack([batch, data]).reshape(-1, 5)
     with torch.no_grad():
         scores = model.forward(tensor)
+    checker = getattr(getattr(model, "model", model), "check", None)
+    if checker is not None:
+        checker()          # synchronises (the reference's elapsed time is a wall clock too); raises on out-of-range coordinates
     scan_scores = scores[: len(scan_points)]
     elapsed_time = time.time() - start_time
     return scan_scores.to(device), elapsed_time

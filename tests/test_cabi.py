@@ -49,7 +49,8 @@ def test_argument_validation_without_gpu():
     assert lib.sps_ctx_create(C.byref(h), None, 0, 100) == _cabi.SPS_ERR_BAD_ARG
     assert lib.sps_voxelize(None, None, 0, 5, 0.1, None) == _cabi.SPS_ERR_BAD_ARG
     assert lib.sps_conv_fwd(None, None) == _cabi.SPS_ERR_BAD_ARG
-    assert lib.sps_set_conv_backend(7) == _cabi.SPS_ERR_BAD_ARG
+    assert lib.sps_ctx_set_conv_backend(None, 0) == _cabi.SPS_ERR_BAD_ARG      # settings live in a context: no process-wide switch
+    assert lib.sps_ctx_set_pattern_sort(None, 1) == _cabi.SPS_ERR_BAD_ARG
     net = C.c_void_p()
     assert lib.sps_net_create(C.byref(net)) == 0
     x = np.zeros(8, np.float32)

@@ -127,7 +127,7 @@ def test_sparse_conv_fp16_rows(cin, cout):
                                shift=dev(shift) if kw.get("shift") else None,
                                in2=dev(x2, half) if kw.get("fused") else None, weight2=dev(w2) if kw.get("fused") else None,
                                res=dev(res, half) if kw.get("res") else None, relu=kw.get("relu", False),
-                               weight_kmajor=wt, io_f16=True)
+                               weight_kmajor=wt, io_f16=True, backend=3)   # 3: the tensor-core kernel also for 8 output channels
         torch.cuda.synchronize()
         assert out.dtype == half
         got = out[:V].float().cpu().numpy()
@@ -153,10 +153,9 @@ def test_unet_backends_agree():
     d = torch.as_tensor(pts).cuda()
     res = {}
     for backend in (1, 2, 0):   # exact fp32 / TF32 operands on fp32 rows / fp16 rows (default)
-        lib.sps_set_conv_backend(backend)
+        eng.set_conv_backend(backend)
         res[backend] = eng.forward(net, d, 0.1).cpu().numpy()
         eng.status()
-    lib.sps_set_conv_backend(0)
     assert np.abs(res[1] - ref).max() < 1e-5
     for backend in (2, 0):
         assert np.abs(res[backend] - ref).max() < 5e-4, (backend, np.abs(res[backend] - ref).max())
@@ -180,14 +179,83 @@ def test_pattern_sorted_processing_order_does_not_change_results():
     # flip the rounding of a stored activation (2^-11 relative), so the two orders agree to ~3e-4.
     for backend, tol in ((2, 2e-6), (0, 1e-3)):
         out = {}
-        try:
-            lib.sps_set_conv_backend(backend)
-            for mode in (0, 2):
-                assert lib.sps_set_pattern_sort(mode) == 0
-                out[mode] = eng.forward(net, d, 0.1).cpu().numpy()
-                eng.status()
-        finally:
-            lib.sps_set_pattern_sort(1)
-            lib.sps_set_conv_backend(0)
+        eng.set_conv_backend(backend)
+        for mode in (0, 2):
+            eng.set_pattern_sort(mode)
+            out[mode] = eng.forward(net, d, 0.1).cpu().numpy()
+            eng.status()
         assert np.abs(out[0] - out[2]).max() < tol, (backend, np.abs(out[0] - out[2]).max())
         assert np.abs(out[2] - ref).max() < 5e-4
+
+
+@pytest.mark.parametrize("cin,in_f16", [(8, True), (8, False), (16, True), (16, False)])
+@pytest.mark.parametrize("K", [81, 8])
+def test_fma8_kernel_eight_output_channels(cin, in_f16, K):
+    """k_conv_fma8 (SPS_BACKEND_AUTO, cout = 8): fp32 weights, fp32 accumulation, any mix of fp16 / fp32 rows for
+    the input, the fused 1x1 term / residual and the output; fused head.  Against float64 numpy on the STORED
+    operands (weights exact): 1e-5 relative on fp32 outputs, one fp16 rounding on fp16 outputs."""
+    from sps_b200 import convops
+    rng = np.random.default_rng(cin * 10 + K + in_f16)
+    V = 1300
+    nbr = random_map(rng, K, V, V, 0.3 if K == 81 else 0.6)
+    nbr[:, 300:500] = -1                      # rows (and a whole tile) without neighbours
+    if K == 81:
+        nbr[30:60, :] = -1                    # offsets absent everywhere
+    x = rng.standard_normal((V, cin)).astype(np.float32)
+    w = (rng.standard_normal((K, cin, 8)) / np.sqrt(cin * 8)).astype(np.float32)
+    shift = rng.standard_normal(8).astype(np.float32)
+    x2 = rng.standard_normal((V, 16)).astype(np.float32)
+    w2 = (rng.standard_normal((16, 8)) / 4).astype(np.float32)
+    res = rng.standard_normal((V, 8)).astype(np.float32)
+    head_w = rng.standard_normal(8).astype(np.float32)
+    ld = (V + 31) // 32 * 32
+    m = np.full((K, ld), -1, np.int32)
+    m[:, :V] = nbr
+    half = torch.float16
+    dev = lambda a, f16=False: torch.as_tensor(np.ascontiguousarray(a)).cuda().to(half if f16 else torch.float32)
+    n_out = torch.tensor([V], dtype=torch.int32, device="cuda")
+    qx = f16 if in_f16 else (lambda v: v)
+    for side_f16, out_f16 in ((False, False), (True, True), (not in_f16, in_f16)):
+        q2 = f16 if side_f16 else (lambda v: v)
+        # conv + shift + relu
+        out = convops.conv_fwd(dev(x, in_f16), dev(w), n_out, map=dev(m).int(), map_ld=ld, shift=dev(shift), relu=True,
+                               io_f16=(in_f16, side_f16, out_f16))
+        ref = ref_conv(qx(x), nbr, w, shift=shift, relu=True)
+        tol = (2e-3 if out_f16 else 2e-5) * max(1.0, np.abs(ref).max())
+        assert out.dtype == (half if out_f16 else torch.float32)
+        assert np.abs(out[:V].float().cpu().numpy() - ref).max() < tol
+        # fused 1x1 term (BasicBlock downsample) and the fused head
+        head_out = torch.zeros(V, dtype=torch.float32, device="cuda")
+        convops.conv_fwd(dev(x, in_f16), dev(w), n_out, map=dev(m).int(), map_ld=ld, shift=dev(shift), relu=True,
+                         in2=dev(x2, side_f16), weight2=dev(w2), head_w=dev(head_w), head_b=0.25, head_out=head_out,
+                         io_f16=(in_f16, side_f16, out_f16))
+        ref = ref_conv(qx(x), nbr, w, shift=shift, x2=q2(x2), w2=w2, relu=True) @ head_w.astype(np.float64) + 0.25
+        assert np.abs(head_out.cpu().numpy() - ref).max() < 3e-5 * max(1.0, np.abs(ref).max())
+        # identity residual, no ReLU
+        out = convops.conv_fwd(dev(x, in_f16), dev(w), n_out, map=dev(m).int(), map_ld=ld, res=dev(res, side_f16),
+                               io_f16=(in_f16, side_f16, out_f16))
+        ref = ref_conv(qx(x), nbr, w, res=q2(res))
+        tol = (2e-3 if out_f16 else 2e-5) * max(1.0, np.abs(ref).max())
+        assert np.abs(out[:V].float().cpu().numpy() - ref).max() < tol
+
+
+def test_fma8_channel_slices_of_wider_buffers():
+    """Inputs / outputs as channel slices of concat buffers (leading dimension > channel count), as the fused forward
+    uses them: skip0 inside the fp32 [V,16] level-0 buffer, the block output inside an fp16 [V,24] buffer."""
+    from sps_b200 import convops
+    rng = np.random.default_rng(5)
+    V, K = 700, 8
+    nbr = random_map(rng, K, V, V, 0.5)
+    ld = (V + 31) // 32 * 32
+    m = np.full((K, ld), -1, np.int32)
+    m[:, :V] = nbr
+    cat8 = torch.as_tensor(rng.standard_normal((V, 16)).astype(np.float32)).cuda()
+    w = (rng.standard_normal((K, 8, 8)) / 8).astype(np.float32)
+    cat7 = torch.zeros((V, 24), dtype=torch.float16, device="cuda")
+    n_out = torch.tensor([V], dtype=torch.int32, device="cuda")
+    convops.conv_fwd(cat8[:, 8:], torch.as_tensor(w).cuda(), n_out, map=torch.as_tensor(m).cuda(), map_ld=ld, relu=True,
+                     out=cat7[:, 16:], io_f16=(False, False, True))
+    ref = ref_conv(cat8[:, 8:].cpu().numpy(), nbr, w, relu=True)
+    got = cat7.float().cpu().numpy()
+    assert np.abs(got[:, 16:] - ref).max() < 2e-3 * max(1.0, np.abs(ref).max())
+    assert (got[:, :16] == 0).all()            # the rest of the concat buffer is untouched

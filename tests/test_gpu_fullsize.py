@@ -13,31 +13,36 @@ EPS = 0.84
 
 
 def run(pts, sd, backend=0):
-    from sps_b200 import engine, _cabi
-    lib = _cabi.load()
-    lib.sps_set_conv_backend(backend)
-    try:
-        eng = engine.Engine(len(pts))
-        out = eng.forward(engine.Net(sd), torch.as_tensor(np.ascontiguousarray(pts)).cuda(), 0.1 if pts is None else run.voxel)
-        eng.status()
-        return out.cpu().numpy(), [eng.count(L) for L in range(5)]
-    finally:
-        lib.sps_set_conv_backend(0)
+    from sps_b200 import engine
+    eng = engine.Engine(len(pts))
+    eng.set_conv_backend(backend)
+    out = eng.forward(engine.Net(sd), torch.as_tensor(np.ascontiguousarray(pts)).cuda(), 0.1 if pts is None else run.voxel)
+    eng.status()
+    return out.cpu().numpy(), [eng.count(L) for L in range(5)]
 
 
 run.voxel = 0.1
 
 
-def check_against_oracle(pts, sd, voxel, tol):
+def check_against_oracle(pts, sd, voxel, tol, straddle=False):
     run.voxel = voxel
     got, counts = run(pts, sd)
     ref, ref_counts, _ = me_cpu.forward(pts, voxel, me_cpu.pack_weights(sd))
     assert counts == ref_counts.tolist()
-    assert np.isfinite(got).all() and got.min() > 0 and got.max() < 1
+    assert np.isfinite(got).all() and got.min() >= 0 and got.max() <= 1
     err = np.abs(got - ref)
     assert err.max() < tol, err.max()
     assert np.mean((got < EPS) == (ref < EPS)) >= 0.999
+    if straddle:   # the labels must actually be decided by the scores: both classes well populated
+        assert 0.2 < np.mean(ref >= EPS) < 0.8 and ref.min() < 0.3 and ref.max() > 0.95
     return got
+
+
+def spread(sd, pts, voxel=0.1):
+    """Head gain x8 + bias moved so that eps = 0.84 cuts the score distribution in the middle (what a trained
+    checkpoint's scores look like; the random-init head alone keeps every score below eps)."""
+    from test_gpu_parity import spread_state_dict
+    return spread_state_dict(sd, pts, 8.0, voxel)
 
 
 def test_config1_128k_scan_voxel_submap():
@@ -51,6 +56,7 @@ def test_config1_128k_scan_voxel_submap():
     assert len(scan) == 131072
     sd = O.make_state_dict(seed=0)
     got = check_against_oracle(pts, sd, 0.1, 2e-3)
+    check_against_oracle(pts, spread(sd, pts), 0.1, 2e-3, straddle=True)     # same bar, 1x, on spread-out scores
     # determinism: bit-identical on a second run
     again, _ = run(pts, sd)
     assert np.array_equal(got, again)
@@ -72,15 +78,19 @@ def test_config2_batch8_radius_submaps_batch_independence():
     pts = np.ascontiguousarray(rows[:, :5])
     sd = O.make_state_dict(seed=0)
     run.voxel = 0.1
-    got, counts = run(pts, sd)
-    assert np.isfinite(got).all()
-    for b in (0, 5):
-        one = pts[pts[:, 0] == b].copy()
-        one[:, 0] = 0
-        ref, c1, _ = me_cpu.forward(one, 0.1, me_cpu.pack_weights(sd))
-        sel = got[pts[:, 0] == b]
-        assert np.abs(sel - ref).max() < 2e-3
-        assert np.mean((sel < EPS) == (ref < EPS)) >= 0.999
+    first = pts[pts[:, 0] == 0].copy()
+    for weights in (sd, spread(sd, first)):       # contract weights, then scores spread over (0,1) around eps
+        got, counts = run(pts, weights)
+        assert np.isfinite(got).all()
+        for b in (0, 5):
+            one = pts[pts[:, 0] == b].copy()
+            one[:, 0] = 0
+            ref, c1, _ = me_cpu.forward(one, 0.1, me_cpu.pack_weights(weights))
+            sel = got[pts[:, 0] == b]
+            assert np.abs(sel - ref).max() < 2e-3
+            assert np.mean((sel < EPS) == (ref < EPS)) >= 0.999
+            if weights is not sd:
+                assert 0.1 < np.mean(ref >= EPS) < 0.9 and ref.min() < 0.3 and ref.max() > 0.95
 
 
 def test_config5_stress_dense_scan_small_voxels_radius_crop():

@@ -43,10 +43,10 @@ def test_cuda_path_reproduces_golden(name):
     km5 = O.canonical_kernel_map(eng.kernel_map(0, "5"), c0, c0)
     assert len(km5) == int(g["kmap5_pairs"][0]) and np.array_equal(digest(km5.astype(np.int64)), g["kmap5_digest"])
     for backend, tol in ((1, 2e-5), (0, 2e-3)):
-        lib.sps_set_conv_backend(backend)
+        eng.set_conv_backend(backend)
         got = eng.forward(net, d, 0.1).cpu().numpy()
         eng.status()
-        lib.sps_set_conv_backend(0)
+        eng.set_conv_backend(0)
         assert np.abs(got - g["scores"]).max() < tol, (backend, np.abs(got - g["scores"]).max())
 
 
@@ -93,14 +93,12 @@ def test_next_rows_reproduce_golden():
     mm.MinkUNet.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()})
     mm = mm.cuda().eval()
     for backend, tol in ((1, 2e-4), (0, 2e-2)):
-        lib.sps_set_conv_backend(backend)
-        try:
-            a = mos(t(window)).cpu().numpy()
-            ls, lm = mm.predict(t(scans[0]), t(base), t(np.full(len(scans[0]), 6.0, np.float32)), t(map_idx))
-            b = np.concatenate([ls.cpu().numpy(), lm.cpu().numpy()])
-            mos.check(); mm.check()
-        finally:
-            lib.sps_set_conv_backend(0)
+        mos.set_conv_backend(backend)
+        mm.set_conv_backend(backend)
+        a = mos(t(window)).cpu().numpy()
+        ls, lm = mm.predict(t(scans[0]), t(base), t(np.full(len(scans[0]), 6.0, np.float32)), t(map_idx))
+        b = np.concatenate([ls.cpu().numpy(), lm.cpu().numpy()])
+        mos.check(); mm.check()
         for got, ref in ((a, g["mos4d_logits"]), (b, g["mapmos_logits"])):
             assert got.shape == ref.shape
             assert np.abs(got - ref).max() < tol * max(1.0, np.abs(ref).max()), (backend, np.abs(got - ref).max())

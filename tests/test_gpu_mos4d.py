@@ -45,12 +45,9 @@ def test_mos4dnet_matches_oracle(n_scans, t0):
     ref = O.mos4d_forward(shifted, 0.1, sd)                          # mos4d.py:32  out.features[:, 2]
     lib = _cabi.load()
     for backend, tol in ((1, 2e-4), (0, 2e-2)):
-        lib.sps_set_conv_backend(backend)
-        try:
-            got = model(torch.as_tensor(pts).cuda()).cpu().numpy()
-            model.check()
-        finally:
-            lib.sps_set_conv_backend(0)
+        model.set_conv_backend(backend)
+        got = model(torch.as_tensor(pts).cuda()).cpu().numpy()
+        model.check()
         assert got.shape == ref.shape
         scale = max(1.0, np.abs(ref).max())
         assert np.abs(got - ref).max() < tol * scale, (backend, np.abs(got - ref).max(), scale)
@@ -90,12 +87,9 @@ def test_mapmosnet_matches_oracle():
     lib = _cabi.load()
     t = lambda a: torch.as_tensor(a).cuda()
     for backend, tol in ((1, 2e-4), (0, 2e-2)):
-        lib.sps_set_conv_backend(backend)
-        try:
-            ls, lm = model.predict(t(scan), t(mp), t(scan_idx), t(map_idx))
-            model.check()
-        finally:
-            lib.sps_set_conv_backend(0)
+        model.set_conv_backend(backend)
+        ls, lm = model.predict(t(scan), t(mp), t(scan_idx), t(map_idx))
+        model.check()
         got = np.concatenate([ls.cpu().numpy(), lm.cpu().numpy()])
         scale = max(1.0, np.abs(ref).max())
         assert np.abs(got - ref).max() < tol * scale, (backend, np.abs(got - ref).max(), scale)

@@ -25,11 +25,10 @@ def engine_mod():
 def conv_backend(request):
     """Exactness-oriented tests pin the fp32 CUDA-core kernels (backend 1); tests marked
     ``tensor_path`` run the default dispatch (tcgen05 TF32 where the layer shape allows)."""
-    from sps_b200 import _cabi
-    lib = _cabi.load()
-    lib.sps_set_conv_backend(0 if request.node.get_closest_marker("tensor_path") else 1)
+    from sps_b200 import engine
+    engine.set_defaults(conv_backend=0 if request.node.get_closest_marker("tensor_path") else 1)
     yield
-    lib.sps_set_conv_backend(0)
+    engine.set_defaults(conv_backend=0)
 
 
 def dev(a, dtype=torch.float32):
@@ -121,24 +120,41 @@ def test_coordinate_range_is_reported(engine_mod, state_dict):
     eng.status()  # sticky word was cleared
 
 
+def spread_state_dict(sd, pts, gain=8.0, voxel=0.1):
+    """A state_dict whose scores behave like a trained checkpoint's: the head is amplified so that the scores span
+    (0.05, 1) and the bias is moved so that the decision threshold eps = 0.84 (config/config.yaml:33) cuts through the
+    middle of the score distribution.  The random-init head alone squashes every score into [0.46, 0.84): a parity
+    bound measured there says nothing about thresholded labels."""
+    sd = amplified(sd, gain)
+    ref, _, _ = me_cpu.forward(pts, voxel, me_cpu.pack_weights(sd))
+    logit = np.log(ref.astype(np.float64) / (1.0 - ref.astype(np.float64) + 1e-12) + 1e-12)
+    shift = np.log(EPS / (1.0 - EPS)) - np.median(logit)
+    sd["final.bias"] = (sd["final.bias"] + np.float32(shift)).astype(np.float32)
+    return sd
+
+
 @pytest.mark.tensor_path
 @pytest.mark.parametrize("sensor,seed,submap", [("tiny", 3, "voxel"), ("hdl-32", 2, "voxel"), ("os1-64", 0, "radius")])
 def test_scores_match_oracle(engine_mod, state_dict, sensor, seed, submap):
+    """Default arithmetic (tcgen05 on fp16 rows + exact-fp32 FMA kernels on the 8-channel layers, fp32 level-0 tail)
+    against the fp32 oracle at the north-star bar: 2e-3 on the scores, >= 99.9 % equal labels -- on the contract
+    network AND on weights whose scores spread over (0,1) and straddle eps (1x tolerance for both)."""
     rows = make_case(sensor, seed=seed, submap=submap, n_map_poses=6)
     pts = rows[:, :5]
-    # the contract network (random init) must meet the 2e-3 bar: measured 4e-4 (fp16 rows) / 3.8e-4
-    # (TF32).  The second pass multiplies the head by 8 so that scores span (0.1, 1): a stress case outside the
-    # contract whose error grows with the gain (measured 2.2e-3 fp16 / 1.9e-3 TF32) -- bar 2x, labels still 99.9 %.
-    for sd, tol in ((state_dict, SCORE_TOL), (amplified(state_dict, 8.0), 2 * SCORE_TOL)):
+    for sd in (state_dict, spread_state_dict(state_dict, pts)):
         net = engine_mod.Net(sd)
         eng = engine_mod.Engine(len(pts))
         got = eng.forward(net, dev(pts), 0.1).cpu().numpy()
         eng.status()
         ref, _, _ = me_cpu.forward(pts, 0.1, me_cpu.pack_weights(sd))
         err = np.abs(got - ref)
-        assert err.max() < tol, f"max |score diff| {err.max():.3e}"
+        assert err.max() < SCORE_TOL, f"max |score diff| {err.max():.3e}"
         agree = np.mean(O.threshold_labels(got, EPS) == O.threshold_labels(ref, EPS))
         assert agree >= 0.999
+        if sd is not state_dict:      # the labels are really decided by the scores: both classes populated, wide spread
+            unstable = np.mean(ref >= EPS)
+            assert 0.2 < unstable < 0.8, unstable
+            assert sensor == "tiny" or (ref.min() < 0.3 and ref.max() > 0.95), (ref.min(), ref.max())
     if sensor == "tiny":
         ref64 = O.sps_forward(pts, 0.1, sd, dtype=np.float64)
         assert np.abs(got - ref64).max() < SCORE_TOL

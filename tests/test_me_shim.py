@@ -124,11 +124,9 @@ def test_layer_by_layer_shim_matches_fused_forward_and_oracle():
     scores = torch.sigmoid(out.features.reshape(-1)).cpu().numpy()
     ref = O.sps_forward(pts, 0.1, sd)
     assert np.abs(scores - ref).max() < 2e-5
-    lib = _cabi.load()
-    lib.sps_set_conv_backend(1)
     eng = engine.Engine(len(pts))
+    eng.set_conv_backend(1)
     fused = eng.forward(engine.Net(sd), torch.as_tensor(pts).cuda(), 0.1).cpu().numpy()
-    lib.sps_set_conv_backend(0)
     assert np.abs(scores - fused).max() < 2e-5
     # non-constant point features exercise the voxel mean
     f2 = torch.rand(len(coords), 1, device="cuda")

@@ -17,10 +17,9 @@ for gain in (1.0, 8.0, 40.0):
     ref, _, _ = me_cpu.forward(pts, 0.1, me_cpu.pack_weights(sd))
     net = engine.Net(sd); eng = engine.Engine(len(pts))
     line = [f"gain {gain:5.1f} spread [{ref.min():.3f},{ref.max():.3f}]"]
-    for b in (1, 2, 3):
-        lib.sps_set_conv_backend(b)
+    for b in (1, 2, 0):
+        eng.set_conv_backend(b)
         got = eng.forward(net, d, 0.1).cpu().numpy(); eng.status()
         e = np.abs(got - ref)
         line.append(f"backend {b}: max {e.max():.2e} mean {e.mean():.2e} label agree {np.mean((got < 0.84) == (ref < 0.84)):.5f}")
-    lib.sps_set_conv_backend(0)
     print(" | ".join(line))

@@ -9,8 +9,7 @@ import bench
 
 n_scans = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 if os.environ.get("SPS_PATTERN_SORT"):      # 0 never, 1 inputs >= 400k rows (default), 2 always
-    from sps_b200 import _cabi
-    assert _cabi.load().sps_set_pattern_sort(int(os.environ["SPS_PATTERN_SORT"])) == 0
+    engine.set_defaults(pattern_sort=int(os.environ["SPS_PATTERN_SORT"]))
 world = synth.World(0)
 traj = synth.loop_trajectory(radius=35.0, n=400)
 t0 = time.time()
