@@ -39,10 +39,9 @@ SENSOR, BATCH, VOXEL, N_DISTINCT = "os1-64", 8, 0.1, 2
 PTS_PER_SCAN = 65536
 WORKLOAD = "config2: os1-64 (65536 pts/scan) x batch 8 + radius-0.1m submap (duplicates kept), 0.1 m voxels"
 DTYPE = {0: "f16", 1: "f32", 2: "tf32", 3: "f16"}
-ARITH = {0: "fp16 operands and stored activations with fp32 accumulate on tcgen05 (layers with >= 16 output channels); "
-            "fp32 CUDA-core FMA with fp32 weights on the 8-output-channel layers; fp32 rows on the level-0 tail",
-         1: "fp32 CUDA cores", 2: "TF32 operands on fp32 rows (tcgen05), fp32 FMA on the 8-output-channel layers",
-         3: "as 0"}
+ARITH = {0: "fp16 operands and stored activations, fp32 accumulate and epilogue (tcgen05); 8-output-channel layers with "
+            "split hi+lo fp16 weights, level-0 tail (conv0 out, convtr7p2s2 out, block8) stored as fp16 hi|lo pairs",
+         1: "fp32 CUDA cores", 2: "TF32 operands on fp32 rows (tcgen05), fp32 accumulate", 3: "as 0"}
 
 
 def make_batches(rank: int, n_distinct=N_DISTINCT, batch=BATCH):
@@ -177,7 +176,7 @@ def stage_accounting(V, P3, P5, n_points, half_rows=True, planes=PLANES):
     acc["slices"] = {"bytes": sum(2 * 4 * P3[L] + V[L] * 16 for L in range(4))}
     eb = 2 if half_rows else 4
 
-    def esize(name):   # level-0 tail tensors stay fp32 rows in every mode
+    def esize(name):   # level-0 tail tensors: fp16 hi|lo pairs (4 bytes per value) in the fp16 forward, fp32 otherwise
         return 4 if name in ("conv1p1s2:in", "convtr7p2s2:out", "block8.conv1:in", "block8.conv1:out",
                              "block8.conv2+final:in", "block8.conv2+final:in2") else eb
     for name, kind, cin, cout, L, cin2 in conv_layers(planes):
@@ -196,7 +195,7 @@ def stage_accounting(V, P3, P5, n_points, half_rows=True, planes=PLANES):
         if name.endswith("+final"):
             b += vout * 4
             f += 2 * vout * cout
-        acc[name] = {"bytes": b, "flops": f, "tensor_core": cout >= 16}
+        acc[name] = {"bytes": b, "flops": f, "tensor_core": True}
     return acc
 
 

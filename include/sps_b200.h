@@ -96,14 +96,19 @@ int sps_unpack_coords(sps_ctx* ctx, int level, int32_t* d_out, void* stream);
 #define SPS_CONV_UP 1     /* transposed 2x2x2x1: out[child[k][c]] = in[c] @ W[k] for coarse rows c */
 
 #define SPS_TILE_SLICE_ENTRIES 82
-/* sps_conv_args.io_dtype: bit 0 = `in` rows are fp16, bit 1 = `in2` / `res` rows are fp16, bit 2 = `out` rows are fp16
- * (leading dimensions then count halves).  The tensor-core kernel takes all-fp32 (0) or all-fp16 (7) rows; the
- * 8-output-channel CUDA-core kernel takes any combination. */
 #define SPS_IO_F32 0
-#define SPS_IO_IN_F16 1
-#define SPS_IO_IN2_F16 2
-#define SPS_IO_OUT_F16 4
-#define SPS_IO_F16 7
+#define SPS_IO_F16 1
+/* sps_conv_args.flags (tensor-core path, fp16 rows): how the fused forward keeps the level-0 tail of the network at
+ * ~21 bits although every tensor-core operand is fp16 (tools/precision_study.py):
+ *   SPS_CONV_FOLD_LO    cout == 8: rows 8..15 of weight_kmajor hold the LOW parts of the weights (w - fp16(w), as
+ *                       fp16); the accumulator's columns 8..15 are added to columns 0..7 in the epilogue.  The
+ *                       N = 16 accumulator of an 8-channel layer has those columns anyway: split weights for free.
+ *   SPS_CONV_OUT_SPLIT  `out` rows are written as hi|lo pairs: per 8 channels 16 halves, [fp16(v) x 8 | fp16(v - hi) x 8]
+ *                       (out_ld counts halves of that doubled row).  A consumer reads such a row as 2 x cin fp16
+ *                       channels with its weights duplicated along K (sps_conv_pack_kmajor_f16x, SPS_PACK_IN_SPLIT):
+ *                       sum_c (hi_c + lo_c) * w_c, exact products, fp32 accumulation. */
+#define SPS_CONV_FOLD_LO 1
+#define SPS_CONV_OUT_SPLIT 2
 typedef struct sps_conv_args {
   int mode;                 /* SPS_CONV_NBR | SPS_CONV_UP                                    */
   int K;                    /* kernel volume (125, 81, 8, 1)                                 */
@@ -147,6 +152,7 @@ typedef struct sps_conv_args {
                                (same 10-bit mantissa as the TF32 operands, half the bytes per gathered row)   */
   int backend;              /* SPS_BACKEND_*: which kernel family serves this call (AUTO: tensor cores where
                                the layer shape and the optional inputs allow, CUDA cores otherwise)          */
+  int flags;                /* SPS_CONV_FOLD_LO | SPS_CONV_OUT_SPLIT (fp16 rows on the tensor-core path only) */
 } sps_conv_args;
 /* MinkowskiConvolution / MinkowskiConvolutionTranspose (+ folded MinkowskiBatchNorm, ReLU,
  * residual) forward: minkunet.py:55-158, resnet.py:97-108, ME BasicBlock.  Served by the tcgen05
@@ -257,10 +263,10 @@ int sps_submap_ball_query(const sps_ballmap* bm, const float* d_scan_xyz, int64_
 
 /* ---------------------------------------------------------------- arithmetic / processing order ---- */
 /* Which kernels serve the fused forward of a context (and, through sps_conv_args.backend, one sps_conv_fwd call):
- *   SPS_BACKEND_AUTO (0)  tcgen05 implicit GEMM on fp16 rows (fp16 operands, fp32 accumulate and epilogue) for the
- *                         layers with >= 16 output channels; fp32 CUDA-core FMA kernels with fp32 weights for the
- *                         8-output-channel layers; the level-0 tail of the network (conv0 output, convtr7p2s2,
- *                         block8) keeps fp32 rows, which is what holds the 2e-3 score bar on spread-out scores;
+ *   SPS_BACKEND_AUTO (0)  tcgen05 implicit GEMM on fp16 rows (fp16 operands, fp32 accumulate and epilogue); the
+ *                         8-output-channel layers carry split (hi + lo) fp16 weights in the spare accumulator columns
+ *                         and the level-0 tail of the network (conv0 output, convtr7p2s2, block8) stores its
+ *                         activations as fp16 hi|lo pairs -- what holds the 2e-3 score bar on spread-out scores;
  *   SPS_BACKEND_FP32 (1)  fp32 CUDA-core kernels everywhere (exact fp32);
  *   SPS_BACKEND_TF32 (2)  as AUTO but fp32 rows everywhere, TF32 operands in the tensor-core layers;
  *   SPS_BACKEND_F16  (3)  = AUTO regardless of build flags. */
@@ -278,6 +284,15 @@ int sps_ctx_set_pattern_sort(sps_ctx* ctx, int mode);
  * 8k groups of 8 channels). */
 int64_t sps_conv_kmajor_ld_f16(int K, int cin, int cin2);
 int sps_conv_pack_kmajor_f16(const float* w, int K, int cin, int cout, const float* w2, int cin2, void* out);
+/* The same with the two precision options of sps_conv_args.flags.  pack_flags: SPS_PACK_IN_SPLIT = `in` rows are
+ * hi|lo pairs (every 8-channel group of W[k] appears twice along K; the kernel is then called with cin = 2 x cin),
+ * SPS_PACK_IN2_SPLIT = the same for the fused 1x1 term, SPS_PACK_FOLD_LO = cout == 8 and rows 8..15 of the matrix hold
+ * the low parts of rows 0..7 (the matrix then has 16 rows).  ld and the packed rows count the DOUBLED channels. */
+#define SPS_PACK_IN_SPLIT 1
+#define SPS_PACK_IN2_SPLIT 2
+#define SPS_PACK_FOLD_LO 4
+int64_t sps_conv_kmajor_ld_f16x(int K, int cin, int cin2, int pack_flags);
+int sps_conv_pack_kmajor_f16x(const float* w, int K, int cin, int cout, const float* w2, int cin2, int pack_flags, void* out);
 /* Per-tile present-offset bitmasks of a kernel map (K <= 81) for the tensor-core path:
  * d_masks uint32 [ceil(n_out_max/128)][4]. */
 int sps_kernel_map_tile_masks(const int32_t* d_map, int64_t map_ld, int K, const int32_t* d_n_out,

@@ -44,6 +44,41 @@ def pack_kmajor_f16(weight: torch.Tensor, weight2: torch.Tensor | None = None) -
     return torch.as_tensor(out).to(weight.device)
 
 
+def pack_kmajor_f16x(weight: torch.Tensor, weight2: torch.Tensor | None = None, in_split=False, in2_split=False,
+                     fold_lo=False) -> torch.Tensor:
+    """``sps_conv_pack_kmajor_f16x``: the fp16 weight matrix with the precision options of the fused forward --
+    ``in_split`` / ``in2_split``: the rows of ``in`` / ``in2`` are hi|lo pairs (weights duplicated along K);
+    ``fold_lo`` (cout == 8): rows 8..15 hold the low parts of the weights (SPS_CONV_FOLD_LO)."""
+    lib = _cabi.load()
+    w = np.ascontiguousarray(weight.detach().cpu().numpy(), np.float32)
+    K, cin, cout = w.shape
+    w2 = None if weight2 is None else np.ascontiguousarray(weight2.detach().cpu().numpy(), np.float32)
+    cin2 = 0 if w2 is None else w2.shape[0]
+    flags = (1 if in_split else 0) | (2 if in2_split else 0) | (4 if fold_lo else 0)
+    ld = lib.sps_conv_kmajor_ld_f16x(K, cin, cin2, flags)
+    out = np.zeros((16 if fold_lo else cout, ld), np.float16)
+    check(lib.sps_conv_pack_kmajor_f16x(w.ctypes.data_as(C.c_void_p), K, cin, cout,
+                                        None if w2 is None else w2.ctypes.data_as(C.c_void_p), cin2, flags,
+                                        out.ctypes.data_as(C.c_void_p)), "sps_conv_pack_kmajor_f16x")
+    return torch.as_tensor(out).to(weight.device)
+
+
+def split_rows(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [V, C] (C multiple of 8) -> the hi|lo row format of SPS_CONV_OUT_SPLIT: fp16 [V, 2C], per 8 channels
+    [fp16(v) x 8 | fp16(v - hi) x 8] (test helper: the kernels produce this format themselves)."""
+    V, Cc = x.shape
+    hi = x.to(torch.float16)
+    lo = (x - hi.float()).to(torch.float16)
+    return torch.stack([hi.reshape(V, Cc // 8, 8), lo.reshape(V, Cc // 8, 8)], dim=2).reshape(V, 2 * Cc).contiguous()
+
+
+def merge_rows(x2: torch.Tensor) -> torch.Tensor:
+    """Inverse of :func:`split_rows`: fp16 hi|lo rows [V, 2C] -> fp32 [V, C]."""
+    V, C2 = x2.shape
+    g = x2.float().reshape(V, C2 // 16, 2, 8)
+    return (g[:, :, 0] + g[:, :, 1]).reshape(V, C2 // 2)
+
+
 def kernel_map_tile_masks(map, map_ld, K, n_out, n_out_max):
     """Present-offset bitmask per 128-row tile of a dense kernel map (tensor-core path input)."""
     lib = _cabi.load()
@@ -55,21 +90,22 @@ def kernel_map_tile_masks(map, map_ld, K, n_out, n_out_max):
 
 def conv_fwd(inp, weight, n_out, *, map=None, map_ld=0, mode=_cabi.SPS_CONV_NBR, shift=None, in2=None, weight2=None,
              res=None, relu=False, out=None, head_w=None, head_b=0.0, head_out=None, weight_kmajor=None,
-             round_out=False, n_out_max=None, backend=None, tile_mask=None, io_f16=False):
+             round_out=False, n_out_max=None, backend=None, tile_mask=None, io_f16=False, flags=0, cin=None, cin2=None):
     """out[o] = act(sum_k in[map[k][o]] @ W[k] (+ in2[o] @ W2) + shift (+ res[o])); ``n_out`` is a
     1-element int32 CUDA tensor (device-side count).  ``inp``/``out``/``in2``/``res`` may be
     channel slices (stride(0) is the leading dimension).  ``io_f16``: ``inp``/``in2``/``res``/``out`` are fp16
-    rows and ``weight_kmajor`` comes from :func:`pack_kmajor_f16` (SPS_IO_F16, the fused forward's format); a
-    3-tuple gives the formats of (in, in2/res, out) separately (the 8-output-channel FMA kernel takes any mix).
-    ``backend``: SPS_BACKEND_* of this one call (default AUTO) -- the library has no process-wide switch."""
+    rows and ``weight_kmajor`` comes from :func:`pack_kmajor_f16` (SPS_IO_F16, the fused forward's format).
+    ``flags``: SPS_CONV_FOLD_LO / SPS_CONV_OUT_SPLIT; ``cin`` / ``cin2``: channel counts the kernel sees when the rows are
+    hi|lo pairs (2 x the weight's).  ``backend``: SPS_BACKEND_* of this one call (default AUTO) -- the library has no
+    process-wide switch."""
     lib = _cabi.load()
     K = weight.shape[0] if weight.dim() == 3 else 1
     cin, cout = weight.shape[-2], weight.shape[-1]
     if n_out_max is None:
         n_out_max = int(n_out.item())
     if out is None and head_out is None:
-        out_f16 = io_f16[2] if isinstance(io_f16, (tuple, list)) else io_f16
-        out = torch.empty((max(n_out_max, 1), cout), dtype=torch.float16 if out_f16 else torch.float32, device=inp.device)
+        width = 2 * cout if (flags & _cabi.SPS_CONV_OUT_SPLIT) else cout
+        out = torch.empty((max(n_out_max, 1), width), dtype=torch.float16 if io_f16 else torch.float32, device=inp.device)
     a = _cabi.ConvArgs()
     a.mode, a.K, a.cin, a.cout = mode, K, cin, cout
     a.map, a.map_ld = (map.data_ptr() if map is not None else None), int(map_ld)
@@ -89,11 +125,13 @@ def conv_fwd(inp, weight, n_out, *, map=None, map_ld=0, mode=_cabi.SPS_CONV_NBR,
     if weight_kmajor is not None:
         a.weight_kmajor, a.kmajor_ld = weight_kmajor.data_ptr(), weight_kmajor.stride(0)
     a.round_out = int(round_out)
-    if isinstance(io_f16, (tuple, list)):      # (in, in2/res, out) row formats given separately
-        a.io_dtype = (1 if io_f16[0] else 0) | (2 if io_f16[1] else 0) | (4 if io_f16[2] else 0)
-    else:
-        a.io_dtype = _cabi.SPS_IO_F16 if io_f16 else _cabi.SPS_IO_F32
+    a.io_dtype = _cabi.SPS_IO_F16 if io_f16 else _cabi.SPS_IO_F32
     a.backend = int(backend) if backend is not None else _cabi.SPS_BACKEND_AUTO
+    a.flags = int(flags)
+    if cin is not None:        # hi|lo input rows: the kernel sees the doubled channel count
+        a.cin = int(cin)
+    if cin2 is not None:
+        a.cin2 = int(cin2)
     if weight_kmajor is not None and map is not None and tile_mask is None and K <= 81:
         tile_mask = kernel_map_tile_masks(map, map_ld, K, n_out, n_out_max)
     if tile_mask is not None:

@@ -79,22 +79,16 @@ static size_t carve(sps_ctx* c, void* base, int64_t max_points) {
 
 int conv_simt(const sps_conv_args& a, cudaStream_t st);
 int conv_umma(const sps_conv_args& a, cudaStream_t st);
-int conv_fma8(const sps_conv_args& a, cudaStream_t st);
 bool conv_umma_supports(const sps_conv_args& a);
 bool conv_umma_f16_supports(const sps_conv_args& a);
-bool conv_fma8_supports(const sps_conv_args& a);
 
 // Kernel family of one convolution call (sps_conv_args.backend; the fused forward passes its context's mode):
-//   FP32: CUDA-core fp32 kernels.  TF32 / F16: the tensor-core kernel whenever the call fits it.  AUTO: the
-//   8-output-channel FMA kernel where it fits, else the tensor-core kernel, else the generic CUDA-core kernel.
+// FP32 -> the fp32 CUDA-core kernels; otherwise the tcgen05 kernel whenever the call fits it (fp16 rows: always, there
+// is no CUDA-core kernel for them), else the CUDA-core kernels.
 int conv_dispatch(const sps_conv_args& a, cudaStream_t st) {
-  const bool mixed = a.io_dtype != SPS_IO_F32 && a.io_dtype != SPS_IO_F16;
-  if (a.backend == SPS_BACKEND_FP32) return a.io_dtype == SPS_IO_F32 ? conv_simt(a, st) : SPS_ERR_UNSUPPORTED;
-  if (a.backend == SPS_BACKEND_AUTO && conv_fma8_supports(a)) return conv_fma8(a, st);
-  if (a.io_dtype == SPS_IO_F16 && conv_umma_f16_supports(a)) return conv_umma(a, st);
-  if (a.io_dtype == SPS_IO_F32 && conv_umma_supports(a)) return conv_umma(a, st);
-  if (conv_fma8_supports(a)) return conv_fma8(a, st);
-  if (mixed || a.io_dtype == SPS_IO_F16) return SPS_ERR_UNSUPPORTED;
+  if (a.io_dtype == SPS_IO_F16) return conv_umma_f16_supports(a) ? conv_umma(a, st) : SPS_ERR_UNSUPPORTED;
+  if (a.flags) return SPS_ERR_UNSUPPORTED;      // split-precision options exist on fp16 rows only
+  if (a.backend != SPS_BACKEND_FP32 && conv_umma_supports(a)) return conv_umma(a, st);
   return conv_simt(a, st);
 }
 

@@ -11,14 +11,31 @@ namespace sps {
 // mode 0: fp32 as computed; 1: fp32 rounded to TF32 (nearest), so a tensor-core consumer does not truncate;
 // 2: fp16 rows (`out` then points at __half, out_ld counts halves) -- same 10-bit mantissa as TF32, half the
 // bytes per gathered row; saturating conversion (|x| > 65504 -> +-65504).
-enum { kStoreF32 = 0, kStoreTF32 = 1, kStoreF16 = 2 };
+// mode 3: fp16 hi|lo pairs -- per 8 channels 16 halves [fp16(v) x 8 | fp16(v - hi) x 8], ~21 bits per value; the consumer
+// contracts such a row as 2 x 8 fp16 channels against weights duplicated along K (exact products, fp32 accumulation).
+enum { kStoreF32 = 0, kStoreTF32 = 1, kStoreF16 = 2, kStoreF16x2 = 3 };
 __device__ __forceinline__ uint32_t pack_half2_sat(float a, float b) {
   uint32_t r;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // low half = a
   return r;
 }
 __device__ __forceinline__ void store_row8(float* out, int64_t out_ld, int64_t row, const float (&v)[8], int mode) {
-  if (mode == kStoreF16) {
+  if (mode == kStoreF16x2) {
+    // `out` already points at the 16-half slot of this channel group inside the (doubled) row
+    __half* op = reinterpret_cast<__half*>(out) + row * out_ld;
+    float lo[8];
+    uint32_t hi[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      hi[j] = pack_half2_sat(v[2 * j], v[2 * j + 1]);
+      const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi[j]));
+      lo[2 * j] = v[2 * j] - h.x;          // exact in fp32 (unless hi saturated: then lo saturates too)
+      lo[2 * j + 1] = v[2 * j + 1] - h.y;
+    }
+    *reinterpret_cast<uint4*>(op) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(op + 8) = make_uint4(pack_half2_sat(lo[0], lo[1]), pack_half2_sat(lo[2], lo[3]),
+                                                   pack_half2_sat(lo[4], lo[5]), pack_half2_sat(lo[6], lo[7]));
+  } else if (mode == kStoreF16) {
     __half* op = reinterpret_cast<__half*>(out) + row * out_ld;
     *reinterpret_cast<uint4*>(op) = make_uint4(pack_half2_sat(v[0], v[1]), pack_half2_sat(v[2], v[3]),
                                                pack_half2_sat(v[4], v[5]), pack_half2_sat(v[6], v[7]));

@@ -298,19 +298,19 @@ int conv_simt(const sps_conv_args& a, cudaStream_t st) {
 extern "C" int sps_conv_fwd(const sps_conv_args* a, void* stream) {
   if (!a || !a->in || !a->weight || !a->n_out || (!a->out && !a->head_out)) return SPS_ERR_BAD_ARG;
   if (a->mode != SPS_CONV_NBR && a->mode != SPS_CONV_UP) return SPS_ERR_BAD_ARG;
-  if (a->backend < SPS_BACKEND_AUTO || a->backend > SPS_BACKEND_F16 || (a->io_dtype & ~SPS_IO_F16)) return SPS_ERR_BAD_ARG;
+  if (a->backend < SPS_BACKEND_AUTO || a->backend > SPS_BACKEND_F16) return SPS_ERR_BAD_ARG;
+  if ((a->io_dtype != SPS_IO_F32 && a->io_dtype != SPS_IO_F16) || (a->flags & ~(SPS_CONV_FOLD_LO | SPS_CONV_OUT_SPLIT)))
+    return SPS_ERR_BAD_ARG;
   if (a->mode == SPS_CONV_UP && (!a->map || a->K != 8 || !a->out || a->in2 || a->res || a->head_out || (a->cin & 3)))
     return SPS_ERR_BAD_ARG;
   if (a->mode == SPS_CONV_NBR && !a->map && a->K != 1) return SPS_ERR_BAD_ARG;
-  // element counts per 16 bytes of the three row formats (fp32: 4, fp16: 8)
-  const int ea = (a->io_dtype & SPS_IO_IN_F16) ? 8 : 4, e2 = (a->io_dtype & SPS_IO_IN2_F16) ? 8 : 4,
-            eo = (a->io_dtype & SPS_IO_OUT_F16) ? 8 : 4;
+  const int ea = a->io_dtype == SPS_IO_F16 ? 8 : 4;   // elements per 16 bytes of a row
   if (a->cin < 1 || (a->cin != 1 && a->cin % ea) || (a->in_ld % ea && a->cin != 1)) return SPS_ERR_BAD_ARG;
-  if (a->in2 && (!a->weight2 || a->cin2 % e2 || a->in2_ld % e2)) return SPS_ERR_BAD_ARG;
+  if (a->in2 && (!a->weight2 || a->cin2 % ea || a->in2_ld % ea)) return SPS_ERR_BAD_ARG;
   const bool narrow = a->K == 1 && !a->map && a->cout < 8 && a->io_dtype == SPS_IO_F32;   // scalar kernel, no vector alignment needed
   if (narrow) return sps::conv_dispatch(*a, (cudaStream_t)stream);
-  if (a->out && a->out_ld % eo) return SPS_ERR_BAD_ARG;
-  if (a->res && a->res_ld % e2) return SPS_ERR_BAD_ARG;
+  if (a->out && a->out_ld % ea) return SPS_ERR_BAD_ARG;
+  if (a->res && a->res_ld % ea) return SPS_ERR_BAD_ARG;
   if (a->head_out && (a->cout != 8 || !a->head_w)) return SPS_ERR_BAD_ARG;
   if (a->n_out_max < 0) return SPS_ERR_BAD_ARG;
   const uintptr_t al = (uintptr_t)a->weight | (uintptr_t)a->out | (uintptr_t)a->in2 | (uintptr_t)a->weight2 |

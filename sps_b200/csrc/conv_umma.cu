@@ -99,7 +99,7 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
 // 16-byte group, so a stage carries twice the channels).  GPC = 16-byte groups per kernel offset: 1 (fp16
 // only), 2 or 4 -> 8/GPC offsets share a stage; 8 -> one offset spans GP/8 stages.
 template <int NPAD, int GPC, typename T>
-__global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_args a, const UmmaParams p) {
+__global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_args a, const __grid_constant__ UmmaParams p) {
   using Cfg = V6Cfg<NPAD>;
   constexpr int EB = sizeof(T);                         // bytes per stored activation
   constexpr bool kHalf = EB == 2;
@@ -136,6 +136,12 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < 64) sshift[tid] = (a.shift && tid < a.cout) ? __ldg(a.shift + tid) : 0.f;
+  // Weight stages by TMA: a full-width K slab (64 fp16 channels of one kernel offset, all NPAD rows) is ONE 2-D box of
+  // the K-major weight matrix, landed in the SWIZZLE_128B layout the MMA descriptor reads -- off the LSU path that
+  // the gathers saturate.  Narrower slabs (several offsets per stage) would need one small box per offset: those
+  // layers keep the cp.async weight copies.
+  const bool tma_b = kHalf && GPC == 8 && p.use_tma != 0;
+  if (tma_b && tid == 0) tma_prefetch_desc(&p.tmap);
   if (warp == kV6MmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)Cfg::kTmemCols)
@@ -186,7 +192,7 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
       const int n = r0 + 32 * i;
-      wok[i] = n < a.cout && n < NPAD;
+      wok[i] = n < ((p.flags & SPS_CONV_FOLD_LO) ? 16 : a.cout) && n < NPAD;
       wrow[i] = reinterpret_cast<const char*>(p.wt) + (int64_t)(wok[i] ? n : 0) * p.ldk * EB;
       b_off[i] = (uint32_t)((n >> 3) * 1024 + (n & 7) * 128) + (((uint32_t)cB ^ (uint32_t)(n & 7)) << 4);
     }
@@ -289,7 +295,12 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
             const uint32_t row = (uint32_t)(idx[i] < 0 ? 0 : idx[i]);
             cp_async16_or_zero<SPS_V6_A_CG != 0>(dstA + a_off[i], base + (uint64_t)row * ld_b, !ok);
           }
-          if (b_lane) {
+          if (tma_b) {
+            if (tid == 0) {   // thread 0 holds column 0 of the slab: wofs = byte offset of the slab in a weight row
+              mbar_expect_tx(bar_full + 8 * s, (uint32_t)kBStageBytes);
+              tma_load_2d(sB_u + (uint32_t)s * kBStageBytes, &p.tmap, (int)(wofs >> 1), 0, bar_full + 8 * s);
+            }
+          } else if (b_lane) {
 #pragma unroll
             for (int i = 0; i < NB; ++i)
               cp_async16_or_zero<SPS_V6_B_CG != 0>(sB_u + (uint32_t)s * kBStageBytes + b_off[i], wrow[i] + wofs, !(bok && wok[i]));
@@ -445,6 +456,10 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
         for (int c = 0; c < NPAD; ++c) acc[c] = 0.f;
       }
       if (row < 0) continue;
+      if (NPAD == 16 && (p.flags & SPS_CONV_FOLD_LO)) {   // columns 8..15 = the row times the LOW parts of the weights
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] += acc[c + 8];
+      }
 #pragma unroll
       for (int c = 0; c < NPAD; c += 8)
         if (c < cout) {
@@ -484,7 +499,8 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
         for (int c = 0; c < NPAD; c += 8)
           if (c < cout) {
             const float v8[8] = {acc[c], acc[c + 1], acc[c + 2], acc[c + 3], acc[c + 4], acc[c + 5], acc[c + 6], acc[c + 7]};
-            store_row8(a.out + (kHalf ? c / 2 : c), a.out_ld, row, v8, kHalf ? kStoreF16 : (p.round_out ? kStoreTF32 : kStoreF32));
+            if (kHalf && (p.flags & SPS_CONV_OUT_SPLIT)) store_row8(a.out + c, a.out_ld, row, v8, kStoreF16x2);   // 16 halves per 8 channels
+            else store_row8(a.out + (kHalf ? c / 2 : c), a.out_ld, row, v8, kHalf ? kStoreF16 : (p.round_out ? kStoreTF32 : kStoreF32));
           }
       }
     }
@@ -497,8 +513,38 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
                  : "memory");
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (the library does not link libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    if (getenv("SPS_NO_TMA_B")) return nullptr;     // A/B switch: weight stages through cp.async everywhere
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+// 2-D map of the fp16 K-major weight matrix [cout][ldk]: box = 64 halves (one 128-byte swizzle row) x npad rows
+static bool make_weight_tmap(CUtensorMap* m, const void* wt, int64_t ldk, int cout, int npad) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc || (ldk & 7) || (reinterpret_cast<uintptr_t>(wt) & 15)) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)ldk, (cuuint64_t)cout};
+  const cuuint64_t strides[1] = {(cuuint64_t)ldk * 2};
+  const cuuint32_t box[2] = {64, (cuuint32_t)npad};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(wt), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int NPAD, int GPC, typename T>
-static int launch_umma6(const sps_conv_args& a, const UmmaParams& p, cudaStream_t st) {
+static int launch_umma6(const sps_conv_args& a, const UmmaParams& p_in, cudaStream_t st) {
+  UmmaParams p = p_in;
+  if (sizeof(T) == 2 && GPC == 8) p.use_tma = make_weight_tmap(&p.tmap, p.wt, p.ldk, (a.flags & SPS_CONV_FOLD_LO) ? 16 : a.cout, NPAD) ? 1 : 0;
   const size_t smem = V6Cfg<NPAD>::smem;
   static unsigned long long attr_done = 0;   // bit per device: the opt-in is per device and per kernel
   SPS_CUDA_CHECK(ensure_dynamic_smem(k_conv_umma6<NPAD, GPC, T>, smem, &attr_done));
@@ -533,9 +579,11 @@ static int conv_umma6_t(const sps_conv_args& a, const UmmaParams& p, cudaStream_
 
 int conv_umma(const sps_conv_args& a, cudaStream_t st) {
   UmmaParams p;
+  memset(&p, 0, sizeof(p));
   p.wt = a.weight_kmajor;
   p.ldk = a.kmajor_ld;
   p.round_out = a.round_out;
+  p.flags = a.flags;
   return a.io_dtype == SPS_IO_F16 ? conv_umma6_t<__half>(a, p, st) : conv_umma6_t<float>(a, p, st);
 }
 
@@ -582,29 +630,61 @@ bool conv_umma_f16_supports(const sps_conv_args& a) {
   if (a.out && (a.out_ld & 7)) return false;
   if (!(a.cout == 8 || a.cout == 16 || a.cout == 32 || a.cout == 64)) return false;
   if (a.kmajor_ld & 7) return false;
+  if ((a.flags & SPS_CONV_FOLD_LO) && a.cout != 8) return false;
+  if ((a.flags & SPS_CONV_OUT_SPLIT) && a.out && (a.out_ld & 15)) return false;
   return true;
 }
 
 }  // namespace sps
 
 // fp16 twin of sps_conv_pack_kmajor: ME-layout weights [K][cin][cout] (+ optional 1x1 term [cin2][cout]) ->
-// K-major __half [cout][ld]; per kernel offset padded_groups_of(cin/8) * 8 halves, the 1x1 term padded to 64.
-extern "C" int64_t sps_conv_kmajor_ld_f16(int K, int cin, int cin2) {
-  return (int64_t)K * sps::padded_groups_of((cin + 7) >> 3, true) * 8 + ((cin2 + 63) & ~63);
+// K-major __half [rows][ld]; per kernel offset padded_groups_of(cin_eff/8) * 8 halves, the 1x1 term padded to 64.
+// pack_flags (include/sps_b200.h): SPS_PACK_IN_SPLIT / SPS_PACK_IN2_SPLIT double the channels of `in` / `in2` (rows stored
+// as hi|lo pairs: every 8-channel group of the weights appears twice along K), SPS_PACK_FOLD_LO appends the low parts
+// of the weights as rows 8..15 (cout == 8).
+extern "C" int64_t sps_conv_kmajor_ld_f16x(int K, int cin, int cin2, int pack_flags) {
+  const int ce = (pack_flags & SPS_PACK_IN_SPLIT) ? 2 * cin : cin, c2e = (pack_flags & SPS_PACK_IN2_SPLIT) ? 2 * cin2 : cin2;
+  return (int64_t)K * sps::padded_groups_of((ce + 7) >> 3, true) * 8 + ((c2e + 63) & ~63);
 }
-extern "C" int sps_conv_pack_kmajor_f16(const float* w, int K, int cin, int cout, const float* w2, int cin2, void* out_) {
+extern "C" int sps_conv_pack_kmajor_f16x(const float* w, int K, int cin, int cout, const float* w2, int cin2, int pack_flags,
+                                         void* out_) {
   if (!w || !out_ || K < 1 || cin < 1 || cout < 1 || (w2 == nullptr) != (cin2 == 0)) return SPS_ERR_BAD_ARG;
+  const bool in_split = pack_flags & SPS_PACK_IN_SPLIT, in2_split = pack_flags & SPS_PACK_IN2_SPLIT,
+             fold = pack_flags & SPS_PACK_FOLD_LO;
+  if (fold && cout != 8) return SPS_ERR_BAD_ARG;
+  if ((in_split && (cin & 7)) || (in2_split && (cin2 & 7))) return SPS_ERR_BAD_ARG;
   __half* out = static_cast<__half*>(out_);
-  const int64_t ldk = sps_conv_kmajor_ld_f16(K, cin, cin2);
-  const int cpad = sps::padded_groups_of((cin + 7) >> 3, true) * 8;
-  for (int n = 0; n < cout; ++n) {
-    __half* row = out + (int64_t)n * ldk;
+  const int64_t ldk = sps_conv_kmajor_ld_f16x(K, cin, cin2, pack_flags);
+  const int ce = in_split ? 2 * cin : cin;
+  const int cpad = sps::padded_groups_of((ce + 7) >> 3, true) * 8;
+  const int rows = fold ? 16 : cout;
+  // position of input channel ci inside its (possibly doubled) block, and of its low-half twin
+  auto pos = [](int ci, bool split) { return split ? (ci >> 3) * 16 + (ci & 7) : ci; };
+  for (int r = 0; r < rows; ++r) {
+    __half* row = out + (int64_t)r * ldk;
     for (int64_t i = 0; i < ldk; ++i) row[i] = __float2half_rn(0.f);
+    const int nn = fold ? (r & 7) : r;      // output channel this row belongs to
+    auto val = [&](float x) {
+      const __half hi = __float2half_rn(x);
+      return (fold && r >= 8) ? __float2half_rn(x - __half2float(hi)) : hi;
+    };
     for (int k = 0; k < K; ++k)
-      for (int ci = 0; ci < cin; ++ci) row[(int64_t)k * cpad + ci] = __float2half_rn(w[((int64_t)k * cin + ci) * cout + n]);
-    for (int ci = 0; ci < cin2; ++ci) row[(int64_t)K * cpad + ci] = __float2half_rn(w2[(int64_t)ci * cout + n]);
+      for (int ci = 0; ci < cin; ++ci) {
+        const __half v = val(w[((int64_t)k * cin + ci) * cout + nn]);
+        row[(int64_t)k * cpad + pos(ci, in_split)] = v;
+        if (in_split) row[(int64_t)k * cpad + pos(ci, true) + 8] = v;
+      }
+    for (int ci = 0; ci < cin2; ++ci) {
+      const __half v = val(w2[(int64_t)ci * cout + nn]);
+      row[(int64_t)K * cpad + pos(ci, in2_split)] = v;
+      if (in2_split) row[(int64_t)K * cpad + pos(ci, true) + 8] = v;
+    }
   }
   return SPS_OK;
+}
+extern "C" int64_t sps_conv_kmajor_ld_f16(int K, int cin, int cin2) { return sps_conv_kmajor_ld_f16x(K, cin, cin2, 0); }
+extern "C" int sps_conv_pack_kmajor_f16(const float* w, int K, int cin, int cout, const float* w2, int cin2, void* out) {
+  return sps_conv_pack_kmajor_f16x(w, K, cin, cout, w2, cin2, 0, out);
 }
 
 extern "C" int sps_kernel_map_tile_masks(const int32_t* d_map, int64_t map_ld, int K, const int32_t* d_n_out,

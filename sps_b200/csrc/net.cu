@@ -25,6 +25,8 @@ struct ConvW {
   int64_t ldk = 0;
   float* wth = nullptr;    // K-major fp16 copy (every conv but conv0): the fp16-storage forward
   int64_t ldkh = 0;
+  int pack_flags = 0;      // SPS_PACK_*: how `wth` was packed (split inputs double the K columns, folded low parts add rows)
+  int conv_flags = 0;      // SPS_CONV_*: what the fp16 forward asks of the kernel for this layer
   int K = 0, cin = 0, cout = 0, cin2 = 0;
 };
 
@@ -127,9 +129,11 @@ extern "C" int sps_net_finalize(sps_net* net, void* d_weights, size_t bytes, voi
   // fp16 K-major copy, stored inside the float image (two halves per float slot)
   auto add_kmajor_h = [&](Pending& p, const std::vector<float>& w, int K, int cin, int cout,
                           const std::vector<float>* w2, int cin2) {
-    const int64_t ldk = sps_conv_kmajor_ld_f16(K, cin, cin2);
-    std::vector<float> wt(((size_t)cout * ldk + 1) / 2);
-    sps_conv_pack_kmajor_f16(w.data(), K, cin, cout, w2 ? w2->data() : nullptr, cin2, wt.data());
+    const int pf = p.cw->pack_flags;
+    const int64_t ldk = sps_conv_kmajor_ld_f16x(K, cin, cin2, pf);
+    const int rows = (pf & SPS_PACK_FOLD_LO) ? 16 : cout;
+    std::vector<float> wt(((size_t)rows * ldk + 1) / 2);
+    sps_conv_pack_kmajor_f16x(w.data(), K, cin, cout, w2 ? w2->data() : nullptr, cin2, pf, wt.data());
     p.cw->ldkh = ldk;
     p.wth = pk.add(wt);
     p.has_wth = true;
@@ -144,23 +148,34 @@ extern "C" int sps_net_finalize(sps_net* net, void* d_weights, size_t bytes, voi
     p.has_wt = true;
   };
   std::vector<Pending> pend;
-  auto add_conv = [&](ConvW& cw, const std::string& kname, const std::string& bn, int K, int cin, int cout) {
+  // Precision plan of the fp16 forward (tools/precision_study.py): every 8-output-channel layer carries the low parts of
+  // its weights in the spare accumulator columns (free); the level-0 tail -- conv0's output, convtr7p2s2's output and
+  // block8.conv1's output -- is stored as fp16 hi|lo pairs and read back as doubled channels.
+  auto plan = [](ConvW& cw, int cout, bool in_split, bool in2_split, bool out_split) {
+    cw.pack_flags = (cout == 8 ? SPS_PACK_FOLD_LO : 0) | (in_split ? SPS_PACK_IN_SPLIT : 0) | (in2_split ? SPS_PACK_IN2_SPLIT : 0);
+    cw.conv_flags = (cout == 8 ? SPS_CONV_FOLD_LO : 0) | (out_split ? SPS_CONV_OUT_SPLIT : 0);
+  };
+  auto add_conv = [&](ConvW& cw, const std::string& kname, const std::string& bn, int K, int cin, int cout,
+                      bool in_split = false, bool out_split = false) {
     std::vector<float> w; std::vector<double> sh;
     if (!fold_conv(net, kname, bn, K, cin, cout, w, sh)) return false;
     std::vector<float> shf(sh.begin(), sh.end());
     cw.K = K; cw.cin = cin; cw.cout = cout; cw.cin2 = 0;
+    plan(cw, cout, in_split, false, out_split);
     Pending p{&cw, pk.add(w), pk.add(shf), 0, false};
     if (K == 81 || (K == 8 && cin >= 16 && cin % 4 == 0)) add_kmajor(p, w, K, cin, cout, nullptr, 0);  // 8-channel 2x2x2 layers stay on the CUDA-core kernel (measured faster)
     if (K == 81 || K == 8) add_kmajor_h(p, w, K, cin, cout, nullptr, 0);
     pend.push_back(p);
     return true;
   };
-  auto add_block = [&](int b, const std::string& name, int cin, int cout) {
-    if (!add_conv(net->blk1[b], name + ".0.conv1.kernel", name + ".0.norm1", 81, cin, cout)) return false;
+  auto add_block = [&](int b, const std::string& name, int cin, int cout, bool tail = false) {
+    // tail = block8: its input (the level-0 concat buffer) and conv1's output are hi|lo rows
+    if (!add_conv(net->blk1[b], name + ".0.conv1.kernel", name + ".0.norm1", 81, cin, cout, tail, tail)) return false;
     std::vector<float> w; std::vector<double> sh;
     if (!fold_conv(net, name + ".0.conv2.kernel", name + ".0.norm2", 81, cout, cout, w, sh)) return false;
     ConvW& cw = net->blk2[b];
     cw.K = 81; cw.cin = cout; cw.cout = cout; cw.cin2 = 0;
+    plan(cw, cout, tail, tail && cin != cout, false);
     Pending p{&cw, pk.add(w), 0, 0, false};
     if (cin != cout) {
       std::vector<float> w2; std::vector<double> sh2;
@@ -190,14 +205,14 @@ extern "C" int sps_net_finalize(sps_net* net, void* d_weights, size_t bytes, voi
   const char* dec_b[4] = {"bntr4", "bntr5", "bntr6", "bntr7"};
   int inpl = I;
   for (int i = 0; i < 4 && ok; ++i) {
-    ok = ok && add_conv(net->down[i], std::string(enc_c[i]) + ".kernel", enc_b[i], 8, inpl, inpl);
+    ok = ok && add_conv(net->down[i], std::string(enc_c[i]) + ".kernel", enc_b[i], 8, inpl, inpl, /*in_split=*/i == 0);   // conv1p1s2 reads skip0
     ok = ok && add_block(i, "block" + std::to_string(i + 1), inpl, P[i]);
     inpl = P[i];
   }
   const int skip[4] = {P[2], P[1], P[0], I};
   for (int i = 0; i < 4 && ok; ++i) {
-    ok = ok && add_conv(net->up[i], std::string(dec_c[i]) + ".kernel", dec_b[i], 8, inpl, P[4 + i]);
-    ok = ok && add_block(4 + i, "block" + std::to_string(5 + i), P[4 + i] + skip[i], P[4 + i]);
+    ok = ok && add_conv(net->up[i], std::string(dec_c[i]) + ".kernel", dec_b[i], 8, inpl, P[4 + i], false, /*out_split=*/i == 3);
+    ok = ok && add_block(4 + i, "block" + std::to_string(5 + i), P[4 + i] + skip[i], P[4 + i], /*tail=*/i == 3);
     inpl = P[4 + i];
   }
   const std::vector<float>*fw, *fb;
@@ -260,31 +275,34 @@ struct ConvIo {
   int mode; const int32_t* map;
 };
 
-// One layer of the fused forward.  Kernel family by arithmetic mode of the context and by layer shape:
-//   FP32 mode: generic fp32 CUDA-core kernels.  Otherwise: 8 output channels -> the fp32 FMA kernel (exact weights),
-//   >= 16 output channels -> the tcgen05 kernel on fp16 rows (AUTO / F16) or TF32 operands on fp32 rows (TF32).
+// One layer of the fused forward.  FP32 mode: generic fp32 CUDA-core kernels; TF32 mode: fp32 rows, the tcgen05 kernel
+// with TF32 operands where the layer fits it; AUTO / F16: fp16 rows through the tcgen05 kernel, with the layer's
+// precision plan (folded low weight parts, hi|lo rows: sps_net_finalize).
 static int run_conv(sps_ctx* c, const ConvIo& io, const char* name, const ConvW& w, const int32_t* n_out, int64_t n_out_max,
-                    Act in, Act in2, Act res, Act out, bool round_out, cudaStream_t st, const float* head_w = nullptr,
+                    Act in, Act in2, Act res, Act out, cudaStream_t st, const float* head_w = nullptr,
                     float head_b = 0.f, float* head_out = nullptr) {
   sps_conv_args a;
   memset(&a, 0, sizeof(a));
+  const bool half = c->run_half;
   a.mode = io.mode; a.K = w.K; a.cin = w.cin; a.cout = w.cout;
   a.map = io.map; a.map_ld = c->ld; a.n_out = n_out; a.n_out_max = n_out_max;
   a.in = in.p; a.in_ld = in.ld; a.weight = w.w; a.shift = w.shift;
   if (in2.p) { a.in2 = in2.p; a.in2_ld = in2.ld; a.cin2 = w.cin2; a.weight2 = w.w2; }
   a.res = res.p; a.res_ld = res.ld; a.relu = 1; a.out = out.p; a.out_ld = out.ld;
   a.head_w = head_w; a.head_b = head_b; a.head_out = head_out;
-  const bool side_f16 = in2.p ? in2.f16 : res.p ? res.f16 : in.f16;
-  a.io_dtype = (in.f16 ? SPS_IO_IN_F16 : 0) | (side_f16 ? SPS_IO_IN2_F16 : 0) | ((out.p ? out.f16 : in.f16) ? SPS_IO_OUT_F16 : 0);
-  const bool fma = c->backend != SPS_BACKEND_FP32 && w.cout == 8 && io.mode == SPS_CONV_NBR;
-  if (!fma && c->backend != SPS_BACKEND_FP32) {
-    if (a.io_dtype != SPS_IO_F16 && a.io_dtype != SPS_IO_F32) return SPS_ERR_STATE;   // the tensor-core kernel takes one row format
-    a.weight_kmajor = c->run_half ? w.wth : w.wt; a.kmajor_ld = c->run_half ? w.ldkh : w.ldk;
+  if (half) {
+    if ((w.pack_flags & SPS_PACK_IN_SPLIT)) a.cin = 2 * w.cin;        // hi|lo rows read as doubled channels
+    if (in2.p && (w.pack_flags & SPS_PACK_IN2_SPLIT)) a.cin2 = 2 * w.cin2;
+    a.flags = w.conv_flags;
+    a.io_dtype = SPS_IO_F16;
+    a.weight_kmajor = w.wth; a.kmajor_ld = w.ldkh;
+  } else {
+    a.io_dtype = SPS_IO_F32;
+    a.weight_kmajor = w.wt; a.kmajor_ld = w.ldk;
   }
   a.tile_mask = io.tmask; a.perm = io.perm; a.tile_slices = io.perm ? io.slices : nullptr;
-  a.round_out = round_out;
-  // FMA layers go to their kernel explicitly (AUTO prefers it anyway); the other layers take the context's family
-  a.backend = c->backend == SPS_BACKEND_FP32 ? SPS_BACKEND_FP32 : fma ? SPS_BACKEND_AUTO : c->run_half ? SPS_BACKEND_F16 : SPS_BACKEND_TF32;
+  a.round_out = c->backend != SPS_BACKEND_FP32;   // pure fp32 mode keeps full-precision activations
+  a.backend = c->backend;
   ++c->forward_launches;
   const int rc = conv_dispatch(a, st);
   prof_mark(c, name, st);
@@ -305,15 +323,17 @@ int unet_forward(sps_ctx* c, const sps_net* net, const float* feat0, float* logi
   float** B = c->buf;
   using C = sps_ctx;
   const bool exact = c->backend == SPS_BACKEND_FP32;
-  const bool hm = ctx_half_storage(c);     // fp16 rows (except the level-0 tail, which is fp32 in every mode)
+  // fp16 rows need conv0's output in the hi|lo format, which only the fused forward's conv0 kernels write
+  const bool hm = ctx_half_storage(c) && conv0_done;
   c->run_half = hm;
-  const bool rnd = c->backend == SPS_BACKEND_TF32;   // fp32 rows that a TF32 tensor-core layer reads are stored rounded (cvt.rna)
-  // Storage plan.  Level-0 tail (conv0 output = skip0, convtr7p2s2 output, block8.conv1 output): fp32 rows in every
-  // mode -- their rounding is what dominated the score error of fp16 storage (tools/precision_study.py).
-  const Act cat8(B[C::CAT8], kCatLd[0], false), h8(B[C::H8], 8, false);
+  // Storage plan.  fp16 forward: plain fp16 rows, except the level-0 tail -- the concat buffer [convtr7p2s2 out | skip0]
+  // and block8.conv1's output -- whose rows are fp16 hi|lo pairs (16 halves per 8 channels): their rounding dominated
+  // the score error of plain fp16 storage (tools/precision_study.py).  Other modes: fp32 rows.
+  const int x2 = hm ? 2 : 1;
+  const Act cat8(B[C::CAT8], kCatLd[0] * x2, hm), h8(B[C::H8], 8 * x2, hm);
   const Act cat[4] = {cat8, Act(B[C::CAT7], kCatLd[1], hm), Act(B[C::CAT6], kCatLd[2], hm), Act(B[C::CAT5], kCatLd[3], hm)};
   // skip tensors live in the tail channel slice of the concat buffers (ME.cat(out, skip), minkunet.py:192)
-  const Act skip[4] = {cat[0].at(8), cat[1].at(16), cat[2].at(32), cat[3].at(64)};
+  const Act skip[4] = {cat[0].at(8 * x2), cat[1].at(16), cat[2].at(32), cat[3].at(64)};
   const Act E[4] = {Act(B[C::E1], 8, hm), Act(B[C::E2], 8, hm), Act(B[C::E3], 16, hm), Act(B[C::E4], 32, hm)};
   const Act H[4] = {Act(B[C::H1], 8, hm), Act(B[C::H2], 16, hm), Act(B[C::H3], 32, hm), Act(B[C::H4], 64, hm)};
   const Act b4(B[C::B4], 64, hm);
@@ -331,26 +351,20 @@ int unet_forward(sps_ctx* c, const sps_net* net, const float* feat0, float* logi
   // conv0p1s1 + bn0 + relu  (minkunet.py:162-164); the fused forward computed it while the level-0 block table was alive
   if (!conv0_done) {
     if (!c->have_nbr5) return SPS_ERR_STATE;
-    const int keep = c->backend;
-    c->backend = SPS_BACKEND_FP32;   // Cin = 1, 125 offsets: the generic fp32 kernel in every mode
     const Act f0(const_cast<float*>(feat0), 1, false);
-    rc = run_conv(c, ConvIo{nullptr, nullptr, nullptr, SPS_CONV_NBR, c->nbr5}, "conv0", net->conv0, c->counts + 0, nmax, f0, none, none,
-                  skip[0], false, st);
-    c->backend = keep;
-    if (rc != SPS_OK) return rc;
+    RUN(ConvIo{nullptr, nullptr, nullptr, SPS_CONV_NBR, c->nbr5}, "conv0", net->conv0, c->counts + 0, nmax, f0, none, none, skip[0], st);
   }
   // encoder (minkunet.py:166-185)
   for (int i = 0; i < 4; ++i) {
     const int L = i + 1;
-    const ConvIo down{c->tmask8, nullptr, nullptr, SPS_CONV_NBR, c->child[L]};
-    // E2 feeds a tensor-core layer (block2.conv1): stored TF32-rounded in TF32 mode; E1 only feeds FMA layers
-    RUN(down, nm_down[i], net->down[i], c->counts + L, nmax, skip[i], none, none, E[i], rnd && i >= 1, st);
+    RUN(ConvIo{c->tmask8, nullptr, nullptr, SPS_CONV_NBR, c->child[L]}, nm_down[i], net->down[i], c->counts + L, nmax, skip[i], none,
+        none, E[i], st);
     const ConvW& c1 = net->blk1[i];
     const ConvW& c2 = net->blk2[i];
-    RUN(io3(c, L), nm_c1[i], c1, c->counts + L, nmax, E[i], none, none, H[i], rnd && i >= 1, st);
+    RUN(io3(c, L), nm_c1[i], c1, c->counts + L, nmax, E[i], none, none, H[i], st);
     const Act out = (L < 4) ? skip[L] : b4;
-    if (c2.cin2) RUN(io3(c, L), nm_c2[i], c2, c->counts + L, nmax, H[i], E[i], none, out, rnd, st);
-    else RUN(io3(c, L), nm_c2[i], c2, c->counts + L, nmax, H[i], none, E[i], out, rnd, st);
+    if (c2.cin2) RUN(io3(c, L), nm_c2[i], c2, c->counts + L, nmax, H[i], E[i], none, out, st);
+    else RUN(io3(c, L), nm_c2[i], c2, c->counts + L, nmax, H[i], none, E[i], out, st);
   }
   // decoder (minkunet.py:188-217)
   Act dec_in = b4;
@@ -358,21 +372,20 @@ int unet_forward(sps_ctx* c, const sps_net* net, const float* feat0, float* logi
     const int L = 3 - i;  // output level
     if (exact) {   // exact-fp32 mode: scatter over the child table (no atomics, each row once)
       RUN(ConvIo{nullptr, nullptr, nullptr, SPS_CONV_UP, c->child[L + 1]}, nm_up[i], net->up[i], c->counts + L + 1, nmax, dec_in, none,
-          none, cat[L], false, st);
+          none, cat[L], st);
     } else {       // the same transposed conv as an 8-offset gather map of the fine rows
       RUN(ConvIo{c->tmask8, nullptr, nullptr, SPS_CONV_NBR, c->upmap[L]}, nm_up[i], net->up[i], c->counts + L, nmax, dec_in, none, none,
-          cat[L], rnd && L > 0, st);
+          cat[L], st);
     }
     const ConvW& c1 = net->blk1[4 + i];
     const ConvW& c2 = net->blk2[4 + i];
-    RUN(io3(c, L), nm_c1[4 + i], c1, c->counts + L, nmax, cat[L], none, none, Hd[i], rnd && L > 0, st);
+    RUN(io3(c, L), nm_c1[4 + i], c1, c->counts + L, nmax, cat[L], none, none, Hd[i], st);
     if (i < 3) {
-      // B7 (block7 output) only feeds the FMA layer convtr7p2s2
-      RUN(io3(c, L), nm_c2[4 + i], c2, c->counts + L, nmax, Hd[i], cat[L], none, Bd[i], rnd && i < 2, st);
+      RUN(io3(c, L), nm_c2[4 + i], c2, c->counts + L, nmax, Hd[i], cat[L], none, Bd[i], st);
       dec_in = Bd[i];
     } else {
       // block8.conv2 + norm2 + downsample + relu, with `final` (8->1, bias; minkunet.py:219) fused
-      RUN(io3(c, L), nm_c2[4 + i], c2, c->counts + L, nmax, Hd[i], cat[L], none, none, false, st, net->head_w, net->head_b, logits);
+      RUN(io3(c, L), nm_c2[4 + i], c2, c->counts + L, nmax, Hd[i], cat[L], none, none, st, net->head_w, net->head_b, logits);
     }
   }
 #undef RUN
@@ -433,15 +446,18 @@ static int forward_feat_impl(sps_ctx* ctx, const sps_net* net, const float* d_po
   if (rc != SPS_OK) return rc;
   // TensorField.sparse(): voxel feature = mean of the constant 0.5 point features = 0.5
   // (src/sps/models/models.py:22-25)
-  // conv0's output (skip0 = channels 8..15 of the level-0 concat buffer) is stored as fp32 rows in every mode
-  float* c0_out = ctx->buf[sps_ctx::CAT8] + 8;
+  // conv0's output = skip0, channels 8..15 of the level-0 concat buffer: fp16 hi|lo pairs in the fp16 forward (halves
+  // 16..31 of 32-half rows), fp32 otherwise (TF32-rounded when a TF32 tensor-core layer reads it)
+  const bool hm = ctx_half_storage(ctx);
+  float* c0_out = ctx->buf[sps_ctx::CAT8] + 8;      // 8 floats = 16 halves into the row, either way
   const float* vfeat = nullptr;
   if (d_feat) {   // voxel feature = mean of its points' features; the logits buffer is free until the last layer
     rc = sps_voxel_mean(ctx, d_feat, 1, 1, ctx->buf[sps_ctx::FEAT0], ctx->buf[sps_ctx::LOGITS], st);
     if (rc != SPS_OK) return rc;
     vfeat = ctx->buf[sps_ctx::FEAT0];
   }
-  Conv0Fused c0{vfeat, 0.5f, net->conv0.w, net->conv0.shift, kStoreF32, c0_out, kCatLd[0]};
+  Conv0Fused c0{vfeat, 0.5f, net->conv0.w, net->conv0.shift, hm ? kStoreF16x2 : (ctx->backend != SPS_BACKEND_FP32 ? kStoreTF32 : kStoreF32),
+                c0_out, hm ? 2 * kCatLd[0] : kCatLd[0]};
   rc = build_maps_impl(ctx, &c0, st);
   if (rc != SPS_OK) return rc;
   rc = unet_forward(ctx, net, ctx->buf[sps_ctx::FEAT0], ctx->buf[sps_ctx::LOGITS], st, /*conv0_done=*/true);

@@ -2,6 +2,7 @@
 // tcgen05 MMA / TMEM, UMMA descriptors).
 #pragma once
 #include <cstring>
+#include <cuda.h>   // CUtensorMap (types only: the encoder entry point is fetched at run time, no -lcuda)
 #include "common.cuh"
 
 namespace sps {
@@ -115,7 +116,24 @@ struct UmmaParams {
                     // layout sps_conv_pack_kmajor_f16, ldk in halves
   int64_t ldk;
   int round_out;
+  int flags;        // SPS_CONV_FOLD_LO | SPS_CONV_OUT_SPLIT
+  int use_tma;      // the weight stages of a full-width (64-channel) K slab come through TMA: `tmap` is valid
+  alignas(64) CUtensorMap tmap;   // 2-D map of the fp16 K-major weight matrix, box = 64 halves x NPAD rows, SWIZZLE_128B
 };
+
+// ---- TMA (cp.async.bulk.tensor) of one weight stage: box (64 halves, NPAD rows) at column c0 of the K-major matrix ----
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");

@@ -35,7 +35,8 @@ def test_struct_layouts_match_header():
     a = _cabi.ConvArgs
     assert a.mode.offset == 0 and a.map.offset == 16 and a.n_out.offset == 32
     assert a.weight_kmajor.offset == a.head_out.offset + 8 and a.tile_slices.offset == a.perm.offset + 8
-    assert a.io_dtype.offset == a.tile_slices.offset + 8 and a.io_dtype.offset + 8 == C.sizeof(a)
+    assert a.io_dtype.offset == a.tile_slices.offset + 8 and a.backend.offset == a.io_dtype.offset + 4
+    assert a.flags.offset == a.backend.offset + 4 and a.flags.offset + 8 == C.sizeof(a)   # 3 ints + tail padding
 
 
 def test_argument_validation_without_gpu():
@@ -189,6 +190,36 @@ def test_kmajor_weight_packers_host_side():
         assert np.abs(blk4[:, :, :cin] - ref).max() <= np.abs(ref).max() * 2.0 ** -11
         assert not blk4[:, :, cin:].any()
     assert lib.sps_conv_pack_kmajor_f16(None, 81, 8, 8, None, 0, None) == _cabi.SPS_ERR_BAD_ARG
+
+
+def test_split_precision_weight_packer_host_side():
+    """sps_conv_pack_kmajor_f16x: hi|lo input rows duplicate every 8-channel group of the weights along K; folded low
+    parts appear as rows 8..15, and hi + lo reproduces the fp32 weight to 2^-22 relative."""
+    from sps_b200 import _cabi
+    lib = _cabi.load()
+    rng = np.random.default_rng(1)
+    K, cin, cin2 = 81, 16, 16
+    w = rng.standard_normal((K, cin, 8)).astype(np.float32)
+    w2 = rng.standard_normal((cin2, 8)).astype(np.float32)
+    flags = _cabi.SPS_PACK_IN_SPLIT | _cabi.SPS_PACK_IN2_SPLIT | _cabi.SPS_PACK_FOLD_LO
+    ld = lib.sps_conv_kmajor_ld_f16x(K, cin, cin2, flags)
+    assert ld == K * 32 + 64                      # 2 x 16 channels per offset (4 groups), the 1x1 term 2 x 16 padded to 64
+    out = np.full((16, ld), np.nan, np.float16)
+    assert lib.sps_conv_pack_kmajor_f16x(w.ctypes.data_as(C.c_void_p), K, cin, 8, w2.ctypes.data_as(C.c_void_p), cin2, flags,
+                                         out.ctypes.data_as(C.c_void_p)) == 0
+    assert np.isfinite(out).all()
+    blk = out[:, : K * 32].reshape(16, K, 2, 2, 8)            # [row][offset][8-channel group][hi|lo slot of the ROW format][8]
+    assert np.array_equal(blk[:, :, :, 0], blk[:, :, :, 1])   # the same weight meets the hi and the lo half of an activation
+    hi, lo = blk[:8, :, :, 0].astype(np.float64), blk[8:, :, :, 0].astype(np.float64)
+    ref = w.transpose(2, 0, 1).reshape(8, K, 2, 8).astype(np.float64)
+    assert np.array_equal(blk[:8, :, :, 0], ref.astype(np.float16))
+    assert np.abs(hi + lo - ref).max() <= 2.0 ** -21 * np.abs(ref).max()
+    t2 = out[:, K * 32: K * 32 + 32].reshape(16, 2, 2, 8)
+    assert np.abs(t2[:8, :, 0].astype(np.float64) + t2[8:, :, 0].astype(np.float64) - w2.T.reshape(8, 2, 8)).max() <= 2.0 ** -21 * np.abs(w2).max()
+    assert not out[:, K * 32 + 32:].any()
+    # plain packing is the flags == 0 case
+    assert lib.sps_conv_kmajor_ld_f16x(K, cin, cin2, 0) == lib.sps_conv_kmajor_ld_f16(K, cin, cin2)
+    assert lib.sps_conv_pack_kmajor_f16x(w.ctypes.data_as(C.c_void_p), K, cin, 16, None, 0, _cabi.SPS_PACK_FOLD_LO, out.ctypes.data_as(C.c_void_p)) == _cabi.SPS_ERR_BAD_ARG
 
 
 def test_product_never_imports_oracle():

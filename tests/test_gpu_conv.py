@@ -188,74 +188,71 @@ def test_pattern_sorted_processing_order_does_not_change_results():
         assert np.abs(out[2] - ref).max() < 5e-4
 
 
-@pytest.mark.parametrize("cin,in_f16", [(8, True), (8, False), (16, True), (16, False)])
+@pytest.mark.parametrize("cin,in_split", [(8, False), (8, True), (16, False), (16, True)])
 @pytest.mark.parametrize("K", [81, 8])
-def test_fma8_kernel_eight_output_channels(cin, in_f16, K):
-    """k_conv_fma8 (SPS_BACKEND_AUTO, cout = 8): fp32 weights, fp32 accumulation, any mix of fp16 / fp32 rows for
-    the input, the fused 1x1 term / residual and the output; fused head.  Against float64 numpy on the STORED
-    operands (weights exact): 1e-5 relative on fp32 outputs, one fp16 rounding on fp16 outputs."""
-    from sps_b200 import convops
-    rng = np.random.default_rng(cin * 10 + K + in_f16)
+def test_split_precision_options_of_the_fp16_path(cin, in_split, K):
+    """SPS_CONV_FOLD_LO (low weight parts in accumulator columns 8..15) and hi|lo rows (SPS_CONV_OUT_SPLIT on the way
+    out, doubled channels + K-duplicated weights on the way in): with all of them an 8-output-channel fp16-row layer
+    reproduces float64 numpy on UNROUNDED operands to ~1e-6 relative, i.e. ~1000x tighter than plain fp16 operands."""
+    from sps_b200 import convops, _cabi
+    rng = np.random.default_rng(cin * 10 + K + in_split)
     V = 1300
     nbr = random_map(rng, K, V, V, 0.3 if K == 81 else 0.6)
-    nbr[:, 300:500] = -1                      # rows (and a whole tile) without neighbours
-    if K == 81:
-        nbr[30:60, :] = -1                    # offsets absent everywhere
+    nbr[:, 300:500] = -1
     x = rng.standard_normal((V, cin)).astype(np.float32)
     w = (rng.standard_normal((K, cin, 8)) / np.sqrt(cin * 8)).astype(np.float32)
     shift = rng.standard_normal(8).astype(np.float32)
     x2 = rng.standard_normal((V, 16)).astype(np.float32)
     w2 = (rng.standard_normal((16, 8)) / 4).astype(np.float32)
-    res = rng.standard_normal((V, 8)).astype(np.float32)
     head_w = rng.standard_normal(8).astype(np.float32)
     ld = (V + 31) // 32 * 32
     m = np.full((K, ld), -1, np.int32)
     m[:, :V] = nbr
-    half = torch.float16
-    dev = lambda a, f16=False: torch.as_tensor(np.ascontiguousarray(a)).cuda().to(half if f16 else torch.float32)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a)).cuda()
     n_out = torch.tensor([V], dtype=torch.int32, device="cuda")
-    qx = f16 if in_f16 else (lambda v: v)
-    for side_f16, out_f16 in ((False, False), (True, True), (not in_f16, in_f16)):
-        q2 = f16 if side_f16 else (lambda v: v)
-        # conv + shift + relu
-        out = convops.conv_fwd(dev(x, in_f16), dev(w), n_out, map=dev(m).int(), map_ld=ld, shift=dev(shift), relu=True,
-                               io_f16=(in_f16, side_f16, out_f16))
-        ref = ref_conv(qx(x), nbr, w, shift=shift, relu=True)
-        tol = (2e-3 if out_f16 else 2e-5) * max(1.0, np.abs(ref).max())
-        assert out.dtype == (half if out_f16 else torch.float32)
-        assert np.abs(out[:V].float().cpu().numpy() - ref).max() < tol
-        # fused 1x1 term (BasicBlock downsample) and the fused head
-        head_out = torch.zeros(V, dtype=torch.float32, device="cuda")
-        convops.conv_fwd(dev(x, in_f16), dev(w), n_out, map=dev(m).int(), map_ld=ld, shift=dev(shift), relu=True,
-                         in2=dev(x2, side_f16), weight2=dev(w2), head_w=dev(head_w), head_b=0.25, head_out=head_out,
-                         io_f16=(in_f16, side_f16, out_f16))
-        ref = ref_conv(qx(x), nbr, w, shift=shift, x2=q2(x2), w2=w2, relu=True) @ head_w.astype(np.float64) + 0.25
-        assert np.abs(head_out.cpu().numpy() - ref).max() < 3e-5 * max(1.0, np.abs(ref).max())
-        # identity residual, no ReLU
-        out = convops.conv_fwd(dev(x, in_f16), dev(w), n_out, map=dev(m).int(), map_ld=ld, res=dev(res, side_f16),
-                               io_f16=(in_f16, side_f16, out_f16))
-        ref = ref_conv(qx(x), nbr, w, res=q2(res))
-        tol = (2e-3 if out_f16 else 2e-5) * max(1.0, np.abs(ref).max())
-        assert np.abs(out[:V].float().cpu().numpy() - ref).max() < tol
+    xin = convops.split_rows(t(x)) if in_split else t(x).half()
+    xq = x if in_split else f16(x)                       # plain fp16 rows round the input once
+    # (a) folded low weights, hi|lo output
+    wt = convops.pack_kmajor_f16x(t(w), in_split=in_split, fold_lo=True)
+    out = convops.conv_fwd(xin, t(w), n_out, map=t(m), map_ld=ld, shift=t(shift), relu=True, weight_kmajor=wt, io_f16=True,
+                           flags=_cabi.SPS_CONV_FOLD_LO | _cabi.SPS_CONV_OUT_SPLIT, cin=2 * cin if in_split else None)
+    ref = ref_conv(xq, nbr, w, shift=shift, relu=True)
+    assert out.shape[1] == 16 and out.dtype == torch.float16
+    got = convops.merge_rows(out[:V]).cpu().numpy()
+    assert np.abs(got - ref).max() < 4e-6 * max(1.0, np.abs(ref).max()), np.abs(got - ref).max()
+    # (b) the same with plain fp16 output: one rounding on the way out
+    out = convops.conv_fwd(xin, t(w), n_out, map=t(m), map_ld=ld, shift=t(shift), relu=True, weight_kmajor=wt, io_f16=True,
+                           flags=_cabi.SPS_CONV_FOLD_LO, cin=2 * cin if in_split else None)
+    assert out.shape[1] == 8
+    assert np.abs(out[:V].float().cpu().numpy() - ref).max() < 1e-3 * max(1.0, np.abs(ref).max())
+    # (c) fused 1x1 term on hi|lo rows + fused head (block8.conv2 + final)
+    wt = convops.pack_kmajor_f16x(t(w), t(w2), in_split=in_split, in2_split=True, fold_lo=True)
+    head_out = torch.zeros(V, dtype=torch.float32, device="cuda")
+    convops.conv_fwd(xin, t(w), n_out, map=t(m), map_ld=ld, shift=t(shift), relu=True, in2=convops.split_rows(t(x2)),
+                     weight2=t(w2), head_w=t(head_w), head_b=0.25, head_out=head_out, weight_kmajor=wt, io_f16=True,
+                     flags=_cabi.SPS_CONV_FOLD_LO, cin=2 * cin if in_split else None, cin2=32)
+    ref = ref_conv(xq, nbr, w, shift=shift, x2=x2, w2=w2, relu=True) @ head_w.astype(np.float64) + 0.25
+    assert np.abs(head_out.cpu().numpy() - ref).max() < 1e-5 * max(1.0, np.abs(ref).max())
 
 
-def test_fma8_channel_slices_of_wider_buffers():
-    """Inputs / outputs as channel slices of concat buffers (leading dimension > channel count), as the fused forward
-    uses them: skip0 inside the fp32 [V,16] level-0 buffer, the block output inside an fp16 [V,24] buffer."""
-    from sps_b200 import convops
+def test_split_rows_into_concat_buffer_slices():
+    """hi|lo output into a channel slice of a wider hi|lo buffer (convtr7p2s2 -> the level-0 concat buffer)."""
+    from sps_b200 import convops, _cabi
     rng = np.random.default_rng(5)
     V, K = 700, 8
     nbr = random_map(rng, K, V, V, 0.5)
     ld = (V + 31) // 32 * 32
     m = np.full((K, ld), -1, np.int32)
     m[:, :V] = nbr
-    cat8 = torch.as_tensor(rng.standard_normal((V, 16)).astype(np.float32)).cuda()
-    w = (rng.standard_normal((K, 8, 8)) / 8).astype(np.float32)
-    cat7 = torch.zeros((V, 24), dtype=torch.float16, device="cuda")
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a)).cuda()
+    x = rng.standard_normal((V, 16)).astype(np.float32)
+    w = (rng.standard_normal((K, 16, 8)) / 8).astype(np.float32)
+    cat8 = torch.zeros((V, 32), dtype=torch.float16, device="cuda")
     n_out = torch.tensor([V], dtype=torch.int32, device="cuda")
-    convops.conv_fwd(cat8[:, 8:], torch.as_tensor(w).cuda(), n_out, map=torch.as_tensor(m).cuda(), map_ld=ld, relu=True,
-                     out=cat7[:, 16:], io_f16=(False, False, True))
-    ref = ref_conv(cat8[:, 8:].cpu().numpy(), nbr, w, relu=True)
-    got = cat7.float().cpu().numpy()
-    assert np.abs(got[:, 16:] - ref).max() < 2e-3 * max(1.0, np.abs(ref).max())
-    assert (got[:, :16] == 0).all()            # the rest of the concat buffer is untouched
+    wt = convops.pack_kmajor_f16x(t(w), fold_lo=True)
+    convops.conv_fwd(t(x).half(), t(w), n_out, map=t(m), map_ld=ld, relu=True, out=cat8[:, :16], weight_kmajor=wt, io_f16=True,
+                     flags=_cabi.SPS_CONV_FOLD_LO | _cabi.SPS_CONV_OUT_SPLIT)
+    ref = ref_conv(f16(x), nbr, w, relu=True)
+    got = convops.merge_rows(cat8[:, :16].contiguous()).cpu().numpy()
+    assert np.abs(got - ref).max() < 4e-6 * max(1.0, np.abs(ref).max())
+    assert (cat8[:, 16:] == 0).all()           # the other half of the concat buffer is untouched
