@@ -521,7 +521,7 @@ def run_config2(args):
                    "scans_per_step_per_gpu": BATCH, "weights": "random-init (seed 0), BN eval fresh stats",
                    "l2": f"per-step working set (kernel maps + features, several GB) exceeds the 126 MB L2; "
                          f"{len(host)} distinct batches rotate",
-                   "conv_backend": args.backend, "lanes": args.lanes,
+                   "conv_backend": args.backend, "lanes": args.lanes, "tma_weight_stages": bool(engine.lib.sps_tma_weights_available()),
                    "sharding": "scan-sharded, replicated weights; per step one NCCL all_gather_into_tensor of the "
                                f"scan-row scores (fp32 [{BATCH} x {PTS_PER_SCAN}] per rank) on a dedicated stream"},
         "mpoints_per_s": value * PTS_PER_SCAN / 1e6,

@@ -293,6 +293,10 @@ int sps_conv_pack_kmajor_f16(const float* w, int K, int cin, int cout, const flo
 #define SPS_PACK_FOLD_LO 4
 int64_t sps_conv_kmajor_ld_f16x(int K, int cin, int cin2, int pack_flags);
 int sps_conv_pack_kmajor_f16x(const float* w, int K, int cin, int cout, const float* w2, int cin2, int pack_flags, void* out);
+/* 1 when the tensor-core kernel can stage its 64-channel weight slabs through TMA (cp.async.bulk.tensor): the driver's
+ * cuTensorMapEncodeTiled was found (cudaGetDriverEntryPoint) and SPS_NO_TMA_B is not set in the environment; 0: every
+ * weight stage goes through cp.async (same results). */
+int sps_tma_weights_available(void);
 /* Per-tile present-offset bitmasks of a kernel map (K <= 81) for the tensor-core path:
  * d_masks uint32 [ceil(n_out_max/128)][4]. */
 int sps_kernel_map_tile_masks(const int32_t* d_map, int64_t map_ld, int K, const int32_t* d_n_out,

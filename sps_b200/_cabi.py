@@ -28,7 +28,7 @@ SYMBOLS = [
     "sps_net_create", "sps_net_destroy", "sps_net_set_tensor", "sps_net_set_output", "sps_net_device_bytes", "sps_net_finalize",
     "sps_forward", "sps_forward_features", "sps_forward_host", "sps_unet_forward", "sps_devox_sigmoid", "sps_ctx_launch_count",
     "sps_map_bytes", "sps_map_build", "sps_map_destroy", "sps_submap_crop_voxel", "sps_submap_crop_radius",
-    "sps_assemble", "sps_memcpy_d2h", "sps_memcpy_h2d", "sps_infer_scan", "sps_infer_scan_scratch_bytes", "sps_conv_kmajor_ld", "sps_conv_pack_kmajor", "sps_conv_kmajor_ld_f16", "sps_conv_pack_kmajor_f16", "sps_conv_kmajor_ld_f16x", "sps_conv_pack_kmajor_f16x", "sps_kernel_map_tile_masks", "sps_ctx_set_pattern_sort",
+    "sps_assemble", "sps_memcpy_d2h", "sps_memcpy_h2d", "sps_infer_scan", "sps_infer_scan_scratch_bytes", "sps_conv_kmajor_ld", "sps_conv_pack_kmajor", "sps_conv_kmajor_ld_f16", "sps_conv_pack_kmajor_f16", "sps_conv_kmajor_ld_f16x", "sps_conv_pack_kmajor_f16x", "sps_kernel_map_tile_masks", "sps_tma_weights_available", "sps_ctx_set_pattern_sort",
     "sps_ctx_set_conv_backend", "sps_profile_enable", "sps_profile_read", "sps_ctx_pair_count",
     "sps_confusion_counts", "sps_voxel_mean", "sps_gather_rows", "sps_affine_relu",
     "sps_ballmap_bytes", "sps_ballmap_build", "sps_ballmap_destroy", "sps_ball_query_scratch_bytes", "sps_submap_ball_query",
@@ -108,6 +108,7 @@ def load() -> C.CDLL:
         "sps_infer_scan": (i32, [vp, vp, vp, vp, i64, f32, vp, vp, sz, vp, vp]),
         "sps_infer_scan_scratch_bytes": (sz, [i64]),
         "sps_ctx_set_pattern_sort": (i32, [vp, i32]),
+        "sps_tma_weights_available": (i32, []),
         "sps_kernel_map_tile_masks": (i32, [vp, i64, i32, vp, i64, vp, vp]),
         "sps_conv_kmajor_ld": (i64, [i32, i32, i32]),
         "sps_conv_pack_kmajor": (i32, [vp, i32, i32, i32, vp, i32, vp]),

@@ -90,12 +90,12 @@ def kernel_map_tile_masks(map, map_ld, K, n_out, n_out_max):
 
 def conv_fwd(inp, weight, n_out, *, map=None, map_ld=0, mode=_cabi.SPS_CONV_NBR, shift=None, in2=None, weight2=None,
              res=None, relu=False, out=None, head_w=None, head_b=0.0, head_out=None, weight_kmajor=None,
-             round_out=False, n_out_max=None, backend=None, tile_mask=None, io_f16=False, flags=0, cin=None, cin2=None):
+             round_out=False, n_out_max=None, backend=None, tile_mask=None, io_f16=False, flags=0, cin_rows=None, cin2_rows=None):
     """out[o] = act(sum_k in[map[k][o]] @ W[k] (+ in2[o] @ W2) + shift (+ res[o])); ``n_out`` is a
     1-element int32 CUDA tensor (device-side count).  ``inp``/``out``/``in2``/``res`` may be
     channel slices (stride(0) is the leading dimension).  ``io_f16``: ``inp``/``in2``/``res``/``out`` are fp16
     rows and ``weight_kmajor`` comes from :func:`pack_kmajor_f16` (SPS_IO_F16, the fused forward's format).
-    ``flags``: SPS_CONV_FOLD_LO / SPS_CONV_OUT_SPLIT; ``cin`` / ``cin2``: channel counts the kernel sees when the rows are
+    ``flags``: SPS_CONV_FOLD_LO / SPS_CONV_OUT_SPLIT; ``cin_rows`` / ``cin2_rows``: channel counts the kernel sees when the rows are
     hi|lo pairs (2 x the weight's).  ``backend``: SPS_BACKEND_* of this one call (default AUTO) -- the library has no
     process-wide switch."""
     lib = _cabi.load()
@@ -128,10 +128,10 @@ def conv_fwd(inp, weight, n_out, *, map=None, map_ld=0, mode=_cabi.SPS_CONV_NBR,
     a.io_dtype = _cabi.SPS_IO_F16 if io_f16 else _cabi.SPS_IO_F32
     a.backend = int(backend) if backend is not None else _cabi.SPS_BACKEND_AUTO
     a.flags = int(flags)
-    if cin is not None:        # hi|lo input rows: the kernel sees the doubled channel count
-        a.cin = int(cin)
-    if cin2 is not None:
-        a.cin2 = int(cin2)
+    if cin_rows is not None:   # hi|lo input rows: the kernel sees the doubled channel count
+        a.cin = int(cin_rows)
+    if cin2_rows is not None:
+        a.cin2 = int(cin2_rows)
     if weight_kmajor is not None and map is not None and tile_mask is None and K <= 81:
         tile_mask = kernel_map_tile_masks(map, map_ld, K, n_out, n_out_max)
     if tile_mask is not None:

@@ -19,6 +19,8 @@
 //     "copies landed" arrive is a single uniform-address instruction;
 //   * the per-stage parameters of the next stage are fetched before waiting for its slot;
 //   * global addresses are one IMAD.WIDE per 16-byte chunk.
+//   * (tried and dropped, profiles/r2_experiments.md: a warp issuing prefetch.global.L2 for the next tile's rows made
+//     every layer 3-6x slower -- the prefetches go through the same L1 data pipe the gathers saturate.)
 // Warp roles (448 threads): 0-7 producers, 8 loader, 9 MMA issuer, 10-13 epilogue.
 #include "umma_common.cuh"
 
@@ -686,6 +688,8 @@ extern "C" int64_t sps_conv_kmajor_ld_f16(int K, int cin, int cin2) { return sps
 extern "C" int sps_conv_pack_kmajor_f16(const float* w, int K, int cin, int cout, const float* w2, int cin2, void* out) {
   return sps_conv_pack_kmajor_f16x(w, K, cin, cout, w2, cin2, 0, out);
 }
+
+extern "C" int sps_tma_weights_available(void) { return sps::encode_tiled_fn() != nullptr ? 1 : 0; }
 
 extern "C" int sps_kernel_map_tile_masks(const int32_t* d_map, int64_t map_ld, int K, const int32_t* d_n_out,
                                          int64_t n_out_max, uint32_t* d_masks, void* stream) {

@@ -215,14 +215,14 @@ def test_split_precision_options_of_the_fp16_path(cin, in_split, K):
     # (a) folded low weights, hi|lo output
     wt = convops.pack_kmajor_f16x(t(w), in_split=in_split, fold_lo=True)
     out = convops.conv_fwd(xin, t(w), n_out, map=t(m), map_ld=ld, shift=t(shift), relu=True, weight_kmajor=wt, io_f16=True,
-                           flags=_cabi.SPS_CONV_FOLD_LO | _cabi.SPS_CONV_OUT_SPLIT, cin=2 * cin if in_split else None)
+                           flags=_cabi.SPS_CONV_FOLD_LO | _cabi.SPS_CONV_OUT_SPLIT, cin_rows=2 * cin if in_split else None)
     ref = ref_conv(xq, nbr, w, shift=shift, relu=True)
     assert out.shape[1] == 16 and out.dtype == torch.float16
     got = convops.merge_rows(out[:V]).cpu().numpy()
     assert np.abs(got - ref).max() < 4e-6 * max(1.0, np.abs(ref).max()), np.abs(got - ref).max()
     # (b) the same with plain fp16 output: one rounding on the way out
     out = convops.conv_fwd(xin, t(w), n_out, map=t(m), map_ld=ld, shift=t(shift), relu=True, weight_kmajor=wt, io_f16=True,
-                           flags=_cabi.SPS_CONV_FOLD_LO, cin=2 * cin if in_split else None)
+                           flags=_cabi.SPS_CONV_FOLD_LO, cin_rows=2 * cin if in_split else None)
     assert out.shape[1] == 8
     assert np.abs(out[:V].float().cpu().numpy() - ref).max() < 1e-3 * max(1.0, np.abs(ref).max())
     # (c) fused 1x1 term on hi|lo rows + fused head (block8.conv2 + final)
@@ -230,7 +230,7 @@ def test_split_precision_options_of_the_fp16_path(cin, in_split, K):
     head_out = torch.zeros(V, dtype=torch.float32, device="cuda")
     convops.conv_fwd(xin, t(w), n_out, map=t(m), map_ld=ld, shift=t(shift), relu=True, in2=convops.split_rows(t(x2)),
                      weight2=t(w2), head_w=t(head_w), head_b=0.25, head_out=head_out, weight_kmajor=wt, io_f16=True,
-                     flags=_cabi.SPS_CONV_FOLD_LO, cin=2 * cin if in_split else None, cin2=32)
+                     flags=_cabi.SPS_CONV_FOLD_LO, cin_rows=2 * cin if in_split else None, cin2_rows=32)
     ref = ref_conv(xq, nbr, w, shift=shift, x2=x2, w2=w2, relu=True) @ head_w.astype(np.float64) + 0.25
     assert np.abs(head_out.cpu().numpy() - ref).max() < 1e-5 * max(1.0, np.abs(ref).max())
 
