@@ -40,8 +40,6 @@ static size_t carve(sps_ctx* c, void* base, int64_t max_points) {
   c->ticket = reinterpret_cast<uint32_t*>(c->counts + 32);
   c->nblocks = c->counts + 64;
   c->status = c->counts + 96;
-  c->cells = cv.take<int32_t>((size_t)N * 64);
-  c->occ = cv.take<unsigned long long>(N);
   c->staging = cv.take<float>((size_t)N * 8);
   c->scores = cv.take<float>(N);
   c->table_cap = table_capacity(N);
@@ -57,22 +55,22 @@ static size_t carve(sps_ctx* c, void* base, int64_t max_points) {
     c->ptmask[L] = cv.take<uint32_t>((size_t)(ld / 128 + 1) * 4);
     c->perm[L] = cv.take<int32_t>(N);
     c->tslice[L] = (L <= 3) ? cv.take<int32_t>((size_t)(ld / 128 + 1) * SPS_TILE_SLICE_ENTRIES * 128) : nullptr;
+    c->btab[L] = cv.take<Slot>(c->table_cap);
+    c->bcells[L] = cv.take<int32_t>((size_t)N * 64);
+    c->bocc[L] = cv.take<unsigned long long>(N);
+    c->vmask[L] = cv.take<uint32_t>((size_t)3 * ld);
     c->parent[L] = (L < SPS_NUM_LEVELS - 1) ? cv.take<int32_t>(N) : nullptr;
     c->child[L] = (L > 0) ? cv.take<int32_t>((size_t)8 * ld) : nullptr;
     c->upmap[L] = (L < SPS_NUM_LEVELS - 1) ? cv.take<int32_t>((size_t)8 * ld) : nullptr;
   }
   c->nbr5 = cv.take<int32_t>((size_t)125 * ld);
   c->tmask8 = cv.take<uint32_t>((size_t)(ld / 128 + 1) * 4);
-  c->vmask = cv.take<uint32_t>((size_t)3 * ld);
-  c->sort_keys[0] = cv.take<uint32_t>(N);
-  c->sort_keys[1] = cv.take<uint32_t>(N);
-  c->sort_vals = cv.take<int32_t>(N);
-  {
-    const size_t hn = (size_t)256 * (N / 1024 + 1);
-    c->sort_hist = cv.take<int32_t>(hn);
-    c->sort_hrank = cv.take<int32_t>(hn);
-    c->sort_hsums = cv.take<int32_t>(hn / 1024 + 2);
+  for (int j = 0; j < 2; ++j) {
+    c->sort_keys[j] = cv.take<uint32_t>((size_t)4 * N);
+    c->sort_vals[j] = cv.take<int32_t>((size_t)4 * N);
   }
+  c->sort_hist = cv.take<uint32_t>(1028);
+  c->sort_status = cv.take<uint32_t>(((size_t)4 * N / 1024 + 2) * 1024);
   for (int b = 0; b < sps_ctx::NBUF; ++b) c->buf[b] = cv.take<float>((size_t)N * kBufWidth[b]);
   return (cv.off + 255) & ~size_t(255);
 }

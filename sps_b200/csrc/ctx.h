@@ -6,10 +6,6 @@
 #include <vector>
 #include "common.cuh"
 
-// 8-bit radix passes of the shape sort: 4 = full 29-bit key; 3 = 20-bit key without the centre and corner offsets
-#ifndef SPS_SORT_PASSES
-#define SPS_SORT_PASSES 4
-#endif
 
 struct sps_ctx {
   int64_t max_points = 0;
@@ -38,9 +34,11 @@ struct sps_ctx {
   int32_t* status = nullptr;   // sticky status word
   uint32_t* ticket = nullptr;  // last-block-done counters, one per unique() call
   int32_t* n_dev = nullptr;    // device copy of n (so level-0 kernels share the code path)
-  int32_t* nblocks = nullptr;  // blocks in the current level's block table
-  int32_t* cells = nullptr;    // [max_points][64] voxel rows per 4x4x4 block (upper bound: one block per voxel)
-  unsigned long long* occ = nullptr;  // [max_points] 64-bit occupancy word per block
+  int32_t* nblocks = nullptr;  // [SPS_NUM_LEVELS] blocks in each level's block table
+  // 4x4x4 block tables, one per level (all levels are built and probed by the same launches)
+  sps::Slot* btab[SPS_NUM_LEVELS] = {};              // block key -> block id, capacity table_capacity(max_points)
+  int32_t* bcells[SPS_NUM_LEVELS] = {};              // [max_points][64] voxel rows per block (upper bound: one block per voxel)
+  unsigned long long* bocc[SPS_NUM_LEVELS] = {};     // [max_points] 64-bit occupancy word per block
 
   float* staging = nullptr;    // [max_points][8] host->device landing zone
   float* scores = nullptr;     // [max_points]
@@ -55,13 +53,16 @@ struct sps_ctx {
   int32_t* parent[SPS_NUM_LEVELS] = {};        // [L] fine row -> parent*8 + k   (L = 0..3)
   int32_t* child[SPS_NUM_LEVELS] = {};         // [L] [8][ld] children of level-L rows (L = 1..4)
   int32_t* upmap[SPS_NUM_LEVELS] = {};         // [L] [8][ld] transposed-conv map of level-L rows (L = 0..3)
-  uint32_t* vmask = nullptr;                   // [3][ld] per-voxel 27-bit presence of the 3x3x3 neighbours per time plane (current level)
+  uint32_t* vmask[SPS_NUM_LEVELS] = {};        // [L] [3][ld] per-voxel 27-bit presence of the 3x3x3 neighbours per time plane
   int32_t* perm[SPS_NUM_LEVELS] = {};          // [L] rows of level L in neighbourhood-shape order (conv processing order)
   uint32_t* ptmask[SPS_NUM_LEVELS] = {};       // [L] tile masks of nbr3 in perm order
   int32_t* tslice[SPS_NUM_LEVELS] = {};        // [L] [tiles][82][128] nbr3 gathered per tile in perm order (sorted levels)
-  uint32_t* sort_keys[2] = {};                 // radix sort ping-pong
-  int32_t* sort_vals = nullptr;
-  int32_t* sort_hist = nullptr; int32_t* sort_hrank = nullptr; int32_t* sort_hsums = nullptr;
+  // shape sort of levels 0..3 together (4 x max_points keys): ping-pong buffers, [4][256] digit histograms + 4 tile
+  // tickets, look-back status words [tiles][4][256]
+  uint32_t* sort_keys[2] = {};
+  int32_t* sort_vals[2] = {};
+  uint32_t* sort_hist = nullptr;
+  uint32_t* sort_status = nullptr;
   uint32_t* tmask8 = nullptr;                  // [tiles][4] all-eight-offsets mask for the 2x2x2x1 maps
   int32_t* nbr3[SPS_NUM_LEVELS] = {};          // [81][ld]
   int32_t* nbr5 = nullptr;                     // [125][ld]

@@ -18,11 +18,24 @@ constexpr uint32_t kInvalidSlot = 0xFFFFFFFFu;
 
 __global__ void k_set_i32(int32_t* p, int32_t v) { *p = v; }
 
-__global__ void k_table_clear(Slot* __restrict__ tab, const int32_t* __restrict__ n_ptr) {
-  const uint32_t cap = table_capacity(*n_ptr);
+// First kernel of a level: empties the open-addressing table for `n` keys and, for a strided level, presets the
+// child table of the level being built to "absent" for every column a coarse row can take (coarse count <= fine count).
+// n comes from the device (`n_ptr`) or, at level 0, from the host (`n_host` >= 0, also published to `n_dev`).
+__global__ void k_level_begin(Slot* __restrict__ tab, const int32_t* __restrict__ n_ptr, int32_t n_host, int32_t* n_dev,
+                              int32_t* __restrict__ child, int64_t ld) {
+  const int n = n_host >= 0 ? n_host : *n_ptr;
+  if (n_dev && blockIdx.x == 0 && threadIdx.x == 0) *n_dev = n;
+  const uint32_t cap = table_capacity(n);
   const int4 empty = make_int4(-1, -1, -1, INT_MAX);
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x)
-    reinterpret_cast<int4*>(tab)[i] = empty;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += stride) reinterpret_cast<int4*>(tab)[i] = empty;
+  if (child) {
+    const int64_t total = (int64_t)8 * n;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += stride) {
+      const int r = (int)(idx / n), c = (int)(idx - (int64_t)r * n);
+      child[r * ld + c] = -1;
+    }
+  }
 }
 
 // a1 + a2: fp32 IEEE division by the voxel size (src/sps/models/models.py:21), floor
@@ -169,17 +182,6 @@ k_first_rank(Slot* tab, const uint32_t* __restrict__ slot_of, const int32_t* __r
   if (flag && !filter) tab[s].val = excl;
 }
 
-__global__ void k_fill_i32(int32_t* __restrict__ p, int64_t ld, int rows, const int32_t* __restrict__ count_ptr,
-                           int32_t value) {
-  const int n = *count_ptr;
-  const int64_t total = (int64_t)rows * n;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(idx / n), c = (int)(idx - (int64_t)r * n);
-    p[r * ld + c] = value;
-  }
-}
-
 // Level 0: inverse mapping point -> voxel row; the first occurrence publishes the voxel.
 __global__ void k_assign_points(Slot* tab, const uint32_t* __restrict__ slot_of, const int32_t* __restrict__ n_ptr,
                                 const int32_t* __restrict__ rank, const int32_t* __restrict__ block_sums,
@@ -221,51 +223,50 @@ __global__ void k_assign_coarse(Slot* tab, const uint32_t* __restrict__ slot_of,
 }
 
 
-// ---- block table: 4x4x4-cell blocks of a level's lattice -> 64 voxel rows each -----------------
+// ---- block tables: 4x4x4-cell blocks of a level's lattice -> 64 voxel rows each ----------------------
 // The kernel-map probes of one voxel fall into at most 8 such blocks per time plane, and
 // neighbouring voxels share them, so a probe costs a (mostly L1/L2-resident) 4-byte read inside a
 // 256-byte block instead of one random 32-byte sector of a per-voxel hash table.
-__global__ void __launch_bounds__(256)
-k_block_insert(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr,
-               int log2b, Slot* tab, uint32_t* __restrict__ bslot, int32_t* nblocks) {
-  // Block ids come from ONE global counter.  ncu's source view put 75 % of this kernel's stall samples on the result of
-  // that same-address atomicAdd (the compiler's warp aggregation still leaves ~10^5 of them at level 0), so the winners
-  // of a whole CTA are ranked in shared memory first and one thread takes the CTA's id range with a single global atomic.
-  __shared__ int s_cnt, s_base;
-  const int n = *n_ptr;
-  const uint32_t mask = table_capacity(n) - 1;
-  if (threadIdx.x == 0) s_cnt = 0;
-  __syncthreads();
-  for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {   // CTA-uniform trip count
-    const int i = base + threadIdx.x;
-    uint32_t s = 0;
-    int local = -1;
-    if (i < n) {
-      const unsigned long long bkey = coarsen_key(keys[i], log2b);
-      s = hash_key(bkey) & mask;
-      while (true) {
-        const unsigned long long prev = atomicCAS(&tab[s].key, kEmptyKey, bkey);
-        if (prev == kEmptyKey) { local = atomicAdd(&s_cnt, 1); break; }
-        if (prev == bkey) break;
-        s = (s + 1) & mask;
-      }
-      bslot[i] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) { s_base = s_cnt ? atomicAdd(nblocks, s_cnt) : 0; s_cnt = 0; }
-    __syncthreads();
-    if (local >= 0) tab[s].val = s_base + local;
-  }
-}
+// The tables of ALL levels are built by the same three launches (blockIdx.y = level): the coarse levels hold a few
+// thousand voxels each and were pure launch latency as separate kernels.
+struct LevelTabs {
+  const unsigned long long* keys[SPS_NUM_LEVELS];
+  const int32_t* counts;                 // [SPS_NUM_LEVELS] device voxel counts
+  Slot* btab[SPS_NUM_LEVELS];            // block key -> block id
+  int32_t* cells[SPS_NUM_LEVELS];        // [blocks][64] voxel rows
+  unsigned long long* occ[SPS_NUM_LEVELS];   // [blocks] 64-bit occupancy words
+  int32_t* nblocks;                      // [SPS_NUM_LEVELS] block counters
+};
 
-__global__ void k_cells_clear(int32_t* __restrict__ cells, unsigned long long* __restrict__ occ,
-                              const int32_t* __restrict__ nblocks) {
-  const int64_t nb = *nblocks;
-  const int64_t total = nb * 16;  // int4 stores
-  const int4 v = make_int4(-1, -1, -1, -1);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    reinterpret_cast<int4*>(cells)[i] = v;
-    if (i < nb) occ[i] = 0ull;
+// Clears the block tables and zeroes the small scratch arrays the map-building pass accumulates into: the
+// physical-order tile masks (atomicOr targets) and the shape sort's digit histograms, tile tickets and look-back words.
+struct ScratchZero {
+  uint32_t* tmask3[SPS_NUM_LEVELS];   // nullptr: level keeps no physical-order tile masks
+  uint32_t* sort_hist;                // [4][256] + 4 tile tickets (1028 words), or nullptr: no shape sort this forward
+  uint32_t* sort_status;              // [tiles][4][256]
+  int sort_first, sort_levels;
+};
+__device__ __forceinline__ int sort_total(const int32_t* counts, int first, int nlv) {
+  int t = 0;
+  for (int j = 0; j < nlv; ++j) t += counts[first + j];
+  return t;
+}
+__global__ void k_blocks_begin(const LevelTabs T, const ScratchZero z) {
+  const int L = blockIdx.y;
+  const int n = T.counts[L];
+  const uint32_t cap = table_capacity(n);
+  const int4 empty = make_int4(-1, -1, -1, INT_MAX);
+  const uint32_t stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint32_t i = t0; i < cap; i += stride) reinterpret_cast<int4*>(T.btab[L])[i] = empty;
+  if (t0 == 0) T.nblocks[L] = 0;
+  if (z.tmask3[L]) {
+    const uint32_t w = 4u * (uint32_t)(n / 128 + 1);
+    for (uint32_t i = t0; i < w; i += stride) z.tmask3[L][i] = 0u;
+  }
+  if (L == 0 && z.sort_hist) {
+    for (uint32_t i = t0; i < 1028u; i += stride) z.sort_hist[i] = 0u;
+    const int64_t w = (int64_t)((sort_total(T.counts, z.sort_first, z.sort_levels) + 1023) / 1024) * 1024;
+    for (int64_t i = t0; i < w; i += stride) z.sort_status[i] = 0u;
   }
 }
 
@@ -273,14 +274,60 @@ __device__ __forceinline__ int cell_local(unsigned long long key, int L) {
   return ((int)(key >> (kXShift + L)) & 3) + 4 * ((int)(key >> (kYShift + L)) & 3) + 16 * ((int)(key >> (kZShift + L)) & 3);
 }
 
-__global__ void k_cells_fill(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr, int L,
-                             const Slot* __restrict__ tab, const uint32_t* __restrict__ bslot,
-                             int32_t* __restrict__ cells, unsigned long long* __restrict__ occ) {
-  const int n = *n_ptr;
+__global__ void __launch_bounds__(256)
+k_block_insert(const LevelTabs T) {
+  // Block ids come from ONE counter per level.  ncu's source view put 75 % of the stall samples of the first version on
+  // the result of that same-address atomicAdd (the compiler's warp aggregation still leaves ~10^5 of them at level 0), so
+  // the winners of a whole CTA are ranked in shared memory first and one thread takes the CTA's id range with a single
+  // global atomic.  The winner of a block also presets the block's 64 cells and its occupancy word.
+  __shared__ int s_cnt, s_base;
+  const int L = blockIdx.y;
+  const int n = T.counts[L];
+  const uint32_t mask = table_capacity(n) - 1;
+  Slot* tab = T.btab[L];
+  const unsigned long long* keys = T.keys[L];
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {   // CTA-uniform trip count
+    const int i = base + threadIdx.x;
+    uint32_t s = 0;
+    int local = -1;
+    if (i < n) {
+      const unsigned long long bkey = coarsen_key(keys[i], L + 2);
+      s = hash_key(bkey) & mask;
+      while (true) {
+        const unsigned long long prev = atomicCAS(&tab[s].key, kEmptyKey, bkey);
+        if (prev == kEmptyKey) { local = atomicAdd(&s_cnt, 1); break; }
+        if (prev == bkey) break;
+        s = (s + 1) & mask;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { s_base = s_cnt ? atomicAdd(T.nblocks + L, s_cnt) : 0; s_cnt = 0; }
+    __syncthreads();
+    if (local >= 0) {
+      const int id = s_base + local;
+      tab[s].val = id;
+      int4* c4 = reinterpret_cast<int4*>(T.cells[L] + (int64_t)id * 64);
+      const int4 v = make_int4(-1, -1, -1, -1);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) c4[j] = v;
+      T.occ[L][id] = 0ull;
+    }
+  }
+}
+
+__global__ void k_cells_fill(const LevelTabs T) {
+  const int L = blockIdx.y;
+  const int n = T.counts[L];
+  const uint32_t mask = table_capacity(n) - 1;
+  const unsigned long long* keys = T.keys[L];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int id = tab[bslot[i]].val, l = cell_local(keys[i], L);
-    cells[(int64_t)id * 64 + l] = i;
-    atomicOr(occ + id, 1ull << l);     // 64-bit occupancy word per block: presence tests without the index read
+    const unsigned long long key = keys[i];
+    const int id = table_find(T.btab[L], mask, coarsen_key(key, L + 2));
+    const int l = cell_local(key, L);
+    T.cells[L][(int64_t)id * 64 + l] = i;
+    atomicOr(T.occ[L] + id, 1ull << l);     // 64-bit occupancy word per block: presence tests without the index read
   }
 }
 
@@ -362,16 +409,31 @@ k_kernel_map_blk(const unsigned long long* __restrict__ keys, const int32_t* __r
 // block id + occupancy word in shared memory, then answers the 27 lookups with a bit test and, for present
 // neighbours only, one 4-byte read.  (The generic kernel above re-probes whenever the block changes along
 // x: ~13 probes per thread; this was the dominant kernel after the convolutions were sped up.)
+struct KmapOut {
+  int32_t* nbr[SPS_NUM_LEVELS];           // [81][ld] per level
+  uint32_t* tile_masks[SPS_NUM_LEVELS];   // physical-order tile masks, or nullptr (shape-sorted level of the fused forward)
+  uint32_t* vmask[SPS_NUM_LEVELS];        // [3][ld] per-voxel 27-bit presence words per time plane
+  int64_t ld;
+  int dense_mask;                         // bit L: level L stores absent entries (-1) too
+};
+// All levels in one launch: blockIdx.z = level, blockIdx.y = time plane of the kernel.
 template <int KT>
 __global__ void __launch_bounds__(256)
-k_kernel_map_blk3(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr,
-                  const Slot* __restrict__ tab, const int32_t* __restrict__ cells,
-                  const unsigned long long* __restrict__ occ, int L, int32_t* __restrict__ nbr, int64_t ld,
-                  uint32_t* __restrict__ tile_masks, uint32_t* __restrict__ vmask, int dense) {
+k_kernel_map_blk3(const LevelTabs T, const KmapOut O) {
   __shared__ int sId[8][256];
   __shared__ unsigned long long sOcc[8][256];
-  const int n = *n_ptr;
+  const int L = blockIdx.z;
+  const int n = T.counts[L];
   if (n == 0) return;
+  const unsigned long long* __restrict__ keys = T.keys[L];
+  const Slot* __restrict__ tab = T.btab[L];
+  const int32_t* __restrict__ cells = T.cells[L];
+  const unsigned long long* __restrict__ occ = T.occ[L];
+  int32_t* __restrict__ nbr = O.nbr[L];
+  uint32_t* __restrict__ tile_masks = O.tile_masks[L];
+  uint32_t* __restrict__ vmask = O.vmask[L];
+  const int64_t ld = O.ld;
+  const int dense = (O.dense_mask >> L) & 1;
   const uint32_t mask = table_capacity(n) - 1;
   const int xlim = 1 << (kXBits - L), zlim = 1 << (kZBits - L);
   const int it = blockIdx.y;   // time plane of the kernel: t + (it - KT/2)
@@ -447,66 +509,67 @@ k_kernel_map_blk3(const unsigned long long* __restrict__ keys, const int32_t* __
 //   [has dt=+1 neighbours][has dt=-1 neighbours][27-bit spatial presence, OR over the time planes]
 // (measured on the bench scan: offsets walked per tile 46-50 -> 26-28).  The physical voxel order is
 // untouched: `perm` is only the order in which the conv kernels visit rows.
-__global__ void k_pattern_keys(const uint32_t* __restrict__ vmask, int64_t ld, const int32_t* __restrict__ n_ptr,
-                               uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
-  const int n = *n_ptr;
+//
+// All sorted levels are sorted TOGETHER: the level index sits above the shape key (31-bit keys), so one stable LSD
+// radix sort (4 passes of 8 bits) orders every level at once and its last pass scatters straight into the per-level
+// `perm` arrays.  Each pass is ONE kernel ("onesweep"): the digit histograms of all four passes are taken while the
+// keys are produced, and a tile learns the number of equal digits in the tiles before it by decoupled look-back over
+// per-tile status words (aggregate / inclusive-prefix flags in the top two bits).  Round 1 ran 13 launches per level.
+struct SortArgs {
+  const uint32_t* vmask[SPS_NUM_LEVELS];
+  int32_t* perm[SPS_NUM_LEVELS];
+  const int32_t* counts;
+  int32_t* status;      // sticky status word of the context (a look-back that never completes is reported, not waited for)
+  int64_t ld;
+  int first, nlv;
+};
+constexpr int kSortTile = 1024;
+constexpr uint32_t kOsAggregate = 1u << 30, kOsPrefix = 2u << 30, kOsValue = (1u << 30) - 1u;
+
+__global__ void __launch_bounds__(256)
+k_pattern_keys(const SortArgs A, uint32_t* __restrict__ keys, int32_t* __restrict__ vals, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t h[4][256];
+  const int j = blockIdx.y, L = A.first + j;
+  const int n = A.counts[L];
+  int off = 0;
+  for (int q = 0; q < j; ++q) off += A.counts[A.first + q];
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) (&h[0][0])[i] = 0u;
+  __syncthreads();
+  const uint32_t* __restrict__ vm = A.vmask[L];
   for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += gridDim.x * blockDim.x) {
-    const uint32_t m0 = vmask[o], m1 = vmask[ld + o], m2 = vmask[2 * ld + o];
-    const uint32_t pat = m0 | m1 | m2;
-#if SPS_SORT_PASSES == 3
-    // 20-bit key, three 8-bit passes: the centre (always present) and the 8 corner offsets (rarest on surfaces) are left
-    // out of the key; rows that differ only there share a bucket
-    constexpr int kept[18] = {1, 3, 4, 5, 7, 9, 10, 11, 12, 14, 15, 16, 17, 19, 21, 22, 23, 25};
-    uint32_t key = 0;
+    const uint32_t m0 = vm[o], m1 = vm[A.ld + o], m2 = vm[2 * A.ld + o];
+    const uint32_t key = (m0 | m1 | m2) | ((m0 ? 1u : 0u) << 27) | ((m2 ? 1u : 0u) << 28) | ((uint32_t)j << 29);
+    keys[off + o] = key;
+    vals[off + o] = o;
 #pragma unroll
-    for (int j = 0; j < 18; ++j) key |= ((pat >> kept[j]) & 1u) << j;
-    keys[o] = key | ((m0 ? 1u : 0u) << 18) | ((m2 ? 1u : 0u) << 19);
-#else
-    keys[o] = pat | ((m0 ? 1u : 0u) << 27) | ((m2 ? 1u : 0u) << 28);
-#endif
-    vals[o] = o;
+    for (int p = 0; p < 4; ++p) atomicAdd(&h[p][(key >> (8 * p)) & 255u], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+    const uint32_t c = (&h[0][0])[i];
+    if (c) atomicAdd(hist + i, c);
   }
 }
 
-// Stable LSD radix sort, 8 bits per pass: per-block digit histograms -> one global exclusive scan
-// (digit-major) -> stable scatter (warp match + per-warp digit counts).
-constexpr int kSortBlock = 1024;
-__global__ void __launch_bounds__(kSortBlock)
-k_radix_hist(const uint32_t* __restrict__ keys, const int32_t* __restrict__ n_ptr, int shift, int32_t* __restrict__ hist) {
-  __shared__ int h[256];
-  const int n = *n_ptr;
-  const int nb_act = (n + kSortBlock - 1) / kSortBlock;   // histogram layout [digit][active block]: sized by the
-  if ((int)blockIdx.x >= nb_act) return;                  // real element count, not by the launch bound
-  if (threadIdx.x < 256) h[threadIdx.x] = 0;
-  __syncthreads();
-  const int i = blockIdx.x * kSortBlock + threadIdx.x;
-  if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1);
-  __syncthreads();
-  if (threadIdx.x < 256) hist[threadIdx.x * nb_act + blockIdx.x] = h[threadIdx.x];
-}
-
-__global__ void __launch_bounds__(kScanBlock)
-k_scan_hist(const int32_t* __restrict__ in, const int32_t* __restrict__ n_ptr, int32_t* __restrict__ rank,
-            int32_t* block_sums, uint32_t* ticket, int32_t* total) {
-  const int n = 256 * ((*n_ptr + kSortBlock - 1) / kSortBlock);   // 256 digits x active blocks
-  const int nb = (n + kScanBlock - 1) / kScanBlock;
-  if ((int)blockIdx.x >= nb) return;
-  const int i = blockIdx.x * kScanBlock + threadIdx.x;
-  scan_flags(i < n ? in[i] : 0, i, n, nb, rank, block_sums, ticket, total);
-}
-
-__global__ void __launch_bounds__(kSortBlock)
-k_radix_scatter(const uint32_t* __restrict__ keys, const int32_t* __restrict__ vals, const int32_t* __restrict__ n_ptr,
-                int shift, const int32_t* __restrict__ hrank, const int32_t* __restrict__ hsums,
+// One radix pass over the concatenated levels.  LAST: the sorted row numbers go to the per-level perm arrays.
+template <bool LAST>
+__global__ void __launch_bounds__(kSortTile)
+k_onesweep_pass(const SortArgs A, const uint32_t* __restrict__ keys, const int32_t* __restrict__ vals, int shift,
+                const uint32_t* __restrict__ hist, uint32_t* status, uint32_t* ticket, int pass,
                 uint32_t* __restrict__ keys_out, int32_t* __restrict__ vals_out) {
-  __shared__ int wcount[kSortBlock / 32][256];   // per-warp digit counts, then exclusive offsets across warps
-  const int n = *n_ptr;
-  const int nb_act = (n + kSortBlock - 1) / kSortBlock;
-  if ((int)blockIdx.x >= nb_act) return;
+  __shared__ int wcount[kSortTile / 32][256];   // per-warp digit counts, then exclusive offsets across warps
+  __shared__ int s_tile;
+  __shared__ int s_base[256];                   // global position of this tile's first element per digit
+  __shared__ int s_scan[8];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  for (int j = tid; j < (kSortBlock / 32) * 256; j += kSortBlock) (&wcount[0][0])[j] = 0;
+  if (tid == 0) s_tile = (int)atomicAdd(ticket, 1u);   // tiles are handed out in launch order: a tile's predecessors run
+  for (int j = tid; j < (kSortTile / 32) * 256; j += kSortTile) (&wcount[0][0])[j] = 0;
   __syncthreads();
-  const int i = blockIdx.x * kSortBlock + tid;
+  const int tile = s_tile;
+  const int n = sort_total(A.counts, A.first, A.nlv);
+  const int ntiles = (n + kSortTile - 1) / kSortTile;
+  if (tile >= ntiles) return;
+  const int i = tile * kSortTile + tid;
   const bool live = i < n;
   const uint32_t key = live ? keys[i] : 0u;
   const int val = live ? vals[i] : 0;
@@ -515,32 +578,91 @@ k_radix_scatter(const uint32_t* __restrict__ keys, const int32_t* __restrict__ v
   const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
   if (live && rank_in_warp == 0) wcount[w][digit] = __popc(peers);
   __syncthreads();
-  if (tid < 256) {   // exclusive prefix over the warps of this block, per digit
-    int run = 0;
-    for (int ww = 0; ww < kSortBlock / 32; ++ww) {
+  if (tid < 256) {
+    int run = 0;   // exclusive prefix over the warps of this tile, per digit
+    for (int ww = 0; ww < kSortTile / 32; ++ww) {
       const int c = wcount[ww][tid];
       wcount[ww][tid] = run;
       run += c;
     }
+    // decoupled look-back: digits of the tiles before this one
+    uint32_t* st = status + ((size_t)tile * 4 + pass) * 256 + tid;
+    int excl = 0;
+    if (tile == 0) {
+      atomicExch(st, kOsPrefix | (uint32_t)run);
+    } else {
+      atomicExch(st, kOsAggregate | (uint32_t)run);
+      int t = tile - 1;
+      unsigned spins = 0;
+      while (true) {
+        const uint32_t v = *reinterpret_cast<volatile uint32_t*>(status + ((size_t)t * 4 + pass) * 256 + tid);
+        if ((v >> 30) == 0u) {                         // predecessor has not published yet (it is running: ticket order)
+          if (++spins > (1u << 26)) { atomicOr(A.status, kStatusCapacity); break; }   // never hang: report instead
+          continue;
+        }
+        excl += (int)(v & kOsValue);
+        if ((v >> 30) == 2u) break;
+        --t;
+      }
+      atomicExch(st, kOsPrefix | (uint32_t)(excl + run));
+    }
+    // exclusive scan of the global digit histogram (256 values) = start of every digit's run
+    const int hv = (int)hist[tid];
+    int inc = hv;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += u;
+    }
+    if (lane == 31) s_scan[w] = inc;
+    s_base[tid] = inc - hv + excl;
+  }
+  __syncthreads();
+  if (tid < 256) {
+    int add = 0;
+    for (int ww = 0; ww < w; ++ww) add += s_scan[ww];
+    s_base[tid] += add;
   }
   __syncthreads();
   if (live) {
-    const int e = (int)digit * nb_act + blockIdx.x;                       // this block's slot in the digit-major scan
-    const int pos = hrank[e] + hsums[e / kScanBlock] + wcount[w][digit] + rank_in_warp;
-    keys_out[pos] = key;
-    vals_out[pos] = val;
+    const int pos = s_base[digit] + wcount[w][digit] + rank_in_warp;
+    if (LAST) {
+      const int j = (int)(key >> 29);
+      int off = 0;
+      for (int q = 0; q < j; ++q) off += A.counts[A.first + q];
+      A.perm[A.first + j][pos - off] = val;
+    } else {
+      keys_out[pos] = key;
+      vals_out[pos] = val;
+    }
   }
 }
 
 // present-offset masks of the 128-row tiles taken in `perm` order, and (slices != nullptr) the tiles' slices of
 // the kernel map gathered once for all the convolutions of the level: slices[tile][e][r] = input row
 // of sorted row r under the tile's e-th present offset, entry e = #present = the tile's own rows.
+// All sorted levels in one launch (blockIdx.y).
+struct SliceArgs {
+  const uint32_t* vmask[SPS_NUM_LEVELS];
+  const int32_t* perm[SPS_NUM_LEVELS];
+  uint32_t* masks[SPS_NUM_LEVELS];
+  const int32_t* nbr[SPS_NUM_LEVELS];
+  int32_t* slices[SPS_NUM_LEVELS];
+  const int32_t* counts;
+  int64_t ld;
+  int first;
+};
 __global__ void __launch_bounds__(128)
-k_tile_masks_perm(const uint32_t* __restrict__ vmask, int64_t ld, const int32_t* __restrict__ perm,
-                  const int32_t* __restrict__ n_ptr, uint32_t* __restrict__ masks,
-                  const int32_t* __restrict__ nbr, int32_t* __restrict__ slices) {
-  const int n = *n_ptr;
+k_tile_masks_perm(const SliceArgs A) {
+  const int L = A.first + blockIdx.y;
+  const int n = A.counts[L];
   const int ntiles = (n + 127) / 128;
+  const uint32_t* __restrict__ vmask = A.vmask[L];
+  const int32_t* __restrict__ perm = A.perm[L];
+  uint32_t* __restrict__ masks = A.masks[L];
+  const int32_t* __restrict__ nbr = A.nbr[L];
+  int32_t* __restrict__ slices = A.slices[L];
+  const int64_t ld = A.ld;
   __shared__ uint32_t m[4][3];
   __shared__ uint8_t klist[96];
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -765,7 +887,6 @@ static inline int grid_for(int64_t work, int block, int cap = 148 * 32) {
 using namespace sps;
 
 namespace sps {
-__global__ void k_copy_i32(int32_t* dst, const int32_t* src) { *dst = *src; }
 
 // n_upper sizes the launches; the true row count is n_upper, or *d_n when d_n is given.
 int voxelize_impl(sps_ctx* ctx, const float* d_points, int64_t n, const int32_t* d_n, int64_t ld_points,
@@ -775,10 +896,8 @@ int voxelize_impl(sps_ctx* ctx, const float* d_points, int64_t n, const int32_t*
   ctx->n = n;
   ctx->have_l0 = ctx->have_maps = false;
   // n travels as a kernel-visible scalar so that every level shares one code path
-  if (d_n) k_copy_i32<<<1, 1, 0, st>>>(ctx->n_dev, d_n);
-  else k_set_i32<<<1, 1, 0, st>>>(ctx->n_dev, (int32_t)n);
   const int nblk = cdiv(n > 0 ? n : 1, kScanBlock);
-  k_table_clear<<<grid_for(table_capacity(n), 256), 256, 0, st>>>(ctx->table, ctx->n_dev);
+  k_level_begin<<<grid_for(table_capacity(n), 256), 256, 0, st>>>(ctx->table, d_n, d_n ? -1 : (int32_t)n, ctx->n_dev, nullptr, 0);
   prof_mark(ctx, "vox.clear", st);
   k_insert_points<<<grid_for(n, 256), 256, 0, st>>>(d_points, ld_points, ctx->n_dev, voxel_size, ctx->table,
                                                      ctx->slot_of, ctx->status);
@@ -814,40 +933,50 @@ static const int g_tile_slices = SPS_TILE_SLICES;   // gather the kernel map per
 #endif
 constexpr int kFirstSortedLevel = SPS_FIRST_SORTED_LEVEL;
 #ifndef SPS_LAST_SORTED_LEVEL
-#define SPS_LAST_SORTED_LEVEL 3
+#define SPS_LAST_SORTED_LEVEL 3     // level 4 is too small: sorting it costs more than it saves
 #endif
 constexpr int kLastSortedLevel = SPS_LAST_SORTED_LEVEL;
-constexpr int64_t kMinRowsForSort = 400000;   // small inputs (single scans) are launch-bound: 42 extra launches do not pay     // level 4 is too small: the sort's launches cost more than it saves   // level 0 hosts only the 8/16-channel block8 convs: sorting it does not pay
+constexpr int kSortedLevels = kLastSortedLevel - kFirstSortedLevel + 1;
+constexpr int64_t kMinRowsForSort = 400000;   // small inputs (single scans) are launch-bound: the sort does not pay
 
-// perm[L] = voxel rows of level L sorted by neighbourhood-shape key; ptmask[L] = tile masks in that order
-static int pattern_order(sps_ctx* ctx, int L, cudaStream_t st) {
-  if (!ctx->pattern_sort || L < kFirstSortedLevel || L > kLastSortedLevel || (ctx->pattern_sort == 1 && ctx->n < kMinRowsForSort)) return SPS_OK;
+static inline bool sort_active(const sps_ctx* ctx) {
+  return ctx->pattern_sort == 2 || (ctx->pattern_sort == 1 && ctx->n >= kMinRowsForSort);
+}
+
+// perm[L] = voxel rows of level L sorted by neighbourhood-shape key, ptmask[L] = tile masks in that order, tslice[L] = the
+// kernel map gathered per sorted tile -- for all sorted levels at once: 1 + 4 + 1 launches.
+static int pattern_order(sps_ctx* ctx, cudaStream_t st) {
+  if (!sort_active(ctx)) return SPS_OK;
   const int64_t n = ctx->n > 0 ? ctx->n : 1;
-  const int nb_max = cdiv(n, kSortBlock);
-  const int hist_n = 256 * nb_max;
-  const int32_t* cnt = ctx->counts + L;
-  uint32_t* ka = ctx->sort_keys[0];
-  uint32_t* kb = ctx->sort_keys[1];
-  // the values ping-pong between two buffers; start so that the LAST pass writes perm[L]
-  int32_t* va = (SPS_SORT_PASSES % 2 == 0) ? ctx->perm[L] : ctx->sort_vals;
-  int32_t* vb = (SPS_SORT_PASSES % 2 == 0) ? ctx->sort_vals : ctx->perm[L];
-  k_pattern_keys<<<grid_for(n, 256), 256, 0, st>>>(ctx->vmask, ctx->ld, cnt, ka, va);
-  for (int pass = 0; pass < SPS_SORT_PASSES; ++pass) {
-    k_radix_hist<<<nb_max, kSortBlock, 0, st>>>(ka, cnt, 8 * pass, ctx->sort_hist);
-    k_scan_hist<<<cdiv(hist_n, kScanBlock), kScanBlock, 0, st>>>(ctx->sort_hist, cnt, ctx->sort_hrank, ctx->sort_hsums,
-                                                                   ctx->ticket, ctx->counts + 160);
-    k_radix_scatter<<<nb_max, kSortBlock, 0, st>>>(ka, va, cnt, 8 * pass, ctx->sort_hrank, ctx->sort_hsums, kb, vb);
-    std::swap(ka, kb);
-    std::swap(va, vb);
+  SortArgs A;
+  for (int L = 0; L < SPS_NUM_LEVELS; ++L) { A.vmask[L] = ctx->vmask[L]; A.perm[L] = ctx->perm[L]; }
+  A.counts = ctx->counts; A.status = ctx->status; A.ld = ctx->ld; A.first = kFirstSortedLevel; A.nlv = kSortedLevels;
+  uint32_t* hist = ctx->sort_hist;
+  k_pattern_keys<<<dim3(grid_for(n, 256, 148 * 8), kSortedLevels), 256, 0, st>>>(A, ctx->sort_keys[0], ctx->sort_vals[0], hist);
+  const int tiles_max = cdiv(n * kSortedLevels, kSortTile);
+  for (int pass = 0; pass < 4; ++pass) {
+    const uint32_t* ki = ctx->sort_keys[pass & 1];
+    const int32_t* vi = ctx->sort_vals[pass & 1];
+    uint32_t* ko = ctx->sort_keys[(pass & 1) ^ 1];
+    int32_t* vo = ctx->sort_vals[(pass & 1) ^ 1];
+    if (pass < 3)
+      k_onesweep_pass<false><<<tiles_max, kSortTile, 0, st>>>(A, ki, vi, 8 * pass, hist + 256 * pass, ctx->sort_status, hist + 1024 + pass,
+                                                              pass, ko, vo);
+    else
+      k_onesweep_pass<true><<<tiles_max, kSortTile, 0, st>>>(A, ki, vi, 8 * pass, hist + 256 * pass, ctx->sort_status, hist + 1024 + pass,
+                                                             pass, nullptr, nullptr);
   }
-  static const char* nm_sort[5] = {"sort.L0", "sort.L1", "sort.L2", "sort.L3", "sort.L4"};
-  static const char* nm_slice[5] = {"slices.L0", "slices.L1", "slices.L2", "slices.L3", "slices.L4"};
-  prof_mark(ctx, nm_sort[L], st);
-  k_tile_masks_perm<<<grid_for(n / 128 + 1, 1, 148 * 16), 128, 0, st>>>(ctx->vmask, ctx->ld, ctx->perm[L], cnt,
-                                                                       ctx->ptmask[L], ctx->nbr3[L],
-                                                                       g_tile_slices && ctx->tslice[L] ? ctx->tslice[L] : nullptr);
-  prof_mark(ctx, nm_slice[L], st);
+  prof_mark(ctx, "sort", st);
+  SliceArgs S;
+  for (int L = 0; L < SPS_NUM_LEVELS; ++L) {
+    S.vmask[L] = ctx->vmask[L]; S.perm[L] = ctx->perm[L]; S.masks[L] = ctx->ptmask[L]; S.nbr[L] = ctx->nbr3[L];
+    S.slices[L] = g_tile_slices ? ctx->tslice[L] : nullptr;
+  }
+  S.counts = ctx->counts; S.ld = ctx->ld; S.first = kFirstSortedLevel;
+  k_tile_masks_perm<<<dim3(grid_for(n / 128 + 1, 1, 148 * 8), kSortedLevels), 128, 0, st>>>(S);
+  prof_mark(ctx, "slices", st);
   SPS_CUDA_CHECK(cudaGetLastError());
+  ctx->forward_launches += 6;
   return SPS_OK;
 }
 }
@@ -862,74 +991,71 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
   if (!ctx->have_l0) return SPS_ERR_STATE;
   const int64_t n = ctx->n > 0 ? ctx->n : 1;  // host upper bound of every level's voxel count
   const int nblk = cdiv(n, kScanBlock);
-  // level-0 block table (the voxelize table is no longer needed), then both level-0 kernel maps
-  auto build_blocks = [&](int L) {
-    k_table_clear<<<grid_for(table_capacity(n), 256), 256, 0, st>>>(ctx->table, ctx->counts + L);
-    k_set_i32<<<1, 1, 0, st>>>(ctx->nblocks, 0);
-    k_block_insert<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[L], ctx->counts + L, L + 2, ctx->table, ctx->slot_of,
-                                                      ctx->nblocks);
-    k_cells_clear<<<grid_for(n * 16, 256), 256, 0, st>>>(ctx->cells, ctx->occ, ctx->nblocks);
-    k_cells_fill<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[L], ctx->counts + L, L, ctx->table, ctx->slot_of,
-                                                    ctx->cells, ctx->occ);
-  };
-  build_blocks(0);
-  prof_mark(ctx, "blocks.L0", st);
-  if (c0) {
-    if (c0->feat)   // per-voxel features: gather them through the block table
-      k_conv0_blk<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->table, ctx->cells, c0->feat,
-                                                     c0->w, c0->shift, c0->round_out, c0->out, c0->out_ld);
-    else            // one constant feature (SPSModel.forward): presence bits only
-      k_conv0_const<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->table, ctx->occ, c0->cfeat,
-                                                       c0->w, c0->shift, c0->round_out, c0->out, c0->out_ld);
-    prof_mark(ctx, "conv0+kmap5", st);
-  } else {
-    k_kernel_map_blk<5, 1><<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->table, ctx->cells, ctx->occ, 0,
-                                                              ctx->nbr5, ctx->ld, nullptr, nullptr);
-    prof_mark(ctx, "kmap5.L0", st);
-  }
-  ctx->have_nbr5 = c0 == nullptr;
-  const size_t mask_bytes = (size_t)(n / 128 + 1) * 16;
-  SPS_CUDA_CHECK(cudaMemsetAsync(ctx->tmask3[0], 0, mask_bytes, st));
-  // fused forward on a shape-sorted level: the convolutions read the tile slices and the sorted tile masks, the slices
-  // read only present entries -> neither the -1 entries nor the physical-order tile masks are produced
-  auto sparse_ok = [&](int L) {
-    return c0 != nullptr && !needs_dense_maps(ctx) && g_tile_slices && ctx->tslice[L] != nullptr && ctx->pattern_sort && L >= kFirstSortedLevel &&
-           L <= kLastSortedLevel && (ctx->pattern_sort == 2 || ctx->n >= kMinRowsForSort);
-  };
-  k_kernel_map_blk3<3><<<dim3(grid_for(n, 256, 148 * 8), 3), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->table,
-                                                                              ctx->cells, ctx->occ, 0, ctx->nbr3[0],
-                                                                              ctx->ld, sparse_ok(0) ? nullptr : ctx->tmask3[0],
-                                                                              ctx->vmask, sparse_ok(0) ? 0 : 1);
-  prof_mark(ctx, "kmap3.L0", st);
-  { const int rc = pattern_order(ctx, 0, st); if (rc != SPS_OK) return rc; }
+  // ---- 1. strided coordinate sets, levels 1..4 (each level hashes the keys of the one below: a sequential chain) ----
   for (int L = 1; L < SPS_NUM_LEVELS; ++L) {
     const int32_t* n_fine = ctx->counts + (L - 1);
-    k_table_clear<<<grid_for(table_capacity(n), 256), 256, 0, st>>>(ctx->table, n_fine);
+    k_level_begin<<<grid_for(table_capacity(n), 256), 256, 0, st>>>(ctx->table, n_fine, -1, nullptr, ctx->child[L], ctx->ld);
     k_insert_coarse<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[L - 1], n_fine, L, ctx->table, ctx->slot_of);
     k_first_rank<<<nblk, kScanBlock, 0, st>>>(ctx->table, ctx->slot_of, n_fine, ctx->rank, ctx->block_sums,
                                               ctx->ticket, ctx->counts + L, nullptr, 0, nullptr);
-    k_fill_i32<<<grid_for(8 * n, 256), 256, 0, st>>>(ctx->child[L], ctx->ld, 8, ctx->counts + L, -1);
     k_assign_coarse<<<grid_for(n, 256), 256, 0, st>>>(ctx->table, ctx->slot_of, n_fine, ctx->rank, ctx->block_sums,
                                                        ctx->keys[L - 1], L - 1, ctx->keys[L], ctx->parent[L - 1],
                                                        ctx->child[L], ctx->upmap[L - 1], ctx->ld);
     static const char* nm_s[5] = {"", "stride.L1", "stride.L2", "stride.L3", "stride.L4"};
-    static const char* nm_b[5] = {"", "blocks.L1", "blocks.L2", "blocks.L3", "blocks.L4"};
-    static const char* nm_k[5] = {"", "kmap3.L1", "kmap3.L2", "kmap3.L3", "kmap3.L4"};
     prof_mark(ctx, nm_s[L], st);
-    build_blocks(L);
-    prof_mark(ctx, nm_b[L], st);
-    SPS_CUDA_CHECK(cudaMemsetAsync(ctx->tmask3[L], 0, mask_bytes, st));
-    k_kernel_map_blk3<3><<<dim3(grid_for(n, 256, 148 * 8), 3), 256, 0, st>>>(ctx->keys[L], ctx->counts + L, ctx->table,
-                                                                                ctx->cells, ctx->occ, L, ctx->nbr3[L],
-                                                                                ctx->ld, sparse_ok(L) ? nullptr : ctx->tmask3[L],
-                                                                                ctx->vmask, sparse_ok(L) ? 0 : 1);
-    prof_mark(ctx, nm_k[L], st);
-    { const int rc = pattern_order(ctx, L, st); if (rc != SPS_OK) return rc; }
   }
+  // ---- 2. block tables of all five levels (three launches) ----
+  // fused forward on a shape-sorted level: the convolutions read the tile slices and the sorted tile masks, the slices
+  // read only present entries -> neither the -1 entries nor the physical-order tile masks are produced
+  const bool sorting = sort_active(ctx);
+  auto sparse_ok = [&](int L) {
+    return c0 != nullptr && !needs_dense_maps(ctx) && g_tile_slices && ctx->tslice[L] != nullptr && sorting && L >= kFirstSortedLevel &&
+           L <= kLastSortedLevel;
+  };
+  LevelTabs T;
+  ScratchZero Z;
+  KmapOut O;
+  O.dense_mask = 0;
+  for (int L = 0; L < SPS_NUM_LEVELS; ++L) {
+    T.keys[L] = ctx->keys[L]; T.btab[L] = ctx->btab[L]; T.cells[L] = ctx->bcells[L]; T.occ[L] = ctx->bocc[L];
+    Z.tmask3[L] = sparse_ok(L) ? nullptr : ctx->tmask3[L];
+    O.nbr[L] = ctx->nbr3[L]; O.tile_masks[L] = Z.tmask3[L]; O.vmask[L] = ctx->vmask[L];
+    if (!sparse_ok(L)) O.dense_mask |= 1 << L;
+  }
+  T.counts = ctx->counts; T.nblocks = ctx->nblocks;
+  Z.sort_hist = sorting ? ctx->sort_hist : nullptr; Z.sort_status = ctx->sort_status;
+  Z.sort_first = kFirstSortedLevel; Z.sort_levels = kSortedLevels;
+  O.ld = ctx->ld;
+  const int gx = grid_for(n, 256, 148 * 8);
+  k_blocks_begin<<<dim3(grid_for(table_capacity(n), 256, 148 * 8), SPS_NUM_LEVELS), 256, 0, st>>>(T, Z);
+  k_block_insert<<<dim3(gx, SPS_NUM_LEVELS), 256, 0, st>>>(T);
+  k_cells_fill<<<dim3(gx, SPS_NUM_LEVELS), 256, 0, st>>>(T);
+  prof_mark(ctx, "blocks", st);
+  // ---- 3. conv0 off the level-0 block table (fused forward), or the 5x5x5x1 table (layer-level API) ----
+  if (c0) {
+    if (c0->feat)   // per-voxel features: gather them through the block table
+      k_conv0_blk<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->btab[0], ctx->bcells[0], c0->feat,
+                                                     c0->w, c0->shift, c0->round_out, c0->out, c0->out_ld);
+    else            // one constant feature (SPSModel.forward): presence bits only
+      k_conv0_const<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->btab[0], ctx->bocc[0], c0->cfeat,
+                                                       c0->w, c0->shift, c0->round_out, c0->out, c0->out_ld);
+    prof_mark(ctx, "conv0+kmap5", st);
+  } else {
+    k_kernel_map_blk<5, 1><<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->btab[0], ctx->bcells[0], ctx->bocc[0], 0,
+                                                              ctx->nbr5, ctx->ld, nullptr, nullptr);
+    prof_mark(ctx, "kmap5.L0", st);
+  }
+  ctx->have_nbr5 = c0 == nullptr;
+  // ---- 4. 3x3x3x3 kernel maps of all five levels (one launch: level x time plane) ----
+  k_kernel_map_blk3<3><<<dim3(gx, 3, SPS_NUM_LEVELS), 256, 0, st>>>(T, O);
+  prof_mark(ctx, "kmap3", st);
   SPS_CUDA_CHECK(cudaGetLastError());
+  ctx->forward_launches += 16 + 3 + 1 + 1;
+  // ---- 5. shape sort + per-tile slices of the sorted levels ----
+  { const int rc = pattern_order(ctx, st); if (rc != SPS_OK) return rc; }
   ctx->have_maps = true;
-  ctx->dense_maps = !(sparse_ok(0) || sparse_ok(1) || sparse_ok(2) || sparse_ok(3));
-  ctx->have_perm = ctx->pattern_sort == 2 || (ctx->pattern_sort == 1 && ctx->n >= kMinRowsForSort);
+  ctx->dense_maps = O.dense_mask == (1 << SPS_NUM_LEVELS) - 1;
+  ctx->have_perm = sorting;
   ctx->have_slices = ctx->have_perm && g_tile_slices && kLastSortedLevel <= 3;
   ctx->first_sorted = kFirstSortedLevel;
   ctx->last_sorted = kLastSortedLevel;
@@ -1089,8 +1215,7 @@ extern "C" int sps_map_build(sps_map** out, void* d_storage, size_t bytes, const
   if (s.bytes > bytes) return SPS_ERR_CAPACITY;
   cudaStream_t st = (cudaStream_t)stream_;
   SPS_CUDA_CHECK(cudaMemsetAsync(s.scalars, 0, 64 * 4, st));
-  k_set_i32<<<1, 1, 0, st>>>(s.scalars + 0, (int32_t)n);
-  k_table_clear<<<grid_for(s.cap, 256), 256, 0, st>>>(s.table, s.scalars + 0);
+  k_level_begin<<<grid_for(s.cap, 256), 256, 0, st>>>(s.table, nullptr, (int32_t)n, s.scalars + 0, nullptr, 0);
   k_insert_xyz<<<grid_for(n, 256), 256, 0, st>>>(d_map_xyz, s.scalars + 0, ds, s.table, nullptr, s.scalars + 40);
   SPS_CUDA_CHECK(cudaGetLastError());
   int32_t status = 0;
@@ -1119,8 +1244,7 @@ extern "C" int sps_submap_crop_voxel(const sps_map* map, const float* d_scan_xyz
   cudaStream_t st = (cudaStream_t)stream_;
   SPS_CUDA_CHECK(cudaMemsetAsync(s.scalars, 0, 64 * 4, st));
   SPS_CUDA_CHECK(cudaMemsetAsync(d_counts, 0, 2 * 4, st));
-  k_set_i32<<<1, 1, 0, st>>>(s.scalars + 0, (int32_t)n_scan);
-  k_table_clear<<<grid_for(s.cap, 256), 256, 0, st>>>(s.table, s.scalars + 0);
+  k_level_begin<<<grid_for(s.cap, 256), 256, 0, st>>>(s.table, nullptr, (int32_t)n_scan, s.scalars + 0, nullptr, 0);
   k_insert_xyz<<<grid_for(n, 256), 256, 0, st>>>(d_scan_xyz, s.scalars + 0, map->ds, s.table, s.slot_of,
                                                   s.scalars + 40);
   k_first_rank<<<cdiv(n, kScanBlock), kScanBlock, 0, st>>>(s.table, s.slot_of, s.scalars + 0, s.rank, s.block_sums,

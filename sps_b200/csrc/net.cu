@@ -467,10 +467,7 @@ static int forward_feat_impl(sps_ctx* ctx, const sps_net* net, const float* d_po
   rc = devox(ctx->buf[sps_ctx::LOGITS], ctx->inv, n_scores, d_scores, net->apply_sigmoid, st);
   if (rc != SPS_OK) return rc;
   prof_mark(ctx, "devox_sigmoid", st);
-  // voxelize 5; map building 51 (block tables, strided levels, kernel maps) + 2 + 3 * passes per shape-sorted level (keys,
-  // the radix passes of 3 kernels each, permuted tile masks + slices); devox 1
-  const int sorted_levels = ctx->have_perm ? ctx->last_sorted - ctx->first_sorted + 1 : 0;
-  ctx->forward_launches += 5 + 51 + (2 + 3 * SPS_SORT_PASSES) * sorted_levels + 1;
+  ctx->forward_launches += 4 + 1;   // voxelise (4) and the devoxelisation; build_maps_impl / run_conv count their own
   return SPS_OK;
 }
 }  // namespace sps
