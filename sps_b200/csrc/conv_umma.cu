@@ -44,7 +44,6 @@ constexpr int kV6EpiWarp0 = kV6MmaWarp + 1;
 constexpr int kV6Threads = (kV6EpiWarp0 + 4) * 32;
 constexpr int kV6Entries = kMaxK + 1;                 // present offsets + the tile's own rows
 constexpr int kV6EntryBytes = kTileM * 4;
-constexpr int kV6ParBytes = kV6Entries * kV6EntryBytes;  // staged row indices of one 81-offset tile
 // The index area (2 x 82 entries) holds as many tiles as fit: 2 for the 81-offset kernels, 8 for the 2x2x2 ones
 // (9 entries per tile).  Tiles of the small kernels are one or two stages long, so the number of tiles in flight
 // -- not the stage ring -- bounds their memory-level parallelism.
@@ -58,13 +57,18 @@ constexpr int kV6KlistBytes = 256;
 #endif
 template <int NPAD>
 struct V6Cfg {
-  static constexpr int S = NPAD == 64 ? SPS_V6_S64 : NPAD == 32 ? SPS_V6_S32 : SPS_V6_S16;
+  // SPS's own widths (N <= 64): 4 stages, two tiles of kernel-map slices staged.  Wide accumulators of the width sweep
+  // (N = 128 / 256, 16 / 32 KB of weights per stage): 4 / 3 stages and ONE staged slice -- a stage of such a layer keeps
+  // the tensor pipe busy for 256 / 512 cycles, the loader's bubble at a tile boundary is noise there.
+  static constexpr int S = NPAD == 256 ? 3 : NPAD == 128 ? 4 : NPAD == 64 ? SPS_V6_S64 : NPAD == 32 ? SPS_V6_S32 : SPS_V6_S16;
   static constexpr int kBStage = NPAD * 128;
   static constexpr int kTmemCols = 2 * NPAD < 32 ? 32 : 2 * NPAD;
-  // A ring | B ring | row indices [2][82][128] | barriers | klists | nact [8] | shift [64] | tmem slot
-  static constexpr size_t smem = (size_t)S * (kAStageBytes + kBStage) + 2 * (size_t)kV6ParBytes +
+  static constexpr int kIdxEntries = NPAD >= 128 ? kV6Entries : 2 * kV6Entries;
+  static constexpr int kShift = NPAD < 64 ? 64 : NPAD;
+  // A ring | B ring | row indices [kIdxEntries][128] | barriers | klists | nact [8] | shift | tmem slot
+  static constexpr size_t smem = (size_t)S * (kAStageBytes + kBStage) + (size_t)kIdxEntries * kV6EntryBytes +
                                  8 * (2 * S + 2 * kV6MaxTilesAhead + 4) + kV6KlistBytes + 4 * kV6MaxTilesAhead +
-                                 64 * 4 + 16 + SPS_V6_PAD_KB * 1024;
+                                 kShift * 4 + 16 + SPS_V6_PAD_KB * 1024;
 };
 
 // 16-byte copy that writes zeros instead when `skip` is set (the ignore-src form: one predicate, no size select)
@@ -111,12 +115,12 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
   uint8_t* sA = smem;
   uint8_t* sB = smem + S * kAStageBytes;
   int32_t* sidx = reinterpret_cast<int32_t*>(sB + S * kBStageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sidx) + 2 * kV6ParBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sidx) + Cfg::kIdxEntries * kV6EntryBytes);
   // bars: full[S], empty[S], idx_full[8], idx_empty[8], acc_full[2], acc_empty[2]
   uint8_t* klist = reinterpret_cast<uint8_t*>(bars + 2 * S + 2 * kV6MaxTilesAhead + 4);
   int32_t* snact = reinterpret_cast<int32_t*>(klist + kV6KlistBytes);
   float* sshift = reinterpret_cast<float*>(snact + kV6MaxTilesAhead);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sshift + 64);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sshift + Cfg::kShift);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB), sidx_u = smem_u32(sidx);
@@ -137,7 +141,7 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (tid < 64) sshift[tid] = (a.shift && tid < a.cout) ? __ldg(a.shift + tid) : 0.f;
+  for (int i = tid; i < NPAD; i += kV6Threads) sshift[i] = (a.shift && i < a.cout) ? __ldg(a.shift + i) : 0.f;
   // Weight stages by TMA: a full-width K slab (64 fp16 channels of one kernel offset, all NPAD rows) is ONE 2-D box of
   // the K-major weight matrix, landed in the SWIZZLE_128B layout the MMA descriptor reads -- off the LSU path that
   // the gathers saturate.  Narrower slabs (several offsets per stage) would need one small box per offset: those
@@ -167,7 +171,7 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
   const uint32_t* tmask = a.tile_mask;
   const int gstep = gridDim.x;
   // tiles whose index slices fit in the staging area at once, and the bytes each takes
-  const int NP = min(kV6MaxTilesAhead, (2 * kV6Entries) / (K + 1));
+  const int NP = min(kV6MaxTilesAhead, Cfg::kIdxEntries / (K + 1));
   const uint32_t par_bytes = (uint32_t)(K + 1) * kV6EntryBytes;
   const int kl_stride = (K + 1 + 15) & ~15;
   auto tile_nact = [&](int tile) {
@@ -442,68 +446,78 @@ __global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_arg
       const int row = row_next;
       if (tile + gstep < ntiles) look(tile + gstep);
       const int b = n_acc & 1;
-      float acc[NPAD];
-      if (nstages > 0) {
+      const bool have = nstages > 0;
+      if (have) {
         mbar_wait(bar_accf + 8 * b, (n_acc >> 1) & 1);
         ++n_acc;
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * NPAD);
-#pragma unroll
-        for (int cb = 0; cb < NPAD / 8; ++cb) tmem_ld8(taddr + cb * 8, acc + cb * 8);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        tc_fence_before();
-        mbar_arrive(bar_acce + 8 * b);
-      } else {
-#pragma unroll
-        for (int c = 0; c < NPAD; ++c) acc[c] = 0.f;
       }
-      if (row < 0) continue;
-      if (NPAD == 16 && (p.flags & SPS_CONV_FOLD_LO)) {   // columns 8..15 = the row times the LOW parts of the weights
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * NPAD);
+      const bool live = row >= 0;
+      // 16 accumulator columns at a time: few live registers (the CTA leaves room for another lane's map kernels on
+      // the same SM), and the same code serves the wide accumulators of the width sweep
+#pragma unroll 4
+      for (int c0 = 0; c0 < NPAD; c0 += 16) {
+        float acc[16];
+        __syncwarp();                       // tcgen05.ld is warp-collective: every lane is back from the stores
+        if (have) {
+          tmem_ld8(taddr + c0, acc);
+          tmem_ld8(taddr + c0 + 8, acc + 8);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (c0 + 16 >= NPAD) {            // last chunk read: the accumulator may be overwritten
+            tc_fence_before();
+            mbar_arrive(bar_acce + 8 * b);
+          }
+        } else {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[c] += acc[c + 8];
-      }
+          for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+        }
+        if (live && c0 < cout) {
+          if (NPAD == 16 && (p.flags & SPS_CONV_FOLD_LO)) {   // columns 8..15 = the row times the LOW parts of the weights
 #pragma unroll
-      for (int c = 0; c < NPAD; c += 8)
-        if (c < cout) {
-          float rv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (a.res) {
-            if (kHalf) {
-              const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.res) + (int64_t)row * a.res_ld + c));
-              const __half2* h = reinterpret_cast<const __half2*>(&u);
+            for (int c = 0; c < 8; ++c) acc[c] += acc[c + 8];
+          }
 #pragma unroll
-              for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); rv[2 * j] = f.x; rv[2 * j + 1] = f.y; }
-            } else {
-              const float* resp = a.res + (int64_t)row * a.res_ld + c;
-              if (res_vec) {
-                const float4 r0 = __ldg(reinterpret_cast<const float4*>(resp)), r1 = __ldg(reinterpret_cast<const float4*>(resp + 4));
-                rv[0] = r0.x; rv[1] = r0.y; rv[2] = r0.z; rv[3] = r0.w; rv[4] = r1.x; rv[5] = r1.y; rv[6] = r1.z; rv[7] = r1.w;
+          for (int c = 0; c < 16; c += 8) {
+            const int cc = c0 + c;
+            if (cc >= cout) continue;
+            float rv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (a.res) {
+              if (kHalf) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.res) + (int64_t)row * a.res_ld + cc));
+                const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); rv[2 * j] = f.x; rv[2 * j + 1] = f.y; }
               } else {
+                const float* resp = a.res + (int64_t)row * a.res_ld + cc;
+                if (res_vec) {
+                  const float4 r0 = __ldg(reinterpret_cast<const float4*>(resp)), r1 = __ldg(reinterpret_cast<const float4*>(resp + 4));
+                  rv[0] = r0.x; rv[1] = r0.y; rv[2] = r0.z; rv[3] = r0.w; rv[4] = r1.x; rv[5] = r1.y; rv[6] = r1.z; rv[7] = r1.w;
+                } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) rv[j] = __ldg(resp + j);
+                  for (int j = 0; j < 8; ++j) rv[j] = __ldg(resp + j);
+                }
               }
             }
-          }
+            float v8[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float v = acc[c + j] + sshift[c + j] + rv[j];
-            if (a.relu) v = fmaxf(v, 0.f);
-            acc[c + j] = v;
+            for (int j = 0; j < 8; ++j) {
+              float v = acc[c + j] + sshift[cc + j] + rv[j];
+              if (a.relu) v = fmaxf(v, 0.f);
+              v8[j] = v;
+            }
+            if (a.head_out && cc == 0) {     // final 1x1 conv + bias on the 8 channels of the block output
+              float sum = a.head_b;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) sum = fmaf(v8[j], __ldg(a.head_w + j), sum);
+              a.head_out[row] = sum;
+            }
+            if (a.out) {
+              if (kHalf && (p.flags & SPS_CONV_OUT_SPLIT)) store_row8(a.out + cc, a.out_ld, row, v8, kStoreF16x2);   // 16 halves per 8 channels
+              else store_row8(a.out + (kHalf ? cc / 2 : cc), a.out_ld, row, v8, kHalf ? kStoreF16 : (p.round_out ? kStoreTF32 : kStoreF32));
+            }
           }
         }
-      if (a.head_out) {
-        float s = a.head_b;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) s = fmaf(acc[c], __ldg(a.head_w + c), s);
-        a.head_out[row] = s;
-      }
-      if (a.out) {
-#pragma unroll
-        for (int c = 0; c < NPAD; c += 8)
-          if (c < cout) {
-            const float v8[8] = {acc[c], acc[c + 1], acc[c + 2], acc[c + 3], acc[c + 4], acc[c + 5], acc[c + 6], acc[c + 7]};
-            if (kHalf && (p.flags & SPS_CONV_OUT_SPLIT)) store_row8(a.out + c, a.out_ld, row, v8, kStoreF16x2);   // 16 halves per 8 channels
-            else store_row8(a.out + (kHalf ? c / 2 : c), a.out_ld, row, v8, kHalf ? kStoreF16 : (p.round_out ? kStoreTF32 : kStoreF32));
-          }
       }
     }
   }
@@ -575,8 +589,28 @@ static int conv_umma6_t(const sps_conv_args& a, const UmmaParams& p, cudaStream_
     case 16: return launch_umma6_n<16, T>(a, p, st);
     case 32: return launch_umma6_n<32, T>(a, p, st);
     case 64: return launch_umma6_n<64, T>(a, p, st);
-    default: return SPS_ERR_UNSUPPORTED;
+    default: break;
   }
+  if (sizeof(T) != 2) return SPS_ERR_UNSUPPORTED;
+  // wide layers (the PLANES x2 .. x8 sweep of BASELINE config 5), fp16 rows only
+  if (a.cout == 128) return launch_umma6<128, 8, T>(a, p, st);
+  if (a.cout == 256) return launch_umma6<256, 8, T>(a, p, st);
+  if (a.cout == 512) {
+    // two passes of 256 output channels: the accumulator pair of one pass fills the 512 TMEM columns
+    for (int h = 0; h < 2; ++h) {
+      sps_conv_args b = a;
+      UmmaParams q = p;
+      b.cout = 256;
+      q.wt = reinterpret_cast<const float*>(reinterpret_cast<const __half*>(p.wt) + (int64_t)h * 256 * p.ldk);
+      if (a.shift) b.shift = a.shift + 256 * h;
+      if (a.out) b.out = reinterpret_cast<float*>(reinterpret_cast<__half*>(a.out) + 256 * h);
+      if (a.res) b.res = reinterpret_cast<const float*>(reinterpret_cast<const __half*>(a.res) + 256 * h);
+      const int rc = launch_umma6<256, 8, T>(b, q, st);
+      if (rc != SPS_OK) return rc;
+    }
+    return SPS_OK;
+  }
+  return SPS_ERR_UNSUPPORTED;
 }
 
 int conv_umma(const sps_conv_args& a, cudaStream_t st) {
@@ -630,7 +664,8 @@ bool conv_umma_f16_supports(const sps_conv_args& a) {
   if (a.in2 && ((a.cin2 & 7) || (a.in2_ld & 7))) return false;
   if (a.res && (a.res_ld & 7)) return false;
   if (a.out && (a.out_ld & 7)) return false;
-  if (!(a.cout == 8 || a.cout == 16 || a.cout == 32 || a.cout == 64)) return false;
+  if (!(a.cout == 8 || a.cout == 16 || a.cout == 32 || a.cout == 64 || a.cout == 128 || a.cout == 256 || a.cout == 512)) return false;
+  if (a.cout > 64 && (a.cin < 64 || a.head_out)) return false;   // wide accumulators: full 64-channel K slabs only
   if (a.kmajor_ld & 7) return false;
   if ((a.flags & SPS_CONV_FOLD_LO) && a.cout != 8) return false;
   if ((a.flags & SPS_CONV_OUT_SPLIT) && a.out && (a.out_ld & 15)) return false;

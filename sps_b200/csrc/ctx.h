@@ -93,7 +93,8 @@ struct Conv0Fused {
 constexpr int kCatLd[4] = {16, SPS_CAT_PAD ? 32 : 24, SPS_CAT_PAD ? 64 : 48, SPS_CAT_PAD ? 128 : 96};   // CAT8, CAT7, CAT6, CAT5
 constexpr int kBufWidth[sps_ctx::NBUF] = {16, 8, 8, kCatLd[1], 8, 16, kCatLd[2], 16, 32, kCatLd[3], 32, 64, 64, 64, 64, 32, 32,
                                           16, 16, 8, 1, 1};
-constexpr int kScanBlock = 1024;
+// threads per block of the grid-wide scans: small enough (512 x ~31 registers) to co-run with another lane's convolution CTAs
+constexpr int kScanBlock = 512;
 
 // arithmetic mode of a context (see sps_ctx_set_conv_backend)
 inline bool ctx_half_storage(const sps_ctx* c) { return c->backend == SPS_BACKEND_AUTO || c->backend == SPS_BACKEND_F16; }

@@ -97,14 +97,14 @@ __device__ inline int scan_flags(int flag, int i, int n, int nb, int32_t* __rest
   if (lane == 31) warp_sums[wid] = incl;
   __syncthreads();
   if (wid == 0) {
-    int w = warp_sums[lane];
+    int w = lane < kScanBlock / 32 ? warp_sums[lane] : 0;
     int wi = w;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       int v = __shfl_up_sync(0xffffffffu, wi, d);
       if (lane >= d) wi += v;
     }
-    warp_sums[lane] = wi - w;  // exclusive
+    if (lane < kScanBlock / 32) warp_sums[lane] = wi - w;  // exclusive
   }
   __syncthreads();
   const int excl = incl - flag + warp_sums[wid];
@@ -132,14 +132,14 @@ __device__ inline int scan_flags(int flag, int i, int n, int nb, int32_t* __rest
     if (lane == 31) warp_sums[wid] = inc;
     __syncthreads();
     if (wid == 0) {
-      int w = warp_sums[lane];
+      int w = lane < kScanBlock / 32 ? warp_sums[lane] : 0;
       int wi = w;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         int u = __shfl_up_sync(0xffffffffu, wi, d);
         if (lane >= d) wi += u;
       }
-      warp_sums[lane] = wi - w;
+      if (lane < kScanBlock / 32) warp_sums[lane] = wi - w;
     }
     __syncthreads();
     const int ex = inc - v + warp_sums[wid] + carry;
@@ -523,7 +523,7 @@ struct SortArgs {
   int64_t ld;
   int first, nlv;
 };
-constexpr int kSortTile = 1024;
+constexpr int kSortThreads = 256, kSortItems = 4, kSortTile = kSortThreads * kSortItems;
 constexpr uint32_t kOsAggregate = 1u << 30, kOsPrefix = 2u << 30, kOsValue = (1u << 30) - 1u;
 
 __global__ void __launch_bounds__(256)
@@ -552,37 +552,50 @@ k_pattern_keys(const SortArgs A, uint32_t* __restrict__ keys, int32_t* __restric
 }
 
 // One radix pass over the concatenated levels.  LAST: the sorted row numbers go to the per-level perm arrays.
+// 256 threads x 4 keys per tile (1024 keys, element order = round-major): small blocks with few registers and 17 KB of
+// shared memory, so that the sort co-runs with another lane's convolution CTAs instead of waiting for a free SM.
 template <bool LAST>
-__global__ void __launch_bounds__(kSortTile)
+__global__ void __launch_bounds__(kSortThreads)
 k_onesweep_pass(const SortArgs A, const uint32_t* __restrict__ keys, const int32_t* __restrict__ vals, int shift,
                 const uint32_t* __restrict__ hist, uint32_t* status, uint32_t* ticket, int pass,
                 uint32_t* __restrict__ keys_out, int32_t* __restrict__ vals_out) {
-  __shared__ int wcount[kSortTile / 32][256];   // per-warp digit counts, then exclusive offsets across warps
+  constexpr int kWarps = kSortThreads / 32, kSlots = kSortItems * kWarps;   // (round, warp) slots in element order
+  __shared__ uint16_t wcount[kSlots][256];      // per-slot digit counts, then exclusive offsets across slots
   __shared__ int s_tile;
   __shared__ int s_base[256];                   // global position of this tile's first element per digit
-  __shared__ int s_scan[8];
+  __shared__ int s_scan[kWarps];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   if (tid == 0) s_tile = (int)atomicAdd(ticket, 1u);   // tiles are handed out in launch order: a tile's predecessors run
-  for (int j = tid; j < (kSortTile / 32) * 256; j += kSortTile) (&wcount[0][0])[j] = 0;
+  for (int j = tid; j < kSlots * 128; j += kSortThreads) reinterpret_cast<uint32_t*>(&wcount[0][0])[j] = 0u;
   __syncthreads();
   const int tile = s_tile;
   const int n = sort_total(A.counts, A.first, A.nlv);
   const int ntiles = (n + kSortTile - 1) / kSortTile;
   if (tile >= ntiles) return;
-  const int i = tile * kSortTile + tid;
-  const bool live = i < n;
-  const uint32_t key = live ? keys[i] : 0u;
-  const int val = live ? vals[i] : 0;
-  const unsigned digit = live ? ((key >> shift) & 255u) : (256u + lane);   // dead lanes match nobody
-  const unsigned peers = __match_any_sync(0xffffffffu, digit);
-  const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
-  if (live && rank_in_warp == 0) wcount[w][digit] = __popc(peers);
+  uint32_t key[kSortItems];
+  int val[kSortItems], rank[kSortItems];
+#pragma unroll
+  for (int r = 0; r < kSortItems; ++r) {
+    const int i = tile * kSortTile + r * kSortThreads + tid;
+    const bool live = i < n;
+    key[r] = live ? keys[i] : 0xFFFFFFFFu;
+    val[r] = live ? vals[i] : -1;
+  }
+#pragma unroll
+  for (int r = 0; r < kSortItems; ++r) {
+    const bool live = val[r] >= 0;
+    const unsigned digit = live ? ((key[r] >> shift) & 255u) : (256u + lane);   // dead lanes match nobody
+    const unsigned peers = __match_any_sync(0xffffffffu, digit);
+    rank[r] = __popc(peers & ((1u << lane) - 1u));
+    if (live && rank[r] == 0) wcount[r * kWarps + w][digit] = (uint16_t)__popc(peers);
+  }
   __syncthreads();
-  if (tid < 256) {
-    int run = 0;   // exclusive prefix over the warps of this tile, per digit
-    for (int ww = 0; ww < kSortTile / 32; ++ww) {
-      const int c = wcount[ww][tid];
-      wcount[ww][tid] = run;
+  {
+    int run = 0;   // exclusive prefix over the slots of this tile for digit `tid`
+#pragma unroll 8
+    for (int sl = 0; sl < kSlots; ++sl) {
+      const int c = wcount[sl][tid];
+      wcount[sl][tid] = (uint16_t)run;
       run += c;
     }
     // decoupled look-back: digits of the tiles before this one
@@ -597,7 +610,8 @@ k_onesweep_pass(const SortArgs A, const uint32_t* __restrict__ keys, const int32
       while (true) {
         const uint32_t v = *reinterpret_cast<volatile uint32_t*>(status + ((size_t)t * 4 + pass) * 256 + tid);
         if ((v >> 30) == 0u) {                         // predecessor has not published yet (it is running: ticket order)
-          if (++spins > (1u << 26)) { atomicOr(A.status, kStatusCapacity); break; }   // never hang: report instead
+          if (++spins > (1u << 22)) { atomicOr(A.status, kStatusCapacity); break; }   // never hang: report instead
+          __nanosleep(40);
           continue;
         }
         excl += (int)(v & kOsValue);
@@ -618,22 +632,25 @@ k_onesweep_pass(const SortArgs A, const uint32_t* __restrict__ keys, const int32
     s_base[tid] = inc - hv + excl;
   }
   __syncthreads();
-  if (tid < 256) {
+  {
     int add = 0;
     for (int ww = 0; ww < w; ++ww) add += s_scan[ww];
     s_base[tid] += add;
   }
   __syncthreads();
-  if (live) {
-    const int pos = s_base[digit] + wcount[w][digit] + rank_in_warp;
+#pragma unroll
+  for (int r = 0; r < kSortItems; ++r) {
+    if (val[r] < 0) continue;
+    const unsigned digit = (key[r] >> shift) & 255u;
+    const int pos = s_base[digit] + wcount[r * kWarps + w][digit] + rank[r];
     if (LAST) {
-      const int j = (int)(key >> 29);
+      const int j = (int)(key[r] >> 29);
       int off = 0;
       for (int q = 0; q < j; ++q) off += A.counts[A.first + q];
-      A.perm[A.first + j][pos - off] = val;
+      A.perm[A.first + j][pos - off] = val[r];
     } else {
-      keys_out[pos] = key;
-      vals_out[pos] = val;
+      keys_out[pos] = key[r];
+      vals_out[pos] = val[r];
     }
   }
 }
@@ -960,10 +977,10 @@ static int pattern_order(sps_ctx* ctx, cudaStream_t st) {
     uint32_t* ko = ctx->sort_keys[(pass & 1) ^ 1];
     int32_t* vo = ctx->sort_vals[(pass & 1) ^ 1];
     if (pass < 3)
-      k_onesweep_pass<false><<<tiles_max, kSortTile, 0, st>>>(A, ki, vi, 8 * pass, hist + 256 * pass, ctx->sort_status, hist + 1024 + pass,
+      k_onesweep_pass<false><<<tiles_max, kSortThreads, 0, st>>>(A, ki, vi, 8 * pass, hist + 256 * pass, ctx->sort_status, hist + 1024 + pass,
                                                               pass, ko, vo);
     else
-      k_onesweep_pass<true><<<tiles_max, kSortTile, 0, st>>>(A, ki, vi, 8 * pass, hist + 256 * pass, ctx->sort_status, hist + 1024 + pass,
+      k_onesweep_pass<true><<<tiles_max, kSortThreads, 0, st>>>(A, ki, vi, 8 * pass, hist + 256 * pass, ctx->sort_status, hist + 1024 + pass,
                                                              pass, nullptr, nullptr);
   }
   prof_mark(ctx, "sort", st);

@@ -256,3 +256,41 @@ def test_split_rows_into_concat_buffer_slices():
     got = convops.merge_rows(cat8[:, :16].contiguous()).cpu().numpy()
     assert np.abs(got - ref).max() < 4e-6 * max(1.0, np.abs(ref).max())
     assert (cat8[:, 16:] == 0).all()           # the other half of the concat buffer is untouched
+
+
+@pytest.mark.parametrize("cin,cout", [(64, 128), (128, 128), (192, 128), (96, 64), (128, 256), (384, 256), (256, 512), (768, 512)])
+def test_wide_layers_of_the_width_sweep(cin, cout):
+    """BASELINE configs[4]: PLANES x2 ... x8 (Cin / Cout up to 768 / 512).  N = 128 / 256 accumulators (512 output channels
+    as two passes), weight slabs through TMA, chunked epilogue -- against float64 numpy on the fp16-rounded operands,
+    with the fused 1x1 term and the identity residual."""
+    from sps_b200 import convops
+    rng = np.random.default_rng(cin + cout)
+    V, K = 700, 81
+    nbr = random_map(rng, K, V, V, 0.3)
+    nbr[:, 300:450] = -1
+    nbr[50:, 500:] = -1
+    x = rng.standard_normal((V, cin)).astype(np.float32)
+    w = (rng.standard_normal((K, cin, cout)) / np.sqrt(cin * 8)).astype(np.float32)
+    shift = rng.standard_normal(cout).astype(np.float32)
+    cin2 = cin // 2 if (cin // 2) % 64 == 0 else 64
+    x2 = rng.standard_normal((V, cin2)).astype(np.float32)
+    w2 = (rng.standard_normal((cin2, cout)) / np.sqrt(cin2)).astype(np.float32)
+    res = rng.standard_normal((V, cout)).astype(np.float32)
+    ld = (V + 31) // 32 * 32
+    m = np.full((K, ld), -1, np.int32)
+    m[:, :V] = nbr
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a)).cuda()
+    n_out = torch.tensor([V], dtype=torch.int32, device="cuda")
+    for kw in (dict(shift=True, relu=True, fused=True), dict(res=True)):
+        wt = convops.pack_kmajor_f16(t(w), t(w2) if kw.get("fused") else None)
+        out = convops.conv_fwd(t(x).half(), t(w), n_out, map=t(m), map_ld=ld, shift=t(shift) if kw.get("shift") else None,
+                               in2=t(x2).half() if kw.get("fused") else None, weight2=t(w2) if kw.get("fused") else None,
+                               res=t(res).half() if kw.get("res") else None, relu=kw.get("relu", False), weight_kmajor=wt,
+                               io_f16=True, backend=3)
+        torch.cuda.synchronize()
+        got = out[:V].float().cpu().numpy()
+        ref = ref_conv(x, nbr, w, shift=shift if kw.get("shift") else None, x2=x2 if kw.get("fused") else None,
+                       w2=w2 if kw.get("fused") else None, res=f16(res) if kw.get("res") else None, relu=kw.get("relu", False),
+                       quant=f16)
+        assert got.shape == (V, cout)
+        assert np.abs(got - ref).max() < 2e-3 * max(1.0, np.abs(ref).max()), (kw, np.abs(got - ref).max())
