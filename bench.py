@@ -456,6 +456,7 @@ def setup_model(args, n_max, local, sd=None):
     model.MinkUNet.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()})
     model = model.cuda().eval()
     model.lanes = args.lanes
+    model.use_graphs = model.use_graphs and not args.no_graphs
     model.set_conv_backend(args.backend)
     engine, net = model._prepare(n_max, torch.device("cuda", local))
     return model, engine, net, sd
@@ -492,7 +493,9 @@ def run_config2(args):
 
     def measure(inputs, steps):
         fn = step(inputs)
-        for k in range(max(args.warmup, 3)):
+        # warm-up: every (lane, batch) pair is seen twice before it replays as a CUDA graph (eager, then capture)
+        nwarm = max(args.warmup, 3, (3 * model.lanes * len(inputs)) if model.use_graphs else 0)
+        for k in range(nwarm):
             fn(k)
         drain()
         return d.timed(fn, steps, finish=drain)
@@ -523,7 +526,7 @@ def run_config2(args):
                    "scans_per_step_per_gpu": BATCH, "weights": "random-init (seed 0), BN eval fresh stats",
                    "l2": f"per-step working set (kernel maps + features, several GB) exceeds the 126 MB L2; "
                          f"{len(host)} distinct batches rotate",
-                   "conv_backend": args.backend, "lanes": args.lanes, "tma_weight_stages": bool(engine.lib.sps_tma_weights_available()),
+                   "conv_backend": args.backend, "lanes": args.lanes, "cuda_graphs": bool(model.use_graphs), "tma_weight_stages": bool(engine.lib.sps_tma_weights_available()),
                    "sharding": "scan-sharded, replicated weights; per step one NCCL all_gather_into_tensor of the "
                                f"scan-row scores (fp32 [{BATCH} x {PTS_PER_SCAN}] per rank) on a dedicated stream"},
         "mpoints_per_s": value * PTS_PER_SCAN / 1e6,
@@ -677,7 +680,7 @@ def run_config4(args):
         while pending:
             finish_one()
 
-    for k in range(max(args.warmup, 3)):
+    for k in range(max(args.warmup, 3, (3 * model.lanes * len(dev)) if model.use_graphs else 0)):
         fn(k)
     drain()
     sampler = ClockSampler(d.local)
@@ -724,6 +727,7 @@ def main():
                          "2 tcgen05 TF32 on fp32 rows, 3 = 0")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt", action="store_true", help="skip the backend-2 (TF32) comparison line")
+    ap.add_argument("--no-graphs", action="store_true", help="enqueue every forward kernel by kernel instead of replaying CUDA graphs")
     ap.add_argument("--lanes", type=int, default=3, help="engine contexts/streams forward_async alternates between")
     ap.add_argument("--widths", default="1,2,4,8", help="config 5: PLANES multipliers of the sweep")
     args = ap.parse_args()

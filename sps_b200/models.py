@@ -11,6 +11,7 @@ computed inline.  Training (models.py:62-82,154-160) is out of scope (inference-
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 import torch
@@ -160,6 +161,9 @@ class SPSModel(nn.Module):
         self.lanes = 3            # engine contexts / streams that forward_async alternates between
         self.output_channel, self.apply_sigmoid = 0, True   # models.py:28-29: sigmoid of the single output channel
         self.conv_backend = None  # None: the host default of sps_b200.engine.DEFAULTS at engine creation
+        # forward_async replays the whole forward (56 kernels) as ONE CUDA graph per (lane, input buffer, row count):
+        # the first call with a given input runs eagerly, the second is captured, later ones are replays
+        self.use_graphs = os.environ.get("SPS_NO_GRAPHS", "0") != "1"
 
     def set_conv_backend(self, backend: int):
         """Arithmetic mode of every engine this model owns (0 auto, 1 exact fp32, 2 TF32 on fp32 rows, 3 fp16 rows)."""
@@ -246,7 +250,7 @@ class SPSModel(nn.Module):
                               "d_in": [torch.empty((cap, ld), dtype=torch.float32, device=device) for _ in range(self.lanes)],
                               "d_out": [torch.empty(cap, dtype=torch.float32, device=device) for _ in range(self.lanes)],
                               "h_out": [torch.empty(cap, dtype=torch.float32).pin_memory() for _ in range(self.lanes)],
-                              "busy": [None] * self.lanes}
+                              "busy": [None] * self.lanes, "graphs": [dict() for _ in range(self.lanes)]}
         slot = p["k"] % self.lanes
         p["k"] += 1
         if p["busy"][slot] is not None:
@@ -257,7 +261,7 @@ class SPSModel(nn.Module):
         if on_device:
             # inputs already resident in HBM: no copies, the scores stay on the device
             with torch.cuda.stream(compute):
-                lane_engine.forward(net, coordinates, self.voxel_size, out=d_out)
+                self._lane_forward(p, slot, lane_engine, net, coordinates, d_out, compute)
                 done = torch.cuda.Event()
                 done.record(compute)
             p["busy"][slot] = done
@@ -268,13 +272,37 @@ class SPSModel(nn.Module):
             ready.record(p["copy"])
         with torch.cuda.stream(compute):
             compute.wait_event(ready)
-            lane_engine.forward(net, d_in, self.voxel_size, out=d_out)
+            self._lane_forward(p, slot, lane_engine, net, d_in, d_out, compute)
             h_out.copy_(d_out, non_blocking=True)
             done = torch.cuda.Event()
             done.record(compute)
         p["busy"][slot] = done
         engine = lane_engine
         return _Pending(done, h_out, engine, device_scores=d_out)
+
+    def _lane_forward(self, p, slot, lane_engine, net, src, d_out, compute):
+        """One forward on a lane's stream (current), eagerly or as a CUDA-graph replay.  Every size that only exists on
+        the device stays there, so the captured launch sequence is valid for any content of the same buffers."""
+        if not self.use_graphs:
+            lane_engine.forward(net, src, self.voxel_size, out=d_out)
+            return
+        graphs = p["graphs"][slot]
+        key = (src.data_ptr(), src.shape[0], src.stride(0), d_out.data_ptr(), lane_engine.conv_backend, id(net))
+        entry = graphs.get(key)
+        if entry is None:                      # first sight: eager (also sets one-time kernel attributes)
+            if len(graphs) >= 8:
+                graphs.clear()
+            graphs[key] = "warm"
+            lane_engine.forward(net, src, self.voxel_size, out=d_out)
+        elif entry == "warm":                  # second sight: capture, then replay
+            compute.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=compute):
+                lane_engine.forward(net, src, self.voxel_size, out=d_out)
+            graphs[key] = (g, src, d_out, net)   # the graph holds raw pointers: keep the tensors alive with it
+            g.replay()
+        else:
+            entry[0].replay()
 
     def check(self):
         """Synchronise and raise if a forward since the last check met an out-of-range coordinate."""

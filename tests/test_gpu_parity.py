@@ -310,3 +310,32 @@ def test_scan_streamer_graph_replay_matches_eager_call(engine_mod, state_dict):
         torch.cuda.synchronize()
         assert got.shape == ref.shape == (len(pts),)
         assert torch.equal(got, ref), (i, float((got - ref).abs().max()))
+
+
+def test_forward_async_graph_replay_equals_eager(engine_mod, state_dict):
+    """forward_async replays the whole forward as a CUDA graph from the third call with the same input buffer on a lane:
+    bit-identical to the eager call, for device inputs and for pinned host inputs, also after the input CONTENT changed
+    (device-side counts: the captured launches do not depend on the data)."""
+    from sps_b200.models import SPSModel
+    rows_a = make_case("tiny", seed=21, batch=2)[:, :5]
+    rows_b = make_case("tiny", seed=22, batch=2)[:, :5]
+    n = min(len(rows_a), len(rows_b))
+    rows_a, rows_b = np.ascontiguousarray(rows_a[:n]), np.ascontiguousarray(rows_b[:n])
+    model = SPSModel(0.1)
+    model.MinkUNet.load_state_dict({k: torch.as_tensor(v) for k, v in state_dict.items()})
+    model = model.cuda().eval()
+    model.lanes = 1
+    assert model.use_graphs
+    eager = {}
+    for name, rows in (("a", rows_a), ("b", rows_b)):
+        eager[name] = model(torch.as_tensor(rows).cuda()).cpu().numpy()
+        model.check()
+    for make in (lambda r: torch.as_tensor(r).cuda(), lambda r: torch.as_tensor(r).pin_memory()):
+        buf = make(rows_a)
+        outs = [model.forward_async(buf).result().cpu().numpy().copy() for _ in range(4)]   # eager, capture + replay, replay, replay
+        for o in outs:
+            assert np.array_equal(o, eager["a"])
+        buf.copy_(torch.as_tensor(rows_b))              # same buffer, new content: the graph is still the right one
+        if buf.is_cuda:
+            torch.cuda.synchronize()
+        assert np.array_equal(model.forward_async(buf).result().cpu().numpy(), eager["b"])
