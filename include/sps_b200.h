@@ -69,12 +69,18 @@ typedef struct sps_level_view {
   const int32_t* parent;    /* [count] parent*8 + child-offset index into level+1 (NULL at 4)*/
   const int32_t* child;     /* [8][ld] child table of the level BELOW (NULL at level 0)     */
   int64_t ld;               /* leading dimension (in voxels) of nbr3/nbr5/child             */
+  /* Processing order of the 3x3x3x3 convolutions after a fused forward that shape-sorted this level (levels 0-3 of
+   * inputs >= 400 000 rows, or sps_ctx_set_pattern_sort(ctx, 2)); all NULL otherwise.  These are what
+   * sps_conv_args.perm / tile_mask / tile_slices take: a caller can run its own layers on the forward's maps. */
+  const int32_t* perm;          /* [count] rows in neighbourhood-shape order                                  */
+  const uint32_t* tile_mask;    /* [ceil(count/128)][4] present-offset masks of the tiles in that order       */
+  const int32_t* tile_slices;   /* [tiles][SPS_TILE_SLICE_ENTRIES][128] kernel map gathered per tile          */
 } sps_level_view;
 /* Valid after sps_voxelize (+ sps_build_maps for the maps).  After a FUSED forward (sps_forward*, sps_infer_scan) on
  * an input large enough for the shape sort (>= 400 000 rows), the 3x3x3x3 tables of levels 0-3 hold only their PRESENT
  * entries (absent ones are not rewritten to -1: every reader inside the library goes through the presence words):
- * the view then carries nbr3 == NULL for every level and sps_ctx_pair_count returns SPS_ERR_STATE; call
- * sps_build_maps to get the complete tables back. */
+ * the view then carries nbr3 == NULL for every level; call sps_build_maps to get the complete tables back
+ * (sps_ctx_pair_count counts from the presence words and works in both states). */
 int sps_ctx_level(sps_ctx* ctx, int level, sps_level_view* out);
 const int32_t* sps_ctx_inverse_map(sps_ctx* ctx);   /* [n] point -> level-0 voxel row        */
 

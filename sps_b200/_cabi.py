@@ -37,7 +37,8 @@ SYMBOLS = [
 
 class LevelView(C.Structure):
     _fields_ = [("keys", C.c_void_p), ("count", C.c_void_p), ("nbr3", C.c_void_p), ("nbr5", C.c_void_p),
-                ("parent", C.c_void_p), ("child", C.c_void_p), ("ld", C.c_int64)]
+                ("parent", C.c_void_p), ("child", C.c_void_p), ("ld", C.c_int64),
+                ("perm", C.c_void_p), ("tile_mask", C.c_void_p), ("tile_slices", C.c_void_p)]
 
 
 class ConvArgs(C.Structure):

@@ -163,6 +163,10 @@ extern "C" int sps_ctx_level(sps_ctx* ctx, int level, sps_level_view* v) {
   v->parent = ctx->parent[level];
   v->child = ctx->child[level];
   v->ld = ctx->ld;
+  const bool sorted = ctx->have_maps && ctx->have_perm && level >= ctx->first_sorted && level <= ctx->last_sorted;
+  v->perm = sorted ? ctx->perm[level] : nullptr;
+  v->tile_mask = sorted ? ctx->ptmask[level] : nullptr;
+  v->tile_slices = sorted && ctx->have_slices ? ctx->tslice[level] : nullptr;
   return SPS_OK;
 }
 
@@ -229,6 +233,18 @@ extern "C" int sps_profile_read(sps_ctx* ctx, char* names, float* ms, int max, i
 }
 
 namespace sps {
+// pairs of a 3x3x3x3 map from the per-voxel presence words (valid also when the tables hold only present entries)
+__global__ void k_count_presence(const uint32_t* __restrict__ vmask, int64_t ld, const int32_t* __restrict__ n_ptr,
+                                 unsigned long long* out) {
+  const int n = *n_ptr;
+  unsigned long long local = 0;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < (int64_t)3 * n; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int it = (int)(idx / n), o = (int)(idx - (int64_t)it * n);
+    local += __popc(vmask[(int64_t)it * ld + o]);
+  }
+  for (int d = 16; d; d >>= 1) local += __shfl_down_sync(0xffffffffu, local, d);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
+}
 __global__ void k_count_nonneg(const int32_t* __restrict__ map, int64_t ld, int K, const int32_t* __restrict__ n_ptr,
                                unsigned long long* out) {
   const int n = *n_ptr;
@@ -247,7 +263,6 @@ __global__ void k_count_nonneg(const int32_t* __restrict__ map, int64_t ld, int 
 extern "C" int sps_ctx_pair_count(sps_ctx* ctx, int level, int kind, int64_t* h_out, void* stream) {
   if (!ctx || !h_out || level < 0 || level >= SPS_NUM_LEVELS) return SPS_ERR_BAD_ARG;
   if (!ctx->have_maps || (kind == 5 && !ctx->have_nbr5)) return SPS_ERR_STATE;
-  if (kind == 3 && !ctx->dense_maps) return SPS_ERR_STATE;   // the fused forward left sparse tables: call sps_build_maps
   const int32_t* map = kind == 3 ? ctx->nbr3[level] : kind == 5 ? (level == 0 ? ctx->nbr5 : nullptr)
                                                     : kind == 8 ? ctx->child[level] : nullptr;
   const int K = kind == 3 ? 81 : kind == 5 ? 125 : 8;
@@ -255,7 +270,8 @@ extern "C" int sps_ctx_pair_count(sps_ctx* ctx, int level, int kind, int64_t* h_
   cudaStream_t st = (cudaStream_t)stream;
   unsigned long long* d_out = reinterpret_cast<unsigned long long*>(ctx->counts + 128);
   SPS_CUDA_CHECK(cudaMemsetAsync(d_out, 0, 8, st));
-  k_count_nonneg<<<148 * 8, 256, 0, st>>>(map, ctx->ld, K, ctx->counts + level, d_out);
+  if (kind == 3) k_count_presence<<<148 * 8, 256, 0, st>>>(ctx->vmask[level], ctx->ld, ctx->counts + level, d_out);
+  else k_count_nonneg<<<148 * 8, 256, 0, st>>>(map, ctx->ld, K, ctx->counts + level, d_out);
   SPS_CUDA_CHECK(cudaGetLastError());
   unsigned long long h = 0;
   SPS_CUDA_CHECK(cudaMemcpyAsync(&h, d_out, 8, cudaMemcpyDeviceToHost, st));

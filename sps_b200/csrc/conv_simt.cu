@@ -303,7 +303,7 @@ extern "C" int sps_conv_fwd(const sps_conv_args* a, void* stream) {
     return SPS_ERR_BAD_ARG;
   if (a->mode == SPS_CONV_UP && (!a->map || a->K != 8 || !a->out || a->in2 || a->res || a->head_out || (a->cin & 3)))
     return SPS_ERR_BAD_ARG;
-  if (a->mode == SPS_CONV_NBR && !a->map && a->K != 1) return SPS_ERR_BAD_ARG;
+  if (a->mode == SPS_CONV_NBR && !a->map && !a->tile_slices && a->K != 1) return SPS_ERR_BAD_ARG;
   const int ea = a->io_dtype == SPS_IO_F16 ? 8 : 4;   // elements per 16 bytes of a row
   if (a->cin < 1 || (a->cin != 1 && a->cin % ea) || (a->in_ld % ea && a->cin != 1)) return SPS_ERR_BAD_ARG;
   if (a->in2 && (!a->weight2 || a->cin2 % ea || a->in2_ld % ea)) return SPS_ERR_BAD_ARG;

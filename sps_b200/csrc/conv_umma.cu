@@ -658,7 +658,8 @@ k_tile_masks(const int32_t* __restrict__ map, int64_t ld, int K, const int32_t* 
 
 // fp16 storage: every layer of the network fits (channel counts are multiples of 8, rows 16-byte aligned)
 bool conv_umma_f16_supports(const sps_conv_args& a) {
-  if (a.io_dtype != SPS_IO_F16 || a.mode != SPS_CONV_NBR || !a.map || !a.weight_kmajor || !a.tile_mask) return false;
+  if (a.io_dtype != SPS_IO_F16 || a.mode != SPS_CONV_NBR || (!a.map && !a.tile_slices) || !a.weight_kmajor || !a.tile_mask) return false;
+  if (a.tile_slices && !a.perm) return false;
   if (a.K < 1 || a.K > kMaxK) return false;
   if (a.cin < 8 || (a.cin & 7) || (a.in_ld & 7)) return false;
   if (a.in2 && ((a.cin2 & 7) || (a.in2_ld & 7))) return false;

@@ -161,9 +161,12 @@ class SPSModel(nn.Module):
         self.lanes = 3            # engine contexts / streams that forward_async alternates between
         self.output_channel, self.apply_sigmoid = 0, True   # models.py:28-29: sigmoid of the single output channel
         self.conv_backend = None  # None: the host default of sps_b200.engine.DEFAULTS at engine creation
-        # forward_async replays the whole forward (56 kernels) as ONE CUDA graph per (lane, input buffer, row count):
-        # the first call with a given input runs eagerly, the second is captured, later ones are replays
+        # forward_async replays the whole forward (~56 kernels) as ONE CUDA graph per (lane, input buffer, row count):
+        # the first call with a given input runs eagerly, the second is captured, later ones are replays.  Only for
+        # inputs of at most `graph_max_rows` rows, whose forward is bound by launch overhead; measured on the batch-8
+        # workload (2.47 M rows, GPU-bound) replay was 2 % SLOWER than enqueueing kernel by kernel.
         self.use_graphs = os.environ.get("SPS_NO_GRAPHS", "0") != "1"
+        self.graph_max_rows = 400_000
 
     def set_conv_backend(self, backend: int):
         """Arithmetic mode of every engine this model owns (0 auto, 1 exact fp32, 2 TF32 on fp32 rows, 3 fp16 rows)."""
@@ -283,7 +286,7 @@ class SPSModel(nn.Module):
     def _lane_forward(self, p, slot, lane_engine, net, src, d_out, compute):
         """One forward on a lane's stream (current), eagerly or as a CUDA-graph replay.  Every size that only exists on
         the device stays there, so the captured launch sequence is valid for any content of the same buffers."""
-        if not self.use_graphs:
+        if not self.use_graphs or src.shape[0] > self.graph_max_rows:
             lane_engine.forward(net, src, self.voxel_size, out=d_out)
             return
         graphs = p["graphs"][slot]

@@ -30,8 +30,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     from sps_b200 import _cabi
-    # sizes follow from the C declaration order (LP64): 7*8 and the conv argument block
-    assert C.sizeof(_cabi.LevelView) == 56
+    # sizes follow from the C declaration order (LP64): 10*8 and the conv argument block
+    assert C.sizeof(_cabi.LevelView) == 80
     a = _cabi.ConvArgs
     assert a.mode.offset == 0 and a.map.offset == 16 and a.n_out.offset == 32
     assert a.weight_kmajor.offset == a.head_out.offset + 8 and a.tile_slices.offset == a.perm.offset + 8

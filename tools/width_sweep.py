@@ -1,0 +1,201 @@
+"""BASELINE.json configs[4] (stress): 0.05 m voxels, a 524 288-point dense scan + a 30 m radius crop of the base map
+(~4 M active voxels): kernel-map build + sparse-convolution sweep across layer widths with a roofline report.
+
+One fused forward of the standard network builds the coordinate levels, kernel maps, shape-sorted processing order and
+tile slices of the stress input (timed per stage).  Then every BasicBlock / transposed / strided convolution SHAPE of
+CustomMinkUNet is run on those maps with PLANES (and INIT_DIM) multiplied by 1, 2, 4 and 8 -- Cin / Cout up to 768 / 512 --
+through the layer-level C-ABI call (sps_conv_fwd, fp16 rows, tcgen05), on random fp16 activations and weights; each launch
+is timed with CUDA events on its stream (inputs larger than L2 for the level 0-2 layers; the L2 is flushed between
+repetitions for all of them).  Reported per layer: time, useful TFLOP/s (2 * pairs * Cin * Cout) against the measured bf16
+tensor peak, minimum-bytes GB/s against the measured copy peak.
+
+    python bench.py --config 5 [--widths 1,2,4,8]        (prints one JSON line; writes profiles/r2_width_sweep.md)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+VOXEL5 = 0.05
+WORKLOAD5 = ("config5: 0.05 m voxels, 524288-point dense scan (128 x 4096) + 30 m radius submap crop; kernel-map build + "
+             "3x3x3x3 / 2x2x2 convolution sweep with PLANES x1, x2, x4, x8 on the stress maps")
+
+
+def stress_input():
+    import torch
+    from sps_b200 import synth
+    from sps_b200.engine import MapHash
+    world = synth.World(3)
+    scan = synth.scan(world, "dense-128x4096", pose=(2.0, -1.0, 0.4), seed=3)
+    base = synth.base_map(world, "os1-128", n_poses=12, seed=3, voxel=VOXEL5)
+    mh = MapHash(torch.as_tensor(base).cuda(), VOXEL5)
+    idx = mh.crop_radius((2.0, -1.0, 1.8), 30.0).cpu().numpy()
+    return np.ascontiguousarray(synth.assemble(scan, base[idx])[:, :5])
+
+
+def run(args):
+    import torch
+    import bench
+    from sps_b200 import _cabi, convops
+    from sps_b200.engine import Engine, Net, _stream
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    if int(os.environ.get("RANK", "0")) != 0:      # one workload, one GPU: extra ranks of a torchrun launch idle
+        return
+    lib = _cabi.load()
+    widths = [int(w) for w in args.widths.split(",")]
+    peaks = bench.load_peaks()
+    pts = torch.as_tensor(stress_input()).cuda()
+    n = len(pts)
+    sd = bench.random_state_dict()
+    net = Net(sd)
+    eng = Engine(n)
+    eng.set_conv_backend(args.backend)
+    eng.set_pattern_sort(2)
+    # ---- the standard network on the stress input: stage times of the map building, device-resident steps ----
+    for _ in range(3):
+        eng.forward(net, pts, VOXEL5)
+    eng.status()
+    sampler = bench.ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
+    steps = args.steps if getattr(args, "steps_given", True) else 5
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        eng.forward(net, pts, VOXEL5)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_fwd = e0.elapsed_time(e1) / steps
+    stage_ms = bench.profile_pass(eng, net, [pts], 3, voxel=VOXEL5)
+    eng.forward(net, pts, VOXEL5)            # leave the sorted maps of a fused forward in the context
+    torch.cuda.synchronize()
+    V = [eng.count(L) for L in range(5)]
+
+    def pairs(level):
+        out = C.c_int64()
+        lib.sps_ctx_pair_count(eng.handle, level, 3, C.byref(out), _stream())
+        return out.value
+    P3 = [pairs(L) for L in range(5)]
+    views = [eng.level(L) for L in range(5)]
+    flush = torch.empty(192 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+    # ---- the sweep ----
+    rows = []
+    rng = torch.Generator(device="cuda")
+    rng.manual_seed(0)
+    for m in widths:
+        planes = tuple(p * m for p in bench.PLANES)
+        for name, kind, cin, cout, L, cin2 in bench.conv_layers(planes, 8 * m):
+            if kind != "k3":
+                continue            # the sweep covers the 81-offset BasicBlock convolutions (95 % of the network's FLOPs)
+            v = views[L]
+            if not v.perm:
+                continue            # level 4 is not shape-sorted: physical order through the dense table is not kept by a fused forward
+            Vl, P = V[L], P3[L]
+            x = (torch.randn((Vl, cin), device="cuda", generator=rng) * 0.5).half()
+            w = torch.randn((81, cin, cout), device="cuda", generator=rng) * (1.0 / np.sqrt(20 * cin))
+            wt = convops.pack_kmajor_f16(w)
+            out = torch.empty((Vl, cout), dtype=torch.float16, device="cuda")
+            a = _cabi.ConvArgs()
+            a.mode, a.K, a.cin, a.cout = _cabi.SPS_CONV_NBR, 81, cin, cout
+            a.map, a.map_ld = v.nbr3, v.ld                       # NULL after a fused forward: the tile slices carry the map
+            a.n_out, a.n_out_max = v.count, Vl
+            a.in_, a.in_ld = x.data_ptr(), cin
+            a.weight = w.data_ptr()
+            a.relu = 1
+            a.out, a.out_ld = out.data_ptr(), cout
+            a.weight_kmajor, a.kmajor_ld = wt.data_ptr(), wt.stride(0)
+            a.tile_mask, a.perm, a.tile_slices = v.tile_mask, v.perm, v.tile_slices
+            a.io_dtype, a.backend = _cabi.SPS_IO_F16, _cabi.SPS_BACKEND_F16
+            reps = 5
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+            _cabi.check(lib.sps_conv_fwd(C.byref(a), _stream()), "sps_conv_fwd")      # warm-up
+            for s, e in ev:
+                flush.zero_()
+                s.record()
+                _cabi.check(lib.sps_conv_fwd(C.byref(a), _stream()), "sps_conv_fwd")
+                e.record()
+            torch.cuda.synchronize()
+            ms = float(np.median([s.elapsed_time(e) for s, e in ev]))
+            flops = 2.0 * P * cin * cout
+            nbytes = 2.0 * (Vl * cin + Vl * cout + 81 * cin * cout) + 4.0 * P
+            tf = flops / (ms * 1e-3) / 1e12
+            gbs = nbytes / (ms * 1e-3) / 1e9
+            rows.append({"width": m, "layer": name, "level": L, "voxels": Vl, "pairs": P, "cin": cin, "cout": cout,
+                         "ms": round(ms, 4), "TFLOP/s": round(tf, 2), "tensor_frac": round(tf / peaks["tensor"], 4),
+                         "tensor_frac_burst": round(tf / peaks["tensor_burst"], 4),
+                         "GB/s": round(gbs, 1), "hbm_frac": round(gbs / peaks["hbm"], 4)})
+            del x, w, wt, out
+    clocks = sampler.stop()
+    eng.status()
+    best = max(rows, key=lambda r: r["tensor_frac"]) if rows else None
+    per_width = {}
+    for r in rows:
+        d = per_width.setdefault(r["width"], {"ms": 0.0, "flops": 0.0})
+        d["ms"] += r["ms"]
+        d["flops"] += 2.0 * r["pairs"] * r["cin"] * r["cout"]
+    for m, d in per_width.items():
+        d["TFLOP/s"] = round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 2)
+        d["tensor_frac"] = round(d["TFLOP/s"] / peaks["tensor"], 4)
+        d["ms"] = round(d["ms"], 3)
+        d.pop("flops")
+    maps_ms = sum(t for k, t in stage_ms.items()
+                  if k.split(".")[0] in ("vox", "stride") or k in ("blocks", "conv0+kmap5", "kmap3", "sort", "slices"))
+    table = os.path.join(ROOT, "profiles", "r2_width_sweep.md")
+    with open(table, "w") as f:
+        f.write(f"# Width sweep on the stress shape ({WORKLOAD5})\n\n"
+                f"`python bench.py --config 5` on one B200: {n} input rows, voxels per level {V}, 3x3x3x3 pairs per level {P3}.\n"
+                f"Standard network (x1) on this input: {ms_fwd:.2f} ms per forward, single stream; map building "
+                f"{maps_ms:.2f} ms of it.\n"
+                f"Peaks (MEASURED_PEAKS.json): bf16 {peaks['tensor']} TFLOP/s sustained / {peaks['tensor_burst']} burst, copy {peaks['hbm']} GB/s.\n"
+                "Times: median of 5 launches, CUDA events on the launch stream, L2 flushed before each.  FLOPs = 2 x pairs x Cin x Cout "
+                "(padding and absent-neighbour MMA work does not count); bytes = activations in + out + weights + 4 per pair.\n\n"
+                "| width | layer | level | voxels | Cin | Cout | ms | useful TFLOP/s | of sustained bf16 | GB/s (min bytes) | of copy peak |\n"
+                "|---:|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|\n")
+        for r in rows:
+            f.write(f"| x{r['width']} | {r['layer']} | {r['level']} | {r['voxels']} | {r['cin']} | {r['cout']} | {r['ms']:.3f} | "
+                    f"{r['TFLOP/s']:.1f} | {100 * r['tensor_frac']:.1f} % | {r['GB/s']:.0f} | {100 * r['hbm_frac']:.1f} % |\n")
+        f.write("\n| width | all sixteen 3x3x3x3 layers of levels 0-3, ms | useful TFLOP/s | of sustained bf16 |\n|---:|---:|---:|---:|\n")
+        for m, d in per_width.items():
+            f.write(f"| x{m} | {d['ms']} | {d['TFLOP/s']} | {100 * d['tensor_frac']:.1f} % |\n")
+    scratch = os.path.join(ROOT, "gpurun_out")          # the GPU box only brings gpurun_out/ back
+    if os.path.isdir(scratch):
+        import shutil
+        shutil.copy(table, os.path.join(scratch, "r2_width_sweep.md"))
+    result = {
+        "metric": "scans/s", "value": 1e3 / ms_fwd, "unit": "scans/s", "n_gpus": 1, "steps": steps, "warmup": 3,
+        "ms_per_step": ms_fwd, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": bench.DTYPE[args.backend], "data": "synthetic",
+        "config": {"workload": WORKLOAD5, "rows": n, "voxels_per_level": V, "pairs3": P3, "widths": widths,
+                   "l2": "flushed (192 MB memset) before every timed layer launch", "table": "profiles/r2_width_sweep.md"},
+        "mpoints_per_s": 524288 / ms_fwd / 1e3,
+        "e2e": {"value": 1e3 / ms_fwd, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "note": "layer sweep on device-resident tensors; the end-to-end number of the path is config 2's"},
+        "gpu_launches": eng.launch_count() * steps + 6 * len(rows), "clocks": clocks,
+        "stages_x1": {k: round(v, 4) for k, v in stage_ms.items()},
+        "per_width": per_width, "layers": rows,
+    }
+    if best:
+        result["roofline"] = {"kernel": f"k_conv_umma, {best['layer']} at width x{best['width']} ({best['cin']}->{best['cout']})",
+                              "bound": "tensor", "achieved": best["TFLOP/s"], "peak": peaks["tensor"], "unit": "TFLOP/s",
+                              "frac": best["tensor_frac"], "traffic": None, "peak_source": peaks["src"]}
+    print(json.dumps(result))
+
+
+if __name__ == "__main__":
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--widths", default="1,2,4,8")
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--backend", type=int, default=0)
+    run(ap.parse_args())
