@@ -244,6 +244,25 @@ int sps_infer_scan(sps_ctx* ctx, const sps_net* net, const sps_map* map, const f
                    int64_t n_scan, float voxel_size, float* d_scores, void* d_scratch,
                    size_t scratch_bytes, int32_t* d_counts, void* stream);
 
+/* ---------------------------------------------------------------- ROS-path scan I/O --- */
+/* util.to_numpy (src/sps/datasets/util.py:146-153): the payload of a sensor_msgs/PointCloud2 -> fp32 [height*width,
+ * nfields], every field cast to float32, fields in message order.  d_data: the message's `data` bytes on the device;
+ * h_offsets / h_datatypes: PointField.offset / PointField.datatype (1 INT8 ... 7 FLOAT32, 8 FLOAT64) of each field. */
+int sps_pointcloud2_unpack(const void* d_data, int64_t width, int64_t height, int64_t point_step, int64_t row_step,
+                           int nfields, const int32_t* h_offsets, const int32_t* h_datatypes, int is_bigendian,
+                           float* d_out, void* stream);
+/* util.transform_point_cloud (util.py:187-194) as sps_node.py:103-107 uses it: fp32 points promoted to float64,
+ * homogeneous product with the row-major 4x4 float64 matrix (host pointer), division by the homogeneous coordinate,
+ * result rounded to fp32.  d_xyz: fp32 [n, ld>=3]; d_out: fp32 [n,3]. */
+int sps_transform_points(const float* d_xyz, int64_t ld, int64_t n, const double* h_matrix, float* d_out, void* stream);
+/* sps_node.py:148-149 + util.to_rosmsg (util.py:117-143): the scan rows (sensor frame x, y, z, intensity = columns
+ * 0..3 of d_scan, fp32 [n, ld>=4]) whose score is <= eps, in scan order, as the PointCloud2 payload the node publishes
+ * (point_step 16, fields x/y/z/intensity FLOAT32): d_out fp32 [n,4] (16-byte aligned), d_count[0] = rows kept.
+ * d_scratch: sps_pointcloud2_pack_scratch_bytes(n) bytes, 256-byte aligned. */
+size_t sps_pointcloud2_pack_scratch_bytes(int64_t n);
+int sps_pointcloud2_pack(const float* d_scan, int64_t ld, int64_t n, const float* d_scores, float eps, float* d_out,
+                         int32_t* d_count, void* d_scratch, size_t scratch_bytes, void* stream);
+
 /* ---------------------------------------------------------------- offline-loader submap --- */
 /* BLTDataset.select_closest_points (src/sps/datasets/blt_dataset.py:222-226,258-271):
  *     kd_tree_scan.query_ball_tree(kd_tree_target, VOXEL_SIZE) -> np.concatenate(lists)
@@ -338,6 +357,10 @@ int sps_confusion_counts(const float* d_scores, const float* d_rows, int64_t ld_
  * d_count [>= n] scratch. */
 int sps_voxel_mean(sps_ctx* ctx, const float* d_feat, int64_t ld, int channels, float* d_out,
                    float* d_count, void* stream);
+/* The same without the division: per-voxel SUM of the point features and the member count (d_count).  This is the
+ * feature rule of ME.MinkowskiUnion (coincident coordinates add, src/sps/datasets/util.py:98-99). */
+int sps_voxel_sum(sps_ctx* ctx, const float* d_feat, int64_t ld, int channels, float* d_out,
+                  float* d_count, void* stream);
 /* SparseTensor.slice(tensor_field) (models.py:28): out[p, :] = F[inv[p], :]. */
 int sps_gather_rows(const float* d_f, int64_t ld, int channels, const int32_t* d_inv, int64_t n,
                     float* d_out, void* stream);

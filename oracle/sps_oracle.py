@@ -513,3 +513,38 @@ def mapmos_forward(coordinates, indices, voxel_size, sd, dtype=np.float32):
     np.add.at(cnt, inv, 1.0)
     feat0 = (s / cnt).astype(dtype)[:, None]
     return unet_forward(Levels(c0), feat0, sd, dtype)[inv, 0].astype(dtype)
+
+
+# --------------------------------------------------------------------------------------
+# f3  ROS-path scan I/O   (src/sps/datasets/util.py:117-153,187-194; sps_node.py:89-107,146-149)
+# --------------------------------------------------------------------------------------
+_PF_NUMPY = {1: "i1", 2: "u1", 3: "i2", 4: "u2", 5: "i4", 6: "u4", 7: "f4", 8: "f8"}   # sensor_msgs/PointField datatypes
+
+
+def pointcloud2_to_array(data: bytes, width, height, point_step, row_step, fields, is_bigendian=False):
+    """util.to_numpy (util.py:146-153) without ros_numpy: ``fields`` = [(name, offset, datatype)]; every field is
+    read through a numpy structured dtype (what ros_numpy.numpify builds) and assigned into a float32 column."""
+    order = ">" if is_bigendian else "<"
+    dt = np.dtype({"names": [f[0] for f in fields], "formats": [order + _PF_NUMPY[f[2]] for f in fields],
+                   "offsets": [f[1] for f in fields], "itemsize": point_step})
+    buf = np.frombuffer(data, dtype=np.uint8)
+    rows = [np.frombuffer(buf[r * row_step: r * row_step + width * point_step].tobytes(), dtype=dt) for r in range(height)]
+    pc = np.concatenate(rows) if rows else np.zeros(0, dt)
+    scan = np.zeros((height * width, len(fields)), dtype=np.float32)
+    for i, f in enumerate(fields):
+        scan[:, i] = np.resize(pc[f[0]], height * width)
+    return scan
+
+
+def transform_point_cloud(point_cloud, transformation_matrix):
+    """util.py:187-194 verbatim semantics (float64 homogeneous product), followed by the float32 cast of its only
+    caller (sps_node.py:106 ``torch.tensor(scan_tr[:, :3], dtype=torch.float32)``)."""
+    pc = np.asarray(point_cloud)
+    homogeneous = np.hstack((pc, np.ones((pc.shape[0], 1))))
+    transformed = np.dot(homogeneous, np.asarray(transformation_matrix).T)
+    return (transformed[:, :3] / transformed[:, 3][:, np.newaxis]).astype(np.float32)
+
+
+def filter_scan(scan, scores, epsilon):
+    """sps_node.py:148: rows of the raw scan whose predicted score is <= epsilon."""
+    return np.asarray(scan)[np.asarray(scores) <= epsilon]

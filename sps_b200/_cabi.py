@@ -30,7 +30,8 @@ SYMBOLS = [
     "sps_map_bytes", "sps_map_build", "sps_map_destroy", "sps_submap_crop_voxel", "sps_submap_crop_radius",
     "sps_assemble", "sps_memcpy_d2h", "sps_memcpy_h2d", "sps_infer_scan", "sps_infer_scan_scratch_bytes", "sps_conv_kmajor_ld", "sps_conv_pack_kmajor", "sps_conv_kmajor_ld_f16", "sps_conv_pack_kmajor_f16", "sps_conv_kmajor_ld_f16x", "sps_conv_pack_kmajor_f16x", "sps_kernel_map_tile_masks", "sps_tma_weights_available", "sps_ctx_set_pattern_sort",
     "sps_ctx_set_conv_backend", "sps_profile_enable", "sps_profile_read", "sps_ctx_pair_count",
-    "sps_confusion_counts", "sps_voxel_mean", "sps_gather_rows", "sps_affine_relu",
+    "sps_confusion_counts", "sps_voxel_mean", "sps_voxel_sum", "sps_gather_rows", "sps_affine_relu",
+    "sps_pointcloud2_unpack", "sps_transform_points", "sps_pointcloud2_pack_scratch_bytes", "sps_pointcloud2_pack",
     "sps_ballmap_bytes", "sps_ballmap_build", "sps_ballmap_destroy", "sps_ball_query_scratch_bytes", "sps_submap_ball_query",
 ]
 
@@ -120,8 +121,13 @@ def load() -> C.CDLL:
         "sps_ctx_set_conv_backend": (i32, [vp, i32]),
         "sps_confusion_counts": (i32, [vp, vp, i64, i64, f32, f32, vp, vp, vp]),
         "sps_voxel_mean": (i32, [vp, vp, i64, i32, vp, vp, vp]),
+        "sps_voxel_sum": (i32, [vp, vp, i64, i32, vp, vp, vp]),
         "sps_gather_rows": (i32, [vp, i64, i32, vp, i64, vp, vp]),
         "sps_affine_relu": (i32, [vp, i64, i32, i64, vp, vp, i32, vp, i64, vp]),
+        "sps_pointcloud2_unpack": (i32, [vp, i64, i64, i64, i64, i32, vp, vp, i32, vp, vp]),
+        "sps_transform_points": (i32, [vp, i64, i64, vp, vp, vp]),
+        "sps_pointcloud2_pack_scratch_bytes": (sz, [i64]),
+        "sps_pointcloud2_pack": (i32, [vp, i64, i64, vp, f32, vp, vp, vp, sz, vp]),
         "sps_ballmap_bytes": (sz, [i64]),
         "sps_ballmap_build": (i32, [C.POINTER(vp), vp, sz, vp, i64, C.c_double, vp]),
         "sps_ballmap_destroy": (i32, [vp]),

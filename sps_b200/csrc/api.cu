@@ -393,6 +393,19 @@ extern "C" int sps_voxel_mean(sps_ctx* ctx, const float* d_feat, int64_t ld, int
   return SPS_OK;
 }
 
+extern "C" int sps_voxel_sum(sps_ctx* ctx, const float* d_feat, int64_t ld, int channels, float* d_out, float* d_count,
+                             void* stream) {
+  if (!ctx || !d_feat || !d_out || !d_count || channels < 1 || ld < channels) return SPS_ERR_BAD_ARG;
+  if (!ctx->have_l0) return SPS_ERR_STATE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = ctx->n;
+  SPS_CUDA_CHECK(cudaMemsetAsync(d_out, 0, (size_t)n * channels * sizeof(float), st));   // V0 <= n rows
+  SPS_CUDA_CHECK(cudaMemsetAsync(d_count, 0, (size_t)n * sizeof(float), st));
+  if (n > 0) k_voxel_accumulate<<<ew_grid(n * channels), 256, 0, st>>>(d_feat, ld, channels, ctx->inv, n, d_out, d_count);
+  SPS_CUDA_CHECK(cudaGetLastError());
+  return SPS_OK;
+}
+
 extern "C" int sps_gather_rows(const float* d_f, int64_t ld, int channels, const int32_t* d_inv, int64_t n, float* d_out,
                                void* stream) {
   if (!d_f || !d_inv || !d_out || channels < 1 || n < 0) return SPS_ERR_BAD_ARG;

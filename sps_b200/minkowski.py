@@ -49,15 +49,65 @@ class CoordinateManager:
         self.counts = [self.engine.count(L) for L in range(5)]
 
 
+class _SetManager:
+    """Coordinate manager of SparseTensors built directly from integer coordinates (util.prune, util.py:86-95): the
+    tensors that share it live on one integer lattice; there are no strided levels or kernel maps behind it."""
+
+
+def _unique_rows(coords: torch.Tensor, feats: torch.Tensor, reduce: str):
+    """Unique integer rows in first-occurrence order through the voxel hash of the library (columns padded to the
+    5-column key (b, x, y, z, t)); features of coincident rows are summed (``sum``) or the first one is kept (``first``,
+    ME's default RANDOM_SUBSAMPLE picks an arbitrary member: the first is a deterministic choice)."""
+    n, d = coords.shape
+    if d > 3:
+        raise NotImplementedError("directly constructed SparseTensors take up to 3 coordinate columns (util.py:86-95)")
+    dev = coords.device
+    rows = torch.zeros((n, 5), dtype=torch.float32, device=dev)
+    rows[:, 1:1 + d] = coords.to(torch.float32)          # exact: |c| < 2^24
+    eng = Engine(max(n, 1), dev)
+    eng.voxelize(rows, 1.0)
+    eng.status()
+    v = eng.count(0)
+    uc = torch.as_tensor(eng.coords(0)[:, 1:1 + d], device=dev).to(coords.dtype)
+    c = feats.shape[1]
+    f = feats.contiguous().to(torch.float32)
+    if reduce == "sum":
+        out = torch.empty((max(n, 1), c), dtype=torch.float32, device=dev)
+        cnt = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(eng.lib.sps_voxel_sum(eng.handle, _ptr(f), f.stride(0), c, _ptr(out), _ptr(cnt), _stream()), "sps_voxel_sum")
+        uf = out[:v].clone()
+    else:
+        inv = torch.as_tensor(eng.inverse_map(), device=dev).long()
+        first = torch.full((v,), n, dtype=torch.long, device=dev)
+        first.scatter_reduce_(0, inv, torch.arange(n, device=dev), reduce="amin")
+        uf = f[first]
+    return uc, uf
+
+
 class SparseTensor:
     def __init__(self, features, coordinates=None, coordinate_manager=None, tensor_stride=1, level=0):
-        if coordinate_manager is None:
-            raise NotImplementedError("build SparseTensors through TensorField(...).sparse() (models.py:24-25); "
-                                      "for util.prune use sps_b200.util.prune")
-        self.F = features
-        self.coordinate_manager = coordinate_manager
         self.level = level
         self.tensor_stride = [2 ** level] * 3 + [1]
+        self._coords = None
+        if coordinates is not None:
+            # ME.SparseTensor(features=, coordinates=[, coordinate_manager=]) on integer coordinates (util.py:86-95):
+            # duplicates collapse to one row
+            if not coordinates.is_cuda:
+                raise RuntimeError("sps_b200 has no CPU path: SparseTensor needs CUDA tensors")
+            self._coords, self.F = _unique_rows(coordinates, features, "first")
+            self.coordinate_manager = coordinate_manager if coordinate_manager is not None else _SetManager()
+            return
+        if coordinate_manager is None:
+            raise NotImplementedError("a SparseTensor needs coordinates or the coordinate manager of TensorField(...).sparse()")
+        self.F = features
+        self.coordinate_manager = coordinate_manager
+
+    @classmethod
+    def _from_set(cls, coords, feats, manager):
+        t = cls.__new__(cls)
+        t.level, t.tensor_stride, t._coords, t.F, t.coordinate_manager = 0, [1, 1, 1, 1], coords, feats, manager
+        return t
 
     @property
     def features(self):
@@ -65,6 +115,8 @@ class SparseTensor:
 
     @property
     def C(self):
+        if self._coords is not None:
+            return self._coords
         return torch.as_tensor(self.coordinate_manager.engine.coords(self.level), device=self.F.device)
 
     coordinates = C
@@ -258,11 +310,29 @@ SparseTensor.__iadd__ = _add
 
 
 class MinkowskiUnion(nn.Module):
+    """ME.MinkowskiUnion (util.py:98-99): union of the coordinate sets of tensors that share a coordinate manager, the
+    features of coincident coordinates add.  Rows come in first-occurrence order over the arguments."""
+
     def forward(self, *args):
-        raise NotImplementedError("use sps_b200.util.prune (replicated map hash) instead of Union+Pruning (util.py:85-114)")
+        if len(args) < 2 or any(a._coords is None for a in args):
+            raise NotImplementedError("MinkowskiUnion takes SparseTensors built from integer coordinates (util.py:86-99)")
+        if any(a.coordinate_manager is not args[0].coordinate_manager for a in args):
+            raise RuntimeError("MinkowskiUnion: all inputs must share one coordinate manager")
+        coords = torch.cat([a._coords for a in args], dim=0)
+        feats = torch.cat([a.F for a in args], dim=0)
+        uc, uf = _unique_rows(coords, feats, "sum")
+        return SparseTensor._from_set(uc, uf, args[0].coordinate_manager)
 
 
-MinkowskiPruning = MinkowskiUnion
+class MinkowskiPruning(nn.Module):
+    """ME.MinkowskiPruning (util.py:105-106): keep the rows whose mask entry is true."""
+
+    def forward(self, x: SparseTensor, mask: torch.Tensor):
+        if x._coords is None:
+            raise NotImplementedError("MinkowskiPruning takes SparseTensors built from integer coordinates (util.py:86-106)")
+        mask = mask.to(device=x.F.device, dtype=torch.bool).reshape(-1)
+        assert mask.numel() == len(x)
+        return SparseTensor._from_set(x._coords[mask], x.F[mask], x.coordinate_manager)
 
 
 class _Utils(types.ModuleType):

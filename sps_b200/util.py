@@ -110,3 +110,150 @@ def calculate_metrics(true_labels, predicted_labels):
     accuracy = (tp + tn) / (tp + tn + fp + fn)
     dIoU = tp / (tp + fn + fp)
     return precision, recall, f1, accuracy, dIoU
+
+
+# --------------------------------------------------------------------------------------------------------------
+# ROS-path scan I/O on the device: the per-scan host work of sps_node.py:89-107,146-149.
+# Messages are duck-typed (sensor_msgs/PointCloud2 and nav_msgs/Odometry attribute names): rospy is not a dependency.
+# --------------------------------------------------------------------------------------------------------------
+_PF_SIZES = {1: 1, 2: 1, 3: 2, 4: 2, 5: 4, 6: 4, 7: 4, 8: 8}   # sensor_msgs/PointField datatypes -> bytes
+
+
+class PointField:
+    """sensor_msgs/PointField (name, offset, datatype, count)."""
+    INT8, UINT8, INT16, UINT16, INT32, UINT32, FLOAT32, FLOAT64 = range(1, 9)
+
+    def __init__(self, name, offset, datatype, count=1):
+        self.name, self.offset, self.datatype, self.count = name, offset, datatype, count
+
+
+class PointCloud2:
+    """The attributes of sensor_msgs/PointCloud2 that util.to_numpy / util.to_rosmsg touch (util.py:117-153)."""
+
+    def __init__(self):
+        self.header = None
+        self.height = self.width = 0
+        self.fields = []
+        self.is_bigendian = False
+        self.point_step = self.row_step = 0
+        self.data = b""
+        self.is_dense = True
+
+
+def pointcloud2_to_tensor(pointcloud_msg, device="cuda"):
+    """``util.to_numpy`` (util.py:146-153) with the result left on the device: fp32 ``[height*width, nfields]``, every
+    field cast to float32, fields in message order.  ``pointcloud_msg.data`` may be bytes / bytearray / numpy uint8 or
+    a uint8 tensor (already on the device: no copy)."""
+    import ctypes as C
+    from . import _cabi
+    from .engine import _ptr, _stream
+    lib = _cabi.load()
+    m = pointcloud_msg
+    fields = list(m.fields)
+    if any(getattr(f, "count", 1) != 1 for f in fields):
+        raise NotImplementedError("PointField.count != 1")
+    data = m.data
+    if not isinstance(data, torch.Tensor):
+        data = torch.frombuffer(bytearray(data), dtype=torch.uint8) if not isinstance(data, np.ndarray) else torch.as_tensor(data)
+    dev = torch.device(device)
+    with torch.cuda.device(dev):
+        data = data.to(device=dev, non_blocking=True)
+        n = int(m.height) * int(m.width)
+        out = torch.empty((n, len(fields)), dtype=torch.float32, device=dev)
+        offs = (C.c_int32 * len(fields))(*[int(f.offset) for f in fields])
+        dts = (C.c_int32 * len(fields))(*[int(f.datatype) for f in fields])
+        _cabi.check(lib.sps_pointcloud2_unpack(_ptr(data), int(m.width), int(m.height), int(m.point_step), int(m.row_step),
+                                               len(fields), offs, dts, int(bool(m.is_bigendian)), _ptr(out), _stream()),
+                    "sps_pointcloud2_unpack")
+    return out
+
+
+def to_numpy(pointcloud_msg):
+    """util.py:146-153, same return type as the reference (host fp32 array); the unpacking itself runs on the GPU."""
+    return pointcloud2_to_tensor(pointcloud_msg).cpu().numpy()
+
+
+def transform_point_cloud(point_cloud, transformation_matrix):
+    """util.py:187-194 on the device: CUDA fp32 ``[N, >=3]`` points x float64 4x4 matrix -> fp32 ``[N,3]`` (the reference
+    returns the float64 product and its caller casts it to float32, sps_node.py:106; the kernel does both)."""
+    import ctypes as C
+    from . import _cabi
+    from .engine import _ptr, _stream
+    pts = point_cloud if isinstance(point_cloud, torch.Tensor) else torch.as_tensor(np.asarray(point_cloud))
+    if not pts.is_cuda:
+        raise RuntimeError("transform_point_cloud needs a CUDA tensor: sps_b200 has no CPU path")
+    pts = pts.to(torch.float32)
+    if pts.stride(-1) != 1:
+        pts = pts.contiguous()
+    T = np.ascontiguousarray(np.asarray(transformation_matrix, dtype=np.float64).reshape(4, 4))
+    out = torch.empty((pts.shape[0], 3), dtype=torch.float32, device=pts.device)
+    with torch.cuda.device(pts.device):
+        _cabi.check(_cabi.load().sps_transform_points(_ptr(pts), pts.stride(0), pts.shape[0], T.ctypes.data_as(C.c_void_p), _ptr(out),
+                                                      _stream()), "sps_transform_points")
+    return out
+
+
+def inverse_transform_point_cloud(transformed_point_cloud, transformation_matrix):
+    """util.py:197-206."""
+    return transform_point_cloud(transformed_point_cloud, np.linalg.inv(np.asarray(transformation_matrix, dtype=np.float64)))
+
+
+def quaternion_matrix(quaternion):
+    """tf.transformations.quaternion_matrix for a (x, y, z, w) quaternion: homogeneous 4x4 rotation (float64)."""
+    q = np.array(quaternion[:4], dtype=np.float64, copy=True)
+    nq = np.dot(q, q)
+    if nq < np.finfo(float).eps * 4.0:
+        return np.identity(4)
+    q *= np.sqrt(2.0 / nq)
+    q = np.outer(q, q)
+    return np.array(((1.0 - q[1, 1] - q[2, 2], q[0, 1] - q[2, 3], q[0, 2] + q[1, 3], 0.0),
+                     (q[0, 1] + q[2, 3], 1.0 - q[0, 0] - q[2, 2], q[1, 2] - q[0, 3], 0.0),
+                     (q[0, 2] - q[1, 3], q[1, 2] + q[0, 3], 1.0 - q[0, 0] - q[1, 1], 0.0),
+                     (0.0, 0.0, 0.0, 1.0)), dtype=np.float64)
+
+
+def to_tr_matrix(odom_msg):
+    """util.py:209-232: translation x rotation of a nav_msgs/Odometry pose (host scalar arithmetic, one 4x4 per scan)."""
+    p, o = odom_msg.pose.pose.position, odom_msg.pose.pose.orientation
+    translation = np.array([[1, 0, 0, p.x], [0, 1, 0, p.y], [0, 0, 1, p.z], [0, 0, 0, 1]], dtype=np.float64)
+    return np.dot(translation, quaternion_matrix([o.x, o.y, o.z, o.w]))
+
+
+def filter_scan(scan, scores, epsilon):
+    """sps_node.py:148: ``scan[scores <= epsilon]`` on the device -- the rows (sensor-frame x, y, z, intensity) of the
+    published cloud, in scan order.  Returns (fp32 ``[n,4]`` buffer, device int32 count): no host synchronisation."""
+    from . import _cabi
+    from .engine import _ptr, _stream
+    lib = _cabi.load()
+    assert scan.is_cuda and scan.dtype == torch.float32 and scan.shape[1] >= 4 and scan.stride(1) == 1
+    n = scan.shape[0]
+    scores = scores.reshape(-1).to(torch.float32).contiguous()
+    assert scores.numel() == n
+    with torch.cuda.device(scan.device):
+        nbytes = lib.sps_pointcloud2_pack_scratch_bytes(n)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=scan.device)
+        out = torch.empty((max(n, 1), 4), dtype=torch.float32, device=scan.device)
+        count = torch.zeros(1, dtype=torch.int32, device=scan.device)
+        _cabi.check(lib.sps_pointcloud2_pack(_ptr(scan), scan.stride(0), n, _ptr(scores), float(epsilon), _ptr(out), _ptr(count),
+                                             _ptr(scratch), nbytes, _stream()), "sps_pointcloud2_pack")
+    return out, count
+
+
+def to_rosmsg(data, header, frame_id=None):
+    """util.py:117-143: x, y, z, intensity FLOAT32, point_step 16.  ``data``: fp32 ``[M,4]`` (tensor or array)."""
+    cloud = PointCloud2()
+    cloud.header = header
+    if frame_id and header is not None:
+        cloud.header.frame_id = frame_id
+    cloud.fields = [PointField("x", 0, PointField.FLOAT32, 1), PointField("y", 4, PointField.FLOAT32, 1),
+                    PointField("z", 8, PointField.FLOAT32, 1), PointField("intensity", 12, PointField.FLOAT32, 1)]
+    arr = data.detach().cpu().numpy() if isinstance(data, torch.Tensor) else np.asarray(data)
+    arr = np.array(arr, dtype=np.float32)
+    cloud.is_bigendian = False
+    cloud.point_step = 16
+    cloud.row_step = cloud.point_step * len(arr)
+    cloud.is_dense = True
+    cloud.width = len(arr)
+    cloud.height = 1
+    cloud.data = arr.tobytes()
+    return cloud

@@ -135,3 +135,48 @@ def test_layer_by_layer_shim_matches_fused_forward_and_oracle():
     mean = np.zeros(len(c0)); cnt = np.zeros(len(c0))
     np.add.at(mean, inv, f2.cpu().numpy()[:, 0]); np.add.at(cnt, inv, 1)
     assert np.abs(st.F.cpu().numpy()[:, 0] - mean / cnt).max() < 1e-5
+
+
+@pytest.mark.gpu
+def test_reference_prune_call_sequence_through_the_shim():
+    """The body of the reference's util.prune (src/sps/datasets/util.py:85-114: SparseTensor x2 on one coordinate
+    manager, MinkowskiUnion, mask on the one-hot feature product, MinkowskiPruning, coordinates * ds) runs against the
+    shim as written, and agrees with the library's own prune (replicated map hash) and with the oracle."""
+    import sps_b200.minkowski as ME
+    from oracle import sps_oracle as O
+    from sps_b200 import util, synth
+    world = synth.World(2)
+    base = synth.base_map(world, "tiny", n_poses=6, seed=2)
+    scan = synth.scan(world, "tiny", (0.5, -1.0, 0.7), seed=9)
+    scan[:50] *= -1.0                                          # negative coordinates: truncation, not floor (util.py:75)
+    ds = 0.1
+    map_cf = util.to_coords_features(torch.as_tensor(base).cuda(), "map", ds)
+    scan_cf = util.to_coords_features(torch.as_tensor(scan).cuda(), "scan", ds)
+
+    def reference_prune(map_coords_feat, scan_coords_feat, ds):
+        map_sparse = ME.SparseTensor(features=map_coords_feat.features, coordinates=map_coords_feat.cloud_coords)
+        scan_sparse = ME.SparseTensor(features=scan_coords_feat.features, coordinates=scan_coords_feat.cloud_coords,
+                                      coordinate_manager=map_sparse.coordinate_manager)
+        union = ME.MinkowskiUnion()
+        output = union(scan_sparse, map_sparse)
+        mask = (output.F[:, 0] * output.F[:, 1]) == 1
+        pruning = ME.MinkowskiPruning()
+        output = pruning(output, mask)
+        submap_points = output.coordinates
+        submap_points = submap_points * ds
+        return submap_points, len(scan_sparse)
+
+    got, n_scan = reference_prune(map_cf, scan_cf, ds)
+    lib_pts, lib_n = util.prune(map_cf, scan_cf, ds)
+    ora_pts, ora_n = O.prune(base, scan, ds)
+    assert n_scan == lib_n == ora_n
+    assert got.dtype == torch.float32
+    assert np.array_equal(O.canonical(got.cpu().numpy()), O.canonical(ora_pts))
+    assert np.array_equal(O.canonical(lib_pts.cpu().numpy()), O.canonical(ora_pts))
+    # union semantics on their own: coincident coordinates add their features, rows in first-occurrence order
+    a = ME.SparseTensor(features=torch.tensor([[1., 0.], [1., 0.], [1., 0.]]).cuda(), coordinates=torch.tensor([[1, 2, 3], [1, 2, 3], [4, 5, 6]]).int().cuda())
+    b = ME.SparseTensor(features=torch.tensor([[0., 1.], [0., 1.]]).cuda(), coordinates=torch.tensor([[4, 5, 6], [7, 8, -9]]).int().cuda(),
+                        coordinate_manager=a.coordinate_manager)
+    assert len(a) == 2 and len(b) == 2
+    u = ME.MinkowskiUnion()(a, b)
+    assert u.C.cpu().tolist() == [[1, 2, 3], [4, 5, 6], [7, 8, -9]] and u.F.cpu().tolist() == [[1., 0.], [1., 1.], [0., 1.]]
