@@ -153,6 +153,8 @@ def pointcloud2_to_tensor(pointcloud_msg, device="cuda"):
     if any(getattr(f, "count", 1) != 1 for f in fields):
         raise NotImplementedError("PointField.count != 1")
     data = m.data
+    if int(m.height) * int(m.width) == 0:
+        return torch.empty((0, len(fields)), dtype=torch.float32, device=device)
     if not isinstance(data, torch.Tensor):
         data = torch.frombuffer(bytearray(data), dtype=torch.uint8) if not isinstance(data, np.ndarray) else torch.as_tensor(data)
     dev = torch.device(device)
@@ -225,7 +227,7 @@ def filter_scan(scan, scores, epsilon):
     from . import _cabi
     from .engine import _ptr, _stream
     lib = _cabi.load()
-    assert scan.is_cuda and scan.dtype == torch.float32 and scan.shape[1] >= 4 and scan.stride(1) == 1
+    assert scan.is_cuda and scan.dtype == torch.float32 and scan.shape[1] >= 4 and (scan.stride(1) == 1 or scan.shape[0] == 0)
     n = scan.shape[0]
     scores = scores.reshape(-1).to(torch.float32).contiguous()
     assert scores.numel() == n

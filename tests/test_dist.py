@@ -84,3 +84,72 @@ def test_single_process_path_matches():
     res = ShardedPredictor(fake_scores, EPS, partials_fn=cpu_partials).predict(scans)
     assert len(res["scores"]) == 3 and res["counts"].shape == (3, 4)
     assert int(res["counts"].sum()) == sum(int((s[:, 4] == 1).sum()) for s in scans)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The same plumbing under NCCL with the real network and the library's metric kernel (BASELINE.json configs[3]).
+# Needs two GPUs (NCCL refuses two ranks on one device): skipped on a single-GPU box, run with `gpurun --gpus 2`.
+# ---------------------------------------------------------------------------------------------------------------
+import pytest
+
+
+def _nccl_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from conftest import make_case
+    from sps_b200.models import SPSNet
+    from sps_b200.parallel import ShardedPredictor
+    sd = O.make_state_dict(seed=0, randomize_bn=True)
+    sd["final.kernel"] = sd["final.kernel"] * np.float32(8.0)      # scores on both sides of eps
+    cfg = {"MODEL": {"VOXEL_SIZE": 0.1}, "FILTER": {"THRESHOLD": EPS}}
+    net = SPSNet(cfg)
+    net.model.MinkUNet.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()})
+    net = net.cuda()
+    net.freeze()
+    scans = [torch.as_tensor(make_case("tiny", seed=40 + i)).cuda() for i in range(5)]
+    res = ShardedPredictor(lambda rows: net(rows), EPS).predict(scans)
+    net.model.check()
+    if rank == 0:
+        out["metrics"] = res["metrics"]
+        out["scores"] = [s.cpu().numpy().copy() for s in res["scores"]]
+        out["counts"] = res["counts"].numpy().copy()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_sharded_predict_world2_nccl_real_network():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (NCCL: one rank per device)")
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from conftest import make_case
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_nccl_worker, args=(2, port, out), nprocs=2, join=True)
+    sd = O.make_state_dict(seed=0, randomize_bn=True)
+    sd["final.kernel"] = sd["final.kernel"] * np.float32(8.0)
+    exp = {k: [] for k in ("loss", "r2", "precision", "recall", "f1", "dIoU")}
+    for i in range(5):
+        rows = make_case("tiny", seed=40 + i)
+        ref = O.sps_forward(rows[:, :5], 0.1, sd)
+        scan = rows[:, 4] == 1
+        assert np.abs(out["scores"][i] - ref[scan]).max() < 2e-3       # gathered in scan-id order from both ranks
+        m = O.predict_step_metrics(_scores_full(out["scores"][i], scan, ref), rows[:, 5], rows[:, 4], EPS)
+        for k in exp:
+            exp[k].append(m[k])
+    got = out["metrics"]
+    for a, b in (("Loss", "loss"), ("R2", "r2"), ("Precision", "precision"), ("Recall", "recall"), ("F1", "f1"), ("dIoU", "dIoU")):
+        assert abs(got[a] - np.mean(exp[b])) < 1e-5, (a, got[a], np.mean(exp[b]))
+    assert out["counts"].sum() == sum(int((make_case("tiny", seed=40 + i)[:, 4] == 1).sum()) for i in range(5))
+
+
+def _scores_full(scan_scores, scan_mask, ref):
+    """Per-row score vector with the GPU's scan-row scores in place (the metrics only read the scan rows)."""
+    full = ref.copy()
+    full[scan_mask] = scan_scores
+    return full

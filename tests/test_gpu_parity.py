@@ -339,3 +339,44 @@ def test_forward_async_graph_replay_equals_eager(engine_mod, state_dict):
         if buf.is_cuda:
             torch.cuda.synchronize()
         assert np.array_equal(model.forward_async(buf).result().cpu().numpy(), eager["b"])
+
+
+def test_two_host_threads_two_contexts(engine_mod, state_dict):
+    """The library keeps no process-wide mutable state (include/sps_b200.h): two host threads drive two contexts on two
+    streams at once, in DIFFERENT arithmetic modes, and each gets exactly what it gets alone."""
+    import threading
+    rows = [make_case("tiny", seed=31, batch=2)[:, :5], make_case("hdl-32", seed=32)[:, :5]]
+    backends = [1, 0]
+    net = engine_mod.Net(state_dict)
+    alone = []
+    for r, b in zip(rows, backends):
+        eng = engine_mod.Engine(len(r))
+        eng.set_conv_backend(b)
+        alone.append(eng.forward(net, dev(r), 0.1).cpu().numpy())
+        eng.status()
+    results, errors = [None, None], []
+
+    def work(i):
+        try:
+            eng = engine_mod.Engine(len(rows[i]))
+            eng.set_conv_backend(backends[i])
+            eng.profile(i == 0)                               # per-context stage timers too
+            stream = torch.cuda.Stream()
+            d = dev(rows[i])
+            torch.cuda.current_stream().synchronize()
+            with torch.cuda.stream(stream):
+                for _ in range(10):
+                    out = eng.forward(net, d, 0.1)
+                stream.synchronize()
+            eng.status()
+            results[i] = out.cpu().numpy()
+        except Exception as e:   # noqa: BLE001
+            errors.append(e)
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for i in range(2):
+        assert np.array_equal(results[i], alone[i])
