@@ -231,6 +231,8 @@ def filter_scan(scan, scores, epsilon):
     n = scan.shape[0]
     scores = scores.reshape(-1).to(torch.float32).contiguous()
     assert scores.numel() == n
+    if n == 0:
+        return torch.empty((0, 4), dtype=torch.float32, device=scan.device), torch.zeros(1, dtype=torch.int32, device=scan.device)
     with torch.cuda.device(scan.device):
         nbytes = lib.sps_pointcloud2_pack_scratch_bytes(n)
         scratch = torch.empty(nbytes, dtype=torch.uint8, device=scan.device)
