@@ -50,7 +50,7 @@ static size_t carve(sps_ctx* c, void* base, int64_t max_points) {
   c->inv = cv.take<int32_t>(N);
   for (int L = 0; L < SPS_NUM_LEVELS; ++L) {
     c->keys[L] = cv.take<unsigned long long>(N);
-    c->nbr3[L] = cv.take<int32_t>((size_t)96 * ld);
+    c->nbr3[L] = cv.take<int32_t>((size_t)81 * ld);
     c->tmask3[L] = cv.take<uint32_t>((size_t)(ld / 128 + 1) * 4);
     c->ptmask[L] = cv.take<uint32_t>((size_t)(ld / 128 + 1) * 4);
     c->perm[L] = cv.take<int32_t>(N);

@@ -13,7 +13,6 @@ struct sps_ctx {
   int64_t n = 0;             // rows of the last voxelize call
   bool have_l0 = false, have_maps = false, have_nbr5 = false, have_perm = false, have_slices = false;
   bool dense_maps = true;    // false after a fused forward that stored only the present entries of the sorted levels' tables
-  int packed_mask = 0;       // bit L: nbr3[L] holds the front-packed present-only form [voxel][3][32] (fused forward, sorted level)
   int first_sorted = 0, last_sorted = -1;   // levels whose 3^4 convs may visit rows in pattern-sorted order
 
   // ---- settings (sps_ctx_set_conv_backend / sps_ctx_set_pattern_sort) and per-forward state ----
@@ -65,7 +64,7 @@ struct sps_ctx {
   uint32_t* sort_hist = nullptr;
   uint32_t* sort_status = nullptr;
   uint32_t* tmask8 = nullptr;                  // [tiles][4] all-eight-offsets mask for the 2x2x2x1 maps
-  int32_t* nbr3[SPS_NUM_LEVELS] = {};          // [81][ld] (96 * ld ints allocated: the packed form takes [ld][3][32])
+  int32_t* nbr3[SPS_NUM_LEVELS] = {};          // [81][ld]
   int32_t* nbr5 = nullptr;                     // [125][ld]
   uint32_t* tmask3[SPS_NUM_LEVELS] = {};       // [L] [tiles][4] present-offset masks of nbr3 per 128-row tile
 

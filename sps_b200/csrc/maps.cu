@@ -333,9 +333,8 @@ k_kernel_map_blk(const unsigned long long* __restrict__ keys, const int32_t* __r
 // block id + occupancy word in shared memory, then answers the 27 lookups with a bit test and, for present
 // neighbours only, one 4-byte read.  (The generic kernel above re-probes whenever the block changes along
 // x: ~13 probes per thread; this was the dominant kernel after the convolutions were sped up.)
-constexpr int kPackedPlane = 32;           // ints per (voxel, time plane) of a packed (present-only) neighbour table: one 128-byte line
 struct KmapOut {
-  int32_t* nbr[SPS_NUM_LEVELS];           // [81][ld] per level (dense), or [voxel][3][32] front-packed present entries
+  int32_t* nbr[SPS_NUM_LEVELS];           // [81][ld] per level
   uint32_t* tile_masks[SPS_NUM_LEVELS];   // physical-order tile masks, or nullptr (shape-sorted level of the fused forward)
   uint32_t* vmask[SPS_NUM_LEVELS];        // [3][ld] per-voxel 27-bit presence words per time plane
   int64_t ld;
@@ -370,7 +369,6 @@ k_kernel_map_blk3(const LevelTabs T, const KmapOut O) {
     const int t2 = (int)(key & ((1u << kTBits) - 1)) + it - KT / 2;
     const bool pok = live && (unsigned)t2 < (1u << kTBits);
     int32_t* out = nbr + (int64_t)it * 27 * ld + o;
-    int32_t* packed = nbr + ((int64_t)o * 3 + it) * kPackedPlane;      // dense == 0 only
     const int cx = (int)((key >> kXShift) & ((1u << kXBits) - 1)) >> L;
     const int cy = (int)((key >> kYShift) & ((1u << kYBits) - 1)) >> L;
     const int cz = (int)((key >> kZShift) & ((1u << kZBits) - 1)) >> L;
@@ -413,13 +411,9 @@ k_kernel_map_blk3(const LevelTabs T, const KmapOut O) {
           int res = -1;
           if ((sOcc[j][tid] >> l) & 1ull) res = __ldg(cells + (int64_t)sId[j][tid] * 64 + l);
           const int k3 = (dx + 1) + 3 * ((dy + 1) + 3 * (dz + 1));
-          // dense = 0 (shape-sorted level of the fused forward: the only reader is the tile-slice pass, which goes
-          // through the presence words): only PRESENT entries are stored (87 % of the table is -1), packed at the front
-          // of the voxel's own 128-byte line per time plane -- packed[(o * 3 + it) * 32 + j] = row of the j-th present
-          // neighbour.  The slice pass reads whole lines of the voxels it visits instead of one 4-byte entry out of
-          // a 32-byte sector per (voxel, offset): 840 MB -> ~250 MB of DRAM reads on the bench workload.
-          if (dense) { if (live) out[(int64_t)k3 * ld] = res; }
-          else if (res >= 0) packed[__popc(present)] = res;
+          // dense = 0: only present entries are stored (87 % of the table is -1); allowed when every reader of this
+          // level's table goes through the presence words `vmask` (the tile slices of a shape-sorted level)
+          if (live && (dense || res >= 0)) out[(int64_t)k3 * ld] = res;
           if (res >= 0) present |= 1u << k3;
           if (tm) {
             const int k = it * 27 + k3;
@@ -598,7 +592,6 @@ struct SliceArgs {
   const int32_t* counts;
   int64_t ld;
   int first;
-  int packed_mask;     // bit L: nbr[L] is the front-packed present-only table of k_kernel_map_blk3
 };
 __global__ void __launch_bounds__(128)
 k_tile_masks_perm(const SliceArgs A) {
@@ -611,17 +604,15 @@ k_tile_masks_perm(const SliceArgs A) {
   const int32_t* __restrict__ nbr = A.nbr[L];
   int32_t* __restrict__ slices = A.slices[L];
   const int64_t ld = A.ld;
-  const bool packed = (A.packed_mask >> L) & 1;
   __shared__ uint32_t m[4][3];
   __shared__ uint8_t klist[96];
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int r = tile * 128 + threadIdx.x;
     uint32_t w0 = 0, w1 = 0, w2 = 0;
-    uint32_t m0 = 0, m1 = 0, m2 = 0;
     int v = -1;
     if (r < n) {
       v = perm[r];
-      m0 = vmask[v]; m1 = vmask[ld + v]; m2 = vmask[2 * ld + v];   // 27 bits per time plane
+      const uint32_t m0 = vmask[v], m1 = vmask[ld + v], m2 = vmask[2 * ld + v];   // 27 bits per time plane
       w0 = m0 | (m1 << 27);
       w1 = (m1 >> 5) | (m2 << 22);
       w2 = m2 >> 10;
@@ -651,15 +642,7 @@ k_tile_masks_perm(const SliceArgs A) {
       for (int e = 0; e < nact; ++e) {
         const int k = klist[e];
         int val = -1;
-        if ((mine[k >> 5] >> (k & 31)) & 1u) {
-          if (packed) {
-            const int it = k >= 54 ? 2 : (k >= 27 ? 1 : 0), k3 = k - 27 * it;
-            const uint32_t mp = it == 0 ? m0 : (it == 1 ? m1 : m2);
-            val = __ldg(nbr + ((int64_t)v * 3 + it) * kPackedPlane + __popc(mp & ((1u << k3) - 1u)));
-          } else {
-            val = __ldg(nbr + (int64_t)k * ld + v);
-          }
-        }
+        if ((mine[k >> 5] >> (k & 31)) & 1u) val = __ldg(nbr + (int64_t)k * ld + v);
         dst[e * 128] = val;
       }
       dst[nact * 128] = v;
@@ -931,7 +914,6 @@ static int pattern_order(sps_ctx* ctx, cudaStream_t st) {
     S.slices[L] = g_tile_slices ? ctx->tslice[L] : nullptr;
   }
   S.counts = ctx->counts; S.ld = ctx->ld; S.first = kFirstSortedLevel;
-  S.packed_mask = ctx->packed_mask;
   k_tile_masks_perm<<<dim3(grid_for(n / 128 + 1, 1, 148 * 8), kSortedLevels), 128, 0, st>>>(S);
   prof_mark(ctx, "slices", st);
   SPS_CUDA_CHECK(cudaGetLastError());
@@ -1010,7 +992,6 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
   prof_mark(ctx, "kmap3", st);
   SPS_CUDA_CHECK(cudaGetLastError());
   ctx->forward_launches += 16 + 3 + 1 + 1;
-  ctx->packed_mask = ~O.dense_mask & ((1 << SPS_NUM_LEVELS) - 1);
   // ---- 5. shape sort + per-tile slices of the sorted levels ----
   { const int rc = pattern_order(ctx, st); if (rc != SPS_OK) return rc; }
   ctx->have_maps = true;
