@@ -63,7 +63,10 @@ struct V6Cfg {
   static constexpr int S = NPAD == 256 ? 3 : NPAD == 128 ? 4 : NPAD == 64 ? SPS_V6_S64 : NPAD == 32 ? SPS_V6_S32 : SPS_V6_S16;
   static constexpr int kBStage = NPAD * 128;
   static constexpr int kTmemCols = 2 * NPAD < 32 ? 32 : 2 * NPAD;
-  static constexpr int kIdxEntries = NPAD >= 128 ? kV6Entries : 2 * kV6Entries;
+#ifndef SPS_V6_IDX_TILES
+#define SPS_V6_IDX_TILES 2
+#endif
+  static constexpr int kIdxEntries = NPAD >= 128 ? kV6Entries : SPS_V6_IDX_TILES * kV6Entries;
   static constexpr int kShift = NPAD < 64 ? 64 : NPAD;
   // A ring | B ring | row indices [kIdxEntries][128] | barriers | klists | nact [8] | shift | tmem slot
   static constexpr size_t smem = (size_t)S * (kAStageBytes + kBStage) + (size_t)kIdxEntries * kV6EntryBytes +

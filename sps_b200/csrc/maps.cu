@@ -341,6 +341,8 @@ struct KmapOut {
   int dense_mask;                         // bit L: level L stores absent entries (-1) too
 };
 // All levels in one launch: blockIdx.z = level, blockIdx.y = time plane of the kernel.
+// (capping this kernel at 32 registers to fit more blocks beside another lane's convolution CTA made it 1.5x slower
+// and the step 18 % slower: profiles/r2_experiments.md)
 template <int KT>
 __global__ void __launch_bounds__(256)
 k_kernel_map_blk3(const LevelTabs T, const KmapOut O) {
