@@ -39,6 +39,7 @@ static size_t carve(sps_ctx* c, void* base, int64_t max_points) {
   c->n_dev = c->counts + 5;
   c->ticket = reinterpret_cast<uint32_t*>(c->counts + 32);
   c->nblocks = c->counts + 64;
+  c->tplanes = c->counts + 160;
   c->status = c->counts + 96;
   c->staging = cv.take<float>((size_t)N * 8);
   c->scores = cv.take<float>(N);

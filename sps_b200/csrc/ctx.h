@@ -35,6 +35,7 @@ struct sps_ctx {
   uint32_t* ticket = nullptr;  // last-block-done counters, one per unique() call
   int32_t* n_dev = nullptr;    // device copy of n (so level-0 kernels share the code path)
   int32_t* nblocks = nullptr;  // [SPS_NUM_LEVELS] blocks in each level's block table
+  int32_t* tplanes = nullptr;  // bit t: the input holds voxels in time plane t (written by the voxelisation)
   // 4x4x4 block tables, one per level (all levels are built and probed by the same launches)
   sps::Slot* btab[SPS_NUM_LEVELS] = {};              // block key -> block id, capacity table_capacity(max_points)
   int32_t* bcells[SPS_NUM_LEVELS] = {};              // [max_points][64] voxel rows per block (upper bound: one block per voxel)
