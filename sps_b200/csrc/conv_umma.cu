@@ -26,15 +26,18 @@
 
 namespace sps {
 
-// ring depth per accumulator width (measured: 4 beats 2, 3 and 5-7; deeper rings cost L1)
+// ring depth per accumulator width.  Round 1 ran ONE CTA per SM with a 4-deep ring (4 beat 2, 3 and 5-7).  Round 2: TWO
+// CTAs per SM, each with a 2-deep ring and one staged kernel-map slice (<= 113 KB of shared memory, <= 72 registers):
+// convolution family 1.79 -> 1.61 ms per forward (3-deep rings: 1.64) -- two independent gather streams fill the L1 data
+// pipe better than one deep ring, and the loader's bubble at a tile boundary hides behind the other CTA.
 #ifndef SPS_V6_S16
-#define SPS_V6_S16 4
+#define SPS_V6_S16 2
 #endif
 #ifndef SPS_V6_S32
-#define SPS_V6_S32 4
+#define SPS_V6_S32 2
 #endif
 #ifndef SPS_V6_S64
-#define SPS_V6_S64 4
+#define SPS_V6_S64 2
 #endif
 constexpr int kV6ProducerWarps = 8;
 constexpr int kV6ProducerThreads = kV6ProducerWarps * 32;
@@ -64,7 +67,7 @@ struct V6Cfg {
   static constexpr int kBStage = NPAD * 128;
   static constexpr int kTmemCols = 2 * NPAD < 32 ? 32 : 2 * NPAD;
 #ifndef SPS_V6_IDX_TILES
-#define SPS_V6_IDX_TILES 2
+#define SPS_V6_IDX_TILES 1
 #endif
   static constexpr int kIdxEntries = NPAD >= 128 ? kV6Entries : SPS_V6_IDX_TILES * kV6Entries;
   static constexpr int kShift = NPAD < 64 ? 64 : NPAD;
@@ -108,7 +111,10 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
 // 16-byte group, so a stage carries twice the channels).  GPC = 16-byte groups per kernel offset: 1 (fp16
 // only), 2 or 4 -> 8/GPC offsets share a stage; 8 -> one offset spans GP/8 stages.
 template <int NPAD, int GPC, typename T>
-__global__ void __launch_bounds__(kV6Threads, 1) k_conv_umma6(const sps_conv_args a, const __grid_constant__ UmmaParams p) {
+#ifndef SPS_V6_CTAS_PER_SM
+#define SPS_V6_CTAS_PER_SM 2   // resident CTAs per SM for N <= 64 (the wide accumulators of the width sweep take a whole SM)
+#endif
+__global__ void __launch_bounds__(kV6Threads, NPAD <= 64 ? SPS_V6_CTAS_PER_SM : 1) k_conv_umma6(const sps_conv_args a, const __grid_constant__ UmmaParams p) {
   using Cfg = V6Cfg<NPAD>;
   constexpr int EB = sizeof(T);                         // bytes per stored activation
   constexpr bool kHalf = EB == 2;
@@ -569,7 +575,8 @@ static int launch_umma6(const sps_conv_args& a, const UmmaParams& p_in, cudaStre
   SPS_CUDA_CHECK(ensure_dynamic_smem(k_conv_umma6<NPAD, GPC, T>, smem, &attr_done));
   int64_t tiles = (a.n_out_max + kTileM - 1) / kTileM;
   if (tiles < 1) tiles = 1;
-  const int grid = (int)(tiles < 148 ? tiles : 148);
+  const int per_sm = NPAD <= 64 ? SPS_V6_CTAS_PER_SM : 1;
+  const int grid = (int)(tiles < 148 * per_sm ? tiles : 148 * per_sm);
   k_conv_umma6<NPAD, GPC, T><<<grid, kV6Threads, smem, st>>>(a, p);
   SPS_CUDA_CHECK(cudaGetLastError());
   return SPS_OK;
