@@ -159,6 +159,10 @@ typedef struct sps_conv_args {
   int backend;              /* SPS_BACKEND_*: which kernel family serves this call (AUTO: tensor cores where
                                the layer shape and the optional inputs allow, CUDA cores otherwise)          */
   int flags;                /* SPS_CONV_FOLD_LO | SPS_CONV_OUT_SPLIT (fp16 rows on the tensor-core path only) */
+  int cin_split;            /* 0, or the channels of the FIRST of two segments of `in` rows (a concat buffer,
+                               minkunet.py:192: 64 + 32, 32 + 16 or 16 + 8 channels, fp16 rows, tensor-core path):
+                               the K axis of weight_kmajor (sps_conv_pack_kmajor_f16s) then walks segment by
+                               segment, so that neither carries padded columns.  Results do not depend on it */
 } sps_conv_args;
 /* MinkowskiConvolution / MinkowskiConvolutionTranspose (+ folded MinkowskiBatchNorm, ReLU,
  * residual) forward: minkunet.py:55-158, resnet.py:97-108, ME BasicBlock.  Served by the tcgen05
@@ -318,6 +322,12 @@ int sps_conv_pack_kmajor_f16(const float* w, int K, int cin, int cout, const flo
 #define SPS_PACK_FOLD_LO 4
 int64_t sps_conv_kmajor_ld_f16x(int K, int cin, int cin2, int pack_flags);
 int sps_conv_pack_kmajor_f16x(const float* w, int K, int cin, int cout, const float* w2, int cin2, int pack_flags, void* out);
+/* The same for two-segment input rows (sps_conv_args.cin_split; not together with SPS_PACK_IN_SPLIT): along K the first
+ * cin_split channels of every offset (padded to 1, 2, 4 or 8k groups), then the remaining cin - cin_split channels of every
+ * offset (unpadded), then the 1x1 term.  cin_split = 0: identical to the _f16x functions. */
+int64_t sps_conv_kmajor_ld_f16s(int K, int cin, int cin2, int pack_flags, int cin_split);
+int sps_conv_pack_kmajor_f16s(const float* w, int K, int cin, int cout, const float* w2, int cin2, int pack_flags, int cin_split,
+                              void* out);
 /* 1 when the tensor-core kernel can stage its 64-channel weight slabs through TMA (cp.async.bulk.tensor): the driver's
  * cuTensorMapEncodeTiled was found (cudaGetDriverEntryPoint) and SPS_NO_TMA_B is not set in the environment; 0: every
  * weight stage goes through cp.async (same results). */

@@ -28,7 +28,7 @@ SYMBOLS = [
     "sps_net_create", "sps_net_destroy", "sps_net_set_tensor", "sps_net_set_output", "sps_net_device_bytes", "sps_net_finalize",
     "sps_forward", "sps_forward_features", "sps_forward_host", "sps_unet_forward", "sps_devox_sigmoid", "sps_ctx_launch_count",
     "sps_map_bytes", "sps_map_build", "sps_map_destroy", "sps_submap_crop_voxel", "sps_submap_crop_radius",
-    "sps_assemble", "sps_memcpy_d2h", "sps_memcpy_h2d", "sps_infer_scan", "sps_infer_scan_scratch_bytes", "sps_conv_kmajor_ld", "sps_conv_pack_kmajor", "sps_conv_kmajor_ld_f16", "sps_conv_pack_kmajor_f16", "sps_conv_kmajor_ld_f16x", "sps_conv_pack_kmajor_f16x", "sps_kernel_map_tile_masks", "sps_tma_weights_available", "sps_ctx_set_pattern_sort",
+    "sps_assemble", "sps_memcpy_d2h", "sps_memcpy_h2d", "sps_infer_scan", "sps_infer_scan_scratch_bytes", "sps_conv_kmajor_ld", "sps_conv_pack_kmajor", "sps_conv_kmajor_ld_f16", "sps_conv_pack_kmajor_f16", "sps_conv_kmajor_ld_f16x", "sps_conv_pack_kmajor_f16x", "sps_conv_kmajor_ld_f16s", "sps_conv_pack_kmajor_f16s", "sps_kernel_map_tile_masks", "sps_tma_weights_available", "sps_ctx_set_pattern_sort",
     "sps_ctx_set_conv_backend", "sps_profile_enable", "sps_profile_read", "sps_ctx_pair_count",
     "sps_confusion_counts", "sps_voxel_mean", "sps_voxel_sum", "sps_gather_rows", "sps_affine_relu",
     "sps_pointcloud2_unpack", "sps_transform_points", "sps_pointcloud2_pack_scratch_bytes", "sps_pointcloud2_pack",
@@ -52,7 +52,7 @@ class ConvArgs(C.Structure):
                 ("head_w", C.c_void_p), ("head_b", C.c_float), ("head_out", C.c_void_p),
                 ("weight_kmajor", C.c_void_p), ("kmajor_ld", C.c_int64), ("round_out", C.c_int),
                 ("tile_mask", C.c_void_p), ("perm", C.c_void_p), ("tile_slices", C.c_void_p), ("io_dtype", C.c_int),
-                ("backend", C.c_int), ("flags", C.c_int)]
+                ("backend", C.c_int), ("flags", C.c_int), ("cin_split", C.c_int)]
 
 
 class SpsError(RuntimeError):
@@ -118,6 +118,8 @@ def load() -> C.CDLL:
         "sps_conv_pack_kmajor_f16": (i32, [vp, i32, i32, i32, vp, i32, vp]),
         "sps_conv_kmajor_ld_f16x": (i64, [i32, i32, i32, i32]),
         "sps_conv_pack_kmajor_f16x": (i32, [vp, i32, i32, i32, vp, i32, i32, vp]),
+        "sps_conv_kmajor_ld_f16s": (i64, [i32, i32, i32, i32, i32]),
+        "sps_conv_pack_kmajor_f16s": (i32, [vp, i32, i32, i32, vp, i32, i32, i32, vp]),
         "sps_ctx_set_conv_backend": (i32, [vp, i32]),
         "sps_confusion_counts": (i32, [vp, vp, i64, i64, f32, f32, vp, vp, vp]),
         "sps_voxel_mean": (i32, [vp, vp, i64, i32, vp, vp, vp]),

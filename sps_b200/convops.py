@@ -45,21 +45,22 @@ def pack_kmajor_f16(weight: torch.Tensor, weight2: torch.Tensor | None = None) -
 
 
 def pack_kmajor_f16x(weight: torch.Tensor, weight2: torch.Tensor | None = None, in_split=False, in2_split=False,
-                     fold_lo=False) -> torch.Tensor:
+                     fold_lo=False, cin_split=0) -> torch.Tensor:
     """``sps_conv_pack_kmajor_f16x``: the fp16 weight matrix with the precision options of the fused forward --
     ``in_split`` / ``in2_split``: the rows of ``in`` / ``in2`` are hi|lo pairs (weights duplicated along K);
-    ``fold_lo`` (cout == 8): rows 8..15 hold the low parts of the weights (SPS_CONV_FOLD_LO)."""
+    ``fold_lo`` (cout == 8): rows 8..15 hold the low parts of the weights (SPS_CONV_FOLD_LO); ``cin_split``: the rows are two
+    channel segments (``sps_conv_args.cin_split``, ``sps_conv_pack_kmajor_f16s``)."""
     lib = _cabi.load()
     w = np.ascontiguousarray(weight.detach().cpu().numpy(), np.float32)
     K, cin, cout = w.shape
     w2 = None if weight2 is None else np.ascontiguousarray(weight2.detach().cpu().numpy(), np.float32)
     cin2 = 0 if w2 is None else w2.shape[0]
     flags = (1 if in_split else 0) | (2 if in2_split else 0) | (4 if fold_lo else 0)
-    ld = lib.sps_conv_kmajor_ld_f16x(K, cin, cin2, flags)
+    ld = lib.sps_conv_kmajor_ld_f16s(K, cin, cin2, flags, int(cin_split))
     out = np.zeros((16 if fold_lo else cout, ld), np.float16)
-    check(lib.sps_conv_pack_kmajor_f16x(w.ctypes.data_as(C.c_void_p), K, cin, cout,
-                                        None if w2 is None else w2.ctypes.data_as(C.c_void_p), cin2, flags,
-                                        out.ctypes.data_as(C.c_void_p)), "sps_conv_pack_kmajor_f16x")
+    check(lib.sps_conv_pack_kmajor_f16s(w.ctypes.data_as(C.c_void_p), K, cin, cout,
+                                        None if w2 is None else w2.ctypes.data_as(C.c_void_p), cin2, flags, int(cin_split),
+                                        out.ctypes.data_as(C.c_void_p)), "sps_conv_pack_kmajor_f16s")
     return torch.as_tensor(out).to(weight.device)
 
 
@@ -90,7 +91,7 @@ def kernel_map_tile_masks(map, map_ld, K, n_out, n_out_max):
 
 def conv_fwd(inp, weight, n_out, *, map=None, map_ld=0, mode=_cabi.SPS_CONV_NBR, shift=None, in2=None, weight2=None,
              res=None, relu=False, out=None, head_w=None, head_b=0.0, head_out=None, weight_kmajor=None,
-             round_out=False, n_out_max=None, backend=None, tile_mask=None, io_f16=False, flags=0, cin_rows=None, cin2_rows=None):
+             round_out=False, n_out_max=None, backend=None, tile_mask=None, io_f16=False, flags=0, cin_rows=None, cin2_rows=None, cin_split=0):
     """out[o] = act(sum_k in[map[k][o]] @ W[k] (+ in2[o] @ W2) + shift (+ res[o])); ``n_out`` is a
     1-element int32 CUDA tensor (device-side count).  ``inp``/``out``/``in2``/``res`` may be
     channel slices (stride(0) is the leading dimension).  ``io_f16``: ``inp``/``in2``/``res``/``out`` are fp16
@@ -128,6 +129,7 @@ def conv_fwd(inp, weight, n_out, *, map=None, map_ld=0, mode=_cabi.SPS_CONV_NBR,
     a.io_dtype = _cabi.SPS_IO_F16 if io_f16 else _cabi.SPS_IO_F32
     a.backend = int(backend) if backend is not None else _cabi.SPS_BACKEND_AUTO
     a.flags = int(flags)
+    a.cin_split = int(cin_split)
     if cin_rows is not None:   # hi|lo input rows: the kernel sees the doubled channel count
         a.cin = int(cin_rows)
     if cin2_rows is not None:

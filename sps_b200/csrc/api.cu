@@ -86,7 +86,7 @@ bool conv_umma_f16_supports(const sps_conv_args& a);
 // is no CUDA-core kernel for them), else the CUDA-core kernels.
 int conv_dispatch(const sps_conv_args& a, cudaStream_t st) {
   if (a.io_dtype == SPS_IO_F16) return conv_umma_f16_supports(a) ? conv_umma(a, st) : SPS_ERR_UNSUPPORTED;
-  if (a.flags) return SPS_ERR_UNSUPPORTED;      // split-precision options exist on fp16 rows only
+  if (a.flags || a.cin_split) return SPS_ERR_UNSUPPORTED;      // split-precision options and K segments exist on fp16 rows only
   if (a.backend != SPS_BACKEND_FP32 && conv_umma_supports(a)) return conv_umma(a, st);
   return conv_simt(a, st);
 }

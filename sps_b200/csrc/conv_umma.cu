@@ -110,7 +110,11 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
 // T = float: fp32 rows, TF32 operands (kind::tf32); T = __half: fp16 rows and weights (kind::f16, 8 channels per
 // 16-byte group, so a stage carries twice the channels).  GPC = 16-byte groups per kernel offset: 1 (fp16
 // only), 2 or 4 -> 8/GPC offsets share a stage; 8 -> one offset spans GP/8 stages.
-template <int NPAD, int GPC, typename T>
+// GPC2 > 0: the input row is TWO channel segments (the halves of a concat buffer, minkunet.py:192): `split_groups`
+// 16-byte groups walked as above (GPC), then GPC2 (1, 2 or 4) groups packed 8 / GPC2 offsets per stage -- 96 = 64 + 32,
+// 48 = 32 + 16 and 24 = 16 + 8 channels without a single padded column (1.5 / 0.75 / 0.375 stages per offset instead
+// of 2 / 1 / 0.5).
+template <int NPAD, int GPC, typename T, int GPC2 = 0>
 #ifndef SPS_V6_CTAS_PER_SM
 #define SPS_V6_CTAS_PER_SM 2   // resident CTAs per SM for N <= 64 (the wide accumulators of the width sweep take a whole SM)
 #endif
@@ -171,10 +175,11 @@ __global__ void __launch_bounds__(kV6Threads, NPAD <= 64 ? SPS_V6_CTAS_PER_SM : 
   const int n_out = *a.n_out;
   const int ntiles = (n_out + kTileM - 1) / kTileM;
   const int K = a.K;
-  const int gpk = (a.cin * EB) >> 4;                    // real 16-byte groups per offset
+  const int gpk = GPC2 ? p.split_groups : ((a.cin * EB) >> 4);   // real 16-byte groups per offset (of the first segment)
   const int GP = GPC < 8 ? GPC : padded_groups_of(gpk, kHalf);  // padded groups per offset
   const int SPE = GPC < 8 ? 1 : GP >> 3;                // stages per offset (Cin >= 24)
   constexpr int EPS = GPC < 8 ? 8 / GPC : 1;            // offsets per stage (Cin <= 16)
+  constexpr int EPS2 = GPC2 ? 8 / GPC2 : 1;             // second segment: offsets per stage
   const int gpk2 = a.in2 ? ((a.cin2 * EB) >> 4) : 0;
   const int st2 = (gpk2 + 7) >> 3;                      // stages of the fused 1x1 term
   const uint32_t* tmask = a.tile_mask;
@@ -186,7 +191,9 @@ __global__ void __launch_bounds__(kV6Threads, NPAD <= 64 ? SPS_V6_CTAS_PER_SM : 
   auto tile_nact = [&](int tile) {
     return __popc(__ldg(tmask + 4 * tile)) + __popc(__ldg(tmask + 4 * tile + 1)) + __popc(__ldg(tmask + 4 * tile + 2));
   };
-  auto tile_stages = [&](int nact) { return (GPC < 8 ? (nact + EPS - 1) / EPS : nact * SPE) + st2; };
+  auto stages_a = [&](int nact) { return GPC < 8 ? (nact + EPS - 1) / EPS : nact * SPE; };
+  auto stages_b = [&](int nact) { return GPC2 ? (nact + EPS2 - 1) / EPS2 : 0; };
+  auto tile_stages = [&](int nact) { return stages_a(nact) + stages_b(nact) + st2; };
 
   if (warp < kV6ProducerWarps) {
     // =========================== PRODUCERS (256 threads) ===========================
@@ -215,10 +222,14 @@ __global__ void __launch_bounds__(kV6Threads, NPAD <= 64 ? SPS_V6_CTAS_PER_SM : 
     constexpr int GPCc = GPC < 8 ? GPC : 1;
     const int e_off = GPC < 8 ? cB / GPCc : 0;      // small Cin: which of the stage's offsets this column belongs to
     const int cg0 = GPC < 8 ? cB % GPCc : cB;       // channel group inside the offset
+    constexpr int GPC2c = GPC2 ? GPC2 : 1;
+    const int e_off2 = cB / GPC2c, cg02 = cB % GPC2c;   // the same for the second segment
 
     // ---- cursor over the stages of this CTA's tiles ----
     int tile = blockIdx.x, it_tile = 0;
     int nact = 0, m = 0, nst = 0;                   // present offsets, current stage, stages of the tile
+    int ns_a = 0, ns_b = 0;                         // stages of the two channel segments of the tile
+    bool stage_tma = false;                         // the weights of the stage about to be issued come through TMA
     int e = 0, sub = 0;                             // large Cin: offset entry and sub-stage
     uint32_t sx = 0;                                // shared byte address of this thread's int4 in entry 0
     const uint8_t* kl = klist;
@@ -234,32 +245,42 @@ __global__ void __launch_bounds__(kV6Threads, NPAD <= 64 ? SPS_V6_CTAS_PER_SM : 
                    : "=r"(idx[0]), "=r"(idx[1]), "=r"(idx[2]), "=r"(idx[3])
                    : "r"(addr));
     };
-    // fetch the parameters of stage m of the current tile
+    // fetch the parameters of stage m of the current tile: first channel segment, second segment, fused 1x1 term
     auto fetch = [&]() {
-      if (GPC < 8) {
-        const int nmap = (nact + EPS - 1) / EPS;
-        if (m < nmap) {
+      if (m < ns_a) {
+        if (GPC < 8) {
           const int ee = m * EPS + e_off;
           const bool e_ok = ee < nact;
           lds4(sx + (uint32_t)(e_ok ? ee : 0) * kV6EntryBytes);
           base = in_b + cg0 * 16; ld_b = in_ld_b;
           okc = e_ok && cg0 < gpk; bok = e_ok;
           wofs = (uint32_t)((int)kl[e_ok ? ee : 0] * GPCc + cg0) * 16u;
+          stage_tma = false;
         } else {
-          const int cg = cB + 8 * (m - nmap);
-          lds4(sx + (uint32_t)nact * kV6EntryBytes);
-          base = in2_b + cg * 16; ld_b = in2_ld_b;
-          okc = cg < gpk2; bok = okc;
-          wofs = (uint32_t)(K * GPCc + cg) * 16u;
+          // entry e = kernel offset klist[e], sub-stage `sub` of its SPE stages
+          if (sub == 0) lds4(sx + (uint32_t)e * kV6EntryBytes);
+          const int cg = cB + 8 * sub;
+          base = in_b + cg * 16; ld_b = in_ld_b;
+          okc = cg < gpk; bok = okc;
+          wofs = (uint32_t)((int)kl[e] * GP + cg) * 16u;
+          stage_tma = tma_b;
         }
+      } else if (GPC2 && m < ns_a + ns_b) {
+        const int ee = (m - ns_a) * EPS2 + e_off2;
+        const bool e_ok = ee < nact;
+        lds4(sx + (uint32_t)(e_ok ? ee : 0) * kV6EntryBytes);
+        base = in_b + (gpk + cg02) * 16; ld_b = in_ld_b;
+        okc = e_ok; bok = e_ok;
+        wofs = (uint32_t)(K * GP + (int)kl[e_ok ? ee : 0] * GPC2c + cg02) * 16u;
+        stage_tma = false;
       } else {
-        // entry e (< nact: kernel offset klist[e]; == nact: the fused 1x1 term on the tile's own rows)
-        if (sub == 0) lds4(sx + (uint32_t)e * kV6EntryBytes);
-        const int cg = cB + 8 * sub;
-        const bool self = e >= nact;
-        base = (self ? in2_b : in_b) + cg * 16; ld_b = self ? in2_ld_b : in_ld_b;
-        okc = cg < (self ? gpk2 : gpk); bok = okc;
-        wofs = (uint32_t)((self ? K : (int)kl[e]) * GP + cg) * 16u;
+        // the fused 1x1 term on the tile's own rows (entry nact)
+        const int cg = cB + 8 * (m - ns_a - ns_b);
+        lds4(sx + (uint32_t)nact * kV6EntryBytes);
+        base = in2_b + cg * 16; ld_b = in2_ld_b;
+        okc = cg < gpk2; bok = okc;
+        wofs = (uint32_t)(K * (GP + GPC2) + cg) * 16u;
+        stage_tma = tma_b;
       }
     };
     // make `tile` current (skipping tiles without stages); false when the CTA has no tile left
@@ -269,7 +290,8 @@ __global__ void __launch_bounds__(kV6Threads, NPAD <= 64 ? SPS_V6_CTAS_PER_SM : 
         const int par = it_tile % NP;
         mbar_wait(bar_idxf + 8 * par, (it_tile / NP) & 1);
         nact = snact[par];
-        nst = tile_stages(nact);
+        ns_a = stages_a(nact); ns_b = stages_b(nact);
+        nst = ns_a + ns_b + st2;
         sx = sidx_u + (uint32_t)par * par_bytes + (uint32_t)r0 * 16u;
         kl = klist + par * kl_stride;
         m = 0; e = 0; sub = 0;
@@ -283,9 +305,8 @@ __global__ void __launch_bounds__(kV6Threads, NPAD <= 64 ? SPS_V6_CTAS_PER_SM : 
     auto advance = [&]() -> bool {
       ++m;
       if (m < nst) {
-        if (GPC >= 8) {
-          const int lim = e < nact ? SPE : st2;
-          if (++sub == lim) { sub = 0; ++e; }
+        if (GPC >= 8 && m < ns_a) {
+          if (++sub == SPE) { sub = 0; ++e; }
         }
         fetch();
         return true;
@@ -310,7 +331,7 @@ __global__ void __launch_bounds__(kV6Threads, NPAD <= 64 ? SPS_V6_CTAS_PER_SM : 
             const uint32_t row = (uint32_t)(idx[i] < 0 ? 0 : idx[i]);
             cp_async16_or_zero<SPS_V6_A_CG != 0>(dstA + a_off[i], base + (uint64_t)row * ld_b, !ok);
           }
-          if (tma_b) {
+          if (stage_tma) {
             if (tid == 0) {   // thread 0 holds column 0 of the slab: wofs = byte offset of the slab in a weight row
               mbar_expect_tx(bar_full + 8 * s, (uint32_t)kBStageBytes);
               tma_load_2d(sB_u + (uint32_t)s * kBStageBytes, &p.tmap, (int)(wofs >> 1), 0, bar_full + 8 * s);
@@ -566,18 +587,19 @@ static bool make_weight_tmap(CUtensorMap* m, const void* wt, int64_t ldk, int co
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int NPAD, int GPC, typename T>
+template <int NPAD, int GPC, typename T, int GPC2 = 0>
 static int launch_umma6(const sps_conv_args& a, const UmmaParams& p_in, cudaStream_t st) {
   UmmaParams p = p_in;
+  p.split_groups = GPC2 ? a.cin_split >> 3 : 0;
   if (sizeof(T) == 2 && GPC == 8) p.use_tma = make_weight_tmap(&p.tmap, p.wt, p.ldk, (a.flags & SPS_CONV_FOLD_LO) ? 16 : a.cout, NPAD) ? 1 : 0;
   const size_t smem = V6Cfg<NPAD>::smem;
   static unsigned long long attr_done = 0;   // bit per device: the opt-in is per device and per kernel
-  SPS_CUDA_CHECK(ensure_dynamic_smem(k_conv_umma6<NPAD, GPC, T>, smem, &attr_done));
+  SPS_CUDA_CHECK(ensure_dynamic_smem(k_conv_umma6<NPAD, GPC, T, GPC2>, smem, &attr_done));
   int64_t tiles = (a.n_out_max + kTileM - 1) / kTileM;
   if (tiles < 1) tiles = 1;
   const int per_sm = NPAD <= 64 ? SPS_V6_CTAS_PER_SM : 1;
   const int grid = (int)(tiles < 148 * per_sm ? tiles : 148 * per_sm);
-  k_conv_umma6<NPAD, GPC, T><<<grid, kV6Threads, smem, st>>>(a, p);
+  k_conv_umma6<NPAD, GPC, T, GPC2><<<grid, kV6Threads, smem, st>>>(a, p);
   SPS_CUDA_CHECK(cudaGetLastError());
   return SPS_OK;
 }
@@ -585,6 +607,16 @@ static int launch_umma6(const sps_conv_args& a, const UmmaParams& p_in, cudaStre
 template <int NPAD, typename T>
 static int launch_umma6_n(const sps_conv_args& a, const UmmaParams& p, cudaStream_t st) {
   constexpr bool kHalf = sizeof(T) == 2;
+  if (a.cin_split) {
+    // two channel segments (fp16 rows): 64 + 32, 32 + 16 or 16 + 8 channels
+    if constexpr (kHalf) {
+      const int ga = a.cin_split >> 3, gb = (a.cin - a.cin_split) >> 3;
+      if (ga == 8 && gb == 4) return launch_umma6<NPAD, 8, T, 4>(a, p, st);
+      if (ga == 4 && gb == 2) return launch_umma6<NPAD, 4, T, 2>(a, p, st);
+      if (ga == 2 && gb == 1) return launch_umma6<NPAD, 2, T, 1>(a, p, st);
+    }
+    return SPS_ERR_UNSUPPORTED;
+  }
   const int gp = padded_groups_of((a.cin * (int)sizeof(T)) >> 4, kHalf);
   if (kHalf && gp == 1) return launch_umma6<NPAD, kHalf ? 1 : 2, T>(a, p, st);
   if (gp == 2) return launch_umma6<NPAD, 2, T>(a, p, st);
@@ -636,7 +668,7 @@ int conv_umma(const sps_conv_args& a, cudaStream_t st) {
 // fp32 rows, TF32 operands
 bool conv_umma_supports(const sps_conv_args& a) {
   if (a.io_dtype != SPS_IO_F32 || a.mode != SPS_CONV_NBR || !a.map || !a.weight_kmajor || !a.tile_mask) return false;
-  if (a.K < 1 || a.K > kMaxK) return false;
+  if (a.K < 1 || a.K > kMaxK || a.cin_split) return false;
   if (a.cin < 4 || (a.cin & 3) || (a.in_ld & 3)) return false;
   if (a.in2 && ((a.cin2 & 3) || (a.in2_ld & 3))) return false;
   if (!(a.cout == 8 || a.cout == 16 || a.cout == 32 || a.cout == 64)) return false;
@@ -680,6 +712,11 @@ bool conv_umma_f16_supports(const sps_conv_args& a) {
   if (a.kmajor_ld & 7) return false;
   if ((a.flags & SPS_CONV_FOLD_LO) && a.cout != 8) return false;
   if ((a.flags & SPS_CONV_OUT_SPLIT) && a.out && (a.out_ld & 15)) return false;
+  if (a.cin_split) {   // two channel segments: 64 + 32, 32 + 16, 16 + 8
+    const int ga = a.cin_split >> 3, gb = (a.cin - a.cin_split) >> 3;
+    if ((a.cin_split & 7) || a.cout > 64) return false;
+    if (!((ga == 8 && gb == 4) || (ga == 4 && gb == 2) || (ga == 2 && gb == 1))) return false;
+  }
   return true;
 }
 
@@ -690,21 +727,32 @@ bool conv_umma_f16_supports(const sps_conv_args& a) {
 // pack_flags (include/sps_b200.h): SPS_PACK_IN_SPLIT / SPS_PACK_IN2_SPLIT double the channels of `in` / `in2` (rows stored
 // as hi|lo pairs: every 8-channel group of the weights appears twice along K), SPS_PACK_FOLD_LO appends the low parts
 // of the weights as rows 8..15 (cout == 8).
-extern "C" int64_t sps_conv_kmajor_ld_f16x(int K, int cin, int cin2, int pack_flags) {
+// cin_split > 0 (sps_conv_args.cin_split): the K axis holds the first cin_split channels of every offset, THEN the remaining
+// channels of every offset (unpadded: 8, 16 or 32 of them), then the 1x1 term.
+extern "C" int64_t sps_conv_kmajor_ld_f16s(int K, int cin, int cin2, int pack_flags, int cin_split) {
   const int ce = (pack_flags & SPS_PACK_IN_SPLIT) ? 2 * cin : cin, c2e = (pack_flags & SPS_PACK_IN2_SPLIT) ? 2 * cin2 : cin2;
+  if (cin_split > 0 && cin_split < cin)
+    return (int64_t)K * (sps::padded_groups_of((cin_split + 7) >> 3, true) * 8 + (((cin - cin_split) + 7) & ~7)) + ((c2e + 63) & ~63);
   return (int64_t)K * sps::padded_groups_of((ce + 7) >> 3, true) * 8 + ((c2e + 63) & ~63);
 }
-extern "C" int sps_conv_pack_kmajor_f16x(const float* w, int K, int cin, int cout, const float* w2, int cin2, int pack_flags,
-                                         void* out_) {
+extern "C" int64_t sps_conv_kmajor_ld_f16x(int K, int cin, int cin2, int pack_flags) {
+  return sps_conv_kmajor_ld_f16s(K, cin, cin2, pack_flags, 0);
+}
+extern "C" int sps_conv_pack_kmajor_f16s(const float* w, int K, int cin, int cout, const float* w2, int cin2, int pack_flags,
+                                         int cin_split, void* out_) {
   if (!w || !out_ || K < 1 || cin < 1 || cout < 1 || (w2 == nullptr) != (cin2 == 0)) return SPS_ERR_BAD_ARG;
+  if (cin_split < 0 || cin_split >= cin) return SPS_ERR_BAD_ARG;
+  if (cin_split && ((pack_flags & SPS_PACK_IN_SPLIT) || (cin_split & 7) || (cin & 7))) return SPS_ERR_BAD_ARG;
   const bool in_split = pack_flags & SPS_PACK_IN_SPLIT, in2_split = pack_flags & SPS_PACK_IN2_SPLIT,
              fold = pack_flags & SPS_PACK_FOLD_LO;
   if (fold && cout != 8) return SPS_ERR_BAD_ARG;
   if ((in_split && (cin & 7)) || (in2_split && (cin2 & 7))) return SPS_ERR_BAD_ARG;
   __half* out = static_cast<__half*>(out_);
-  const int64_t ldk = sps_conv_kmajor_ld_f16x(K, cin, cin2, pack_flags);
-  const int ce = in_split ? 2 * cin : cin;
-  const int cpad = sps::padded_groups_of((ce + 7) >> 3, true) * 8;
+  const int64_t ldk = sps_conv_kmajor_ld_f16s(K, cin, cin2, pack_flags, cin_split);
+  const int ce = cin_split ? cin_split : (in_split ? 2 * cin : cin);
+  const int cpad = sps::padded_groups_of((ce + 7) >> 3, true) * 8;       // first segment, per offset
+  const int cb = cin_split ? cin - cin_split : 0;                         // second segment, per offset
+  const int64_t k_end = (int64_t)K * (cpad + cb);                         // where the 1x1 term starts
   const int rows = fold ? 16 : cout;
   // position of input channel ci inside its (possibly doubled) block, and of its low-half twin
   auto pos = [](int ci, bool split) { return split ? (ci >> 3) * 16 + (ci & 7) : ci; };
@@ -719,16 +767,21 @@ extern "C" int sps_conv_pack_kmajor_f16x(const float* w, int K, int cin, int cou
     for (int k = 0; k < K; ++k)
       for (int ci = 0; ci < cin; ++ci) {
         const __half v = val(w[((int64_t)k * cin + ci) * cout + nn]);
+        if (cin_split && ci >= cin_split) { row[(int64_t)K * cpad + (int64_t)k * cb + (ci - cin_split)] = v; continue; }
         row[(int64_t)k * cpad + pos(ci, in_split)] = v;
         if (in_split) row[(int64_t)k * cpad + pos(ci, true) + 8] = v;
       }
     for (int ci = 0; ci < cin2; ++ci) {
       const __half v = val(w2[(int64_t)ci * cout + nn]);
-      row[(int64_t)K * cpad + pos(ci, in2_split)] = v;
-      if (in2_split) row[(int64_t)K * cpad + pos(ci, true) + 8] = v;
+      row[k_end + pos(ci, in2_split)] = v;
+      if (in2_split) row[k_end + pos(ci, true) + 8] = v;
     }
   }
   return SPS_OK;
+}
+extern "C" int sps_conv_pack_kmajor_f16x(const float* w, int K, int cin, int cout, const float* w2, int cin2, int pack_flags,
+                                         void* out) {
+  return sps_conv_pack_kmajor_f16s(w, K, cin, cout, w2, cin2, pack_flags, 0, out);
 }
 extern "C" int64_t sps_conv_kmajor_ld_f16(int K, int cin, int cin2) { return sps_conv_kmajor_ld_f16x(K, cin, cin2, 0); }
 extern "C" int sps_conv_pack_kmajor_f16(const float* w, int K, int cin, int cout, const float* w2, int cin2, void* out) {

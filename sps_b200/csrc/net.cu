@@ -27,6 +27,7 @@ struct ConvW {
   int64_t ldkh = 0;
   int pack_flags = 0;      // SPS_PACK_*: how `wth` was packed (split inputs double the K columns, folded low parts add rows)
   int conv_flags = 0;      // SPS_CONV_*: what the fp16 forward asks of the kernel for this layer
+  int cin_split = 0;       // fp16 forward: channels of the first of two input segments (sps_conv_args.cin_split), 0 = one segment
   int K = 0, cin = 0, cout = 0, cin2 = 0;
 };
 
@@ -130,10 +131,11 @@ extern "C" int sps_net_finalize(sps_net* net, void* d_weights, size_t bytes, voi
   auto add_kmajor_h = [&](Pending& p, const std::vector<float>& w, int K, int cin, int cout,
                           const std::vector<float>* w2, int cin2) {
     const int pf = p.cw->pack_flags;
-    const int64_t ldk = sps_conv_kmajor_ld_f16x(K, cin, cin2, pf);
+    const int cs = p.cw->cin_split;
+    const int64_t ldk = sps_conv_kmajor_ld_f16s(K, cin, cin2, pf, cs);
     const int rows = (pf & SPS_PACK_FOLD_LO) ? 16 : cout;
     std::vector<float> wt(((size_t)rows * ldk + 1) / 2);
-    sps_conv_pack_kmajor_f16x(w.data(), K, cin, cout, w2 ? w2->data() : nullptr, cin2, pf, wt.data());
+    sps_conv_pack_kmajor_f16s(w.data(), K, cin, cout, w2 ? w2->data() : nullptr, cin2, pf, cs, wt.data());
     p.cw->ldkh = ldk;
     p.wth = pk.add(wt);
     p.has_wth = true;
@@ -158,11 +160,11 @@ extern "C" int sps_net_finalize(sps_net* net, void* d_weights, size_t bytes, voi
     cw.conv_flags = (cout == 8 ? SPS_CONV_FOLD_LO : 0) | (out_split ? SPS_CONV_OUT_SPLIT : 0);
   };
   auto add_conv = [&](ConvW& cw, const std::string& kname, const std::string& bn, int K, int cin, int cout,
-                      bool in_split = false, bool out_split = false) {
+                      bool in_split = false, bool out_split = false, int cin_split = 0) {
     std::vector<float> w; std::vector<double> sh;
     if (!fold_conv(net, kname, bn, K, cin, cout, w, sh)) return false;
     std::vector<float> shf(sh.begin(), sh.end());
-    cw.K = K; cw.cin = cin; cw.cout = cout; cw.cin2 = 0;
+    cw.K = K; cw.cin = cin; cw.cout = cout; cw.cin2 = 0; cw.cin_split = cin_split;
     plan(cw, cout, in_split, false, out_split);
     Pending p{&cw, pk.add(w), pk.add(shf), 0, false};
     if (K == 81 || (K == 8 && cin >= 16 && cin % 4 == 0)) add_kmajor(p, w, K, cin, cout, nullptr, 0);  // 8-channel 2x2x2 layers stay on the CUDA-core kernel (measured faster)
@@ -171,8 +173,12 @@ extern "C" int sps_net_finalize(sps_net* net, void* d_weights, size_t bytes, voi
     return true;
   };
   auto add_block = [&](int b, const std::string& name, int cin, int cout, bool tail = false) {
-    // tail = block8: its input (the level-0 concat buffer) holds hi|lo rows
-    if (!add_conv(net->blk1[b], name + ".0.conv1.kernel", name + ".0.norm1", 81, cin, cout, tail, false)) return false;
+    // tail = block8: its input (the level-0 concat buffer) holds hi|lo rows.  block5 reads a concat buffer of 64 + 32
+    // channels: two K segments (1.5 stages per offset instead of 2; measured 135 -> 121 us).  The 32 + 16 and 16 + 8
+    // buffers of block6 / block7 stay one padded segment: splitting them fetches every row twice and the gather is bound
+    // by rows, not bytes (block7.conv1 119 -> 132 us with the split).
+    const int seg = (!tail && cin > cout && cout == 64 && !getenv("SPS_NO_CIN_SPLIT")) ? cout : 0;
+    if (!add_conv(net->blk1[b], name + ".0.conv1.kernel", name + ".0.norm1", 81, cin, cout, tail, false, seg)) return false;
     std::vector<float> w; std::vector<double> sh;
     if (!fold_conv(net, name + ".0.conv2.kernel", name + ".0.norm2", 81, cout, cout, w, sh)) return false;
     ConvW& cw = net->blk2[b];
@@ -296,6 +302,7 @@ static int run_conv(sps_ctx* c, const ConvIo& io, const char* name, const ConvW&
     if ((w.pack_flags & SPS_PACK_IN_SPLIT)) a.cin = 2 * w.cin;        // hi|lo rows read as doubled channels
     if (in2.p && (w.pack_flags & SPS_PACK_IN2_SPLIT)) a.cin2 = 2 * w.cin2;
     a.flags = w.conv_flags;
+    a.cin_split = w.cin_split;
     a.io_dtype = SPS_IO_F16;
     a.weight_kmajor = w.wth; a.kmajor_ld = w.ldkh;
   } else {

@@ -117,6 +117,7 @@ struct UmmaParams {
   int64_t ldk;
   int round_out;
   int flags;        // SPS_CONV_FOLD_LO | SPS_CONV_OUT_SPLIT
+  int split_groups; // two-segment input rows: 16-byte groups of the FIRST segment (0 = one segment)
   int use_tma;      // the weight stages of a full-width (64-channel) K slab come through TMA: `tmap` is valid
   alignas(64) CUtensorMap tmap;   // 2-D map of the fp16 K-major weight matrix, box = 64 halves x NPAD rows, SWIZZLE_128B
 };

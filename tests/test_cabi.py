@@ -239,3 +239,44 @@ def test_calculate_metrics_matches_reference_formulas():
     tp = np.sum((gt == 1) & (pred == 1)); fp = np.sum((gt == 0) & (pred == 1)); fn = np.sum((gt == 1) & (pred == 0))
     assert util.calculate_metrics(gt, pred)[4] == tp / (tp + fn + fp)
     assert util.calculate_metrics(np.zeros(4), np.zeros(4))[:3] == (0, 0, 0)
+
+
+def test_two_segment_weight_packer_host_side():
+    """sps_conv_pack_kmajor_f16s: with cin_split the K axis holds segment A of every offset (group-padded), then segment B of
+    every offset (unpadded), then the 1x1 term; cin_split = 0 reproduces sps_conv_pack_kmajor_f16x."""
+    from sps_b200 import _cabi
+    lib = _cabi.load()
+    rng = np.random.default_rng(2)
+    for K, cin, cs, cout in [(81, 96, 64, 64), (81, 48, 32, 32), (81, 24, 16, 16), (8, 24, 16, 8)]:
+        w = rng.standard_normal((K, cin, cout)).astype(np.float32)
+        w2 = rng.standard_normal((cin, cout)).astype(np.float32)
+        ga = cs // 8
+        gpa = 1 if ga <= 1 else 2 if ga <= 2 else 4 if ga <= 4 else (ga + 7) // 8 * 8
+        cb = cin - cs
+        ld = lib.sps_conv_kmajor_ld_f16s(K, cin, cin, 0, cs)
+        assert ld == K * (gpa * 8 + cb) + (cin + 63) // 64 * 64
+        out = np.full((cout, ld), 7, np.float16)
+        assert lib.sps_conv_pack_kmajor_f16s(w.ctypes.data_as(C.c_void_p), K, cin, cout, w2.ctypes.data_as(C.c_void_p), cin, 0, cs,
+                                             out.ctypes.data_as(C.c_void_p)) == 0
+        wt = w.astype(np.float16).transpose(2, 0, 1)                       # [cout][K][cin]
+        seg_a = out[:, : K * gpa * 8].reshape(cout, K, gpa * 8)
+        assert np.array_equal(seg_a[:, :, :cs], wt[:, :, :cs]) and not seg_a[:, :, cs:].any()
+        seg_b = out[:, K * gpa * 8: K * (gpa * 8 + cb)].reshape(cout, K, cb)
+        assert np.array_equal(seg_b, wt[:, :, cs:])
+        tail = out[:, K * (gpa * 8 + cb):]
+        assert np.array_equal(tail[:, :cin], w2.astype(np.float16).T) and not tail[:, cin:].any()
+        # one segment: the _f16x layout
+        ld0 = lib.sps_conv_kmajor_ld_f16s(K, cin, cin, 0, 0)
+        assert ld0 == lib.sps_conv_kmajor_ld_f16x(K, cin, cin, 0)
+        a = np.zeros((cout, ld0), np.float16)
+        b = np.zeros((cout, ld0), np.float16)
+        assert lib.sps_conv_pack_kmajor_f16s(w.ctypes.data_as(C.c_void_p), K, cin, cout, w2.ctypes.data_as(C.c_void_p), cin, 0, 0,
+                                             a.ctypes.data_as(C.c_void_p)) == 0
+        assert lib.sps_conv_pack_kmajor_f16x(w.ctypes.data_as(C.c_void_p), K, cin, cout, w2.ctypes.data_as(C.c_void_p), cin, 0,
+                                             b.ctypes.data_as(C.c_void_p)) == 0
+        assert np.array_equal(a, b)
+    # bad arguments: split together with hi|lo rows, split not a multiple of 8, split >= cin
+    w = np.zeros((8, 24, 8), np.float32)
+    o = np.zeros((16, 4096), np.float16)
+    for pf, cs in [(1, 16), (0, 12), (0, 24)]:
+        assert lib.sps_conv_pack_kmajor_f16s(w.ctypes.data_as(C.c_void_p), 8, 24, 8, None, 0, pf, cs, o.ctypes.data_as(C.c_void_p)) != 0

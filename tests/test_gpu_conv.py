@@ -294,3 +294,40 @@ def test_wide_layers_of_the_width_sweep(cin, cout):
                        quant=f16)
         assert got.shape == (V, cout)
         assert np.abs(got - ref).max() < 2e-3 * max(1.0, np.abs(ref).max()), (kw, np.abs(got - ref).max())
+
+
+@pytest.mark.parametrize("cin,cin_split,cout", [(96, 64, 64), (48, 32, 32), (24, 16, 16), (96, 64, 32), (24, 16, 8)])
+def test_two_segment_input_rows(cin, cin_split, cout):
+    """sps_conv_args.cin_split: the rows of a concat buffer walked segment by segment along K (no padded columns).  Same
+    products, same fp32 accumulator: equal to the float64 reference at the fp16 bound, and to the one-segment kernel
+    within fp32 summation-order noise.  With the fused 1x1 term on the same rows (the decoder blocks' downsample)."""
+    from sps_b200 import convops
+    rng = np.random.default_rng(cin * 7 + cout)
+    V, K = 2100, 81
+    nbr = random_map(rng, K, V, V, 0.3)
+    nbr[:, 700:900] = -1
+    nbr[33:, 1000:1400] = -1                  # tiles with an odd number of present offsets (ragged last stage of both segments)
+    x = rng.standard_normal((V, cin)).astype(np.float32)
+    w = (rng.standard_normal((K, cin, cout)) / np.sqrt(cin * 8)).astype(np.float32)
+    w2 = (rng.standard_normal((cin, cout)) / np.sqrt(cin)).astype(np.float32)
+    shift = rng.standard_normal(cout).astype(np.float32)
+    ld = (V + 31) // 32 * 32
+    m = np.full((K, ld), -1, np.int32)
+    m[:, :V] = nbr
+    dev = lambda a, dt=None: torch.as_tensor(np.ascontiguousarray(a)).cuda().to(dt) if dt else torch.as_tensor(np.ascontiguousarray(a)).cuda()
+    n_out = torch.tensor([V], dtype=torch.int32, device="cuda")
+    half = torch.float16
+    for fused in (False, True):
+        outs = []
+        for cs in (0, cin_split):
+            wt = convops.pack_kmajor_f16x(dev(w), dev(w2) if fused else None, cin_split=cs, fold_lo=cout == 8)
+            out = convops.conv_fwd(dev(x, half), dev(w), n_out, map=dev(m), map_ld=ld, shift=dev(shift), relu=True,
+                                   in2=dev(x, half) if fused else None, weight2=dev(w2) if fused else None,
+                                   weight_kmajor=wt, io_f16=True, backend=3, cin_split=cs, flags=1 if cout == 8 else 0)
+            torch.cuda.synchronize()
+            outs.append(out[:V].float().cpu().numpy())
+        ref = ref_conv(x, nbr, w, shift=shift, x2=x if fused else None, w2=w2 if fused else None, relu=True, quant=f16)
+        scale = max(1.0, np.abs(ref).max())
+        if cout != 8:   # (folded low weight parts are more exact than the fp16-weight reference)
+            assert np.abs(outs[1] - ref).max() < 2e-3 * scale, (fused, np.abs(outs[1] - ref).max())
+        assert np.abs(outs[1] - outs[0]).max() < 2e-3 * scale, (fused, np.abs(outs[1] - outs[0]).max())
