@@ -216,6 +216,55 @@ def measure_sizes(engine, points):
     return V, [pairs(L, 3) for L in range(5)], pairs(0, 5)
 
 
+def tile_walk(engine, V):
+    """Present kernel offsets of every 128-row tile of the 3x3x3x3 maps, per level, in the order the convolution walks them
+    (sps_ctx_level.tile_mask: the shape-sorted order where the level was sorted).  Call after measure_sizes."""
+    out = []
+    for L in range(5):
+        v = engine.level(L)
+        nt = (V[L] + 127) // 128
+        if not v.tile_mask or nt == 0:
+            out.append(np.zeros(0, np.int64))
+            continue
+        m = engine._read(v.tile_mask, nt * 4, np.uint32).reshape(nt, 4)[:, :3]
+        out.append(np.array([bin(int(a)).count("1") + bin(int(b)).count("1") + bin(int(c)).count("1") for a, b, c in m], np.int64))
+    return out
+
+
+def staging_accounting(nact, planes=PLANES):
+    """Shared-memory staging work of the 81-offset layers of the fp16 forward -- the resource the kernel is actually
+    bound by.  Every stage is a 128-row x 128-byte A slab (16 KB: 32 warp-wide 16-byte cp.async instructions) plus an N-row
+    weight slab; the stage count per tile mirrors csrc/conv_umma.cu (offsets per stage by channel count, two-segment walk of
+    block5.conv1, hi|lo rows of the level-0 tail, fused 1x1 term).  LDGSTS retires one warp instruction per 8 cycles and SM
+    (B300_MICROARCH.md, `LDGSTS rt`): 64 bytes per cycle and SM is the roof."""
+    def gp(groups):
+        return 1 if groups <= 1 else 2 if groups <= 2 else 4 if groups <= 4 else (groups + 7) // 8 * 8
+    out = {}
+    for name, kind, cin, cout, L, cin2 in conv_layers(planes):
+        if kind != "k3" or len(nact[L]) == 0:
+            continue
+        na = nact[L]
+        split_in = L == 0                       # level-0 tail: hi|lo rows, doubled channels
+        g = (cin * (2 if split_in and name.startswith("block8.conv1") else 1)) // 8
+        g2 = (cin2 * (2 if split_in else 1)) // 8
+        packed2 = gp(g) < 8 and 0 < g2 <= 8     # the 1x1 term rides as extra offset slots of the last stage
+        n2 = -(-g2 // gp(g)) if packed2 else 0
+        if name == "block5.conv1" and cin == 96:
+            st = na + (na + 1) // 2              # 64 channels per offset, then 32-channel halves two offsets per stage
+        elif gp(g) < 8:
+            eps = 8 // gp(g)
+            st = (na + n2 + eps - 1) // eps
+        else:
+            st = na * (gp(g) // 8)
+        if cin2 and not packed2:
+            st = st + (g2 + 7) // 8
+        stages = int(st.sum())
+        weights_tma = gp(g) >= 8
+        winstr = 0 if weights_tma else max(cout if cout > 8 else 16, 16) // 4      # N rows x 8 chunks / 32 lanes
+        out[name] = {"stages": stages, "staged_bytes": stages * 128 * 128, "ldgsts_warp_instr": stages * (32 + winstr)}
+    return out
+
+
 def profile_pass(engine, net, d_batches, steps, voxel=VOXEL):
     """Per-stage CUDA-event durations (events recorded by the library on its launch stream)."""
     import torch
@@ -544,6 +593,24 @@ def run_config2(args):
         V, P3, P5 = measure_sizes(engine, dev[(nprof - 1) % len(dev)])
         acc = stage_accounting(V, P3, P5, len(dev[(nprof - 1) % len(dev)]), half_rows=args.backend in (0, 3))
         roof, rows = roofline_from(stage_ms, acc, peaks)
+        if args.backend in (0, 3) and roof:
+            # the resource the kernel is bound by: 16-byte cp.async copies into the shared-memory stages
+            nact = tile_walk(engine, V)
+            stg = staging_accounting(nact)
+            sm_hz = (clocks.get("sm_mhz") or 1920) * 1e6
+            t_lsu = 0.0
+            for nm, a in stg.items():
+                if nm in rows:
+                    bound_ms = a["ldgsts_warp_instr"] * 8 / 148 / sm_hz * 1e3
+                    rows[nm].update({"stages": a["stages"], "staged_GB/s": round(a["staged_bytes"] / (rows[nm]["ms"] * 1e-3) / 1e9, 1),
+                                     "ldgsts_bound_ms": round(bound_ms, 4), "ldgsts_frac": round(bound_ms / rows[nm]["ms"], 3)})
+                    t_lsu += bound_ms
+            t_k3 = sum(rows[nm]["ms"] for nm in stg if nm in rows)
+            roof["staging"] = {"what": "81-offset layers: warp-wide 16-byte cp.async instructions into the A/B stages at 8 cycles "
+                                       "per instruction and SM (64 B/cycle/SM) -- the issue rate that bounds the gather",
+                               "layers": len(stg), "layers_ms": round(t_k3, 4), "bound_ms": round(t_lsu, 4),
+                               "frac": round(t_lsu / t_k3, 3) if t_k3 else None,
+                               "tile_fill": {f"L{L}": round(P3[L] / max(int(nact[L].sum()) * 128, 1), 3) for L in range(4)}}
         result["roofline"] = roof
         result["stages"] = rows
         result["stage_sum_ms"] = round(sum(stage_ms.values()), 4)

@@ -181,7 +181,13 @@ __global__ void __launch_bounds__(kV6Threads, NPAD <= 64 ? SPS_V6_CTAS_PER_SM : 
   constexpr int EPS = GPC < 8 ? 8 / GPC : 1;            // offsets per stage (Cin <= 16)
   constexpr int EPS2 = GPC2 ? 8 / GPC2 : 1;             // second segment: offsets per stage
   const int gpk2 = a.in2 ? ((a.cin2 * EB) >> 4) : 0;
-  const int st2 = (gpk2 + 7) >> 3;                      // stages of the fused 1x1 term
+  // The fused 1x1 term: a pseudo-offset appended to the tile's list of present offsets when its row fits the slot of an
+  // offset (several offsets per stage, Cin2 <= padded Cin) -- it then rides in the last, usually partial stage; otherwise
+  // stages of its own.
+  constexpr int kGpcDiv = GPC < 8 ? GPC : 1;
+  const int n2 = (GPC < 8 && GPC2 == 0 && gpk2 > 0 && gpk2 <= 8) ? (gpk2 + kGpcDiv - 1) / kGpcDiv : 0;   // slots it takes (a wide row: several)
+  const bool in2_packed = n2 > 0;
+  const int st2 = in2_packed ? 0 : (gpk2 + 7) >> 3;     // stages of the fused 1x1 term
   const uint32_t* tmask = a.tile_mask;
   const int gstep = gridDim.x;
   // tiles whose index slices fit in the staging area at once, and the bytes each takes
@@ -191,7 +197,7 @@ __global__ void __launch_bounds__(kV6Threads, NPAD <= 64 ? SPS_V6_CTAS_PER_SM : 
   auto tile_nact = [&](int tile) {
     return __popc(__ldg(tmask + 4 * tile)) + __popc(__ldg(tmask + 4 * tile + 1)) + __popc(__ldg(tmask + 4 * tile + 2));
   };
-  auto stages_a = [&](int nact) { return GPC < 8 ? (nact + EPS - 1) / EPS : nact * SPE; };
+  auto stages_a = [&](int nact) { return GPC < 8 ? (nact + n2 + EPS - 1) / EPS : nact * SPE; };
   auto stages_b = [&](int nact) { return GPC2 ? (nact + EPS2 - 1) / EPS2 : 0; };
   auto tile_stages = [&](int nact) { return stages_a(nact) + stages_b(nact) + st2; };
 
@@ -251,10 +257,18 @@ __global__ void __launch_bounds__(kV6Threads, NPAD <= 64 ? SPS_V6_CTAS_PER_SM : 
         if (GPC < 8) {
           const int ee = m * EPS + e_off;
           const bool e_ok = ee < nact;
-          lds4(sx + (uint32_t)(e_ok ? ee : 0) * kV6EntryBytes);
-          base = in_b + cg0 * 16; ld_b = in_ld_b;
-          okc = e_ok && cg0 < gpk; bok = e_ok;
-          wofs = (uint32_t)((int)kl[e_ok ? ee : 0] * GPCc + cg0) * 16u;
+          const bool e_in2 = ee >= nact && ee < nact + n2;  // the slots after the last present offset: the 1x1 term
+          lds4(sx + (uint32_t)(e_ok ? ee : (e_in2 ? nact : 0)) * kV6EntryBytes);
+          if (e_in2) {
+            const int cg = (ee - nact) * GPCc + cg0;        // group of the in2 row this column carries
+            base = in2_b + cg * 16; ld_b = in2_ld_b;
+            okc = cg < gpk2; bok = true;
+            wofs = (uint32_t)(K * GPCc + cg) * 16u;
+          } else {
+            base = in_b + cg0 * 16; ld_b = in_ld_b;
+            okc = e_ok && cg0 < gpk; bok = e_ok;
+            wofs = (uint32_t)((int)kl[e_ok ? ee : 0] * GPCc + cg0) * 16u;
+          }
           stage_tma = false;
         } else {
           // entry e = kernel offset klist[e], sub-stage `sub` of its SPE stages
@@ -441,6 +455,7 @@ __global__ void __launch_bounds__(kV6Threads, NPAD <= 64 ? SPS_V6_CTAS_PER_SM : 
       for (int it = 0; it < nstages; ++it, ++gs) {
         const uint32_t slot = gs % S;
         mbar_wait(bar_full + 8 * slot, (gs / S) & 1);
+        fence_proxy_async();   // the stage was written through the generic proxy (cp.async); the MMA reads it through the async proxy
         tc_fence_after();
         if (lane == 0) {
           const uint64_t adesc = make_smem_desc(sA_u + slot * kAStageBytes);

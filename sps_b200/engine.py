@@ -185,8 +185,10 @@ class Engine:
         if not ptr:
             raise ValueError(f"no '{kind}' map at level {L}")
         n = self.count(L)
-        full = self._read(ptr, K * v.ld, np.int32).reshape(K, v.ld)
-        return full[:, :n].copy()
+        out = np.empty((K, n), np.int32)
+        for k in range(K):      # row by row: the padding columns [n, ld) of the table are never written
+            out[k] = self._read(ptr + 4 * k * v.ld, n, np.int32)
+        return out
 
     def parent(self, L: int) -> np.ndarray:
         v = self.level(L)

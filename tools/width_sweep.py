@@ -36,7 +36,10 @@ def stress_input():
     from sps_b200.engine import MapHash
     world = synth.World(3)
     scan = synth.scan(world, "dense-128x4096", pose=(2.0, -1.0, 0.4), seed=3)
-    base = synth.base_map(world, "os1-128", n_poses=12, seed=3, voxel=VOXEL5)
+    # the static map around the scan at 0.05 m: 96 dense scans from poses spread over the crop disc (about a minute of host
+    # time) -> ~3 M map voxels inside the 30 m radius, 12.5 M in the whole base map
+    base = synth.base_map(world, "dense-128x4096", n_poses=int(os.environ.get("SPS_STRESS_POSES", "96")), seed=3, voxel=VOXEL5,
+                          jitter=20.0)
     mh = MapHash(torch.as_tensor(base).cuda(), VOXEL5)
     idx = mh.crop_radius((2.0, -1.0, 1.8), 30.0).cpu().numpy()
     return np.ascontiguousarray(synth.assemble(scan, base[idx])[:, :5])
