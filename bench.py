@@ -216,6 +216,11 @@ def measure_sizes(engine, points):
     return V, [pairs(L, 3) for L in range(5)], pairs(0, 5)
 
 
+# shared-memory fill rate of the LDGSTS path on one B200 (tools/gather4_probe.cu 64 0: rows resident in L1, so neither L2 nor
+# DRAM limits it): 8.77 TB/s with two 256-thread producer groups per SM, 4.95 TB/s with one
+LDGSTS_FILL_PEAK_GBS = 8770.0
+
+
 def tile_walk(engine, V):
     """Present kernel offsets of every 128-row tile of the 3x3x3x3 maps, per level, in the order the convolution walks them
     (sps_ctx_level.tile_mask: the shape-sorted order where the level was sorted).  Call after measure_sizes."""
@@ -606,10 +611,16 @@ def run_config2(args):
                                      "ldgsts_bound_ms": round(bound_ms, 4), "ldgsts_frac": round(bound_ms / rows[nm]["ms"], 3)})
                     t_lsu += bound_ms
             t_k3 = sum(rows[nm]["ms"] for nm in stg if nm in rows)
-            roof["staging"] = {"what": "81-offset layers: warp-wide 16-byte cp.async instructions into the A/B stages at 8 cycles "
-                                       "per instruction and SM (64 B/cycle/SM) -- the issue rate that bounds the gather",
-                               "layers": len(stg), "layers_ms": round(t_k3, 4), "bound_ms": round(t_lsu, 4),
-                               "frac": round(t_lsu / t_k3, 3) if t_k3 else None,
+            staged = sum(a["staged_bytes"] for nm, a in stg.items() if nm in rows)
+            roof["staging"] = {"what": "81-offset layers: bytes written into the shared-memory A stages by 16-byte cp.async (LDGSTS) copies, "
+                                       "absent and padded slots included -- the resource that bounds the gather",
+                               "layers": len(stg), "layers_ms": round(t_k3, 4),
+                               "staged_GBs": round(staged / (t_k3 * 1e-3) / 1e9, 1) if t_k3 else None,
+                               "peak_GBs": LDGSTS_FILL_PEAK_GBS,
+                               "frac": round(staged / (t_k3 * 1e-3) / 1e9 / LDGSTS_FILL_PEAK_GBS, 3) if t_k3 else None,
+                               "peak_source": "measured: tools/gather4_probe.cu (256 producer threads, L1-resident rows, 2 CTAs per SM), "
+                                              "profiles/r2_gather_probe.md",
+                               "issue_bound_ms": round(t_lsu, 4),
                                "tile_fill": {f"L{L}": round(P3[L] / max(int(nact[L].sum()) * 128, 1), 3) for L in range(4)}}
         result["roofline"] = roof
         result["stages"] = rows
