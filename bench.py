@@ -155,7 +155,7 @@ def stage_accounting(V, P3, P5, n_points, half_rows=True, planes=PLANES):
     Kernel maps: V * 20 (coordinates) + 8 * pairs (the pair-list form of §8d: what a present-only table holds)."""
     acc = {}
     cap = 1024
-    while cap < 2 * n_points:
+    while 2 * cap < 3 * n_points:      # csrc/common.cuh table_capacity: power of two >= 1.5 n
         cap *= 2
     acc["vox.clear"] = {"bytes": cap * 16}                       # the open-addressing table, 16-byte slots
     acc["vox.insert"] = {"bytes": n_points * 20 + n_points * 4}   # rows in, slot index out
