@@ -55,7 +55,7 @@ static size_t carve(sps_ctx* c, void* base, int64_t max_points) {
     c->tmask3[L] = cv.take<uint32_t>((size_t)(ld / 128 + 1) * 4);
     c->ptmask[L] = cv.take<uint32_t>((size_t)(ld / 128 + 1) * 4);
     c->perm[L] = cv.take<int32_t>(N);
-    c->tslice[L] = (L <= 3) ? cv.take<int32_t>((size_t)(ld / 128 + 1) * SPS_TILE_SLICE_ENTRIES * 128) : nullptr;
+    c->tslice[L] = (L <= 4) ? cv.take<int32_t>((size_t)(ld / 128 + 1) * SPS_TILE_SLICE_ENTRIES * 128) : nullptr;
     c->btab[L] = cv.take<Slot>(c->table_cap);
     c->bcells[L] = cv.take<int32_t>((size_t)N * 64);
     c->bocc[L] = cv.take<unsigned long long>(N);
@@ -67,11 +67,11 @@ static size_t carve(sps_ctx* c, void* base, int64_t max_points) {
   c->nbr5 = cv.take<int32_t>((size_t)125 * ld);
   c->tmask8 = cv.take<uint32_t>((size_t)(ld / 128 + 1) * 4);
   for (int j = 0; j < 2; ++j) {
-    c->sort_keys[j] = cv.take<uint32_t>((size_t)4 * N);
-    c->sort_vals[j] = cv.take<int32_t>((size_t)4 * N);
+    c->sort_keys[j] = cv.take<uint32_t>((size_t)SPS_NUM_LEVELS * N);
+    c->sort_vals[j] = cv.take<int32_t>((size_t)SPS_NUM_LEVELS * N);
   }
   c->sort_hist = cv.take<uint32_t>(1028);
-  c->sort_status = cv.take<uint32_t>(((size_t)4 * N / 1024 + 2) * 1024);
+  c->sort_status = cv.take<uint32_t>(((size_t)SPS_NUM_LEVELS * N / 1024 + 2) * 1024);
   for (int b = 0; b < sps_ctx::NBUF; ++b) c->buf[b] = cv.take<float>((size_t)N * kBufWidth[b]);
   return (cv.off + 255) & ~size_t(255);
 }

@@ -522,13 +522,15 @@ k_onesweep_pass(const SortArgs A, const uint32_t* __restrict__ keys, const int32
   __shared__ int s_base[256];                   // global position of this tile's first element per digit
   __shared__ int s_scan[kWarps];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int n = sort_total(A.counts, A.first, A.nlv);
+  const int ntiles = (n + kSortTile - 1) / kSortTile;
+  // the grid is sized by the host bound (rows x levels): the surplus blocks leave before touching anything, the first
+  // ntiles blocks take one ticket each
+  if ((int)blockIdx.x >= ntiles) return;
   if (tid == 0) s_tile = (int)atomicAdd(ticket, 1u);   // tiles are handed out in launch order: a tile's predecessors run
   for (int j = tid; j < kSlots * 128; j += kSortThreads) reinterpret_cast<uint32_t*>(&wcount[0][0])[j] = 0u;
   __syncthreads();
   const int tile = s_tile;
-  const int n = sort_total(A.counts, A.first, A.nlv);
-  const int ntiles = (n + kSortTile - 1) / kSortTile;
-  if (tile >= ntiles) return;
   uint32_t key[kSortItems];
   int val[kSortItems], rank[kSortItems];
 #pragma unroll
@@ -908,7 +910,7 @@ static const int g_tile_slices = SPS_TILE_SLICES;   // gather the kernel map per
 #endif
 constexpr int kFirstSortedLevel = SPS_FIRST_SORTED_LEVEL;
 #ifndef SPS_LAST_SORTED_LEVEL
-#define SPS_LAST_SORTED_LEVEL 3     // level 4 is too small: sorting it costs more than it saves
+#define SPS_LAST_SORTED_LEVEL 4     // all levels ride in the one concatenated sort (level 4 adds 2 % to its keys)
 #endif
 constexpr int kLastSortedLevel = SPS_LAST_SORTED_LEVEL;
 constexpr int kSortedLevels = kLastSortedLevel - kFirstSortedLevel + 1;
@@ -1031,7 +1033,7 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
   ctx->have_maps = true;
   ctx->dense_maps = O.dense_mask == (1 << SPS_NUM_LEVELS) - 1;
   ctx->have_perm = sorting;
-  ctx->have_slices = ctx->have_perm && g_tile_slices && kLastSortedLevel <= 3;
+  ctx->have_slices = ctx->have_perm && g_tile_slices && ctx->tslice[kLastSortedLevel] != nullptr;
   ctx->first_sorted = kFirstSortedLevel;
   ctx->last_sorted = kLastSortedLevel;
   return SPS_OK;
