@@ -48,6 +48,8 @@ struct sps_ctx {
   uint32_t* slot_of = nullptr; // [max_points]
   int32_t* rank = nullptr;     // [max_points]
   int32_t* block_sums = nullptr;
+  int32_t* lsum[SPS_NUM_LEVELS] = {};          // [L >= 2] block sums of level L's first-occurrence scan, kept: with them the level's
+                                               // voxel hash (built in btab[L - 2]) maps a key to its ROW, i.e. it is the block table of level L - 2
 
   unsigned long long* keys[SPS_NUM_LEVELS] = {};
   int32_t* inv = nullptr;                      // [max_points] point -> level-0 row
@@ -94,8 +96,6 @@ struct Conv0Fused {
 constexpr int kCatLd[4] = {16, SPS_CAT_PAD ? 32 : 24, SPS_CAT_PAD ? 64 : 48, SPS_CAT_PAD ? 128 : 96};   // CAT8, CAT7, CAT6, CAT5
 constexpr int kBufWidth[sps_ctx::NBUF] = {16, 8, 8, kCatLd[1], 8, 16, kCatLd[2], 16, 32, kCatLd[3], 32, 64, 64, 64, 64, 32, 32,
                                           16, 16, 8, 1, 1};
-// threads per block of the grid-wide scans: small enough (512 x ~31 registers) to co-run with another lane's convolution CTAs
-constexpr int kScanBlock = 512;
 
 // arithmetic mode of a context (see sps_ctx_set_conv_backend)
 inline bool ctx_half_storage(const sps_ctx* c) { return c->backend == SPS_BACKEND_AUTO || c->backend == SPS_BACKEND_F16; }

@@ -162,7 +162,10 @@ __global__ void k_assign_coarse(Slot* tab, const uint32_t* __restrict__ slot_of,
 struct LevelTabs {
   const unsigned long long* keys[SPS_NUM_LEVELS];
   const int32_t* counts;                 // [SPS_NUM_LEVELS] device voxel counts
-  Slot* btab[SPS_NUM_LEVELS];            // block key -> block id
+  Slot* btab[SPS_NUM_LEVELS];            // block key -> block id (own hash), or the voxel hash of level L + 2 (bsum != nullptr)
+  const int32_t* bsum[SPS_NUM_LEVELS];   // block sums that turn that voxel hash's slots into rows (common.cuh block_find), or nullptr
+  int capn[SPS_NUM_LEVELS];              // the table was sized for counts[capn[L]] keys
+  const int32_t* parent[SPS_NUM_LEVELS]; // fine row -> parent * 8 + k (levels 0..3)
   int32_t* cells[SPS_NUM_LEVELS];        // [blocks][64] voxel rows
   unsigned long long* occ[SPS_NUM_LEVELS];   // [blocks] 64-bit occupancy words
   int32_t* nblocks;                      // [SPS_NUM_LEVELS] block counters
@@ -185,11 +188,19 @@ __device__ __forceinline__ int sort_total(const int32_t* counts, int first, int 
 __global__ void k_blocks_begin(const LevelTabs T, const ScratchZero z) {
   const int L = blockIdx.y;
   const int n = T.counts[L];
-  const uint32_t cap = table_capacity(n);
-  const int4 empty = make_int4(-1, -1, -1, INT_MAX);
   const uint32_t stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
-  for (uint32_t i = t0; i < cap; i += stride) reinterpret_cast<int4*>(T.btab[L])[i] = empty;
-  if (t0 == 0) T.nblocks[L] = 0;
+  if (T.bsum[L]) {
+    // the blocks are the voxels of level L + 2 (their hash was built by the stride chain): only the occupancy words start
+    // from zero; every reader of the cells goes through them
+    const int nb = T.counts[L + 2];
+    for (uint32_t i = t0; i < (uint32_t)nb; i += stride) T.occ[L][i] = 0ull;
+    if (t0 == 0) T.nblocks[L] = nb;
+  } else {
+    const uint32_t cap = table_capacity(n);
+    const int4 empty = make_int4(-1, -1, -1, INT_MAX);
+    for (uint32_t i = t0; i < cap; i += stride) reinterpret_cast<int4*>(T.btab[L])[i] = empty;
+    if (t0 == 0) T.nblocks[L] = 0;
+  }
   if (z.tmask3[L]) {
     const uint32_t w = 4u * (uint32_t)(n / 128 + 1);
     for (uint32_t i = t0; i < w; i += stride) z.tmask3[L][i] = 0u;
@@ -213,6 +224,7 @@ k_block_insert(const LevelTabs T) {
   // global atomic.  The winner of a block also presets the block's 64 cells and its occupancy word.
   __shared__ int s_cnt, s_base;
   const int L = blockIdx.y;
+  if (T.bsum[L]) return;                 // blocks = voxels of level L + 2: nothing to insert
   const int n = T.counts[L];
   const uint32_t mask = table_capacity(n) - 1;
   Slot* tab = T.btab[L];
@@ -253,9 +265,12 @@ __global__ void k_cells_fill(const LevelTabs T) {
   const int n = T.counts[L];
   const uint32_t mask = table_capacity(n) - 1;
   const unsigned long long* keys = T.keys[L];
+  const bool by_parent = T.bsum[L] != nullptr;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const unsigned long long key = keys[i];
-    const int id = table_find(T.btab[L], mask, coarsen_key(key, L + 2));
+    // block id = the voxel's grandparent row (two reads of the parent arrays), or a lookup in the level's block hash
+    const int id = by_parent ? (__ldg(T.parent[L + 1] + (__ldg(T.parent[L] + i) >> 3)) >> 3)
+                             : table_find(T.btab[L], mask, coarsen_key(key, L + 2));
     const int l = cell_local(key, L);
     T.cells[L][(int64_t)id * 64 + l] = i;
     atomicOr(T.occ[L] + id, 1ull << l);     // 64-bit occupancy word per block: presence tests without the index read
@@ -268,13 +283,14 @@ __global__ void k_cells_fill(const LevelTabs T) {
 template <int K0, int KT>
 __global__ void __launch_bounds__(256)
 k_kernel_map_blk(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr,
-                 const Slot* __restrict__ tab, const int32_t* __restrict__ cells,
+                 const Slot* __restrict__ tab, const int32_t* __restrict__ cap_n, const int32_t* __restrict__ sums,
+                 const int32_t* __restrict__ cells,
                  const unsigned long long* __restrict__ occ, int L, int32_t* __restrict__ nbr, int64_t ld,
                  uint32_t* __restrict__ tile_masks, uint32_t* __restrict__ vmask) {
   const int n = *n_ptr;
   if (n == 0) return;
   constexpr int R = K0 / 2, K3 = K0 * K0 * K0;
-  const uint32_t mask = table_capacity(n) - 1;
+  const uint32_t mask = table_capacity(*cap_n) - 1;
   const int xlim = 1 << (kXBits - L), zlim = 1 << (kZBits - L);
   const int it = blockIdx.y;   // time plane of the kernel: t + (it - KT/2)
   const int lane = threadIdx.x & 31;
@@ -313,7 +329,7 @@ k_kernel_map_blk(const unsigned long long* __restrict__ keys, const int32_t* __r
             const unsigned long long bkey = byz | ((unsigned long long)(unsigned)((nx >> 2) << (L + 2)) << kXShift);
             if (bkey != cached_key) {
               cached_key = bkey;
-              const int id = table_find(tab, mask, bkey);
+              const int id = block_find(tab, mask, sums, bkey);
               cached = cells + (int64_t)(id >= 0 ? id : 0) * 64;
               cached_occ = id >= 0 ? __ldg(occ + id) : 0ull;
             }
@@ -367,7 +383,8 @@ k_kernel_map_blk3(const LevelTabs T, const KmapOut O) {
   uint32_t* __restrict__ vmask = O.vmask[L];
   const int64_t ld = O.ld;
   const int dense = (O.dense_mask >> L) & 1;
-  const uint32_t mask = table_capacity(n) - 1;
+  const uint32_t mask = table_capacity(T.counts[T.capn[L]]) - 1;
+  const int32_t* __restrict__ sums = T.bsum[L];
   const int xlim = 1 << (kXBits - L), zlim = 1 << (kZBits - L);
   const int it = blockIdx.y;   // time plane of the kernel: t + (it - KT/2)
   const int tid = threadIdx.x, lane = tid & 31;
@@ -399,7 +416,7 @@ k_kernel_map_blk3(const LevelTabs T, const KmapOut O) {
         const unsigned long long bkey = bt | ((unsigned long long)(unsigned)((bx >> 2) << (L + 2)) << kXShift) |
                                         ((unsigned long long)(unsigned)((by >> 2) << (L + 2)) << kYShift) |
                                         ((unsigned long long)(unsigned)((bz >> 2) << (L + 2)) << kZShift);
-        id = table_find(tab, mask, bkey);
+        id = block_find(tab, mask, sums, bkey);
         if (id >= 0) oc = __ldg(occ + id);
       }
       sId[j][tid] = id;
@@ -692,7 +709,8 @@ k_tile_masks_perm(const SliceArgs A) {
 // block: 8 block probes per voxel, no index reads at all; the weight sum goes through per-row tables.
 __global__ void __launch_bounds__(256)
 k_conv0_const(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr,
-              const Slot* __restrict__ tab, const unsigned long long* __restrict__ occ, float cfeat,
+              const Slot* __restrict__ tab, const int32_t* __restrict__ cap_n, const int32_t* __restrict__ sums,
+              const unsigned long long* __restrict__ occ, float cfeat,
               const float* __restrict__ w, const float* __restrict__ shift, int round_out, float* __restrict__ out,
               int64_t out_ld) {
   // row tables: T[row = (dz, dy)][5-bit x pattern][8] = sum of W[k][:] over the pattern's present dx.  A voxel then
@@ -709,7 +727,7 @@ k_conv0_const(const unsigned long long* __restrict__ keys, const int32_t* __rest
   __syncthreads();
   const int n = *n_ptr;
   if (n == 0) return;
-  const uint32_t mask = table_capacity(n) - 1;
+  const uint32_t mask = table_capacity(*cap_n) - 1;
   const int blim = 1 << (kXBits - 2), zblim = 1 << (kZBits - 2);
   for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += gridDim.x * blockDim.x) {
     const unsigned long long key = keys[o];
@@ -733,7 +751,7 @@ k_conv0_const(const unsigned long long* __restrict__ keys, const int32_t* __rest
       const unsigned long long bkey = bt | ((unsigned long long)(unsigned)(bx << 2) << kXShift) |
                                       ((unsigned long long)(unsigned)(by << 2) << kYShift) |
                                       ((unsigned long long)(unsigned)(bz << 2) << kZShift);
-      const int id = table_find(tab, mask, bkey);
+      const int id = block_find(tab, mask, sums, bkey);
       if (id < 0) continue;
       const unsigned long long m = __ldg(occ + id);
       const unsigned long long xmask = (1ull << (x_hi - x_lo + 1)) - 1ull;
@@ -777,7 +795,8 @@ k_conv0_const(const unsigned long long* __restrict__ keys, const int32_t* __rest
 // block table on the fly, so the 125 x V index table is neither written nor read back.
 __global__ void __launch_bounds__(256)
 k_conv0_blk(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr,
-            const Slot* __restrict__ tab, const int32_t* __restrict__ cells, const float* __restrict__ feat,
+            const Slot* __restrict__ tab, const int32_t* __restrict__ cap_n, const int32_t* __restrict__ sums,
+            const int32_t* __restrict__ cells, const unsigned long long* __restrict__ occ, const float* __restrict__ feat,
             const float* __restrict__ w, const float* __restrict__ shift, int round_out, float* __restrict__ out,
             int64_t out_ld) {
   __shared__ float w_s[125 * 8];
@@ -785,7 +804,7 @@ k_conv0_blk(const unsigned long long* __restrict__ keys, const int32_t* __restri
   __syncthreads();
   const int n = *n_ptr;
   if (n == 0) return;
-  const uint32_t mask = table_capacity(n) - 1;
+  const uint32_t mask = table_capacity(*cap_n) - 1;
   const int xlim = 1 << kXBits, zlim = 1 << kZBits;
   for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += gridDim.x * blockDim.x) {
     const unsigned long long key = keys[o];
@@ -793,7 +812,7 @@ k_conv0_blk(const unsigned long long* __restrict__ keys, const int32_t* __restri
     const int cy = (int)((key >> kYShift) & ((1u << kYBits) - 1));
     const int cz = (int)((key >> kZShift) & ((1u << kZBits) - 1));
     const unsigned long long bt = key & ((0xFFull << kBShift) | ((1ull << kTBits) - 1));
-    unsigned long long cached_key = kEmptyKey;
+    unsigned long long cached_key = kEmptyKey, cached_occ = 0ull;
     const int32_t* cached = nullptr;
     float acc[8];
 #pragma unroll
@@ -817,12 +836,13 @@ k_conv0_blk(const unsigned long long* __restrict__ keys, const int32_t* __restri
           const unsigned long long bkey = byz | ((unsigned long long)(unsigned)((nx >> 2) << 2) << kXShift);
           if (bkey != cached_key) {
             cached_key = bkey;
-            const int id = table_find(tab, mask, bkey);
+            const int id = block_find(tab, mask, sums, bkey);
             cached = id >= 0 ? cells + (int64_t)id * 64 : nullptr;
+            cached_occ = id >= 0 ? __ldg(occ + id) : 0ull;
           }
-          if (!cached) continue;
-          const int idx = __ldg(cached + lyz + (nx & 3));
-          if (idx < 0) continue;
+          const int l = lyz + (nx & 3);
+          if (!((cached_occ >> l) & 1ull)) continue;     // the cells of a block are only defined where its occupancy bit is set
+          const int idx = __ldg(cached + l);
           const float x = __ldg(feat + idx);
           const float4 w0 = *reinterpret_cast<const float4*>(wk + (dx + 2) * 8);
           const float4 w1 = *reinterpret_cast<const float4*>(wk + (dx + 2) * 8 + 4);
@@ -905,6 +925,10 @@ static inline bool needs_dense_maps(const sps_ctx* ctx) { return ctx->backend ==
 #define SPS_TILE_SLICES 1
 #endif
 static const int g_tile_slices = SPS_TILE_SLICES;   // gather the kernel map per sorted tile once per level
+#ifndef SPS_BLOCKS_FROM_LEVELS
+#define SPS_BLOCKS_FROM_LEVELS 1
+#endif
+static const int g_blocks_from_levels = SPS_BLOCKS_FROM_LEVELS;   // block tables of levels 0..2 = voxel hashes of levels 2..4
 #ifndef SPS_FIRST_SORTED_LEVEL
 #define SPS_FIRST_SORTED_LEVEL 0
 #endif
@@ -971,11 +995,16 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
   // ---- 1. strided coordinate sets, levels 1..4 (each level hashes the keys of the one below: a sequential chain) ----
   for (int L = 1; L < SPS_NUM_LEVELS; ++L) {
     const int32_t* n_fine = ctx->counts + (L - 1);
-    k_level_begin<<<grid_for(table_capacity(n), 256), 256, 0, st>>>(ctx->table, n_fine, -1, nullptr, ctx->child[L], ctx->ld);
-    k_insert_coarse<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[L - 1], n_fine, L, ctx->table, ctx->slot_of);
-    k_first_rank<<<nblk, kScanBlock, 0, st>>>(ctx->table, ctx->slot_of, n_fine, ctx->rank, ctx->block_sums,
+    // The voxels of level L are the 4x4x4-cell blocks of level L - 2: levels 2..4 build their hash where the block table
+    // of that level lives and keep the block sums of their scan, so the table answers "block key -> block row" later
+    // without a second hash build (k_block_insert was 100 us per forward).
+    Slot* tab = (g_blocks_from_levels && L >= 2) ? ctx->btab[L - 2] : ctx->table;
+    int32_t* sums = (g_blocks_from_levels && L >= 2) ? ctx->lsum[L] : ctx->block_sums;
+    k_level_begin<<<grid_for(table_capacity(n), 256), 256, 0, st>>>(tab, n_fine, -1, nullptr, ctx->child[L], ctx->ld);
+    k_insert_coarse<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[L - 1], n_fine, L, tab, ctx->slot_of);
+    k_first_rank<<<nblk, kScanBlock, 0, st>>>(tab, ctx->slot_of, n_fine, ctx->rank, sums,
                                               ctx->ticket, ctx->counts + L, nullptr, 0, nullptr);
-    k_assign_coarse<<<grid_for(n, 256), 256, 0, st>>>(ctx->table, ctx->slot_of, n_fine, ctx->rank, ctx->block_sums,
+    k_assign_coarse<<<grid_for(n, 256), 256, 0, st>>>(tab, ctx->slot_of, n_fine, ctx->rank, sums,
                                                        ctx->keys[L - 1], L - 1, ctx->keys[L], ctx->parent[L - 1],
                                                        ctx->child[L], ctx->upmap[L - 1], ctx->ld);
     static const char* nm_s[5] = {"", "stride.L1", "stride.L2", "stride.L3", "stride.L4"};
@@ -995,6 +1024,10 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
   O.dense_mask = 0;
   for (int L = 0; L < SPS_NUM_LEVELS; ++L) {
     T.keys[L] = ctx->keys[L]; T.btab[L] = ctx->btab[L]; T.cells[L] = ctx->bcells[L]; T.occ[L] = ctx->bocc[L];
+    const bool from_level = g_blocks_from_levels && L + 2 < SPS_NUM_LEVELS;
+    T.bsum[L] = from_level ? ctx->lsum[L + 2] : nullptr;
+    T.capn[L] = from_level ? L + 1 : L;      // level L + 2's hash was sized for the rows of level L + 1
+    T.parent[L] = ctx->parent[L];
     Z.tmask3[L] = sparse_ok(L) ? nullptr : ctx->tmask3[L];
     O.nbr[L] = ctx->nbr3[L]; O.tile_masks[L] = Z.tmask3[L]; O.vmask[L] = ctx->vmask[L];
     if (!sparse_ok(L)) O.dense_mask |= 1 << L;
@@ -1011,14 +1044,14 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
   // ---- 3. conv0 off the level-0 block table (fused forward), or the 5x5x5x1 table (layer-level API) ----
   if (c0) {
     if (c0->feat)   // per-voxel features: gather them through the block table
-      k_conv0_blk<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->btab[0], ctx->bcells[0], c0->feat,
+      k_conv0_blk<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->btab[0], ctx->counts + T.capn[0], T.bsum[0], ctx->bcells[0], ctx->bocc[0], c0->feat,
                                                      c0->w, c0->shift, c0->round_out, c0->out, c0->out_ld);
     else            // one constant feature (SPSModel.forward): presence bits only
-      k_conv0_const<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->btab[0], ctx->bocc[0], c0->cfeat,
+      k_conv0_const<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->btab[0], ctx->counts + T.capn[0], T.bsum[0], ctx->bocc[0], c0->cfeat,
                                                        c0->w, c0->shift, c0->round_out, c0->out, c0->out_ld);
     prof_mark(ctx, "conv0+kmap5", st);
   } else {
-    k_kernel_map_blk<5, 1><<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->btab[0], ctx->bcells[0], ctx->bocc[0], 0,
+    k_kernel_map_blk<5, 1><<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->btab[0], ctx->counts + T.capn[0], T.bsum[0], ctx->bcells[0], ctx->bocc[0], 0,
                                                               ctx->nbr5, ctx->ld, nullptr, nullptr);
     prof_mark(ctx, "kmap5.L0", st);
   }
