@@ -172,6 +172,7 @@ def stage_accounting(V, P3, P5, n_points, half_rows=True, planes=PLANES):
     for L in range(4):   # shape sort (key + row index in, row index out) and per-tile slices (present entries x 4 B, read + write)
         acc[f"sort.L{L}"] = {"bytes": V[L] * 12 + V[L] * 4}
         acc[f"slices.L{L}"] = {"bytes": 2 * 4 * P3[L] + V[L] * 16}
+    acc["up_order"] = {"bytes": sum(V[L] * 8 for L in range(4))}       # parent word in, row index out (class order of the transposed convs)
     acc["blocks"] = {"bytes": sum(V[L] * 12 for L in range(5))}
     acc["kmap3"] = {"bytes": sum(V[L] * 20 + 8 * P3[L] for L in range(5))}
     acc["sort"] = {"bytes": sum(V[L] * 16 for L in range(4))}

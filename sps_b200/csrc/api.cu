@@ -40,6 +40,7 @@ static size_t carve(sps_ctx* c, void* base, int64_t max_points) {
   c->ticket = reinterpret_cast<uint32_t*>(c->counts + 32);
   c->nblocks = c->counts + 64;
   c->tplanes = c->counts + 160;
+  c->up_cls = c->counts + 192;
   c->status = c->counts + 96;
   c->staging = cv.take<float>((size_t)N * 8);
   c->scores = cv.take<float>(N);
@@ -64,6 +65,8 @@ static size_t carve(sps_ctx* c, void* base, int64_t max_points) {
     c->parent[L] = (L < SPS_NUM_LEVELS - 1) ? cv.take<int32_t>(N) : nullptr;
     c->child[L] = (L > 0) ? cv.take<int32_t>((size_t)8 * ld) : nullptr;
     c->upmap[L] = (L < SPS_NUM_LEVELS - 1) ? cv.take<int32_t>((size_t)8 * ld) : nullptr;
+    c->perm_up[L] = (L < SPS_NUM_LEVELS - 1) ? cv.take<int32_t>(N) : nullptr;
+    c->tmask_up[L] = (L < SPS_NUM_LEVELS - 1) ? cv.take<uint32_t>((size_t)(ld / 128 + 1) * 4) : nullptr;
   }
   c->nbr5 = cv.take<int32_t>((size_t)125 * ld);
   c->tmask8 = cv.take<uint32_t>((size_t)(ld / 128 + 1) * 4);

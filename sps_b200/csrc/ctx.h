@@ -66,6 +66,9 @@ struct sps_ctx {
   int32_t* sort_vals[2] = {};
   uint32_t* sort_hist = nullptr;
   uint32_t* sort_status = nullptr;
+  int32_t* up_cls = nullptr;                   // [4][16] per fine level: rows per 2x2x2 child class (8) + scatter cursors (8)
+  int32_t* perm_up[SPS_NUM_LEVELS] = {};       // [L] rows of level L grouped by child class: processing order of the transposed conv INTO level L
+  uint32_t* tmask_up[SPS_NUM_LEVELS] = {};     // [L] tile masks of upmap[L] in that order (one or two classes per tile)
   uint32_t* tmask8 = nullptr;                  // [tiles][4] all-eight-offsets mask for the 2x2x2x1 maps
   int32_t* nbr3[SPS_NUM_LEVELS] = {};          // [81][ld]
   int32_t* nbr5 = nullptr;                     // [125][ld]

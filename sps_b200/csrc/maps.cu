@@ -23,10 +23,11 @@ __global__ void k_set_i32(int32_t* p, int32_t v) { *p = v; }
 // child table of the level being built to "absent" for every column a coarse row can take (coarse count <= fine count).
 // n comes from the device (`n_ptr`) or, at level 0, from the host (`n_host` >= 0, also published to `n_dev`).
 __global__ void k_level_begin(Slot* __restrict__ tab, const int32_t* __restrict__ n_ptr, int32_t n_host, int32_t* n_dev,
-                              int32_t* __restrict__ child, int64_t ld, int32_t* tplanes = nullptr) {
+                              int32_t* __restrict__ child, int64_t ld, int32_t* tplanes = nullptr, int32_t* cls = nullptr) {
   const int n = n_host >= 0 ? n_host : *n_ptr;
   if (n_dev && blockIdx.x == 0 && threadIdx.x == 0) *n_dev = n;
   if (tplanes && blockIdx.x == 0 && threadIdx.x == 0) *tplanes = 0;
+  if (cls && blockIdx.x == 0 && threadIdx.x < 16) cls[threadIdx.x] = 0;     // child-class counters of the fine level
   const uint32_t cap = table_capacity(n);
   const int4 empty = make_int4(-1, -1, -1, INT_MAX);
   const uint32_t stride = gridDim.x * blockDim.x;
@@ -134,7 +135,11 @@ __global__ void k_assign_coarse(Slot* tab, const uint32_t* __restrict__ slot_of,
                                 const int32_t* __restrict__ rank, const int32_t* __restrict__ block_sums,
                                 const unsigned long long* __restrict__ fine, int log2s,
                                 unsigned long long* __restrict__ ukeys, int32_t* __restrict__ parent,
-                                int32_t* __restrict__ child, int32_t* __restrict__ upmap, int64_t ld) {
+                                int32_t* __restrict__ child, int32_t* __restrict__ upmap, int64_t ld,
+                                int32_t* __restrict__ cls) {
+  __shared__ int s_cls[8];
+  if (threadIdx.x < 8) s_cls[threadIdx.x] = 0;
+  __syncthreads();
   const int n = *n_ptr;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t s = slot_of[i];
@@ -142,6 +147,7 @@ __global__ void k_assign_coarse(Slot* tab, const uint32_t* __restrict__ slot_of,
     const int f = raw.w;
     const int id = raw.z + block_sums[f / kScanBlock];
     const int k = child_index(fine[i], log2s);
+    atomicAdd(&s_cls[k], 1);                                    // rows per child class (order of the transposed conv)
     parent[i] = id * 8 + k;
     child[(int64_t)k * ld + id] = i;
     // transposed-conv kernel map in the dense [8][ld] form the tensor-core kernel walks:
@@ -149,6 +155,62 @@ __global__ void k_assign_coarse(Slot* tab, const uint32_t* __restrict__ slot_of,
 #pragma unroll
     for (int kk = 0; kk < 8; ++kk) upmap[(int64_t)kk * ld + i] = kk == k ? id : -1;
     if (f == i) ukeys[id] = ((unsigned long long)(unsigned)raw.y << 32) | (unsigned)raw.x;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8 && s_cls[threadIdx.x]) atomicAdd(cls + threadIdx.x, s_cls[threadIdx.x]);
+}
+
+// Processing order of the transposed convolutions (minkunet.py:107-147): a fine row has exactly ONE input row (its parent)
+// and one of eight weight matrices (its child class k), so in physical order every 128-row tile walks all eight offsets
+// with one slot in eight filled.  Grouped by class a tile walks one offset (two where a class ends).  The order inside a
+// class is whatever the atomics give: every output row is computed on its own, so results do not depend on it.
+struct UpOrderArgs {
+  const int32_t* parent[SPS_NUM_LEVELS];
+  int32_t* perm[SPS_NUM_LEVELS];
+  uint32_t* masks[SPS_NUM_LEVELS];
+  const int32_t* counts;
+  int32_t* cls;           // [4][16]: class counts, cursors
+};
+__global__ void __launch_bounds__(256)
+k_up_order(const UpOrderArgs A) {
+  const int L = blockIdx.y;
+  const int n = A.counts[L];
+  int32_t* cls = A.cls + 16 * L;
+  __shared__ int s_base[9], s_cnt[8], s_cur[8];
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int k = 0; k < 8; ++k) { s_base[k] = run; run += cls[k]; }
+    s_base[8] = run;
+  }
+  if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  // each block owns one contiguous chunk of rows: count its classes, take its eight ranges with ONE global atomic per
+  // class (a cursor per row, even warp-aggregated, serialises on eight addresses), then scatter
+  const int lane = threadIdx.x & 31;
+  const int chunk = ((n + (int)gridDim.x - 1) / (int)gridDim.x + 31) & ~31;
+  const int r0 = blockIdx.x * chunk, r1 = min(n, r0 + chunk);
+  const int32_t* __restrict__ parent = A.parent[L];
+  for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x) atomicAdd(&s_cnt[__ldg(parent + i) & 7], 1);
+  __syncthreads();
+  if (threadIdx.x < 8) s_cur[threadIdx.x] = s_base[threadIdx.x] + (s_cnt[threadIdx.x] ? atomicAdd(cls + 8 + threadIdx.x, s_cnt[threadIdx.x]) : 0);
+  __syncthreads();
+  for (int i0 = r0 + (threadIdx.x & ~31); i0 < r1; i0 += blockDim.x) {
+    const int i = i0 + lane;
+    const int k = i < r1 ? (__ldg(parent + i) & 7) : 8 + lane;          // dead lanes match nobody
+    const unsigned peers = __match_any_sync(0xffffffffu, k);
+    const int leader = __ffs(peers) - 1;
+    int pos = 0;
+    if (lane == leader && i < r1) pos = atomicAdd(&s_cur[k], __popc(peers));
+    pos = __shfl_sync(0xffffffffu, pos, leader);
+    if (i < r1) A.perm[L][pos + __popc(peers & ((1u << lane) - 1u))] = i;
+  }
+  // tile masks in this order: the classes whose row range meets the tile
+  const int ntiles = (n + 127) / 128;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ntiles; t += gridDim.x * blockDim.x) {
+    uint32_t m = 0;
+    for (int k = 0; k < 8; ++k)
+      if (s_base[k] < 128 * (t + 1) && s_base[k + 1] > 128 * t) m |= 1u << k;
+    reinterpret_cast<uint4*>(A.masks[L])[t] = make_uint4(m, 0u, 0u, 0u);
   }
 }
 
@@ -1000,15 +1062,23 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
     // without a second hash build (k_block_insert was 100 us per forward).
     Slot* tab = (g_blocks_from_levels && L >= 2) ? ctx->btab[L - 2] : ctx->table;
     int32_t* sums = (g_blocks_from_levels && L >= 2) ? ctx->lsum[L] : ctx->block_sums;
-    k_level_begin<<<grid_for(table_capacity(n), 256), 256, 0, st>>>(tab, n_fine, -1, nullptr, ctx->child[L], ctx->ld);
+    k_level_begin<<<grid_for(table_capacity(n), 256), 256, 0, st>>>(tab, n_fine, -1, nullptr, ctx->child[L], ctx->ld, nullptr,
+                                                                    ctx->up_cls + 16 * (L - 1));
     k_insert_coarse<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[L - 1], n_fine, L, tab, ctx->slot_of);
     k_first_rank<<<nblk, kScanBlock, 0, st>>>(tab, ctx->slot_of, n_fine, ctx->rank, sums,
                                               ctx->ticket, ctx->counts + L, nullptr, 0, nullptr);
     k_assign_coarse<<<grid_for(n, 256), 256, 0, st>>>(tab, ctx->slot_of, n_fine, ctx->rank, sums,
                                                        ctx->keys[L - 1], L - 1, ctx->keys[L], ctx->parent[L - 1],
-                                                       ctx->child[L], ctx->upmap[L - 1], ctx->ld);
+                                                       ctx->child[L], ctx->upmap[L - 1], ctx->ld, ctx->up_cls + 16 * (L - 1));
     static const char* nm_s[5] = {"", "stride.L1", "stride.L2", "stride.L3", "stride.L4"};
     prof_mark(ctx, nm_s[L], st);
+  }
+  {   // class order of the fine rows of levels 0..3 for the transposed convolutions (one launch)
+    UpOrderArgs U;
+    for (int L = 0; L < SPS_NUM_LEVELS; ++L) { U.parent[L] = ctx->parent[L]; U.perm[L] = ctx->perm_up[L]; U.masks[L] = ctx->tmask_up[L]; }
+    U.counts = ctx->counts; U.cls = ctx->up_cls;
+    k_up_order<<<dim3(grid_for(n, 256, 148 * 4), SPS_NUM_LEVELS - 1), 256, 0, st>>>(U);
+    prof_mark(ctx, "up_order", st);
   }
   // ---- 2. block tables of all five levels (three launches) ----
   // fused forward on a shape-sorted level: the convolutions read the tile slices and the sorted tile masks, the slices
@@ -1060,7 +1130,7 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
   k_kernel_map_blk3<3><<<dim3(gx, 3, SPS_NUM_LEVELS), 256, 0, st>>>(T, O);
   prof_mark(ctx, "kmap3", st);
   SPS_CUDA_CHECK(cudaGetLastError());
-  ctx->forward_launches += 16 + 3 + 1 + 1;
+  ctx->forward_launches += 16 + 1 + 3 + 1 + 1;
   // ---- 5. shape sort + per-tile slices of the sorted levels ----
   { const int rc = pattern_order(ctx, st); if (rc != SPS_OK) return rc; }
   ctx->have_maps = true;

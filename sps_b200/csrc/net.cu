@@ -383,7 +383,8 @@ int unet_forward(sps_ctx* c, const sps_net* net, const float* feat0, float* logi
       RUN(ConvIo{nullptr, nullptr, nullptr, SPS_CONV_UP, c->child[L + 1]}, nm_up[i], net->up[i], c->counts + L + 1, nmax, dec_in, none,
           none, cat[L], st);
     } else {       // the same transposed conv as an 8-offset gather map of the fine rows
-      RUN(ConvIo{c->tmask8, nullptr, nullptr, SPS_CONV_NBR, c->upmap[L]}, nm_up[i], net->up[i], c->counts + L, nmax, dec_in, none, none,
+      // rows visited by child class (perm_up): a tile walks one of the eight offsets instead of all of them
+      RUN(ConvIo{c->tmask_up[L], c->perm_up[L], nullptr, SPS_CONV_NBR, c->upmap[L]}, nm_up[i], net->up[i], c->counts + L, nmax, dec_in, none, none,
           cat[L], st);
     }
     const ConvW& c1 = net->blk1[4 + i];
