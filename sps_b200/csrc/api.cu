@@ -49,7 +49,6 @@ static size_t carve(sps_ctx* c, void* base, int64_t max_points) {
   c->slot_of = cv.take<uint32_t>(N);
   c->rank = cv.take<int32_t>(N);
   c->block_sums = cv.take<int32_t>(N / kScanBlock + 2);
-  for (int L = 2; L < SPS_NUM_LEVELS; ++L) c->lsum[L] = cv.take<int32_t>(N / kScanBlock + 2);
   c->inv = cv.take<int32_t>(N);
   for (int L = 0; L < SPS_NUM_LEVELS; ++L) {
     c->keys[L] = cv.take<unsigned long long>(N);

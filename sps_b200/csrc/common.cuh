@@ -137,21 +137,6 @@ __device__ inline int table_find(const Slot* __restrict__ tab, uint32_t mask, un
 // threads per block of the grid-wide scans: small enough (512 x ~31 registers) to co-run with another lane's convolution CTAs
 constexpr int kScanBlock = 512;
 
-// Block lookup.  sums == nullptr: `tab` is a block hash (val = block id).  Otherwise `tab` is the voxel hash of the level
-// two strides up, whose voxels ARE the 4x4x4 blocks of this level: slot = {key, block-local rank of the first occurrence,
-// first occurrence}, and the block id is the voxel's row = rank + sums[first / kScanBlock] (the scan's block sums).
-__device__ inline int block_find(const Slot* __restrict__ tab, uint32_t mask, const int32_t* __restrict__ sums,
-                                 unsigned long long key) {
-  uint32_t s = hash_key(key) & mask;
-  while (true) {
-    const int4 raw = __ldg(reinterpret_cast<const int4*>(tab + s));
-    unsigned long long k = ((unsigned long long)(unsigned)raw.y << 32) | (unsigned)raw.x;
-    if (k == key) return sums ? raw.z + __ldg(sums + raw.w / kScanBlock) : raw.z;
-    if (k == kEmptyKey) return -1;
-    s = (s + 1) & mask;
-  }
-}
-
 // returns the slot index of `key` (inserting it if absent)
 __device__ inline uint32_t table_insert(Slot* tab, uint32_t mask, unsigned long long key) {
   uint32_t s = hash_key(key) & mask;

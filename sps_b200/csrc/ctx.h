@@ -48,8 +48,6 @@ struct sps_ctx {
   uint32_t* slot_of = nullptr; // [max_points]
   int32_t* rank = nullptr;     // [max_points]
   int32_t* block_sums = nullptr;
-  int32_t* lsum[SPS_NUM_LEVELS] = {};          // [L >= 2] block sums of level L's first-occurrence scan, kept: with them the level's
-                                               // voxel hash (built in btab[L - 2]) maps a key to its ROW, i.e. it is the block table of level L - 2
 
   unsigned long long* keys[SPS_NUM_LEVELS] = {};
   int32_t* inv = nullptr;                      // [max_points] point -> level-0 row

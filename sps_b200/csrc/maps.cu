@@ -224,8 +224,8 @@ k_up_order(const UpOrderArgs A) {
 struct LevelTabs {
   const unsigned long long* keys[SPS_NUM_LEVELS];
   const int32_t* counts;                 // [SPS_NUM_LEVELS] device voxel counts
-  Slot* btab[SPS_NUM_LEVELS];            // block key -> block id (own hash), or the voxel hash of level L + 2 (bsum != nullptr)
-  const int32_t* bsum[SPS_NUM_LEVELS];   // block sums that turn that voxel hash's slots into rows (common.cuh block_find), or nullptr
+  Slot* btab[SPS_NUM_LEVELS];            // block key -> block id (own hash), or the voxel hash of level L + 2 (from_level)
+  int from_level[SPS_NUM_LEVELS];        // 1: btab[L] is the voxel hash of level L + 2 (its voxels are this level's blocks)
   int capn[SPS_NUM_LEVELS];              // the table was sized for counts[capn[L]] keys
   const int32_t* parent[SPS_NUM_LEVELS]; // fine row -> parent * 8 + k (levels 0..3)
   int32_t* cells[SPS_NUM_LEVELS];        // [blocks][64] voxel rows
@@ -251,11 +251,21 @@ __global__ void k_blocks_begin(const LevelTabs T, const ScratchZero z) {
   const int L = blockIdx.y;
   const int n = T.counts[L];
   const uint32_t stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
-  if (T.bsum[L]) {
-    // the blocks are the voxels of level L + 2 (their hash was built by the stride chain): only the occupancy words start
-    // from zero; every reader of the cells goes through them
+  if (T.from_level[L]) {
+    // the blocks are the voxels of level L + 2 and their hash was built by the stride chain: its slots still hold the
+    // scan's block-local ranks, so every voxel writes its ROW into its slot (one probe each) -- from here on the table maps
+    // a block key to the block id.  Only the occupancy words start from zero: every reader of the cells goes through them.
     const int nb = T.counts[L + 2];
-    for (uint32_t i = t0; i < (uint32_t)nb; i += stride) T.occ[L][i] = 0ull;
+    const uint32_t mask = table_capacity(T.counts[T.capn[L]]) - 1;
+    const unsigned long long* __restrict__ bkeys = T.keys[L + 2];
+    Slot* tab = T.btab[L];
+    for (uint32_t i = t0; i < (uint32_t)nb; i += stride) {
+      T.occ[L][i] = 0ull;
+      const unsigned long long key = bkeys[i];
+      uint32_t s = hash_key(key) & mask;
+      while (tab[s].key != key) s = (s + 1) & mask;
+      tab[s].val = (int)i;
+    }
     if (t0 == 0) T.nblocks[L] = nb;
   } else {
     const uint32_t cap = table_capacity(n);
@@ -286,7 +296,7 @@ k_block_insert(const LevelTabs T) {
   // global atomic.  The winner of a block also presets the block's 64 cells and its occupancy word.
   __shared__ int s_cnt, s_base;
   const int L = blockIdx.y;
-  if (T.bsum[L]) return;                 // blocks = voxels of level L + 2: nothing to insert
+  if (T.from_level[L]) return;           // blocks = voxels of level L + 2: nothing to insert
   const int n = T.counts[L];
   const uint32_t mask = table_capacity(n) - 1;
   Slot* tab = T.btab[L];
@@ -327,7 +337,7 @@ __global__ void k_cells_fill(const LevelTabs T) {
   const int n = T.counts[L];
   const uint32_t mask = table_capacity(n) - 1;
   const unsigned long long* keys = T.keys[L];
-  const bool by_parent = T.bsum[L] != nullptr;
+  const bool by_parent = T.from_level[L] != 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const unsigned long long key = keys[i];
     // block id = the voxel's grandparent row (two reads of the parent arrays), or a lookup in the level's block hash
@@ -345,8 +355,7 @@ __global__ void k_cells_fill(const LevelTabs T) {
 template <int K0, int KT>
 __global__ void __launch_bounds__(256)
 k_kernel_map_blk(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr,
-                 const Slot* __restrict__ tab, const int32_t* __restrict__ cap_n, const int32_t* __restrict__ sums,
-                 const int32_t* __restrict__ cells,
+                 const Slot* __restrict__ tab, const int32_t* __restrict__ cap_n, const int32_t* __restrict__ cells,
                  const unsigned long long* __restrict__ occ, int L, int32_t* __restrict__ nbr, int64_t ld,
                  uint32_t* __restrict__ tile_masks, uint32_t* __restrict__ vmask) {
   const int n = *n_ptr;
@@ -391,7 +400,7 @@ k_kernel_map_blk(const unsigned long long* __restrict__ keys, const int32_t* __r
             const unsigned long long bkey = byz | ((unsigned long long)(unsigned)((nx >> 2) << (L + 2)) << kXShift);
             if (bkey != cached_key) {
               cached_key = bkey;
-              const int id = block_find(tab, mask, sums, bkey);
+              const int id = table_find(tab, mask, bkey);
               cached = cells + (int64_t)(id >= 0 ? id : 0) * 64;
               cached_occ = id >= 0 ? __ldg(occ + id) : 0ull;
             }
@@ -446,7 +455,6 @@ k_kernel_map_blk3(const LevelTabs T, const KmapOut O) {
   const int64_t ld = O.ld;
   const int dense = (O.dense_mask >> L) & 1;
   const uint32_t mask = table_capacity(T.counts[T.capn[L]]) - 1;
-  const int32_t* __restrict__ sums = T.bsum[L];
   const int xlim = 1 << (kXBits - L), zlim = 1 << (kZBits - L);
   const int it = blockIdx.y;   // time plane of the kernel: t + (it - KT/2)
   const int tid = threadIdx.x, lane = tid & 31;
@@ -478,7 +486,7 @@ k_kernel_map_blk3(const LevelTabs T, const KmapOut O) {
         const unsigned long long bkey = bt | ((unsigned long long)(unsigned)((bx >> 2) << (L + 2)) << kXShift) |
                                         ((unsigned long long)(unsigned)((by >> 2) << (L + 2)) << kYShift) |
                                         ((unsigned long long)(unsigned)((bz >> 2) << (L + 2)) << kZShift);
-        id = block_find(tab, mask, sums, bkey);
+        id = table_find(tab, mask, bkey);
         if (id >= 0) oc = __ldg(occ + id);
       }
       sId[j][tid] = id;
@@ -771,7 +779,7 @@ k_tile_masks_perm(const SliceArgs A) {
 // block: 8 block probes per voxel, no index reads at all; the weight sum goes through per-row tables.
 __global__ void __launch_bounds__(256)
 k_conv0_const(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr,
-              const Slot* __restrict__ tab, const int32_t* __restrict__ cap_n, const int32_t* __restrict__ sums,
+              const Slot* __restrict__ tab, const int32_t* __restrict__ cap_n,
               const unsigned long long* __restrict__ occ, float cfeat,
               const float* __restrict__ w, const float* __restrict__ shift, int round_out, float* __restrict__ out,
               int64_t out_ld) {
@@ -813,7 +821,7 @@ k_conv0_const(const unsigned long long* __restrict__ keys, const int32_t* __rest
       const unsigned long long bkey = bt | ((unsigned long long)(unsigned)(bx << 2) << kXShift) |
                                       ((unsigned long long)(unsigned)(by << 2) << kYShift) |
                                       ((unsigned long long)(unsigned)(bz << 2) << kZShift);
-      const int id = block_find(tab, mask, sums, bkey);
+      const int id = table_find(tab, mask, bkey);
       if (id < 0) continue;
       const unsigned long long m = __ldg(occ + id);
       const unsigned long long xmask = (1ull << (x_hi - x_lo + 1)) - 1ull;
@@ -857,7 +865,7 @@ k_conv0_const(const unsigned long long* __restrict__ keys, const int32_t* __rest
 // block table on the fly, so the 125 x V index table is neither written nor read back.
 __global__ void __launch_bounds__(256)
 k_conv0_blk(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr,
-            const Slot* __restrict__ tab, const int32_t* __restrict__ cap_n, const int32_t* __restrict__ sums,
+            const Slot* __restrict__ tab, const int32_t* __restrict__ cap_n,
             const int32_t* __restrict__ cells, const unsigned long long* __restrict__ occ, const float* __restrict__ feat,
             const float* __restrict__ w, const float* __restrict__ shift, int round_out, float* __restrict__ out,
             int64_t out_ld) {
@@ -898,7 +906,7 @@ k_conv0_blk(const unsigned long long* __restrict__ keys, const int32_t* __restri
           const unsigned long long bkey = byz | ((unsigned long long)(unsigned)((nx >> 2) << 2) << kXShift);
           if (bkey != cached_key) {
             cached_key = bkey;
-            const int id = block_find(tab, mask, sums, bkey);
+            const int id = table_find(tab, mask, bkey);
             cached = id >= 0 ? cells + (int64_t)id * 64 : nullptr;
             cached_occ = id >= 0 ? __ldg(occ + id) : 0ull;
           }
@@ -1058,10 +1066,10 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
   for (int L = 1; L < SPS_NUM_LEVELS; ++L) {
     const int32_t* n_fine = ctx->counts + (L - 1);
     // The voxels of level L are the 4x4x4-cell blocks of level L - 2: levels 2..4 build their hash where the block table
-    // of that level lives and keep the block sums of their scan, so the table answers "block key -> block row" later
-    // without a second hash build (k_block_insert was 100 us per forward).
+    // of that level lives, so that it answers "block key -> block row" later without a second hash build
+    // (k_block_insert was 100 us per forward); k_blocks_begin writes the rows into the slots.
     Slot* tab = (g_blocks_from_levels && L >= 2) ? ctx->btab[L - 2] : ctx->table;
-    int32_t* sums = (g_blocks_from_levels && L >= 2) ? ctx->lsum[L] : ctx->block_sums;
+    int32_t* sums = ctx->block_sums;
     k_level_begin<<<grid_for(table_capacity(n), 256), 256, 0, st>>>(tab, n_fine, -1, nullptr, ctx->child[L], ctx->ld, nullptr,
                                                                     ctx->up_cls + 16 * (L - 1));
     k_insert_coarse<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[L - 1], n_fine, L, tab, ctx->slot_of);
@@ -1095,7 +1103,7 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
   for (int L = 0; L < SPS_NUM_LEVELS; ++L) {
     T.keys[L] = ctx->keys[L]; T.btab[L] = ctx->btab[L]; T.cells[L] = ctx->bcells[L]; T.occ[L] = ctx->bocc[L];
     const bool from_level = g_blocks_from_levels && L + 2 < SPS_NUM_LEVELS;
-    T.bsum[L] = from_level ? ctx->lsum[L + 2] : nullptr;
+    T.from_level[L] = from_level ? 1 : 0;
     T.capn[L] = from_level ? L + 1 : L;      // level L + 2's hash was sized for the rows of level L + 1
     T.parent[L] = ctx->parent[L];
     Z.tmask3[L] = sparse_ok(L) ? nullptr : ctx->tmask3[L];
@@ -1114,14 +1122,14 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
   // ---- 3. conv0 off the level-0 block table (fused forward), or the 5x5x5x1 table (layer-level API) ----
   if (c0) {
     if (c0->feat)   // per-voxel features: gather them through the block table
-      k_conv0_blk<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->btab[0], ctx->counts + T.capn[0], T.bsum[0], ctx->bcells[0], ctx->bocc[0], c0->feat,
+      k_conv0_blk<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->btab[0], ctx->counts + T.capn[0], ctx->bcells[0], ctx->bocc[0], c0->feat,
                                                      c0->w, c0->shift, c0->round_out, c0->out, c0->out_ld);
     else            // one constant feature (SPSModel.forward): presence bits only
-      k_conv0_const<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->btab[0], ctx->counts + T.capn[0], T.bsum[0], ctx->bocc[0], c0->cfeat,
+      k_conv0_const<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->btab[0], ctx->counts + T.capn[0], ctx->bocc[0], c0->cfeat,
                                                        c0->w, c0->shift, c0->round_out, c0->out, c0->out_ld);
     prof_mark(ctx, "conv0+kmap5", st);
   } else {
-    k_kernel_map_blk<5, 1><<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->btab[0], ctx->counts + T.capn[0], T.bsum[0], ctx->bcells[0], ctx->bocc[0], 0,
+    k_kernel_map_blk<5, 1><<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[0], ctx->counts + 0, ctx->btab[0], ctx->counts + T.capn[0], ctx->bcells[0], ctx->bocc[0], 0,
                                                               ctx->nbr5, ctx->ld, nullptr, nullptr);
     prof_mark(ctx, "kmap5.L0", st);
   }
