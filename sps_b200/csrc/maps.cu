@@ -466,6 +466,18 @@ k_kernel_map_blk3(const LevelTabs T, const KmapOut O) {
     const int t2 = (int)(key & ((1u << kTBits) - 1)) + it - KT / 2;
     const bool pok = live && (unsigned)t2 < (1u << kTBits) && ((planes >> t2) & 1u);   // empty time planes are not probed
     int32_t* out = nbr + (int64_t)it * 27 * ld + o;
+    if (!__any_sync(0xffffffffu, pok)) {
+      // no row of this warp has the time plane (rows of one scan / one submap are contiguous, so a third of the warps end
+      // here: the map rows have no t - 1 plane, the scan rows no t + 1 plane): nothing to probe, nothing present
+      if (live) {
+        if (dense) {
+#pragma unroll
+          for (int k3 = 0; k3 < 27; ++k3) out[(int64_t)k3 * ld] = -1;
+        }
+        if (vmask) vmask[(int64_t)it * ld + o] = 0u;
+      }
+      continue;
+    }
     const int cx = (int)((key >> kXShift) & ((1u << kXBits) - 1)) >> L;
     const int cy = (int)((key >> kYShift) & ((1u << kYBits) - 1)) >> L;
     const int cz = (int)((key >> kZShift) & ((1u << kZBits) - 1)) >> L;
@@ -493,7 +505,10 @@ k_kernel_map_blk3(const LevelTabs T, const KmapOut O) {
       sOcc[j][tid] = oc;
     }
     uint32_t* tm = tile_masks ? tile_masks + 4 * (o0 >> 7) : nullptr;
+    // Presence first, from the occupancy words alone: per (dz, dy) row the three x-neighbours are three adjacent bits of a
+    // 6-bit line = [last cell of the -x block | the four cells of the own block's x-row | first cell of the +x block].
     uint32_t present = 0;   // bit k3: neighbour k3 of this time plane exists
+    const int lx = cx & 3;
 #pragma unroll
     for (int dz = -1; dz <= 1; ++dz) {
       const int jz = (sz != 0 && dz == sz) ? 4 : 0;
@@ -501,22 +516,34 @@ k_kernel_map_blk3(const LevelTabs T, const KmapOut O) {
       for (int dy = -1; dy <= 1; ++dy) {
         const int jyz = jz + ((sy != 0 && dy == sy) ? 2 : 0);
         const int lyz = 4 * ((cy + dy) & 3) + 16 * ((cz + dz) & 3);
+        const uint32_t rowA = (uint32_t)(sOcc[jyz][tid] >> lyz) & 15u;
+        const uint32_t rowB = (uint32_t)(sOcc[jyz + 1][tid] >> lyz) & 15u;    // the x-adjacent block (all zero when sx == 0)
+        const uint32_t line = (sx < 0 ? (rowB >> 3) : 0u) | (rowA << 1) | (sx > 0 ? ((rowB & 1u) << 5) : 0u);
+        present |= ((line >> lx) & 7u) << (3 * ((dy + 1) + 3 * (dz + 1)));
+      }
+    }
+    // dense = 0: only present entries are stored (87 % of the table is -1); allowed when every reader of this level's
+    // table goes through the presence words `vmask` (the tile slices of a shape-sorted level)
+    if (dense && live) {
 #pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-          const int j = jyz + ((sx != 0 && dx == sx) ? 1 : 0);
-          const int l = lyz + ((cx + dx) & 3);
-          int res = -1;
-          if ((sOcc[j][tid] >> l) & 1ull) res = __ldg(cells + (int64_t)sId[j][tid] * 64 + l);
-          const int k3 = (dx + 1) + 3 * ((dy + 1) + 3 * (dz + 1));
-          // dense = 0: only present entries are stored (87 % of the table is -1); allowed when every reader of this
-          // level's table goes through the presence words `vmask` (the tile slices of a shape-sorted level)
-          if (live && (dense || res >= 0)) out[(int64_t)k3 * ld] = res;
-          if (res >= 0) present |= 1u << k3;
-          if (tm) {
-            const int k = it * 27 + k3;
-            if (__any_sync(0xffffffffu, res >= 0) && lane == 0) atomicOr(tm + (k >> 5), 1u << (k & 31));
-          }
-        }
+      for (int k3 = 0; k3 < 27; ++k3) out[(int64_t)k3 * ld] = -1;
+    }
+    // then one index read and one store per PRESENT neighbour (5-12 of the 27)
+    uint32_t todo = live ? present : 0u;
+    while (todo) {
+      const int k3 = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int dz = k3 / 9 - 1, dy = (k3 / 3) % 3 - 1, dx = k3 % 3 - 1;
+      const int jj = ((sz != 0 && dz == sz) ? 4 : 0) + ((sy != 0 && dy == sy) ? 2 : 0) + ((sx != 0 && dx == sx) ? 1 : 0);
+      const int l = ((cx + dx) & 3) + 4 * ((cy + dy) & 3) + 16 * ((cz + dz) & 3);
+      out[(int64_t)k3 * ld] = __ldg(cells + (int64_t)sId[jj][tid] * 64 + l);
+    }
+    if (tm) {   // physical-order tile masks: the offsets any row of the warp has
+      const uint32_t any = __reduce_or_sync(0xffffffffu, present);
+      if (lane == 0 && any) {
+        const int lo = it * 27, w0 = lo >> 5, sh = lo & 31;
+        atomicOr(tm + w0, any << sh);
+        if (sh + 27 > 32) atomicOr(tm + w0 + 1, any >> (32 - sh));
       }
     }
     if (vmask && live) vmask[(int64_t)it * ld + o] = present;
