@@ -32,11 +32,10 @@ __global__ void k_level_begin(Slot* __restrict__ tab, const int32_t* __restrict_
   const int4 empty = make_int4(-1, -1, -1, INT_MAX);
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += stride) reinterpret_cast<int4*>(tab)[i] = empty;
-  if (child) {
-    const int64_t total = (int64_t)8 * n;
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += stride) {
-      const int r = (int)(idx / n), c = (int)(idx - (int64_t)r * n);
-      child[r * ld + c] = -1;
+  if (child) {   // (no division per element: this loop was 79 % issue-bound with idx / n)
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < (uint32_t)n; c += stride) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) child[r * ld + c] = -1;
     }
   }
 }
@@ -836,49 +835,47 @@ k_conv0_const(const unsigned long long* __restrict__ keys, const int32_t* __rest
     // divergent but ALU-only): collect the presence bits of the 125 neighbours into a 128-bit vector,
     // bit k = kernel offset index.  Pass 2 (warp-uniform over k): weights are shared-memory broadcasts.
     const int bx0 = (cx - 2) >> 2, by0 = (cy - 2) >> 2, bz0 = (cz - 2) >> 2;
-    unsigned long long p_lo = 0ull, p_hi = 0ull;
+    unsigned long long o8[8];     // occupancy words of the 2 x 2 x 2 blocks the window meets (0: no such block)
 #pragma unroll
     for (int jb = 0; jb < 8; ++jb) {
       const int bx = bx0 + (jb & 1), by = by0 + ((jb >> 1) & 1), bz = bz0 + (jb >> 2);
-      const int x_lo = max(cx - 2, bx * 4), x_hi = min(cx + 2, bx * 4 + 3);
-      const int y_lo = max(cy - 2, by * 4), y_hi = min(cy + 2, by * 4 + 3);
-      const int z_lo = max(cz - 2, bz * 4), z_hi = min(cz + 2, bz * 4 + 3);
-      if (x_lo > x_hi || y_lo > y_hi || z_lo > z_hi) continue;
+      o8[jb] = 0ull;
+      if (max(cx - 2, bx * 4) > min(cx + 2, bx * 4 + 3) || max(cy - 2, by * 4) > min(cy + 2, by * 4 + 3) ||
+          max(cz - 2, bz * 4) > min(cz + 2, bz * 4 + 3))
+        continue;
       if ((unsigned)bx >= (unsigned)blim || (unsigned)by >= (unsigned)blim || (unsigned)bz >= (unsigned)zblim) continue;
       const unsigned long long bkey = bt | ((unsigned long long)(unsigned)(bx << 2) << kXShift) |
                                       ((unsigned long long)(unsigned)(by << 2) << kYShift) |
                                       ((unsigned long long)(unsigned)(bz << 2) << kZShift);
       const int id = table_find(tab, mask, bkey);
-      if (id < 0) continue;
-      const unsigned long long m = __ldg(occ + id);
-      const unsigned long long xmask = (1ull << (x_hi - x_lo + 1)) - 1ull;
-      for (int nz = z_lo; nz <= z_hi; ++nz)
-        for (int ny = y_lo; ny <= y_hi; ++ny) {
-          const unsigned long long bits = (m >> (4 * (ny & 3) + 16 * (nz & 3) + (x_lo & 3))) & xmask;
-          const int k0 = (x_lo - cx + 2) + 5 * ((ny - cy + 2) + 5 * (nz - cz + 2));   // 0..124
-          if (k0 < 64) {
-            p_lo |= bits << k0;
-            if (k0 > 60) p_hi |= bits >> (64 - k0);
-          } else {
-            p_hi |= bits << (k0 - 64);
-          }
-        }
+      if (id >= 0) o8[jb] = __ldg(occ + id);
     }
+    // Per (dz, dy) row of the window the five x-neighbours are five adjacent bits of an 8-bit line: the x-rows of the two
+    // blocks side by side.  Rows in ascending kernel-offset order (the order of the weight sums is part of the result).
+    const int offx = (cx - 2) - bx0 * 4;        // 0..3: where the window starts in the line
     float acc[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[c] = 0.f;
 #pragma unroll
-    for (int row = 0; row < 25; ++row) {
-      const int k0 = row * 5;   // compile-time after unrolling
-      unsigned pat;
-      if (k0 + 5 <= 64) pat = (unsigned)(p_lo >> k0) & 31u;
-      else if (k0 >= 64) pat = (unsigned)(p_hi >> (k0 - 64)) & 31u;
-      else pat = (unsigned)((p_lo >> k0) | (p_hi << (64 - k0))) & 31u;
-      if (pat) {
-        const float4 w0 = *reinterpret_cast<const float4*>(w_t + (row * 32 + pat) * 8);
-        const float4 w1 = *reinterpret_cast<const float4*>(w_t + (row * 32 + pat) * 8 + 4);
-        acc[0] += w0.x; acc[1] += w0.y; acc[2] += w0.z; acc[3] += w0.w;
-        acc[4] += w1.x; acc[5] += w1.y; acc[6] += w1.z; acc[7] += w1.w;
+    for (int dz = -2; dz <= 2; ++dz) {
+      const int nz = cz + dz;
+      const bool jz = ((nz >> 2) - bz0) != 0;
+      const unsigned long long a00 = jz ? o8[4] : o8[0], a01 = jz ? o8[5] : o8[1], a10 = jz ? o8[6] : o8[2], a11 = jz ? o8[7] : o8[3];
+#pragma unroll
+      for (int dy = -2; dy <= 2; ++dy) {
+        const int ny = cy + dy;
+        const bool jy = ((ny >> 2) - by0) != 0;
+        const unsigned long long A = jy ? a10 : a00, B = jy ? a11 : a01;
+        const int lyz = 4 * (ny & 3) + 16 * (nz & 3);
+        const uint32_t line = ((uint32_t)(A >> lyz) & 15u) | (((uint32_t)(B >> lyz) & 15u) << 4);
+        const uint32_t pat = (line >> offx) & 31u;
+        const int row = (dy + 2) + 5 * (dz + 2);
+        if (pat) {
+          const float4 w0 = *reinterpret_cast<const float4*>(w_t + (row * 32 + pat) * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(w_t + (row * 32 + pat) * 8 + 4);
+          acc[0] += w0.x; acc[1] += w0.y; acc[2] += w0.z; acc[3] += w0.w;
+          acc[4] += w1.x; acc[5] += w1.y; acc[6] += w1.z; acc[7] += w1.w;
+        }
       }
     }
 #pragma unroll
