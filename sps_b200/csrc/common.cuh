@@ -147,6 +147,34 @@ __device__ inline uint32_t table_insert(Slot* tab, uint32_t mask, unsigned long 
   }
 }
 
+// Insert `key` and lower the slot's `first` to `i` (first-occurrence index).  Most rows find their voxel already in the table
+// (2-3 input rows per voxel, 2-8 fine voxels per coarse one): one 16-byte L2 read of the slot answers both questions, and
+// the two atomics are only issued when they can change something (`first` only ever decreases, so a stale read is safe).
+// `s` / `raw`: the home slot and its content as read by the caller (callers issue the reads of several rows back to back: the
+// insert kernels are bound by the latency of this first random access, not by atomics or bandwidth).
+__device__ inline uint32_t table_insert_first(Slot* tab, uint32_t mask, unsigned long long key, int i, uint32_t s, int4 raw) {
+  while (true) {
+    const unsigned long long cur = ((unsigned long long)(unsigned)raw.y << 32) | (unsigned)raw.x;
+    if (cur == key) {
+      if (raw.w > i) atomicMin(&tab[s].first, i);
+      return s;
+    }
+    if (cur == kEmptyKey) {
+      const unsigned long long prev = atomicCAS(&tab[s].key, kEmptyKey, key);
+      if (prev == kEmptyKey || prev == key) {
+        atomicMin(&tab[s].first, i);
+        return s;
+      }
+    }
+    s = (s + 1) & mask;
+    raw = __ldcg(reinterpret_cast<const int4*>(tab + s));
+  }
+}
+__device__ inline uint32_t table_insert_first(Slot* tab, uint32_t mask, unsigned long long key, int i) {
+  const uint32_t s = hash_key(key) & mask;
+  return table_insert_first(tab, mask, key, i, s, __ldcg(reinterpret_cast<const int4*>(tab + s)));
+}
+
 // sticky status word bits (device)
 constexpr int kStatusRange = 1, kStatusCapacity = 2;
 

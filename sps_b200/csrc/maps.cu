@@ -19,6 +19,8 @@ constexpr uint32_t kInvalidSlot = 0xFFFFFFFFu;
 
 __global__ void k_set_i32(int32_t* p, int32_t v) { *p = v; }
 
+constexpr int kInsertBatch = 4;   // rows a thread of the level-0 insert kernel keeps in flight
+
 // First kernel of a level: empties the open-addressing table for `n` keys and, for a strided level, presets the
 // child table of the level being built to "absent" for every column a coarse row can take (coarse count <= fine count).
 // n comes from the device (`n_ptr`) or, at level 0, from the host (`n_host` >= 0, also published to `n_dev`).
@@ -47,26 +49,42 @@ __global__ void k_insert_points(const float* __restrict__ pts, int64_t ld, const
   const int n = *n_ptr;
   const uint32_t mask = table_capacity(n) - 1;
   uint32_t seen = 0;   // time planes this thread met (bit t)
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const float* p = pts + (int64_t)i * ld;
-    const float fb = floorf(__fdiv_rn(p[0], 1.0f));
-    const float fx = floorf(__fdiv_rn(p[1], vs));
-    const float fy = floorf(__fdiv_rn(p[2], vs));
-    const float fz = floorf(__fdiv_rn(p[3], vs));
-    const float ft = floorf(__fdiv_rn(p[4], 1.0f));
-    const bool ok = fb >= 0.f && fb < 255.f && fx >= -(float)kXBias && fx < (float)kXBias &&
-                    fy >= -(float)kXBias && fy < (float)kXBias && fz >= -(float)kZBias &&
-                    fz < (float)kZBias && ft >= 0.f && ft < 16.f;
-    if (!ok) {  // also catches NaN
-      atomicOr(status, kStatusRange);
-      slot_of[i] = kInvalidSlot;
-      continue;
+  // kInsertBatch rows per thread at a time: their home slots are read back to back, so the L2 / DRAM round trips of the
+  // random accesses overlap (ncu: 53 of 57 stall cycles per issue were long-scoreboard waits with one row at a time), and
+  // the atomics are only issued when they can change something: 57 % of the rows find their voxel already in the table
+  const int stride = gridDim.x * blockDim.x;
+  for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += kInsertBatch * stride) {
+    unsigned long long key[kInsertBatch];
+    uint32_t sl[kInsertBatch];
+    int4 raw[kInsertBatch];
+    bool ok[kInsertBatch];
+#pragma unroll
+    for (int u = 0; u < kInsertBatch; ++u) {
+      const int i = i0 + u * stride;
+      ok[u] = false;
+      if (i >= n) continue;
+      const float* p = pts + (int64_t)i * ld;
+      const float fb = floorf(__fdiv_rn(p[0], 1.0f));
+      const float fx = floorf(__fdiv_rn(p[1], vs));
+      const float fy = floorf(__fdiv_rn(p[2], vs));
+      const float fz = floorf(__fdiv_rn(p[3], vs));
+      const float ft = floorf(__fdiv_rn(p[4], 1.0f));
+      ok[u] = fb >= 0.f && fb < 255.f && fx >= -(float)kXBias && fx < (float)kXBias &&
+              fy >= -(float)kXBias && fy < (float)kXBias && fz >= -(float)kZBias &&
+              fz < (float)kZBias && ft >= 0.f && ft < 16.f;
+      if (!ok[u]) {  // also catches NaN
+        atomicOr(status, kStatusRange);
+        slot_of[i] = kInvalidSlot;
+        continue;
+      }
+      key[u] = pack_key((int)fb, (int)fx, (int)fy, (int)fz, (int)ft);
+      sl[u] = hash_key(key[u]) & mask;
+      raw[u] = __ldcg(reinterpret_cast<const int4*>(tab + sl[u]));
+      seen |= 1u << (int)ft;
     }
-    const unsigned long long key = pack_key((int)fb, (int)fx, (int)fy, (int)fz, (int)ft);
-    const uint32_t s = table_insert(tab, mask, key);
-    atomicMin(&tab[s].first, i);
-    slot_of[i] = s;
-    seen |= 1u << (int)ft;
+#pragma unroll
+    for (int u = 0; u < kInsertBatch; ++u)
+      if (ok[u]) slot_of[i0 + u * stride] = table_insert_first(tab, mask, key[u], i0 + u * stride, sl[u], raw[u]);
   }
   // which time planes hold voxels at all (SPS: t in {0, 1}): the kernel-map pass does not probe the others
   seen = __reduce_or_sync(0xffffffffu, seen);
@@ -990,7 +1008,7 @@ int voxelize_impl(sps_ctx* ctx, const float* d_points, int64_t n, const int32_t*
   k_level_begin<<<grid_for(table_capacity(n), 256), 256, 0, st>>>(ctx->table, d_n, d_n ? -1 : (int32_t)n, ctx->n_dev, nullptr, 0,
                                                                   ctx->tplanes);
   prof_mark(ctx, "vox.clear", st);
-  k_insert_points<<<grid_for(n, 256), 256, 0, st>>>(d_points, ld_points, ctx->n_dev, voxel_size, ctx->table,
+  k_insert_points<<<grid_for(cdiv(n, kInsertBatch), 256, 148 * 8), 256, 0, st>>>(d_points, ld_points, ctx->n_dev, voxel_size, ctx->table,
                                                      ctx->slot_of, ctx->status, ctx->tplanes);
   prof_mark(ctx, "vox.insert", st);
   k_first_rank<<<nblk, kScanBlock, 0, st>>>(ctx->table, ctx->slot_of, ctx->n_dev, ctx->rank, ctx->block_sums,
