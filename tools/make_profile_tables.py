@@ -29,7 +29,7 @@ for d in launch.values():
         a[k] += d.get(m, 0.0) * d.get("gpu__time_duration.sum", 0.0)   # time-weighted
 tot = sum(a["us"] for a in agg.values())
 with open(out_md, "w") as f:
-    f.write("ncu metrics pass over ONE forward of the bench workload (batch 8, 2.47 M rows, 56 launches; second forward of tools/profile_forward.py;\n"
+    f.write(f"ncu metrics pass over ONE forward of the bench workload (batch 8, 2.47 M rows, {len(launch)} launches; second forward of tools/profile_forward.py;\n"
             "`tools/ncu_capture.sh`).  Per-launch times are cold-cache and serialised: compare shares.  Percentages are time-weighted means.\n\n")
     f.write("| kernel | launches | time us | share | DRAM rd MB | DRAM wr MB | dram % | l1tex % | lts % | L1 hit % | L2 hit % | issue % | tensor % | warps % | regs |\n")
     f.write("|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|\n")
@@ -43,7 +43,7 @@ conv_names = ["conv1p1s2", "block1.conv1", "block1.conv2", "conv2p2s2", "block2.
               "block3.conv2", "conv4p8s2", "block4.conv1", "block4.conv2", "convtr4p16s2", "block5.conv1", "block5.conv2", "convtr5p8s2",
               "block6.conv1", "block6.conv2", "convtr6p4s2", "block7.conv1", "block7.conv2", "convtr7p2s2", "block8.conv1", "block8.conv2+final"]
 fam = {"k_conv_umma6": conv_names, "k_kernel_map_blk3": ["kmap3"], "k_conv0_const": ["conv0+kmap5"],
-       "k_insert_points": ["vox.insert"], "k_assign_points": ["vox.assign"], "k_tile_masks_perm": ["slices"]}
+       "k_insert_points": ["vox.insert"], "k_assign_points": ["vox.assign"], "k_tile_masks_perm": ["slices"], "k_up_order": ["up_order"]}
 seen = collections.Counter()
 traffic = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu metrics pass over one forward of the bench workload "
                        "(tools/ncu_capture.sh)"}

@@ -6,13 +6,14 @@
 R=${1:-r2}
 set -x
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,l1tex__throughput.avg.pct_of_peak_sustained_elapsed,lts__throughput.avg.pct_of_peak_sustained_elapsed,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,l1tex__t_sector_hit_rate.pct,lts__t_sector_hit_rate.pct,smsp__issue_active.avg.pct_of_peak_sustained_active
-# the two timed device-resident steps of a single-lane bench run (56 launches per forward; 3 warm-up forwards before)
-ncu --metrics gpu__time_duration.sum --clock-control none -s 168 -c 112 --csv --log-file gpurun_out/${R}_launches.csv python bench.py --steps 2 --warmup 3 --lanes 1 --no-cpu-baseline --no-alt > gpurun_out/${R}_launches_bench.log 2>&1
-ncu --metrics $M --clock-control none -s 56 -c 56 --csv --log-file gpurun_out/${R}_forward_metrics.csv python tools/profile_forward.py 2 > gpurun_out/${R}_forward_metrics.log 2>&1
+# the two timed device-resident steps of a single-lane bench run (NL launches per forward; 3 warm-up forwards before)
+NL=${NL:-57}
+ncu --metrics gpu__time_duration.sum --clock-control none -s $((3 * NL)) -c $((2 * NL)) --csv --log-file gpurun_out/${R}_launches.csv python bench.py --steps 2 --warmup 3 --lanes 1 --no-cpu-baseline --no-alt > gpurun_out/${R}_launches_bench.log 2>&1
+ncu --metrics $M --clock-control none -s $NL -c $NL --csv --log-file gpurun_out/${R}_forward_metrics.csv python tools/profile_forward.py 2 > gpurun_out/${R}_forward_metrics.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"k_kernel_map_blk3|k_conv_umma6|k_onesweep_pass|k_tile_masks_perm" -s 30 -c 18 -o /tmp/top_${R} python tools/profile_forward.py 2 > gpurun_out/${R}_top_full.log 2>&1
 ncu -i /tmp/top_${R}.ncu-rep --page raw --csv > gpurun_out/${R}_top_full.csv 2>/dev/null
 # one wide layer (PLANES x4, block5.conv2: 256 -> 256 on level 3): the 8th 81-offset layer of the sweep, 6 launches each, after 8 forwards
-ncu --set full --clock-control none --import-source on -k regex:k_conv_umma6 -s 235 -c 2 -o /tmp/wide_${R} python tools/width_sweep.py --widths 4 --steps 1 > gpurun_out/${R}_wide_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_conv_umma6<\(int\)256" -s 12 -c 2 -o /tmp/wide_${R} python tools/width_sweep.py --widths 4 --steps 1 > gpurun_out/${R}_wide_full.log 2>&1
 ncu -i /tmp/wide_${R}.ncu-rep --page raw --csv > gpurun_out/${R}_wide_full.csv 2>/dev/null
 cp /tmp/wide_${R}.ncu-rep gpurun_out/ 2>/dev/null
 ls -la gpurun_out | tail -12
