@@ -19,6 +19,7 @@ constexpr uint32_t kInvalidSlot = 0xFFFFFFFFu;
 
 __global__ void k_set_i32(int32_t* p, int32_t v) { *p = v; }
 
+constexpr int kRankChunks = 4;    // chunks of kScanBlock rows a block of k_first_rank scans
 constexpr int kInsertBatch = 4;   // rows a thread of the level-0 insert kernel keeps in flight
 
 // First kernel of a level: empties the open-addressing table for `n` keys and, for a strided level, presets the
@@ -110,24 +111,39 @@ k_first_rank(Slot* tab, const uint32_t* __restrict__ slot_of, const int32_t* __r
              int32_t* __restrict__ rank, int32_t* block_sums, uint32_t* ticket, int32_t* count_out,
              const Slot* __restrict__ filter, uint32_t filter_mask, int32_t* first_count) {
   const int n = *n_ptr;
-  const int nb = max(1, (n + kScanBlock - 1) / kScanBlock);
-  if ((int)blockIdx.x >= nb) return;
-  const int i = blockIdx.x * kScanBlock + threadIdx.x;
-  int flag = 0;
-  uint32_t s = kInvalidSlot;
-  if (i < n) {
-    s = slot_of[i];
-    flag = (s != kInvalidSlot) && (tab[s].first == i);
+  const int nb = max(1, (n + kScanBlock - 1) / kScanBlock);          // chunks of kScanBlock inputs
+  const int nblocks = (nb + kRankChunks - 1) / kRankChunks;          // blocks that take part (kRankChunks chunks each)
+  if ((int)blockIdx.x >= nblocks) return;
+  // A block scans kRankChunks consecutive chunks: the random slot reads behind all its flags are issued first (the kernel
+  // waits on exactly those), and the grid takes a quarter of the tickets (one same-address atomic per block).
+  int flag[kRankChunks];
+  uint32_t s[kRankChunks];
+#pragma unroll
+  for (int r = 0; r < kRankChunks; ++r) {
+    const int i = (blockIdx.x * kRankChunks + r) * kScanBlock + threadIdx.x;
+    s[r] = i < n ? slot_of[i] : kInvalidSlot;
   }
-  if (filter) {
-    const unsigned ballot = __ballot_sync(0xffffffffu, flag);
-    if (first_count && (threadIdx.x & 31) == 0 && ballot) atomicAdd(first_count, __popc(ballot));
-    if (flag) flag = table_find(filter, filter_mask, tab[s].key) >= 0;
+#pragma unroll
+  for (int r = 0; r < kRankChunks; ++r) {
+    const int i = (blockIdx.x * kRankChunks + r) * kScanBlock + threadIdx.x;
+    flag[r] = (s[r] != kInvalidSlot) && (tab[s[r]].first == i);
   }
-  const int excl = scan_flags(flag, i, n, nb, rank, block_sums, ticket, count_out);
-  // the first occurrence leaves its block-local rank in the slot: whoever maps an input to its voxel row later
-  // reads ONE 16-byte slot (key, local rank, first index) instead of chasing slot -> first -> rank[first]
-  if (flag && !filter) tab[s].val = excl;
+#pragma unroll
+  for (int r = 0; r < kRankChunks; ++r) {
+    const int chunk = blockIdx.x * kRankChunks + r;
+    if (chunk >= nb) break;                                           // block-uniform
+    const int i = chunk * kScanBlock + threadIdx.x;
+    if (filter) {
+      const unsigned ballot = __ballot_sync(0xffffffffu, flag[r]);
+      if (first_count && (threadIdx.x & 31) == 0 && ballot) atomicAdd(first_count, __popc(ballot));
+      if (flag[r]) flag[r] = table_find(filter, filter_mask, tab[s[r]].key) >= 0;
+    }
+    const int excl = scan_chunk(flag[r], i, n, chunk, rank, block_sums);
+    // the first occurrence leaves its chunk-local rank in the slot: whoever maps an input to its voxel row later
+    // reads ONE 16-byte slot (key, local rank, first index) instead of chasing slot -> first -> rank[first]
+    if (flag[r] && !filter) tab[s[r]].val = excl;
+  }
+  scan_finish(nb, nblocks, block_sums, ticket, count_out);
 }
 
 // Level 0: inverse mapping point -> voxel row; the first occurrence publishes the voxel.
@@ -1011,7 +1027,7 @@ int voxelize_impl(sps_ctx* ctx, const float* d_points, int64_t n, const int32_t*
   k_insert_points<<<grid_for(cdiv(n, kInsertBatch), 256, 148 * 8), 256, 0, st>>>(d_points, ld_points, ctx->n_dev, voxel_size, ctx->table,
                                                      ctx->slot_of, ctx->status, ctx->tplanes);
   prof_mark(ctx, "vox.insert", st);
-  k_first_rank<<<nblk, kScanBlock, 0, st>>>(ctx->table, ctx->slot_of, ctx->n_dev, ctx->rank, ctx->block_sums,
+  k_first_rank<<<cdiv(nblk, kRankChunks), kScanBlock, 0, st>>>(ctx->table, ctx->slot_of, ctx->n_dev, ctx->rank, ctx->block_sums,
                                             ctx->ticket, ctx->counts + 0, nullptr, 0, nullptr);
   prof_mark(ctx, "vox.rank", st);
   k_assign_points<<<grid_for(n, 256), 256, 0, st>>>(ctx->table, ctx->slot_of, ctx->n_dev, ctx->rank,
@@ -1115,7 +1131,7 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
     k_level_begin<<<grid_for(table_capacity(n), 256), 256, 0, st>>>(tab, n_fine, -1, nullptr, ctx->child[L], ctx->ld, nullptr,
                                                                     ctx->up_cls + 16 * (L - 1));
     k_insert_coarse<<<grid_for(n, 256), 256, 0, st>>>(ctx->keys[L - 1], n_fine, L, tab, ctx->slot_of);
-    k_first_rank<<<nblk, kScanBlock, 0, st>>>(tab, ctx->slot_of, n_fine, ctx->rank, sums,
+    k_first_rank<<<cdiv(nblk, kRankChunks), kScanBlock, 0, st>>>(tab, ctx->slot_of, n_fine, ctx->rank, sums,
                                               ctx->ticket, ctx->counts + L, nullptr, 0, nullptr);
     k_assign_coarse<<<grid_for(n, 256), 256, 0, st>>>(tab, ctx->slot_of, n_fine, ctx->rank, sums,
                                                        ctx->keys[L - 1], L - 1, ctx->keys[L], ctx->parent[L - 1],
@@ -1377,7 +1393,7 @@ extern "C" int sps_submap_crop_voxel(const sps_map* map, const float* d_scan_xyz
   k_level_begin<<<grid_for(s.cap, 256), 256, 0, st>>>(s.table, nullptr, (int32_t)n_scan, s.scalars + 0, nullptr, 0);
   k_insert_xyz<<<grid_for(n, 256), 256, 0, st>>>(d_scan_xyz, s.scalars + 0, map->ds, s.table, s.slot_of,
                                                   s.scalars + 40);
-  k_first_rank<<<cdiv(n, kScanBlock), kScanBlock, 0, st>>>(s.table, s.slot_of, s.scalars + 0, s.rank, s.block_sums,
+  k_first_rank<<<cdiv(cdiv(n, kScanBlock), kRankChunks), kScanBlock, 0, st>>>(s.table, s.slot_of, s.scalars + 0, s.rank, s.block_sums,
                                                            (uint32_t*)(s.scalars + 32), d_counts + 0, map->table,
                                                            map->cap - 1, d_counts + 1);
   k_write_submap<<<grid_for(n, 256), 256, 0, st>>>(s.table, s.slot_of, s.scalars + 0, s.rank, s.block_sums,
