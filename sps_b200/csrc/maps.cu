@@ -837,7 +837,7 @@ k_tile_masks_perm(const SliceArgs A) {
 // 0.5 point features, models.py:22-25): out[o] = relu(c * sum_{k present} W[k][:] + shift).  Only the
 // PRESENCE of the 125 neighbours matters, and that is one bit of the 64-bit occupancy word of a 4x4x4
 // block: 8 block probes per voxel, no index reads at all; the weight sum goes through per-row tables.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_conv0_const(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ n_ptr,
               const Slot* __restrict__ tab, const int32_t* __restrict__ cap_n,
               const unsigned long long* __restrict__ occ, float cfeat,
