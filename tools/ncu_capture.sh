@@ -13,7 +13,7 @@ ncu --metrics $M --clock-control none -s $NL -c $NL --csv --log-file gpurun_out/
 ncu --set full --clock-control none --import-source on -k regex:"k_kernel_map_blk3|k_conv_umma6|k_onesweep_pass|k_tile_masks_perm" -s 30 -c 30 -o /tmp/top_${R} python tools/profile_forward.py 2 > gpurun_out/${R}_top_full.log 2>&1
 ncu -i /tmp/top_${R}.ncu-rep --page raw --csv > gpurun_out/${R}_top_full.csv 2>/dev/null
 # one wide layer (PLANES x4, block5.conv2: 256 -> 256 on level 3): the 8th 81-offset layer of the sweep, 6 launches each, after 8 forwards
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"k_conv_umma6<256" -s 12 -c 2 -o /tmp/wide_${R} python tools/width_sweep.py --widths 4 --steps 1 > gpurun_out/${R}_wide_full.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"k_conv_umma6<\(int\)256" -s 12 -c 2 -o /tmp/wide_${R} python tools/width_sweep.py --widths 4 --steps 1 > gpurun_out/${R}_wide_full.log 2>&1
 ncu -i /tmp/wide_${R}.ncu-rep --page raw --csv > gpurun_out/${R}_wide_full.csv 2>/dev/null
 cp /tmp/wide_${R}.ncu-rep gpurun_out/ 2>/dev/null
 python tools/ncu_top_md.py gpurun_out/${R}_top_full.csv "Kernel-map, sort, slice and convolution kernels of ONE forward, full ncu capture (${R})" > gpurun_out/${R}_top_kernels_ncu_full.md
