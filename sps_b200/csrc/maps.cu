@@ -466,12 +466,17 @@ struct KmapOut {
   uint32_t* vmask[SPS_NUM_LEVELS];        // [3][ld] per-voxel 27-bit presence words per time plane
   int64_t ld;
   int dense_mask;                         // bit L: level L stores absent entries (-1) too
+  // shape sort fused in (nullptr: no sort this forward): the voxel's sort key, its row number and the digit histograms of
+  // the four radix passes leave this kernel, so the presence words are not read back by a separate key pass
+  uint32_t* sort_keys; int32_t* sort_vals; uint32_t* sort_hist;
+  int sort_first, sort_last;
 };
 // All levels in one launch: blockIdx.z = level, blockIdx.y = time plane of the kernel.
 // (capping this kernel at 32 registers to fit more blocks beside another lane's convolution CTA made it 1.5x slower
 // and the step 18 % slower: profiles/r2_experiments.md)
+__device__ __forceinline__ uint32_t shape_bits(uint32_t pat);
 template <int KT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 k_kernel_map_blk3(const LevelTabs T, const KmapOut O) {
   __shared__ int sId[8][256];
   __shared__ unsigned long long sOcc[8][256];
@@ -489,13 +494,23 @@ k_kernel_map_blk3(const LevelTabs T, const KmapOut O) {
   const int dense = (O.dense_mask >> L) & 1;
   const uint32_t mask = table_capacity(T.counts[T.capn[L]]) - 1;
   const int xlim = 1 << (kXBits - L), zlim = 1 << (kZBits - L);
-  const int it = blockIdx.y;   // time plane of the kernel: t + (it - KT/2)
   const int tid = threadIdx.x, lane = tid & 31;
   const uint32_t planes = (uint32_t)*T.tplanes;
+  const bool sorting = O.sort_keys != nullptr && L >= O.sort_first && L <= O.sort_last;
+  __shared__ uint32_t s_hist[4][256];
+  int sort_off = 0;
+  if (sorting) {
+    for (int i = tid; i < 1024; i += blockDim.x) (&s_hist[0][0])[i] = 0u;
+    for (int q = O.sort_first; q < L; ++q) sort_off += T.counts[q];
+    __syncthreads();
+  }
   for (int o0 = (blockIdx.x * blockDim.x + tid) & ~31; o0 < n; o0 += gridDim.x * blockDim.x) {
     const int o = o0 + lane;
     const bool live = o < n;
     const unsigned long long key = live ? keys[o] : 0ull;
+    uint32_t por = 0u, has_lo = 0u, has_hi = 0u;   // OR of the planes' presence words; lowest / highest plane non-empty
+#pragma unroll 1
+    for (int it = 0; it < KT; ++it) {             // time plane of the kernel: t + (it - KT/2)
     const int t2 = (int)(key & ((1u << kTBits) - 1)) + it - KT / 2;
     const bool pok = live && (unsigned)t2 < (1u << kTBits) && ((planes >> t2) & 1u);   // empty time planes are not probed
     int32_t* out = nbr + (int64_t)it * 27 * ld + o;
@@ -580,6 +595,27 @@ k_kernel_map_blk3(const LevelTabs T, const KmapOut O) {
       }
     }
     if (vmask && live) vmask[(int64_t)it * ld + o] = present;
+    por |= present;
+    if (it == 0) has_lo = present ? 1u : 0u;
+    if (it == KT - 1) has_hi = present ? 1u : 0u;
+    }   // planes
+    if (sorting && live) {
+      // sort key of the voxel (see k_pattern_keys): Gray-code rank of [has t+1][has t-1][27 spatial bits, OR over the planes]
+      uint32_t g = shape_bits(por) | (has_lo << 27) | (has_hi << 28);
+      g ^= g >> 1; g ^= g >> 2; g ^= g >> 4; g ^= g >> 8; g ^= g >> 16;
+      const uint32_t skey = g | ((uint32_t)(L - O.sort_first) << 29);
+      O.sort_keys[sort_off + o] = skey;
+      O.sort_vals[sort_off + o] = o;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) atomicAdd(&s_hist[p][(skey >> (8 * p)) & 255u], 1u);
+    }
+  }
+  if (sorting) {
+    __syncthreads();
+    for (int i = tid; i < 1024; i += blockDim.x) {
+      const uint32_t c = (&s_hist[0][0])[i];
+      if (c) atomicAdd(O.sort_hist + i, c);
+    }
   }
 }
 
@@ -1074,14 +1110,15 @@ static inline bool sort_active(const sps_ctx* ctx) {
 
 // perm[L] = voxel rows of level L sorted by neighbourhood-shape key, ptmask[L] = tile masks in that order, tslice[L] = the
 // kernel map gathered per sorted tile -- for all sorted levels at once: 1 + 4 + 1 launches.
-static int pattern_order(sps_ctx* ctx, cudaStream_t st) {
+static int pattern_order(sps_ctx* ctx, cudaStream_t st, bool keys_done) {
   if (!sort_active(ctx)) return SPS_OK;
   const int64_t n = ctx->n > 0 ? ctx->n : 1;
   SortArgs A;
   for (int L = 0; L < SPS_NUM_LEVELS; ++L) { A.vmask[L] = ctx->vmask[L]; A.perm[L] = ctx->perm[L]; }
   A.counts = ctx->counts; A.status = ctx->status; A.ld = ctx->ld; A.first = kFirstSortedLevel; A.nlv = kSortedLevels;
   uint32_t* hist = ctx->sort_hist;
-  k_pattern_keys<<<dim3(grid_for(n, 256, 148 * 8), kSortedLevels), 256, 0, st>>>(A, ctx->sort_keys[0], ctx->sort_vals[0], hist);
+  if (!keys_done)   // (the 3x3x3x3 kernel-map pass normally leaves keys, row numbers and histograms behind)
+    k_pattern_keys<<<dim3(grid_for(n, 256, 148 * 8), kSortedLevels), 256, 0, st>>>(A, ctx->sort_keys[0], ctx->sort_vals[0], hist);
   const int tiles_max = cdiv(n * kSortedLevels, kSortTile);
   for (int pass = 0; pass < 4; ++pass) {
     const uint32_t* ki = ctx->sort_keys[pass & 1];
@@ -1105,7 +1142,7 @@ static int pattern_order(sps_ctx* ctx, cudaStream_t st) {
   k_tile_masks_perm<<<dim3(grid_for(n / 128 + 1, 1, 148 * 8), kSortedLevels), 128, 0, st>>>(S);
   prof_mark(ctx, "slices", st);
   SPS_CUDA_CHECK(cudaGetLastError());
-  ctx->forward_launches += 6;
+  ctx->forward_launches += keys_done ? 5 : 6;
   return SPS_OK;
 }
 }
@@ -1172,6 +1209,8 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
   Z.sort_hist = sorting ? ctx->sort_hist : nullptr; Z.sort_status = ctx->sort_status;
   Z.sort_first = kFirstSortedLevel; Z.sort_levels = kSortedLevels;
   O.ld = ctx->ld;
+  O.sort_keys = sorting ? ctx->sort_keys[0] : nullptr; O.sort_vals = ctx->sort_vals[0]; O.sort_hist = ctx->sort_hist;
+  O.sort_first = kFirstSortedLevel; O.sort_last = kLastSortedLevel;
   const int gx = grid_for(n, 256, 148 * 8);
   k_blocks_begin<<<dim3(grid_for(table_capacity(n), 256, 148 * 8), SPS_NUM_LEVELS), 256, 0, st>>>(T, Z);
   k_block_insert<<<dim3(gx, SPS_NUM_LEVELS), 256, 0, st>>>(T);
@@ -1193,12 +1232,12 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
   }
   ctx->have_nbr5 = c0 == nullptr;
   // ---- 4. 3x3x3x3 kernel maps of all five levels (one launch: level x time plane) ----
-  k_kernel_map_blk3<3><<<dim3(gx, 3, SPS_NUM_LEVELS), 256, 0, st>>>(T, O);
+  k_kernel_map_blk3<3><<<dim3(gx, 1, SPS_NUM_LEVELS), 256, 0, st>>>(T, O);
   prof_mark(ctx, "kmap3", st);
   SPS_CUDA_CHECK(cudaGetLastError());
   ctx->forward_launches += 16 + 1 + 3 + 1 + 1;
   // ---- 5. shape sort + per-tile slices of the sorted levels ----
-  { const int rc = pattern_order(ctx, st); if (rc != SPS_OK) return rc; }
+  { const int rc = pattern_order(ctx, st, /*keys_done=*/sorting); if (rc != SPS_OK) return rc; }
   ctx->have_maps = true;
   ctx->dense_maps = O.dense_mask == (1 << SPS_NUM_LEVELS) - 1;
   ctx->have_perm = sorting;
