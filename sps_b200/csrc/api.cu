@@ -60,7 +60,7 @@ static size_t carve(sps_ctx* c, void* base, int64_t max_points) {
     c->btab[L] = cv.take<Slot>(c->table_cap);
     c->bcells[L] = cv.take<int32_t>((size_t)N * 64);
     c->bocc[L] = cv.take<unsigned long long>(N);
-    c->vmask[L] = cv.take<uint32_t>((size_t)3 * ld);
+    c->vmask[L] = cv.take<uint32_t>((size_t)4 * ld);
     c->parent[L] = (L < SPS_NUM_LEVELS - 1) ? cv.take<int32_t>(N) : nullptr;
     c->child[L] = (L > 0) ? cv.take<int32_t>((size_t)8 * ld) : nullptr;
     c->upmap[L] = (L < SPS_NUM_LEVELS - 1) ? cv.take<int32_t>((size_t)8 * ld) : nullptr;
@@ -242,9 +242,9 @@ __global__ void k_count_presence(const uint32_t* __restrict__ vmask, int64_t ld,
                                  unsigned long long* out) {
   const int n = *n_ptr;
   unsigned long long local = 0;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < (int64_t)3 * n; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int it = (int)(idx / n), o = (int)(idx - (int64_t)it * n);
-    local += __popc(vmask[(int64_t)it * ld + o]);
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 m = reinterpret_cast<const uint4*>(vmask)[o];       // [ld][4]: the three planes of a voxel side by side
+    local += __popc(m.x) + __popc(m.y) + __popc(m.z);
   }
   for (int d = 16; d; d >>= 1) local += __shfl_down_sync(0xffffffffu, local, d);
   if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);

@@ -54,7 +54,7 @@ struct sps_ctx {
   int32_t* parent[SPS_NUM_LEVELS] = {};        // [L] fine row -> parent*8 + k   (L = 0..3)
   int32_t* child[SPS_NUM_LEVELS] = {};         // [L] [8][ld] children of level-L rows (L = 1..4)
   int32_t* upmap[SPS_NUM_LEVELS] = {};         // [L] [8][ld] transposed-conv map of level-L rows (L = 0..3)
-  uint32_t* vmask[SPS_NUM_LEVELS] = {};        // [L] [3][ld] per-voxel 27-bit presence of the 3x3x3 neighbours per time plane
+  uint32_t* vmask[SPS_NUM_LEVELS] = {};        // [L] [ld][4] per-voxel 27-bit presence words of the 3x3x3 neighbours in the three time planes (+ pad)
   int32_t* perm[SPS_NUM_LEVELS] = {};          // [L] rows of level L in neighbourhood-shape order (conv processing order)
   uint32_t* ptmask[SPS_NUM_LEVELS] = {};       // [L] tile masks of nbr3 in perm order
   int32_t* tslice[SPS_NUM_LEVELS] = {};        // [L] [tiles][82][128] nbr3 gathered per tile in perm order (sorted levels)

@@ -450,7 +450,7 @@ k_kernel_map_blk(const unsigned long long* __restrict__ keys, const int32_t* __r
         }
       }
     }
-    if (vmask && live) vmask[(int64_t)it * ld + o] = present;
+    if (vmask && live) vmask[(int64_t)o * 4 + it] = present;
   }
 }
 
@@ -463,7 +463,7 @@ k_kernel_map_blk(const unsigned long long* __restrict__ keys, const int32_t* __r
 struct KmapOut {
   int32_t* nbr[SPS_NUM_LEVELS];           // [81][ld] per level
   uint32_t* tile_masks[SPS_NUM_LEVELS];   // physical-order tile masks, or nullptr (shape-sorted level of the fused forward)
-  uint32_t* vmask[SPS_NUM_LEVELS];        // [3][ld] per-voxel 27-bit presence words per time plane
+  uint32_t* vmask[SPS_NUM_LEVELS];        // [ld][4] per-voxel 27-bit presence words of the three time planes (+ pad): one 16-byte line
   int64_t ld;
   int dense_mask;                         // bit L: level L stores absent entries (-1) too
   // shape sort fused in (nullptr: no sort this forward): the voxel's sort key, its row number and the digit histograms of
@@ -508,7 +508,7 @@ k_kernel_map_blk3(const LevelTabs T, const KmapOut O) {
     const int o = o0 + lane;
     const bool live = o < n;
     const unsigned long long key = live ? keys[o] : 0ull;
-    uint32_t por = 0u, has_lo = 0u, has_hi = 0u;   // OR of the planes' presence words; lowest / highest plane non-empty
+    uint32_t por = 0u, pm0 = 0u, pm1 = 0u, pm2 = 0u;   // presence words of the planes and their OR
 #pragma unroll 1
     for (int it = 0; it < KT; ++it) {             // time plane of the kernel: t + (it - KT/2)
     const int t2 = (int)(key & ((1u << kTBits) - 1)) + it - KT / 2;
@@ -522,7 +522,6 @@ k_kernel_map_blk3(const LevelTabs T, const KmapOut O) {
 #pragma unroll
           for (int k3 = 0; k3 < 27; ++k3) out[(int64_t)k3 * ld] = -1;
         }
-        if (vmask) vmask[(int64_t)it * ld + o] = 0u;
       }
       continue;
     }
@@ -594,11 +593,13 @@ k_kernel_map_blk3(const LevelTabs T, const KmapOut O) {
         if (sh + 27 > 32) atomicOr(tm + w0 + 1, any >> (32 - sh));
       }
     }
-    if (vmask && live) vmask[(int64_t)it * ld + o] = present;
     por |= present;
-    if (it == 0) has_lo = present ? 1u : 0u;
-    if (it == KT - 1) has_hi = present ? 1u : 0u;
+    if (it == 0) pm0 = present;
+    else if (it == 1) pm1 = present;
+    else pm2 = present;
     }   // planes
+    const uint32_t has_lo = pm0 ? 1u : 0u, has_hi = pm2 ? 1u : 0u;    // lowest / highest plane non-empty
+    if (vmask && live) reinterpret_cast<uint4*>(vmask)[o] = make_uint4(pm0, pm1, pm2, 0u);
     if (sorting && live) {
       // sort key of the voxel (see k_pattern_keys): Gray-code rank of [has t+1][has t-1][27 spatial bits, OR over the planes]
       uint32_t g = shape_bits(por) | (has_lo << 27) | (has_hi << 28);
@@ -672,7 +673,8 @@ k_pattern_keys(const SortArgs A, uint32_t* __restrict__ keys, int32_t* __restric
   __syncthreads();
   const uint32_t* __restrict__ vm = A.vmask[L];
   for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += gridDim.x * blockDim.x) {
-    const uint32_t m0 = vm[o], m1 = vm[A.ld + o], m2 = vm[2 * A.ld + o];
+    const uint4 vm4 = reinterpret_cast<const uint4*>(vm)[o];
+    const uint32_t m0 = vm4.x, m1 = vm4.y, m2 = vm4.z;
     // The 29 shape bits are read as a Gray code and replaced by their RANK in the Gray sequence (prefix XOR from the top):
     // neighbouring keys then differ in one offset instead of arbitrarily many in the low bits, so a tile that straddles
     // two shapes walks one offset more, not their whole difference (offsets walked per tile -3..4 %, tools/tile_stats.py)
@@ -830,7 +832,8 @@ k_tile_masks_perm(const SliceArgs A) {
     int v = -1;
     if (r < n) {
       v = perm[r];
-      const uint32_t m0 = vmask[v], m1 = vmask[ld + v], m2 = vmask[2 * ld + v];   // 27 bits per time plane
+      const uint4 vm4 = __ldg(reinterpret_cast<const uint4*>(vmask) + v);          // 27 bits per time plane, one 16-byte read
+      const uint32_t m0 = vm4.x, m1 = vm4.y, m2 = vm4.z;
       w0 = m0 | (m1 << 27);
       w1 = (m1 >> 5) | (m2 << 22);
       w2 = m2 >> 10;

@@ -7,7 +7,7 @@ R=${1:-r2}
 set -x
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,l1tex__throughput.avg.pct_of_peak_sustained_elapsed,lts__throughput.avg.pct_of_peak_sustained_elapsed,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,l1tex__t_sector_hit_rate.pct,lts__t_sector_hit_rate.pct,smsp__issue_active.avg.pct_of_peak_sustained_active
 # the two timed device-resident steps of a single-lane bench run (NL launches per forward; 3 warm-up forwards before)
-NL=${NL:-57}
+NL=${NL:-56}
 ncu --metrics gpu__time_duration.sum --clock-control none -s $((3 * NL)) -c $((2 * NL)) --csv --log-file gpurun_out/${R}_launches.csv python bench.py --steps 2 --warmup 3 --lanes 1 --no-cpu-baseline --no-alt > gpurun_out/${R}_launches_bench.log 2>&1
 ncu --metrics $M --clock-control none -s $NL -c $NL --csv --log-file gpurun_out/${R}_forward_metrics.csv python tools/profile_forward.py 2 > gpurun_out/${R}_forward_metrics.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"k_kernel_map_blk3|k_conv_umma6|k_onesweep_pass|k_tile_masks_perm" -s 30 -c 30 -o /tmp/top_${R} python tools/profile_forward.py 2 > gpurun_out/${R}_top_full.log 2>&1
