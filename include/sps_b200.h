@@ -115,6 +115,10 @@ int sps_unpack_coords(sps_ctx* ctx, int level, int32_t* d_out, void* stream);
  *                       sum_c (hi_c + lo_c) * w_c, exact products, fp32 accumulation. */
 #define SPS_CONV_FOLD_LO 1
 #define SPS_CONV_OUT_SPLIT 2
+/* SPS_CONV_MAP_PARENT (tensor-core path, NBR mode, K == 8): `map` is the fine level's parent array -- parent[row] =
+ * coarse_row * 8 + k (sps_ctx_level.parent) -- instead of a dense [8][map_ld] table: entry k of a row is (p & 7) == k ? p >> 3 : -1.
+ * The transposed convolution (minkunet.py:107-147) needs no up-map this way. */
+#define SPS_CONV_MAP_PARENT 4
 typedef struct sps_conv_args {
   int mode;                 /* SPS_CONV_NBR | SPS_CONV_UP                                    */
   int K;                    /* kernel volume (125, 81, 8, 1)                                 */
@@ -158,7 +162,7 @@ typedef struct sps_conv_args {
                                (same 10-bit mantissa as the TF32 operands, half the bytes per gathered row)   */
   int backend;              /* SPS_BACKEND_*: which kernel family serves this call (AUTO: tensor cores where
                                the layer shape and the optional inputs allow, CUDA cores otherwise)          */
-  int flags;                /* SPS_CONV_FOLD_LO | SPS_CONV_OUT_SPLIT (fp16 rows on the tensor-core path only) */
+  int flags;                /* SPS_CONV_FOLD_LO | SPS_CONV_OUT_SPLIT (fp16 rows on the tensor-core path only) | SPS_CONV_MAP_PARENT */
   int cin_split;            /* 0, or the channels of the FIRST of two segments of `in` rows (a concat buffer,
                                minkunet.py:192: 64 + 32, 32 + 16 or 16 + 8 channels, fp16 rows, tensor-core path):
                                the K axis of weight_kmajor (sps_conv_pack_kmajor_f16s) then walks segment by

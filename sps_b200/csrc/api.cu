@@ -63,7 +63,6 @@ static size_t carve(sps_ctx* c, void* base, int64_t max_points) {
     c->vmask[L] = cv.take<uint32_t>((size_t)4 * ld);
     c->parent[L] = (L < SPS_NUM_LEVELS - 1) ? cv.take<int32_t>(N) : nullptr;
     c->child[L] = (L > 0) ? cv.take<int32_t>((size_t)8 * ld) : nullptr;
-    c->upmap[L] = (L < SPS_NUM_LEVELS - 1) ? cv.take<int32_t>((size_t)8 * ld) : nullptr;
     c->perm_up[L] = (L < SPS_NUM_LEVELS - 1) ? cv.take<int32_t>(N) : nullptr;
     c->tmask_up[L] = (L < SPS_NUM_LEVELS - 1) ? cv.take<uint32_t>((size_t)(ld / 128 + 1) * 4) : nullptr;
   }
@@ -89,8 +88,9 @@ bool conv_umma_f16_supports(const sps_conv_args& a);
 // is no CUDA-core kernel for them), else the CUDA-core kernels.
 int conv_dispatch(const sps_conv_args& a, cudaStream_t st) {
   if (a.io_dtype == SPS_IO_F16) return conv_umma_f16_supports(a) ? conv_umma(a, st) : SPS_ERR_UNSUPPORTED;
-  if (a.flags || a.cin_split) return SPS_ERR_UNSUPPORTED;      // split-precision options and K segments exist on fp16 rows only
+  if ((a.flags & ~SPS_CONV_MAP_PARENT) || a.cin_split) return SPS_ERR_UNSUPPORTED;   // split-precision options and K segments exist on fp16 rows only
   if (a.backend != SPS_BACKEND_FP32 && conv_umma_supports(a)) return conv_umma(a, st);
+  if (a.flags & SPS_CONV_MAP_PARENT) return SPS_ERR_UNSUPPORTED;                      // the CUDA-core kernels want a dense table
   return conv_simt(a, st);
 }
 

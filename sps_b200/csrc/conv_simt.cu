@@ -299,7 +299,7 @@ extern "C" int sps_conv_fwd(const sps_conv_args* a, void* stream) {
   if (!a || !a->in || !a->weight || !a->n_out || (!a->out && !a->head_out)) return SPS_ERR_BAD_ARG;
   if (a->mode != SPS_CONV_NBR && a->mode != SPS_CONV_UP) return SPS_ERR_BAD_ARG;
   if (a->backend < SPS_BACKEND_AUTO || a->backend > SPS_BACKEND_F16) return SPS_ERR_BAD_ARG;
-  if ((a->io_dtype != SPS_IO_F32 && a->io_dtype != SPS_IO_F16) || (a->flags & ~(SPS_CONV_FOLD_LO | SPS_CONV_OUT_SPLIT)) ||
+  if ((a->io_dtype != SPS_IO_F32 && a->io_dtype != SPS_IO_F16) || (a->flags & ~(SPS_CONV_FOLD_LO | SPS_CONV_OUT_SPLIT | SPS_CONV_MAP_PARENT)) ||
       a->cin_split < 0 || (a->cin_split && a->cin_split >= a->cin))
     return SPS_ERR_BAD_ARG;
   if (a->mode == SPS_CONV_UP && (!a->map || a->K != 8 || !a->out || a->in2 || a->res || a->head_out || (a->cin & 3)))

@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(kV6Threads, NPAD <= 64 ? SPS_V6_CTAS_PER_SM : 
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)e * kV6EntryBytes),
                        "l"(src + (size_t)e * kV6EntryBytes)
                        : "memory");
-      } else if (!a.perm && map_vec && tile * kTileM + kTileM <= n_out) {
+      } else if (!a.perm && map_vec && !(p.flags & SPS_CONV_MAP_PARENT) && tile * kTileM + kTileM <= n_out) {
         // physical row order, full tile: the slice of map[k] is contiguous -> one 16-byte copy per lane and entry
         const int row0 = tile * kTileM + 4 * lane;
         asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)nact * kV6EntryBytes), "r"(row0),
@@ -413,17 +413,29 @@ __global__ void __launch_bounds__(kV6Threads, NPAD <= 64 ? SPS_V6_CTAS_PER_SM : 
       } else {
         const int32_t* src[4];
         bool rok[4];
+        int pw[4];   // SPS_CONV_MAP_PARENT: the rows' parent words (coarse row * 8 + child class)
+        const bool from_parent = (p.flags & SPS_CONV_MAP_PARENT) != 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int prow = tile * kTileM + 4 * lane + i;
           rok[i] = prow < n_out;
           const int row = rok[i] ? (a.perm ? __ldg(a.perm + prow) : prow) : 0;
           src[i] = a.map + row;
+          pw[i] = (from_parent && rok[i]) ? __ldg(a.map + row) : -1;
           asm volatile("st.shared.s32 [%0], %1;" ::"r"(dst + (uint32_t)nact * kV6EntryBytes + 4u * i), "r"(rok[i] ? row : -1) : "memory");
         }
         for (int e = 0; e < nact; ++e) {
           const int64_t koff = (int64_t)klp[e] * a.map_ld;
           const uint32_t d = dst + (uint32_t)e * kV6EntryBytes;
+          if (from_parent) {
+            const int k = klp[e];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int val = (pw[i] >= 0 && (pw[i] & 7) == k) ? (pw[i] >> 3) : -1;
+              asm volatile("st.shared.s32 [%0], %1;" ::"r"(d + 4u * i), "r"(val) : "memory");
+            }
+            continue;
+          }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             if (rok[i]) cp_async4(d + 4u * i, src[i] + koff);
@@ -684,6 +696,7 @@ int conv_umma(const sps_conv_args& a, cudaStream_t st) {
 bool conv_umma_supports(const sps_conv_args& a) {
   if (a.io_dtype != SPS_IO_F32 || a.mode != SPS_CONV_NBR || !a.map || !a.weight_kmajor || !a.tile_mask) return false;
   if (a.K < 1 || a.K > kMaxK || a.cin_split) return false;
+  if ((a.flags & SPS_CONV_MAP_PARENT) && a.K != 8) return false;
   if (a.cin < 4 || (a.cin & 3) || (a.in_ld & 3)) return false;
   if (a.in2 && ((a.cin2 & 3) || (a.in2_ld & 3))) return false;
   if (!(a.cout == 8 || a.cout == 16 || a.cout == 32 || a.cout == 64)) return false;
@@ -718,6 +731,7 @@ bool conv_umma_f16_supports(const sps_conv_args& a) {
   if (a.io_dtype != SPS_IO_F16 || a.mode != SPS_CONV_NBR || (!a.map && !a.tile_slices) || !a.weight_kmajor || !a.tile_mask) return false;
   if (a.tile_slices && !a.perm) return false;
   if (a.K < 1 || a.K > kMaxK) return false;
+  if ((a.flags & SPS_CONV_MAP_PARENT) && (a.K != 8 || !a.map || a.tile_slices)) return false;
   if (a.cin < 8 || (a.cin & 7) || (a.in_ld & 7)) return false;
   if (a.in2 && ((a.cin2 & 7) || (a.in2_ld & 7))) return false;
   if (a.res && (a.res_ld & 7)) return false;

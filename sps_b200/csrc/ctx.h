@@ -53,7 +53,6 @@ struct sps_ctx {
   int32_t* inv = nullptr;                      // [max_points] point -> level-0 row
   int32_t* parent[SPS_NUM_LEVELS] = {};        // [L] fine row -> parent*8 + k   (L = 0..3)
   int32_t* child[SPS_NUM_LEVELS] = {};         // [L] [8][ld] children of level-L rows (L = 1..4)
-  int32_t* upmap[SPS_NUM_LEVELS] = {};         // [L] [8][ld] transposed-conv map of level-L rows (L = 0..3)
   uint32_t* vmask[SPS_NUM_LEVELS] = {};        // [L] [ld][4] per-voxel 27-bit presence words of the 3x3x3 neighbours in the three time planes (+ pad)
   int32_t* perm[SPS_NUM_LEVELS] = {};          // [L] rows of level L in neighbourhood-shape order (conv processing order)
   uint32_t* ptmask[SPS_NUM_LEVELS] = {};       // [L] tile masks of nbr3 in perm order
@@ -66,7 +65,7 @@ struct sps_ctx {
   uint32_t* sort_status = nullptr;
   int32_t* up_cls = nullptr;                   // [4][16] per fine level: rows per 2x2x2 child class (8) + scatter cursors (8)
   int32_t* perm_up[SPS_NUM_LEVELS] = {};       // [L] rows of level L grouped by child class: processing order of the transposed conv INTO level L
-  uint32_t* tmask_up[SPS_NUM_LEVELS] = {};     // [L] tile masks of upmap[L] in that order (one or two classes per tile)
+  uint32_t* tmask_up[SPS_NUM_LEVELS] = {};     // [L] tile masks of the 8-class up-map in that order (one or two classes per tile)
   uint32_t* tmask8 = nullptr;                  // [tiles][4] all-eight-offsets mask for the 2x2x2x1 maps
   int32_t* nbr3[SPS_NUM_LEVELS] = {};          // [81][ld]
   int32_t* nbr5 = nullptr;                     // [125][ld]

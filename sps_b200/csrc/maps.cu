@@ -168,8 +168,7 @@ __global__ void k_assign_coarse(Slot* tab, const uint32_t* __restrict__ slot_of,
                                 const int32_t* __restrict__ rank, const int32_t* __restrict__ block_sums,
                                 const unsigned long long* __restrict__ fine, int log2s,
                                 unsigned long long* __restrict__ ukeys, int32_t* __restrict__ parent,
-                                int32_t* __restrict__ child, int32_t* __restrict__ upmap, int64_t ld,
-                                int32_t* __restrict__ cls) {
+                                int32_t* __restrict__ child, int64_t ld, int32_t* __restrict__ cls) {
   __shared__ int s_cls[8];
   if (threadIdx.x < 8) s_cls[threadIdx.x] = 0;
   __syncthreads();
@@ -183,10 +182,7 @@ __global__ void k_assign_coarse(Slot* tab, const uint32_t* __restrict__ slot_of,
     atomicAdd(&s_cls[k], 1);                                    // rows per child class (order of the transposed conv)
     parent[i] = id * 8 + k;
     child[(int64_t)k * ld + id] = i;
-    // transposed-conv kernel map in the dense [8][ld] form the tensor-core kernel walks:
-    // upmap[k'][f] = parent row if k' == k(f), else absent
-#pragma unroll
-    for (int kk = 0; kk < 8; ++kk) upmap[(int64_t)kk * ld + i] = kk == k ? id : -1;
+    // (the transposed convolution reads `parent` itself: SPS_CONV_MAP_PARENT -- no dense [8][ld] up-map is written)
     if (f == i) ukeys[id] = ((unsigned long long)(unsigned)raw.y << 32) | (unsigned)raw.x;
   }
   __syncthreads();
@@ -1175,7 +1171,7 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
                                               ctx->ticket, ctx->counts + L, nullptr, 0, nullptr);
     k_assign_coarse<<<grid_for(n, 256), 256, 0, st>>>(tab, ctx->slot_of, n_fine, ctx->rank, sums,
                                                        ctx->keys[L - 1], L - 1, ctx->keys[L], ctx->parent[L - 1],
-                                                       ctx->child[L], ctx->upmap[L - 1], ctx->ld, ctx->up_cls + 16 * (L - 1));
+                                                       ctx->child[L], ctx->ld, ctx->up_cls + 16 * (L - 1));
     static const char* nm_s[5] = {"", "stride.L1", "stride.L2", "stride.L3", "stride.L4"};
     prof_mark(ctx, nm_s[L], st);
   }

@@ -281,6 +281,7 @@ struct Act {
 struct ConvIo {
   const uint32_t* tmask; const int32_t* perm; const int32_t* slices;   // processing order (see sps_conv_args)
   int mode; const int32_t* map;
+  int flags = 0;                                                        // SPS_CONV_MAP_PARENT
 };
 
 // One layer of the fused forward.  FP32 mode: generic fp32 CUDA-core kernels; TF32 mode: fp32 rows, the tcgen05 kernel
@@ -310,6 +311,7 @@ static int run_conv(sps_ctx* c, const ConvIo& io, const char* name, const ConvW&
     a.weight_kmajor = w.wt; a.kmajor_ld = w.ldk;
   }
   a.tile_mask = io.tmask; a.perm = io.perm; a.tile_slices = io.perm ? io.slices : nullptr;
+  a.flags |= io.flags;
   a.round_out = c->backend != SPS_BACKEND_FP32;   // pure fp32 mode keeps full-precision activations
   a.backend = c->backend;
   ++c->forward_launches;
@@ -384,7 +386,7 @@ int unet_forward(sps_ctx* c, const sps_net* net, const float* feat0, float* logi
           none, cat[L], st);
     } else {       // the same transposed conv as an 8-offset gather map of the fine rows
       // rows visited by child class (perm_up): a tile walks one of the eight offsets instead of all of them
-      RUN(ConvIo{c->tmask_up[L], c->perm_up[L], nullptr, SPS_CONV_NBR, c->upmap[L]}, nm_up[i], net->up[i], c->counts + L, nmax, dec_in, none, none,
+      RUN(ConvIo{c->tmask_up[L], c->perm_up[L], nullptr, SPS_CONV_NBR, c->parent[L], SPS_CONV_MAP_PARENT}, nm_up[i], net->up[i], c->counts + L, nmax, dec_in, none, none,
           cat[L], st);
     }
     const ConvW& c1 = net->blk1[4 + i];
