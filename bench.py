@@ -473,41 +473,57 @@ class Dist:
 
 
 class ScoreGather:
-    """The only collective of the path (north star): all ranks' SCAN-row scores of a step -- fp32 [batch x points per
-    scan], not the padded scores of every input row -- gathered with one all_gather_into_tensor on the comm stream,
-    behind the lane's completion event.  Optionally the per-scan metric partials travel with it (config 4)."""
+    """The only collective of the path (north star): all ranks' SCAN-row scores -- fp32 [batch x points per scan] per step,
+    not the padded scores of every input row -- gathered with one all_gather_into_tensor on the comm stream, behind the
+    lane's completion.  `every` steps share one collective ("at the end, or every B scans"): a collective per
+    step couples the ranks step by step -- every rank's NCCL kernel spins on SMs until the slowest rank arrives, which cost
+    0.1 ms per 2.5 ms step at 2..8 GPUs.  Optionally the per-scan metric partials travel with it (config 4)."""
 
-    def __init__(self, d: Dist, scan_rows, n_scan_total, with_partials=False):
+    def __init__(self, d: Dist, scan_rows, n_scan_total, with_partials=False, every=1):
         torch = d.torch
         self.d = d
         self.scan_rows = scan_rows                     # per distinct batch: int32 device positions of the t == 1 rows
-        self.buf = torch.empty(n_scan_total, dtype=torch.float32, device="cuda")
-        self.all = torch.empty(d.world * n_scan_total, dtype=torch.float32, device="cuda") if d.world > 1 else None
+        self.n, self.every, self.keys = n_scan_total, max(1, every), []
+        self.buf = torch.empty(self.every * n_scan_total, dtype=torch.float32, device="cuda")
+        self.all = torch.empty(d.world * self.every * n_scan_total, dtype=torch.float32, device="cuda") if d.world > 1 else None
         self.events = []
         self.with_partials = with_partials
         if with_partials:
-            self.counts = torch.zeros((BATCH, 4), dtype=torch.int64, device="cuda")
-            self.sums = torch.zeros((BATCH, 5), dtype=torch.float64, device="cuda")
-            self.all_counts = torch.zeros((d.world, BATCH, 4), dtype=torch.int64, device="cuda")
-            self.all_sums = torch.zeros((d.world, BATCH, 5), dtype=torch.float64, device="cuda")
+            self.counts = torch.zeros((self.every, BATCH, 4), dtype=torch.int64, device="cuda")
+            self.sums = torch.zeros((self.every, BATCH, 5), dtype=torch.float64, device="cuda")
+            self.all_counts = torch.zeros((d.world, self.every, BATCH, 4), dtype=torch.int64, device="cuda")
+            self.all_sums = torch.zeros((d.world, self.every, BATCH, 5), dtype=torch.float64, device="cuda")
         from sps_b200 import _cabi
         self.lib = _cabi.load()
 
     def publish(self, scores_dev, k, rows_dev=None, eps=0.84, sink=None):
-        """Enqueue on the comm stream: compact the scan rows of ``scores_dev`` (the step's device scores), gather."""
+        """Enqueue on the comm stream: compact the scan rows of ``scores_dev`` (the step's device scores) into this
+        step's slot; the collective goes out when `every` slots are filled (or at flush())."""
         torch, d = self.d.torch, self.d
         if d.world == 1 and not self.with_partials:
             return
         idx = self.scan_rows[k % len(self.scan_rows)]
+        slot = len(self.keys)
         with torch.cuda.stream(d.comm):
             st = C.c_void_p(d.comm.cuda_stream)
             self.lib.sps_gather_rows(C.c_void_p(scores_dev.data_ptr()), 1, 1, C.c_void_p(idx.data_ptr()), idx.numel(),
-                                     C.c_void_p(self.buf.data_ptr()), st)
+                                     C.c_void_p(self.buf.data_ptr() + 4 * slot * self.n), st)
             if self.with_partials:
                 for b in range(BATCH):   # SPSNet.predict_step partials per scan (models.py:84-104)
                     self.lib.sps_confusion_counts(C.c_void_p(scores_dev.data_ptr()), C.c_void_p(rows_dev.data_ptr()),
                                                   rows_dev.stride(0), rows_dev.shape[0], float(b), float(eps),
-                                                  C.c_void_p(self.counts[b].data_ptr()), C.c_void_p(self.sums[b].data_ptr()), st)
+                                                  C.c_void_p(self.counts[slot, b].data_ptr()),
+                                                  C.c_void_p(self.sums[slot, b].data_ptr()), st)
+        self.keys.append(k)
+        if len(self.keys) >= self.every:
+            self.flush(sink)
+
+    def flush(self, sink=None):
+        """The collective over the filled slots (always the whole buffer: unused slots carry stale bytes)."""
+        torch, d = self.d.torch, self.d
+        if not self.keys:
+            return
+        with torch.cuda.stream(d.comm):
             if d.world > 1:
                 d.dist.all_gather_into_tensor(self.all, self.buf)
                 if self.with_partials:
@@ -517,11 +533,12 @@ class ScoreGather:
                 self.all_counts[0].copy_(self.counts)
                 self.all_sums[0].copy_(self.sums)
             if sink is not None:
-                sink(self)
+                sink(self, list(self.keys))
             ev = torch.cuda.Event()
             ev.record(d.comm)
+        self.keys = []
         self.events.append(ev)
-        if len(self.events) > 2:          # a lane's score buffer is reused three steps later: never overtake its reader
+        if len(self.events) > 1:          # the slot buffer is rewritten by the next round: never overtake the collective
             self.events.pop(0).synchronize()
 
 
@@ -548,7 +565,7 @@ def run_config2(args):
     scan_rows = [torch.as_tensor(np.nonzero(b[:, 4] == 1)[0].astype(np.int32)).cuda() for b in batches]
     n_max = max(len(h) for h in host)
     model, engine, net, sd = setup_model(args, n_max, d.local)
-    gather = ScoreGather(d, scan_rows, BATCH * PTS_PER_SCAN)
+    gather = ScoreGather(d, scan_rows, BATCH * PTS_PER_SCAN, every=args.gather_every)
     pending = []
 
     def step(inputs):
@@ -567,6 +584,7 @@ def run_config2(args):
             kk, p = pending.pop(0)
             p.result()
             gather.publish(p.device_scores, kk)
+        gather.flush()
 
     def measure(inputs, steps):
         fn = step(inputs)
@@ -604,8 +622,8 @@ def run_config2(args):
                    "l2": f"per-step working set (kernel maps + features, several GB) exceeds the 126 MB L2; "
                          f"{len(host)} distinct batches rotate",
                    "conv_backend": args.backend, "lanes": args.lanes, "cuda_graphs": bool(model.use_graphs), "tma_weight_stages": bool(engine.lib.sps_tma_weights_available()),
-                   "sharding": "scan-sharded, replicated weights; per step one NCCL all_gather_into_tensor of the "
-                               f"scan-row scores (fp32 [{BATCH} x {PTS_PER_SCAN}] per rank) on a dedicated stream",
+                   "sharding": f"scan-sharded, replicated weights; every {args.gather_every} steps one NCCL all_gather_into_tensor of the "
+                               f"scan-row scores (fp32 [{BATCH} x {PTS_PER_SCAN}] per rank and step) on a dedicated stream",
                    "cpus_bound_to_gpu_numa": d.numa},
         "mpoints_per_s": value * PTS_PER_SCAN / 1e6,
         "e2e": {"value": e2e, "unit": "scans/s", "ms_per_step": ms_host / args.steps,
@@ -758,19 +776,21 @@ def run_config4(args):
     scan_rows = [torch.as_tensor(np.nonzero(b[:, 4] == 1)[0].astype(np.int32)).cuda() for b in batches]
     n_max = max(len(x) for x in dev)
     model, engine, net, sd = setup_model(args, n_max, d.local)
-    gather = ScoreGather(d, scan_rows, BATCH * PTS_PER_SCAN, with_partials=True)
+    gather = ScoreGather(d, scan_rows, BATCH * PTS_PER_SCAN, with_partials=True, every=args.gather_every)
     tot_counts = torch.zeros((steps, d.world, BATCH, 4), dtype=torch.int64, device="cuda")
     tot_sums = torch.zeros((steps, d.world, BATCH, 5), dtype=torch.float64, device="cuda")
     pending = []
+
+    def sink(g, keys):      # the gathered partials of the steps of one collective -> their rows of the totals
+        for slot, kk in enumerate(keys):
+            if kk < steps:
+                tot_counts[kk].copy_(g.all_counts[:, slot])
+                tot_sums[kk].copy_(g.all_sums[:, slot])
 
     def finish_one():
         kk, p = pending.pop(0)
         p.result()
 
-        def sink(g, kk=kk):
-            if kk < steps:
-                tot_counts[kk].copy_(g.all_counts)
-                tot_sums[kk].copy_(g.all_sums)
         gather.publish(p.device_scores, kk, rows_dev=rows_dev[kk % len(rows_dev)], sink=sink)
 
     def fn(k):
@@ -781,6 +801,7 @@ def run_config4(args):
     def drain():
         while pending:
             finish_one()
+        gather.flush(sink)
 
     for k in range(max(args.warmup, 3, (3 * model.lanes * len(dev)) if model.use_graphs else 0)):
         fn(k)
@@ -830,6 +851,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt", action="store_true", help="skip the backend-2 (TF32) comparison line")
     ap.add_argument("--no-graphs", action="store_true", help="enqueue every forward kernel by kernel instead of replaying CUDA graphs")
+    ap.add_argument("--gather-every", type=int, default=4,
+                    help="multi-GPU: steps whose scan-row scores (and metric partials) share one NCCL all-gather")
     ap.add_argument("--lanes", type=int, default=3, help="engine contexts/streams forward_async alternates between")
     ap.add_argument("--widths", default="1,2,4,8", help="config 5: PLANES multipliers of the sweep")
     args = ap.parse_args()
