@@ -597,7 +597,9 @@ k_kernel_map_blk3(const LevelTabs T, const KmapOut O) {
     const uint32_t has_lo = pm0 ? 1u : 0u, has_hi = pm2 ? 1u : 0u;    // lowest / highest plane non-empty
     if (vmask && live) reinterpret_cast<uint4*>(vmask)[o] = make_uint4(pm0, pm1, pm2, 0u);
     if (sorting && live) {
-      // sort key of the voxel (see k_pattern_keys): Gray-code rank of [has t+1][has t-1][27 spatial bits, OR over the planes]
+      // sort key of the voxel: the Gray-code RANK of [has t+1][has t-1][27 spatial bits, OR over the planes] -- neighbouring
+      // keys then differ in one offset instead of arbitrarily many in the low bits, so a tile that straddles two shapes walks
+      // one offset more, not their whole difference (offsets walked per tile -3..4 %, tools/tile_stats.py)
       uint32_t g = shape_bits(por) | (has_lo << 27) | (has_hi << 28);
       g ^= g >> 1; g ^= g >> 2; g ^= g >> 4; g ^= g >> 8; g ^= g >> 16;
       const uint32_t skey = g | ((uint32_t)(L - O.sort_first) << 29);
@@ -656,37 +658,6 @@ __device__ __forceinline__ uint32_t shape_bits(uint32_t pat) {
 #pragma unroll
   for (int pos = 0; pos < 27; ++pos) key |= ((pat >> order[pos]) & 1u) << pos;
   return key;
-}
-
-__global__ void __launch_bounds__(256)
-k_pattern_keys(const SortArgs A, uint32_t* __restrict__ keys, int32_t* __restrict__ vals, uint32_t* __restrict__ hist) {
-  __shared__ uint32_t h[4][256];
-  const int j = blockIdx.y, L = A.first + j;
-  const int n = A.counts[L];
-  int off = 0;
-  for (int q = 0; q < j; ++q) off += A.counts[A.first + q];
-  for (int i = threadIdx.x; i < 1024; i += blockDim.x) (&h[0][0])[i] = 0u;
-  __syncthreads();
-  const uint32_t* __restrict__ vm = A.vmask[L];
-  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += gridDim.x * blockDim.x) {
-    const uint4 vm4 = reinterpret_cast<const uint4*>(vm)[o];
-    const uint32_t m0 = vm4.x, m1 = vm4.y, m2 = vm4.z;
-    // The 29 shape bits are read as a Gray code and replaced by their RANK in the Gray sequence (prefix XOR from the top):
-    // neighbouring keys then differ in one offset instead of arbitrarily many in the low bits, so a tile that straddles
-    // two shapes walks one offset more, not their whole difference (offsets walked per tile -3..4 %, tools/tile_stats.py)
-    uint32_t g = shape_bits(m0 | m1 | m2) | ((m0 ? 1u : 0u) << 27) | ((m2 ? 1u : 0u) << 28);
-    g ^= g >> 1; g ^= g >> 2; g ^= g >> 4; g ^= g >> 8; g ^= g >> 16;
-    const uint32_t key = g | ((uint32_t)j << 29);
-    keys[off + o] = key;
-    vals[off + o] = o;
-#pragma unroll
-    for (int p = 0; p < 4; ++p) atomicAdd(&h[p][(key >> (8 * p)) & 255u], 1u);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
-    const uint32_t c = (&h[0][0])[i];
-    if (c) atomicAdd(hist + i, c);
-  }
 }
 
 // One radix pass over the concatenated levels.  LAST: the sorted row numbers go to the per-level perm arrays.
@@ -1109,15 +1080,14 @@ static inline bool sort_active(const sps_ctx* ctx) {
 
 // perm[L] = voxel rows of level L sorted by neighbourhood-shape key, ptmask[L] = tile masks in that order, tslice[L] = the
 // kernel map gathered per sorted tile -- for all sorted levels at once: 1 + 4 + 1 launches.
-static int pattern_order(sps_ctx* ctx, cudaStream_t st, bool keys_done) {
+static int pattern_order(sps_ctx* ctx, cudaStream_t st) {
   if (!sort_active(ctx)) return SPS_OK;
   const int64_t n = ctx->n > 0 ? ctx->n : 1;
   SortArgs A;
   for (int L = 0; L < SPS_NUM_LEVELS; ++L) { A.vmask[L] = ctx->vmask[L]; A.perm[L] = ctx->perm[L]; }
   A.counts = ctx->counts; A.status = ctx->status; A.ld = ctx->ld; A.first = kFirstSortedLevel; A.nlv = kSortedLevels;
   uint32_t* hist = ctx->sort_hist;
-  if (!keys_done)   // (the 3x3x3x3 kernel-map pass normally leaves keys, row numbers and histograms behind)
-    k_pattern_keys<<<dim3(grid_for(n, 256, 148 * 8), kSortedLevels), 256, 0, st>>>(A, ctx->sort_keys[0], ctx->sort_vals[0], hist);
+  // (keys, row numbers and digit histograms were left behind by the 3x3x3x3 kernel-map pass)
   const int tiles_max = cdiv(n * kSortedLevels, kSortTile);
   for (int pass = 0; pass < 4; ++pass) {
     const uint32_t* ki = ctx->sort_keys[pass & 1];
@@ -1141,7 +1111,7 @@ static int pattern_order(sps_ctx* ctx, cudaStream_t st, bool keys_done) {
   k_tile_masks_perm<<<dim3(grid_for(n / 128 + 1, 1, 148 * 8), kSortedLevels), 128, 0, st>>>(S);
   prof_mark(ctx, "slices", st);
   SPS_CUDA_CHECK(cudaGetLastError());
-  ctx->forward_launches += keys_done ? 5 : 6;
+  ctx->forward_launches += 5;
   return SPS_OK;
 }
 }
@@ -1236,7 +1206,7 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
   SPS_CUDA_CHECK(cudaGetLastError());
   ctx->forward_launches += 16 + 1 + 3 + 1 + 1;
   // ---- 5. shape sort + per-tile slices of the sorted levels ----
-  { const int rc = pattern_order(ctx, st, /*keys_done=*/sorting); if (rc != SPS_OK) return rc; }
+  { const int rc = pattern_order(ctx, st); if (rc != SPS_OK) return rc; }
   ctx->have_maps = true;
   ctx->dense_maps = O.dense_mask == (1 << SPS_NUM_LEVELS) - 1;
   ctx->have_perm = sorting;

@@ -19,7 +19,7 @@ fwd = seq[n:]
 groups = [("`k_conv_umma6<*>` (all instantiations)", lambda k: k.startswith("k_conv_umma6"),
            [k for k in st if k.startswith(("conv1", "conv2", "conv3", "conv4", "convtr", "block")) and k != "blocks"]),
           ("`k_kernel_map_blk3<3>`", lambda k: k.startswith("k_kernel_map_blk3"), ["kmap3"]),
-          ("shape sort (`k_pattern_keys`, 4 x `k_onesweep_pass`)", lambda k: k.startswith(("k_pattern_keys", "k_onesweep")), ["sort"]),
+          ("shape sort (4 x `k_onesweep_pass`; the keys come out of the kernel-map pass)", lambda k: k.startswith("k_onesweep"), ["sort"]),
           ("`k_tile_masks_perm`", lambda k: k.startswith("k_tile_masks_perm"), ["slices"]),
           ("`k_conv0_const`", lambda k: k.startswith("k_conv0"), ["conv0+kmap5"]),
           ("strided levels (`k_level_begin`, `k_insert_coarse`, `k_first_rank`, `k_assign_coarse` x 4)", None,

@@ -16,7 +16,7 @@ from sps_b200 import synth  # noqa: E402
 
 
 def shape_key(nbr):
-    """the 29-bit key of csrc/maps.cu:k_pattern_keys: [has dt=+1][has dt=-1][27-bit spatial presence, OR over t]"""
+    """the 29-bit key of csrc/maps.cu (k_kernel_map_blk3): [has dt=+1][has dt=-1][27-bit spatial presence, OR over t]"""
     pres = (nbr >= 0)
     V = nbr.shape[1]
     m = [np.zeros(V, np.int64) for _ in range(3)]
