@@ -639,7 +639,7 @@ struct SortArgs {
   int64_t ld;
   int first, nlv;
 };
-constexpr int kSortThreads = 256, kSortItems = 4, kSortTile = kSortThreads * kSortItems;
+constexpr int kSortThreads = 256, kSortItems = 8, kSortTile = kSortThreads * kSortItems;
 constexpr uint32_t kOsAggregate = 1u << 30, kOsPrefix = 2u << 30, kOsValue = (1u << 30) - 1u;
 
 // Bit order of the spatial part of the key: a tile of 128 consecutive sorted rows shares the HIGH bits of the key and
@@ -661,8 +661,9 @@ __device__ __forceinline__ uint32_t shape_bits(uint32_t pat) {
 }
 
 // One radix pass over the concatenated levels.  LAST: the sorted row numbers go to the per-level perm arrays.
-// 256 threads x 4 keys per tile (1024 keys, element order = round-major): small blocks with few registers and 17 KB of
-// shared memory, so that the sort co-runs with another lane's convolution CTAs instead of waiting for a free SM.
+// 256 threads x 8 keys per tile (2048 keys, element order = round-major; 48 registers, 34 KB of shared memory): the per-tile
+// work -- prefix over the slot counters, look-back over the predecessors' status words -- is amortised over twice the keys
+// of the first version (4 keys per thread: 49 us per pass, now 37 us; 10 keys per thread measured the same as 8).
 template <bool LAST>
 __global__ void __launch_bounds__(kSortThreads)
 k_onesweep_pass(const SortArgs A, const uint32_t* __restrict__ keys, const int32_t* __restrict__ vals, int shift,
