@@ -20,6 +20,9 @@ constexpr uint32_t kInvalidSlot = 0xFFFFFFFFu;
 __global__ void k_set_i32(int32_t* p, int32_t v) { *p = v; }
 
 constexpr int kRankChunks = 4;    // chunks of kScanBlock rows a block of k_first_rank scans
+#ifndef SPS_SLICE_BATCH
+#define SPS_SLICE_BATCH 8
+#endif
 constexpr int kInsertBatch = 4;   // rows a thread of the level-0 insert kernel keeps in flight
 
 // First kernel of a level: empties the open-addressing table for `n` keys and, for a strided level, presets the
@@ -827,12 +830,21 @@ k_tile_masks_perm(const SliceArgs A) {
       __syncthreads();
       int32_t* dst = slices + (int64_t)tile * (SPS_TILE_SLICE_ENTRIES * 128) + threadIdx.x;
       const uint32_t mine[3] = {w0, w1, w2};
-#pragma unroll 4
-      for (int e = 0; e < nact; ++e) {
-        const int k = klist[e];
-        int val = -1;
-        if ((mine[k >> 5] >> (k & 31)) & 1u) val = __ldg(nbr + (int64_t)k * ld + v);
-        dst[e * 128] = val;
+      // eight entries at a time: the loads of a batch are issued before the first store (the pass waits on these random
+      // 4-byte reads; unroll depth = reads in flight per thread)
+      static_assert(SPS_SLICE_BATCH >= 1, "");
+      for (int e0 = 0; e0 < nact; e0 += SPS_SLICE_BATCH) {
+        int val[SPS_SLICE_BATCH];
+#pragma unroll
+        for (int u = 0; u < SPS_SLICE_BATCH; ++u) {
+          const int e = e0 + u;
+          const int k = e < nact ? klist[e] : 0;
+          val[u] = -1;
+          if (e < nact && ((mine[k >> 5] >> (k & 31)) & 1u)) val[u] = __ldg(nbr + (int64_t)k * ld + v);
+        }
+#pragma unroll
+        for (int u = 0; u < SPS_SLICE_BATCH; ++u)
+          if (e0 + u < nact) dst[(e0 + u) * 128] = val[u];
       }
       dst[nact * 128] = v;
     }
@@ -1181,7 +1193,7 @@ int sps::build_maps_impl(sps_ctx* ctx, const Conv0Fused* c0, cudaStream_t st) {
   O.ld = ctx->ld;
   O.sort_keys = sorting ? ctx->sort_keys[0] : nullptr; O.sort_vals = ctx->sort_vals[0]; O.sort_hist = ctx->sort_hist;
   O.sort_first = kFirstSortedLevel; O.sort_last = kLastSortedLevel;
-  const int gx = grid_for(n, 256, 148 * 8);
+  const int gx = grid_for(n, 256, 148 * 6);   // one wave of the kernel-map pass (6 blocks of 256 threads per SM at 40 registers)
   k_blocks_begin<<<dim3(grid_for(table_capacity(n), 256, 148 * 8), SPS_NUM_LEVELS), 256, 0, st>>>(T, Z);
   k_block_insert<<<dim3(gx, SPS_NUM_LEVELS), 256, 0, st>>>(T);
   k_cells_fill<<<dim3(gx, SPS_NUM_LEVELS), 256, 0, st>>>(T);
