@@ -16,7 +16,7 @@ SPS_NUM_LEVELS = 5
 SPS_CONV_NBR, SPS_CONV_UP = 0, 1
 SPS_BACKEND_AUTO, SPS_BACKEND_FP32, SPS_BACKEND_TF32, SPS_BACKEND_F16 = 0, 1, 2, 3
 SPS_IO_F32, SPS_IO_F16 = 0, 1
-SPS_CONV_FOLD_LO, SPS_CONV_OUT_SPLIT = 1, 2
+SPS_CONV_FOLD_LO, SPS_CONV_OUT_SPLIT, SPS_CONV_MAP_PARENT = 1, 2, 4
 SPS_PACK_IN_SPLIT, SPS_PACK_IN2_SPLIT, SPS_PACK_FOLD_LO = 1, 2, 4
 _ERR_NAMES = {1: "SPS_ERR_BAD_ARG", 2: "SPS_ERR_CAPACITY", 3: "SPS_ERR_COORD_RANGE", 4: "SPS_ERR_CUDA",
               5: "SPS_ERR_UNSUPPORTED", 6: "SPS_ERR_STATE"}

@@ -331,3 +331,47 @@ def test_two_segment_input_rows(cin, cin_split, cout):
         if cout != 8:   # (folded low weight parts are more exact than the fp16-weight reference)
             assert np.abs(outs[1] - ref).max() < 2e-3 * scale, (fused, np.abs(outs[1] - ref).max())
         assert np.abs(outs[1] - outs[0]).max() < 2e-3 * scale, (fused, np.abs(outs[1] - outs[0]).max())
+
+
+@pytest.mark.parametrize("cin,cout,io_f16", [(64, 64, True), (32, 16, True), (16, 8, True), (64, 32, False)])
+def test_transposed_conv_reads_the_parent_array(cin, cout, io_f16):
+    """SPS_CONV_MAP_PARENT: `map` is the fine level's parent array (coarse row * 8 + child class) instead of a dense
+    [8][ld] up-map; the result equals the dense-map call bit for bit (same products, same order) and the float64
+    reference at the operand precision.  Ragged last tile, rows of every class."""
+    from sps_b200 import convops, _cabi
+    rng = np.random.default_rng(cin + cout)
+    v_out, v_in, K = 1000, 300, 8
+    parent_row = rng.integers(0, v_in, v_out)
+    cls = rng.integers(0, 8, v_out)
+    parent = (parent_row * 8 + cls).astype(np.int32)
+    ld = (v_out + 31) // 32 * 32
+    up = np.full((K, ld), -1, np.int32)
+    up[cls, np.arange(v_out)] = parent_row
+    x = rng.standard_normal((v_in, cin)).astype(np.float32)
+    w = (rng.standard_normal((K, cin, cout)) / np.sqrt(cin)).astype(np.float32)
+    shift = rng.standard_normal(cout).astype(np.float32)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a)).cuda()
+    n_out = torch.tensor([v_out], dtype=torch.int32, device="cuda")
+    masks = torch.zeros(((v_out + 127) // 128, 4), dtype=torch.int32, device="cuda")
+    masks[:, 0] = 0xFF
+    if io_f16:
+        wt = convops.pack_kmajor_f16x(t(w), fold_lo=cout == 8)
+        xin = t(x).half()
+        kw = dict(io_f16=True, backend=3, flags=1 if cout == 8 else 0)
+        quant = f16
+    else:
+        wt = convops.pack_kmajor(t(w))
+        xin = t(x)
+        kw = dict(backend=2)
+        quant = tf32
+    dense = convops.conv_fwd(xin, t(w), n_out, map=t(up), map_ld=ld, shift=t(shift), relu=True, weight_kmajor=wt,
+                             tile_mask=masks, **kw)
+    kw["flags"] = kw.get("flags", 0) | _cabi.SPS_CONV_MAP_PARENT
+    par = convops.conv_fwd(xin, t(w), n_out, map=t(parent), map_ld=ld, shift=t(shift), relu=True, weight_kmajor=wt,
+                           tile_mask=masks, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(dense[:v_out], par[:v_out])
+    ref = ref_conv(x, up[:, :v_out], w, shift=shift, relu=True, quant=quant)
+    got = par[:v_out].float().cpu().numpy()
+    if cout != 8:
+        assert np.abs(got - ref).max() < 2e-3 * max(1.0, np.abs(ref).max())
