@@ -21,7 +21,7 @@ __global__ void k_set_i32(int32_t* p, int32_t v) { *p = v; }
 
 constexpr int kRankChunks = 4;    // chunks of kScanBlock rows a block of k_first_rank scans
 #ifndef SPS_SLICE_BATCH
-#define SPS_SLICE_BATCH 8
+#define SPS_SLICE_BATCH 16
 #endif
 constexpr int kInsertBatch = 4;   // rows a thread of the level-0 insert kernel keeps in flight
 
@@ -830,7 +830,7 @@ k_tile_masks_perm(const SliceArgs A) {
       __syncthreads();
       int32_t* dst = slices + (int64_t)tile * (SPS_TILE_SLICE_ENTRIES * 128) + threadIdx.x;
       const uint32_t mine[3] = {w0, w1, w2};
-      // eight entries at a time: the loads of a batch are issued before the first store (the pass waits on these random
+      // SPS_SLICE_BATCH (16) entries at a time: the loads of a batch are issued before the first store (the pass waits on these random
       // 4-byte reads; unroll depth = reads in flight per thread)
       static_assert(SPS_SLICE_BATCH >= 1, "");
       for (int e0 = 0; e0 < nact; e0 += SPS_SLICE_BATCH) {
