@@ -74,10 +74,12 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.lines, self.proc = index, [], None
+    def __init__(self, index, enabled=True):
+        self.index, self.lines, self.proc, self.enabled = index, [], None, enabled
 
     def start(self):
+        if not self.enabled:      # only the rank that prints the line samples (eight pollers contend for the driver's locks)
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "200"],
@@ -595,7 +597,7 @@ def run_config2(args):
         drain()
         return d.timed(fn, steps, finish=drain)
 
-    sampler = ClockSampler(d.local)
+    sampler = ClockSampler(d.local, enabled=d.rank == 0)
     sampler.start()
     ms_dev = measure(dev, args.steps)       # inputs resident in HBM
     ms_host = measure(host, args.steps)     # public host-side API: pinned H2D of step k+1 overlaps the kernels of step k
@@ -706,7 +708,7 @@ def run_config3(args):
 
     for k in range(max(args.warmup, 3)):
         step_dev(k)
-    sampler = ClockSampler(d.local)
+    sampler = ClockSampler(d.local, enabled=d.rank == 0)
     sampler.start()
     ms_dev = d.timed(step_dev, steps)
     for k in range(3):
@@ -806,7 +808,7 @@ def run_config4(args):
     for k in range(max(args.warmup, 3, (3 * model.lanes * len(dev)) if model.use_graphs else 0)):
         fn(k)
     drain()
-    sampler = ClockSampler(d.local)
+    sampler = ClockSampler(d.local, enabled=d.rank == 0)
     sampler.start()
     ms = d.timed(fn, steps, finish=drain)
     clocks = sampler.stop()
